@@ -1,0 +1,177 @@
+/* me_b200.h — C ABI of the B200-native ensemble Metropolis hot path (libme_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of jklebes/MetropolisEngine: the user's loop
+ *     engine.step_all() ... engine.measure()                 (README.md:39-44)
+ * over an ensemble of independent chains.  The reference has no native interface (it is one Python class,
+ * metropolisengine/metropolis_engine.py "ME"), so every entry point below cites the Python method it
+ * replaces.  The reference-side binding a maintainer would add is the ctypes stub in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, int return codes (0 = ME_OK); no exceptions cross the boundary;
+ *     me_last_error() returns the message of the last failing call on that handle (or of me_create).
+ *   - every `double*` / `unsigned char*` argument is a DEVICE pointer owned by the caller (torch tensors in
+ *     the Python host); the library borrows it for the duration of the call and never frees it.
+ *   - all work is stream-ordered on the `stream` argument (a cudaStream_t; NULL = default stream);
+ *     no call synchronises the device except me_create / me_set_energy_source (compilation, no GPU work).
+ *   - one handle per GPU (rank); calls on one handle are not thread-safe (the reference is single-threaded).
+ *   - arrays over chains are chain-minor: a[word * ld + chain], ld = cfg.n_chains.
+ *     Parameter order inside a chain: [real..., Re c..., Im c...]  (ME:288).
+ */
+#ifndef ME_B200_H
+#define ME_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ME_ABI_VERSION 3
+
+enum me_status_code {
+    ME_OK = 0,
+    ME_ERR_INVALID = 1,      /* bad argument (reference: ValueError, ME:37-39) */
+    ME_ERR_CUDA = 2,         /* CUDA runtime / driver error */
+    ME_ERR_COMPILE = 3,      /* NVRTC compilation of a user functor failed (log in me_last_error) */
+    ME_ERR_UNSUPPORTED = 4,  /* shape / functor not available (e.g. NVRTC missing) */
+    ME_ERR_STATE = 5         /* call order (nothing bound, no energy set, ...) */
+};
+
+/* built-in device energy functors (me_energies.cuh).  The energy function is the reference's plugin
+ * surface (ME:20, ME:110-120, call sites ME:231, ME:250). */
+enum me_energy_id {
+    ME_ENERGY_X2 = 0,          /* README.md:26-27            E = x^2                           consts: -            */
+    ME_ENERGY_XY_WELL = 1,     /* demo/toymodel_xypotentialwell.py:13-18  E = k0 (x^2+y^2)     consts: k0           */
+    ME_ENERGY_MIXED_WELL = 2,  /* demo/toymodel_complex_and_real.py:17-26 and its 3r+4c scale-up consts: k, alpha, beta */
+    ME_ENERGY_CYLINDER = 3,    /* cylinder-style Fourier-mode field, wall |a|>=1               consts: kappa, alpha, gamma, beta */
+    ME_ENERGY_EXTERNAL = 99,   /* energy evaluated by the caller between me_propose and me_accept (torch callable) */
+    ME_ENERGY_USER = 100       /* CUDA source given to me_set_energy_source */
+};
+
+/* per-chain status bits (STATUS word of the state block); the reference's failure modes, SURVEY.md §5 */
+#define ME_STATUS_NOT_PSD 1        /* numpy "covariance is not symmetric positive-semidefinite" (ME:270) */
+#define ME_STATUS_SIGMA_NONPOS 2   /* assert sampling_width > 0 (ME:438) */
+#define ME_STATUS_ENERGY_NAN 4
+
+typedef struct me_engine me_engine;   /* opaque */
+
+/* Replaces the scalar part of MetropolisEngine.__init__ (ME:17-133). */
+typedef struct me_config {
+    int32_t n_real;             /* ME:42  */
+    int32_t n_complex;          /* ME:52  */
+    int64_t n_chains;           /* chains owned by this handle (this GPU) */
+    int64_t chain_offset;       /* global id of local chain 0; the RNG stream of a chain depends only on
+                                   (seed, global id), so results do not depend on how chains are sharded */
+    double temp;                /* ME:91  */
+    double target_acceptance;   /* ME:101 */
+    double ratio;               /* ME:105-107 (the host computes it: needs the normal quantile, ME:102) */
+    uint64_t seed;              /* Philox4x32-10 key (reference: process-global MT19937 state) */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t strict;             /* 1: reference operation order, no FMA contraction, draw injection available */
+} me_config;
+
+/* Word offsets of the per-chain state block (state[word * ld + chain]) and derived sizes. */
+typedef struct me_layout {
+    int32_t X;        /* D words: current parameters        (real_params ME:41, complex_params ME:51)          */
+    int32_t E;        /* live energy                        (energy['total'] / energy_total, ME:125,236,255)   */
+    int32_t SIG;      /* 2 words: real_group_sampling_width, complex_group_sampling_width (ME:97-99)           */
+    int32_t MEAN;     /* D words: real_mean, complex_mean   (ME:77-78)                                         */
+    int32_t COVR;     /* NR(NR+1)/2 lower-packed covariance_matrix_real    (ME:63-66)                          */
+    int32_t COVC;     /* NC^2 Hermitian-packed covariance_matrix_complex   (ME:67-70)                          */
+    int32_t OBSM;     /* 2NR+NC observables_mean            (ME:80-81)                                         */
+    int32_t FACR;     /* Cholesky factor of COVR  (replaces the per-step SVD inside numpy, ME:268)             */
+    int32_t FACC;     /* Cholesky factor of COVC  (ME:300)                                                     */
+    int32_t NACC;     /* accepted-step count (the reference's commented-out accepted_counter, ME:71)           */
+    int32_t STATUS;   /* ME_STATUS_* bits                                                                      */
+    int32_t WORDS;    /* total words per chain                                                                 */
+    int32_t D;        /* NR + 2 NC                                                                             */
+    int32_t TS_COLS;  /* time-series columns per row: x[D], energy, sigma                                      */
+    int32_t POOL_WORDS; /* pooled-moment words: sum(x-s)[D], sum (x-s)(x-s)^T [D(D+1)/2 lower], sum obs [2NR+NC];
+                           0 when the shape is too large for in-kernel pooling                               */
+} me_layout;
+
+int me_abi_version(void);
+
+/* Layout of the state block for a parameter-space shape (pure function, no GPU). */
+int me_state_layout(int32_t n_real, int32_t n_complex, me_layout *out);
+
+/* MetropolisEngine.__init__ (ME:17): creates the handle; no device memory is allocated. */
+int me_create(const me_config *cfg, me_engine **out);
+int me_destroy(me_engine *eng);
+
+/* Energy plugin registration — replaces the `energy_functions` constructor argument / set_energy_function
+ * (ME:110-120, ME:136-140) and set_reject_condition (ME:142-146).
+ *   builtin : one of me_energy_id with its constants;
+ *   source  : CUDA C++ text defining
+ *                 __device__ double me_user_energy(const double* x, const double* c_re, const double* c_im, const double* k);
+ *             and, when use_reject != 0,
+ *                 __device__ bool   me_user_reject(const double* x, const double* c_re, const double* c_im, const double* k);
+ *             compiled for sm_100a with NVRTC and fused into the step kernel (ME_NR / ME_NC are predefined macros);
+ *   external: the caller evaluates energies itself between me_propose and me_accept. */
+int me_set_energy_builtin(me_engine *eng, int32_t energy_id, const double *consts, int32_t n_consts, int32_t use_reject);
+int me_set_energy_source(me_engine *eng, const char *cuda_source, const double *consts, int32_t n_consts, int32_t use_reject);
+int me_set_energy_external(me_engine *eng);
+
+/* Compile-only check of a user functor (works without a GPU): 0 = compiles; log (may be NULL) receives the
+ * NVRTC log. */
+int me_check_energy_source(const char *cuda_source, int32_t n_real, int32_t n_complex, int32_t use_reject,
+                           int32_t strict, char *log, int64_t log_cap);
+
+/* Launch geometry the handle uses; the pool buffer has grid * POOL_WORDS doubles. */
+int me_launch_dims(me_engine *eng, int32_t *grid, int32_t *block);
+
+typedef struct me_buffers {
+    double *state;              /* [WORDS][n_chains] */
+    double *pool;               /* [grid][POOL_WORDS] pooled-moment accumulators (may be NULL: no pooling) */
+    double *shift;              /* [D] shift of the pooled moments (required when pool != NULL) */
+    unsigned char *last_accept; /* [n_chains] accept flag of the most recent step — the return value of step_all() (ME:259) */
+} me_buffers;
+int me_bind(me_engine *eng, const me_buffers *buffers);
+
+/* State initialisation (ME:40-125): x <- x0, means <- x0, covariances <- given or identity, widths <- sigma0,
+ * observable means <- observables(x0), energy <- functor(x0) (or e0 for external energies), counters <- 1.
+ *   x0: [D][n_chains], or [D] when x0_broadcast;  cov_r: [NR*NR];  cov_c_re / cov_c_im: [NC*NC] (NULL = identity) */
+int me_init(me_engine *eng, const double *x0, int32_t x0_broadcast, double sigma0, const double *cov_r,
+            const double *cov_c_re, const double *cov_c_im, const double *e0, void *stream);
+
+/* The hot path.  One launch runs  n_blocks x ( steps_per_measure x step_all() [+ measure()] )  for every chain:
+ *   step_all   ME:241-259 (mixed) / ME:225-239 (all-real) / ME:209-223 (all-complex): Philox Gaussian proposal
+ *              through the Cholesky factors (ME:261-302), hard-wall predicate (ME:247), energy functor (ME:250),
+ *              Metropolis test (ME:319-338), Robbins-Monro width update (ME:429-456);
+ *   measure    ME:342-427: running means, covariance recursion (+ refactorisation), observable means, and, when
+ *              ts != NULL, one time-series row per chain at ts[((ts_row0 + block) * TS_COLS + col) * n_chains + chain]
+ *              (the lists of ME:31-35,350-356).
+ *   me_run(e, 1, k, 0, ...) is k plain step_all() calls; me_run(e, 1, 0, 1, ...) is one measure(). */
+int me_run(me_engine *eng, int64_t n_blocks, int64_t steps_per_measure, int32_t do_measure, double *ts,
+           int64_t ts_row0, void *stream);
+
+/* Parity mode (strict handles only): the same schedule driven by recorded draws instead of Philox —
+ * delta[(step * D + k) * n_chains + chain] is added to the parameters, u[step * n_chains + chain] is the accept
+ * uniform (NaN where the reference drew none).  SURVEY.md §8(c) level L-A. */
+int me_run_injected(me_engine *eng, int64_t n_blocks, int64_t steps_per_measure, int32_t do_measure,
+                    const double *delta, const double *u, double *ts, int64_t ts_row0, void *stream);
+
+/* Unfused step for energies evaluated by the caller (torch-vectorised callable):
+ *   me_propose writes the proposal block prop[D][n_chains]  (draw_real_group / draw_complex_group, ME:261-302);
+ *   the caller computes e_new[n_chains] (and optionally a hard-wall mask rej[n_chains]);
+ *   me_accept applies ME:247-258 and advances the step counter.
+ * inj_delta [D][n_chains] / inj_u [n_chains] (strict handles, may be NULL) inject draws for one step. */
+int me_propose(me_engine *eng, double *prop, const double *inj_delta, void *stream);
+int me_accept(me_engine *eng, const double *prop, const double *e_new, const unsigned char *rej,
+              const double *inj_u, void *stream);
+
+/* Pooled ensemble moments: out[POOL_WORDS] = sum over CTAs (fixed order, deterministic) of the accumulators
+ * filled at every measure; reset != 0 zeroes the accumulators afterwards.  The caller all-reduces `out` across
+ * ranks (NCCL) — the only collective of the path.  No reference counterpart. */
+int me_pool_reduce(me_engine *eng, double *out, int32_t reset, void *stream);
+
+/* measure_step_counter (ME:73) and the global step index (Philox counter); for checkpoint / resume. */
+int me_get_counters(me_engine *eng, int64_t *n_measure, uint64_t *step);
+int me_set_counters(me_engine *eng, int64_t n_measure, uint64_t step);
+
+const char *me_last_error(me_engine *eng);   /* eng may be NULL: error of the last failing me_create */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ME_B200_H */

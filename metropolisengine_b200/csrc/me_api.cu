@@ -1,0 +1,546 @@
+/* me_api.cu — host side of libme_b200.so: the C ABI declared in include/me_b200.h.
+ *
+ * Responsibilities: pick the kernel set for (shape, energy functor, strict) from the ahead-of-time tables or
+ * compile it with NVRTC; keep the two counters the reference keeps on the host (measure_step_counter ME:73 and
+ * a global step index for the Philox counter); fill MeParams and launch on the caller's stream.
+ * No device memory is owned here except nothing: every buffer is borrowed from the caller.
+ */
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/me_b200.h"
+#include "me_kernels.cuh"
+#include "me_embedded.inc"   /* generated: the kernel headers as string constants for NVRTC */
+
+extern "C" const MeAotEntry *me_aot_fast_table(int *n);
+extern "C" const MeAotEntry *me_aot_strict_table(int *n);
+
+namespace {
+
+std::string g_create_error;
+
+/* ----------------------------------------------------------------------------------------- kernel handles */
+struct KernelRef {
+    const void *rt = nullptr;   /* runtime-API function pointer (ahead-of-time kernels) */
+    CUfunction drv = nullptr;   /* driver-API function (NVRTC kernels) */
+    bool valid() const { return rt != nullptr || drv != nullptr; }
+};
+struct KernelSet {
+    KernelRef run, init, propose, accept;
+    bool valid() const { return run.valid(); }
+};
+
+/* ----------------------------------------------------------------------------------------- driver + NVRTC, loaded lazily */
+typedef CUresult (*cuModuleLoadData_t)(CUmodule *, const void *);
+typedef CUresult (*cuModuleGetFunction_t)(CUfunction *, CUmodule, const char *);
+typedef CUresult (*cuLaunchKernel_t)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                     CUstream, void **, void **);
+typedef CUresult (*cuGetErrorString_t)(CUresult, const char **);
+
+struct Driver {
+    cuModuleLoadData_t moduleLoadData = nullptr;
+    cuModuleGetFunction_t moduleGetFunction = nullptr;
+    cuLaunchKernel_t launchKernel = nullptr;
+    cuGetErrorString_t getErrorString = nullptr;
+    bool ok = false;
+    std::string err;
+};
+
+Driver &driver() {
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto get = [&](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult q;
+            cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+            if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || *fn == nullptr) {
+                d.err = std::string("driver entry point not available: ") + name;
+                cudaGetLastError();
+                return false;
+            }
+            return true;
+        };
+        d.ok = get("cuModuleLoadData", (void **)&d.moduleLoadData) &&
+               get("cuModuleGetFunction", (void **)&d.moduleGetFunction) &&
+               get("cuLaunchKernel", (void **)&d.launchKernel) && get("cuGetErrorString", (void **)&d.getErrorString);
+    });
+    return d;
+}
+
+typedef struct _nvrtcProgram *nvrtcProgram;
+struct Nvrtc {
+    int (*createProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+    int (*compileProgram)(nvrtcProgram, int, const char *const *) = nullptr;
+    int (*getCUBINSize)(nvrtcProgram, size_t *) = nullptr;
+    int (*getCUBIN)(nvrtcProgram, char *) = nullptr;
+    int (*getProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
+    int (*getProgramLog)(nvrtcProgram, char *) = nullptr;
+    int (*destroyProgram)(nvrtcProgram *) = nullptr;
+    const char *(*getErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string err;
+};
+
+Nvrtc &nvrtc() {
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::vector<std::string> names;
+        if (const char *env = getenv("ME_NVRTC_PATH")) names.push_back(env);
+        names.push_back("libnvrtc.so.12");
+        names.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+        names.push_back("libnvrtc.so");
+        void *h = nullptr;
+        for (auto &nm : names) {
+            h = dlopen(nm.c_str(), RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) { n.err = "libnvrtc.so.12 not found (set ME_NVRTC_PATH)"; return; }
+        bool all = true;
+        auto sym = [&](const char *s, void **fn) { *fn = dlsym(h, s); if (!*fn) all = false; };
+        sym("nvrtcCreateProgram", (void **)&n.createProgram);
+        sym("nvrtcCompileProgram", (void **)&n.compileProgram);
+        sym("nvrtcGetCUBINSize", (void **)&n.getCUBINSize);
+        sym("nvrtcGetCUBIN", (void **)&n.getCUBIN);
+        sym("nvrtcGetProgramLogSize", (void **)&n.getProgramLogSize);
+        sym("nvrtcGetProgramLog", (void **)&n.getProgramLog);
+        sym("nvrtcDestroyProgram", (void **)&n.destroyProgram);
+        sym("nvrtcGetErrorString", (void **)&n.getErrorString);
+        n.ok = all;
+        if (!all) n.err = "libnvrtc is missing required symbols";
+    });
+    return n;
+}
+
+const char *builtin_template(int energy_id) {
+    switch (energy_id) {
+    case ME_ENERGY_X2: return "me::EnergyX2";
+    case ME_ENERGY_XY_WELL: return "me::EnergyXYWell";
+    case ME_ENERGY_MIXED_WELL: return "me::EnergyMixedWell";
+    case ME_ENERGY_CYLINDER: return "me::EnergyCylinder";
+    case ME_ENERGY_EXTERNAL: return "me::EnergyNone";
+    case ME_ENERGY_USER: return "me::EnergyUser";
+    default: return nullptr;
+    }
+}
+
+/* Runtime compilation of the kernel set for one (shape, functor, strict).  Returns the CUBIN. */
+int nvrtc_compile(int n_real, int n_complex, int energy_id, const std::string &user_src, int use_reject, int strict,
+                  std::vector<char> &cubin, std::string &log) {
+    Nvrtc &n = nvrtc();
+    if (!n.ok) { log = n.err; return ME_ERR_UNSUPPORTED; }
+    const char *tmpl = builtin_template(energy_id);
+    if (!tmpl) { log = "unknown energy id"; return ME_ERR_INVALID; }
+    std::string src = "#include \"me_kernels.cuh\"\n";
+    if (energy_id == ME_ENERGY_USER) {
+        src += "#line 1 \"user_energy.cu\"\n";
+        src += user_src;
+        src += "\nnamespace me {\n"
+               "template <int NR, int NC> struct EnergyUser {\n"
+               "  __device__ static __forceinline__ double eval(const double* x, const double* cr, const double* ci, const double* k) {\n"
+               "    return me_user_energy(x, cr, ci, k); }\n"
+               "  __device__ static __forceinline__ bool reject(const double* x, const double* cr, const double* ci, const double* k) {\n";
+        src += use_reject ? "    return me_user_reject(x, cr, ci, k); }\n" : "    return false; }\n";
+        src += "};\n}\n";
+    }
+    src += std::string("typedef me::Cfg<ME_NR, ME_NC, ") + tmpl + ", (ME_STRICT != 0)> UserCfg;\n";
+    src += "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_run(const __grid_constant__ MeParams p) { me::run_body<UserCfg>(p); }\n"
+           "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_init(const __grid_constant__ MeParams p) { me::init_body<UserCfg>(p); }\n"
+           "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_propose(const __grid_constant__ MeParams p) { me::propose_body<UserCfg>(p); }\n"
+           "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_accept(const __grid_constant__ MeParams p) { me::accept_body<UserCfg>(p); }\n";
+    const char *hdr_names[] = {"me_params.h", "me_device.cuh", "me_energies.cuh", "me_kernels.cuh"};
+    const char *hdr_src[] = {me_src_params_h, me_src_device_cuh, me_src_energies_cuh, me_src_kernels_cuh};
+    nvrtcProgram prog = nullptr;
+    int rc = n.createProgram(&prog, src.c_str(), "me_user_kernels.cu", 4, hdr_src, hdr_names);
+    if (rc != 0) { log = std::string("nvrtcCreateProgram: ") + n.getErrorString(rc); return ME_ERR_COMPILE; }
+    std::string d_nr = "-DME_NR=" + std::to_string(n_real), d_nc = "-DME_NC=" + std::to_string(n_complex);
+    std::string d_st = std::string("-DME_STRICT=") + (strict ? "1" : "0");
+    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DME_NVRTC=1",
+                                      d_nr.c_str(), d_nc.c_str(), d_st.c_str()};
+    if (strict) opts.push_back("--fmad=false");
+    rc = n.compileProgram(prog, (int)opts.size(), opts.data());
+    size_t lsz = 0;
+    n.getProgramLogSize(prog, &lsz);
+    if (lsz > 1) { log.resize(lsz); n.getProgramLog(prog, &log[0]); }
+    if (rc != 0) {
+        log = std::string("NVRTC: ") + n.getErrorString(rc) + "\n" + log;
+        n.destroyProgram(&prog);
+        return ME_ERR_COMPILE;
+    }
+    size_t csz = 0;
+    n.getCUBINSize(prog, &csz);
+    cubin.resize(csz);
+    n.getCUBIN(prog, cubin.data());
+    n.destroyProgram(&prog);
+    return ME_OK;
+}
+
+/* process-wide cache of loaded runtime-compiled kernel sets */
+std::mutex g_cache_mu;
+std::map<std::string, KernelSet> g_cache;
+
+}  // namespace
+
+/* ----------------------------------------------------------------------------------------- the handle */
+struct me_engine {
+    me_config cfg;
+    me_layout lay;
+    KernelSet ks;
+    int energy_id = -1;
+    int use_reject = 0;
+    double consts[ME_MAX_CONSTS];
+    me_buffers buf;
+    bool bound = false;
+    long long n_measure = 1;           /* ME:73 */
+    unsigned long long step = 0;       /* global step index (Philox counter word 2) */
+    int block = 128, grid = 1;
+    int n_sm = 148;
+    std::string err;
+};
+
+namespace {
+
+int fail(me_engine *e, int code, const std::string &msg) {
+    if (e) e->err = msg; else g_create_error = msg;
+    return code;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int launch(me_engine *e, const KernelRef &k, MeParams &p, void *stream) {
+    if (!k.valid()) return fail(e, ME_ERR_STATE, "no energy functor registered (call me_set_energy_* first)");
+    DeviceGuard g(e->cfg.device);
+    void *args[] = {&p};
+    if (k.rt) {
+        cudaError_t ce = cudaLaunchKernel(k.rt, dim3(e->grid), dim3(e->block), args, 0, (cudaStream_t)stream);
+        if (ce != cudaSuccess) return fail(e, ME_ERR_CUDA, std::string("cudaLaunchKernel: ") + cudaGetErrorString(ce));
+    } else {
+        Driver &d = driver();
+        CUresult r = d.launchKernel(k.drv, e->grid, 1, 1, e->block, 1, 1, 0, (CUstream)stream, args, nullptr);
+        if (r != CUDA_SUCCESS) {
+            const char *s = nullptr;
+            d.getErrorString(r, &s);
+            return fail(e, ME_ERR_CUDA, std::string("cuLaunchKernel: ") + (s ? s : "?"));
+        }
+    }
+    return ME_OK;
+}
+
+void base_params(me_engine *e, MeParams &p) {
+    memset(&p, 0, sizeof(p));
+    p.state = e->buf.state;
+    p.ld = e->cfg.n_chains;
+    p.n_chains = e->cfg.n_chains;
+    p.chain_offset = (unsigned long long)e->cfg.chain_offset;
+    p.seed = e->cfg.seed;
+    p.step0 = e->step;
+    p.n_meas0 = e->n_measure;
+    p.use_reject = e->use_reject;
+    p.m = e->cfg.n_real + e->cfg.n_complex;
+    p.temp = e->cfg.temp;
+    p.inv_temp = e->cfg.temp != 0 ? 1.0 / e->cfg.temp : 0.0;
+    p.target = e->cfg.target_acceptance;
+    p.ratio = e->cfg.ratio;
+    memcpy(p.consts, e->consts, sizeof(p.consts));
+    p.last_accept = e->buf.last_accept;
+    p.pool = e->lay.POOL_WORDS > 0 ? e->buf.pool : nullptr;
+    p.shift = e->buf.shift;
+}
+
+/* Launch geometry.  One thread per chain, so the CTA size only trades scheduling granularity against the
+ * per-CTA pooled reduction: when the whole ensemble fits in one wave use 32-thread CTAs (finest balance over
+ * the 148 SMs), otherwise 128. */
+void choose_dims(me_engine *e) {
+    const long long n = e->cfg.n_chains;
+    int block = 128;
+    if (const char *env = getenv("ME_BLOCK")) block = atoi(env);
+    else if (n <= (long long)e->n_sm * 32 * 32) block = 32;
+    else if (n <= (long long)e->n_sm * 32 * 64) block = 64;
+    if (block < 32) block = 32;
+    if (block > ME_MAX_BLOCK) block = ME_MAX_BLOCK;
+    block = (block / 32) * 32;
+    e->block = block;
+    e->grid = (int)((n + block - 1) / block);
+}
+
+int resolve_kernels(me_engine *e, int energy_id, const std::string &user_src) {
+    const int nr = e->cfg.n_real, nc = e->cfg.n_complex, strict = e->cfg.strict ? 1 : 0;
+    if (energy_id != ME_ENERGY_USER) {
+        int n = 0;
+        const MeAotEntry *t = strict ? me_aot_strict_table(&n) : me_aot_fast_table(&n);
+        for (int i = 0; i < n; i++)
+            if (t[i].n_real == nr && t[i].n_complex == nc && t[i].energy_id == energy_id) {
+                e->ks.run.rt = t[i].run; e->ks.init.rt = t[i].init;
+                e->ks.propose.rt = t[i].propose; e->ks.accept.rt = t[i].accept;
+                return ME_OK;
+            }
+    }
+    /* not instantiated ahead of time: NVRTC */
+    std::string key = std::to_string(nr) + "," + std::to_string(nc) + "," + std::to_string(energy_id) + "," +
+                      std::to_string(strict) + "," + std::to_string(e->use_reject) + "," +
+                      std::to_string(e->cfg.device) + "|" + user_src;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) { e->ks = it->second; return ME_OK; }
+    std::vector<char> cubin;
+    std::string log;
+    int rc = nvrtc_compile(nr, nc, energy_id, user_src, e->use_reject, strict, cubin, log);
+    if (rc != ME_OK) return fail(e, rc, log);
+    Driver &d = driver();
+    if (!d.ok) return fail(e, ME_ERR_UNSUPPORTED, d.err);
+    DeviceGuard g(e->cfg.device);
+    cudaFree(0);   /* make sure the primary context exists and is current */
+    CUmodule mod = nullptr;
+    CUresult r = d.moduleLoadData(&mod, cubin.data());
+    if (r != CUDA_SUCCESS) {
+        const char *s = nullptr;
+        d.getErrorString(r, &s);
+        return fail(e, ME_ERR_CUDA, std::string("cuModuleLoadData: ") + (s ? s : "?"));
+    }
+    KernelSet ks;
+    if (d.moduleGetFunction(&ks.run.drv, mod, "me_k_run") != CUDA_SUCCESS ||
+        d.moduleGetFunction(&ks.init.drv, mod, "me_k_init") != CUDA_SUCCESS ||
+        d.moduleGetFunction(&ks.propose.drv, mod, "me_k_propose") != CUDA_SUCCESS ||
+        d.moduleGetFunction(&ks.accept.drv, mod, "me_k_accept") != CUDA_SUCCESS)
+        return fail(e, ME_ERR_CUDA, "cuModuleGetFunction failed on the runtime-compiled module");
+    g_cache[key] = ks;
+    e->ks = ks;
+    return ME_OK;
+}
+
+__global__ void k_pool_reduce(double *pool, double *out, int grid, int words, int reset) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    double t = 0.0;
+    for (int b = 0; b < grid; b++) {
+        t += pool[(long long)b * words + w];
+        if (reset) pool[(long long)b * words + w] = 0.0;
+    }
+    out[w] = t;
+}
+
+}  // namespace
+
+/* ========================================================================================= C ABI */
+extern "C" {
+
+int me_abi_version(void) { return ME_ABI_VERSION; }
+
+int me_state_layout(int32_t nr, int32_t nc, me_layout *o) {
+    if (!o || nr < 0 || nc < 0 || nr + nc == 0) return ME_ERR_INVALID;
+    const int d = nr + 2 * nc;
+    int w = 0;
+    o->X = w; w += d;
+    o->E = w; w += 1;
+    o->SIG = w; w += 2;
+    o->MEAN = w; w += d;
+    o->COVR = w; w += nr * (nr + 1) / 2;
+    o->COVC = w; w += nc * nc;
+    o->OBSM = w; w += 2 * nr + nc;
+    o->FACR = w; w += nr * (nr + 1) / 2;
+    o->FACC = w; w += nc * nc;
+    o->NACC = w; w += 1;
+    o->STATUS = w; w += 1;
+    o->WORDS = w;
+    o->D = d;
+    o->TS_COLS = d + 2;
+    const long long pw = (long long)d + (long long)d * (d + 1) / 2 + 2 * nr + nc;
+    o->POOL_WORDS = pw <= ME_MAX_POOLW ? (int)pw : 0;
+    return ME_OK;
+}
+
+int me_create(const me_config *cfg, me_engine **out) {
+    if (!cfg || !out) return fail(nullptr, ME_ERR_INVALID, "null argument");
+    if (cfg->n_real < 0 || cfg->n_complex < 0 || cfg->n_real + cfg->n_complex == 0)
+        return fail(nullptr, ME_ERR_INVALID, "need at least one real or complex parameter (reference: ValueError, ME:37-39)");
+    if (cfg->n_chains <= 0) return fail(nullptr, ME_ERR_INVALID, "n_chains must be positive");
+    if (!(cfg->temp >= 0)) return fail(nullptr, ME_ERR_INVALID, "temp must be >= 0 (reference: assert, ME:92)");
+    me_engine *e = new me_engine();
+    e->cfg = *cfg;
+    me_state_layout(cfg->n_real, cfg->n_complex, &e->lay);
+    memset(e->consts, 0, sizeof(e->consts));
+    memset(&e->buf, 0, sizeof(e->buf));
+    int n_sm = 0;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0)
+        e->n_sm = n_sm;
+    else
+        cudaGetLastError();
+    choose_dims(e);
+    *out = e;
+    return ME_OK;
+}
+
+int me_destroy(me_engine *e) {
+    delete e;
+    return ME_OK;
+}
+
+static int set_energy(me_engine *e, int id, const char *src, const double *consts, int n_consts, int use_reject) {
+    if (!e) return ME_ERR_INVALID;
+    if (n_consts < 0 || n_consts > ME_MAX_CONSTS) return fail(e, ME_ERR_INVALID, "at most 16 functor constants");
+    if (!builtin_template(id)) return fail(e, ME_ERR_INVALID, "unknown energy id");
+    memset(e->consts, 0, sizeof(e->consts));
+    for (int i = 0; i < n_consts; i++) e->consts[i] = consts[i];
+    e->use_reject = use_reject ? 1 : 0;
+    e->ks = KernelSet();
+    int rc = resolve_kernels(e, id, src ? std::string(src) : std::string());
+    if (rc == ME_OK) e->energy_id = id;
+    return rc;
+}
+
+int me_set_energy_builtin(me_engine *e, int32_t id, const double *consts, int32_t n_consts, int32_t use_reject) {
+    if (id == ME_ENERGY_USER) return fail(e, ME_ERR_INVALID, "use me_set_energy_source for user functors");
+    return set_energy(e, id, nullptr, consts, n_consts, use_reject);
+}
+
+int me_set_energy_source(me_engine *e, const char *src, const double *consts, int32_t n_consts, int32_t use_reject) {
+    if (!src) return fail(e, ME_ERR_INVALID, "null source");
+    return set_energy(e, ME_ENERGY_USER, src, consts, n_consts, use_reject);
+}
+
+int me_set_energy_external(me_engine *e) { return set_energy(e, ME_ENERGY_EXTERNAL, nullptr, nullptr, 0, 0); }
+
+int me_check_energy_source(const char *src, int32_t nr, int32_t nc, int32_t use_reject, int32_t strict, char *log,
+                           int64_t cap) {
+    std::vector<char> cubin;
+    std::string l;
+    int rc = nvrtc_compile(nr, nc, src ? ME_ENERGY_USER : ME_ENERGY_EXTERNAL, src ? src : "", use_reject, strict, cubin, l);
+    if (log && cap > 0) {
+        strncpy(log, l.c_str(), (size_t)cap - 1);
+        log[cap - 1] = 0;
+    }
+    return rc;
+}
+
+int me_launch_dims(me_engine *e, int32_t *grid, int32_t *block) {
+    if (!e) return ME_ERR_INVALID;
+    if (grid) *grid = e->grid;
+    if (block) *block = e->block;
+    return ME_OK;
+}
+
+int me_bind(me_engine *e, const me_buffers *b) {
+    if (!e || !b) return ME_ERR_INVALID;
+    if (!b->state) return fail(e, ME_ERR_INVALID, "state buffer is required");
+    if (b->pool && !b->shift) return fail(e, ME_ERR_INVALID, "pool needs a shift vector");
+    e->buf = *b;
+    e->bound = true;
+    return ME_OK;
+}
+
+int me_init(me_engine *e, const double *x0, int32_t bc, double sigma0, const double *cov_r, const double *cov_c_re,
+            const double *cov_c_im, const double *e0, void *stream) {
+    if (!e) return ME_ERR_INVALID;
+    if (!e->bound) return fail(e, ME_ERR_STATE, "me_bind first");
+    if (!x0) return fail(e, ME_ERR_INVALID, "x0 is required");
+    if (e->energy_id == ME_ENERGY_EXTERNAL && !e0) return fail(e, ME_ERR_INVALID, "external energies need e0");
+    MeParams p;
+    base_params(e, p);
+    p.x0 = x0; p.x0_broadcast = bc; p.sigma0 = sigma0;
+    p.cov_r0 = cov_r; p.cov_c0_re = cov_c_re; p.cov_c0_im = cov_c_im;
+    p.e_new = e0; p.have_e0 = e0 != nullptr;
+    e->n_measure = 1;
+    e->step = 0;
+    return launch(e, e->ks.init, p, stream);
+}
+
+static int run_common(me_engine *e, int64_t n_blocks, int64_t spm, int do_measure, const double *delta, const double *u,
+                      double *ts, int64_t ts_row0, void *stream) {
+    if (!e) return ME_ERR_INVALID;
+    if (!e->bound) return fail(e, ME_ERR_STATE, "me_bind first");
+    if (n_blocks < 0 || spm < 0) return fail(e, ME_ERR_INVALID, "negative schedule");
+    if (n_blocks == 0 || (spm == 0 && !do_measure)) return ME_OK;
+    if (spm > 0 && e->energy_id == ME_ENERGY_EXTERNAL)
+        return fail(e, ME_ERR_STATE, "external energies step through me_propose / me_accept");
+    if (e->step + (unsigned long long)(n_blocks * spm) >= 0xffffffffull)
+        return fail(e, ME_ERR_INVALID, "step index exceeds the 32-bit Philox counter word");
+    MeParams p;
+    base_params(e, p);
+    p.n_blocks = n_blocks; p.spm = spm; p.do_measure = do_measure ? 1 : 0;
+    p.ts = ts; p.ts_row0 = ts_row0; p.record = (ts != nullptr && do_measure) ? 1 : 0;
+    p.inj_delta = delta; p.inj_u = u;
+    int rc = launch(e, e->ks.run, p, stream);
+    if (rc != ME_OK) return rc;
+    e->step += (unsigned long long)(n_blocks * spm);
+    if (do_measure) e->n_measure += n_blocks;
+    return ME_OK;
+}
+
+int me_run(me_engine *e, int64_t n_blocks, int64_t spm, int32_t do_measure, double *ts, int64_t ts_row0, void *stream) {
+    return run_common(e, n_blocks, spm, do_measure, nullptr, nullptr, ts, ts_row0, stream);
+}
+
+int me_run_injected(me_engine *e, int64_t n_blocks, int64_t spm, int32_t do_measure, const double *delta,
+                    const double *u, double *ts, int64_t ts_row0, void *stream) {
+    if (!e) return ME_ERR_INVALID;
+    if (!e->cfg.strict) return fail(e, ME_ERR_STATE, "draw injection needs a strict handle (cfg.strict = 1)");
+    if (!delta || !u) return fail(e, ME_ERR_INVALID, "delta and u are required");
+    return run_common(e, n_blocks, spm, do_measure, delta, u, ts, ts_row0, stream);
+}
+
+int me_propose(me_engine *e, double *prop, const double *inj_delta, void *stream) {
+    if (!e) return ME_ERR_INVALID;
+    if (!e->bound) return fail(e, ME_ERR_STATE, "me_bind first");
+    if (!prop) return fail(e, ME_ERR_INVALID, "prop is required");
+    if (inj_delta && !e->cfg.strict) return fail(e, ME_ERR_STATE, "draw injection needs a strict handle");
+    MeParams p;
+    base_params(e, p);
+    p.prop = prop; p.inj_delta = inj_delta;
+    return launch(e, e->ks.propose, p, stream);
+}
+
+int me_accept(me_engine *e, const double *prop, const double *e_new, const unsigned char *rej, const double *inj_u,
+              void *stream) {
+    if (!e) return ME_ERR_INVALID;
+    if (!e->bound) return fail(e, ME_ERR_STATE, "me_bind first");
+    if (!prop || !e_new) return fail(e, ME_ERR_INVALID, "prop and e_new are required");
+    if (inj_u && !e->cfg.strict) return fail(e, ME_ERR_STATE, "draw injection needs a strict handle");
+    MeParams p;
+    base_params(e, p);
+    p.prop = const_cast<double *>(prop); p.e_new = e_new; p.rej = rej; p.inj_u = inj_u;
+    int rc = launch(e, e->ks.accept, p, stream);
+    if (rc == ME_OK) e->step += 1;
+    return rc;
+}
+
+int me_pool_reduce(me_engine *e, double *out, int32_t reset, void *stream) {
+    if (!e || !out) return ME_ERR_INVALID;
+    if (!e->bound || !e->buf.pool || e->lay.POOL_WORDS == 0) return fail(e, ME_ERR_STATE, "no pool buffer bound");
+    DeviceGuard g(e->cfg.device);
+    const int words = e->lay.POOL_WORDS;
+    k_pool_reduce<<<(words + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->buf.pool, out, e->grid, words, reset);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return fail(e, ME_ERR_CUDA, std::string("pool reduce: ") + cudaGetErrorString(ce));
+    return ME_OK;
+}
+
+int me_get_counters(me_engine *e, int64_t *n_measure, uint64_t *step) {
+    if (!e) return ME_ERR_INVALID;
+    if (n_measure) *n_measure = e->n_measure;
+    if (step) *step = e->step;
+    return ME_OK;
+}
+
+int me_set_counters(me_engine *e, int64_t n_measure, uint64_t step) {
+    if (!e || n_measure < 1) return ME_ERR_INVALID;
+    e->n_measure = n_measure;
+    e->step = step;
+    return ME_OK;
+}
+
+const char *me_last_error(me_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"

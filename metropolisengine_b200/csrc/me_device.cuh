@@ -1,0 +1,677 @@
+/* me_device.cuh — device side of the fused Metropolis hot path (sm_100a).
+ *
+ * One thread owns one chain; the chain's parameters, energy, sampling width and proposal factors live in
+ * registers for the whole launch, which runs  n_blocks x (spm steps [+ one measure])  without touching HBM except
+ * for the time-series rows.  This is the B200 counterpart of the reference's user loop
+ *     for ...: for ...: engine.step_all()         (metropolis_engine.py:241-259 / 225-239 / 209-223)
+ *              engine.measure()                   (metropolis_engine.py:342-427)
+ * (README.md:39-44, demo/toymodel_xypotentialwell.py:39-44).
+ *
+ * The same text is compiled three ways: ahead of time for the named workloads (me_aot_fast.cu with FMA
+ * contraction, me_aot_strict.cu with -fmad=false and the reference's operation order for draw-injected parity),
+ * and at run time by NVRTC for user energy functors / shapes that were not instantiated ahead of time.
+ * Therefore: no #include of anything but the sibling headers (handed to NVRTC as in-memory includes),
+ * built-in types only.
+ *
+ * State layout (chain-minor, `state[word*ld + chain]`), D = NR + 2 NC, parameter order [real, Re c, Im c]
+ * (the reference's embedding order, metropolis_engine.py:288):
+ *   X D | E 1 | SIG 2 | MEAN D | COVR NR(NR+1)/2 | COVC NC^2 | OBSM 2NR+NC | FACR NR(NR+1)/2 | FACC NC^2 | NACC | STATUS
+ * Hermitian packing: strictly-lower pairs p=i(i-1)/2+j at [2p]=Re,[2p+1]=Im, then NC real diagonal entries.
+ */
+#ifndef ME_DEVICE_CUH
+#define ME_DEVICE_CUH
+
+#include "me_params.h"
+
+#define ME_MAX_BLOCK 256
+#define ME_FULL 0xffffffffu
+#define ME_MAX_POOLW 600
+
+namespace me {
+
+template <int NR_, int NC_>
+struct Lay {
+    static constexpr int NR = NR_, NC = NC_;
+    static constexpr int D = NR + 2 * NC;
+    static constexpr int NCOVR = NR * (NR + 1) / 2;
+    static constexpr int NCOVC = NC * NC;
+    static constexpr int NOBS = 2 * NR + NC;
+    static constexpr int X = 0;
+    static constexpr int E = D;
+    static constexpr int SIG = D + 1;
+    static constexpr int MEAN = D + 3;
+    static constexpr int COVR = MEAN + D;
+    static constexpr int COVC = COVR + NCOVR;
+    static constexpr int OBSM = COVC + NCOVC;
+    static constexpr int FACR = OBSM + NOBS;
+    static constexpr int FACC = FACR + NCOVR;
+    static constexpr int NACC = FACC + NCOVC;
+    static constexpr int STATUS = NACC + 1;
+    static constexpr int WORDS = STATUS + 1;
+    static constexpr int TSCOLS = D + 2;                       /* x[D], E, sigma */
+    static constexpr int POOLW = D + D * (D + 1) / 2 + NOBS;   /* sum(x-s), sum (x-s)(x-s)^T lower, sum obs */
+    static constexpr int KIND = (NR > 0 && NC > 0) ? 0 : (NR > 0 ? 1 : 2);   /* 0 mixed, 1 all-real, 2 all-complex */
+    static constexpr int SIGIDX = (KIND == 2) ? 1 : 0;         /* which width step_all adapts (ME:46,56) */
+};
+
+__host__ __device__ constexpr int nz(int n) { return n > 0 ? n : 1; }
+__device__ __forceinline__ constexpr int herm_lo(int i, int j) { return 2 * (i * (i - 1) / 2 + j); }
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+/* ------------------------------------------------------------------------------------------ Philox4x32-10 */
+struct U4 { unsigned x, y, z, w; };
+
+__device__ __forceinline__ U4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                            unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0;
+        const unsigned n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+/* 53-bit uniform on [0,1): (hi>>5)*2^-27 + (lo>>6)*2^-53 — the bit recipe of CPython's random.random(), the
+ * generator behind the reference's accept test (metropolis_engine.py:335).  Integer->double conversion is done
+ * with exponent-biased magic numbers (exact, 3 DADD, no I2F). */
+__device__ __forceinline__ double u53(unsigned hi, unsigned lo) {
+    const double a = __hiloint2double(0x43300000 - (27 << 20), (int)(hi >> 5)) - 33554432.0;   /* (hi>>5) * 2^-27 */
+    const double b = __hiloint2double(0x43300000 - (53 << 20), (int)(lo >> 6)) - 0.5;          /* (lo>>6) * 2^-53 */
+    return a + b;
+}
+
+struct Rng {
+    unsigned c0, c1, k0, k1;
+    __device__ __forceinline__ Rng(unsigned long long seed, unsigned long long gchain)
+        : c0((unsigned)gchain), c1((unsigned)(gchain >> 32)), k0((unsigned)seed), k1((unsigned)(seed >> 32)) {}
+    __device__ __forceinline__ U4 bits(unsigned step, unsigned slot) const {
+        return philox4x32_10(c0, c1, step, slot, k0, k1);
+    }
+    /* one Philox call -> one Box-Muller pair of standard normals */
+    __device__ __forceinline__ void normal_pair(unsigned step, unsigned slot, double &z0, double &z1) const {
+        const U4 r = bits(step, slot);
+        const double u1 = u53(r.x, r.y) + 1.1102230246251565e-16;   /* (0,1] */
+        const double u2 = u53(r.z, r.w);                            /* [0,1) */
+        const double rad = sqrt(-2.0 * log(u1));
+        double s, c;
+        sincospi(2.0 * u2, &s, &c);
+        z0 = rad * c;
+        z1 = rad * s;
+    }
+    __device__ __forceinline__ double uniform(unsigned step, unsigned slot) const {
+        const U4 r = bits(step, slot);
+        return u53(r.x, r.y);
+    }
+};
+
+/* ------------------------------------------------------------------------------------------ per-chain registers */
+template <class L>
+struct Chain {
+    double x[L::D];
+    double e;
+    double sig[2];
+    double facr[nz(L::NCOVR)];
+    double facc[nz(L::NCOVC)];
+    double nacc;
+    int status;
+};
+
+template <class L>
+struct Stats {
+    double mean[L::D];
+    double covr[nz(L::NCOVR)];
+    double covc[nz(L::NCOVC)];
+    double obsm[L::NOBS];
+};
+
+template <class L>
+__device__ __forceinline__ void load_chain(Chain<L> &c, const double *st, long long ld, long long ch) {
+#pragma unroll
+    for (int i = 0; i < L::D; i++) c.x[i] = st[(long long)(L::X + i) * ld + ch];
+    c.e = st[(long long)L::E * ld + ch];
+    c.sig[0] = st[(long long)L::SIG * ld + ch];
+    c.sig[1] = st[(long long)(L::SIG + 1) * ld + ch];
+#pragma unroll
+    for (int i = 0; i < L::NCOVR; i++) c.facr[i] = st[(long long)(L::FACR + i) * ld + ch];
+#pragma unroll
+    for (int i = 0; i < L::NCOVC; i++) c.facc[i] = st[(long long)(L::FACC + i) * ld + ch];
+    c.nacc = st[(long long)L::NACC * ld + ch];
+    c.status = (int)st[(long long)L::STATUS * ld + ch];
+}
+
+template <class L>
+__device__ __forceinline__ void store_chain(const Chain<L> &c, double *st, long long ld, long long ch) {
+#pragma unroll
+    for (int i = 0; i < L::D; i++) st[(long long)(L::X + i) * ld + ch] = c.x[i];
+    st[(long long)L::E * ld + ch] = c.e;
+    st[(long long)L::SIG * ld + ch] = c.sig[0];
+    st[(long long)(L::SIG + 1) * ld + ch] = c.sig[1];
+#pragma unroll
+    for (int i = 0; i < L::NCOVR; i++) st[(long long)(L::FACR + i) * ld + ch] = c.facr[i];
+#pragma unroll
+    for (int i = 0; i < L::NCOVC; i++) st[(long long)(L::FACC + i) * ld + ch] = c.facc[i];
+    st[(long long)L::NACC * ld + ch] = c.nacc;
+    st[(long long)L::STATUS * ld + ch] = (double)c.status;
+}
+
+template <class L>
+__device__ __forceinline__ void load_stats(Stats<L> &s, const double *st, long long ld, long long ch) {
+#pragma unroll
+    for (int i = 0; i < L::D; i++) s.mean[i] = st[(long long)(L::MEAN + i) * ld + ch];
+#pragma unroll
+    for (int i = 0; i < L::NCOVR; i++) s.covr[i] = st[(long long)(L::COVR + i) * ld + ch];
+#pragma unroll
+    for (int i = 0; i < L::NCOVC; i++) s.covc[i] = st[(long long)(L::COVC + i) * ld + ch];
+#pragma unroll
+    for (int i = 0; i < L::NOBS; i++) s.obsm[i] = st[(long long)(L::OBSM + i) * ld + ch];
+}
+
+template <class L>
+__device__ __forceinline__ void store_stats(const Stats<L> &s, double *st, long long ld, long long ch) {
+#pragma unroll
+    for (int i = 0; i < L::D; i++) st[(long long)(L::MEAN + i) * ld + ch] = s.mean[i];
+#pragma unroll
+    for (int i = 0; i < L::NCOVR; i++) st[(long long)(L::COVR + i) * ld + ch] = s.covr[i];
+#pragma unroll
+    for (int i = 0; i < L::NCOVC; i++) st[(long long)(L::COVC + i) * ld + ch] = s.covc[i];
+#pragma unroll
+    for (int i = 0; i < L::NOBS; i++) st[(long long)(L::OBSM + i) * ld + ch] = s.obsm[i];
+}
+
+/* ------------------------------------------------------------------------------------------ Cholesky factors
+ * Replaces the SVD hidden inside np.random.multivariate_normal (metropolis_engine.py:268,300): the factor only
+ * changes when measure() changes the covariance, so it is recomputed there, not per step.
+ * Real block C_r = L L^T; complex block C_c = G G^H.  Returns nonzero if a pivot was not positive. */
+template <class L>
+__device__ __forceinline__ int refactor(const Stats<L> &s, Chain<L> &c) {
+    int bad = 0;
+#pragma unroll
+    for (int i = 0; i < L::NR; i++) {
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double a = s.covr[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; k++) a -= c.facr[tri(i, k)] * c.facr[tri(j, k)];
+            if (i == j) {
+                if (!(a > 0.0)) { bad = 1; a = 0.0; }
+                c.facr[tri(i, i)] = sqrt(a);
+            } else {
+                const double piv = c.facr[tri(j, j)];
+                c.facr[tri(i, j)] = piv > 0.0 ? a / piv : 0.0;
+            }
+        }
+    }
+    constexpr int dg = L::NC * (L::NC - 1);
+#pragma unroll
+    for (int i = 0; i < L::NC; i++) {
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            if (i == j) {
+                double a = s.covc[dg + i];
+#pragma unroll
+                for (int k = 0; k < j; k++) {
+                    const double re = c.facc[herm_lo(i, k)], im = c.facc[herm_lo(i, k) + 1];
+                    a -= re * re + im * im;
+                }
+                if (!(a > 0.0)) { bad = 1; a = 0.0; }
+                c.facc[dg + i] = sqrt(a);
+            } else {
+                double are = s.covc[herm_lo(i, j)], aim = s.covc[herm_lo(i, j) + 1];
+#pragma unroll
+                for (int k = 0; k < j; k++) {   /* a -= G_ik conj(G_jk) */
+                    const double pr = c.facc[herm_lo(i, k)], pi = c.facc[herm_lo(i, k) + 1];
+                    const double qr = c.facc[herm_lo(j, k)], qi = c.facc[herm_lo(j, k) + 1];
+                    are -= pr * qr + pi * qi;
+                    aim -= pi * qr - pr * qi;
+                }
+                const double piv = c.facc[dg + j];
+                c.facc[herm_lo(i, j)] = piv > 0.0 ? are / piv : 0.0;
+                c.facc[herm_lo(i, j) + 1] = piv > 0.0 ? aim / piv : 0.0;
+            }
+        }
+    }
+    return bad;
+}
+
+/* ------------------------------------------------------------------------------------------ proposal
+ * real block   x' = x + sigma_r L z                         ~ N(x, sigma_r^2 C_r)          (ME:268-270)
+ * complex      c' = c + sigma_c conj(G) xi, xi=(z+iz')/sqrt2 ~ CN(c, sigma_c^2 conj(C_c))   (ME:288-302; App. B-8)
+ * Draw order per step: real block first, then complex (ME:246).  Normals (2q, 2q+1) come from Philox slot q. */
+template <class L>
+__device__ __forceinline__ void propose(const Chain<L> &c, const Rng &rng, unsigned step, double (&prop)[L::D]) {
+    constexpr int NZ = (L::D + 1) / 2 * 2;
+    double z[NZ];
+#pragma unroll
+    for (int q = 0; q < NZ / 2; q++) rng.normal_pair(step, (unsigned)q, z[2 * q], z[2 * q + 1]);
+#pragma unroll
+    for (int i = 0; i < L::NR; i++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j <= i; j++) acc = acc + c.facr[tri(i, j)] * z[j];
+        prop[i] = c.x[i] + c.sig[0] * acc;
+    }
+    constexpr int dg = L::NC * (L::NC - 1);
+    const double sc = c.sig[1] * 0.70710678118654752440;
+#pragma unroll
+    for (int i = 0; i < L::NC; i++) {
+        double are = 0.0, aim = 0.0;
+#pragma unroll
+        for (int j = 0; j < i; j++) {
+            const double lre = c.facc[herm_lo(i, j)], lim = -c.facc[herm_lo(i, j) + 1];
+            const double zre = z[L::NR + 2 * j], zim = z[L::NR + 2 * j + 1];
+            are = are + (lre * zre - lim * zim);
+            aim = aim + (lre * zim + lim * zre);
+        }
+        are = are + c.facc[dg + i] * z[L::NR + 2 * i];
+        aim = aim + c.facc[dg + i] * z[L::NR + 2 * i + 1];
+        prop[L::NR + i] = c.x[L::NR + i] + sc * are;
+        prop[L::NR + L::NC + i] = c.x[L::NR + L::NC + i] + sc * aim;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ decision + adaptation */
+struct Gains {            /* per measure-block constants of the Robbins-Monro update (ME:429-456) */
+    double f;             /* max(n_measure / m, 200) */
+    double up, down;      /* fast mode: ratio (1 - target) / f and ratio target / f */
+};
+
+__device__ __forceinline__ Gains make_gains(long long n_meas, const MeParams &p) {
+    Gains g;
+    double f = (double)n_meas / (double)p.m;
+    if (!(f > 200.0)) f = 200.0;
+    g.f = f;
+    g.up = p.ratio * (1 - p.target) / f;
+    g.down = p.ratio * p.target / f;
+    return g;
+}
+
+/* Metropolis test (ME:319-338): ties accept; T == 0 rejects every uphill move; otherwise u <= exp(-1*diff/T). */
+template <bool STRICT>
+__device__ __forceinline__ bool decide(double diff, double u, const MeParams &p) {
+    if (diff <= 0) return true;
+    if (p.temp == 0) return false;
+    const double prob = STRICT ? exp(-1 * diff / p.temp) : exp(-diff * p.inv_temp);
+    return u <= prob;
+}
+
+template <bool STRICT>
+__device__ __forceinline__ double adapt_sigma(double sig, bool accept, const Gains &g, const MeParams &p) {
+    if (STRICT) {
+        const double c = sig * p.ratio;
+        return accept ? sig + (c * (1 - p.target)) / g.f : sig - (c * p.target) / g.f;
+    }
+    return accept ? sig + sig * g.up : sig - sig * g.down;
+}
+
+/* ------------------------------------------------------------------------------------------ measure (ME:342-427)
+ * Running means, Haario recursion + sigma^2/n regulariser once n > 50, observable means; evaluation order as in
+ * the reference.  numpy divides a complex array by a real as multiplication by the reciprocal,
+ * so the complex block uses inv_n / inv_n1 where the real block divides. */
+template <class L>
+__device__ __forceinline__ void measure_update(Chain<L> &c, Stats<L> &s, long long n) {
+    constexpr int NR = L::NR, NC = L::NC;
+    const double dn = (double)n, dn1 = (double)(n - 1), dn2 = (double)(n - 2);
+    const double shrink = dn1 / dn;
+    const bool adapt_cov = n > 50;
+    const double decay = dn2 / dn1, grow = dn / dn1;
+    if (NR > 0) {
+        double old[nz(NR)];
+#pragma unroll
+        for (int i = 0; i < NR; i++) old[i] = s.mean[i];
+#pragma unroll
+        for (int i = 0; i < NR; i++) { s.mean[i] = s.mean[i] * shrink; s.mean[i] = s.mean[i] + c.x[i] / dn; }
+        if (adapt_cov) {
+            const double small = (c.sig[0] * c.sig[0]) / dn;
+#pragma unroll
+            for (int i = 0; i < NR; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) {
+                    const double v = s.covr[tri(i, j)] * decay;
+                    const double add = ((old[i] * old[j] - grow * (s.mean[i] * s.mean[j])) + (c.x[i] * c.x[j]) / dn1)
+                                       + (i == j ? small : 0.0);
+                    s.covr[tri(i, j)] = v + add;
+                }
+        }
+    }
+    if (NC > 0) {
+        const double inv_n = 1.0 / dn, inv_n1 = 1.0 / dn1;
+        double *xr = c.x + NR, *xi = c.x + NR + NC, *mr = s.mean + NR, *mi = s.mean + NR + NC;
+        double orr[nz(NC)], oi[nz(NC)];
+#pragma unroll
+        for (int j = 0; j < NC; j++) { orr[j] = mr[j]; oi[j] = mi[j]; }
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            mr[j] = mr[j] * shrink; mi[j] = mi[j] * shrink;
+            mr[j] = mr[j] + xr[j] * inv_n; mi[j] = mi[j] + xi[j] * inv_n;
+        }
+        if (adapt_cov) {
+            const double small = (c.sig[1] * c.sig[1]) / dn;
+            constexpr int dg = NC * (NC - 1);
+#pragma unroll
+            for (int i = 0; i < NC; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) {
+                    const double o_re = orr[i] * orr[j] + oi[i] * oi[j], o_im = oi[i] * orr[j] - orr[i] * oi[j];
+                    const double m_re = mr[i] * mr[j] + mi[i] * mi[j], m_im = mi[i] * mr[j] - mr[i] * mi[j];
+                    const double x_re = xr[i] * xr[j] + xi[i] * xi[j], x_im = xi[i] * xr[j] - xr[i] * xi[j];
+                    const double a_re = ((o_re - grow * m_re) + x_re * inv_n1) + (i == j ? small : 0.0);
+                    const double a_im = ((o_im - grow * m_im) + x_im * inv_n1);
+                    if (i == j) {
+                        s.covc[dg + i] = s.covc[dg + i] * decay + a_re;
+                    } else {
+                        s.covc[herm_lo(i, j)] = s.covc[herm_lo(i, j)] * decay + a_re;
+                        s.covc[herm_lo(i, j) + 1] = s.covc[herm_lo(i, j) + 1] * decay + a_im;
+                    }
+                }
+        }
+    }
+    /* observables |x_i|, |c_j|, x_i^2 (ME:458-463) and their running mean (ME:412-414) */
+#pragma unroll
+    for (int i = 0; i < NR; i++) s.obsm[i] = s.obsm[i] * shrink + fabs(c.x[i]) / dn;
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+        s.obsm[NR + j] = s.obsm[NR + j] * shrink + hypot(c.x[NR + j], c.x[NR + NC + j]) / dn;
+#pragma unroll
+    for (int i = 0; i < NR; i++) s.obsm[NR + NC + i] = s.obsm[NR + NC + i] * shrink + (c.x[i] * c.x[i]) / dn;
+    if (adapt_cov && refactor<L>(s, c)) c.status |= ME_STATUS_NOT_PSD;
+}
+
+/* ------------------------------------------------------------------------------------------ pooled moments
+ * Ensemble-level shifted raw moments  sum(x-s), sum (x-s)(x-s)^T, sum obs  over every (chain, measure) sample —
+ * the quantity the pooled-statistics all-reduce sums across GPUs.  No reference counterpart
+ * (the reference is one chain); pooled mean/covariance are derived on the host. */
+template <class L, class F>
+__device__ __forceinline__ void for_each_pool_word(const Chain<L> &c, const double (&sh)[L::D], F &&f) {
+    constexpr int D = L::D, NR = L::NR, NC = L::NC;
+    double dx[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) dx[i] = c.x[i] - sh[i];
+#pragma unroll
+    for (int i = 0; i < D; i++) f(i, dx[i]);
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) f(D + tri(i, j), dx[i] * dx[j]);
+    constexpr int O = D + D * (D + 1) / 2;
+#pragma unroll
+    for (int i = 0; i < NR; i++) f(O + i, fabs(c.x[i]));
+#pragma unroll
+    for (int j = 0; j < NC; j++) f(O + NR + j, hypot(c.x[NR + j], c.x[NR + NC + j]));
+#pragma unroll
+    for (int i = 0; i < NR; i++) f(O + NR + NC + i, c.x[i] * c.x[i]);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ME_FULL, v, o);
+    return v;
+}
+
+/* ------------------------------------------------------------------------------------------ the fused kernel body
+ * Cfg:  NR, NC, Energy (functor with eval / reject), STRICT (reference operation order + draw injection).   */
+template <class Cfg>
+__device__ __forceinline__ void run_body(const MeParams &p) {
+    using L = Lay<Cfg::NR, Cfg::NC>;
+    using Energy = typename Cfg::Energy;
+    constexpr bool STRICT = Cfg::STRICT;
+    constexpr int D = L::D;
+    /* small problems keep running statistics and pooled accumulators in registers for the whole launch;
+       larger ones touch them in global memory at measure time only */
+    constexpr bool STATS_REG = (L::D + L::NCOVR + L::NCOVC + L::NOBS) <= 12;
+    constexpr bool POOL_REG = L::POOLW <= 9;
+    constexpr bool POOL_OK = L::POOLW <= ME_MAX_POOLW;        /* static shared-memory budget */
+    constexpr int PW = POOL_OK ? L::POOLW : 1;
+
+    __shared__ double pool_warp[ME_MAX_BLOCK / 32][PW];
+    __shared__ double pool_cta[PW];
+
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = tid < p.n_chains;
+    const long long ch = active ? tid : p.n_chains - 1;
+    const long long ld = p.ld;
+    double *st = p.state;
+
+    Chain<L> c;
+    load_chain<L>(c, st, ld, ch);
+    Stats<L> sreg;
+    if (STATS_REG) load_stats<L>(sreg, st, ld, ch);
+    double pacc[nz(POOL_REG ? L::POOLW : 0)];
+    if (POOL_REG) {
+#pragma unroll
+        for (int w = 0; w < L::POOLW; w++) pacc[w] = 0.0;
+    }
+    const bool pooling = POOL_OK && p.pool != nullptr && p.do_measure;
+    if (pooling && !POOL_REG) {
+        for (int w = threadIdx.x; w < L::POOLW; w += blockDim.x) pool_cta[w] = 0.0;
+        __syncthreads();
+    }
+    double shift[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) shift[i] = pooling ? p.shift[i] : 0.0;
+
+    const Rng rng(p.seed, p.chain_offset + (unsigned long long)ch);
+    const bool inject = STRICT && p.inj_delta != nullptr;
+    long long n = p.n_meas0;
+    unsigned long long step = p.step0;
+    long long s_local = 0;
+    bool accept = false;
+
+    for (long long b = 0; b < p.n_blocks; b++) {
+        const Gains g = make_gains(n, p);
+        for (long long k = 0; k < p.spm; k++, step++, s_local++) {
+            double prop[D];
+            if (inject) {
+#pragma unroll
+                for (int i = 0; i < D; i++) prop[i] = p.inj_delta[(s_local * D + i) * ld + ch] + c.x[i];
+            } else {
+                propose<L>(c, rng, (unsigned)step, prop);
+            }
+            accept = false;
+            const bool wall = p.use_reject && Energy::reject(prop, prop + L::NR, prop + L::NR + L::NC, p.consts);
+            if (!wall) {
+                const double e_new = Energy::eval(prop, prop + L::NR, prop + L::NR + L::NC, p.consts);
+                if (e_new != e_new) c.status |= ME_STATUS_ENERGY_NAN;
+                const double diff = e_new - c.e;
+                double u = 0.0;
+                if (inject) u = p.inj_u[s_local * ld + ch];
+                else if (diff > 0 && p.temp != 0) u = rng.uniform((unsigned)step, (unsigned)((D + 1) / 2));
+                accept = decide<STRICT>(diff, u, p);
+                if (accept) {
+                    c.e = e_new;
+#pragma unroll
+                    for (int i = 0; i < D; i++) c.x[i] = prop[i];
+                    c.nacc += 1.0;
+                }
+            }
+            const double sg = adapt_sigma<STRICT>(c.sig[L::SIGIDX], accept, g, p);
+            c.sig[L::SIGIDX] = sg;
+            if (L::KIND == 0) { c.sig[1] = sg; if (!(sg > 0)) c.status |= ME_STATUS_SIGMA_NONPOS; }
+        }
+        if (p.do_measure) {
+            n += 1;
+            if (STATS_REG) {
+                measure_update<L>(c, sreg, n);
+            } else {
+                Stats<L> s;
+                load_stats<L>(s, st, ld, ch);
+                measure_update<L>(c, s, n);
+                if (active) store_stats<L>(s, st, ld, ch);
+            }
+            if (p.record && active) {
+                double *row = p.ts + (p.ts_row0 + b) * (long long)L::TSCOLS * ld + ch;
+#pragma unroll
+                for (int i = 0; i < D; i++) __stcs(row + (long long)i * ld, c.x[i]);
+                __stcs(row + (long long)D * ld, c.e);
+                __stcs(row + (long long)(D + 1) * ld, c.sig[L::SIGIDX]);
+            }
+            if (pooling) {
+                if (POOL_REG) {
+for_each_pool_word<L>(c, shift, [&](int w, double v) { pacc[w] += v; });
+                } else {
+                    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                    for_each_pool_word<L>(c, shift, [&](int w, double v) {
+                        v = warp_sum(active ? v : 0.0);
+                        if (lane == 0) pool_warp[warp][w] = v;
+                    });
+                    __syncthreads();
+                    const int nw = (blockDim.x + 31) >> 5;
+                    for (int w = threadIdx.x; w < L::POOLW; w += blockDim.x) {
+                        double t = 0.0;
+                        for (int q = 0; q < nw; q++) t += pool_warp[q][w];
+                        pool_cta[w] += t;
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+    }
+
+    if (active) {
+        store_chain<L>(c, st, ld, ch);
+        if (STATS_REG && p.do_measure) store_stats<L>(sreg, st, ld, ch);
+        if (p.last_accept && p.spm > 0 && p.n_blocks > 0) p.last_accept[ch] = (unsigned char)accept;
+    }
+    if (pooling) {
+        if (POOL_REG) {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+            for (int w = 0; w < L::POOLW; w++) {
+                const double v = warp_sum(active ? pacc[w] : 0.0);
+                if (lane == 0) pool_warp[warp][w] = v;
+            }
+            __syncthreads();
+            const int nw = (blockDim.x + 31) >> 5;
+            for (int w = threadIdx.x; w < L::POOLW; w += blockDim.x) {
+                double t = 0.0;
+                for (int q = 0; q < nw; q++) t += pool_warp[q][w];
+                p.pool[(long long)blockIdx.x * L::POOLW + w] += t;
+            }
+        } else {
+            for (int w = threadIdx.x; w < L::POOLW; w += blockDim.x)
+                p.pool[(long long)blockIdx.x * L::POOLW + w] += pool_cta[w];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ initialisation (ME:40-125)
+ * x <- x0; means <- x0; covariances <- identity or the constructor-supplied matrices (ME:63-70); observable means
+ * <- observables of x0 (ME:80-81); widths <- sampling_width (ME:93-99); energy <- functor(x0) (ME:123-125). */
+template <class Cfg>
+__device__ __forceinline__ void init_body(const MeParams &p) {
+    using L = Lay<Cfg::NR, Cfg::NC>;
+    using Energy = typename Cfg::Energy;
+    constexpr int NR = L::NR, NC = L::NC, D = L::D;
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_chains) return;
+    const long long ld = p.ld;
+    Chain<L> c;
+    Stats<L> s;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        c.x[i] = p.x0_broadcast ? p.x0[i] : p.x0[(long long)i * ld + ch];
+        s.mean[i] = c.x[i];
+    }
+    c.sig[0] = c.sig[1] = p.sigma0;
+#pragma unroll
+    for (int i = 0; i < NR; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) s.covr[tri(i, j)] = p.cov_r0 ? p.cov_r0[i * NR + j] : (i == j ? 1.0 : 0.0);
+    constexpr int dg = NC * (NC - 1);
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        s.covc[dg + i] = p.cov_c0_re ? p.cov_c0_re[i * NC + i] : 1.0;
+#pragma unroll
+        for (int j = 0; j < i; j++) {
+            s.covc[herm_lo(i, j)] = p.cov_c0_re ? p.cov_c0_re[i * NC + j] : 0.0;
+            s.covc[herm_lo(i, j) + 1] = p.cov_c0_im ? p.cov_c0_im[i * NC + j] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NR; i++) s.obsm[i] = fabs(c.x[i]);
+#pragma unroll
+    for (int j = 0; j < NC; j++) s.obsm[NR + j] = hypot(c.x[NR + j], c.x[NR + NC + j]);
+#pragma unroll
+    for (int i = 0; i < NR; i++) s.obsm[NR + NC + i] = c.x[i] * c.x[i];
+    c.e = p.have_e0 ? p.e_new[ch] : Energy::eval(c.x, c.x + NR, c.x + NR + NC, p.consts);
+    c.nacc = 0.0;
+    c.status = 0;
+    if (c.e != c.e) c.status |= ME_STATUS_ENERGY_NAN;
+    if (refactor<L>(s, c)) c.status |= ME_STATUS_NOT_PSD;
+    store_chain<L>(c, p.state, ld, ch);
+    store_stats<L>(s, p.state, ld, ch);
+}
+
+/* ------------------------------------------------------------------------------------------ unfused path
+ * For energies given as a torch-vectorised callable: propose -> (callable on the proposal block) -> accept.
+ * Same proposal / decision / adaptation code as the fused kernel, with one HBM round trip in between. */
+template <class Cfg>
+__device__ __forceinline__ void propose_body(const MeParams &p) {
+    using L = Lay<Cfg::NR, Cfg::NC>;
+    constexpr int D = L::D;
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_chains) return;
+    Chain<L> c;
+    load_chain<L>(c, p.state, p.ld, ch);
+    double prop[D];
+    if (Cfg::STRICT && p.inj_delta != nullptr) {
+#pragma unroll
+        for (int i = 0; i < D; i++) prop[i] = p.inj_delta[(long long)i * p.ld + ch] + c.x[i];
+    } else {
+        const Rng rng(p.seed, p.chain_offset + (unsigned long long)ch);
+        propose<L>(c, rng, (unsigned)p.step0, prop);
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) p.prop[(long long)i * p.ld + ch] = prop[i];
+}
+
+template <class Cfg>
+__device__ __forceinline__ void accept_body(const MeParams &p) {
+    using L = Lay<Cfg::NR, Cfg::NC>;
+    constexpr bool STRICT = Cfg::STRICT;
+    constexpr int D = L::D;
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_chains) return;
+    const long long ld = p.ld;
+    double *st = p.state;
+    double e = st[(long long)L::E * ld + ch];
+    double sg = st[(long long)(L::SIG + L::SIGIDX) * ld + ch];
+    int status = (int)st[(long long)L::STATUS * ld + ch];
+    const Gains g = make_gains(p.n_meas0, p);
+    bool accept = false;
+    const bool wall = p.rej != nullptr && p.rej[ch] != 0;
+    if (!wall) {
+        const double e_new = p.e_new[ch];
+        if (e_new != e_new) status |= ME_STATUS_ENERGY_NAN;
+        const double diff = e_new - e;
+        double u = 0.0;
+        if (STRICT && p.inj_u != nullptr) u = p.inj_u[ch];
+        else if (diff > 0 && p.temp != 0) {
+            const Rng rng(p.seed, p.chain_offset + (unsigned long long)ch);
+            u = rng.uniform((unsigned)p.step0, (unsigned)((D + 1) / 2));
+        }
+        accept = decide<STRICT>(diff, u, p);
+        if (accept) {
+            st[(long long)L::E * ld + ch] = e_new;
+#pragma unroll
+            for (int i = 0; i < D; i++) st[(long long)(L::X + i) * ld + ch] = p.prop[(long long)i * ld + ch];
+            st[(long long)L::NACC * ld + ch] += 1.0;
+        }
+    }
+    sg = adapt_sigma<STRICT>(sg, accept, g, p);
+    st[(long long)(L::SIG + L::SIGIDX) * ld + ch] = sg;
+    if (L::KIND == 0) {
+        st[(long long)(L::SIG + 1) * ld + ch] = sg;
+        if (!(sg > 0)) status |= ME_STATUS_SIGMA_NONPOS;
+    }
+    st[(long long)L::STATUS * ld + ch] = (double)status;
+    if (p.last_accept) p.last_accept[ch] = (unsigned char)accept;
+}
+
+}  // namespace me
+
+#endif

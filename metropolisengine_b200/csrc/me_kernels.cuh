@@ -1,0 +1,52 @@
+/* me_kernels.cuh — __global__ entry points around the device bodies of me_device.cuh, and the table type the
+ * host library uses to find ahead-of-time instantiations. */
+#ifndef ME_KERNELS_CUH
+#define ME_KERNELS_CUH
+
+#include "me_device.cuh"
+#include "me_energies.cuh"
+
+namespace me {
+
+template <int NR_, int NC_, template <int, int> class EnergyT, bool STRICT_>
+struct Cfg {
+    static constexpr int NR = NR_, NC = NC_;
+    static constexpr bool STRICT = STRICT_;
+    using Energy = EnergyT<NR_, NC_>;
+};
+
+template <class C>
+__global__ void __launch_bounds__(ME_MAX_BLOCK) k_run(const __grid_constant__ MeParams p) { run_body<C>(p); }
+template <class C>
+__global__ void __launch_bounds__(ME_MAX_BLOCK) k_init(const __grid_constant__ MeParams p) { init_body<C>(p); }
+template <class C>
+__global__ void __launch_bounds__(ME_MAX_BLOCK) k_propose(const __grid_constant__ MeParams p) { propose_body<C>(p); }
+template <class C>
+__global__ void __launch_bounds__(ME_MAX_BLOCK) k_accept(const __grid_constant__ MeParams p) { accept_body<C>(p); }
+
+}  // namespace me
+
+/* one ahead-of-time instantiation */
+struct MeAotEntry {
+    int n_real, n_complex, energy_id, strict;
+    const void *run, *init, *propose, *accept;
+};
+
+#define ME_AOT_ENTRY(NR, NC, ETMPL, EID, STRICT)                                                        \
+    { NR, NC, EID, STRICT, (const void *)&me::k_run<me::Cfg<NR, NC, ETMPL, STRICT>>,                      \
+      (const void *)&me::k_init<me::Cfg<NR, NC, ETMPL, STRICT>>,                                          \
+      (const void *)&me::k_propose<me::Cfg<NR, NC, ETMPL, STRICT>>,                                       \
+      (const void *)&me::k_accept<me::Cfg<NR, NC, ETMPL, STRICT>> }
+
+/* the shapes of BASELINE.json's configs plus the shapes of the golden fixtures */
+#define ME_AOT_TABLE(STRICT)                                                      \
+    ME_AOT_ENTRY(1, 0, me::EnergyX2, 0, STRICT),        /* C1 README            */ \
+    ME_AOT_ENTRY(2, 0, me::EnergyXYWell, 1, STRICT),    /* C2 xy-well           */ \
+    ME_AOT_ENTRY(2, 1, me::EnergyMixedWell, 2, STRICT), /* demo 2r+1c           */ \
+    ME_AOT_ENTRY(3, 4, me::EnergyMixedWell, 2, STRICT), /* C3 mixed 3r+4c       */ \
+    ME_AOT_ENTRY(1, 8, me::EnergyCylinder, 3, STRICT),  /* cylinder-shaped 1r+8c */ \
+    ME_AOT_ENTRY(1, 0, me::EnergyNone, 99, STRICT),     /* caller-evaluated energies */ \
+    ME_AOT_ENTRY(2, 0, me::EnergyNone, 99, STRICT),                                  \
+    ME_AOT_ENTRY(2, 1, me::EnergyNone, 99, STRICT)
+
+#endif

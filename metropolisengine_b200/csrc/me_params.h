@@ -1,0 +1,55 @@
+/* me_params.h — plain-old-data launch parameters shared by the host library, the ahead-of-time kernels and the
+ * NVRTC-compiled user-functor kernels.  Built-in types only (this text is also fed to NVRTC, which has no libc
+ * headers).  Any change here changes the ABI between libme_b200.so and runtime-compiled kernels: bump
+ * ME_PARAMS_VERSION. */
+#ifndef ME_PARAMS_H
+#define ME_PARAMS_H
+
+#define ME_PARAMS_VERSION 3
+#define ME_MAX_CONSTS 16
+
+/* status bits written to the per-chain STATUS word (SURVEY §5 "failure detection") */
+#define ME_STATUS_NOT_PSD 1      /* covariance lost positive-definiteness (reference: numpy raises, ME:270) */
+#define ME_STATUS_SIGMA_NONPOS 2 /* sampling width <= 0 (reference: assert, ME:438) */
+#define ME_STATUS_ENERGY_NAN 4   /* energy functor returned NaN */
+
+struct MeParams {
+    double *state;                 /* [WORDS][ld] chain-minor state block (layout: me_state_layout) */
+    long long ld;                  /* leading dimension of every [..][chain] array = local chain capacity */
+    long long n_chains;            /* chains owned by this launch (<= ld) */
+    unsigned long long chain_offset; /* global id of local chain 0: Philox counters carry GLOBAL chain ids */
+    unsigned long long seed;       /* Philox key */
+    unsigned long long step0;      /* global index of the first step of this launch */
+    long long n_blocks;            /* schedule: n_blocks x (spm steps [+ measure]) */
+    long long spm;
+    long long n_meas0;             /* measure_step_counter before this launch (reference starts at 1, ME:73) */
+    int do_measure;
+    int use_reject;
+    int m;                         /* n_real + n_complex (ME:103) */
+    int record;                    /* 1: store a time-series row at every measure */
+    double temp, inv_temp;
+    double target;                 /* target acceptance p* (ME:101) */
+    double ratio;                  /* ME:105-107 */
+    double consts[ME_MAX_CONSTS];  /* energy-functor constants */
+    double *ts;                    /* time series [row][TSCOLS][ld]; row = ts_row0 + block index */
+    long long ts_row0;
+    const double *inj_delta;       /* parity mode: increments [step][D][ld] (NULL = Philox) */
+    const double *inj_u;           /* parity mode: uniforms [step][ld], NaN = "reference drew none" */
+    unsigned char *last_accept;    /* [ld] accept flag of the last step of the launch (may be NULL) */
+    double *pool;                  /* [gridDim.x][POOLW] per-CTA pooled-moment accumulators (may be NULL) */
+    const double *shift;           /* [D] shift vector of the pooled moments */
+    /* unfused path (torch-callable energies) */
+    double *prop;                  /* [D][ld] proposals */
+    const double *e_new;           /* [ld] energies of the proposals */
+    const unsigned char *rej;      /* [ld] hard-constraint mask (may be NULL) */
+    /* initialisation */
+    const double *x0;              /* [D][ld] or [D] when x0_broadcast */
+    int x0_broadcast;
+    int have_e0;                   /* 1: take initial energies from e_new instead of the functor */
+    double sigma0;
+    const double *cov_r0;          /* [NR*NR] row-major, shared by all chains (NULL = identity) */
+    const double *cov_c0_re;       /* [NC*NC] */
+    const double *cov_c0_im;
+};
+
+#endif

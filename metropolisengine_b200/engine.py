@@ -1,0 +1,705 @@
+"""Host-side mirror of the reference's one public class, driving the CUDA hot path through the C ABI.
+
+``MetropolisEngine`` keeps the reference's constructor signature, method names and read attributes
+(/root/reference/metropolisengine/metropolis_engine.py, "ME"; README.md:23-58) and adds keyword-only ensemble
+controls.  A 1-chain engine behaves like the reference (numpy values, ``step_all()`` returns a bool); an
+``n_chains > 1`` engine runs that many independent chains on the GPU and reports pooled values, with
+``*_per_chain`` tensors beside them.
+
+Energy plugin forms (the reference's plugin surface, ME:20, ME:110-120):
+  * ``BuiltinEnergy`` / a name such as ``"xy_well"``     -> ahead-of-time fused kernels
+  * ``CudaEnergy(source)``                               -> device functor compiled with NVRTC, fused
+  * a python callable over torch tensors, or a dict of them (ME:111-115) -> unfused propose / callable / accept
+
+PyTorch is used for device memory, streams and torch.distributed only; all arithmetic of the path runs in
+libme_b200.so.  There is no CPU fallback.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import parallel
+
+
+class BuiltinEnergy:
+    """A built-in device energy functor (csrc/me_energies.cuh): ``x2``, ``xy_well(const)``,
+    ``mixed_well(k, alpha, beta)``, ``cylinder(kappa, alpha, gamma, beta)`` (the latter with its hard wall
+    ``|a| >= 1`` when ``reject=True``)."""
+
+    def __init__(self, name, *consts, reject=False):
+        if name not in _lib.ENERGY_IDS:
+            raise ValueError("unknown built-in energy %r (have %s)" % (name, sorted(_lib.ENERGY_IDS)))
+        self.name, self.consts, self.reject = name, tuple(float(c) for c in consts), bool(reject)
+
+
+class CudaEnergy:
+    """User device functor.  ``source`` is CUDA C++ defining::
+
+        __device__ double me_user_energy(const double* x, const double* c_re, const double* c_im, const double* k);
+        __device__ bool   me_user_reject(...same...);      // only when has_reject=True
+
+    ``x`` holds the real parameters, ``c_re`` / ``c_im`` the complex ones, ``k`` the ``consts``; the macros
+    ``ME_NR`` / ``ME_NC`` give the shape.  Compiled for sm_100a by NVRTC and fused into the step kernel."""
+
+    def __init__(self, source, consts=(), has_reject=False):
+        self.source, self.consts, self.has_reject = source, tuple(float(c) for c in consts), bool(has_reject)
+
+
+def adaptation_constants(n_real, n_complex, target_acceptance):
+    """alpha, m, ratio exactly as the reference evaluates them (ME:101-107; note ``/ 2 * alpha``)."""
+    try:
+        from scipy.stats import norm
+        alpha = -1 * norm.ppf(target_acceptance / 2)
+    except ImportError:                                    # pragma: no cover
+        from statistics import NormalDist
+        alpha = -1 * NormalDist().inv_cdf(target_acceptance / 2)
+    m = n_real + n_complex
+    ratio = ((1 - (1 / m)) * math.sqrt(2 * math.pi) * math.exp(alpha ** 2 / 2) / 2 * alpha
+             + 1 / (m * target_acceptance * (1 - target_acceptance)))
+    return float(alpha), m, float(ratio)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class MetropolisEngine:
+    """Adaptive random-walk Metropolis over real and complex parameters, many chains per GPU.
+
+    Positional/keyword arguments up to ``complex_sample_method`` are the reference's (ME:17).  Keyword-only
+    additions:
+
+    n_chains          chains in the whole job (default 1 = reference behaviour)
+    seed              Philox key; chain i of the job always uses sub-stream i
+    device            torch device (default: current CUDA device)
+    strict            reference operation order without FMA contraction; enables ``run_injected``
+    record            keep a time-series row per chain at every ``measure()`` (default True)
+    callable_layout   layout of the tensors handed to a python energy callable: ``"chains_first"``
+                      ([chains, n_params], default) or ``"params_first"`` ([n_params, chains], so reference-style
+                      bodies such as ``real_params[0]**2`` vectorise unchanged)
+    distributed       shard ``n_chains`` over the ranks of the default torch.distributed group
+    """
+
+    def __init__(self, energy_functions, reject_condition=None, initial_real_params=None,
+                 initial_complex_params=None, sampling_width=0.05, covariance_matrix_real=None,
+                 covariance_matrix_complex=None, params_names=None, target_acceptance=.3, temp=0,
+                 complex_sample_method="multivariate-gaussian", *, n_chains=1, seed=0, device=None, strict=False,
+                 record=True, callable_layout="chains_first", distributed=False, ts_chunk_bytes=1 << 30,
+                 _shard=None):
+        if initial_real_params is None and initial_complex_params is None:
+            raise ValueError("must give a list containing at least one value for initial real or complex "
+                             "parameters")                                                   # ME:37-39
+        if complex_sample_method != "multivariate-gaussian":
+            raise NotImplementedError("only the multivariate-gaussian complex proposal is on the accelerated path "
+                                      "(magnitude-phase is SURVEY.md §8 row f4)")
+        if temp is None or not temp >= 0:
+            raise AssertionError("temp must be >= 0")                                        # ME:92
+        if isinstance(sampling_width, (list, tuple)):
+            raise NotImplementedError("per-group sampling widths belong to group-wise stepping (SURVEY §8 row f1)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("MetropolisEngine needs a CUDA device: the hot path is CUDA-only (no CPU fallback)")
+        self._lib = _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+
+        # ---- parameter space (ME:40-60)
+        xr = None if initial_real_params is None else np.asarray(initial_real_params, dtype=np.float64)
+        xc = None if initial_complex_params is None else np.asarray(initial_complex_params, dtype=np.complex128)
+        self.num_real_params = 0 if xr is None else xr.shape[-1]
+        self.num_complex_params = 0 if xc is None else xc.shape[-1]
+        self.param_space_dims = self.num_real_params + self.num_complex_params
+        if self.param_space_dims == 0:
+            raise ValueError("empty parameter space")
+        nr, nc = self.num_real_params, self.num_complex_params
+        self._kind = "mixed" if (nr and nc) else ("real" if nr else "complex")
+        self._lay = _lib.layout(nr, nc)
+        self._d = self._lay.D
+
+        # ---- chains and sharding
+        self.n_chains_total = int(n_chains)
+        self._group = None
+        self._rank, self._world = (parallel.world() if distributed else (0, 1))
+        lo, hi = parallel.shard_range(self.n_chains_total, self._rank, self._world)
+        if _shard is not None:          # explicit global chain range [lo, hi) (tests, custom launchers)
+            lo, hi = int(_shard[0]), int(_shard[1])
+        self.chain_offset, self.n_chains = lo, hi - lo
+        self._distributed = bool(distributed) and self._world > 1
+
+        per_chain_init = (xr is not None and xr.ndim == 2) or (xc is not None and xc.ndim == 2)
+        x0 = np.zeros((self._d, self.n_chains_total if per_chain_init else 1))
+        if xr is not None:
+            x0[:nr] = xr.T if xr.ndim == 2 else xr[:, None]
+        if xc is not None:
+            x0[nr:nr + nc] = (xc.real.T if xc.ndim == 2 else xc.real[:, None])
+            x0[nr + nc:] = (xc.imag.T if xc.ndim == 2 else xc.imag[:, None])
+        if per_chain_init and x0.shape[1] != self.n_chains_total:
+            raise ValueError("per-chain initial parameters must have n_chains rows")
+        self._shift_host = x0.mean(axis=1)
+
+        # ---- names (ME:82-87)
+        self.params_names = list(params_names) if params_names else ["param_" + str(i) for i in range(nr + nc)]
+        self.observables_names = ["abs_param_" + str(i) for i in range(nr + nc)]
+        self.observables_names.extend(["param_" + str(i) + "_squared" for i in range(nr)])
+
+        # ---- adaptation constants (ME:91-107)
+        self.temp = temp
+        self.target_acceptance = target_acceptance
+        self.alpha, self.m, self.ratio = adaptation_constants(nr, nc, target_acceptance)
+        self._sampling_width0 = float(sampling_width)
+        self.strict = bool(strict)
+        self.seed = int(seed)
+        self.df = None                                                                       # ME:108
+
+        # ---- native handle
+        cfg = _lib.MeConfig(nr, nc, self.n_chains, self.chain_offset, float(temp), float(target_acceptance),
+                            self.ratio, self.seed, self.device.index, int(self.strict))
+        h = ctypes.c_void_p()
+        _lib.check(None, self._lib.me_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        grid, block = ctypes.c_int32(), ctypes.c_int32()
+        self._lib.me_launch_dims(self._h, ctypes.byref(grid), ctypes.byref(block))
+        self._grid, self._block = grid.value, block.value
+
+        # ---- device buffers (owned here, borrowed by the library)
+        dev, f64 = self.device, torch.float64
+        self.state = torch.zeros((self._lay.WORDS, self.n_chains), dtype=f64, device=dev)
+        pw = self._lay.POOL_WORDS
+        self._pool = torch.zeros((self._grid, pw), dtype=f64, device=dev) if pw > 0 else None
+        self._shift = torch.tensor(self._shift_host, dtype=f64, device=dev)
+        self._last_accept = torch.zeros(self.n_chains, dtype=torch.uint8, device=dev)
+        self._pool_out = torch.zeros(max(pw, 1), dtype=f64, device=dev)
+        self._pool_sum = np.zeros(max(pw, 1))
+        self._pool_count = 0
+        bufs = _lib.MeBuffers(_ptr(self.state), _ptr(self._pool), _ptr(self._shift), _ptr(self._last_accept))
+        self._check(self._lib.me_bind(self._h, ctypes.byref(bufs)))
+
+        # ---- energy plugin (ME:110-120) and hard-wall predicate (ME:126-127, 142-146)
+        self._callable = None
+        self._terms = None
+        self._callable_layout = callable_layout
+        if callable_layout not in ("chains_first", "params_first"):
+            raise ValueError("callable_layout must be 'chains_first' or 'params_first'")
+        self.reject_condition = reject_condition
+        self._install_energy(energy_functions)
+
+        # ---- state initialisation (ME:63-81, 123-125)
+        if per_chain_init:
+            x0_dev = torch.tensor(np.ascontiguousarray(x0[:, lo:hi]), dtype=f64, device=dev)
+        else:
+            x0_dev = torch.tensor(np.ascontiguousarray(x0[:, 0]), dtype=f64, device=dev)
+        cov_r = cov_c_re = cov_c_im = None
+        if covariance_matrix_real is not None and nr:
+            cov_r = torch.tensor(np.ascontiguousarray(covariance_matrix_real, dtype=np.float64), device=dev)
+            assert cov_r.shape == (nr, nr)
+        if covariance_matrix_complex is not None and nc:
+            cc = np.asarray(covariance_matrix_complex, dtype=np.complex128)
+            assert cc.shape == (nc, nc)
+            cov_c_re = torch.tensor(np.ascontiguousarray(cc.real), device=dev)
+            cov_c_im = torch.tensor(np.ascontiguousarray(cc.imag), device=dev)
+        e0 = None
+        if self._callable is not None:
+            full = x0_dev if per_chain_init else x0_dev[:, None].expand(self._d, self.n_chains).contiguous()
+            e0 = self._eval_callable(full)
+        self._check(self._lib.me_init(self._h, _ptr(x0_dev), 0 if per_chain_init else 1, self._sampling_width0,
+                                      _ptr(cov_r), _ptr(cov_c_re), _ptr(cov_c_im), _ptr(e0), self._stream()))
+        self._energy0 = self.state[self._lay.E].clone()
+        self._term_energy0 = None
+        if self._terms is not None:
+            full = self.state[:self._d]
+            self._term_energy0 = {t: self._eval_term(fn, full).clone() for t, fn in self._terms["all"].items()}
+        self.step_counter = 1                                                               # ME:72
+        self.complex_group_step_counter = 1
+        self.real_group_step_counter = 1
+
+        # ---- time series (the lists of ME:31-35)
+        self.record = bool(record)
+        self._ts_chunks = []          # list of [tensor (rows, TS_COLS, n_chains), used_rows]
+        self._ts_rows = 0
+        self._ts_chunk_rows = max(1, min(1 << 16, int(ts_chunk_bytes) // (self._lay.TS_COLS * self.n_chains * 8)))
+        self._term_series = {} if self._terms is not None else None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        _lib.check(self._h, rc)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and getattr(self, "_lib", None) is not None:
+            self._lib.me_destroy(h)
+            self._h = None
+
+    def _install_energy(self, energy):
+        if isinstance(energy, str):
+            energy = BuiltinEnergy(energy)
+        elif isinstance(energy, tuple) and energy and isinstance(energy[0], str):
+            energy = BuiltinEnergy(energy[0], *energy[1:])
+        if isinstance(energy, BuiltinEnergy):
+            consts = (ctypes.c_double * max(len(energy.consts), 1))(*energy.consts)
+            self._check(self._lib.me_set_energy_builtin(self._h, _lib.ENERGY_IDS[energy.name], consts,
+                                                        len(energy.consts), int(energy.reject)))
+            self.energy_term_names = ["total"]
+        elif isinstance(energy, CudaEnergy):
+            consts = (ctypes.c_double * max(len(energy.consts), 1))(*energy.consts)
+            self._check(self._lib.me_set_energy_source(self._h, energy.source.encode(), consts, len(energy.consts),
+                                                       int(energy.has_reject)))
+            self.energy_term_names = ["total"]
+        elif isinstance(energy, dict):                       # dict of terms (ME:111-115)
+            names = set()
+            for group in energy.values():
+                names = names.union(group)
+            self.energy_term_names = names
+            self._terms = energy
+            self._callable = lambda r, c: sum(fn(r, c) for fn in energy["all"].values())
+            self._check(self._lib.me_set_energy_external(self._h))
+        elif callable(energy):
+            self.energy_term_names = ["total"]
+            self._callable = energy
+            self._check(self._lib.me_set_energy_external(self._h))
+        else:
+            raise TypeError("energy_functions must be a built-in name, BuiltinEnergy, CudaEnergy, a callable or a "
+                            "dict of callables")
+        self._energy_spec = energy
+
+    def set_energy_function(self, energy_function):                                        # ME:136-140
+        self._callable = self._terms = None
+        self._install_energy(energy_function)
+
+    def set_reject_condition(self, reject_fct):                                            # ME:142-146
+        self.reject_condition = reject_fct
+
+    def _split(self, block):
+        """[D, chains] block -> (real, complex) tensors in the callable's layout."""
+        nr, nc = self.num_real_params, self.num_complex_params
+        r = block[:nr]
+        c = torch.complex(block[nr:nr + nc], block[nr + nc:nr + 2 * nc]) if nc else block[:0].to(torch.complex128)
+        if self._callable_layout == "chains_first":
+            return r.t(), c.t()
+        return r, c
+
+    def _eval_term(self, fn, block):
+        r, c = self._split(block)
+        e = fn(r, c)
+        if not torch.is_tensor(e):
+            e = torch.as_tensor(e, device=self.device)
+        if e.is_complex():
+            e = e.real                                         # reference energies may carry a zero imaginary part (App. B-9)
+        e = e.to(torch.float64)
+        if e.dim() == 0:
+            e = e.expand(self.n_chains)
+        if e.shape != (self.n_chains,):
+            raise ValueError("energy callable must return one value per chain, shape (%d,), got %s; check "
+                             "callable_layout=%r" % (self.n_chains, tuple(e.shape), self._callable_layout))
+        return e.contiguous()
+
+    def _eval_callable(self, block):
+        return self._eval_term(self._callable, block)
+
+    # ------------------------------------------------------------------ time-series storage
+    def _ts_segments(self, n_rows):
+        """Reserve n_rows rows; yields (chunk tensor, first row in chunk, rows) per launch."""
+        out = []
+        while n_rows > 0:
+            if not self._ts_chunks or self._ts_chunks[-1][1] == self._ts_chunks[-1][0].shape[0]:
+                t = torch.empty((self._ts_chunk_rows, self._lay.TS_COLS, self.n_chains), dtype=torch.float64,
+                                device=self.device)
+                self._ts_chunks.append([t, 0])
+            t, used = self._ts_chunks[-1]
+            take = min(n_rows, t.shape[0] - used)
+            out.append((t, used, take))
+            self._ts_chunks[-1][1] = used + take
+            self._ts_rows += take
+            n_rows -= take
+        return out
+
+    # ------------------------------------------------------------------ the hot path
+    def run(self, n_measures, steps_per_measure):
+        """``n_measures x (steps_per_measure x step_all() + measure())`` — the README/demo loop
+        (README.md:39-44, demo/toymodel_xypotentialwell.py:39-44) in as few launches as possible."""
+        n_measures, steps_per_measure = int(n_measures), int(steps_per_measure)
+        if n_measures <= 0:
+            return
+        if self._callable is not None:
+            for _ in range(n_measures):
+                for _ in range(steps_per_measure):
+                    self._step_external()
+                self.measure()
+            return
+        if self.record:
+            for t, row0, rows in self._ts_segments(n_measures):
+                self._check(self._lib.me_run(self._h, rows, steps_per_measure, 1, _ptr(t), row0, self._stream()))
+        else:
+            self._check(self._lib.me_run(self._h, n_measures, steps_per_measure, 1, None, 0, self._stream()))
+        self._pool_count += n_measures * self.n_chains
+        self.step_counter += n_measures * steps_per_measure if self._kind == "complex" else 0
+
+    def step(self, k=1):
+        """``k`` calls of ``step_all()`` in one launch (no measure)."""
+        k = int(k)
+        if self._callable is not None:
+            for _ in range(k):
+                self._step_external()
+            return
+        self._check(self._lib.me_run(self._h, 1, k, 0, None, 0, self._stream()))
+        self.step_counter += k if self._kind == "complex" else 0
+
+    def step_all(self):
+        """One Metropolis step of every chain over all parameters (ME:241-259; for all-real / all-complex engines
+        the reference rebinds this to the group step, ME:46,56).  Returns the accept decision: a python bool for a
+        1-chain engine (as the reference), a bool tensor [n_chains] on the device otherwise."""
+        self.step(1)
+        if self.n_chains_total == 1:
+            return bool(self._last_accept.item())
+        return self._last_accept.bool()
+
+    def _step_external(self, inj_delta=None, inj_u=None):
+        prop = torch.empty((self._d, self.n_chains), dtype=torch.float64, device=self.device)
+        self._check(self._lib.me_propose(self._h, _ptr(prop), _ptr(inj_delta), self._stream()))
+        rej = None
+        if self.reject_condition is not None:
+            r, c = self._split(prop)
+            rej = torch.as_tensor(self.reject_condition(r, c), device=self.device)
+            rej = rej.to(torch.uint8).expand(self.n_chains).contiguous() if rej.dim() == 0 else rej.to(torch.uint8).contiguous()
+        e_new = self._eval_callable(prop)
+        self._check(self._lib.me_accept(self._h, _ptr(prop), _ptr(e_new), _ptr(rej), _ptr(inj_u), self._stream()))
+        self.step_counter += 1 if self._kind == "complex" else 0
+
+    def measure(self):
+        """Running means, covariance recursion, observable means and one time-series row (ME:342-427)."""
+        if self.record:
+            (t, row0, rows), = self._ts_segments(1)
+            self._check(self._lib.me_run(self._h, 1, 0, 1, _ptr(t), row0, self._stream()))
+        else:
+            self._check(self._lib.me_run(self._h, 1, 0, 1, None, 0, self._stream()))
+        self._pool_count += self.n_chains
+        if self._term_series is not None and self.record:
+            full = self.state[:self._d]
+            for tname, fn in self._terms["all"].items():
+                self._term_series.setdefault(tname, []).append(self._eval_term(fn, full).clone())
+
+    def run_injected(self, delta, u, n_measures, steps_per_measure, do_measure=True):
+        """Parity mode (strict engines): drive the schedule with recorded draws (SURVEY §8c level L-A).
+        ``delta``: [steps, D] or [steps, D, n_chains] increments in the order [real, Re c, Im c];
+        ``u``: [steps] or [steps, n_chains] accept uniforms, NaN where none was drawn."""
+        S = int(n_measures) * int(steps_per_measure)
+        delta = torch.as_tensor(np.asarray(delta, dtype=np.float64), device=self.device)
+        u = torch.as_tensor(np.asarray(u, dtype=np.float64), device=self.device)
+        if delta.dim() == 2:
+            delta = delta[:, :, None].expand(S, self._d, self.n_chains)
+        if u.dim() == 1:
+            u = u[:, None].expand(S, self.n_chains)
+        delta, u = delta.contiguous(), u.contiguous()
+        assert delta.shape == (S, self._d, self.n_chains) and u.shape == (S, self.n_chains)
+        if self._callable is not None:
+            s = 0
+            for _ in range(int(n_measures)):
+                for _ in range(int(steps_per_measure)):
+                    self._step_external(delta[s], u[s])
+                    s += 1
+                if do_measure:
+                    self.measure()
+            return
+        ts, row0 = None, 0
+        if self.record and do_measure:
+            segs = self._ts_segments(int(n_measures))
+            if len(segs) != 1:
+                raise RuntimeError("run_injected spans time-series chunks; use a smaller schedule")
+            ts, row0, _ = segs[0]
+        self._check(self._lib.me_run_injected(self._h, int(n_measures), int(steps_per_measure), int(bool(do_measure)),
+                                              _ptr(delta), _ptr(u), _ptr(ts), row0, self._stream()))
+        if do_measure:
+            self._pool_count += int(n_measures) * self.n_chains
+        self.step_counter += S if self._kind == "complex" else 0
+
+    # ------------------------------------------------------------------ counters
+    @property
+    def measure_step_counter(self):                                                        # ME:73
+        n, s = ctypes.c_int64(), ctypes.c_uint64()
+        self._lib.me_get_counters(self._h, ctypes.byref(n), ctypes.byref(s))
+        return n.value
+
+    @property
+    def steps_done(self):
+        n, s = ctypes.c_int64(), ctypes.c_uint64()
+        self._lib.me_get_counters(self._h, ctypes.byref(n), ctypes.byref(s))
+        return s.value
+
+    # ------------------------------------------------------------------ per-chain device views
+    def _rows(self, off, n):
+        return self.state[off:off + n]
+
+    @property
+    def real_params_per_chain(self):
+        return self._rows(self._lay.X, self.num_real_params).t()
+
+    @property
+    def complex_params_per_chain(self):
+        nr, nc = self.num_real_params, self.num_complex_params
+        return torch.complex(self._rows(nr, nc), self._rows(nr + nc, nc)).t()
+
+    @property
+    def energy_per_chain(self):
+        return self.state[self._lay.E]
+
+    @property
+    def real_group_sampling_width_per_chain(self):
+        return self.state[self._lay.SIG]
+
+    @property
+    def complex_group_sampling_width_per_chain(self):
+        return self.state[self._lay.SIG + 1]
+
+    @property
+    def sampling_width_per_chain(self):
+        return self.state[self._lay.SIG + (1 if self._kind == "complex" else 0)]
+
+    @property
+    def real_mean_per_chain(self):
+        return self._rows(self._lay.MEAN, self.num_real_params).t()
+
+    @property
+    def complex_mean_per_chain(self):
+        nr, nc = self.num_real_params, self.num_complex_params
+        m = self._lay.MEAN
+        return torch.complex(self._rows(m + nr, nc), self._rows(m + nr + nc, nc)).t()
+
+    @property
+    def observables_mean_per_chain(self):
+        return self._rows(self._lay.OBSM, 2 * self.num_real_params + self.num_complex_params).t()
+
+    def _unpack_sym(self, off):
+        nr = self.num_real_params
+        out = torch.zeros((self.n_chains, nr, nr), dtype=torch.float64, device=self.device)
+        for i in range(nr):
+            for j in range(i + 1):
+                v = self.state[off + i * (i + 1) // 2 + j]
+                out[:, i, j] = v
+                out[:, j, i] = v
+        return out
+
+    def _unpack_herm(self, off, lower_only=False):
+        nc = self.num_complex_params
+        out = torch.zeros((self.n_chains, nc, nc), dtype=torch.complex128, device=self.device)
+        dg = nc * (nc - 1)
+        for i in range(nc):
+            out[:, i, i] = self.state[off + dg + i].to(torch.complex128)
+            for j in range(i):
+                p = 2 * (i * (i - 1) // 2 + j)
+                v = torch.complex(self.state[off + p], self.state[off + p + 1])
+                out[:, i, j] = v
+                if not lower_only:
+                    out[:, j, i] = v.conj()
+        return out
+
+    @property
+    def covariance_matrix_real_per_chain(self):
+        return self._unpack_sym(self._lay.COVR)
+
+    @property
+    def covariance_matrix_complex_per_chain(self):
+        return self._unpack_herm(self._lay.COVC)
+
+    @property
+    def accept_count_per_chain(self):
+        return self.state[self._lay.NACC]
+
+    @property
+    def status_per_chain(self):
+        return self.state[self._lay.STATUS].to(torch.int32)
+
+    def check_status(self):
+        """Raise the exception the reference would have raised for a device-side fault."""
+        st = self.status_per_chain
+        bad = int(st.max().item()) if st.numel() else 0
+        if bad & _lib.STATUS_NOT_PSD:
+            raise ValueError("covariance is not symmetric positive-semidefinite.")           # numpy's message, ME:270
+        if bad & _lib.STATUS_SIGMA_NONPOS:
+            raise AssertionError("sampling_width > 0 violated")                              # ME:438
+        if bad & _lib.STATUS_ENERGY_NAN:
+            raise FloatingPointError("energy functor returned NaN")
+
+    # ------------------------------------------------------------------ pooled reads (reference attribute names)
+    def _pooled(self, t):
+        """Mean over all chains of the job of a per-chain tensor [n_chains, ...] -> numpy."""
+        s = t.sum(dim=0)
+        if self._distributed:
+            parallel.allreduce_sum_(s, self._group)
+        return (s / self.n_chains_total).cpu().numpy()
+
+    def _single(self):
+        return self.n_chains_total == 1
+
+    @property
+    def real_params(self):
+        if self._single():
+            return self.real_params_per_chain[0].cpu().numpy()
+        return self.real_params_per_chain
+
+    @property
+    def complex_params(self):
+        if self._single():
+            return self.complex_params_per_chain[0].cpu().numpy()
+        return self.complex_params_per_chain
+
+    @property
+    def real_mean(self):                                                                   # ME:77
+        return self._pooled(self.real_mean_per_chain)
+
+    @property
+    def complex_mean(self):                                                                # ME:78
+        return self._pooled(self.complex_mean_per_chain)
+
+    @property
+    def covariance_matrix_real(self):                                                      # ME:63-66
+        return self._pooled(self.covariance_matrix_real_per_chain) if self.num_real_params else None
+
+    @property
+    def covariance_matrix_complex(self):                                                   # ME:67-70
+        return self._pooled(self.covariance_matrix_complex_per_chain) if self.num_complex_params else None
+
+    @property
+    def observables_mean(self):                                                            # ME:80-81
+        return self._pooled(self.observables_mean_per_chain)
+
+    @property
+    def observables(self):                                                                 # ME:458-463
+        nr, nc = self.num_real_params, self.num_complex_params
+        x = self.state[:self._d]
+        obs = torch.cat([x[:nr].abs(), torch.hypot(x[nr:nr + nc], x[nr + nc:nr + 2 * nc]), x[:nr] * x[:nr]], dim=0)
+        return self._pooled(obs.t())
+
+    @property
+    def real_group_sampling_width(self):                                                   # ME:98
+        v = self._pooled(self.real_group_sampling_width_per_chain[:, None])[0]
+        return float(v)
+
+    @property
+    def complex_group_sampling_width(self):                                                # ME:99
+        return float(self._pooled(self.complex_group_sampling_width_per_chain[:, None])[0])
+
+    @property
+    def sampling_width(self):
+        """ME:97.  Only the mixed ``step_all`` adapts this attribute; all-real / all-complex engines adapt their
+        group width and leave it at its initial value."""
+        if self._kind == "mixed":
+            return self.real_group_sampling_width
+        return self._sampling_width0
+
+    @property
+    def energy_total(self):
+        """ME:125.  Live for mixed engines (ME:255); all-real / all-complex engines leave it at its initial value
+        and keep the live energy in ``energy``."""
+        src = self.state[self._lay.E] if self._kind == "mixed" else self._energy0
+        return float(self._pooled(src[:, None])[0])
+
+    @property
+    def energy(self):
+        """ME:152-156: dict of energy terms.  Single-callable engines have the one key ``"total"`` holding the live
+        energy; for dict-of-terms engines each term is re-evaluated on the current state."""
+        if self._terms is None:
+            return {"total": float(self._pooled(self.state[self._lay.E][:, None])[0])}
+        full = self.state[:self._d]
+        return {t: float(self._pooled(self._eval_term(fn, full)[:, None])[0]) for t, fn in self._terms["all"].items()}
+
+    @property
+    def acceptance_rate(self):
+        steps = self.steps_done
+        if steps == 0:
+            return float("nan")
+        return float(self._pooled(self.accept_count_per_chain[:, None])[0]) / steps
+
+    # ------------------------------------------------------------------ clean pooled ensemble statistics
+    def pooled_statistics(self):
+        """Ensemble mean / covariance / observable means over every (chain, measure) sample of the whole job,
+        from the in-kernel shifted moments; across ranks this is the path's one all-reduce."""
+        pw = self._lay.POOL_WORDS
+        if pw == 0:
+            raise NotImplementedError("parameter space too large for in-kernel pooled moments")
+        self._check(self._lib.me_pool_reduce(self._h, _ptr(self._pool_out), 1, self._stream()))
+        # running totals live on the host in f64; the all-reduce sums them across ranks
+        self._pool_sum[:pw] += self._pool_out[:pw].cpu().numpy()
+        tot = torch.tensor(np.concatenate([self._pool_sum[:pw], [float(self._pool_count)]]), dtype=torch.float64,
+                           device=self.device)
+        if self._distributed:
+            parallel.allreduce_sum_(tot, self._group)
+        tot = tot.cpu().numpy()
+        if tot[-1] < 2:
+            raise RuntimeError("pooled statistics need at least two measured samples")
+        return parallel.finalize_pooled(tot[:pw], tot[-1], self._shift_host, self.num_real_params,
+                                        self.num_complex_params)
+
+    def reset_pooled_statistics(self):
+        """Forget the pooled moments accumulated so far (e.g. after burn-in)."""
+        if self._lay.POOL_WORDS:
+            self._check(self._lib.me_pool_reduce(self._h, _ptr(self._pool_out), 1, self._stream()))
+        self._pool_sum[:] = 0.0
+        self._pool_count = 0
+
+    # ------------------------------------------------------------------ output (ME:466-479)
+    def time_series(self):
+        """All recorded rows as one tensor [rows, TS_COLS, n_chains] (columns: parameters in the order
+        [real, Re c, Im c], live energy, sampling width)."""
+        parts = [t[:used] for t, used in self._ts_chunks if used]
+        if not parts:
+            return torch.empty((0, self._lay.TS_COLS, self.n_chains), dtype=torch.float64, device=self.device)
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+
+    def save_time_series(self, chain=0):
+        """Build ``self.df`` for one chain with the reference's columns and order (ME:466-478): observables,
+        ``<term>_energy``, real parameters + ``real_group_sampling_width``, complex parameters +
+        ``complex_group_sampling_width``.  Derived columns (abs, squares) are recomputed from the stored
+        parameters.  Unlike the reference nothing is printed."""
+        import pandas
+        nr, nc, d = self.num_real_params, self.num_complex_params, self._d
+        parts = [t[:used, :, chain] for t, used in self._ts_chunks if used]
+        rows = (torch.cat(parts, dim=0) if parts else torch.empty((0, d + 2), dtype=torch.float64)).cpu().numpy()
+        x = rows[:, :nr]
+        c = rows[:, nr:nr + nc] + 1j * rows[:, nr + nc:d]
+        cols = {}
+        for i in range(nr):
+            cols[self.observables_names[i]] = np.abs(x[:, i])
+        for j in range(nc):
+            cols[self.observables_names[nr + j]] = np.abs(c[:, j])
+        for i in range(nr):
+            cols[self.observables_names[nr + nc + i]] = x[:, i] * x[:, i]
+        if self._terms is None:
+            cols["total_energy"] = rows[:, d]
+        else:
+            for tname in self._terms["all"]:
+                ser = self._term_series.get(tname, [])
+                cols[tname + "_energy"] = np.array([v[chain].item() for v in ser]) if ser else np.zeros(0)
+        if nr:
+            for i in range(nr):
+                cols[self.params_names[i]] = x[:, i]
+            cols["real_group_sampling_width"] = rows[:, d + 1]
+        if nc:
+            for j in range(nc):
+                cols[self.params_names[nr + j]] = c[:, j]
+            cols["complex_group_sampling_width"] = rows[:, d + 1]
+        self.df = pandas.DataFrame.from_dict(cols)
+        return self.df
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        n, s = ctypes.c_int64(), ctypes.c_uint64()
+        self._lib.me_get_counters(self._h, ctypes.byref(n), ctypes.byref(s))
+        return dict(state=self.state.clone(), n_measure=n.value, step=s.value, seed=self.seed,
+                    chain_offset=self.chain_offset, pool=None if self._pool is None else self._pool.clone(),
+                    pool_sum=self._pool_sum.copy(), pool_count=self._pool_count)
+
+    def load_state_dict(self, sd):
+        if sd["state"].shape != self.state.shape:
+            raise ValueError("checkpoint shape %s does not match engine %s" % (tuple(sd["state"].shape),
+                                                                             tuple(self.state.shape)))
+        self.state.copy_(sd["state"])
+        if self._pool is not None and sd.get("pool") is not None:
+            self._pool.copy_(sd["pool"])
+        self._pool_sum = np.array(sd["pool_sum"], dtype=np.float64)
+        self._pool_count = int(sd["pool_count"])
+        self._check(self._lib.me_set_counters(self._h, int(sd["n_measure"]), int(sd["step"])))

@@ -1,0 +1,81 @@
+"""Sharding of chains across ranks and the algebra of the pooled-statistics all-reduce.
+
+Chains are independent (the reference is a single chain; an ensemble is N replicas with different RNG
+sub-streams), so stepping needs no communication.  The only collective of the path is a sum all-reduce of the
+shifted raw moments ``[sum(x-s), sum (x-s)(x-s)^T, sum obs]`` (plus counts) at measure / reporting boundaries.
+Everything here is plain tensor code so that it can be exercised with the ``gloo`` backend on CPU.
+"""
+import numpy as np
+import torch
+
+
+def shard_range(n_total, rank, world_size):
+    """Contiguous global chain-id range [lo, hi) owned by ``rank``.  The Philox counter of a chain carries its
+    GLOBAL id, so results do not depend on ``world_size``."""
+    if n_total < world_size:
+        raise ValueError("fewer chains (%d) than ranks (%d)" % (n_total, world_size))
+    base, rem = divmod(n_total, world_size)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def allreduce_sum_(t, group=None):
+    """In-place sum all-reduce when a process group is up (NCCL for CUDA tensors, gloo for CPU); identity
+    otherwise."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def pool_words(n_real, n_complex):
+    d = n_real + 2 * n_complex
+    return d + d * (d + 1) // 2 + 2 * n_real + n_complex
+
+
+def pooled_moments_reference(samples, shift, n_real, n_complex):
+    """Moment vector in the kernel's layout, computed with numpy from explicit samples [N, D] (tests)."""
+    x = np.asarray(samples, dtype=np.float64)
+    d = n_real + 2 * n_complex
+    dx = x - np.asarray(shift)[None, :]
+    out = [dx.sum(0)]
+    il = np.tril_indices(d)
+    out.append((dx[:, il[0]] * dx[:, il[1]]).sum(0))
+    obs = [np.abs(x[:, :n_real]), np.hypot(x[:, n_real:n_real + n_complex], x[:, n_real + n_complex:]),
+           x[:, :n_real] ** 2]
+    out.append(np.concatenate(obs, axis=1).sum(0))
+    return np.concatenate(out)
+
+
+def finalize_pooled(sums, count, shift, n_real, n_complex):
+    """Pooled ensemble statistics from the all-reduced moment vector.
+
+    Returns dict(mean_real, mean_complex, cov_real, cov_complex, observables_mean, count); covariances are the
+    unbiased sample covariances over every (chain, measure) sample — the *clean* ensemble estimate, unlike the
+    reference's per-chain recursion which carries the sigma^2/n regulariser.
+    """
+    sums = np.asarray(sums, dtype=np.float64)
+    shift = np.asarray(shift, dtype=np.float64)
+    d = n_real + 2 * n_complex
+    n = float(count)
+    s1 = sums[:d]
+    il = np.tril_indices(d)
+    s2 = np.zeros((d, d))
+    s2[il] = sums[d:d + d * (d + 1) // 2]
+    s2 = s2 + np.tril(s2, -1).T
+    obs = sums[d + d * (d + 1) // 2:]
+    mean = shift + s1 / n
+    cov = (s2 - np.outer(s1, s1) / n) / max(n - 1.0, 1.0)
+    nr, nc = n_real, n_complex
+    re, im = slice(nr, nr + nc), slice(nr + nc, nr + 2 * nc)
+    cov_c = (cov[re, re] + cov[im, im]) + 1j * (cov[im, re] - cov[re, im])
+    return dict(mean_real=mean[:nr].copy(), mean_complex=mean[re] + 1j * mean[im], cov_real=cov[:nr, :nr].copy(),
+                cov_complex=cov_c, observables_mean=obs / n, count=int(count))

@@ -1,0 +1,161 @@
+"""Statistical parity of large CUDA ensembles (Philox + Cholesky proposals, throughput build) with
+(i) ensembles of the unmodified reference run as independent seeded processes (tests/golden/ensemble_*.npz,
+two-sample KS on per-chain end-of-run quantities and z-tests on their means) and (ii) exact facts about the
+stationary law exp(-E/T) (SURVEY §8c "pins available" (2)).  Tolerances are stated per assertion."""
+import numpy as np
+import pytest
+import torch
+from scipy import stats
+
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+KS_P = 1e-3        # two-sample KS rejection level per quantity (about 10 quantities per config)
+Z_MAX = 4.5        # z-test bound on the difference of means
+
+
+def _ks_and_z(gpu, ref, name):
+    gpu, ref = np.asarray(gpu, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    p = stats.ks_2samp(gpu, ref).pvalue
+    se = np.sqrt(gpu.var(ddof=1) / gpu.size + ref.var(ddof=1) / ref.size)
+    z = (gpu.mean() - ref.mean()) / se
+    assert p > KS_P, "%s: KS p=%.2e (gpu mean %.6g, ref mean %.6g)" % (name, p, gpu.mean(), ref.mean())
+    assert abs(z) < Z_MAX, "%s: z=%.2f (gpu mean %.6g, ref mean %.6g)" % (name, z, gpu.mean(), ref.mean())
+
+
+def _run_with_half_acceptance(eng, M, K):
+    eng.run(M // 2, K)
+    a0 = eng.accept_count_per_chain.clone()
+    eng.run(M - M // 2, K)
+    total = eng.accept_count_per_chain
+    half2 = (total - a0) / float((M - M // 2) * K)
+    return (total / float(M * K)).cpu().numpy(), half2.cpu().numpy()
+
+
+def test_c1_readme_ensemble_matches_reference_ensemble():
+    """C1: 1 real param, E = x^2, T = .01, 1000 x (1 step + measure) — reference ensemble M=512."""
+    import metropolisengine_b200 as me
+    ref = load_golden("ensemble_c1")
+    cols = {str(c): ref["rows"][:, i] for i, c in enumerate(ref["columns"])}
+    eng = me.MetropolisEngine("x2", initial_real_params=[0.0], temp=.01, n_chains=8192, seed=101, record=False)
+    acc_all, acc_half2 = _run_with_half_acceptance(eng, 1000, 1)
+    eng.check_status()
+    _ks_and_z(eng.sampling_width_per_chain.cpu().numpy(), cols["sigma"], "sigma")
+    _ks_and_z(acc_all, cols["acc_all"], "acceptance(all)")
+    _ks_and_z(acc_half2, cols["acc_half2"], "acceptance(2nd half)")
+    _ks_and_z(eng.real_params_per_chain[:, 0].cpu().numpy(), cols["x0"], "x")
+    _ks_and_z(eng.real_mean_per_chain[:, 0].cpu().numpy(), cols["mean0"], "real_mean")
+    _ks_and_z(eng.covariance_matrix_real_per_chain[:, 0, 0].cpu().numpy(), cols["cov00"], "covariance_matrix_real")
+    om = eng.observables_mean_per_chain.cpu().numpy()
+    _ks_and_z(om[:, 0], cols["obs_abs0"], "<|x|>")
+    _ks_and_z(om[:, 1], cols["obs_sq0"], "<x^2>")
+
+
+def test_c2_xy_well_ensemble_matches_reference_ensemble():
+    """C2: xy-well, T = .1, 1000 x (10 steps + measure) — reference ensemble M=256."""
+    import metropolisengine_b200 as me
+    ref = load_golden("ensemble_c2")
+    cols = {str(c): ref["rows"][:, i] for i, c in enumerate(ref["columns"])}
+    eng = me.MetropolisEngine(("xy_well", 1.0), initial_real_params=np.array([0., 0.]), temp=.1, n_chains=8192,
+                              seed=202, record=False)
+    acc_all, acc_half2 = _run_with_half_acceptance(eng, 1000, 10)
+    eng.check_status()
+    _ks_and_z(eng.sampling_width_per_chain.cpu().numpy(), cols["sigma"], "sigma")
+    _ks_and_z(acc_all, cols["acc_all"], "acceptance(all)")
+    _ks_and_z(acc_half2, cols["acc_half2"], "acceptance(2nd half)")
+    x = eng.real_params_per_chain.cpu().numpy()
+    _ks_and_z(x[:, 0], cols["x0"], "x0")
+    _ks_and_z(x[:, 1], cols["x1"], "x1")
+    m = eng.real_mean_per_chain.cpu().numpy()
+    _ks_and_z(m[:, 0], cols["mean0"], "mean0")
+    cv = eng.covariance_matrix_real_per_chain.cpu().numpy()
+    _ks_and_z(cv[:, 0, 0], cols["cov00"], "cov00")
+    _ks_and_z(cv[:, 1, 1], cols["cov11"], "cov11")
+    om = eng.observables_mean_per_chain.cpu().numpy()
+    _ks_and_z(om[:, 0], cols["obs_abs0"], "<|x0|>")
+    _ks_and_z(om[:, 3], cols["obs_sq1"], "<x1^2>")
+    # exact stationary facts: var = T/2 = 0.05 per coordinate, zero mean (z-test against the cross-chain spread)
+    assert abs(x[:, 0].mean()) < 4.5 * x[:, 0].std() / np.sqrt(x.shape[0])
+    assert abs(x[:, 0].var() - 0.05) < 4.5 * 0.05 * np.sqrt(2.0 / x.shape[0])
+    assert abs(np.corrcoef(x.T)[0, 1]) < 4.5 / np.sqrt(x.shape[0])
+
+
+def test_c3_mixed_ensemble_matches_reference_ensemble():
+    """C3: 3 real + 4 complex, per-chain adaptive covariance — reference ensemble M=96, 300 x (10 + measure)."""
+    import metropolisengine_b200 as me
+    ref = load_golden("ensemble_c3")
+    cols = {str(c): ref["rows"][:, i] for i, c in enumerate(ref["columns"])}
+    eng = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5), initial_real_params=np.zeros(3),
+                              initial_complex_params=np.zeros(4, dtype=complex), temp=.1, n_chains=4096, seed=303,
+                              record=False)
+    acc_all, acc_half2 = _run_with_half_acceptance(eng, 300, 10)
+    eng.check_status()
+    _ks_and_z(eng.sampling_width_per_chain.cpu().numpy(), cols["sigma"], "sigma")
+    _ks_and_z(acc_all, cols["acc_all"], "acceptance(all)")
+    _ks_and_z(acc_half2, cols["acc_half2"], "acceptance(2nd half)")
+    x = eng.real_params_per_chain.cpu().numpy()
+    m = eng.real_mean_per_chain.cpu().numpy()
+    cv = eng.covariance_matrix_real_per_chain.cpu().numpy()
+    for i in range(3):
+        _ks_and_z(x[:, i], cols["x%d" % i], "x%d" % i)
+        _ks_and_z(m[:, i], cols["mean%d" % i], "mean%d" % i)
+        _ks_and_z(cv[:, i, i], cols["cov%d%d" % (i, i)], "cov%d%d" % (i, i))
+    cabs = eng.complex_params_per_chain.abs().cpu().numpy()
+    cc = eng.covariance_matrix_complex_per_chain.cpu().numpy()
+    for j in range(4):
+        _ks_and_z(cabs[:, j], cols["absc%d" % j], "|c%d|" % j)
+        _ks_and_z(cc[:, j, j].real, cols["covc%d%d" % (j, j)], "covC%d%d" % (j, j))
+    om = eng.observables_mean_per_chain.cpu().numpy()
+    _ks_and_z(om[:, -1], cols["obs_sq2"], "<x2^2>")
+
+
+def test_full_size_c2_pooled_statistics_are_exact():
+    """BASELINE config 2 chain count (65,536 chains) through size-independent properties: pooled mean 0, pooled
+    variance T/2, zero correlation, <|x|> = sqrt(T/pi), acceptance -> target 0.3; and the pooled moments equal
+    the moments recomputed from the stored time series."""
+    import metropolisengine_b200 as me
+    n = 65536
+    eng = me.MetropolisEngine(("xy_well", 1.0), initial_real_params=np.array([0., 0.]), temp=.1, n_chains=n, seed=7,
+                              record=False)
+    eng.run(300, 10)                       # burn-in and sigma adaptation
+    eng.reset_pooled_statistics()
+    acc0 = eng.accept_count_per_chain.clone()
+    eng.record = True
+    eng.run(40, 10)
+    ps = eng.pooled_statistics()
+    N = ps["count"]
+    assert N == 40 * n
+    g_ineff = 8.0                          # statistical inefficiency of successive measures is < 8 (7.3 per step)
+    se = np.sqrt(0.05 * g_ineff / N)
+    assert np.all(np.abs(ps["mean_real"]) < 5 * se)
+    assert np.all(np.abs(np.diag(ps["cov_real"]) - 0.05) < 5 * 0.05 * np.sqrt(2 * g_ineff / N))
+    assert abs(ps["cov_real"][0, 1]) < 5 * 0.05 * np.sqrt(g_ineff / N)
+    assert np.all(np.abs(ps["observables_mean"][:2] - np.sqrt(0.1 / np.pi)) < 5 * 0.14 * np.sqrt(g_ineff / N))
+    acc = ((eng.accept_count_per_chain - acc0).sum() / (400.0 * n)).item()
+    assert abs(acc - 0.3) < 0.01
+    # pooled moments vs the stored rows
+    ts = eng.time_series()
+    assert ts.shape == (40, 4, n)
+    x = ts[:, :2, :].permute(0, 2, 1).reshape(-1, 2).cpu().numpy()
+    assert np.allclose(ps["mean_real"], x.mean(0), rtol=0, atol=1e-12)
+    assert np.allclose(ps["cov_real"], np.cov(x.T), rtol=1e-9, atol=1e-13)
+    assert np.allclose(ps["observables_mean"], np.concatenate([np.abs(x).mean(0), (x * x).mean(0)]), rtol=1e-10)
+
+
+def test_pooled_moments_mixed_shape_against_time_series():
+    import metropolisengine_b200 as me
+    n = 2048
+    eng = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5), initial_real_params=np.zeros(3),
+                              initial_complex_params=np.zeros(4, dtype=complex), temp=.1, n_chains=n, seed=5)
+    eng.run(60, 5)
+    ps = eng.pooled_statistics()
+    ts = eng.time_series().cpu().numpy()
+    x = np.transpose(ts[:, :11, :], (0, 2, 1)).reshape(-1, 11)
+    assert np.allclose(ps["mean_real"], x[:, :3].mean(0), atol=1e-12)
+    assert np.allclose(ps["cov_real"], np.cov(x[:, :3].T), rtol=1e-9, atol=1e-13)
+    c = x[:, 3:7] + 1j * x[:, 7:11]
+    cm = c - c.mean(0)
+    cov_c = cm.T @ cm.conj() / (c.shape[0] - 1)
+    assert np.allclose(ps["cov_complex"], cov_c, rtol=1e-9, atol=1e-12)
+    assert np.allclose(ps["observables_mean"][3:7], np.abs(c).mean(0), rtol=1e-10)

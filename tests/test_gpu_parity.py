@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the Python facade) against the oracle.
+
+Level L-A: a single strict chain driven by the reference's own recorded draws must reproduce the
+reference chain's accept/reject decisions exactly and its state within 1e-12 relative (FP64).
+Philox level: a throughput-mode ensemble must match the C oracle running the same Philox streams chain by chain.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import load_golden
+from tests.golden.cases import cases, fresh_ctor
+
+pytestmark = pytest.mark.gpu
+
+CASES = cases()
+RTOL = 1e-12          # north_star: parameters within 1e-12 relative (FP64)
+
+USER_SOURCES = {
+    # E = (|c0|^2 - 1)^2 + |c1 - c0|^2      (tests/golden/cases.py::_pure_2c)
+    "pure_2c": """
+__device__ double me_user_energy(const double* x, const double* cr, const double* ci, const double* k) {
+    const double a = cr[0] * cr[0] + ci[0] * ci[0];
+    const double dr = cr[1] - cr[0], di = ci[1] - ci[0];
+    return (a - 1.0) * (a - 1.0) + (dr * dr + di * di);
+}
+""",
+    # E = sum (1-r_i)^2 + r0 r1 mean_j(-|c_j|^2 + .5 |c_j|^4)   (tests/golden/cases.py::_warm_3r2c)
+    "warm_3r2c": """
+__device__ double me_user_energy(const double* x, const double* cr, const double* ci, const double* k) {
+    double area = 0.0, s = 0.0;
+    for (int i = 0; i < ME_NR; i++) { const double e = 1.0 - x[i]; area += e * e; }
+    for (int j = 0; j < ME_NC; j++) { const double a = cr[j] * cr[j] + ci[j] * ci[j]; s += -1.0 * a + .5 * (a * a); }
+    return area + x[0] * x[1] * (s / ME_NC);
+}
+""",
+}
+
+
+def close(a, b, rtol=RTOL):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.max(np.abs(b)) if b.size else 1.0
+    return bool(np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), scale)))
+
+
+def make_engine(name, me, **extra):
+    case, g = CASES[name], load_golden(name)
+    ctor = fresh_ctor(case)
+    if case["builtin"] is not None:
+        bname, consts = case["builtin"]
+        energy = me.BuiltinEnergy(bname, *consts, reject=("reject" in case))
+    elif name in USER_SOURCES:
+        energy = me.CudaEnergy(USER_SOURCES[name])
+    else:
+        raise KeyError(name)
+    return me.MetropolisEngine(energy, **ctor, **extra), g
+
+
+def drive_injected_and_compare(eng, g):
+    M, K = int(g["n_measures"]), int(g["steps_per_measure"])
+    n_r, n_c = int(g["n_r"]), int(g["n_c"])
+    nacc = 0
+    for im in range(M):
+        sl = slice(im * K, (im + 1) * K)
+        eng.run_injected(g["delta"][sl], g["u"][sl], 1, K)
+        nacc += int(g["accept"][sl].sum())
+        assert int(eng.accept_count_per_chain.item()) == nacc, "accept/reject decisions differ in block %d" % im
+        last = g["step_x"][(im + 1) * K - 1]
+        if n_r:
+            assert close(eng.real_params, last[:n_r]), im
+            assert close(eng.real_group_sampling_width, g["m_sigma_r"][im]), im
+            assert close(eng.real_mean, g["m_real_mean"][im]), im
+            assert close(eng.covariance_matrix_real, g["m_cov_r"][im]), im
+        if n_c:
+            assert close(eng.complex_params, last[n_r:n_r + n_c] + 1j * last[n_r + n_c:]), im
+            assert close(eng.complex_group_sampling_width, g["m_sigma_c"][im]), im
+            assert close(eng.complex_mean, g["m_complex_mean"][im]), im
+            assert close(eng.covariance_matrix_complex, g["m_cov_c"][im]), im
+        assert close(eng.observables_mean, g["m_obs_mean"][im]), im
+        assert close(eng.energy["total"], g["m_energy"][im], 1e-11), im
+    assert eng.measure_step_counter == int(g["measure_step_counter"])
+    eng.check_status()
+
+
+@pytest.mark.parametrize("name", ["kat1_x2", "kat2_xy", "kat3_2r1c", "c3_3r4c", "cyl_1r8c_reject", "xy_temp0"])
+def test_injected_parity_builtin(name):
+    import metropolisengine_b200 as me
+    eng, g = make_engine(name, me, strict=True)
+    drive_injected_and_compare(eng, g)
+
+
+@pytest.mark.parametrize("name", ["pure_2c", "warm_3r2c"])
+def test_injected_parity_user_functor_nvrtc(name):
+    """User CUDA functors compiled at run time (NVRTC, --fmad=false) and fused into the step kernel."""
+    import metropolisengine_b200 as me
+    eng, g = make_engine(name, me, strict=True)
+    drive_injected_and_compare(eng, g)
+
+
+def test_injected_parity_whole_schedule_single_launch():
+    """The whole KAT2 schedule (1000 x (10 steps + measure)) in ONE launch reproduces the reference's final
+    values of SURVEY §4 KAT2."""
+    import metropolisengine_b200 as me
+    eng, g = make_engine("kat2_xy", me, strict=True)
+    eng.run_injected(g["delta"], g["u"], 1000, 10)
+    assert int(eng.accept_count_per_chain.item()) == 3167
+    assert close(eng.real_params, [0.2477655113830379, -0.0020188999856143724])
+    assert close(eng.real_group_sampling_width, 0.6737107772882164)
+    assert close(eng.real_mean, [-0.002096715114169222, 0.004685569814294245])
+    assert close(eng.covariance_matrix_real[0, 0], 0.479512502307138)
+    assert eng.sampling_width == 0.05            # all-real engines never adapt this attribute (App. B-1)
+    # time series rows equal the per-measure snapshots
+    ts = eng.time_series().cpu().numpy()[:, :, 0]
+    assert ts.shape == (1000, 4)
+    assert close(ts[:, :2], g["m_x"])
+    assert close(ts[:, 3], g["m_sigma_r"])
+
+
+def test_kat1_readme_loop_with_python_level_calls():
+    """README.md:39-44 driven call by call: step_all() returns the reference's decisions (python bools)."""
+    import metropolisengine_b200 as me
+    eng, g = make_engine("kat1_x2", me, strict=True)
+    decisions = []
+    for s in range(200):
+        eng.run_injected(g["delta"][s:s + 1], g["u"][s:s + 1], 1, 1, do_measure=False)
+        decisions.append(bool(eng._last_accept.item()))
+        eng.measure()
+    assert decisions == [bool(a) for a in g["accept"][:200]]
+    assert close(eng.real_mean, g["m_real_mean"][199])
+    assert close(eng.observables_mean, g["m_obs_mean"][199])
+
+
+def test_torch_callable_injected_parity_dict_terms():
+    """Dict-of-terms energy (ME:111-115, demo/toymodel_complex_and_real.py:33-35) as torch callables on the
+    unfused propose / callable / accept path, draw-injected against the reference."""
+    import metropolisengine_b200 as me
+    g = load_golden("dict_2r1c")
+    k, al, be = 1.0, -1.0, 0.5
+    area = lambda r, c: k * (1 - r[0]) ** 2 + k * (1 - r[1]) ** 2
+    field = lambda r, c: r[0] * r[1] * (al * (c[0] * c[0].conj()).real + be * (c[0] * c[0].conj()).real ** 2)
+    terms = {"complex": {"field": field}, "real": {"field": field, "area": area},
+             "all": {"field": field, "area": area}}
+    eng = me.MetropolisEngine(terms, initial_real_params=np.array([0.2, 0.1]),
+                              initial_complex_params=np.array([0.5 + 0j]), temp=.1, strict=True,
+                              callable_layout="params_first")
+    M, K = int(g["n_measures"]), int(g["steps_per_measure"])
+    eng.run_injected(g["delta"], g["u"], M, K)
+    assert int(eng.accept_count_per_chain.item()) == int(g["accept"].sum())
+    assert close(eng.real_params, g["step_x"][-1][:2], 1e-11)
+    assert close(eng.sampling_width, g["m_sigma"][-1], 1e-11)
+    assert close(eng.covariance_matrix_real, g["m_cov_r"][-1], 1e-10)
+    assert close(eng.covariance_matrix_complex, g["m_cov_c"][-1], 1e-10)
+    df = eng.save_time_series()
+    assert list(df.columns) == [str(c) for c in g["df_columns"]]
+
+
+def test_readme_example_with_torch_callable():
+    """README.md:23-58 with the energy as a python callable (params_first layout lets the reference-style body
+    vectorise unchanged); checks the reference's read API."""
+    import metropolisengine_b200 as me
+    eng = me.MetropolisEngine(lambda real_params, complex_params: real_params[0] ** 2, initial_real_params=[0.0],
+                              temp=.01, callable_layout="params_first", seed=1)
+    n_acc = 0
+    for i in range(300):
+        a = eng.step_all()
+        assert isinstance(a, bool)
+        n_acc += a
+        eng.measure()
+    assert 60 < n_acc < 260
+    assert eng.real_mean.shape == (1,) and eng.covariance_matrix_real.shape == (1, 1)
+    names = list(zip(eng.observables_names, eng.observables_mean))
+    assert [n for n, _ in names] == ["abs_param_0", "param_0_squared"]
+    eng.save_time_series()
+    assert list(eng.df.columns) == ["abs_param_0", "param_0_squared", "total_energy", "param_0",
+                                    "real_group_sampling_width"]
+    assert len(eng.df) == 300
+
+
+# ---------------------------------------------------------------------------------------------- Philox level
+PHILOX_CASES = [
+    ("x2", 1, 0, [], dict(temp=.01), 40, 1),
+    ("xy_well", 2, 0, [1.0], dict(temp=.1), 70, 10),
+    ("mixed_well", 2, 1, [1.0, -1.0, 0.5], dict(temp=.1), 70, 5),
+    ("mixed_well", 3, 4, [1.0, -1.0, 0.5], dict(temp=.1), 70, 5),
+    ("cylinder", 1, 8, [10.0, -1.0, 0.05, 1.0], dict(temp=.1, sampling_width=0.2), 60, 4),
+]
+
+
+@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("bname,n_r,n_c,consts,kw,M,K", PHILOX_CASES)
+def test_philox_ensemble_matches_c_oracle_chain_by_chain(bname, n_r, n_c, consts, kw, M, K, strict):
+    """Same Philox key/counter definition on both sides: every chain of the CUDA ensemble follows the oracle's
+    chain (crosses n > 50, so the in-kernel Cholesky refactorisation is exercised)."""
+    import metropolisengine_b200 as me
+    from oracle import c_oracle as co
+    n = 96
+    x0r = np.full(n_r, 0.3) if bname == "cylinder" else np.zeros(n_r)
+    x0c = np.zeros(n_c, dtype=complex)
+    eng = me.MetropolisEngine(me.BuiltinEnergy(bname, *consts, reject=(bname == "cylinder")),
+                              initial_real_params=x0r if n_r else None,
+                              initial_complex_params=x0c if n_c else None, n_chains=n, seed=1234, strict=strict, **kw)
+    eng.run(M, K)
+    eng.check_status()
+    st = eng.state.cpu().numpy()
+    lay = eng._lay
+    tol = 2e-10 if strict else 2e-9
+    for ch in (0, 1, 31, 32, 95):
+        o = co.CChain(n_r, n_c, bname, consts=consts, temp=kw["temp"], sampling_width=kw.get("sampling_width", 0.05),
+                      x0=np.concatenate([x0r, x0c.real, x0c.imag]), use_reject=(bname == "cylinder"))
+        acc, _ = o.run(M, K, True, seed=1234, chain_id=ch)
+        assert st[lay.NACC, ch] == acc.sum(), (ch, st[lay.NACC, ch], acc.sum())
+        assert close(st[:lay.WORDS - 2, ch], o.state[:lay.WORDS - 2], tol), ch
+
+
+def test_results_do_not_depend_on_sharding():
+    """Philox counters carry GLOBAL chain ids: one 96-chain engine == two engines owning [0,40) and [40,96)."""
+    import metropolisengine_b200 as me
+    kw = dict(initial_real_params=np.array([0., 0., 0.]), initial_complex_params=np.zeros(4, dtype=complex), temp=.1,
+              seed=9)
+    e_all = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5), n_chains=96, **kw)
+    e_all.run(60, 4)
+    parts = []
+    for lo, hi in ((0, 40), (40, 96)):
+        e = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5), n_chains=96, _shard=(lo, hi), **kw)
+        e.run(60, 4)
+        parts.append(e.state)
+    assert torch.equal(torch.cat(parts, dim=1), e_all.state)
+
+
+def test_checkpoint_resume_is_bit_identical():
+    import metropolisengine_b200 as me
+    kw = dict(initial_real_params=np.array([0., 0.]), temp=.1, n_chains=256, seed=3)
+    a = me.MetropolisEngine(("xy_well", 1.0), **kw)
+    a.run(30, 7)
+    sd = a.state_dict()
+    a.run(40, 7)
+    b = me.MetropolisEngine(("xy_well", 1.0), **kw)
+    b.load_state_dict(sd)
+    b.run(40, 7)
+    assert torch.equal(a.state, b.state)
+
+
+def test_single_steps_equal_fused_run():
+    """1000 python-level step_all()/measure() calls == one fused launch (same Philox counters)."""
+    import metropolisengine_b200 as me
+    kw = dict(initial_real_params=np.array([0., 0.]), temp=.1, n_chains=64, seed=3)
+    a = me.MetropolisEngine(("xy_well", 1.0), **kw)
+    for _ in range(60):
+        for _ in range(3):
+            acc = a.step_all()
+        a.measure()
+    assert acc.dtype == torch.bool and acc.shape == (64,)
+    b = me.MetropolisEngine(("xy_well", 1.0), **kw)
+    b.run(60, 3)
+    assert torch.equal(a.state, b.state)
+    assert torch.equal(a.time_series(), b.time_series())
+
+
+def test_external_callable_matches_fused_functor():
+    """The unfused propose / torch-callable / accept path consumes the same Philox slots as the fused kernel."""
+    import metropolisengine_b200 as me
+    kw = dict(initial_real_params=np.array([0., 0.]), temp=.1, n_chains=128, seed=21)
+    a = me.MetropolisEngine(("xy_well", 1.0), **kw)
+    a.run(55, 3)
+    b = me.MetropolisEngine(lambda r, c: 1.0 * (r[:, 0] * r[:, 0] + r[:, 1] * r[:, 1]), **kw)
+    b.run(55, 3)
+    assert torch.equal(a.accept_count_per_chain, b.accept_count_per_chain)
+    assert torch.allclose(a.state, b.state, rtol=1e-11, atol=1e-13)
+
+
+def test_status_flags_surface_as_reference_exceptions():
+    import metropolisengine_b200 as me
+    eng = me.MetropolisEngine(me.CudaEnergy("""
+__device__ double me_user_energy(const double* x, const double* cr, const double* ci, const double* k) {
+    return x[0] > 0.2 ? nan("") : x[0] * x[0];
+}"""), initial_real_params=[0.0], temp=1.0, n_chains=64, sampling_width=0.5)
+    eng.run(5, 20)
+    with pytest.raises(FloatingPointError):
+        eng.check_status()
+    with pytest.raises(ValueError):
+        me.MetropolisEngine("x2", temp=.1)                          # ME:37-39
+    with pytest.raises(AssertionError):
+        me.MetropolisEngine("x2", initial_real_params=[0.0], temp=-1)   # ME:92
+    with pytest.raises(_me_error()):
+        me.MetropolisEngine(me.CudaEnergy("this is not CUDA"), initial_real_params=[0.0], temp=.1)
+
+
+def _me_error():
+    from metropolisengine_b200._lib import MeError
+    return MeError
