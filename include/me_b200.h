@@ -169,6 +169,11 @@ int me_pool_reduce(me_engine *eng, double *out, int32_t reset, void *stream);
 int me_get_counters(me_engine *eng, int64_t *n_measure, uint64_t *step);
 int me_set_counters(me_engine *eng, int64_t n_measure, uint64_t step);
 
+/* Measurement aid (no reference counterpart): FP64 FMA throughput probe used as the roofline denominator of the
+ * step kernels.  Launches n_sm*8 CTAs of 256 threads, 8 independent FMA streams each, `iters` iterations;
+ * out needs n_sm*8*256 doubles; *flops receives the flop count of the launch.  Time it with CUDA events. */
+int me_probe_fp64(int32_t device, int64_t iters, double *out, int64_t out_len, void *stream, int64_t *flops);
+
 const char *me_last_error(me_engine *eng);   /* eng may be NULL: error of the last failing me_create */
 
 #ifdef __cplusplus

@@ -58,6 +58,7 @@ SIGNATURES = {
     "me_pool_reduce": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "me_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
     "me_set_counters": (ctypes.c_int, [_vp, _i64, _u64]),
+    "me_probe_fp64": (ctypes.c_int, [_i32, _i64, _vp, _i64, _vp, ctypes.POINTER(_i64)]),
     "me_last_error": (_cp, [_vp]),
 }
 

@@ -332,6 +332,18 @@ __global__ void k_pool_reduce(double *pool, double *out, int grid, int words, in
     out[w] = t;
 }
 
+/* FP64 FMA throughput probe: 8 independent dependent-FMA streams per thread.  The roofline denominator of the
+ * step kernels (MEASURED_PEAKS.json carries HBM and bf16 figures only). */
+__global__ void __launch_bounds__(256) k_probe_fp64(double *out, long long iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.99999988, c = 1.25e-7;
+    for (long long i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 }  // namespace
 
 /* ========================================================================================= C ABI */
@@ -538,6 +550,22 @@ int me_set_counters(me_engine *e, int64_t n_measure, uint64_t step) {
     if (!e || n_measure < 1) return ME_ERR_INVALID;
     e->n_measure = n_measure;
     e->step = step;
+    return ME_OK;
+}
+
+int me_probe_fp64(int32_t device, int64_t iters, double *out, int64_t out_len, void *stream, int64_t *flops) {
+    if (!out || iters <= 0) return ME_ERR_INVALID;
+    int n_sm = 0;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+        cudaGetLastError();
+        return ME_ERR_CUDA;
+    }
+    const int block = 256, grid = n_sm * 8;
+    if (out_len < (int64_t)grid * block) return ME_ERR_INVALID;
+    DeviceGuard g(device);
+    k_probe_fp64<<<grid, block, 0, (cudaStream_t)stream>>>(out, iters);
+    if (cudaGetLastError() != cudaSuccess) return ME_ERR_CUDA;
+    if (flops) *flops = (int64_t)grid * block * iters * 8 * 2;
     return ME_OK;
 }
 

@@ -102,6 +102,7 @@ class MetropolisEngine:
         if not torch.cuda.is_available():
             raise RuntimeError("MetropolisEngine needs a CUDA device: the hot path is CUDA-only (no CPU fallback)")
         self._lib = _lib.load()
+        self.launch_count = 0
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -204,7 +205,7 @@ class MetropolisEngine:
         if self._callable is not None:
             full = x0_dev if per_chain_init else x0_dev[:, None].expand(self._d, self.n_chains).contiguous()
             e0 = self._eval_callable(full)
-        self._check(self._lib.me_init(self._h, _ptr(x0_dev), 0 if per_chain_init else 1, self._sampling_width0,
+        self._launch(self._lib.me_init(self._h, _ptr(x0_dev), 0 if per_chain_init else 1, self._sampling_width0,
                                       _ptr(cov_r), _ptr(cov_c_re), _ptr(cov_c_im), _ptr(e0), self._stream()))
         self._energy0 = self.state[self._lay.E].clone()
         self._term_energy0 = None
@@ -219,7 +220,7 @@ class MetropolisEngine:
         self.record = bool(record)
         self._ts_chunks = []          # list of [tensor (rows, TS_COLS, n_chains), used_rows]
         self._ts_rows = 0
-        self._ts_chunk_rows = max(1, min(1 << 16, int(ts_chunk_bytes) // (self._lay.TS_COLS * self.n_chains * 8)))
+        self._ts_chunk_rows = max(1, int(ts_chunk_bytes) // (self._lay.TS_COLS * self.n_chains * 8))
         self._term_series = {} if self._terms is not None else None
 
     # ------------------------------------------------------------------ plumbing
@@ -228,6 +229,11 @@ class MetropolisEngine:
 
     def _check(self, rc):
         _lib.check(self._h, rc)
+
+    def _launch(self, rc):
+        """Bookkeeping for calls that launch one of the library's kernels."""
+        _lib.check(self._h, rc)
+        self.launch_count += 1
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -303,20 +309,70 @@ class MetropolisEngine:
 
     # ------------------------------------------------------------------ time-series storage
     def _ts_segments(self, n_rows):
-        """Reserve n_rows rows; yields (chunk tensor, first row in chunk, rows) per launch."""
+        """Reserve n_rows rows; returns (chunk tensor, first row in chunk, rows) per launch."""
         out = []
-        while n_rows > 0:
-            if not self._ts_chunks or self._ts_chunks[-1][1] == self._ts_chunks[-1][0].shape[0]:
-                t = torch.empty((self._ts_chunk_rows, self._lay.TS_COLS, self.n_chains), dtype=torch.float64,
-                                device=self.device)
-                self._ts_chunks.append([t, 0])
-            t, used = self._ts_chunks[-1]
+        for c in self._ts_chunks:
+            if n_rows <= 0:
+                break
+            t, used = c
             take = min(n_rows, t.shape[0] - used)
-            out.append((t, used, take))
-            self._ts_chunks[-1][1] = used + take
+            if take > 0:
+                out.append((t, used, take))
+                c[1] = used + take
+                self._ts_rows += take
+                n_rows -= take
+        while n_rows > 0:
+            t = torch.empty((self._ts_chunk_rows, self._lay.TS_COLS, self.n_chains), dtype=torch.float64,
+                            device=self.device)
+            take = min(n_rows, t.shape[0])
+            self._ts_chunks.append([t, take])
+            out.append((t, 0, take))
             self._ts_rows += take
             n_rows -= take
         return out
+
+    def reserve_rows(self, n_rows):
+        """Pre-allocate time-series storage for n_rows further measures (keeps cudaMalloc out of the run)."""
+        have = sum(t.shape[0] - used for t, used in self._ts_chunks)
+        while have < n_rows:
+            rows = min(self._ts_chunk_rows, n_rows - have) if not self._ts_chunks else self._ts_chunk_rows
+            rows = max(rows, 1)
+            t = torch.empty((rows, self._lay.TS_COLS, self.n_chains), dtype=torch.float64, device=self.device)
+            self._ts_chunks.append([t, 0])
+            have += rows
+
+    def clear_time_series(self, keep_storage=True):
+        """Forget recorded rows (optionally keeping the allocated storage for reuse)."""
+        if keep_storage:
+            for c in self._ts_chunks:
+                c[1] = 0
+        else:
+            self._ts_chunks = []
+        self._ts_rows = 0
+        if self._term_series is not None:
+            self._term_series = {}
+
+    def reset(self, initial_real_params=None, initial_complex_params=None, sampling_width=None):
+        """Re-initialise every chain (ME:40-125) from host or device arrays without rebuilding the engine:
+        parameters [n_chains, n] (or [n] broadcast), means, identity covariances, widths, counters."""
+        nr, nc, d = self.num_real_params, self.num_complex_params, self._d
+        x0 = torch.empty((d, self.n_chains), dtype=torch.float64, device=self.device)
+        if nr:
+            r = torch.as_tensor(initial_real_params, dtype=torch.float64)
+            r = r.to(self.device, non_blocking=True)
+            x0[:nr] = r.t() if r.dim() == 2 else r[:, None]
+        if nc:
+            c = torch.as_tensor(initial_complex_params, dtype=torch.complex128)
+            c = c.to(self.device, non_blocking=True)
+            x0[nr:nr + nc] = c.real.t() if c.dim() == 2 else c.real[:, None]
+            x0[nr + nc:] = c.imag.t() if c.dim() == 2 else c.imag[:, None]
+        e0 = self._eval_callable(x0) if self._callable is not None else None
+        sw = self._sampling_width0 if sampling_width is None else float(sampling_width)
+        self._launch(self._lib.me_init(self._h, _ptr(x0), 0, sw, None, None, None, _ptr(e0), self._stream()))
+        self._energy0 = self.state[self._lay.E].clone()
+        self.reset_pooled_statistics()
+        self.clear_time_series()
+        self.step_counter = 1
 
     # ------------------------------------------------------------------ the hot path
     def run(self, n_measures, steps_per_measure):
@@ -333,9 +389,9 @@ class MetropolisEngine:
             return
         if self.record:
             for t, row0, rows in self._ts_segments(n_measures):
-                self._check(self._lib.me_run(self._h, rows, steps_per_measure, 1, _ptr(t), row0, self._stream()))
+                self._launch(self._lib.me_run(self._h, rows, steps_per_measure, 1, _ptr(t), row0, self._stream()))
         else:
-            self._check(self._lib.me_run(self._h, n_measures, steps_per_measure, 1, None, 0, self._stream()))
+            self._launch(self._lib.me_run(self._h, n_measures, steps_per_measure, 1, None, 0, self._stream()))
         self._pool_count += n_measures * self.n_chains
         self.step_counter += n_measures * steps_per_measure if self._kind == "complex" else 0
 
@@ -346,7 +402,7 @@ class MetropolisEngine:
             for _ in range(k):
                 self._step_external()
             return
-        self._check(self._lib.me_run(self._h, 1, k, 0, None, 0, self._stream()))
+        self._launch(self._lib.me_run(self._h, 1, k, 0, None, 0, self._stream()))
         self.step_counter += k if self._kind == "complex" else 0
 
     def step_all(self):
@@ -360,23 +416,23 @@ class MetropolisEngine:
 
     def _step_external(self, inj_delta=None, inj_u=None):
         prop = torch.empty((self._d, self.n_chains), dtype=torch.float64, device=self.device)
-        self._check(self._lib.me_propose(self._h, _ptr(prop), _ptr(inj_delta), self._stream()))
+        self._launch(self._lib.me_propose(self._h, _ptr(prop), _ptr(inj_delta), self._stream()))
         rej = None
         if self.reject_condition is not None:
             r, c = self._split(prop)
             rej = torch.as_tensor(self.reject_condition(r, c), device=self.device)
             rej = rej.to(torch.uint8).expand(self.n_chains).contiguous() if rej.dim() == 0 else rej.to(torch.uint8).contiguous()
         e_new = self._eval_callable(prop)
-        self._check(self._lib.me_accept(self._h, _ptr(prop), _ptr(e_new), _ptr(rej), _ptr(inj_u), self._stream()))
+        self._launch(self._lib.me_accept(self._h, _ptr(prop), _ptr(e_new), _ptr(rej), _ptr(inj_u), self._stream()))
         self.step_counter += 1 if self._kind == "complex" else 0
 
     def measure(self):
         """Running means, covariance recursion, observable means and one time-series row (ME:342-427)."""
         if self.record:
             (t, row0, rows), = self._ts_segments(1)
-            self._check(self._lib.me_run(self._h, 1, 0, 1, _ptr(t), row0, self._stream()))
+            self._launch(self._lib.me_run(self._h, 1, 0, 1, _ptr(t), row0, self._stream()))
         else:
-            self._check(self._lib.me_run(self._h, 1, 0, 1, None, 0, self._stream()))
+            self._launch(self._lib.me_run(self._h, 1, 0, 1, None, 0, self._stream()))
         self._pool_count += self.n_chains
         if self._term_series is not None and self.record:
             full = self.state[:self._d]
@@ -411,7 +467,7 @@ class MetropolisEngine:
             if len(segs) != 1:
                 raise RuntimeError("run_injected spans time-series chunks; use a smaller schedule")
             ts, row0, _ = segs[0]
-        self._check(self._lib.me_run_injected(self._h, int(n_measures), int(steps_per_measure), int(bool(do_measure)),
+        self._launch(self._lib.me_run_injected(self._h, int(n_measures), int(steps_per_measure), int(bool(do_measure)),
                                               _ptr(delta), _ptr(u), _ptr(ts), row0, self._stream()))
         if do_measure:
             self._pool_count += int(n_measures) * self.n_chains
@@ -621,7 +677,7 @@ class MetropolisEngine:
         pw = self._lay.POOL_WORDS
         if pw == 0:
             raise NotImplementedError("parameter space too large for in-kernel pooled moments")
-        self._check(self._lib.me_pool_reduce(self._h, _ptr(self._pool_out), 1, self._stream()))
+        self._launch(self._lib.me_pool_reduce(self._h, _ptr(self._pool_out), 1, self._stream()))
         # running totals live on the host in f64; the all-reduce sums them across ranks
         self._pool_sum[:pw] += self._pool_out[:pw].cpu().numpy()
         tot = torch.tensor(np.concatenate([self._pool_sum[:pw], [float(self._pool_count)]]), dtype=torch.float64,
@@ -637,7 +693,7 @@ class MetropolisEngine:
     def reset_pooled_statistics(self):
         """Forget the pooled moments accumulated so far (e.g. after burn-in)."""
         if self._lay.POOL_WORDS:
-            self._check(self._lib.me_pool_reduce(self._h, _ptr(self._pool_out), 1, self._stream()))
+            self._launch(self._lib.me_pool_reduce(self._h, _ptr(self._pool_out), 1, self._stream()))
         self._pool_sum[:] = 0.0
         self._pool_count = 0
 

@@ -151,7 +151,13 @@ def test_torch_callable_injected_parity_dict_terms():
     assert close(eng.covariance_matrix_real, g["m_cov_r"][-1], 1e-10)
     assert close(eng.covariance_matrix_complex, g["m_cov_c"][-1], 1e-10)
     df = eng.save_time_series()
-    assert list(df.columns) == [str(c) for c in g["df_columns"]]
+    want = [str(c) for c in g["df_columns"]]
+    # the reference iterates a *set* of term names (ME:113-115,153-155), so the order of the <term>_energy
+    # columns depends on PYTHONHASHSEED; everything else is ordered
+    got = list(df.columns)
+    assert [c for c in got if not c.endswith("_energy")] == [c for c in want if not c.endswith("_energy")]
+    assert sorted(got) == sorted(want)
+    assert got.index("field_energy") in (4, 5) and len(df) == M
 
 
 def test_readme_example_with_torch_callable():
