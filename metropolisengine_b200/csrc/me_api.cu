@@ -157,10 +157,11 @@ int nvrtc_compile(int n_real, int n_complex, int energy_id, const std::string &u
            "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_init(const __grid_constant__ MeParams p) { me::init_body<UserCfg>(p); }\n"
            "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_propose(const __grid_constant__ MeParams p) { me::propose_body<UserCfg>(p); }\n"
            "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_accept(const __grid_constant__ MeParams p) { me::accept_body<UserCfg>(p); }\n";
-    const char *hdr_names[] = {"me_params.h", "me_device.cuh", "me_energies.cuh", "me_kernels.cuh"};
-    const char *hdr_src[] = {me_src_params_h, me_src_device_cuh, me_src_energies_cuh, me_src_kernels_cuh};
+    const char *hdr_names[] = {"me_params.h", "me_math.cuh", "me_device.cuh", "me_energies.cuh", "me_kernels.cuh"};
+    const char *hdr_src[] = {me_src_params_h, me_src_math_cuh, me_src_device_cuh, me_src_energies_cuh,
+                             me_src_kernels_cuh};
     nvrtcProgram prog = nullptr;
-    int rc = n.createProgram(&prog, src.c_str(), "me_user_kernels.cu", 4, hdr_src, hdr_names);
+    int rc = n.createProgram(&prog, src.c_str(), "me_user_kernels.cu", 5, hdr_src, hdr_names);
     if (rc != 0) { log = std::string("nvrtcCreateProgram: ") + n.getErrorString(rc); return ME_ERR_COMPILE; }
     std::string d_nr = "-DME_NR=" + std::to_string(n_real), d_nc = "-DME_NC=" + std::to_string(n_complex);
     std::string d_st = std::string("-DME_STRICT=") + (strict ? "1" : "0");
@@ -246,6 +247,10 @@ void base_params(me_engine *e, MeParams &p) {
     p.n_chains = e->cfg.n_chains;
     p.chain_offset = (unsigned long long)e->cfg.chain_offset;
     p.seed = e->cfg.seed;
+    for (int r = 0; r < 10; r++) {
+        p.rk[2 * r] = (unsigned)e->cfg.seed + (unsigned)r * 0x9E3779B9u;
+        p.rk[2 * r + 1] = (unsigned)(e->cfg.seed >> 32) + (unsigned)r * 0xBB67AE85u;
+    }
     p.step0 = e->step;
     p.n_meas0 = e->n_measure;
     p.use_reject = e->use_reject;

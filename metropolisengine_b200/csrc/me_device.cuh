@@ -22,6 +22,7 @@
 #define ME_DEVICE_CUH
 
 #include "me_params.h"
+#include "me_math.cuh"
 
 #define ME_MAX_BLOCK 256
 #define ME_FULL 0xffffffffu
@@ -61,16 +62,18 @@ __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) 
 /* ------------------------------------------------------------------------------------------ Philox4x32-10 */
 struct U4 { unsigned x, y, z, w; };
 
+/* rk: the 10 round-key pairs (k0 + r*0x9E3779B9, k1 + r*0xBB67AE85), precomputed on the host: they are the same
+ * for every chain and step, and as kernel parameters they are constant-bank operands of the XORs. */
 __device__ __forceinline__ U4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
-                                            unsigned k0, unsigned k1) {
+                                            const unsigned *rk) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const unsigned n0 = hi1 ^ c1 ^ k0;
-        const unsigned n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        const unsigned k0 = rk[2 * r], k1 = rk[2 * r + 1];
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;   /* one IMAD.WIDE each */
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0;
+        const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (unsigned)p1; c2 = n2; c3 = (unsigned)p0;
     }
     U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
     return o;
@@ -85,27 +88,41 @@ __device__ __forceinline__ double u53(unsigned hi, unsigned lo) {
     return a + b;
 }
 
+/* Stream definition (identical in oracle/me_oracle.c): per step and chain, Philox call q = 0..ceil(D/2)-1 with
+ * counter (chain_lo, chain_hi, step, q), key = seed, output words (x, y, z, w):
+ *   radius uniform u1 = u53(x, y) + 2^-53 in (0,1];  angle t = z 2^-31 in [0,2);
+ *   z_{2q} = sqrt(-2 ln u1) cos(pi t), z_{2q+1} = sqrt(-2 ln u1) sin(pi t);
+ *   accept uniform: u53(w_0, w_1) when there are two or more calls, otherwise the 43 bits
+ *   w_0 : (x_0 & 31) : (y_0 & 63) — the bits u53 discards.  One Philox call per Gaussian pair, nothing else. */
+struct Spare { unsigned w0, w1, lo11; };
+
 struct Rng {
-    unsigned c0, c1, k0, k1;
-    __device__ __forceinline__ Rng(unsigned long long seed, unsigned long long gchain)
-        : c0((unsigned)gchain), c1((unsigned)(gchain >> 32)), k0((unsigned)seed), k1((unsigned)(seed >> 32)) {}
+    unsigned c0, c1;
+    const unsigned *rk;
+    __device__ __forceinline__ Rng(const MeParams &p, unsigned long long gchain)
+        : c0((unsigned)gchain), c1((unsigned)(gchain >> 32)), rk(p.rk) {}
     __device__ __forceinline__ U4 bits(unsigned step, unsigned slot) const {
-        return philox4x32_10(c0, c1, step, slot, k0, k1);
+        return philox4x32_10(c0, c1, step, slot, rk);
     }
-    /* one Philox call -> one Box-Muller pair of standard normals */
-    __device__ __forceinline__ void normal_pair(unsigned step, unsigned slot, double &z0, double &z1) const {
-        const U4 r = bits(step, slot);
-        const double u1 = u53(r.x, r.y) + 1.1102230246251565e-16;   /* (0,1] */
-        const double u2 = u53(r.z, r.w);                            /* [0,1) */
-        const double rad = sqrt(-2.0 * log(u1));
+    template <bool STRICT>
+    __device__ __forceinline__ static void box_muller(const U4 &r, const MathTables &T, double &z0, double &z1) {
+        const double u1 = u53(r.x, r.y) + 1.1102230246251565e-16;                                   /* (0,1] */
+        const double t = __hiloint2double(0x43300000 - (31 << 20), (int)r.z) - 2097152.0;           /* z 2^-31 */
+        const double rad = sqrt(STRICT ? -2.0 * log(u1) : neg2log_unit(u1, T));
         double s, c;
-        sincospi(2.0 * u2, &s, &c);
+        sincospi_02(t, s, c);
         z0 = rad * c;
         z1 = rad * s;
     }
-    __device__ __forceinline__ double uniform(unsigned step, unsigned slot) const {
-        const U4 r = bits(step, slot);
-        return u53(r.x, r.y);
+    __device__ __forceinline__ static void keep_spare(const U4 &r, int q, Spare &sp) {
+        if (q == 0) { sp.w0 = r.w; sp.lo11 = ((r.x & 31u) << 6) | (r.y & 63u); }
+        if (q == 1) sp.w1 = r.w;
+    }
+    __device__ __forceinline__ static double accept_uniform(const Spare &sp, int n_calls) {
+        if (n_calls >= 2) return u53(sp.w0, sp.w1);
+        const double a = __hiloint2double(0x43300000 - (32 << 20), (int)sp.w0) - 1048576.0;         /* w0 2^-32 */
+        const double b = __hiloint2double(0x43300000 - (43 << 20), (int)sp.lo11) - 512.0;           /* lo11 2^-43 */
+        return a + b;
     }
 };
 
@@ -243,11 +260,27 @@ __device__ __forceinline__ int refactor(const Stats<L> &s, Chain<L> &c) {
  * complex      c' = c + sigma_c conj(G) xi, xi=(z+iz')/sqrt2 ~ CN(c, sigma_c^2 conj(C_c))   (ME:288-302; App. B-8)
  * Draw order per step: real block first, then complex (ME:246).  Normals (2q, 2q+1) come from Philox slot q. */
 template <class L>
-__device__ __forceinline__ void propose(const Chain<L> &c, const Rng &rng, unsigned step, double (&prop)[L::D]) {
-    constexpr int NZ = (L::D + 1) / 2 * 2;
-    double z[NZ];
+struct Draws {                 /* everything random one step consumes; independent of the chain's state */
+    double z[(L::D + 1) / 2 * 2];
+    double u;
+};
+
+template <class L, bool STRICT>
+__device__ __forceinline__ void gen_draws(const Rng &rng, unsigned step, const MathTables &T, Draws<L> &d) {
+    constexpr int NQ = (L::D + 1) / 2;
+    Spare sp;
+    sp.w0 = sp.w1 = sp.lo11 = 0;
 #pragma unroll
-    for (int q = 0; q < NZ / 2; q++) rng.normal_pair(step, (unsigned)q, z[2 * q], z[2 * q + 1]);
+    for (int q = 0; q < NQ; q++) {
+        const U4 r = rng.bits(step, (unsigned)q);
+        Rng::keep_spare(r, q, sp);
+        Rng::box_muller<STRICT>(r, T, d.z[2 * q], d.z[2 * q + 1]);
+    }
+    d.u = Rng::accept_uniform(sp, NQ);
+}
+
+template <class L>
+__device__ __forceinline__ void apply_proposal(const Chain<L> &c, const double *z, double (&prop)[L::D]) {
 #pragma unroll
     for (int i = 0; i < L::NR; i++) {
         double acc = 0.0;
@@ -287,16 +320,23 @@ __device__ __forceinline__ Gains make_gains(long long n_meas, const MeParams &p)
     g.f = f;
     g.up = p.ratio * (1 - p.target) / f;
     g.down = p.ratio * p.target / f;
+    /* keep the two quotients as values: without this the compiler sinks the division into the step loop
+       (select the numerator by `accept`, divide once per step) */
+    asm volatile("" : "+d"(g.up), "+d"(g.down));
     return g;
 }
 
 /* Metropolis test (ME:319-338): ties accept; T == 0 rejects every uphill move; otherwise u <= exp(-1*diff/T). */
 template <bool STRICT>
-__device__ __forceinline__ bool decide(double diff, double u, const MeParams &p) {
-    if (diff <= 0) return true;
-    if (p.temp == 0) return false;
-    const double prob = STRICT ? exp(-1 * diff / p.temp) : exp(-diff * p.inv_temp);
-    return u <= prob;
+__device__ __forceinline__ bool decide(double diff, double u, const MeParams &p, const MathTables &T) {
+    if (STRICT) {
+        if (diff <= 0) return true;
+        if (p.temp == 0) return false;
+        return u <= exp(-1 * diff / p.temp);
+    }
+    /* throughput build: branch-free (every lane evaluates the exponential; downhill lanes ignore it) */
+    const double prob = exp_nonpos(fmin(-diff * p.inv_temp, 0.0), T);
+    return (diff <= 0) | ((p.temp != 0) & (u <= prob));
 }
 
 template <bool STRICT>
@@ -311,35 +351,40 @@ __device__ __forceinline__ double adapt_sigma(double sig, bool accept, const Gai
 /* ------------------------------------------------------------------------------------------ measure (ME:342-427)
  * Running means, Haario recursion + sigma^2/n regulariser once n > 50, observable means; evaluation order as in
  * the reference.  numpy divides a complex array by a real as multiplication by the reciprocal,
- * so the complex block uses inv_n / inv_n1 where the real block divides. */
-template <class L>
+ * so the complex block uses inv_n / inv_n1 where the real block divides (strict build); the throughput build
+ * uses the reciprocals everywhere. */
+template <class L, bool STRICT>
 __device__ __forceinline__ void measure_update(Chain<L> &c, Stats<L> &s, long long n) {
     constexpr int NR = L::NR, NC = L::NC;
     const double dn = (double)n, dn1 = (double)(n - 1), dn2 = (double)(n - 2);
-    const double shrink = dn1 / dn;
+    /* throughput build: two reciprocals per measure instead of a division per element */
+    const double inv_n = 1.0 / dn, inv_n1 = 1.0 / dn1;
+    const double shrink = STRICT ? dn1 / dn : dn1 * inv_n;
     const bool adapt_cov = n > 50;
-    const double decay = dn2 / dn1, grow = dn / dn1;
+    const double decay = STRICT ? dn2 / dn1 : dn2 * inv_n1, grow = STRICT ? dn / dn1 : dn * inv_n1;
     if (NR > 0) {
         double old[nz(NR)];
 #pragma unroll
         for (int i = 0; i < NR; i++) old[i] = s.mean[i];
 #pragma unroll
-        for (int i = 0; i < NR; i++) { s.mean[i] = s.mean[i] * shrink; s.mean[i] = s.mean[i] + c.x[i] / dn; }
+        for (int i = 0; i < NR; i++) {
+            s.mean[i] = s.mean[i] * shrink;
+            s.mean[i] = s.mean[i] + (STRICT ? c.x[i] / dn : c.x[i] * inv_n);
+        }
         if (adapt_cov) {
-            const double small = (c.sig[0] * c.sig[0]) / dn;
+            const double small = STRICT ? (c.sig[0] * c.sig[0]) / dn : (c.sig[0] * c.sig[0]) * inv_n;
 #pragma unroll
             for (int i = 0; i < NR; i++)
 #pragma unroll
                 for (int j = 0; j <= i; j++) {
                     const double v = s.covr[tri(i, j)] * decay;
-                    const double add = ((old[i] * old[j] - grow * (s.mean[i] * s.mean[j])) + (c.x[i] * c.x[j]) / dn1)
-                                       + (i == j ? small : 0.0);
+                    const double xx = STRICT ? (c.x[i] * c.x[j]) / dn1 : (c.x[i] * c.x[j]) * inv_n1;
+                    const double add = ((old[i] * old[j] - grow * (s.mean[i] * s.mean[j])) + xx) + (i == j ? small : 0.0);
                     s.covr[tri(i, j)] = v + add;
                 }
         }
     }
     if (NC > 0) {
-        const double inv_n = 1.0 / dn, inv_n1 = 1.0 / dn1;
         double *xr = c.x + NR, *xi = c.x + NR + NC, *mr = s.mean + NR, *mi = s.mean + NR + NC;
         double orr[nz(NC)], oi[nz(NC)];
 #pragma unroll
@@ -350,7 +395,7 @@ __device__ __forceinline__ void measure_update(Chain<L> &c, Stats<L> &s, long lo
             mr[j] = mr[j] + xr[j] * inv_n; mi[j] = mi[j] + xi[j] * inv_n;
         }
         if (adapt_cov) {
-            const double small = (c.sig[1] * c.sig[1]) / dn;
+            const double small = STRICT ? (c.sig[1] * c.sig[1]) / dn : (c.sig[1] * c.sig[1]) * inv_n;
             constexpr int dg = NC * (NC - 1);
 #pragma unroll
             for (int i = 0; i < NC; i++)
@@ -372,12 +417,18 @@ __device__ __forceinline__ void measure_update(Chain<L> &c, Stats<L> &s, long lo
     }
     /* observables |x_i|, |c_j|, x_i^2 (ME:458-463) and their running mean (ME:412-414) */
 #pragma unroll
-    for (int i = 0; i < NR; i++) s.obsm[i] = s.obsm[i] * shrink + fabs(c.x[i]) / dn;
+    for (int i = 0; i < NR; i++)
+        s.obsm[i] = s.obsm[i] * shrink + (STRICT ? fabs(c.x[i]) / dn : fabs(c.x[i]) * inv_n);
 #pragma unroll
-    for (int j = 0; j < NC; j++)
-        s.obsm[NR + j] = s.obsm[NR + j] * shrink + hypot(c.x[NR + j], c.x[NR + NC + j]) / dn;
+    for (int j = 0; j < NC; j++) {
+        const double a = hypot(c.x[NR + j], c.x[NR + NC + j]);
+        s.obsm[NR + j] = s.obsm[NR + j] * shrink + (STRICT ? a / dn : a * inv_n);
+    }
 #pragma unroll
-    for (int i = 0; i < NR; i++) s.obsm[NR + NC + i] = s.obsm[NR + NC + i] * shrink + (c.x[i] * c.x[i]) / dn;
+    for (int i = 0; i < NR; i++) {
+        const double q = c.x[i] * c.x[i];
+        s.obsm[NR + NC + i] = s.obsm[NR + NC + i] * shrink + (STRICT ? q / dn : q * inv_n);
+    }
     if (adapt_cov && refactor<L>(s, c)) c.status |= ME_STATUS_NOT_PSD;
 }
 
@@ -429,6 +480,9 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
 
     __shared__ double pool_warp[ME_MAX_BLOCK / 32][PW];
     __shared__ double pool_cta[PW];
+    __shared__ MathTables tables;
+    init_math_tables(tables);
+    __syncthreads();
 
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = tid < p.n_chains;
@@ -454,22 +508,32 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
 #pragma unroll
     for (int i = 0; i < D; i++) shift[i] = pooling ? p.shift[i] : 0.0;
 
-    const Rng rng(p.seed, p.chain_offset + (unsigned long long)ch);
+    const Rng rng(p, p.chain_offset + (unsigned long long)ch);
     const bool inject = STRICT && p.inj_delta != nullptr;
     long long n = p.n_meas0;
     unsigned long long step = p.step0;
     long long s_local = 0;
     bool accept = false;
 
+    /* Software pipelining: the random draws of step s+1 do not depend on the chain's state, so they are generated
+       while the state-dependent chain of step s (proposal -> energy -> exp -> select) is in flight.  This doubles
+       the instruction-level parallelism of a warp, which is what limits this kernel when an ensemble gives each
+       SM sub-partition only 3-4 warps (65,536 chains on 148 SMs). */
+    Draws<L> cur;
+    if (!inject && p.spm > 0) gen_draws<L, STRICT>(rng, (unsigned)step, tables, cur);
+
     for (long long b = 0; b < p.n_blocks; b++) {
         const Gains g = make_gains(n, p);
         for (long long k = 0; k < p.spm; k++, step++, s_local++) {
             double prop[D];
+            Draws<L> nxt;
             if (inject) {
 #pragma unroll
                 for (int i = 0; i < D; i++) prop[i] = p.inj_delta[(s_local * D + i) * ld + ch] + c.x[i];
+                cur.u = p.inj_u[s_local * ld + ch];
             } else {
-                propose<L>(c, rng, (unsigned)step, prop);
+                gen_draws<L, STRICT>(rng, (unsigned)(step + 1), tables, nxt);
+                apply_proposal<L>(c, cur.z, prop);
             }
             accept = false;
             const bool wall = p.use_reject && Energy::reject(prop, prop + L::NR, prop + L::NR + L::NC, p.consts);
@@ -477,10 +541,7 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
                 const double e_new = Energy::eval(prop, prop + L::NR, prop + L::NR + L::NC, p.consts);
                 if (e_new != e_new) c.status |= ME_STATUS_ENERGY_NAN;
                 const double diff = e_new - c.e;
-                double u = 0.0;
-                if (inject) u = p.inj_u[s_local * ld + ch];
-                else if (diff > 0 && p.temp != 0) u = rng.uniform((unsigned)step, (unsigned)((D + 1) / 2));
-                accept = decide<STRICT>(diff, u, p);
+                accept = decide<STRICT>(diff, cur.u, p, tables);
                 if (accept) {
                     c.e = e_new;
 #pragma unroll
@@ -491,15 +552,16 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
             const double sg = adapt_sigma<STRICT>(c.sig[L::SIGIDX], accept, g, p);
             c.sig[L::SIGIDX] = sg;
             if (L::KIND == 0) { c.sig[1] = sg; if (!(sg > 0)) c.status |= ME_STATUS_SIGMA_NONPOS; }
+            if (!inject) cur = nxt;
         }
         if (p.do_measure) {
             n += 1;
             if (STATS_REG) {
-                measure_update<L>(c, sreg, n);
+                measure_update<L, STRICT>(c, sreg, n);
             } else {
                 Stats<L> s;
                 load_stats<L>(s, st, ld, ch);
-                measure_update<L>(c, s, n);
+                measure_update<L, STRICT>(c, s, n);
                 if (active) store_stats<L>(s, st, ld, ch);
             }
             if (p.record && active) {
@@ -613,6 +675,9 @@ template <class Cfg>
 __device__ __forceinline__ void propose_body(const MeParams &p) {
     using L = Lay<Cfg::NR, Cfg::NC>;
     constexpr int D = L::D;
+    __shared__ MathTables tables;
+    init_math_tables(tables);
+    __syncthreads();
     const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= p.n_chains) return;
     Chain<L> c;
@@ -622,8 +687,10 @@ __device__ __forceinline__ void propose_body(const MeParams &p) {
 #pragma unroll
         for (int i = 0; i < D; i++) prop[i] = p.inj_delta[(long long)i * p.ld + ch] + c.x[i];
     } else {
-        const Rng rng(p.seed, p.chain_offset + (unsigned long long)ch);
-        propose<L>(c, rng, (unsigned)p.step0, prop);
+        const Rng rng(p, p.chain_offset + (unsigned long long)ch);
+        Draws<L> d;
+        gen_draws<L, Cfg::STRICT>(rng, (unsigned)p.step0, tables, d);
+        apply_proposal<L>(c, d.z, prop);
     }
 #pragma unroll
     for (int i = 0; i < D; i++) p.prop[(long long)i * p.ld + ch] = prop[i];
@@ -634,6 +701,9 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
     using L = Lay<Cfg::NR, Cfg::NC>;
     constexpr bool STRICT = Cfg::STRICT;
     constexpr int D = L::D;
+    __shared__ MathTables tables;
+    init_math_tables(tables);
+    __syncthreads();
     const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= p.n_chains) return;
     const long long ld = p.ld;
@@ -650,11 +720,15 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
         const double diff = e_new - e;
         double u = 0.0;
         if (STRICT && p.inj_u != nullptr) u = p.inj_u[ch];
-        else if (diff > 0 && p.temp != 0) {
-            const Rng rng(p.seed, p.chain_offset + (unsigned long long)ch);
-            u = rng.uniform((unsigned)p.step0, (unsigned)((D + 1) / 2));
+        else if (diff > 0 && p.temp != 0) {      /* regenerate the spare words of Philox calls 0 (and 1) */
+            const Rng rng(p, p.chain_offset + (unsigned long long)ch);
+            Spare sp;
+            sp.w1 = 0;
+            Rng::keep_spare(rng.bits((unsigned)p.step0, 0u), 0, sp);
+            if ((D + 1) / 2 >= 2) Rng::keep_spare(rng.bits((unsigned)p.step0, 1u), 1, sp);
+            u = Rng::accept_uniform(sp, (D + 1) / 2);
         }
-        accept = decide<STRICT>(diff, u, p);
+        accept = decide<STRICT>(diff, u, p, tables);
         if (accept) {
             st[(long long)L::E * ld + ch] = e_new;
 #pragma unroll

@@ -5,7 +5,7 @@
 #ifndef ME_PARAMS_H
 #define ME_PARAMS_H
 
-#define ME_PARAMS_VERSION 3
+#define ME_PARAMS_VERSION 4
 #define ME_MAX_CONSTS 16
 
 /* status bits written to the per-chain STATUS word (SURVEY §5 "failure detection") */
@@ -19,6 +19,7 @@ struct MeParams {
     long long n_chains;            /* chains owned by this launch (<= ld) */
     unsigned long long chain_offset; /* global id of local chain 0: Philox counters carry GLOBAL chain ids */
     unsigned long long seed;       /* Philox key */
+    unsigned rk[20];               /* Philox round keys: rk[2r] = lo(seed) + r*0x9E3779B9, rk[2r+1] = hi(seed) + r*0xBB67AE85 */
     unsigned long long step0;      /* global index of the first step of this launch */
     long long n_blocks;            /* schedule: n_blocks x (spm steps [+ measure]) */
     long long spm;

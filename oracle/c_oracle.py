@@ -45,6 +45,7 @@ def lib():
         _lib = ctypes.CDLL(build())
         _lib.meo_run.restype = ctypes.c_int
         _lib.meo_uniform.restype = ctypes.c_double
+        _lib.meo_uniform.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int]
     return _lib
 
 

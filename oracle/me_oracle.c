@@ -155,23 +155,37 @@ static void sincospi_d(double t, double *s, double *c) {
     }
 }
 
-/* one Philox call -> two independent standard normals (Box-Muller) */
+/* Stream definition (shared with the CUDA kernels, me_device.cuh):
+ *   per step and chain, Philox call q = 0 .. ceil(D/2)-1 with counter (chain_lo, chain_hi, step, q), key = seed,
+ *   output words (x, y, z, w):
+ *     radius uniform  u1 = u53(x, y) + 2^-53        in (0,1]
+ *     angle           t  = z * 2^-31                in [0,2)      (sin/cos of pi*t)
+ *     normals         z_{2q} = sqrt(-2 ln u1) cos(pi t),  z_{2q+1} = sqrt(-2 ln u1) sin(pi t)
+ *   accept uniform: two or more calls: u = u53(w_0, w_1) (53 bits);
+ *                   one call: the 32 bits of w_0 followed by the 5 + 6 low bits of x_0, y_0 that u53 discards
+ *                   (43 bits).  All bits used are distinct output bits of the generator. */
 void meo_normal_pair(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot, double *z0, double *z1) {
     uint32_t r[4];
     meo_philox(seed, chain, step, slot, r);
     double u1 = u53(r[0], r[1]) + (1.0 / 9007199254740992.0);   /* (0,1] */
-    double u2 = u53(r[2], r[3]);                                /* [0,1) */
+    double t = (double)r[2] * (1.0 / 2147483648.0);             /* [0,2) */
     double rad = sqrt(-2.0 * log(u1));
     double s, c;
-    sincospi_d(2.0 * u2, &s, &c);
+    sincospi_d(t, &s, &c);
     *z0 = rad * c;
     *z1 = rad * s;
 }
 
-double meo_uniform(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot) {
+double meo_uniform(uint64_t seed, uint64_t chain, uint32_t step, int n_calls) {
     uint32_t r[4];
-    meo_philox(seed, chain, step, slot, r);
-    return u53(r[0], r[1]);
+    meo_philox(seed, chain, step, 0, r);
+    if (n_calls >= 2) {
+        uint32_t r1[4];
+        meo_philox(seed, chain, step, 1, r1);
+        return u53(r[3], r1[3]);
+    }
+    uint64_t bits = ((uint64_t)r[3] << 11) | ((uint64_t)(r[0] & 31u) << 6) | (uint64_t)(r[1] & 63u);
+    return (double)bits * (1.0 / 8796093022208.0);              /* 2^-43 */
 }
 
 /* ------------------------------------------------------------------ Cholesky factors of the proposal covariances */
@@ -375,7 +389,7 @@ int meo_run(const meo_config *c, double *st, int mode, int64_t n_blocks, int64_t
                 else if (c->temp == 0) accept = 0;
                 else {
                     double uu = (mode == MEO_INJECT) ? u[s]
-                              : meo_uniform(seed, chain_id, (uint32_t)(step0 + (uint64_t)s), (uint32_t)((d + 1) / 2));
+                              : meo_uniform(seed, chain_id, (uint32_t)(step0 + (uint64_t)s), (d + 1) / 2);
                     accept = uu <= exp(-1 * diff / c->temp);
                 }
                 if (accept) { st[o.E] = e_new; for (int i = 0; i < d; i++) x[i] = prop[i]; st[o.NACC] += 1.0; }
