@@ -39,7 +39,7 @@ WORKLOADS = {
                     "measure every 10", energy=("xy_well", 1.0), n_r=2, n_c=0, temp=0.1, chains=65536,
                measures=10000, spm=10, flop=20, sf=5),
     "c3": dict(name="mixed 3 real + 4 complex (bounded demo-style well), T=0.1, 262,144 chains, measure every 10",
-               energy=("mixed_well", 1.0, -1.0, 0.5), n_r=3, n_c=4, temp=0.1, chains=262144, measures=100, spm=10,
+               energy=("mixed_well", 1.0, -1.0, 0.5, 1.0), n_r=3, n_c=4, temp=0.1, chains=262144, measures=100, spm=10,
                flop=170, sf=23),
 }
 
@@ -142,7 +142,7 @@ def _cpu_worker(args):
     elif wl_key == "c2":
         ch = PortChain(en.xy_well, initial_real_params=np.array([0., 0.]), temp=wl["temp"])
     else:
-        ch = PortChain(en.mixed_3r4c, initial_real_params=np.zeros(3), initial_complex_params=np.zeros(4, dtype=complex),
+        ch = PortChain(en.mixed_3r4c_bounded, initial_real_params=np.zeros(3), initial_complex_params=np.zeros(4, dtype=complex),
                        temp=wl["temp"])
     spm = wl["spm"]
     for _ in range(20):                       # warm-up

@@ -42,7 +42,7 @@ enum me_status_code {
 enum me_energy_id {
     ME_ENERGY_X2 = 0,          /* README.md:26-27            E = x^2                           consts: -            */
     ME_ENERGY_XY_WELL = 1,     /* demo/toymodel_xypotentialwell.py:13-18  E = k0 (x^2+y^2)     consts: k0           */
-    ME_ENERGY_MIXED_WELL = 2,  /* demo/toymodel_complex_and_real.py:17-26 and its 3r+4c scale-up consts: k, alpha, beta */
+    ME_ENERGY_MIXED_WELL = 2,  /* demo/toymodel_complex_and_real.py:17-26 and its 3r+4c scale-up consts: k, alpha, beta[, bounded] */
     ME_ENERGY_CYLINDER = 3,    /* cylinder-style Fourier-mode field, wall |a|>=1               consts: kappa, alpha, gamma, beta */
     ME_ENERGY_EXTERNAL = 99,   /* energy evaluated by the caller between me_propose and me_accept (torch callable) */
     ME_ENERGY_USER = 100       /* CUDA source given to me_set_energy_source */

@@ -35,8 +35,10 @@ struct EnergyXYWell {
     }
 };
 
-/* demo 2 and its bounded scale-up (demo/toymodel_complex_and_real.py:17-26):
- * E = k0 sum_i (1-x_i)^2 + x0 x1 (1/NC) sum_j (k1 |c_j|^2 + k2 |c_j|^4) */
+/* demo 2 and its scale-up (demo/toymodel_complex_and_real.py:17-26):
+ * E = k0 sum_i (1-x_i)^2 + w (1/NC) sum_j (k1 |c_j|^2 + k2 |c_j|^4),  w = x0 x1 (the demo's form), or
+ * w = |x0 x1| when k3 != 0.  The demo's form is unbounded below where x0 x1 < 0 (a few chains per thousand run
+ * away, in the reference too); the |.| variant is the bounded workload used for large ensembles. */
 template <int NR, int NC>
 struct EnergyMixedWell {
     __device__ static __forceinline__ double eval(const double *x, const double *cr, const double *ci, const double *k) {
@@ -48,7 +50,8 @@ struct EnergyMixedWell {
             const double a = cr[j] * cr[j] + ci[j] * ci[j];
             s = s + (k[1] * a + k[2] * (a * a));
         }
-        return area + (x[0] * x[1]) * (s / (double)NC);
+        const double w = x[0] * x[1];
+        return area + (k[3] != 0.0 ? fabs(w) : w) * (s / (double)NC);
     }
     __device__ static __forceinline__ bool reject(const double *, const double *, const double *, const double *) {
         return false;

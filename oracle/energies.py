@@ -56,8 +56,9 @@ def make_demo_2r1c(k=1.0, alpha=-1.0, beta=0.5):
 demo_2r1c = make_demo_2r1c()
 
 
-def make_mixed_3r4c(k=1.0, alpha=-1.0, beta=0.5):
-    """E = k*sum_i (1-x_i)^2 + x0*x1*(1/n_c)*sum_j (alpha*|c_j|^2 + beta*|c_j|^4); sequential sums."""
+def make_mixed_3r4c(k=1.0, alpha=-1.0, beta=0.5, bounded=False):
+    """E = k*sum_i (1-x_i)^2 + w*(1/n_c)*sum_j (alpha*|c_j|^2 + beta*|c_j|^4); sequential sums; w = x0*x1 (the
+    demo's form, unbounded below where x0*x1 < 0) or |x0*x1| when ``bounded``."""
     def mixed_3r4c(real_params, complex_params):
         area = 0.0
         for i in range(len(real_params)):
@@ -69,11 +70,13 @@ def make_mixed_3r4c(k=1.0, alpha=-1.0, beta=0.5):
             c = complex_params[j]
             a = c.real * c.real + c.imag * c.imag
             s = s + (alpha * a + beta * (a * a))
-        return area + (real_params[0] * real_params[1]) * (s / n_c)
+        w = real_params[0] * real_params[1]
+        return area + (abs(w) if bounded else w) * (s / n_c)
     return mixed_3r4c
 
 
 mixed_3r4c = make_mixed_3r4c()
+mixed_3r4c_bounded = make_mixed_3r4c(bounded=True)
 
 
 def make_cylinder(n_c, kappa=10.0, alpha=-1.0, gamma=0.05, beta=1.0):

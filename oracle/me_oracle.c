@@ -93,7 +93,8 @@ static double energy_eval(const meo_config *c, const double *x) {
             double a = re * re + im * im;
             s = s + (k[1] * a + k[2] * (a * a));
         }
-        return area + (x[0] * x[1]) * (s / (double)n_c);
+        double w = x[0] * x[1];
+        return area + (k[3] != 0.0 ? fabs(w) : w) * (s / (double)n_c);
     }
     case MEO_E_CYL: {
         double a = x[0], a2 = a * a, quad = 0.0, tot = 0.0;

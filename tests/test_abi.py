@@ -114,11 +114,13 @@ def test_engine_fails_loudly_without_cuda():
 
 
 def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: the product may mention it in comments but never import, include, link
+    or load it."""
     pkg = os.path.join(ROOT, "metropolisengine_b200")
+    pat = re.compile(r"(^\s*(import|from)\s+oracle\b)|(#\s*include\s*[\"<][^\">]*oracle)|(libme_oracle)|(c_oracle)|(py_port)",
+                     re.M)
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.replace("oracle/energies.py", "").replace("the oracle", "").lower() \
-                    or f == "me_energies.cuh", "%s mentions the oracle" % f
-                assert "import oracle" not in text and "from oracle" not in text
+                assert not pat.search(text), "%s uses the oracle" % f
