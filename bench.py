@@ -356,6 +356,7 @@ def run_ours(args):
         if it > 0:
             best = ms if best is None else min(best, ms)
     fp64_peak = flops.value / (best * 1e-3) / 1e12
+    acc_rate = eng.acceptance_rate            # collective when sharded: every rank must call it
 
     if rank != 0:
         if world > 1:
@@ -367,7 +368,6 @@ def run_ours(args):
     per_launch_steps = chains * M * spm
     achieved_tf = per_launch_steps * wl["flop"] / (ker_ms * 1e-3) / 1e12
     ts_gbs = ts_bytes / (ker_ms * 1e-3) / 1e9
-    acc_rate = eng.acceptance_rate
     line = {
         "metric": "ensemble chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,

@@ -1,0 +1,62 @@
+"""Run under torchrun (one rank per GPU): a sharded ensemble must equal the single-GPU ensemble bit for bit, and the
+pooled statistics (the path's one all-reduce, NCCL) must agree on every rank.  Exit code 0 = ok."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import metropolisengine_b200 as me  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = 6000 + 7          # deliberately not divisible by the world size
+    kw = dict(initial_real_params=np.zeros(3), initial_complex_params=np.zeros(4, dtype=complex), temp=.1, seed=77)
+    eng = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5, 1.0), n_chains=n, distributed=True, **kw)
+    eng.run(70, 5)
+    ps = eng.pooled_statistics()
+    mean_attr = eng.real_mean                     # pooled over all ranks (all-reduce inside)
+    cov_attr = eng.covariance_matrix_complex
+    # gather the shards on rank 0
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([eng.n_chains], dtype=torch.int64, device="cuda"))
+    sizes = [int(s.item()) for s in sizes]
+    assert sum(sizes) == n
+    pad = max(sizes)
+    buf = torch.zeros((eng.state.shape[0], pad), dtype=torch.float64, device="cuda")
+    buf[:, :eng.n_chains] = eng.state
+    parts = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    ok = True
+    if rank == 0:
+        full = torch.cat([p[:, :s] for p, s in zip(parts, sizes)], dim=1)
+        ref = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5, 1.0), n_chains=n, **kw)
+        ref.run(70, 5)
+        ok = ok and torch.equal(full, ref.state)
+        rps = ref.pooled_statistics()
+        for k in ("mean_real", "cov_real", "cov_complex", "observables_mean"):
+            ok = ok and np.allclose(ps[k], rps[k], rtol=1e-11, atol=1e-13)
+        ok = ok and ps["count"] == rps["count"] == 70 * n
+        ok = ok and np.allclose(mean_attr, ref.real_mean, rtol=1e-12) and np.allclose(cov_attr, ref.covariance_matrix_complex, rtol=1e-12)
+    # every rank must hold the same pooled numbers
+    v = torch.tensor(np.concatenate([ps["mean_real"], np.diag(ps["cov_real"])]), device="cuda")
+    lo, hi = v.clone(), v.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ok = ok and torch.equal(lo, hi)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("dist_invariance world=%d: %s" % (world, "OK" if flag.item() else "FAILED"))
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
