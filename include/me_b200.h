@@ -169,6 +169,47 @@ int me_pool_reduce(me_engine *eng, double *out, int32_t reset, void *stream);
 int me_get_counters(me_engine *eng, int64_t *n_measure, uint64_t *step);
 int me_set_counters(me_engine *eng, int64_t n_measure, uint64_t step);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Shared-covariance tensor-core path (BASELINE config 4: 1 real + 64 complex Fourier-mode coefficients).
+ * Same step as me_run (ME:241-259), but the complex block's proposal covariance is pooled over the ensemble at
+ * measure boundaries and shared by all chains, so the proposal increments of 128 chains are one BF16 tcgen05
+ * contraction  Delta = Z . B^T  with the FP32 accumulator in TMEM (csrc/me_k4.cu).  The caller owns the pooled
+ * covariance / Cholesky factor (host side: engine_shared.py) and hands the factor over in `factor_bf16`:
+ *   B[2i][2j] = Re G_ij / sqrt2, B[2i][2j+1] = Im G_ij / sqrt2, B[2i+1][2j] = -Im G_ij / sqrt2, B[2i+1][2j+1] = Re G_ij / sqrt2
+ *   (C_c = G G^H; ME:288-302 samples CN(0, sigma^2 conj(C_c))), stored BF16 as [16 k-chunks][128 n][8] (UMMA
+ *   canonical K-major, no swizzle).
+ * State block (me_k4_layout): X 129 (a, Re c, Im c) | E | SIG | MEAN 129 | OBSM 66 | NACC | STATUS. */
+typedef struct me_k4 me_k4;
+typedef struct me_k4_config {
+    int32_t n_real;             /* must be 1  */
+    int32_t n_complex;          /* must be 64 */
+    int64_t n_chains;           /* multiple of 128 */
+    int64_t chain_offset;
+    double temp;
+    double target_acceptance;
+    double ratio;               /* ME:105-107 with m = 65 */
+    uint64_t seed;
+    int32_t device;
+    int32_t use_reject;         /* hard wall |a| >= 1 (legacy metropolis_engine.py:103,139) */
+    double consts[4];           /* cylinder energy: kappa, alpha, gamma, beta */
+} me_k4_config;
+typedef struct me_k4_layout {
+    int32_t X, E, SIG, MEAN, OBSM, NACC, STATUS, WORDS, D, TS_COLS, N_COMPLEX, TILE, FACTOR_BYTES;
+} me_k4_layout;
+int me_k4_layout_get(me_k4_layout *out);
+int me_k4_create(const me_k4_config *cfg, me_k4 **out);
+int me_k4_destroy(me_k4 *eng);
+int me_k4_bind(me_k4 *eng, double *state, const void *factor_bf16, unsigned char *last_accept);
+int me_k4_init(me_k4 *eng, const double *x0, int32_t x0_broadcast, double sigma0, void *stream);
+/* n_steps x step_all(); s_a = DEVICE scalar, shared proposal std of the real parameter; dbg_z / dbg_delta (may be NULL) receive
+ * the normals [128][n_chains] and tensor-core increments [128][n_chains] of the first step (tests). */
+int me_k4_step(me_k4 *eng, int64_t n_steps, const double *s_a, float *dbg_z, float *dbg_delta, void *stream);
+/* measure() without the covariance recursion (the caller pools it): means, observable means, one row
+ * ts[(row * TS_COLS + col) * n_chains + chain]. */
+int me_k4_measure(me_k4 *eng, double *ts, int64_t ts_row, void *stream);
+int me_k4_get_counters(me_k4 *eng, int64_t *n_measure, uint64_t *step);
+const char *me_k4_last_error(me_k4 *eng);
+
 /* Measurement aid (no reference counterpart): FP64 FMA throughput probe used as the roofline denominator of the
  * step kernels.  Launches n_sm*8 CTAs of 256 threads, 8 independent FMA streams each, `iters` iterations;
  * out needs n_sm*8*256 doubles; *flops receives the flop count of the launch.  Time it with CUDA events. */

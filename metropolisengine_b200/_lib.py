@@ -38,6 +38,17 @@ class MeBuffers(ctypes.Structure):
     _fields_ = [("state", _vp), ("pool", _vp), ("shift", _vp), ("last_accept", _vp)]
 
 
+class MeK4Config(ctypes.Structure):
+    _fields_ = [("n_real", _i32), ("n_complex", _i32), ("n_chains", _i64), ("chain_offset", _i64),
+                ("temp", _f64), ("target_acceptance", _f64), ("ratio", _f64), ("seed", _u64),
+                ("device", _i32), ("use_reject", _i32), ("consts", _f64 * 4)]
+
+
+class MeK4Layout(ctypes.Structure):
+    _fields_ = [(k, _i32) for k in ("X", "E", "SIG", "MEAN", "OBSM", "NACC", "STATUS", "WORDS", "D", "TS_COLS",
+                                    "N_COMPLEX", "TILE", "FACTOR_BYTES")]
+
+
 # every symbol include/me_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "me_abi_version": (ctypes.c_int, []),
@@ -58,6 +69,15 @@ SIGNATURES = {
     "me_pool_reduce": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "me_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
     "me_set_counters": (ctypes.c_int, [_vp, _i64, _u64]),
+    "me_k4_layout_get": (ctypes.c_int, [ctypes.POINTER(MeK4Layout)]),
+    "me_k4_create": (ctypes.c_int, [ctypes.POINTER(MeK4Config), ctypes.POINTER(_vp)]),
+    "me_k4_destroy": (ctypes.c_int, [_vp]),
+    "me_k4_bind": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "me_k4_init": (ctypes.c_int, [_vp, _vp, _i32, _f64, _vp]),
+    "me_k4_step": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "me_k4_measure": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
+    "me_k4_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
+    "me_k4_last_error": (_cp, [_vp]),
     "me_probe_fp64": (ctypes.c_int, [_i32, _i64, _vp, _i64, _vp, ctypes.POINTER(_i64)]),
     "me_last_error": (_cp, [_vp]),
 }

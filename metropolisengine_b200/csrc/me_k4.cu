@@ -1,0 +1,588 @@
+/* me_k4.cu — shared-covariance step kernel for large parameter spaces (BASELINE config 4: 1 real + 64 complex
+ * Fourier-mode coefficients, 32,768 chains), tcgen05 tensor cores.
+ *
+ * Same Metropolis step as me_device.cuh (reference metropolis_engine.py:241-259: proposal, hard wall ME:247, energy
+ * ME:250, decision ME:319-338, Robbins-Monro width ME:429-438), but the proposal covariance of the complex block is
+ * SHARED by all chains (pooled at measure boundaries), so the proposal increments of a tile of 128 chains are one
+ * dense contraction
+ *        Delta[128 chains x 128] = Z[128 chains x 128 normals] . B^T[128 x 128]
+ * with B the real embedding of conj(G)/sqrt2, C_c = G G^H (ME:288-302: w ~ CN(0, sigma^2 conj(C_c))).  That
+ * contraction runs on the 5th-generation tensor cores: Z is generated in-kernel (Philox4x32-10 + Box-Muller) straight
+ * into the UMMA canonical K-major shared-memory layout as BF16, B is staged once per CTA, the FP32 accumulator lives
+ * in TMEM with TMEM lane = chain, and the epilogue (tcgen05.ld) gives every thread the increments of its own chain
+ * for the FP64 energy sum.  Reduced precision only perturbs the proposal shape; the proposal stays symmetric
+ * (signs of the normals come from independent random bits), so detailed balance is exact; state, energy, energy
+ * difference and the accept test are FP64.
+ *
+ * Layout of the per-chain state block state[word*ld + chain] (shared-covariance engines keep no per-chain covariance):
+ *   X 129 (a, Re c_0..63, Im c_0..63) | E | SIG | MEAN 129 | OBSM 66 | NACC | STATUS      = 328 words
+ * Inside the kernel the complex block is held in shared memory in interleaved order n = 2j (Re c_j), 2j+1 (Im c_j),
+ * [n][chain], 128 KB per tile of 128 chains.
+ */
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+#include "../../include/me_b200.h"
+#include "me_params.h"
+#include "me_math.cuh"
+
+namespace {
+
+constexpr int K4_NC = 64;
+constexpr int K4_N = 2 * K4_NC;          /* embedded real dimension = MMA N = MMA K */
+constexpr int K4_TILE = 128;             /* chains per tile = MMA M = TMEM lanes */
+constexpr int K4_THREADS = 512;
+constexpr int K4_D = 1 + K4_N;
+
+/* state-block word offsets */
+constexpr int K4_X = 0, K4_E = K4_D, K4_SIG = K4_D + 1, K4_MEAN = K4_D + 2, K4_OBSM = K4_MEAN + K4_D,
+              K4_NOBS = 2 + K4_NC, K4_NACC = K4_OBSM + K4_NOBS, K4_STATUS = K4_NACC + 1, K4_WORDS = K4_STATUS + 1;
+
+struct K4Params {
+    double *state;
+    long long ld, n_chains;
+    unsigned long long chain_offset;
+    unsigned rk[20];
+    unsigned long long step0;
+    long long n_steps;
+    long long n_meas;              /* measure_step_counter (for the Robbins-Monro gain) */
+    double temp, inv_temp, target, ratio;
+    int m;
+    double kappa, alpha, gamma, beta;   /* cylinder energy constants */
+    int use_wall;
+    const void *factor;            /* B operand, BF16, UMMA canonical K-major layout [16 k-chunks][128 n][8] */
+    const double *s_a;             /* device scalar: shared proposal std of the real parameter */
+    unsigned char *last_accept;
+    float *dbg_z;                  /* optional [128 k][ld]: the normals of the FIRST step of the launch (tests) */
+    float *dbg_delta;              /* optional [128 n][ld]: the tensor-core increments of the first step */
+    /* measure */
+    double *ts;
+    long long ts_row;
+    int record;
+};
+
+/* -------------------------------------------------------------------------------------------- PTX helpers */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+/* bounded wait: a wrong descriptor must not hang the GPU — trap instead */
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+/* D[tmem] (+)= A[smem] . B[smem]^T, BF16 inputs, FP32 accumulate, M = 128, N = 128, K = 16 */
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+/* K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; row groups 128 B apart (SBO), the two 16-byte
+ * K chunks of one K=16 MMA 2048 B apart (LBO); descriptor fields in 16-byte units; version 1 (Blackwell). */
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+           (1ull << 46);
+}
+/* instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128 */
+constexpr uint32_t K4_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(K4_N >> 3) << 17) |
+                              ((uint32_t)(K4_TILE >> 4) << 24);
+
+/* -------------------------------------------------------------------------------------------- RNG (FP32 path) */
+struct U4 { unsigned x, y, z, w; };
+__device__ __forceinline__ U4 philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, const unsigned *rk) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ rk[2 * r];
+        const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = (unsigned)p1; c2 = n2; c3 = (unsigned)p0;
+    }
+    U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+/* two normals from 64 random bits: radius from 32 bits, first-quadrant angle from 30 bits, the two signs from 2
+ * independent bits -> the pair's law is exactly symmetric whatever the accuracy of the fast intrinsics */
+__device__ __forceinline__ void normal_pair_f32(unsigned a, unsigned b, float &z0, float &z1) {
+    const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   /* (0,1] */
+    const float rad = sqrtf(-2.0f * __logf(fminf(u1, 1.0f)));
+    const float th = __uint2float_rn(b >> 2) * 1.4629180792671596e-09f;                            /* (pi/2) 2^-30 */
+    float s, c;
+    __sincosf(th, &s, &c);
+    z0 = (b & 1u) ? -rad * c : rad * c;
+    z1 = (b & 2u) ? -rad * s : rad * s;
+}
+__device__ __forceinline__ double u53(unsigned hi, unsigned lo) {
+    const double a = __hiloint2double(0x43300000 - (27 << 20), (int)(hi >> 5)) - 33554432.0;
+    const double b = __hiloint2double(0x43300000 - (53 << 20), (int)(lo >> 6)) - 0.5;
+    return a + b;
+}
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const unsigned *>(&v);
+}
+
+/* cylinder-style energy from its sufficient statistics (same functional form as me::EnergyCylinder) */
+__device__ __forceinline__ double k4_energy(double a, double tot, double qsum, const K4Params &p) {
+    const double a2 = a * a;
+    return (p.kappa * a2 + (p.alpha * tot + p.gamma * (1.0 + a2) * qsum)) + (p.beta / (2.0 * K4_NC)) * (tot * tot);
+}
+
+/* -------------------------------------------------------------------------------------------- the step kernel */
+struct K4Smem {
+    double xs[K4_N][K4_TILE];            /* complex block, interleaved [n][chain]              128 KB */
+    alignas(1024) unsigned char zs[K4_TILE * K4_N * 2];   /* A operand (normals), BF16           32 KB */
+    alignas(1024) unsigned char ls[K4_N * K4_N * 2];      /* B operand (factor), BF16            32 KB */
+    double part[4][2][K4_TILE];
+    double a_s[K4_TILE], e_s[K4_TILE], sig_s[K4_TILE], za_s[K4_TILE], u_s[K4_TILE], nacc_s[K4_TILE];
+    int acc_s[K4_TILE];
+    int status_s[K4_TILE];
+    me::MathTables tables;
+    uint64_t mbar;
+    uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant__ K4Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    K4Smem &S = *reinterpret_cast<K4Smem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = 32 * (warp & 3) + lane;        /* chain within the tile = TMEM lane this warp may read */
+    const int g = warp >> 2;                     /* column group: embedded coordinates [32g, 32g+32) = modes [16g, 16g+16) */
+    const long long ld = p.ld;
+
+    me::init_math_tables(S.tables);
+    if (tid == 0) {
+        mbar_init(&S.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&S.tmem_slot, K4_N);
+    /* stage the shared factor once per CTA */
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.factor);
+        uint4 *dst = reinterpret_cast<uint4 *>(S.ls);
+        for (int i = tid; i < K4_N * K4_N * 2 / 16; i += K4_THREADS) dst[i] = src[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = S.tmem_slot;
+    const double s_a = *p.s_a;
+    const uint32_t zs_addr = smem_u32(S.zs), ls_addr = smem_u32(S.ls);
+    uint32_t parity = 0;
+
+    double f = (double)p.n_meas / (double)p.m;
+    if (!(f > 200.0)) f = 200.0;
+    const double g_up = p.ratio * (1 - p.target) / f, g_down = p.ratio * p.target / f;
+
+    const long long n_tiles = p.n_chains / K4_TILE;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long ch = tile * K4_TILE + m;
+        const unsigned long long gch = p.chain_offset + (unsigned long long)ch;
+        const unsigned c0 = (unsigned)gch, c1 = (unsigned)(gch >> 32);
+        /* load the tile's state */
+#pragma unroll 4
+        for (int jj = 0; jj < 16; jj++) {
+            const int j = 16 * g + jj;
+            S.xs[2 * j][m] = p.state[(long long)(K4_X + 1 + j) * ld + ch];
+            S.xs[2 * j + 1][m] = p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch];
+        }
+        if (g == 0) {
+            S.a_s[m] = p.state[(long long)K4_X * ld + ch];
+            S.e_s[m] = p.state[(long long)K4_E * ld + ch];
+            S.sig_s[m] = p.state[(long long)K4_SIG * ld + ch];
+            S.nacc_s[m] = p.state[(long long)K4_NACC * ld + ch];
+            S.status_s[m] = (int)p.state[(long long)K4_STATUS * ld + ch];
+            S.acc_s[m] = 0;
+        }
+        __syncthreads();
+
+        for (long long s = 0; s < p.n_steps; s++) {
+            const unsigned step = (unsigned)(p.step0 + (unsigned long long)s);
+            /* ---- Z tile: 32 normals per thread, BF16, canonical K-major layout (16-byte chunk kc of row m at
+                    kc*2048 + m*16: consecutive lanes write consecutive 16 B) */
+            float dz[32];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const U4 r = philox(c0, c1, step, (unsigned)(8 * g + i), p.rk);
+                normal_pair_f32(r.x, r.y, dz[4 * i], dz[4 * i + 1]);
+                normal_pair_f32(r.z, r.w, dz[4 * i + 2], dz[4 * i + 3]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint4 v;
+                v.x = pack_bf16(dz[8 * c], dz[8 * c + 1]);
+                v.y = pack_bf16(dz[8 * c + 2], dz[8 * c + 3]);
+                v.z = pack_bf16(dz[8 * c + 4], dz[8 * c + 5]);
+                v.w = pack_bf16(dz[8 * c + 6], dz[8 * c + 7]);
+                *reinterpret_cast<uint4 *>(S.zs + (4 * g + c) * 2048 + m * 16) = v;
+            }
+            if (p.dbg_z != nullptr && s == 0) {
+#pragma unroll
+                for (int k = 0; k < 32; k++)
+                    p.dbg_z[(long long)(32 * g + k) * ld + ch] = __bfloat162float(__float2bfloat16_rn(dz[k]));
+            }
+            if (g == 0) {            /* draws of the real parameter and of the accept test */
+                const U4 r = philox(c0, c1, step, 32u, p.rk);
+                float za, zb;
+                normal_pair_f32(r.x, r.y, za, zb);
+                S.za_s[m] = (double)za;
+                S.u_s[m] = u53(r.z, r.w);
+            }
+            fence_async_smem();          /* generic-proxy stores -> visible to the tensor-core (async) proxy */
+            __syncthreads();
+
+            /* ---- Delta = Z . B^T on the tensor cores: 8 x (M128 N128 K16), accumulator in TMEM */
+            if (warp == 0) {
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < K4_N / 16; k++)
+                        umma_bf16(tmem_d, umma_desc(zs_addr + k * 4096), umma_desc(ls_addr + k * 4096), K4_IDESC,
+                                  k > 0 ? 1u : 0u);
+                    umma_commit(&S.mbar);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&S.mbar, parity);
+            parity ^= 1u;
+            tc_fence_after();
+
+            /* ---- epilogue 1: thread (m, g) owns 32 increments of chain m; partial energy statistics */
+            uint32_t raw[32];
+            tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(32 * g), raw);
+            tc_fence_before();
+            if (p.dbg_delta != nullptr && s == 0) {
+#pragma unroll
+                for (int k = 0; k < 32; k++) p.dbg_delta[(long long)(32 * g + k) * ld + ch] = __uint_as_float(raw[k]);
+            }
+            const double sig = S.sig_s[m];
+            double tot = 0.0, qsum = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj++) {
+                const int j = 16 * g + jj;
+                const double re = fma(sig, (double)__uint_as_float(raw[2 * jj]), S.xs[2 * j][m]);
+                const double im = fma(sig, (double)__uint_as_float(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
+                const double m2 = fma(re, re, im * im);
+                const double q = (double)(j - K4_NC / 2);
+                tot += m2;
+                qsum = fma(q * q, m2, qsum);
+            }
+            S.part[g][0][m] = tot;
+            S.part[g][1][m] = qsum;
+            __syncthreads();
+
+            /* ---- decision (one thread per chain): ME:247-258 */
+            if (g == 0) {
+                const double t_all = (S.part[0][0][m] + S.part[1][0][m]) + (S.part[2][0][m] + S.part[3][0][m]);
+                const double q_all = (S.part[0][1][m] + S.part[1][1][m]) + (S.part[2][1][m] + S.part[3][1][m]);
+                const double a_new = fma(sig * s_a, S.za_s[m], S.a_s[m]);
+                bool accept = false;
+                const bool wall = p.use_wall && fabs(a_new) >= 1.0;
+                if (!wall) {
+                    const double e_new = k4_energy(a_new, t_all, q_all, p);
+                    if (e_new != e_new) S.status_s[m] |= ME_STATUS_ENERGY_NAN;
+                    const double diff = e_new - S.e_s[m];
+                    const double prob = me::exp_nonpos(fmin(-diff * p.inv_temp, 0.0), S.tables);
+                    accept = (diff <= 0) | ((p.temp != 0) & (S.u_s[m] <= prob));
+                    if (accept) { S.e_s[m] = e_new; S.a_s[m] = a_new; S.nacc_s[m] += 1.0; }
+                }
+                const double sg = accept ? fma(sig, g_up, sig) : fma(sig, -g_down, sig);
+                S.sig_s[m] = sg;
+                if (!(sg > 0)) S.status_s[m] |= ME_STATUS_SIGMA_NONPOS;
+                S.acc_s[m] = accept ? 1 : 0;
+            }
+            __syncthreads();
+
+            /* ---- epilogue 2: accepted chains take the increments (still in registers) */
+            if (S.acc_s[m]) {
+#pragma unroll
+                for (int jj = 0; jj < 16; jj++) {
+                    const int j = 16 * g + jj;
+                    S.xs[2 * j][m] = fma(sig, (double)__uint_as_float(raw[2 * jj]), S.xs[2 * j][m]);
+                    S.xs[2 * j + 1][m] = fma(sig, (double)__uint_as_float(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
+                }
+            }
+        }
+
+        /* store the tile's state */
+        __syncthreads();
+#pragma unroll 4
+        for (int jj = 0; jj < 16; jj++) {
+            const int j = 16 * g + jj;
+            p.state[(long long)(K4_X + 1 + j) * ld + ch] = S.xs[2 * j][m];
+            p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch] = S.xs[2 * j + 1][m];
+        }
+        if (g == 0) {
+            p.state[(long long)K4_X * ld + ch] = S.a_s[m];
+            p.state[(long long)K4_E * ld + ch] = S.e_s[m];
+            p.state[(long long)K4_SIG * ld + ch] = S.sig_s[m];
+            p.state[(long long)K4_NACC * ld + ch] = S.nacc_s[m];
+            p.state[(long long)K4_STATUS * ld + ch] = (double)S.status_s[m];
+            if (p.last_accept && p.n_steps > 0) p.last_accept[ch] = (unsigned char)S.acc_s[m];
+        }
+        __syncthreads();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, K4_N);
+}
+
+/* -------------------------------------------------------------------------------------------- init / measure */
+__global__ void k4_init(K4Params p, const double *x0, int broadcast, double sigma0) {
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_chains) return;
+    const long long ld = p.ld;
+    double tot = 0.0, qsum = 0.0;
+    const double a = broadcast ? x0[0] : x0[ch];
+    p.state[(long long)K4_X * ld + ch] = a;
+    p.state[(long long)K4_MEAN * ld + ch] = a;
+    for (int j = 0; j < K4_NC; j++) {
+        const double re = broadcast ? x0[1 + j] : x0[(long long)(1 + j) * ld + ch];
+        const double im = broadcast ? x0[1 + K4_NC + j] : x0[(long long)(1 + K4_NC + j) * ld + ch];
+        p.state[(long long)(K4_X + 1 + j) * ld + ch] = re;
+        p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch] = im;
+        p.state[(long long)(K4_MEAN + 1 + j) * ld + ch] = re;
+        p.state[(long long)(K4_MEAN + 1 + K4_NC + j) * ld + ch] = im;
+        const double m2 = re * re + im * im, q = (double)(j - K4_NC / 2);
+        tot += m2;
+        qsum += q * q * m2;
+        p.state[(long long)(K4_OBSM + 1 + j) * ld + ch] = hypot(re, im);
+    }
+    p.state[(long long)K4_OBSM * ld + ch] = fabs(a);
+    p.state[(long long)(K4_OBSM + 1 + K4_NC) * ld + ch] = a * a;
+    p.state[(long long)K4_E * ld + ch] = k4_energy(a, tot, qsum, p);
+    p.state[(long long)K4_SIG * ld + ch] = sigma0;
+    p.state[(long long)K4_NACC * ld + ch] = 0.0;
+    p.state[(long long)K4_STATUS * ld + ch] = 0.0;
+}
+
+/* measure (ME:342-356 without the per-chain covariance, which is shared): running means (ME:404-410), observable
+ * means (ME:412-414, 458-463), one time-series row [129 params, E, sigma].  n = counter after the increment. */
+__global__ void k4_measure(K4Params p) {
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_chains) return;
+    const long long ld = p.ld;
+    const double dn = (double)p.n_meas, inv_n = 1.0 / dn, shrink = (dn - 1.0) * inv_n;
+    double *row = p.record ? p.ts + p.ts_row * (long long)(K4_D + 2) * ld + ch : nullptr;
+    const double a = p.state[(long long)K4_X * ld + ch];
+    {
+        double *mp = &p.state[(long long)K4_MEAN * ld + ch];
+        *mp = *mp * shrink + a * inv_n;
+        double *o0 = &p.state[(long long)K4_OBSM * ld + ch], *o1 = &p.state[(long long)(K4_OBSM + 1 + K4_NC) * ld + ch];
+        *o0 = *o0 * shrink + fabs(a) * inv_n;
+        *o1 = *o1 * shrink + (a * a) * inv_n;
+        if (row) __stcs(row, a);
+    }
+    for (int j = 0; j < K4_NC; j++) {
+        const double re = p.state[(long long)(K4_X + 1 + j) * ld + ch];
+        const double im = p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch];
+        double *mr = &p.state[(long long)(K4_MEAN + 1 + j) * ld + ch];
+        double *mi = &p.state[(long long)(K4_MEAN + 1 + K4_NC + j) * ld + ch];
+        *mr = *mr * shrink + re * inv_n;
+        *mi = *mi * shrink + im * inv_n;
+        double *ob = &p.state[(long long)(K4_OBSM + 1 + j) * ld + ch];
+        *ob = *ob * shrink + hypot(re, im) * inv_n;
+        if (row) {
+            __stcs(row + (long long)(1 + j) * ld, re);
+            __stcs(row + (long long)(1 + K4_NC + j) * ld, im);
+        }
+    }
+    if (row) {
+        __stcs(row + (long long)K4_D * ld, p.state[(long long)K4_E * ld + ch]);
+        __stcs(row + (long long)(K4_D + 1) * ld, p.state[(long long)K4_SIG * ld + ch]);
+    }
+}
+
+}  // namespace
+
+/* ============================================================================================ C ABI */
+struct me_k4 {
+    me_k4_config cfg;
+    double *state = nullptr;
+    const void *factor = nullptr;
+    unsigned char *last_accept = nullptr;
+    long long n_measure = 1;
+    unsigned long long step = 0;
+    int n_sm = 148;
+    std::string err;
+};
+
+static std::string g_k4_create_error;
+static int k4_fail(me_k4 *e, int code, const std::string &msg) {
+    if (e) e->err = msg; else g_k4_create_error = msg;
+    return code;
+}
+
+static void k4_base(me_k4 *e, K4Params &p) {
+    memset(&p, 0, sizeof(p));
+    p.state = e->state;
+    p.ld = e->cfg.n_chains;
+    p.n_chains = e->cfg.n_chains;
+    p.chain_offset = (unsigned long long)e->cfg.chain_offset;
+    for (int r = 0; r < 10; r++) {
+        p.rk[2 * r] = (unsigned)e->cfg.seed + (unsigned)r * 0x9E3779B9u;
+        p.rk[2 * r + 1] = (unsigned)(e->cfg.seed >> 32) + (unsigned)r * 0xBB67AE85u;
+    }
+    p.step0 = e->step;
+    p.n_meas = e->n_measure;
+    p.temp = e->cfg.temp;
+    p.inv_temp = e->cfg.temp != 0 ? 1.0 / e->cfg.temp : 0.0;
+    p.target = e->cfg.target_acceptance;
+    p.ratio = e->cfg.ratio;
+    p.m = 1 + K4_NC;
+    p.kappa = e->cfg.consts[0]; p.alpha = e->cfg.consts[1]; p.gamma = e->cfg.consts[2]; p.beta = e->cfg.consts[3];
+    p.use_wall = e->cfg.use_reject;
+    p.factor = e->factor;
+    p.last_accept = e->last_accept;
+}
+
+extern "C" {
+
+int me_k4_layout_get(me_k4_layout *o) {
+    if (!o) return ME_ERR_INVALID;
+    o->X = K4_X; o->E = K4_E; o->SIG = K4_SIG; o->MEAN = K4_MEAN; o->OBSM = K4_OBSM; o->NACC = K4_NACC;
+    o->STATUS = K4_STATUS; o->WORDS = K4_WORDS; o->D = K4_D; o->TS_COLS = K4_D + 2; o->N_COMPLEX = K4_NC;
+    o->TILE = K4_TILE; o->FACTOR_BYTES = K4_N * K4_N * 2;
+    return ME_OK;
+}
+
+int me_k4_create(const me_k4_config *cfg, me_k4 **out) {
+    if (!cfg || !out) return k4_fail(nullptr, ME_ERR_INVALID, "null argument");
+    if (cfg->n_real != 1 || cfg->n_complex != K4_NC)
+        return k4_fail(nullptr, ME_ERR_UNSUPPORTED, "the shared-covariance tensor-core path is built for 1 real + 64 complex parameters");
+    if (cfg->n_chains <= 0 || cfg->n_chains % K4_TILE != 0)
+        return k4_fail(nullptr, ME_ERR_INVALID, "n_chains must be a positive multiple of 128 (one MMA tile = 128 chains)");
+    if (!(cfg->temp >= 0)) return k4_fail(nullptr, ME_ERR_INVALID, "temp must be >= 0 (reference: assert, ME:92)");
+    me_k4 *e = new me_k4();
+    e->cfg = *cfg;
+    int n_sm = 0;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) e->n_sm = n_sm;
+    else cudaGetLastError();
+    *out = e;
+    return ME_OK;
+}
+
+int me_k4_destroy(me_k4 *e) { delete e; return ME_OK; }
+
+int me_k4_bind(me_k4 *e, double *state, const void *factor_bf16, unsigned char *last_accept) {
+    if (!e || !state || !factor_bf16) return ME_ERR_INVALID;
+    e->state = state; e->factor = factor_bf16; e->last_accept = last_accept;
+    return ME_OK;
+}
+
+int me_k4_init(me_k4 *e, const double *x0, int32_t broadcast, double sigma0, void *stream) {
+    if (!e || !e->state || !x0) return ME_ERR_INVALID;
+    K4Params p;
+    k4_base(e, p);
+    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
+    const int block = 128, grid = (int)((e->cfg.n_chains + block - 1) / block);
+    k4_init<<<grid, block, 0, (cudaStream_t)stream>>>(p, x0, broadcast, sigma0);
+    cudaError_t ce = cudaGetLastError();
+    cudaSetDevice(prev);
+    e->n_measure = 1; e->step = 0;
+    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_init: ") + cudaGetErrorString(ce));
+    return ME_OK;
+}
+
+int me_k4_step(me_k4 *e, int64_t n_steps, const double *s_a, float *dbg_z, float *dbg_delta, void *stream) {
+    if (!e || !e->state || !s_a) return ME_ERR_INVALID;
+    if (n_steps <= 0) return ME_OK;
+    if (e->step + (unsigned long long)n_steps >= 0xffffffffull) return k4_fail(e, ME_ERR_INVALID, "step counter overflow");
+    K4Params p;
+    k4_base(e, p);
+    p.n_steps = n_steps; p.s_a = s_a; p.dbg_z = dbg_z; p.dbg_delta = dbg_delta;
+    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
+    static bool attr_set = false;
+    cudaError_t ce = cudaSuccess;
+    if (!attr_set) {
+        ce = cudaFuncSetAttribute(k4_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
+        attr_set = (ce == cudaSuccess);
+    }
+    if (ce == cudaSuccess) {
+        const long long n_tiles = e->cfg.n_chains / K4_TILE;
+        const int grid = (int)(n_tiles < e->n_sm ? n_tiles : e->n_sm);
+        k4_steps<<<grid, K4_THREADS, sizeof(K4Smem), (cudaStream_t)stream>>>(p);
+        ce = cudaGetLastError();
+    }
+    cudaSetDevice(prev);
+    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_steps: ") + cudaGetErrorString(ce));
+    e->step += (unsigned long long)n_steps;
+    return ME_OK;
+}
+
+int me_k4_measure(me_k4 *e, double *ts, int64_t ts_row, void *stream) {
+    if (!e || !e->state) return ME_ERR_INVALID;
+    e->n_measure += 1;
+    K4Params p;
+    k4_base(e, p);
+    p.ts = ts; p.ts_row = ts_row; p.record = ts != nullptr;
+    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
+    const int block = 128, grid = (int)((e->cfg.n_chains + block - 1) / block);
+    k4_measure<<<grid, block, 0, (cudaStream_t)stream>>>(p);
+    cudaError_t ce = cudaGetLastError();
+    cudaSetDevice(prev);
+    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_measure: ") + cudaGetErrorString(ce));
+    return ME_OK;
+}
+
+int me_k4_get_counters(me_k4 *e, int64_t *n_measure, uint64_t *step) {
+    if (!e) return ME_ERR_INVALID;
+    if (n_measure) *n_measure = e->n_measure;
+    if (step) *step = e->step;
+    return ME_OK;
+}
+
+const char *me_k4_last_error(me_k4 *e) { return e ? e->err.c_str() : g_k4_create_error.c_str(); }
+
+}  // extern "C"

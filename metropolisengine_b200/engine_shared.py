@@ -1,0 +1,300 @@
+"""Shared-covariance ensemble engine for large parameter spaces (BASELINE config 4: cylinder-style field with 1 real
+amplitude + 64 complex Fourier coefficients), driving the tcgen05 kernel of csrc/me_k4.cu.
+
+Same public surface as ``MetropolisEngine`` (reference metropolisengine/metropolis_engine.py: ``step_all`` ME:241-259,
+``measure`` ME:342-356, ``real_mean`` / ``complex_mean`` / ``covariance_matrix_*`` / ``observables_mean`` /
+``save_time_series`` / ``df``), with one difference that north_star asks for: the proposal covariance of the complex
+block is *pooled over the ensemble* and shared by all chains.  It is the running covariance of every (chain, measure)
+sample so far plus the reference's ``sigma^2/n`` regulariser (ME:418,425), used from the 50th measure on (ME:389,396);
+across GPUs its moments are summed with one NCCL all-reduce per measure (the path's only collective).
+
+Host work per measure (all stream-ordered, no host sync): per-chain means / observable means / time-series row in
+libme_b200 (me_k4_measure); pooled moments with one complex GEMM (torch -> cuBLAS, a plain library GEMM), 64x64
+Cholesky, and the BF16 re-packing of the factor into the UMMA operand layout (tensor plumbing).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import parallel
+from .engine import adaptation_constants, _ptr
+
+N_C = 64
+
+
+class SharedCovarianceEngine:
+    def __init__(self, energy_consts=(10.0, -1.0, 0.05, 1.0), reject_condition=True, initial_real_params=None,
+                 initial_complex_params=None, sampling_width=0.05, covariance_matrix_real=None,
+                 covariance_matrix_complex=None, params_names=None, target_acceptance=.3, temp=0, *, n_chains=128,
+                 seed=0, device=None, record=True, distributed=False, ts_chunk_rows=64):
+        """``energy_consts`` = (kappa, alpha, gamma, beta) of the cylinder-style energy;
+        ``reject_condition=True`` enables its hard wall ``|a| >= 1`` (legacy metropolis_engine.py:103,139)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("SharedCovarianceEngine needs a CUDA device: the hot path is CUDA-only (no CPU fallback)")
+        if temp is None or not temp >= 0:
+            raise AssertionError("temp must be >= 0")                                        # ME:92
+        self._lib = _lib.load()
+        self.launch_count = 0
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        lay = _lib.MeK4Layout()
+        self._lib.me_k4_layout_get(ctypes.byref(lay))
+        self._lay = lay
+        self.num_real_params, self.num_complex_params = 1, N_C
+        xr = np.zeros(1) if initial_real_params is None else np.asarray(initial_real_params, dtype=np.float64)
+        xc = (np.zeros(N_C, dtype=np.complex128) if initial_complex_params is None
+              else np.asarray(initial_complex_params, dtype=np.complex128))
+        if xr.shape[-1] != 1 or xc.shape[-1] != N_C:
+            raise ValueError("the shared-covariance path is built for 1 real + 64 complex parameters")
+        self.n_chains_total = int(n_chains)
+        self._rank, self._world = (parallel.world() if distributed else (0, 1))
+        lo, hi = parallel.shard_range(self.n_chains_total, self._rank, self._world)
+        self.chain_offset, self.n_chains = lo, hi - lo
+        self._distributed = bool(distributed) and self._world > 1
+        self.temp, self.target_acceptance = temp, target_acceptance
+        self.alpha, self.m, self.ratio = adaptation_constants(1, N_C, target_acceptance)
+        self.params_names = list(params_names) if params_names else ["param_" + str(i) for i in range(1 + N_C)]
+        self.observables_names = ["abs_param_" + str(i) for i in range(1 + N_C)] + ["param_0_squared"]
+        self.seed = int(seed)
+        self.df = None
+        cfg = _lib.MeK4Config(1, N_C, self.n_chains, self.chain_offset, float(temp), float(target_acceptance),
+                              self.ratio, self.seed, self.device.index, int(bool(reject_condition)),
+                              (ctypes.c_double * 4)(*[float(c) for c in energy_consts]))
+        h = ctypes.c_void_p()
+        rc = self._lib.me_k4_create(ctypes.byref(cfg), ctypes.byref(h))
+        if rc != 0:
+            msg = self._lib.me_k4_last_error(None).decode()
+            raise ValueError(msg) if rc == _lib.ME_ERR_INVALID else _lib.MeError(msg)
+        self._h = h
+        dev, f64 = self.device, torch.float64
+        self.state = torch.zeros((lay.WORDS, self.n_chains), dtype=f64, device=dev)
+        self._factor = torch.zeros((16, 128, 8), dtype=torch.bfloat16, device=dev)
+        self._s_a = torch.ones(1, dtype=f64, device=dev)
+        self._last_accept = torch.zeros(self.n_chains, dtype=torch.uint8, device=dev)
+        self._check(self._lib.me_k4_bind(self._h, _ptr(self.state), _ptr(self._factor), _ptr(self._last_accept)))
+        # shared covariances (ME:63-70): identity unless given
+        self._cov_c = (torch.eye(N_C, dtype=torch.complex128, device=dev) if covariance_matrix_complex is None
+                       else torch.as_tensor(np.asarray(covariance_matrix_complex, dtype=np.complex128), device=dev))
+        self._cov_a = torch.ones(1, dtype=f64, device=dev) if covariance_matrix_real is None else \
+            torch.as_tensor(np.asarray(covariance_matrix_real, dtype=np.float64).reshape(1), device=dev)
+        self._install_factor()
+        # pooled running moments about a fixed shift (the initial ensemble mean)
+        x0 = np.concatenate([xr.reshape(-1)[:1] if xr.ndim == 1 else [xr[:, 0].mean()],
+                             (xc if xc.ndim == 1 else xc.mean(0)).real, (xc if xc.ndim == 1 else xc.mean(0)).imag])
+        self._shift_a = float(x0[0])
+        self._shift_c = torch.as_tensor(x0[1:1 + N_C] + 1j * x0[1 + N_C:], dtype=torch.complex128, device=dev)
+        self._mom = torch.zeros(4 + N_C + N_C * N_C, dtype=torch.complex128, device=dev)   # count, -, sum a, sum a^2, sum c, sum c c^H
+        self._count = 0
+        per_chain = xr.ndim == 2 or xc.ndim == 2
+        if per_chain:
+            full = np.zeros((lay.D, self.n_chains_total))
+            full[0] = xr[:, 0] if xr.ndim == 2 else xr[0]
+            full[1:1 + N_C] = xc.real.T if xc.ndim == 2 else xc.real[:, None]
+            full[1 + N_C:] = xc.imag.T if xc.ndim == 2 else xc.imag[:, None]
+            x0_dev = torch.tensor(np.ascontiguousarray(full[:, lo:hi]), dtype=f64, device=dev)
+        else:
+            x0_dev = torch.tensor(x0, dtype=f64, device=dev)
+        self._sampling_width0 = float(sampling_width)
+        self._launch(self._lib.me_k4_init(self._h, _ptr(x0_dev), 0 if per_chain else 1, self._sampling_width0,
+                                          self._stream()))
+        self.record = bool(record)
+        self._ts_chunks, self._ts_chunk_rows = [], int(ts_chunk_rows)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.me_k4_last_error(self._h).decode()
+            raise ValueError(msg) if rc == _lib.ME_ERR_INVALID else _lib.MeError(msg)
+
+    def _launch(self, rc):
+        self._check(rc)
+        self.launch_count += 1
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None:
+            self._lib.me_k4_destroy(h)
+            self._h = None
+
+    def _install_factor(self):
+        """C_c = G G^H -> real embedding of conj(G)/sqrt2 in interleaved (Re, Im) coordinates -> BF16 in the UMMA
+        canonical K-major layout [k-chunk][n][8]; s_a = sqrt(C_a).  Stream-ordered, no host sync."""
+        G = torch.linalg.cholesky_ex(self._cov_c)[0]
+        gr, gi = G.real / math.sqrt(2.0), G.imag / math.sqrt(2.0)
+        B = torch.zeros((2 * N_C, 2 * N_C), dtype=torch.float64, device=self.device)
+        B[0::2, 0::2] = gr
+        B[0::2, 1::2] = gi
+        B[1::2, 0::2] = -gi
+        B[1::2, 1::2] = gr
+        self._B = B
+        self._factor.copy_(B.view(128, 16, 8).permute(1, 0, 2).to(torch.bfloat16))
+        self._s_a.copy_(torch.sqrt(self._cov_a))
+
+    @property
+    def measure_step_counter(self):
+        n, s = ctypes.c_int64(), ctypes.c_uint64()
+        self._lib.me_k4_get_counters(self._h, ctypes.byref(n), ctypes.byref(s))
+        return n.value
+
+    @property
+    def steps_done(self):
+        n, s = ctypes.c_int64(), ctypes.c_uint64()
+        self._lib.me_k4_get_counters(self._h, ctypes.byref(n), ctypes.byref(s))
+        return s.value
+
+    # ------------------------------------------------------------------ hot path
+    def step(self, k=1, _dbg=None):
+        dz = dd = None
+        if _dbg is not None:
+            dz, dd = _dbg
+        self._launch(self._lib.me_k4_step(self._h, int(k), _ptr(self._s_a), _ptr(dz), _ptr(dd), self._stream()))
+
+    def step_all(self):
+        self.step(1)
+        return self._last_accept.bool()
+
+    def _ts_slot(self):
+        if not self._ts_chunks or self._ts_chunks[-1][1] == self._ts_chunks[-1][0].shape[0]:
+            t = torch.empty((self._ts_chunk_rows, self._lay.TS_COLS, self.n_chains), dtype=torch.float64,
+                            device=self.device)
+            self._ts_chunks.append([t, 0])
+        t, used = self._ts_chunks[-1]
+        self._ts_chunks[-1][1] = used + 1
+        return t, used
+
+    def measure(self):
+        """means / observable means / time-series row per chain, then the pooled covariance update that every
+        chain's next proposals share."""
+        if self.record:
+            t, row = self._ts_slot()
+            self._launch(self._lib.me_k4_measure(self._h, _ptr(t), row, self._stream()))
+        else:
+            self._launch(self._lib.me_k4_measure(self._h, None, 0, self._stream()))
+        n = self.measure_step_counter
+        lay = self._lay
+        a = self.state[lay.X] - self._shift_a
+        c = torch.complex(self.state[lay.X + 1:lay.X + 1 + N_C], self.state[lay.X + 1 + N_C:lay.X + 1 + 2 * N_C]) \
+            - self._shift_c[:, None]
+        inc = torch.cat([
+            torch.tensor([float(self.n_chains)], dtype=torch.complex128, device=self.device),
+            self.state[lay.SIG].sum().reshape(1).to(torch.complex128),
+            a.sum().reshape(1).to(torch.complex128), (a * a).sum().reshape(1).to(torch.complex128),
+            c.sum(dim=1), (c @ c.conj().t()).reshape(-1)])
+        if self._distributed:
+            v = torch.view_as_real(inc)
+            parallel.allreduce_sum_(v)
+            inc = torch.view_as_complex(v)
+        sig_mean = (inc[1].real / inc[0].real)
+        self._mom[0] += inc[0]
+        self._mom[2:] += inc[2:]
+        if n > 50:                                                                            # ME:389,396
+            N = self._mom[0].real
+            small = sig_mean * sig_mean / n                                                   # ME:418,425
+            a1, a2 = self._mom[2].real, self._mom[3].real
+            self._cov_a = ((a2 - a1 * a1 / N) / (N - 1) + small).reshape(1)
+            s1 = self._mom[4:4 + N_C]
+            s2 = self._mom[4 + N_C:].reshape(N_C, N_C)
+            cov = (s2 - torch.outer(s1, s1.conj()) / N) / (N - 1)
+            self._cov_c = cov + small * torch.eye(N_C, dtype=torch.complex128, device=self.device)
+            self._install_factor()
+
+    def run(self, n_measures, steps_per_measure):
+        for _ in range(int(n_measures)):
+            self.step(int(steps_per_measure))
+            self.measure()
+
+    # ------------------------------------------------------------------ reads (reference attribute names)
+    def _pooled(self, t):
+        s = t.sum(dim=-1)
+        if self._distributed:
+            parallel.allreduce_sum_(s)
+        return (s / self.n_chains_total).cpu().numpy()
+
+    @property
+    def real_params_per_chain(self):
+        return self.state[self._lay.X:self._lay.X + 1].t()
+
+    @property
+    def complex_params_per_chain(self):
+        x = self._lay.X
+        return torch.complex(self.state[x + 1:x + 1 + N_C], self.state[x + 1 + N_C:x + 1 + 2 * N_C]).t()
+
+    @property
+    def sampling_width_per_chain(self):
+        return self.state[self._lay.SIG]
+
+    @property
+    def energy_per_chain(self):
+        return self.state[self._lay.E]
+
+    @property
+    def accept_count_per_chain(self):
+        return self.state[self._lay.NACC]
+
+    @property
+    def real_mean(self):
+        return self._pooled(self.state[self._lay.MEAN:self._lay.MEAN + 1])
+
+    @property
+    def complex_mean(self):
+        m = self._lay.MEAN
+        return self._pooled(torch.complex(self.state[m + 1:m + 1 + N_C], self.state[m + 1 + N_C:m + 1 + 2 * N_C]))
+
+    @property
+    def observables_mean(self):
+        return self._pooled(self.state[self._lay.OBSM:self._lay.OBSM + 2 + N_C])
+
+    @property
+    def covariance_matrix_real(self):
+        return self._cov_a.reshape(1, 1).cpu().numpy()
+
+    @property
+    def covariance_matrix_complex(self):
+        return self._cov_c.cpu().numpy()
+
+    @property
+    def sampling_width(self):
+        return float(self._pooled(self.state[self._lay.SIG:self._lay.SIG + 1])[0])
+
+    real_group_sampling_width = sampling_width
+    complex_group_sampling_width = sampling_width
+
+    @property
+    def energy_total(self):
+        return float(self._pooled(self.state[self._lay.E:self._lay.E + 1])[0])
+
+    @property
+    def acceptance_rate(self):
+        return float(self._pooled(self.state[self._lay.NACC:self._lay.NACC + 1])[0]) / max(self.steps_done, 1)
+
+    def time_series(self):
+        parts = [t[:used] for t, used in self._ts_chunks if used]
+        if not parts:
+            return torch.empty((0, self._lay.TS_COLS, self.n_chains), dtype=torch.float64, device=self.device)
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+
+    def save_time_series(self, chain=0):
+        """``self.df`` for one chain, reference column order (ME:466-478)."""
+        import pandas
+        rows = self.time_series()[:, :, chain].cpu().numpy()
+        d = self._lay.D
+        a, c = rows[:, 0], rows[:, 1:1 + N_C] + 1j * rows[:, 1 + N_C:d]
+        cols = {self.observables_names[0]: np.abs(a)}
+        for j in range(N_C):
+            cols[self.observables_names[1 + j]] = np.abs(c[:, j])
+        cols[self.observables_names[1 + N_C]] = a * a
+        cols["total_energy"] = rows[:, d]
+        cols[self.params_names[0]] = a
+        cols["real_group_sampling_width"] = rows[:, d + 1]
+        for j in range(N_C):
+            cols[self.params_names[1 + j]] = c[:, j]
+        cols["complex_group_sampling_width"] = rows[:, d + 1]
+        self.df = pandas.DataFrame.from_dict(cols)
+        return self.df

@@ -40,10 +40,11 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_binding_structs_match_header_field_order(lib):
     text = open(HEADER).read()
-    for cname, struct in (("me_config", lib.MeConfig), ("me_layout", lib.MeLayout), ("me_buffers", lib.MeBuffers)):
+    for cname, struct in (("me_config", lib.MeConfig), ("me_layout", lib.MeLayout), ("me_buffers", lib.MeBuffers),
+                          ("me_k4_config", lib.MeK4Config)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-        fields = re.findall(r"\b(\w+);", body)
+        fields = re.findall(r"\b(\w+)(?:\[\d+\])?;", body)
         assert fields == [f[0] for f in struct._fields_], cname
 
 

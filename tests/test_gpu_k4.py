@@ -1,0 +1,152 @@
+"""Shared-covariance tensor-core path (BASELINE config 4 shape: 1 real + 64 complex), csrc/me_k4.cu.
+
+The reference has no shared-covariance mode (it is one chain), so parity here is: (i) the tensor-core contraction
+equals B.z computed in float64 from the same BF16 operands (FP32 accumulation tolerance 2e-5 relative to |B||z|);
+(ii) the in-kernel normals are standard; (iii) ensembles sample the exact stationary law of decoupled Gaussian
+modes (z-tests, tolerance stated per assertion) and agree with the per-chain FP64 C oracle of the same energy;
+(iv) hard wall, adaptation target, sharding invariance."""
+import numpy as np
+import pytest
+import torch
+from scipy import stats
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(**kw):
+    import metropolisengine_b200 as me
+    return me.SharedCovarianceEngine(**kw)
+
+
+def _rand_cov(n, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    c = a @ a.conj().T / n + 0.5 * np.eye(n)
+    return c
+
+
+@pytest.mark.parametrize("with_cov", [False, True])
+def test_tensor_core_increments_match_float64_matmul(with_cov):
+    n = 256
+    kw = dict(energy_consts=(10.0, 1.0, 0.05, 0.0), temp=.1, n_chains=n, seed=3)
+    if with_cov:
+        kw["covariance_matrix_complex"] = _rand_cov(64, 1)
+    eng = _engine(**kw)
+    dz = torch.zeros((128, n), dtype=torch.float32, device="cuda")
+    dd = torch.zeros((128, n), dtype=torch.float32, device="cuda")
+    eng.step(1, _dbg=(dz, dd))
+    torch.cuda.synchronize()
+    z = dz.double().cpu().numpy()                     # BF16 values of the normals, [k][chain]
+    B = eng._B.to(torch.bfloat16).double().cpu().numpy()   # BF16 values of the factor, [n][k]
+    want = B @ z
+    got = dd.double().cpu().numpy()
+    scale = np.abs(B) @ np.abs(z)
+    assert np.all(np.abs(got - want) <= 2e-5 * scale + 1e-30)
+    if with_cov:
+        # the factor reproduces the reference's proposal law CN(0, conj(C)): E[w w^H] = conj(C) (ME:288-302)
+        Bf = eng._B.cpu().numpy()
+        emb = Bf @ Bf.T                                 # covariance of the embedded increments, interleaved coords
+        C = kw["covariance_matrix_complex"]
+        rr, ii, ir = emb[0::2, 0::2], emb[1::2, 1::2], emb[1::2, 0::2]
+        assert np.allclose(rr + ii, np.conj(C).real, atol=1e-12)
+        assert np.allclose(ir - ir.T, np.conj(C).imag, atol=1e-12)
+
+
+def test_in_kernel_normals_are_standard_and_symmetric():
+    n = 4096
+    eng = _engine(energy_consts=(10.0, 1.0, 0.05, 0.0), temp=.1, n_chains=n, seed=11)
+    dz = torch.zeros((128, n), dtype=torch.float32, device="cuda")
+    dd = torch.zeros((128, n), dtype=torch.float32, device="cuda")
+    eng.step(1, _dbg=(dz, dd))
+    z = dz.double().cpu().numpy()
+    flat = z.reshape(-1)
+    assert abs(flat.mean()) < 5 / np.sqrt(flat.size)
+    assert abs(flat.var() - 1.0) < 5 * np.sqrt(2.0 / flat.size) + 2e-5
+    assert stats.kstest(flat[::7], "norm").pvalue > 1e-4          # BF16 rounding is far below the KS resolution here
+    cm = np.corrcoef(z[:16])                                        # different coordinates are uncorrelated
+    assert np.max(np.abs(cm - np.eye(16))) < 6 / np.sqrt(n)
+    assert abs((flat > 0).mean() - 0.5) < 5 * 0.5 / np.sqrt(flat.size)
+
+
+def test_gaussian_modes_reach_exact_stationary_variances():
+    """beta = 0 and a stiff amplitude decouple the modes: Re/Im c_q ~ N(0, T / (2 (alpha + gamma q^2 (1+a^2)))),
+    a ~ 0.  Pooled variances over 8192 chains after burn-in, z-test with sd sqrt(2/N_eff)."""
+    n, T = 8192, 0.1
+    kappa, alpha, gamma = 500.0, 1.0, 0.05
+    eng = _engine(energy_consts=(kappa, alpha, gamma, 0.0), temp=T, n_chains=n, seed=5, record=False)
+    eng.run(150, 10)
+    acc0 = eng.accept_count_per_chain.clone()
+    eng.run(30, 10)
+    acc = ((eng.accept_count_per_chain - acc0).sum() / (300.0 * n)).item()
+    assert 0.24 < acc < 0.36, acc                                   # Robbins-Monro target 0.3 (ME:101)
+    c = eng.complex_params_per_chain.cpu().numpy()                  # [chains, 64]
+    q = np.arange(64) - 32
+    exact = T / (2.0 * (alpha + gamma * q ** 2))                    # per real component (a^2 ~ T/(2 kappa) negligible)
+    for part in (c.real, c.imag):
+        v = part.var(axis=0)
+        z = (v - exact) / (exact * np.sqrt(2.0 / n))
+        assert np.max(np.abs(z)) < 5.0, (np.argmax(np.abs(z)), np.max(np.abs(z)))
+        assert np.max(np.abs(part.mean(axis=0)) / np.sqrt(exact / n)) < 5.0
+    # after n > 50 the shared covariance is the pooled running covariance: its diagonal tracks 2 * exact
+    diag = np.real(np.diag(eng.covariance_matrix_complex))
+    assert np.all(diag > 0.5 * 2 * exact) and np.all(diag < 3.0 * 2 * exact + 0.2)
+
+
+def test_hard_wall_and_api_surface():
+    n = 256
+    eng = _engine(energy_consts=(0.0, 1.0, 0.05, 1.0), temp=.5, n_chains=n, seed=9,
+                  initial_real_params=np.array([0.95]), sampling_width=0.3)
+    for _ in range(20):
+        acc = eng.step_all()
+    assert acc.dtype == torch.bool and acc.shape == (n,)
+    eng.run(5, 20)
+    a = eng.real_params_per_chain.cpu().numpy()
+    assert np.all(np.abs(a) < 1.0)                                   # |a| >= 1 is never accepted (ME:247)
+    assert eng.real_mean.shape == (1,) and eng.complex_mean.shape == (64,)
+    assert eng.covariance_matrix_complex.shape == (64, 64) and eng.observables_mean.shape == (66,)
+    df = eng.save_time_series()
+    assert len(df) == 5 and list(df.columns)[:2] == ["abs_param_0", "abs_param_1"]
+    assert list(df.columns)[-1] == "complex_group_sampling_width" and "total_energy" in df.columns
+    # energy bookkeeping: the stored energy equals the energy of the stored state
+    x = eng.state[:129].cpu().numpy()
+    a0, c = x[0], x[1:65] + 1j * x[65:129]
+    m2 = np.abs(c) ** 2
+    qq = (np.arange(64) - 32)[:, None] ** 2
+    e = 0.0 * a0 ** 2 + (1.0 * m2.sum(0) + 0.05 * (1 + a0 ** 2) * (qq * m2).sum(0)) + (1.0 / 128.0) * m2.sum(0) ** 2
+    assert np.allclose(eng.energy_per_chain.cpu().numpy(), e, rtol=1e-10)
+
+
+def test_results_do_not_depend_on_tiling_or_sharding():
+    import metropolisengine_b200 as me
+    kw = dict(energy_consts=(10.0, -1.0, 0.05, 1.0), temp=.1, seed=21, record=False)
+    full = me.SharedCovarianceEngine(n_chains=512, **kw)
+    full.step(7)
+    lo = me.SharedCovarianceEngine(n_chains=256, **kw)
+    lo.step(7)
+    assert torch.equal(full.state[:, :256], lo.state)               # chain i depends on (seed, i) only
+
+
+def test_agrees_with_per_chain_fp64_oracle_statistically():
+    """Same energy (full cylinder form incl. the quartic term and the wall) in the C oracle with per-chain FP64
+    proposals: mean energy and mean |c_q|^2 of the two ensembles agree (z-test, 5 sigma)."""
+    from oracle import c_oracle as co
+    T, consts = 0.1, (10.0, -1.0, 0.05, 1.0)
+    n = 2048
+    eng = _engine(energy_consts=consts, temp=T, n_chains=n, seed=2, record=False)
+    eng.run(120, 10)
+    c = eng.complex_params_per_chain.cpu().numpy()
+    e_gpu = eng.energy_per_chain.cpu().numpy()
+    M = 48
+    e_ref, m2_ref = [], []
+    for ch in range(M):
+        o = co.CChain(1, 64, "cylinder", consts=consts, temp=T, x0=np.zeros(129), use_reject=True)
+        o.run(120, 10, True, seed=100, chain_id=ch)
+        e_ref.append(o.energy)
+        m2_ref.append(o.x[1:65] ** 2 + o.x[65:129] ** 2)
+    e_ref, m2_ref = np.array(e_ref), np.array(m2_ref)
+    se = np.sqrt(e_gpu.var() / n + e_ref.var() / M)
+    assert abs(e_gpu.mean() - e_ref.mean()) < 5 * se, (e_gpu.mean(), e_ref.mean(), se)
+    low = slice(28, 37)                                              # the soft (small |q|) modes carry the signal
+    g, r = (np.abs(c) ** 2)[:, low].mean(1), m2_ref[:, low].mean(1)
+    se = np.sqrt(g.var() / n + r.var() / M)
+    assert abs(g.mean() - r.mean()) < 5 * se, (g.mean(), r.mean(), se)
