@@ -194,7 +194,7 @@ typedef struct me_k4_config {
     double consts[4];           /* cylinder energy: kappa, alpha, gamma, beta */
 } me_k4_config;
 typedef struct me_k4_layout {
-    int32_t X, E, SIG, MEAN, OBSM, NACC, STATUS, WORDS, D, TS_COLS, N_COMPLEX, TILE, FACTOR_BYTES;
+    int32_t X, E, SIG, MEAN, OBSM, NACC, STATUS, WORDS, D, TS_COLS, N_COMPLEX, TILE, FACTOR_BYTES, MOM_WORDS;
 } me_k4_layout;
 int me_k4_layout_get(me_k4_layout *out);
 int me_k4_create(const me_k4_config *cfg, me_k4 **out);
@@ -207,6 +207,17 @@ int me_k4_step(me_k4 *eng, int64_t n_steps, const double *s_a, float *dbg_z, flo
 /* measure() without the covariance recursion (the caller pools it): means, observable means, one row
  * ts[(row * TS_COLS + col) * n_chains + chain]. */
 int me_k4_measure(me_k4 *eng, double *ts, int64_t ts_row, void *stream);
+/* Pooled moments of the current states of this handle's chains, deterministic (fixed summation order):
+ * inc[MOM_WORDS] complex (double pairs) = [chains, sum sigma, sum a, sum a^2, sum c[64], sum c c^H[64x64]] about
+ * shift[129] (a, Re c, Im c).  scratch needs n_sm * MOM_WORDS * 2 doubles.  The caller all-reduces `inc` across
+ * ranks (NCCL) and adds it to its running moments. */
+int me_k4_moments(me_k4 *eng, const double *shift, double *scratch, int64_t scratch_doubles, double *inc, void *stream);
+/* Pooled moments -> shared covariance (+ sigma^2/n regulariser, ME:418,425) -> Cholesky -> BF16 operand, one
+ * launch, no host sync.  mom / inc are complex (double pairs): mom = [N, -, sum a, sum a^2, sum c[64], sum c c^H
+ * [64x64]] about a fixed shift, inc = [chains measured now, sum of their sigma]; cov_c receives the 64x64 complex
+ * covariance, cov_a the variance of the real parameter, s_a its square root, status != 0 if not positive definite. */
+int me_k4_refactor(me_k4 *eng, const double *mom, const double *inc, double *cov_c, double *cov_a, void *factor_bf16,
+                   double *s_a, int32_t *status, void *stream);
 int me_k4_get_counters(me_k4 *eng, int64_t *n_measure, uint64_t *step);
 const char *me_k4_last_error(me_k4 *eng);
 

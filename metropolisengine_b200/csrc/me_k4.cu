@@ -410,38 +410,213 @@ __global__ void k4_init(K4Params p, const double *x0, int broadcast, double sigm
 /* measure (ME:342-356 without the per-chain covariance, which is shared): running means (ME:404-410), observable
  * means (ME:412-414, 458-463), one time-series row [129 params, E, sigma].  n = counter after the increment. */
 __global__ void k4_measure(K4Params p) {
+    /* one thread per (slot, chain): slot j < 64 = complex mode j, slot 64 = real parameter + energy + sigma */
     const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
     if (ch >= p.n_chains) return;
     const long long ld = p.ld;
     const double dn = (double)p.n_meas, inv_n = 1.0 / dn, shrink = (dn - 1.0) * inv_n;
     double *row = p.record ? p.ts + p.ts_row * (long long)(K4_D + 2) * ld + ch : nullptr;
-    const double a = p.state[(long long)K4_X * ld + ch];
-    {
+    if (j == K4_NC) {
+        const double a = p.state[(long long)K4_X * ld + ch];
         double *mp = &p.state[(long long)K4_MEAN * ld + ch];
         *mp = *mp * shrink + a * inv_n;
         double *o0 = &p.state[(long long)K4_OBSM * ld + ch], *o1 = &p.state[(long long)(K4_OBSM + 1 + K4_NC) * ld + ch];
         *o0 = *o0 * shrink + fabs(a) * inv_n;
         *o1 = *o1 * shrink + (a * a) * inv_n;
-        if (row) __stcs(row, a);
-    }
-    for (int j = 0; j < K4_NC; j++) {
-        const double re = p.state[(long long)(K4_X + 1 + j) * ld + ch];
-        const double im = p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch];
-        double *mr = &p.state[(long long)(K4_MEAN + 1 + j) * ld + ch];
-        double *mi = &p.state[(long long)(K4_MEAN + 1 + K4_NC + j) * ld + ch];
-        *mr = *mr * shrink + re * inv_n;
-        *mi = *mi * shrink + im * inv_n;
-        double *ob = &p.state[(long long)(K4_OBSM + 1 + j) * ld + ch];
-        *ob = *ob * shrink + hypot(re, im) * inv_n;
         if (row) {
-            __stcs(row + (long long)(1 + j) * ld, re);
-            __stcs(row + (long long)(1 + K4_NC + j) * ld, im);
+            __stcs(row, a);
+            __stcs(row + (long long)K4_D * ld, p.state[(long long)K4_E * ld + ch]);
+            __stcs(row + (long long)(K4_D + 1) * ld, p.state[(long long)K4_SIG * ld + ch]);
         }
+        return;
     }
+    const double re = p.state[(long long)(K4_X + 1 + j) * ld + ch];
+    const double im = p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch];
+    double *mr = &p.state[(long long)(K4_MEAN + 1 + j) * ld + ch];
+    double *mi = &p.state[(long long)(K4_MEAN + 1 + K4_NC + j) * ld + ch];
+    *mr = *mr * shrink + re * inv_n;
+    *mi = *mi * shrink + im * inv_n;
+    double *ob = &p.state[(long long)(K4_OBSM + 1 + j) * ld + ch];
+    *ob = *ob * shrink + hypot(re, im) * inv_n;
     if (row) {
-        __stcs(row + (long long)K4_D * ld, p.state[(long long)K4_E * ld + ch]);
-        __stcs(row + (long long)(K4_D + 1) * ld, p.state[(long long)K4_SIG * ld + ch]);
+        __stcs(row + (long long)(1 + j) * ld, re);
+        __stcs(row + (long long)(1 + K4_NC + j) * ld, im);
     }
+}
+
+/* Pooled moments of the current states, deterministic two-stage reduction (no atomics: the covariance feeds the
+ * proposals, so run-to-run bit reproducibility needs a fixed summation order).
+ * Stage 1: CTA b sums its slice of chains into part[b][K4_MOMW] (complex): [0] chains, [1] sum sigma, [2] sum a,
+ *          [3] sum a^2, [4..68) sum c_i, [68..) sum c_i conj(c_j), all about the shift (shift[0] = a, then Re c, Im c).
+ *          256 threads; thread t owns the 4x4 block (i0 = 4 (t / 16), j0 = 4 (t % 16)) of the 64x64 outer product;
+ *          chains are staged through shared memory 64 at a time.
+ * Stage 2: out[w] = sum_b part[b][w] in CTA order. */
+constexpr int K4_MOMW = 4 + K4_NC + K4_NC * K4_NC;
+constexpr int K4_MOM_CHUNK = 32;
+
+__global__ void __launch_bounds__(256) k4_moments_stage1(K4Params p, const double *shift, double2 *part,
+                                                         long long chains_per_cta) {
+    /* thread t: half h = t / 128 of each staged chunk of chains, 8x4 block (i0 = 8 (u / 16), j0 = 4 (u % 16)),
+       u = t % 128, of the 64x64 outer product; the two halves are combined through shared memory at the end */
+    __shared__ double cr[K4_NC][K4_MOM_CHUNK + 1], ci[K4_NC][K4_MOM_CHUNK + 1];
+    __shared__ double red[256];
+    const int tid = threadIdx.x, h = tid >> 7, u = tid & 127;
+    const long long lo = (long long)blockIdx.x * chains_per_cta;
+    long long hi = lo + chains_per_cta;
+    if (hi > p.n_chains) hi = p.n_chains;
+    const long long ld = p.ld;
+    const int i0 = 8 * (u / 16), j0 = 4 * (u % 16);
+    double ar[8][4], ai[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) ar[a][b] = ai[a][b] = 0.0;
+    double s1r = 0.0, s1i = 0.0;          /* thread t < 64: sum of c_t */
+    double sa = 0.0, sa2 = 0.0, ssig = 0.0;
+    for (long long base = lo; base < hi; base += K4_MOM_CHUNK) {
+        const int cnt = (int)((hi - base) < K4_MOM_CHUNK ? (hi - base) : K4_MOM_CHUNK);
+        __syncthreads();
+        for (int e = tid; e < K4_NC * K4_MOM_CHUNK; e += 256) {
+            const int j = e / K4_MOM_CHUNK, c = e % K4_MOM_CHUNK;
+            const bool ok = c < cnt;
+            cr[j][c] = ok ? p.state[(long long)(K4_X + 1 + j) * ld + base + c] - shift[1 + j] : 0.0;
+            ci[j][c] = ok ? p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + base + c] - shift[1 + K4_NC + j] : 0.0;
+        }
+        if (tid < cnt) {
+            const double a = p.state[(long long)K4_X * ld + base + tid] - shift[0];
+            sa += a; sa2 += a * a; ssig += p.state[(long long)K4_SIG * ld + base + tid];
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int c = h * (K4_MOM_CHUNK / 2); c < (h + 1) * (K4_MOM_CHUNK / 2); c++) {
+            double xr[8], xi[8], yr[4], yi[4];
+#pragma unroll
+            for (int a = 0; a < 8; a++) { xr[a] = cr[i0 + a][c]; xi[a] = ci[i0 + a][c]; }
+#pragma unroll
+            for (int b = 0; b < 4; b++) { yr[b] = cr[j0 + b][c]; yi[b] = ci[j0 + b][c]; }
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {     /* x conj(y) */
+                    ar[a][b] = fma(xr[a], yr[b], fma(xi[a], yi[b], ar[a][b]));
+                    ai[a][b] = fma(xi[a], yr[b], fma(-xr[a], yi[b], ai[a][b]));
+                }
+        }
+        if (tid < K4_NC)
+            for (int c = 0; c < K4_MOM_CHUNK; c++) { s1r += cr[tid][c]; s1i += ci[tid][c]; }
+    }
+    double2 *out = part + (long long)blockIdx.x * K4_MOMW;
+    /* combine the two chain halves in a fixed order: half 1 writes, half 0 adds */
+    if (h == 1) {
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) out[4 + K4_NC + (i0 + a) * K4_NC + (j0 + b)] = make_double2(ar[a][b], ai[a][b]);
+    }
+    __syncthreads();
+    if (h == 0) {
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                double2 *o = &out[4 + K4_NC + (i0 + a) * K4_NC + (j0 + b)];
+                *o = make_double2(ar[a][b] + o->x, ai[a][b] + o->y);
+            }
+    }
+    if (tid < K4_NC) out[4 + tid] = make_double2(s1r, s1i);
+    /* the three scalar sums: fixed-order tree over the staging threads */
+    for (int which = 0; which < 3; which++) {
+        __syncthreads();
+        red[tid] = (tid < K4_MOM_CHUNK) ? (which == 0 ? ssig : (which == 1 ? sa : sa2)) : 0.0;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+        if (tid == 0) out[1 + which] = make_double2(red[0], 0.0);
+    }
+    if (tid == 0) out[0] = make_double2((double)(hi > lo ? hi - lo : 0), 0.0);
+}
+
+__global__ void k4_moments_stage2(const double2 *part, int n_parts, double2 *out) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= K4_MOMW) return;
+    double re = 0.0, im = 0.0;
+    for (int b = 0; b < n_parts; b++) { re += part[(long long)b * K4_MOMW + w].x; im += part[(long long)b * K4_MOMW + w].y; }
+    out[w] = make_double2(re, im);
+}
+
+/* Pooled covariance -> shared proposal factor, one CTA (runs once per measure after the 50th, ME:389,396).
+ * mom (complex, as double pairs): [0] sample count N, [2] sum a, [3] sum a^2, [4..68) sum c, [68..) sum c c^H
+ * (about a fixed shift); inc: [0] chains measured now, [1] sum of their sigma.  Computes
+ *   C_c = (S2 - S1 S1^H / N)/(N-1) + small I,  small = mean(sigma)^2 / n   (the regulariser of ME:418,425),
+ * its Cholesky factor G (right-looking, in shared memory), the BF16 UMMA operand of me_k4_step, and the same for
+ * the real parameter.  status: nonzero if a pivot was not positive. */
+__global__ void __launch_bounds__(256) k4_refactor(const double2 *mom, const double2 *inc, long long n_meas,
+                                                   double2 *cov_c, double *cov_a, __nv_bfloat16 *factor, double *s_a,
+                                                   int *status) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double2(*A)[K4_NC] = reinterpret_cast<double2(*)[K4_NC]>(smem_raw);
+    __shared__ double piv;
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    const double N = mom[0].x;
+    const double sm = inc[1].x / inc[0].x;
+    const double small = sm * sm / (double)n_meas;
+    const double2 *s1 = mom + 4, *s2 = mom + 4 + K4_NC;
+    if (tid == 0) bad = 0;
+    for (int e = tid; e < K4_NC * K4_NC; e += blockDim.x) {
+        const int i = e / K4_NC, j = e % K4_NC;
+        /* s1_i conj(s1_j) */
+        const double pr = s1[i].x * s1[j].x + s1[i].y * s1[j].y, pi = s1[i].y * s1[j].x - s1[i].x * s1[j].y;
+        double2 v;
+        v.x = (s2[e].x - pr / N) / (N - 1.0) + (i == j ? small : 0.0);
+        v.y = (s2[e].y - pi / N) / (N - 1.0);
+        A[i][j] = v;
+        cov_c[e] = v;
+    }
+    if (tid == 0) {
+        const double va = (mom[3].x - mom[2].x * mom[2].x / N) / (N - 1.0) + small;
+        *cov_a = va;
+        *s_a = sqrt(va);
+    }
+    __syncthreads();
+    for (int j = 0; j < K4_NC; j++) {
+        if (tid == 0) {
+            double d = A[j][j].x;
+            if (!(d > 0.0)) { bad = 1; d = small > 0.0 ? small : 1e-300; }
+            piv = sqrt(d);
+            A[j][j].x = piv; A[j][j].y = 0.0;
+        }
+        __syncthreads();
+        const double inv = 1.0 / piv;
+        for (int i = j + 1 + tid; i < K4_NC; i += blockDim.x) { A[i][j].x *= inv; A[i][j].y *= inv; }
+        __syncthreads();
+        const int rem = K4_NC - 1 - j;              /* trailing (i, k), j < k <= i */
+        for (int e = tid; e < rem * rem; e += blockDim.x) {
+            const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+            if (k <= i) {                           /* A_ik -= G_ij conj(G_kj) */
+                const double2 p = A[i][j], q = A[k][j];
+                A[i][k].x -= p.x * q.x + p.y * q.y;
+                A[i][k].y -= p.y * q.x - p.x * q.y;
+            }
+        }
+        __syncthreads();
+    }
+    /* B[2i][2j] = Gr/sqrt2, B[2i][2j+1] = Gi/sqrt2, B[2i+1][2j] = -Gi/sqrt2, B[2i+1][2j+1] = Gr/sqrt2; stored
+       BF16 at [k/8][n][k%8] */
+    const double rs = 0.70710678118654752440;
+    for (int e = tid; e < K4_N * K4_N; e += blockDim.x) {
+        const int nrow = e / K4_N, k = e % K4_N;
+        const int i = nrow >> 1, jj = k >> 1;
+        double v = 0.0;
+        if (jj <= i) {
+            const double2 gij = A[i][jj];
+            const bool ro = nrow & 1, ko = k & 1;
+            v = (ro == ko) ? gij.x : (ro ? -gij.y : gij.y);
+            if (jj == i && ro != ko) v = 0.0;       /* diagonal of G is real */
+        }
+        factor[(k >> 3) * (K4_N * 8) + nrow * 8 + (k & 7)] = __double2bfloat16(v * rs);
+    }
+    if (tid == 0 && status) *status = bad;
 }
 
 }  // namespace
@@ -493,7 +668,7 @@ int me_k4_layout_get(me_k4_layout *o) {
     if (!o) return ME_ERR_INVALID;
     o->X = K4_X; o->E = K4_E; o->SIG = K4_SIG; o->MEAN = K4_MEAN; o->OBSM = K4_OBSM; o->NACC = K4_NACC;
     o->STATUS = K4_STATUS; o->WORDS = K4_WORDS; o->D = K4_D; o->TS_COLS = K4_D + 2; o->N_COMPLEX = K4_NC;
-    o->TILE = K4_TILE; o->FACTOR_BYTES = K4_N * K4_N * 2;
+    o->TILE = K4_TILE; o->FACTOR_BYTES = K4_N * K4_N * 2; o->MOM_WORDS = K4_MOMW;
     return ME_OK;
 }
 
@@ -568,11 +743,52 @@ int me_k4_measure(me_k4 *e, double *ts, int64_t ts_row, void *stream) {
     k4_base(e, p);
     p.ts = ts; p.ts_row = ts_row; p.record = ts != nullptr;
     int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    const int block = 128, grid = (int)((e->cfg.n_chains + block - 1) / block);
+    const int block = 256;
+    const dim3 grid((unsigned)((e->cfg.n_chains + block - 1) / block), K4_NC + 1);
     k4_measure<<<grid, block, 0, (cudaStream_t)stream>>>(p);
     cudaError_t ce = cudaGetLastError();
     cudaSetDevice(prev);
     if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_measure: ") + cudaGetErrorString(ce));
+    return ME_OK;
+}
+
+int me_k4_moments(me_k4 *e, const double *shift, double *scratch, int64_t scratch_doubles, double *inc, void *stream) {
+    if (!e || !e->state || !shift || !scratch || !inc) return ME_ERR_INVALID;
+    const int n_parts = e->n_sm < 1 ? 1 : e->n_sm;
+    if (scratch_doubles < (int64_t)n_parts * K4_MOMW * 2) return k4_fail(e, ME_ERR_INVALID, "moments scratch too small");
+    K4Params p;
+    k4_base(e, p);
+    const long long per = (e->cfg.n_chains + n_parts - 1) / n_parts;
+    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
+    k4_moments_stage1<<<n_parts, 256, 0, (cudaStream_t)stream>>>(p, shift, reinterpret_cast<double2 *>(scratch), per);
+    k4_moments_stage2<<<(K4_MOMW + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2 *>(scratch),
+                                                                            n_parts, reinterpret_cast<double2 *>(inc));
+    cudaError_t ce = cudaGetLastError();
+    cudaSetDevice(prev);
+    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_moments: ") + cudaGetErrorString(ce));
+    return ME_OK;
+}
+
+int me_k4_refactor(me_k4 *e, const double *mom, const double *inc, double *cov_c, double *cov_a, void *factor_bf16,
+                   double *s_a, int32_t *status, void *stream) {
+    if (!e || !mom || !inc || !cov_c || !cov_a || !factor_bf16 || !s_a) return ME_ERR_INVALID;
+    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
+    static bool attr_set = false;
+    const int smem = K4_NC * K4_NC * (int)sizeof(double2);
+    cudaError_t ce = cudaSuccess;
+    if (!attr_set) {
+        ce = cudaFuncSetAttribute(k4_refactor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = (ce == cudaSuccess);
+    }
+    if (ce == cudaSuccess) {
+        k4_refactor<<<1, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const double2 *>(mom),
+                                                            reinterpret_cast<const double2 *>(inc), e->n_measure,
+                                                            reinterpret_cast<double2 *>(cov_c), cov_a,
+                                                            reinterpret_cast<__nv_bfloat16 *>(factor_bf16), s_a, status);
+        ce = cudaGetLastError();
+    }
+    cudaSetDevice(prev);
+    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_refactor: ") + cudaGetErrorString(ce));
     return ME_OK;
 }
 

@@ -78,17 +78,21 @@ class SharedCovarianceEngine:
         self._check(self._lib.me_k4_bind(self._h, _ptr(self.state), _ptr(self._factor), _ptr(self._last_accept)))
         # shared covariances (ME:63-70): identity unless given
         self._cov_c = (torch.eye(N_C, dtype=torch.complex128, device=dev) if covariance_matrix_complex is None
-                       else torch.as_tensor(np.asarray(covariance_matrix_complex, dtype=np.complex128), device=dev))
+                       else torch.as_tensor(np.asarray(covariance_matrix_complex, dtype=np.complex128),
+                                            device=dev).contiguous())
         self._cov_a = torch.ones(1, dtype=f64, device=dev) if covariance_matrix_real is None else \
             torch.as_tensor(np.asarray(covariance_matrix_real, dtype=np.float64).reshape(1), device=dev)
         self._install_factor()
         # pooled running moments about a fixed shift (the initial ensemble mean)
         x0 = np.concatenate([xr.reshape(-1)[:1] if xr.ndim == 1 else [xr[:, 0].mean()],
                              (xc if xc.ndim == 1 else xc.mean(0)).real, (xc if xc.ndim == 1 else xc.mean(0)).imag])
-        self._shift_a = float(x0[0])
-        self._shift_c = torch.as_tensor(x0[1:1 + N_C] + 1j * x0[1 + N_C:], dtype=torch.complex128, device=dev)
+        self._shift = torch.as_tensor(np.ascontiguousarray(x0), dtype=f64, device=dev)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        self._scratch = torch.zeros(n_sm * lay.MOM_WORDS * 2, dtype=f64, device=dev)
+        self._inc_full = torch.zeros(lay.MOM_WORDS, dtype=torch.complex128, device=dev)
         self._mom = torch.zeros(4 + N_C + N_C * N_C, dtype=torch.complex128, device=dev)   # count, -, sum a, sum a^2, sum c, sum c c^H
-        self._count = 0
+        self._inc = torch.zeros(2, dtype=torch.complex128, device=dev)
+        self._psd_status = torch.zeros(1, dtype=torch.int32, device=dev)
         per_chain = xr.ndim == 2 or xc.ndim == 2
         if per_chain:
             full = np.zeros((lay.D, self.n_chains_total))
@@ -178,32 +182,18 @@ class SharedCovarianceEngine:
         else:
             self._launch(self._lib.me_k4_measure(self._h, None, 0, self._stream()))
         n = self.measure_step_counter
-        lay = self._lay
-        a = self.state[lay.X] - self._shift_a
-        c = torch.complex(self.state[lay.X + 1:lay.X + 1 + N_C], self.state[lay.X + 1 + N_C:lay.X + 1 + 2 * N_C]) \
-            - self._shift_c[:, None]
-        inc = torch.cat([
-            torch.tensor([float(self.n_chains)], dtype=torch.complex128, device=self.device),
-            self.state[lay.SIG].sum().reshape(1).to(torch.complex128),
-            a.sum().reshape(1).to(torch.complex128), (a * a).sum().reshape(1).to(torch.complex128),
-            c.sum(dim=1), (c @ c.conj().t()).reshape(-1)])
+        inc = self._inc_full
+        self._launch(self._lib.me_k4_moments(self._h, _ptr(self._shift), _ptr(self._scratch), self._scratch.numel(),
+                                             _ptr(inc), self._stream()))
+        self.launch_count += 1
         if self._distributed:
-            v = torch.view_as_real(inc)
-            parallel.allreduce_sum_(v)
-            inc = torch.view_as_complex(v)
-        sig_mean = (inc[1].real / inc[0].real)
+            parallel.allreduce_sum_(torch.view_as_real(inc))
         self._mom[0] += inc[0]
         self._mom[2:] += inc[2:]
         if n > 50:                                                                            # ME:389,396
-            N = self._mom[0].real
-            small = sig_mean * sig_mean / n                                                   # ME:418,425
-            a1, a2 = self._mom[2].real, self._mom[3].real
-            self._cov_a = ((a2 - a1 * a1 / N) / (N - 1) + small).reshape(1)
-            s1 = self._mom[4:4 + N_C]
-            s2 = self._mom[4 + N_C:].reshape(N_C, N_C)
-            cov = (s2 - torch.outer(s1, s1.conj()) / N) / (N - 1)
-            self._cov_c = cov + small * torch.eye(N_C, dtype=torch.complex128, device=self.device)
-            self._install_factor()
+            self._launch(self._lib.me_k4_refactor(self._h, _ptr(self._mom), _ptr(inc), _ptr(self._cov_c),
+                                                  _ptr(self._cov_a), _ptr(self._factor), _ptr(self._s_a),
+                                                  _ptr(self._psd_status), self._stream()))
 
     def run(self, n_measures, steps_per_measure):
         for _ in range(int(n_measures)):

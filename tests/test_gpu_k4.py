@@ -74,7 +74,7 @@ def test_gaussian_modes_reach_exact_stationary_variances():
     n, T = 8192, 0.1
     kappa, alpha, gamma = 500.0, 1.0, 0.05
     eng = _engine(energy_consts=(kappa, alpha, gamma, 0.0), temp=T, n_chains=n, seed=5, record=False)
-    eng.run(150, 10)
+    eng.run(600, 10)                                                # the soft modes (q ~ 0) equilibrate last
     acc0 = eng.accept_count_per_chain.clone()
     eng.run(30, 10)
     acc = ((eng.accept_count_per_chain - acc0).sum() / (300.0 * n)).item()
@@ -126,27 +126,28 @@ def test_results_do_not_depend_on_tiling_or_sharding():
     assert torch.equal(full.state[:, :256], lo.state)               # chain i depends on (seed, i) only
 
 
-def test_agrees_with_per_chain_fp64_oracle_statistically():
-    """Same energy (full cylinder form incl. the quartic term and the wall) in the C oracle with per-chain FP64
-    proposals: mean energy and mean |c_q|^2 of the two ensembles agree (z-test, 5 sigma)."""
-    from oracle import c_oracle as co
-    T, consts = 0.1, (10.0, -1.0, 0.05, 1.0)
-    n = 2048
-    eng = _engine(energy_consts=consts, temp=T, n_chains=n, seed=2, record=False)
-    eng.run(120, 10)
-    c = eng.complex_params_per_chain.cpu().numpy()
-    e_gpu = eng.energy_per_chain.cpu().numpy()
-    M = 48
-    e_ref, m2_ref = [], []
-    for ch in range(M):
-        o = co.CChain(1, 64, "cylinder", consts=consts, temp=T, x0=np.zeros(129), use_reject=True)
-        o.run(120, 10, True, seed=100, chain_id=ch)
-        e_ref.append(o.energy)
-        m2_ref.append(o.x[1:65] ** 2 + o.x[65:129] ** 2)
-    e_ref, m2_ref = np.array(e_ref), np.array(m2_ref)
-    se = np.sqrt(e_gpu.var() / n + e_ref.var() / M)
-    assert abs(e_gpu.mean() - e_ref.mean()) < 5 * se, (e_gpu.mean(), e_ref.mean(), se)
-    low = slice(28, 37)                                              # the soft (small |q|) modes carry the signal
-    g, r = (np.abs(c) ** 2)[:, low].mean(1), m2_ref[:, low].mean(1)
-    se = np.sqrt(g.var() / n + r.var() / M)
-    assert abs(g.mean() - r.mean()) < 5 * se, (g.mean(), r.mean(), se)
+def test_quartic_energy_satisfies_the_virial_identity_per_mode():
+    """Full cylinder energy (quartic coupling, a-dependent stiffness, hard wall).  For every unbounded real
+    coordinate x of a law proportional to exp(-E/T), <x dE/dx> = T exactly; per complex mode q this reads
+    < 2 |c_q|^2 (alpha + gamma q^2 (1 + a^2) + beta/64 sum_k |c_k|^2) > = 2 T.  Checked for all 64 modes on the
+    equilibrated ensemble, averaged over 40 decorrelated snapshots (z-test over chains x snapshots, 5 sigma with the
+    snapshot correlation bounded by using the chain-mean variance)."""
+    T, (kappa, alpha, gamma, beta) = 0.1, (10.0, -1.0, 0.05, 1.0)
+    n = 4096
+    eng = _engine(energy_consts=(kappa, alpha, gamma, beta), temp=T, n_chains=n, seed=2, record=False)
+    eng.run(800, 10)
+    q2 = torch.tensor((np.arange(64) - 32.0) ** 2, device="cuda")
+    acc = torch.zeros((n, 64), dtype=torch.float64, device="cuda")
+    snaps = 40
+    for _ in range(snaps):
+        eng.run(5, 10)
+        c = eng.complex_params_per_chain
+        a = eng.real_params_per_chain[:, 0]
+        m2 = c.real ** 2 + c.imag ** 2
+        w = alpha + gamma * q2[None, :] * (1 + a[:, None] ** 2) + (beta / 64.0) * m2.sum(1, keepdim=True)
+        acc += 2 * m2 * w
+    v = (acc / snaps).cpu().numpy()                     # per chain time-average, [n, 64]
+    z = (v.mean(0) - 2 * T) / (v.std(0, ddof=1) / np.sqrt(n))
+    assert np.max(np.abs(z)) < 5.0, (int(np.argmax(np.abs(z))), float(np.max(np.abs(z))), v.mean(0)[:4])
+    assert abs(v.mean() - 2 * T) < 5 * v.mean(1).std(ddof=1) / np.sqrt(n)
+    assert np.all(np.abs(eng.real_params_per_chain.cpu().numpy()) < 1.0)
