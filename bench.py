@@ -408,19 +408,106 @@ def run_ours(args):
     return 0
 
 
+def run_c4(args):
+    """BASELINE config 4: cylinder-style field, 1 real + 64 complex parameters, shared proposal covariance,
+    32,768 chains per GPU; tcgen05 path (csrc/me_k4.cu).  One bench step = 100 x (10 x step_all() + measure())
+    including the pooled-covariance update at every measure."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import metropolisengine_b200 as me
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    chains, M, spm = 32768, (args.measures or 100), 10
+    eng = me.SharedCovarianceEngine(energy_consts=(10.0, -1.0, 0.05, 1.0), temp=.1, n_chains=chains * world, seed=2024,
+                                    record=False, distributed=(world > 1), device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    eng.run(60, spm)                      # past the 50th measure: the shared covariance is live
+    for _ in range(args.warmup):
+        eng.run(M, spm)
+    barrier()
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            eng.run(M, spm)
+        ev1.record(stream)
+        barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    value = chains * world * M * spm * args.steps / (ms * 1e-3)
+    # the step kernel alone
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    eng.step(200)
+    b.record(stream)
+    torch.cuda.synchronize(dev)
+    ker_ms = a.elapsed_time(b)
+    acc = eng.acceptance_rate
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peaks = _peaks() or {}
+    tf_peak = peaks.get("bf16_tflops", 1590.0)
+    tf = chains * 200 * 2.0 * 128 * 128 / (ker_ms * 1e-3) / 1e12
+    line = {
+        "metric": "ensemble chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 state/energy/accept, bf16 proposal contraction (fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": "cylinder-style Fourier-mode field: 1 real + 64 complex, shared proposal covariance, "
+                               "32,768 chains per GPU, measure + covariance adaptation every 10 steps",
+                   "chains_per_gpu": chains, "measures_per_bench_step": M, "measure_every": spm},
+        "gpu_launches": eng.launch_count - l0 - 1,
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak,
+                     "traffic": None, "kernel": "k4_steps", "kernel_ms": ker_ms / 200,
+                     "algorithmic": "2*128*128 flop per chain-step in the L.Z contraction (SURVEY.md §8d C4); the kernel "
+                                    "is bound by in-kernel Gaussian generation (Philox + Box-Muller), not by the "
+                                    "tensor pipe",
+                     "step_kernel_only_chain_steps_per_s": chains * 200 / (ker_ms * 1e-3)},
+        "clocks": clocks.summary(), "check": {"acceptance_rate": acc},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"])
     ap.add_argument("--measures", type=int, default=0, help="override measures per bench step (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                   # timing rule: W >= 3
+    if args.workload == "c4":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the c4 reference arm is not wired; use --workload c2"}))
+            return 0
+        return run_c4(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

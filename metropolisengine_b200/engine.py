@@ -184,8 +184,9 @@ class MetropolisEngine:
         self._callable_layout = callable_layout
         if callable_layout not in ("chains_first", "params_first"):
             raise ValueError("callable_layout must be 'chains_first' or 'params_first'")
-        self.reject_condition = reject_condition
         self._install_energy(energy_functions)
+        self._check_reject_supported(reject_condition)
+        self.reject_condition = reject_condition
 
         # ---- state initialisation (ME:63-81, 123-125)
         if per_chain_init:
@@ -278,7 +279,17 @@ class MetropolisEngine:
         self._install_energy(energy_function)
 
     def set_reject_condition(self, reject_fct):                                            # ME:142-146
+        self._check_reject_supported(reject_fct)
         self.reject_condition = reject_fct
+
+    def _check_reject_supported(self, reject_fct):
+        """A python predicate can only run on the unfused (python-callable energy) path; fused device functors
+        carry their hard wall inside the functor (``BuiltinEnergy(..., reject=True)`` / ``CudaEnergy(...,
+        has_reject=True)``).  Refuse instead of silently ignoring the constraint."""
+        if reject_fct is not None and self._callable is None:
+            raise NotImplementedError("reject_condition as a python callable needs a python-callable energy; for "
+                                      "device functors put the wall in the functor (BuiltinEnergy(reject=True) or "
+                                      "CudaEnergy(has_reject=True))")
 
     def _split(self, block):
         """[D, chains] block -> (real, complex) tensors in the callable's layout."""
