@@ -150,20 +150,27 @@ def _cpu_worker(args):
             ch.step()
         ch.measure()
     steps = 0
+    series = []                                # first coordinate after every step (for the ESS estimate)
+    first = (lambda: float(ch.real_params[0])) if ch.n_r else (lambda: float(ch.complex_params[0].real))
     t0 = time.perf_counter()
     if fixed_steps:
         for _ in range(fixed_steps // spm):
             for _ in range(spm):
                 ch.step()
+                series.append(first())
             ch.measure()
         steps = (fixed_steps // spm) * spm
     else:
         while time.perf_counter() - t0 < seconds:
             for _ in range(spm):
                 ch.step()
+                series.append(first())
             ch.measure()
             steps += spm
-    return steps, time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    from oracle.py_port import statistical_inefficiency
+    g = statistical_inefficiency(series[len(series) // 5:]) if len(series) > 2000 else float("nan")
+    return steps, dt, g
 
 
 def cpu_baseline(wl_key, seconds=10.0, fixed_steps=0, procs=None):
@@ -176,6 +183,8 @@ def cpu_baseline(wl_key, seconds=10.0, fixed_steps=0, procs=None):
     wall = time.perf_counter() - t0
     steps = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
+    gs = sorted(r[2] for r in res if r[2] == r[2])
+    cpu_baseline.last_g = gs[len(gs) // 2] if gs else float("nan")
     return steps, busy, wall, procs
 
 
@@ -358,6 +367,20 @@ def run_ours(args):
     fp64_peak = flops.value / (best * 1e-3) / 1e12
     acc_rate = eng.acceptance_rate            # collective when sharded: every rank must call it
 
+    # ---- ESS: statistical inefficiency per STEP from a side ensemble measured at every step (device kernel)
+    g_steps = None
+    if rank == 0:
+        kw2 = dict(kw)
+        kw2.update(n_chains=4096, distributed=False, ts_chunk_bytes=4096 * (d + 2) * 8 * 6000)
+        side = me.MetropolisEngine(wl["energy"], **kw2)
+        side.record = False
+        side.run(300, 10)                     # sigma / covariance adaptation
+        side.record = True
+        side.run(6000, 1)
+        gq = torch.stack([side.statistical_inefficiency(column=c, n_chains=1024, burn_in=0.2) for c in range(d)])
+        g_steps = float(gq.max(dim=0).values.median().item())      # worst coordinate per chain, median over chains
+        del side
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -392,6 +415,9 @@ def run_ours(args):
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}},
         "clocks": clocks.summary(),
         "check": {"acceptance_rate": acc_rate, "pooled_var_x0": float(ps["cov_real"][0, 0]) if n_r else None},
+        "ess": {"g_steps": g_steps, "ess_per_sec": value / g_steps if g_steps else None,
+                "how": "statistical inefficiency per step (pymbar's definition, worst coordinate, median of 1024 "
+                       "chains, 6000 consecutive steps after adaptation), device kernel me_statistical_inefficiency"},
     }
     # ---- CPU baseline on this box's host cores (bounded sample)
     if not args.no_cpu:
@@ -401,6 +427,8 @@ def run_ours(args):
             "sample": "%d processes x %.0f s of the same schedule, one chain each (numpy port of the reference loop, "
                       "oracle/py_port.py, OMP_NUM_THREADS=1)" % (procs, args.cpu_seconds),
             "c_oracle_1core": c_oracle_rate(args.workload),
+            "g_steps": cpu_baseline.last_g,
+            "ess_per_sec": (steps / busy) / cpu_baseline.last_g if cpu_baseline.last_g == cpu_baseline.last_g else None,
         }
     print(json.dumps(line))
     if world > 1:

@@ -226,6 +226,13 @@ const char *me_k4_last_error(me_k4 *eng);
  * out needs n_sm*8*256 doubles; *flops receives the flop count of the launch.  Time it with CUDA events. */
 int me_probe_fp64(int32_t device, int64_t iters, double *out, int64_t out_len, void *stream, int64_t *flops);
 
+/* Statistical inefficiency g (pymbar's definition, reference statistics.py:36-38,46 via metropolis_engine.py:490)
+ * of column `col` of a time-series block ts[row][cols][ld] for chains [chain0, chain0 + n_sel), using rows
+ * [row0, rows); the autocorrelation sum stops at the first non-positive term or at max_lag (<= 0: no cap).
+ * g_out[n_sel].  ESS = N / g.  SURVEY.md §8 row f3 / metric "ESS/sec". */
+int me_statistical_inefficiency(const double *ts, int64_t rows, int64_t row0, int32_t cols, int64_t ld, int32_t col,
+                                int64_t chain0, int64_t n_sel, int64_t max_lag, double *g_out, void *stream);
+
 const char *me_last_error(me_engine *eng);   /* eng may be NULL: error of the last failing me_create */
 
 #ifdef __cplusplus

@@ -349,6 +349,37 @@ __global__ void __launch_bounds__(256) k_probe_fp64(double *out, long long iters
     out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+/* Statistical inefficiency g = 1 + 2 sum_t (1 - t/N) rho_t, truncated at the first non-positive rho_t, of one
+ * time-series column per chain (one thread per chain; consecutive threads read consecutive chains, so every row
+ * access is coalesced).  This is the quantity the reference obtains from pymbar for its equilibrium statistics
+ * (statistics.py:36-38,46; used at metropolis_engine.py:490) and the denominator of ESS/sec. */
+__global__ void k_stat_ineff(const double *ts, long long rows, long long row0, int cols, long long ld, int col,
+                             long long chain0, long long n_sel, long long max_lag, double *g_out) {
+    const long long t_id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_id >= n_sel) return;
+    const double *x = ts + (long long)col * ld + chain0 + t_id;
+    const long long stride = (long long)cols * ld;
+    const long long N = rows - row0;
+    double mean = 0.0;
+    for (long long i = 0; i < N; i++) mean += x[(row0 + i) * stride];
+    mean /= (double)N;
+    double var = 0.0;
+    for (long long i = 0; i < N; i++) { const double d = x[(row0 + i) * stride] - mean; var += d * d; }
+    var /= (double)N;
+    double g = 1.0;
+    if (var > 0.0 && N >= 4) {
+        const long long tmax = max_lag < N - 1 ? max_lag : N - 2;
+        for (long long t = 1; t <= tmax; t++) {
+            double c = 0.0;
+            for (long long i = 0; i + t < N; i++) c += (x[(row0 + i) * stride] - mean) * (x[(row0 + i + t) * stride] - mean);
+            const double rho = c / ((double)(N - t) * var);
+            if (!(rho > 0.0)) break;
+            g += 2.0 * rho * (1.0 - (double)t / (double)N);
+        }
+    }
+    g_out[t_id] = g > 1.0 ? g : 1.0;
+}
+
 }  // namespace
 
 /* ========================================================================================= C ABI */
@@ -571,6 +602,18 @@ int me_probe_fp64(int32_t device, int64_t iters, double *out, int64_t out_len, v
     k_probe_fp64<<<grid, block, 0, (cudaStream_t)stream>>>(out, iters);
     if (cudaGetLastError() != cudaSuccess) return ME_ERR_CUDA;
     if (flops) *flops = (int64_t)grid * block * iters * 8 * 2;
+    return ME_OK;
+}
+
+int me_statistical_inefficiency(const double *ts, int64_t rows, int64_t row0, int32_t cols, int64_t ld, int32_t col,
+                                int64_t chain0, int64_t n_sel, int64_t max_lag, double *g_out, void *stream) {
+    if (!ts || !g_out || rows <= 0 || row0 < 0 || row0 >= rows || col < 0 || col >= cols || n_sel <= 0 ||
+        chain0 < 0 || chain0 + n_sel > ld)
+        return ME_ERR_INVALID;
+    const int block = 128;
+    k_stat_ineff<<<(unsigned)((n_sel + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
+        ts, rows, row0, cols, ld, col, chain0, n_sel, max_lag > 0 ? max_lag : rows, g_out);
+    if (cudaGetLastError() != cudaSuccess) return ME_ERR_CUDA;
     return ME_OK;
 }
 

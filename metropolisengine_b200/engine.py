@@ -752,6 +752,23 @@ class MetropolisEngine:
         self.df = pandas.DataFrame.from_dict(cols)
         return self.df
 
+    def statistical_inefficiency(self, column=0, n_chains=1024, burn_in=0.2, max_lag=0):
+        """Per-chain statistical inefficiency g (in units of measures) of one stored time-series column
+        (``column`` indexes [parameters in the order real, Re c, Im c | energy | sigma]) for the first ``n_chains``
+        local chains, discarding the first ``burn_in`` fraction of rows — the quantity the reference's
+        ``save_equilibrium_stats`` gets from pymbar (ME:490, statistics.py:36-38).  ESS per chain = rows / g."""
+        chunks = [(t, used) for t, used in self._ts_chunks if used]
+        if len(chunks) != 1:
+            raise RuntimeError("statistical_inefficiency needs the series in one storage chunk (raise ts_chunk_bytes)")
+        t, used = chunks[0]
+        n_sel = min(int(n_chains), self.n_chains)
+        g = torch.empty(n_sel, dtype=torch.float64, device=self.device)
+        rc = self._lib.me_statistical_inefficiency(_ptr(t), used, int(used * burn_in), self._lay.TS_COLS, self.n_chains,
+                                                   int(column), 0, n_sel, int(max_lag), _ptr(g), self._stream())
+        if rc != 0:
+            raise ValueError("bad arguments to me_statistical_inefficiency")
+        return g
+
     # ------------------------------------------------------------------ checkpoint / resume (SURVEY §5)
     def state_dict(self):
         n, s = ctypes.c_int64(), ctypes.c_uint64()

@@ -294,3 +294,17 @@ __device__ double me_user_energy(const double* x, const double* cr, const double
 def _me_error():
     from metropolisengine_b200._lib import MeError
     return MeError
+
+
+def test_statistical_inefficiency_kernel_matches_oracle_estimator():
+    """ESS denominator: the device kernel equals the oracle's estimator (pymbar's definition) on the stored series."""
+    import metropolisengine_b200 as me
+    from oracle.py_port import statistical_inefficiency
+    eng = me.MetropolisEngine(("xy_well", 1.0), initial_real_params=np.array([0., 0.]), temp=.1, n_chains=64, seed=4)
+    eng.run(600, 2)
+    g = eng.statistical_inefficiency(column=0, n_chains=8, burn_in=0.25).cpu().numpy()
+    ts = eng.time_series().cpu().numpy()
+    for ch in range(8):
+        want = statistical_inefficiency(ts[150:, 0, ch])
+        assert abs(g[ch] - want) <= 1e-9 * want, (ch, g[ch], want)
+    assert np.all(g >= 1.0)
