@@ -125,6 +125,7 @@ typedef struct me_buffers {
     double *pool;               /* [grid][POOL_WORDS] pooled-moment accumulators (may be NULL: no pooling) */
     double *shift;              /* [D] shift of the pooled moments (required when pool != NULL) */
     unsigned char *last_accept; /* [n_chains] accept flag of the most recent step — the return value of step_all() (ME:259) */
+    double *scratch;            /* [D][n_chains] work space, required when D = n_real + 2 n_complex > 32 (may be NULL otherwise) */
 } me_buffers;
 int me_bind(me_engine *eng, const me_buffers *buffers);
 
@@ -159,6 +160,13 @@ int me_run_injected(me_engine *eng, int64_t n_blocks, int64_t steps_per_measure,
 int me_propose(me_engine *eng, double *prop, const double *inj_delta, void *stream);
 int me_accept(me_engine *eng, const double *prop, const double *e_new, const unsigned char *rej,
               const double *inj_u, void *stream);
+
+/* Large parameter spaces (D > 32, e.g. 1 real + 64 complex with per-chain covariance — the reference's own
+ * algorithm at the cylinder shape): the step is always unfused, me_propose -> energy -> me_accept, with runtime-shape
+ * kernels whose state stays in global memory (csrc/me_generic.cu); me_run then only serves measure().  For built-in
+ * functors this entry point evaluates the energy (and the functor's hard wall) of a proposal block:
+ * e_out[n_chains], rej_out[n_chains] (may be NULL). */
+int me_energy_builtin(me_engine *eng, const double *prop, double *e_out, unsigned char *rej_out, void *stream);
 
 /* Pooled ensemble moments: out[POOL_WORDS] = sum over CTAs (fixed order, deterministic) of the accumulators
  * filled at every measure; reset != 0 zeroes the accumulators afterwards.  The caller all-reduces `out` across

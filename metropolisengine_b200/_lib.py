@@ -35,7 +35,7 @@ class MeLayout(ctypes.Structure):
 
 
 class MeBuffers(ctypes.Structure):
-    _fields_ = [("state", _vp), ("pool", _vp), ("shift", _vp), ("last_accept", _vp)]
+    _fields_ = [("state", _vp), ("pool", _vp), ("shift", _vp), ("last_accept", _vp), ("scratch", _vp)]
 
 
 class MeK4Config(ctypes.Structure):
@@ -66,6 +66,7 @@ SIGNATURES = {
     "me_run_injected": (ctypes.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),
     "me_propose": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "me_accept": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "me_energy_builtin": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "me_pool_reduce": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "me_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
     "me_set_counters": (ctypes.c_int, [_vp, _i64, _u64]),

@@ -23,6 +23,11 @@
 
 extern "C" const MeAotEntry *me_aot_fast_table(int *n);
 extern "C" const MeAotEntry *me_aot_strict_table(int *n);
+extern "C" void me_generic_kernels(const void **run_measure, const void **init, const void **propose,
+                                   const void **accept, const void **energy);
+
+/* shapes with D = n_r + 2 n_c above this use the runtime-shape kernels of me_generic.cu (state in global memory) */
+#define ME_FUSED_MAX_D 32
 
 namespace {
 
@@ -35,7 +40,7 @@ struct KernelRef {
     bool valid() const { return rt != nullptr || drv != nullptr; }
 };
 struct KernelSet {
-    KernelRef run, init, propose, accept;
+    KernelRef run, init, propose, accept, energy;
     bool valid() const { return run.valid(); }
 };
 
@@ -205,6 +210,7 @@ struct me_engine {
     unsigned long long step = 0;       /* global step index (Philox counter word 2) */
     int block = 128, grid = 1;
     int n_sm = 148;
+    bool generic = false;              /* large shape: runtime-shape kernels, unfused step */
     std::string err;
 };
 
@@ -263,6 +269,10 @@ void base_params(me_engine *e, MeParams &p) {
     p.last_accept = e->buf.last_accept;
     p.pool = e->lay.POOL_WORDS > 0 ? e->buf.pool : nullptr;
     p.shift = e->buf.shift;
+    p.n_real = e->cfg.n_real;
+    p.n_complex = e->cfg.n_complex;
+    p.energy_id = e->energy_id;
+    p.scratch = e->buf.scratch;
 }
 
 /* Launch geometry.  One thread per chain, so the CTA size only trades scheduling granularity against the
@@ -283,6 +293,15 @@ void choose_dims(me_engine *e) {
 
 int resolve_kernels(me_engine *e, int energy_id, const std::string &user_src) {
     const int nr = e->cfg.n_real, nc = e->cfg.n_complex, strict = e->cfg.strict ? 1 : 0;
+    if (e->generic) {
+        if (energy_id == ME_ENERGY_USER)
+            return fail(e, ME_ERR_UNSUPPORTED, "user CUDA functors are fused kernels (D <= 32); for larger parameter "
+                                               "spaces use a built-in functor or a torch callable");
+        const void *m, *i, *pr, *ac, *en;
+        me_generic_kernels(&m, &i, &pr, &ac, &en);
+        e->ks.run.rt = m; e->ks.init.rt = i; e->ks.propose.rt = pr; e->ks.accept.rt = ac; e->ks.energy.rt = en;
+        return ME_OK;
+    }
     if (energy_id != ME_ENERGY_USER) {
         int n = 0;
         const MeAotEntry *t = strict ? me_aot_strict_table(&n) : me_aot_fast_table(&n);
@@ -427,6 +446,8 @@ int me_create(const me_config *cfg, me_engine **out) {
     else
         cudaGetLastError();
     choose_dims(e);
+    e->generic = e->lay.D > ME_FUSED_MAX_D;
+    if (e->generic) { e->block = 128; e->grid = (int)((cfg->n_chains + 127) / 128); }
     *out = e;
     return ME_OK;
 }
@@ -444,8 +465,10 @@ static int set_energy(me_engine *e, int id, const char *src, const double *const
     for (int i = 0; i < n_consts; i++) e->consts[i] = consts[i];
     e->use_reject = use_reject ? 1 : 0;
     e->ks = KernelSet();
+    const int prev_id = e->energy_id;
+    e->energy_id = id;
     int rc = resolve_kernels(e, id, src ? std::string(src) : std::string());
-    if (rc == ME_OK) e->energy_id = id;
+    if (rc != ME_OK) e->energy_id = prev_id;
     return rc;
 }
 
@@ -484,6 +507,7 @@ int me_bind(me_engine *e, const me_buffers *b) {
     if (!e || !b) return ME_ERR_INVALID;
     if (!b->state) return fail(e, ME_ERR_INVALID, "state buffer is required");
     if (b->pool && !b->shift) return fail(e, ME_ERR_INVALID, "pool needs a shift vector");
+    if (e->generic && !b->scratch) return fail(e, ME_ERR_INVALID, "large parameter spaces need the scratch buffer");
     e->buf = *b;
     e->bound = true;
     return ME_OK;
@@ -513,6 +537,9 @@ static int run_common(me_engine *e, int64_t n_blocks, int64_t spm, int do_measur
     if (n_blocks == 0 || (spm == 0 && !do_measure)) return ME_OK;
     if (spm > 0 && e->energy_id == ME_ENERGY_EXTERNAL)
         return fail(e, ME_ERR_STATE, "external energies step through me_propose / me_accept");
+    if (e->generic && (spm > 0 || n_blocks != 1))
+        return fail(e, ME_ERR_STATE, "large parameter spaces step through me_propose / me_energy_builtin / me_accept "
+                                     "and measure one block at a time");
     if (e->step + (unsigned long long)(n_blocks * spm) >= 0xffffffffull)
         return fail(e, ME_ERR_INVALID, "step index exceeds the 32-bit Philox counter word");
     MeParams p;
@@ -562,6 +589,17 @@ int me_accept(me_engine *e, const double *prop, const double *e_new, const unsig
     int rc = launch(e, e->ks.accept, p, stream);
     if (rc == ME_OK) e->step += 1;
     return rc;
+}
+
+int me_energy_builtin(me_engine *e, const double *prop, double *e_out, unsigned char *rej_out, void *stream) {
+    if (!e) return ME_ERR_INVALID;
+    if (!e->generic) return fail(e, ME_ERR_STATE, "me_energy_builtin serves the large-shape unfused path only");
+    if (!prop || !e_out) return fail(e, ME_ERR_INVALID, "prop and e_out are required");
+    if (e->energy_id < 0 || e->energy_id == ME_ENERGY_EXTERNAL) return fail(e, ME_ERR_STATE, "no built-in functor registered");
+    MeParams p;
+    base_params(e, p);
+    p.prop = const_cast<double *>(prop); p.e_out = e_out; p.rej_out = rej_out;
+    return launch(e, e->ks.energy, p, stream);
 }
 
 int me_pool_reduce(me_engine *e, double *out, int32_t reset, void *stream) {

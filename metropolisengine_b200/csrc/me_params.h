@@ -5,7 +5,7 @@
 #ifndef ME_PARAMS_H
 #define ME_PARAMS_H
 
-#define ME_PARAMS_VERSION 4
+#define ME_PARAMS_VERSION 5
 #define ME_MAX_CONSTS 16
 
 /* status bits written to the per-chain STATUS word (SURVEY §5 "failure detection") */
@@ -51,6 +51,12 @@ struct MeParams {
     const double *cov_r0;          /* [NR*NR] row-major, shared by all chains (NULL = identity) */
     const double *cov_c0_re;       /* [NC*NC] */
     const double *cov_c0_im;
+    /* generic (runtime-shape) kernels for large parameter spaces: me_generic.cu */
+    int n_real, n_complex;
+    int energy_id;                 /* built-in functor evaluated by gk_energy */
+    double *scratch;               /* [D][ld] per-chain scratch (old means during measure) */
+    double *e_out;                 /* [ld] gk_energy output */
+    unsigned char *rej_out;        /* [ld] gk_energy hard-wall output (may be NULL) */
 };
 
 #endif

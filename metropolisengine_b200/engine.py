@@ -175,7 +175,10 @@ class MetropolisEngine:
         self._pool_out = torch.zeros(max(pw, 1), dtype=f64, device=dev)
         self._pool_sum = np.zeros(max(pw, 1))
         self._pool_count = 0
-        bufs = _lib.MeBuffers(_ptr(self.state), _ptr(self._pool), _ptr(self._shift), _ptr(self._last_accept))
+        self._generic = self._d > 32          # large shapes: runtime-shape kernels, unfused step (me_generic.cu)
+        self._scratch = torch.zeros((self._d, self.n_chains), dtype=f64, device=dev) if self._generic else None
+        bufs = _lib.MeBuffers(_ptr(self.state), _ptr(self._pool), _ptr(self._shift), _ptr(self._last_accept),
+                              _ptr(self._scratch))
         self._check(self._lib.me_bind(self._h, ctypes.byref(bufs)))
 
         # ---- energy plugin (ME:110-120) and hard-wall predicate (ME:126-127, 142-146)
@@ -392,7 +395,7 @@ class MetropolisEngine:
         n_measures, steps_per_measure = int(n_measures), int(steps_per_measure)
         if n_measures <= 0:
             return
-        if self._callable is not None:
+        if self._callable is not None or self._generic:
             for _ in range(n_measures):
                 for _ in range(steps_per_measure):
                     self._step_external()
@@ -409,7 +412,7 @@ class MetropolisEngine:
     def step(self, k=1):
         """``k`` calls of ``step_all()`` in one launch (no measure)."""
         k = int(k)
-        if self._callable is not None:
+        if self._callable is not None or self._generic:
             for _ in range(k):
                 self._step_external()
             return
@@ -429,11 +432,17 @@ class MetropolisEngine:
         prop = torch.empty((self._d, self.n_chains), dtype=torch.float64, device=self.device)
         self._launch(self._lib.me_propose(self._h, _ptr(prop), _ptr(inj_delta), self._stream()))
         rej = None
-        if self.reject_condition is not None:
-            r, c = self._split(prop)
-            rej = torch.as_tensor(self.reject_condition(r, c), device=self.device)
-            rej = rej.to(torch.uint8).expand(self.n_chains).contiguous() if rej.dim() == 0 else rej.to(torch.uint8).contiguous()
-        e_new = self._eval_callable(prop)
+        if self._callable is None:              # large shape with a built-in functor: energy + wall on the device
+            e_new = torch.empty(self.n_chains, dtype=torch.float64, device=self.device)
+            rej = torch.empty(self.n_chains, dtype=torch.uint8, device=self.device)
+            self._launch(self._lib.me_energy_builtin(self._h, _ptr(prop), _ptr(e_new), _ptr(rej), self._stream()))
+        else:
+            if self.reject_condition is not None:
+                r, c = self._split(prop)
+                rej = torch.as_tensor(self.reject_condition(r, c), device=self.device)
+                rej = (rej.to(torch.uint8).expand(self.n_chains).contiguous() if rej.dim() == 0
+                       else rej.to(torch.uint8).contiguous())
+            e_new = self._eval_callable(prop)
         self._launch(self._lib.me_accept(self._h, _ptr(prop), _ptr(e_new), _ptr(rej), _ptr(inj_u), self._stream()))
         self.step_counter += 1 if self._kind == "complex" else 0
 
@@ -463,7 +472,7 @@ class MetropolisEngine:
             u = u[:, None].expand(S, self.n_chains)
         delta, u = delta.contiguous(), u.contiguous()
         assert delta.shape == (S, self._d, self.n_chains) and u.shape == (S, self.n_chains)
-        if self._callable is not None:
+        if self._callable is not None or self._generic:
             s = 0
             for _ in range(int(n_measures)):
                 for _ in range(int(steps_per_measure)):

@@ -58,6 +58,13 @@ def cases():
                                 ctor=dict(initial_real_params=np.array([0.9]),
                                           initial_complex_params=np.zeros(8, dtype=complex), temp=.1,
                                           sampling_width=0.2)),
+        # BASELINE config 4 shape with the reference's own per-chain algorithm: 1 real + 64 complex, 128x128 embedded
+        # proposal covariance (metropolis_engine.py:274-302); crosses n > 50 so the 64x64 complex recursion runs
+        "cyl_1r64c": dict(energy=en.make_cylinder(64), builtin=("cylinder", [10.0, -1.0, 0.05, 1.0]),
+                          reject=en.cylinder_reject, n_measures=53, steps_per_measure=3, seed=13,
+                          ctor=dict(initial_real_params=np.array([0.2]),
+                                    initial_complex_params=np.zeros(64, dtype=complex), temp=.1,
+                                    sampling_width=0.012)),
         # temp = 0 (the constructor default): greedy descent, no uniform is ever drawn (metropolis_engine.py:331-332)
         "xy_temp0": dict(energy=en.xy_well, builtin=("xy_well", [1.0]), n_measures=60, steps_per_measure=4, seed=7,
                          ctor=dict(initial_real_params=np.array([1.0, -2.0]), temp=0)),

@@ -89,6 +89,37 @@ def test_injected_parity_builtin(name):
     drive_injected_and_compare(eng, g)
 
 
+def test_injected_parity_cylinder_shape_1r64c_per_chain_covariance():
+    """BASELINE config 4 shape with the reference's own per-chain algorithm (128x128 embedded proposal covariance,
+    metropolis_engine.py:274-302): runtime-shape kernels (me_generic.cu), draw-injected against the reference."""
+    import metropolisengine_b200 as me
+    eng, g = make_engine("cyl_1r64c", me, strict=True)
+    assert eng._generic
+    drive_injected_and_compare(eng, g)
+
+
+def test_large_shape_philox_matches_c_oracle():
+    """Same shape in Philox mode: proposals through the per-chain 64x64 complex Cholesky factor in global memory
+    follow the C oracle chain by chain."""
+    import metropolisengine_b200 as me
+    from oracle import c_oracle as co
+    n, M, K = 64, 54, 2
+    consts = [10.0, -1.0, 0.05, 1.0]
+    eng = me.MetropolisEngine(me.BuiltinEnergy("cylinder", *consts, reject=True), initial_real_params=np.array([0.2]),
+                              initial_complex_params=np.zeros(64, dtype=complex), temp=.1, sampling_width=0.012,
+                              n_chains=n, seed=99)
+    eng.run(M, K)
+    eng.check_status()
+    st = eng.state.cpu().numpy()
+    lay = eng._lay
+    for ch in (0, 33, 63):
+        o = co.CChain(1, 64, "cylinder", consts=consts, temp=.1, sampling_width=0.012,
+                      x0=np.concatenate([[0.2], np.zeros(128)]), use_reject=True)
+        acc, _ = o.run(M, K, True, seed=99, chain_id=ch)
+        assert st[lay.NACC, ch] == acc.sum()
+        assert close(st[:lay.WORDS - 2, ch], o.state[:lay.WORDS - 2], 1e-9), ch
+
+
 @pytest.mark.parametrize("name", ["pure_2c", "warm_3r2c"])
 def test_injected_parity_user_functor_nvrtc(name):
     """User CUDA functors compiled at run time (NVRTC, --fmad=false) and fused into the step kernel."""
