@@ -44,6 +44,22 @@ WORKLOADS = {
 }
 
 
+def _ncu_traffic_per_chain_measure():
+    """DRAM bytes per chain-measure of the step kernel from the committed ncu --set full capture
+    (profiles/r01_ncu_c2_k_run.csv: a launch of 1000 measures x 65,536 chains)."""
+    try:
+        rd = wr = None
+        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_c2_k_run.csv")):
+            f = line.strip().split(",")
+            if f[0] == "dram__bytes_read.sum":
+                rd = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+            if f[0] == "dram__bytes_write.sum":
+                wr = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
+        return (rd + wr) / (1000.0 * 65536.0)
+    except Exception:
+        return None
+
+
 def _peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -366,6 +382,7 @@ def run_ours(args):
             best = ms if best is None else min(best, ms)
     fp64_peak = flops.value / (best * 1e-3) / 1e12
     acc_rate = eng.acceptance_rate            # collective when sharded: every rank must call it
+    tpm = _ncu_traffic_per_chain_measure() if args.workload == "c2" else None
 
     # ---- ESS: statistical inefficiency per STEP from a side ensemble measured at every step (device kernel)
     g_steps = None
@@ -406,7 +423,12 @@ def run_ours(args):
                                             "final per-chain state and of chain 0's time series"},
         "gpu_launches": launches,
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp64_peak, "traffic": None,
+                     "frac": achieved_tf / fp64_peak,
+                     "traffic": (tpm * chains * M) if tpm else None,
+                     "traffic_note": "DRAM read+write bytes per launch: per chain-measure figure of the committed ncu "
+                                     "--set full capture (profiles/r01_ncu_c2_k_run.csv) x this launch's "
+                                     "chain-measures; algorithmic %d B per chain-measure" % (8 * (d + 2)),
+                     "fp64_pipe_busy_ncu": 0.40 if args.workload == "c2" else None,
                      "kernel": "me::k_run", "kernel_ms": ker_ms,
                      "algorithmic": "%d flop + %d special functions per chain-step (SURVEY.md §8d); special functions "
                                     "and Philox integer work are NOT counted in achieved" % (wl["flop"], wl["sf"]),

@@ -761,6 +761,26 @@ class MetropolisEngine:
         self.df = pandas.DataFrame.from_dict(cols)
         return self.df
 
+    def to_csv(self, path, chain=0):
+        """On-disk time series of one chain in the reference's format: the columns of
+        ``save_time_series`` written with ``DataFrame.to_csv`` — complex parameters print as ``(a+bj)``, exactly
+        like the reference's recorded ``exampledata.csv``; readable by its ``statistics.py:7-23``."""
+        df = self.save_time_series(chain)
+        df.to_csv(path)
+        return path
+
+    def save_npz(self, path):
+        """Dense binary dump of every recorded row of every local chain (for 1e9-row ensembles where CSV is
+        hopeless): ``rows[row, column, chain]`` with ``columns`` = parameters in the order [real, Re c, Im c],
+        ``energy``, ``sampling_width``; plus names and the chain offset of this rank."""
+        ts = self.time_series().cpu().numpy()
+        nr, nc = self.num_real_params, self.num_complex_params
+        cols = ([self.params_names[i] for i in range(nr)] + ["Re_" + self.params_names[nr + j] for j in range(nc)]
+                + ["Im_" + self.params_names[nr + j] for j in range(nc)] + ["energy", "sampling_width"])
+        np.savez_compressed(path, rows=ts, columns=np.array(cols), chain_offset=self.chain_offset,
+                            observables_names=np.array(self.observables_names))
+        return path
+
     def statistical_inefficiency(self, column=0, n_chains=1024, burn_in=0.2, max_lag=0):
         """Per-chain statistical inefficiency g (in units of measures) of one stored time-series column
         (``column`` indexes [parameters in the order real, Re c, Im c | energy | sigma]) for the first ``n_chains``

@@ -339,3 +339,23 @@ def test_statistical_inefficiency_kernel_matches_oracle_estimator():
         want = statistical_inefficiency(ts[150:, 0, ch])
         assert abs(g[ch] - want) <= 1e-9 * want, (ch, g[ch], want)
     assert np.all(g >= 1.0)
+
+
+def test_on_disk_time_series_formats(tmp_path):
+    """CSV in the reference's df.to_csv format (complex printed as (a+bj)) and the dense npz."""
+    import pandas
+    import metropolisengine_b200 as me
+    eng = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5), initial_real_params=np.array([0., 0.]),
+                              initial_complex_params=np.array([0j]), temp=.1, n_chains=8, seed=1)
+    eng.run(12, 3)
+    path = eng.to_csv(str(tmp_path / "series.csv"), chain=2)
+    back = pandas.read_csv(path, index_col=0)
+    assert list(back.columns) == ["abs_param_0", "abs_param_1", "abs_param_2", "param_0_squared", "param_1_squared",
+                                  "total_energy", "param_0", "param_1", "real_group_sampling_width", "param_2",
+                                  "complex_group_sampling_width"]
+    assert len(back) == 12 and str(back["param_2"][0]).startswith("(") and str(back["param_2"][0]).endswith("j)")
+    c = back["param_2"].apply(complex)
+    assert np.allclose(np.abs(c), back["abs_param_2"], rtol=1e-12)
+    z = np.load(eng.save_npz(str(tmp_path / "series.npz")))
+    assert z["rows"].shape == (12, 6, 8) and list(z["columns"])[-2:] == ["energy", "sampling_width"]
+    assert np.allclose(z["rows"][:, 0, 2], back["param_0"], rtol=1e-15)
