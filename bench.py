@@ -275,7 +275,8 @@ def run_ours(args):
         M = args.measures
     n_r, n_c = wl["n_r"], wl["n_c"]
     d = n_r + 2 * n_c
-    ts_bytes = M * (d + 2) * chains * 8
+    ts_cols = d + (3 if (n_r and n_c) else 2)
+    ts_bytes = M * ts_cols * chains * 8
 
     def barrier():
         if world > 1:
@@ -338,7 +339,7 @@ def run_ours(args):
     pin_r = torch.zeros((chains, n_r), dtype=torch.float64).pin_memory() if n_r else None
     pin_c = torch.zeros((chains, n_c), dtype=torch.complex128).pin_memory() if n_c else None
     host_state = torch.empty((lay.WORDS, chains), dtype=torch.float64).pin_memory()
-    host_ts0 = torch.empty((M, d + 2), dtype=torch.float64).pin_memory()
+    host_ts0 = torch.empty((M, ts_cols), dtype=torch.float64).pin_memory()
     h2d = (pin_r.numel() * 8 if n_r else 0) + (pin_c.numel() * 16 if n_c else 0)
     d2h = host_state.numel() * 8 + host_ts0.numel() * 8 + (lay.POOL_WORDS + 1) * 8
 
@@ -388,7 +389,7 @@ def run_ours(args):
     g_steps = None
     if rank == 0:
         kw2 = dict(kw)
-        kw2.update(n_chains=4096, distributed=False, ts_chunk_bytes=4096 * (d + 2) * 8 * 6000)
+        kw2.update(n_chains=4096, distributed=False, ts_chunk_bytes=4096 * ts_cols * 8 * 6000)
         side = me.MetropolisEngine(wl["energy"], **kw2)
         side.record = False
         side.run(300, 10)                     # sigma / covariance adaptation
@@ -427,7 +428,7 @@ def run_ours(args):
                      "traffic": (tpm * chains * M) if tpm else None,
                      "traffic_note": "DRAM read+write bytes per launch: per chain-measure figure of the committed ncu "
                                      "--set full capture (profiles/r01_ncu_c2_k_run.csv) x this launch's "
-                                     "chain-measures; algorithmic %d B per chain-measure" % (8 * (d + 2)),
+                                     "chain-measures; algorithmic %d B per chain-measure" % (8 * ts_cols),
                      "fp64_pipe_busy_ncu": 0.40 if args.workload == "c2" else None,
                      "kernel": "me::k_run", "kernel_ms": ker_ms,
                      "algorithmic": "%d flop + %d special functions per chain-step (SURVEY.md §8d); special functions "

@@ -85,7 +85,7 @@ typedef struct me_layout {
     int32_t STATUS;   /* ME_STATUS_* bits                                                                      */
     int32_t WORDS;    /* total words per chain                                                                 */
     int32_t D;        /* NR + 2 NC                                                                             */
-    int32_t TS_COLS;  /* time-series columns per row: x[D], energy, sigma                                      */
+    int32_t TS_COLS;  /* time-series columns per row: x[D], energy, sigma (mixed engines: sigma_real, sigma_complex)  */
     int32_t POOL_WORDS; /* pooled-moment words: sum(x-s)[D], sum (x-s)(x-s)^T [D(D+1)/2 lower], sum obs [2NR+NC];
                            0 when the shape is too large for in-kernel pooling                               */
 } me_layout;
@@ -116,6 +116,12 @@ int me_set_energy_external(me_engine *eng);
  * NVRTC log. */
 int me_check_energy_source(const char *cuda_source, int32_t n_real, int32_t n_complex, int32_t use_reject,
                            int32_t strict, char *log, int64_t log_cap);
+
+/* Group-wise stepping of mixed engines: subsequent me_run / me_run_injected / me_propose /
+ * me_accept calls perform step_real_group (group 1, ME:225-239: only the real block is proposed, only
+ * real_group_sampling_width adapts, ME:440-446) or step_complex_group (group 2, ME:209-223, ME:449-456) instead of
+ * step_all (group 0).  For all-real / all-complex engines the three coincide (ME:46,56). */
+int me_set_group(me_engine *eng, int32_t group);
 
 /* Launch geometry the handle uses; the pool buffer has grid * POOL_WORDS doubles. */
 int me_launch_dims(me_engine *eng, int32_t *grid, int32_t *block);

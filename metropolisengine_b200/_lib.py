@@ -59,6 +59,7 @@ SIGNATURES = {
     "me_set_energy_source": (ctypes.c_int, [_vp, _cp, ctypes.POINTER(_f64), _i32, _i32]),
     "me_set_energy_external": (ctypes.c_int, [_vp]),
     "me_check_energy_source": (ctypes.c_int, [_cp, _i32, _i32, _i32, _i32, _cp, _i64]),
+    "me_set_group": (ctypes.c_int, [_vp, _i32]),
     "me_launch_dims": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "me_bind": (ctypes.c_int, [_vp, ctypes.POINTER(MeBuffers)]),
     "me_init": (ctypes.c_int, [_vp, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp]),

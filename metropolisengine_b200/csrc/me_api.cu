@@ -211,6 +211,7 @@ struct me_engine {
     int block = 128, grid = 1;
     int n_sm = 148;
     bool generic = false;              /* large shape: runtime-shape kernels, unfused step */
+    int group = 0;                     /* 0 step_all, 1 real group, 2 complex group (mixed engines) */
     std::string err;
 };
 
@@ -273,6 +274,7 @@ void base_params(me_engine *e, MeParams &p) {
     p.n_complex = e->cfg.n_complex;
     p.energy_id = e->energy_id;
     p.scratch = e->buf.scratch;
+    p.group = e->group;
 }
 
 /* Launch geometry.  One thread per chain, so the CTA size only trades scheduling granularity against the
@@ -423,7 +425,7 @@ int me_state_layout(int32_t nr, int32_t nc, me_layout *o) {
     o->STATUS = w; w += 1;
     o->WORDS = w;
     o->D = d;
-    o->TS_COLS = d + 2;
+    o->TS_COLS = d + ((nr > 0 && nc > 0) ? 3 : 2);
     const long long pw = (long long)d + (long long)d * (d + 1) / 2 + 2 * nr + nc;
     o->POOL_WORDS = pw <= ME_MAX_POOLW ? (int)pw : 0;
     return ME_OK;
@@ -494,6 +496,15 @@ int me_check_energy_source(const char *src, int32_t nr, int32_t nc, int32_t use_
         log[cap - 1] = 0;
     }
     return rc;
+}
+
+int me_set_group(me_engine *e, int32_t group) {
+    if (!e) return ME_ERR_INVALID;
+    if (group < 0 || group > 2) return fail(e, ME_ERR_INVALID, "group must be 0 (all), 1 (real) or 2 (complex)");
+    if (group == 1 && e->cfg.n_real == 0) return fail(e, ME_ERR_INVALID, "engine has no real parameters");
+    if (group == 2 && e->cfg.n_complex == 0) return fail(e, ME_ERR_INVALID, "engine has no complex parameters");
+    e->group = group;
+    return ME_OK;
 }
 
 int me_launch_dims(me_engine *e, int32_t *grid, int32_t *block) {

@@ -49,7 +49,8 @@ struct Lay {
     static constexpr int NACC = FACC + NCOVC;
     static constexpr int STATUS = NACC + 1;
     static constexpr int WORDS = STATUS + 1;
-    static constexpr int TSCOLS = D + 2;                       /* x[D], E, sigma */
+    static constexpr int NSIGCOL = (NR > 0 && NC > 0) ? 2 : 1;  /* mixed engines record both group widths */
+    static constexpr int TSCOLS = D + 1 + NSIGCOL;             /* x[D], E, sigma(s) */
     static constexpr int POOLW = D + D * (D + 1) / 2 + NOBS;   /* sum(x-s), sum (x-s)(x-s)^T lower, sum obs */
     static constexpr int KIND = (NR > 0 && NC > 0) ? 0 : (NR > 0 ? 1 : 2);   /* 0 mixed, 1 all-real, 2 all-complex */
     static constexpr int SIGIDX = (KIND == 2) ? 1 : 0;         /* which width step_all adapts (ME:46,56) */
@@ -510,6 +511,7 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
 
     const Rng rng(p, p.chain_offset + (unsigned long long)ch);
     const bool inject = STRICT && p.inj_delta != nullptr;
+    const int group = p.group;
     long long n = p.n_meas0;
     unsigned long long step = p.step0;
     long long s_local = 0;
@@ -535,6 +537,13 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
                 gen_draws<L, STRICT>(rng, (unsigned)(step + 1), tables, nxt);
                 apply_proposal<L>(c, cur.z, prop);
             }
+            if (L::KIND == 0 && group != 0) {       /* group-wise step: the other block keeps its value */
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    const bool real_block = i < L::NR;
+                    if (real_block != (group == 1)) prop[i] = c.x[i];
+                }
+            }
             accept = false;
             const bool wall = p.use_reject && Energy::reject(prop, prop + L::NR, prop + L::NR + L::NC, p.consts);
             if (!wall) {
@@ -549,9 +558,13 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
                     c.nacc += 1.0;
                 }
             }
-            const double sg = adapt_sigma<STRICT>(c.sig[L::SIGIDX], accept, g, p);
-            c.sig[L::SIGIDX] = sg;
-            if (L::KIND == 0) { c.sig[1] = sg; if (!(sg > 0)) c.status |= ME_STATUS_SIGMA_NONPOS; }
+            if (L::KIND == 0 && group != 0) {       /* ME:440-456: only the stepped group's width adapts */
+                c.sig[group - 1] = adapt_sigma<STRICT>(c.sig[group - 1], accept, g, p);
+            } else {
+                const double sg = adapt_sigma<STRICT>(c.sig[L::SIGIDX], accept, g, p);
+                c.sig[L::SIGIDX] = sg;
+                if (L::KIND == 0) { c.sig[1] = sg; if (!(sg > 0)) c.status |= ME_STATUS_SIGMA_NONPOS; }
+            }
             if (!inject) cur = nxt;
         }
         if (p.do_measure) {
@@ -569,7 +582,12 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
 #pragma unroll
                 for (int i = 0; i < D; i++) __stcs(row + (long long)i * ld, c.x[i]);
                 __stcs(row + (long long)D * ld, c.e);
-                __stcs(row + (long long)(D + 1) * ld, c.sig[L::SIGIDX]);
+                if (L::KIND == 0) {
+                    __stcs(row + (long long)(D + 1) * ld, c.sig[0]);
+                    __stcs(row + (long long)(D + 2) * ld, c.sig[1]);
+                } else {
+                    __stcs(row + (long long)(D + 1) * ld, c.sig[L::SIGIDX]);
+                }
             }
             if (pooling) {
                 if (POOL_REG) {
@@ -692,6 +710,11 @@ __device__ __forceinline__ void propose_body(const MeParams &p) {
         gen_draws<L, Cfg::STRICT>(rng, (unsigned)p.step0, tables, d);
         apply_proposal<L>(c, d.z, prop);
     }
+    if (L::KIND == 0 && p.group != 0) {
+#pragma unroll
+        for (int i = 0; i < D; i++)
+            if ((i < L::NR) != (p.group == 1)) prop[i] = c.x[i];
+    }
 #pragma unroll
     for (int i = 0; i < D; i++) p.prop[(long long)i * p.ld + ch] = prop[i];
 }
@@ -709,7 +732,9 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
     const long long ld = p.ld;
     double *st = p.state;
     double e = st[(long long)L::E * ld + ch];
-    double sg = st[(long long)(L::SIG + L::SIGIDX) * ld + ch];
+    const bool grouped = L::KIND == 0 && p.group != 0;
+    const int sidx = grouped ? p.group - 1 : L::SIGIDX;
+    double sg = st[(long long)(L::SIG + sidx) * ld + ch];
     int status = (int)st[(long long)L::STATUS * ld + ch];
     const Gains g = make_gains(p.n_meas0, p);
     bool accept = false;
@@ -737,8 +762,8 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
         }
     }
     sg = adapt_sigma<STRICT>(sg, accept, g, p);
-    st[(long long)(L::SIG + L::SIGIDX) * ld + ch] = sg;
-    if (L::KIND == 0) {
+    st[(long long)(L::SIG + sidx) * ld + ch] = sg;
+    if (L::KIND == 0 && !grouped) {
         st[(long long)(L::SIG + 1) * ld + ch] = sg;
         if (!(sg > 0)) status |= ME_STATUS_SIGMA_NONPOS;
     }

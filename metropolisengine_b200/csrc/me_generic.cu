@@ -160,6 +160,9 @@ __global__ void gk_propose(const __grid_constant__ MeParams p) {
     const int nr = L.nr, nc = L.nc, d = L.d;
     if (p.inj_delta != nullptr) {
         for (int i = 0; i < d; i++) pr[(long long)i * ld] = p.inj_delta[(long long)i * ld + ch] + ST(L.X + i);
+        if (nr > 0 && nc > 0 && p.group != 0)
+            for (int i = 0; i < d; i++)
+                if ((i < nr) != (p.group == 1)) pr[(long long)i * ld] = ST(L.X + i);
         return;
     }
     /* normals go to the scratch block first (z_k at scratch[k]) */
@@ -192,6 +195,9 @@ __global__ void gk_propose(const __grid_constant__ MeParams p) {
         pr[(long long)(nr + i) * ld] = ST(L.X + nr + i) + sc * are;
         pr[(long long)(nr + nc + i) * ld] = ST(L.X + nr + nc + i) + sc * aim;
     }
+    if (nr > 0 && nc > 0 && p.group != 0)          /* group-wise step: the other block keeps its value */
+        for (int i = 0; i < d; i++)
+            if ((i < nr) != (p.group == 1)) pr[(long long)i * ld] = ST(L.X + i);
 }
 
 /* decision + sigma adaptation (ME:247-258, 319-338, 429-456) */
@@ -205,7 +211,8 @@ __global__ void gk_accept(const __grid_constant__ MeParams p) {
     const long long ld = p.ld;
     double *st = p.state;
     const int kind = (L.nr > 0 && L.nc > 0) ? 0 : (L.nr > 0 ? 1 : 2);
-    const int sidx = kind == 2 ? 1 : 0;
+    const bool grouped = kind == 0 && p.group != 0;
+    const int sidx = grouped ? p.group - 1 : (kind == 2 ? 1 : 0);
     double sg = ST(L.SIG + sidx);
     int status = (int)ST(L.STATUS);
     const me::Gains g = me::make_gains(p.n_meas0, p);
@@ -234,7 +241,7 @@ __global__ void gk_accept(const __grid_constant__ MeParams p) {
     }
     sg = me::adapt_sigma<true>(sg, accept, g, p);
     ST(L.SIG + sidx) = sg;
-    if (kind == 0) {
+    if (kind == 0 && !grouped) {
         ST(L.SIG + 1) = sg;
         if (!(sg > 0)) status |= ME_STATUS_SIGMA_NONPOS;
     }
@@ -319,10 +326,16 @@ __global__ void gk_measure(const __grid_constant__ MeParams p) {
     ST(L.STATUS) = (double)status;
     if (p.record) {
         const int kind = (nr > 0 && nc > 0) ? 0 : (nr > 0 ? 1 : 2);
-        double *row = p.ts + p.ts_row0 * (long long)(d + 2) * ld + ch;
+        const int tscols = d + (kind == 0 ? 3 : 2);
+        double *row = p.ts + p.ts_row0 * (long long)tscols * ld + ch;
         for (int i = 0; i < d; i++) __stcs(row + (long long)i * ld, ST(L.X + i));
         __stcs(row + (long long)d * ld, ST(L.E));
-        __stcs(row + (long long)(d + 1) * ld, ST(L.SIG + (kind == 2 ? 1 : 0)));
+        if (kind == 0) {
+            __stcs(row + (long long)(d + 1) * ld, ST(L.SIG));
+            __stcs(row + (long long)(d + 2) * ld, ST(L.SIG + 1));
+        } else {
+            __stcs(row + (long long)(d + 1) * ld, ST(L.SIG + (kind == 2 ? 1 : 0)));
+        }
     }
 }
 

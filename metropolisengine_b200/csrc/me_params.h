@@ -5,7 +5,7 @@
 #ifndef ME_PARAMS_H
 #define ME_PARAMS_H
 
-#define ME_PARAMS_VERSION 5
+#define ME_PARAMS_VERSION 6
 #define ME_MAX_CONSTS 16
 
 /* status bits written to the per-chain STATUS word (SURVEY §5 "failure detection") */
@@ -57,6 +57,7 @@ struct MeParams {
     double *scratch;               /* [D][ld] per-chain scratch (old means during measure) */
     double *e_out;                 /* [ld] gk_energy output */
     unsigned char *rej_out;        /* [ld] gk_energy hard-wall output (may be NULL) */
+    int group;                     /* mixed engines: 0 = step_all (ME:241), 1 = step_real_group (ME:225), 2 = step_complex_group (ME:209) */
 };
 
 #endif

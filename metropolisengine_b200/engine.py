@@ -216,6 +216,7 @@ class MetropolisEngine:
         if self._terms is not None:
             full = self.state[:self._d]
             self._term_energy0 = {t: self._eval_term(fn, full).clone() for t, fn in self._terms["all"].items()}
+        self._group_mode = 0
         self.step_counter = 1                                                               # ME:72
         self.complex_group_step_counter = 1
         self.real_group_step_counter = 1
@@ -427,6 +428,47 @@ class MetropolisEngine:
         if self.n_chains_total == 1:
             return bool(self._last_accept.item())
         return self._last_accept.bool()
+
+    # ---- group-wise stepping (ME:209-239, 440-456)
+    def _set_group(self, group):
+        if group != self._group_mode:
+            self._check(self._lib.me_set_group(self._h, group))
+            self._group_mode = group
+
+    def _group_step(self, group, k=1):
+        self._set_group(group)
+        try:
+            self.step(k)
+        finally:
+            self._set_group(0)
+        if group == 2 and self._kind == "mixed":
+            self.step_counter += int(k)                                                     # ME:450
+        if self.n_chains_total == 1:
+            return bool(self._last_accept.item())
+        return self._last_accept.bool()
+
+    def step_real_group(self, k=1):
+        """Propose and decide the real block only, with its own width (ME:225-239, 440-446).  For all-real engines
+        this is ``step_all`` (ME:56)."""
+        if not self.num_real_params:
+            raise ValueError("engine has no real parameters")
+        return self._group_step(1 if self._kind == "mixed" else 0, k)
+
+    def step_complex_group(self, k=1):
+        """Propose and decide the complex block only, with its own width (ME:209-223, 449-456)."""
+        if not self.num_complex_params:
+            raise ValueError("engine has no complex parameters")
+        return self._group_step(2 if self._kind == "mixed" else 0, k)
+
+    def run_injected_group(self, group, delta, u, k):
+        """Parity mode for group steps: ``k`` injected steps of one group (no measure)."""
+        self._set_group(group if self._kind == "mixed" else 0)
+        try:
+            self.run_injected(delta, u, 1, k, do_measure=False)
+        finally:
+            self._set_group(0)
+        if group == 2 and self._kind == "mixed":
+            self.step_counter += int(k)
 
     def _step_external(self, inj_delta=None, inj_u=None):
         prop = torch.empty((self._d, self.n_chains), dtype=torch.float64, device=self.device)
@@ -720,7 +762,7 @@ class MetropolisEngine:
     # ------------------------------------------------------------------ output (ME:466-479)
     def time_series(self):
         """All recorded rows as one tensor [rows, TS_COLS, n_chains] (columns: parameters in the order
-        [real, Re c, Im c], live energy, sampling width)."""
+        [real, Re c, Im c], live energy, sampling width — both group widths for mixed engines)."""
         parts = [t[:used] for t, used in self._ts_chunks if used]
         if not parts:
             return torch.empty((0, self._lay.TS_COLS, self.n_chains), dtype=torch.float64, device=self.device)
@@ -734,7 +776,7 @@ class MetropolisEngine:
         import pandas
         nr, nc, d = self.num_real_params, self.num_complex_params, self._d
         parts = [t[:used, :, chain] for t, used in self._ts_chunks if used]
-        rows = (torch.cat(parts, dim=0) if parts else torch.empty((0, d + 2), dtype=torch.float64)).cpu().numpy()
+        rows = (torch.cat(parts, dim=0) if parts else torch.empty((0, self._lay.TS_COLS), dtype=torch.float64)).cpu().numpy()
         x = rows[:, :nr]
         c = rows[:, nr:nr + nc] + 1j * rows[:, nr + nc:d]
         cols = {}
@@ -757,7 +799,7 @@ class MetropolisEngine:
         if nc:
             for j in range(nc):
                 cols[self.params_names[nr + j]] = c[:, j]
-            cols["complex_group_sampling_width"] = rows[:, d + 1]
+            cols["complex_group_sampling_width"] = rows[:, d + 2] if self._kind == "mixed" else rows[:, d + 1]
         self.df = pandas.DataFrame.from_dict(cols)
         return self.df
 
@@ -776,7 +818,9 @@ class MetropolisEngine:
         ts = self.time_series().cpu().numpy()
         nr, nc = self.num_real_params, self.num_complex_params
         cols = ([self.params_names[i] for i in range(nr)] + ["Re_" + self.params_names[nr + j] for j in range(nc)]
-                + ["Im_" + self.params_names[nr + j] for j in range(nc)] + ["energy", "sampling_width"])
+                + ["Im_" + self.params_names[nr + j] for j in range(nc)] + ["energy"]
+                + (["real_group_sampling_width", "complex_group_sampling_width"] if self._kind == "mixed"
+                   else ["sampling_width"]))
         np.savez_compressed(path, rows=ts, columns=np.array(cols), chain_offset=self.chain_offset,
                             observables_names=np.array(self.observables_names))
         return path

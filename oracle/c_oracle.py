@@ -44,6 +44,7 @@ def lib():
     if _lib is None:
         _lib = ctypes.CDLL(build())
         _lib.meo_run.restype = ctypes.c_int
+        _lib.meo_run_group.restype = ctypes.c_int
         _lib.meo_uniform.restype = ctypes.c_double
         _lib.meo_uniform.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int]
     return _lib
@@ -104,7 +105,8 @@ class CChain:
         lib().meo_init(ctypes.byref(self.cfg), _dp(self.state), _dp(x0), ctypes.c_double(sampling_width),
                        _dp(cr), _dp(cre), _dp(cim))
 
-    def run(self, n_blocks, spm, do_measure=True, delta=None, u=None, seed=0, chain_id=0, step0=0, want_ts=False):
+    def run(self, n_blocks, spm, do_measure=True, delta=None, u=None, seed=0, chain_id=0, step0=0, want_ts=False,
+            group=0):
         S = n_blocks * spm
         acc = np.zeros(max(S, 1), dtype=np.uint8)
         ts = np.zeros((max(n_blocks, 1), self.d + 3)) if want_ts else None
@@ -114,10 +116,10 @@ class CChain:
             mode = INJECT
         else:
             mode = PHILOX
-        rc = lib().meo_run(ctypes.byref(self.cfg), _dp(self.state), mode, ctypes.c_int64(n_blocks),
-                           ctypes.c_int64(spm), int(do_measure), ctypes.byref(self.n_measure), _dp(delta), _dp(u),
-                           ctypes.c_uint64(seed), ctypes.c_uint64(chain_id), ctypes.c_uint64(step0),
-                           acc.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)), _dp(ts))
+        rc = lib().meo_run_group(ctypes.byref(self.cfg), _dp(self.state), mode, ctypes.c_int64(n_blocks),
+                                 ctypes.c_int64(spm), int(do_measure), ctypes.byref(self.n_measure), _dp(delta), _dp(u),
+                                 ctypes.c_uint64(seed), ctypes.c_uint64(chain_id), ctypes.c_uint64(step0),
+                                 acc.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)), _dp(ts), int(group))
         assert rc == 0
         return acc[:S].astype(bool), ts
 

@@ -335,9 +335,22 @@ static void measure(const meo_config *c, double *st, const meo_offsets *o, int64
  * n_measure: in/out measure_step_counter (starts at 1, ME:73).
  * accept_out[step] (may be NULL); ts_out rows of (d + 3): x[d], E, sigma_r, sigma_c (may be NULL).
  */
+int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, int64_t spm, int do_measure,
+                  int64_t *n_measure, const double *delta, const double *u, uint64_t seed, uint64_t chain_id,
+                  uint64_t step0, unsigned char *accept_out, double *ts_out, int group);
+
 int meo_run(const meo_config *c, double *st, int mode, int64_t n_blocks, int64_t spm, int do_measure,
             int64_t *n_measure, const double *delta, const double *u, uint64_t seed, uint64_t chain_id,
             uint64_t step0, unsigned char *accept_out, double *ts_out) {
+    return meo_run_group(c, st, mode, n_blocks, spm, do_measure, n_measure, delta, u, seed, chain_id, step0,
+                         accept_out, ts_out, 0);
+}
+
+/* group: 0 = step_all; for mixed engines 1 = step_real_group (ME:225-239), 2 = step_complex_group (ME:209-223):
+ * only that block is proposed and only that group's width adapts (ME:440-456). */
+int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, int64_t spm, int do_measure,
+                  int64_t *n_measure, const double *delta, const double *u, uint64_t seed, uint64_t chain_id,
+                  uint64_t step0, unsigned char *accept_out, double *ts_out, int group) {
     meo_offsets o;
     const int n_r = c->n_r, n_c = c->n_c, d = n_r + 2 * n_c;
     if (d > MEO_MAX_D) return -1;
@@ -382,6 +395,9 @@ int meo_run(const meo_config *c, double *st, int mode, int64_t n_blocks, int64_t
                     prop[n_r + n_c + i] = x[n_r + n_c + i] + (sc * rs) * aim;
                 }
             }
+            if (kind == 0 && group != 0)
+                for (int i = 0; i < d; i++)
+                    if ((i < n_r) != (group == 1)) prop[i] = x[i];
             int accept = 0;
             if (!reject_eval(c, prop)) {
                 double e_new = energy_eval(c, prop);
@@ -398,11 +414,12 @@ int meo_run(const meo_config *c, double *st, int mode, int64_t n_blocks, int64_t
             /* sigma adaptation (ME:429-456) */
             {
                 double f = (double)n / (double)c->m; if (!(f > 200.0)) f = 200.0;
-                double *sg = (kind == 2) ? &st[o.SIG + 1] : &st[o.SIG];
+                const int grouped = (kind == 0 && group != 0);
+                double *sg = grouped ? &st[o.SIG + group - 1] : ((kind == 2) ? &st[o.SIG + 1] : &st[o.SIG]);
                 double cc = (*sg) * c->ratio;
                 if (accept) *sg = *sg + (cc * (1 - p)) / f;
                 else *sg = *sg - (cc * p) / f;
-                if (kind == 0) { st[o.SIG + 1] = st[o.SIG]; if (!(st[o.SIG] > 0)) st[o.STATUS] = 2.0; }
+                if (kind == 0 && !grouped) { st[o.SIG + 1] = st[o.SIG]; if (!(st[o.SIG] > 0)) st[o.STATUS] = 2.0; }
             }
             if (accept_out) accept_out[s] = (unsigned char)accept;
         }

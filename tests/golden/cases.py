@@ -65,6 +65,12 @@ def cases():
                           ctor=dict(initial_real_params=np.array([0.2]),
                                     initial_complex_params=np.zeros(64, dtype=complex), temp=.1,
                                     sampling_width=0.012)),
+        # group-wise stepping of a mixed engine: step_real_group / step_complex_group alternate,
+        # each with its own width (metropolis_engine.py:209-239, 440-456)
+        "groups_2r1c": dict(energy=en.demo_2r1c, builtin=("mixed_well", [1.0, -1.0, 0.5]), n_measures=70,
+                            steps_per_measure=8, seed=17, schedule="groups",
+                            ctor=dict(initial_real_params=np.array([0.3, 0.2]),
+                                      initial_complex_params=np.array([0.4 - 0.1j]), temp=.1)),
         # temp = 0 (the constructor default): greedy descent, no uniform is ever drawn (metropolis_engine.py:331-332)
         "xy_temp0": dict(energy=en.xy_well, builtin=("xy_well", [1.0]), n_measures=60, steps_per_measure=4, seed=7,
                          ctor=dict(initial_real_params=np.array([1.0, -2.0]), temp=0)),

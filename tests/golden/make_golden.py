@@ -91,7 +91,7 @@ class Tap:
         random.uniform = self._orig_uniform
 
 
-def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=None, df=True, **ctor):
+def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=None, df=True, schedule="all", **ctor):
     """Drive the reference exactly like the README/demo loops and record everything."""
     np.random.seed(seed)
     random.seed(seed)
@@ -117,6 +117,7 @@ def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=Non
     zs = np.zeros((S, d))
     us = np.full(S, np.nan)
     acc = np.zeros(S, dtype=np.bool_)
+    group = np.zeros(S, dtype=np.int32)      # 0 = step_all, 1 = step_real_group, 2 = step_complex_group
     step_x = np.zeros((S, d))
     step_sig = np.zeros((S, 3))
     step_energy = np.zeros(S)
@@ -125,9 +126,9 @@ def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=Non
     mixed = n_r > 0 and n_c > 0
 
     def live_energy():
-        # all-real / all-complex engines keep the live energy in eng.energy;
-        # mixed engines keep it in eng.energy_total (metropolis_engine.py:255)
-        if mixed:
+        # all-real / all-complex engines and group steps keep the live energy in eng.energy;
+        # the mixed step_all keeps it in eng.energy_total (metropolis_engine.py:255)
+        if mixed and schedule != "groups":
             return float(np.real(eng.energy_total))
         return float(np.real(sum(eng.energy.values())))
 
@@ -136,12 +137,18 @@ def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=Non
         for im in range(n_measures):
             for _ in range(steps_per_measure):
                 nd, nu = len(tap.draws), len(tap.uniforms)
-                a = eng.step_all()
-                new = tap.draws[nd:]
-                parts = [inc for (inc, _z) in new]
-                zparts = [z for (_inc, z) in new]
-                delta[s] = np.concatenate(parts)
-                zs[s] = np.concatenate(zparts)
+                if schedule == "groups":       # alternate the two group steps (how the cylinder app drives it)
+                    group[s] = 1 + (s % 2)
+                    a = eng.step_real_group() if group[s] == 1 else eng.step_complex_group()
+                    (inc, z), = tap.draws[nd:]
+                    sl = slice(0, n_r) if group[s] == 1 else slice(n_r, d)
+                    delta[s, sl] = inc
+                    zs[s, sl] = z
+                else:
+                    a = eng.step_all()
+                    new = tap.draws[nd:]
+                    delta[s] = np.concatenate([inc for (inc, _z) in new])
+                    zs[s] = np.concatenate([z for (_inc, z) in new])
                 if len(tap.uniforms) > nu:
                     assert len(tap.uniforms) == nu + 1
                     us[s] = tap.uniforms[-1]
@@ -167,7 +174,7 @@ def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=Non
                                  else np.zeros((0, 0), complex))
             snap["obs_mean"].append(np.array(eng.observables_mean, dtype=np.float64))
             snap["obs"].append(np.array(eng.observables, dtype=np.float64))
-    rec.update(delta=delta, z=zs, u=us, accept=acc, step_x=step_x, step_sigma=step_sig, step_energy=step_energy)
+    rec.update(group=group, delta=delta, z=zs, u=us, accept=acc, step_x=step_x, step_sigma=step_sig, step_energy=step_energy)
     for k, v in snap.items():
         rec["m_" + k] = np.array(v)
     rec["measure_step_counter"] = int(eng.measure_step_counter)
@@ -243,7 +250,7 @@ def single_chain_cases(me):
     from tests.golden.cases import cases, fresh_ctor
     for name, case in cases().items():
         run_case(me, name, case["energy"], case["n_measures"], case["steps_per_measure"], seed=case["seed"],
-                 reject=case.get("reject"), **fresh_ctor(case))
+                 reject=case.get("reject"), schedule=case.get("schedule", "all"), **fresh_ctor(case))
 
 
 def _ensemble_worker(args):

@@ -56,7 +56,7 @@ def test_state_layout_matches_oracle_layout(lib, nr, nc):
     for k in ("X", "E", "SIG", "MEAN", "COVR", "COVC", "OBSM", "FACR", "FACC", "NACC", "STATUS", "WORDS"):
         assert getattr(lay, k) == getattr(o, k), k
     d = nr + 2 * nc
-    assert lay.D == d and lay.TS_COLS == d + 2
+    assert lay.D == d and lay.TS_COLS == d + (3 if (nr and nc) else 2)   # mixed engines record both group widths
     pw = d + d * (d + 1) // 2 + 2 * nr + nc
     assert lay.POOL_WORDS == (pw if pw <= 600 else 0)
     # unique persistent words 8 / 16 / 78 for C1-C3 (+ factors, accept count, status here)

@@ -357,5 +357,51 @@ def test_on_disk_time_series_formats(tmp_path):
     c = back["param_2"].apply(complex)
     assert np.allclose(np.abs(c), back["abs_param_2"], rtol=1e-12)
     z = np.load(eng.save_npz(str(tmp_path / "series.npz")))
-    assert z["rows"].shape == (12, 6, 8) and list(z["columns"])[-2:] == ["energy", "sampling_width"]
+    assert z["rows"].shape == (12, 7, 8) and list(z["columns"])[-3] == "energy"
     assert np.allclose(z["rows"][:, 0, 2], back["param_0"], rtol=1e-15)
+
+
+def test_group_wise_stepping_injected_parity():
+    """step_real_group / step_complex_group on a mixed engine, each with its own width
+    (ME:209-239, 440-456), alternating as the cylinder app drives them; draw-injected against the reference."""
+    import metropolisengine_b200 as me
+    eng, g = make_engine("groups_2r1c", me, strict=True)
+    M, K = int(g["n_measures"]), int(g["steps_per_measure"])
+    nacc = 0
+    for im in range(M):
+        for s in range(im * K, (im + 1) * K):
+            eng.run_injected_group(int(g["group"][s]), g["delta"][s:s + 1], g["u"][s:s + 1], 1)
+            nacc += int(g["accept"][s])
+        eng.measure()
+        assert int(eng.accept_count_per_chain.item()) == nacc, im
+        assert close(eng.real_params, g["m_x"][im]) and close(eng.complex_params, g["m_c"][im]), im
+        assert close(eng.real_group_sampling_width, g["m_sigma_r"][im]), im
+        assert close(eng.complex_group_sampling_width, g["m_sigma_c"][im]), im
+        assert close(eng.covariance_matrix_real, g["m_cov_r"][im]) and close(eng.covariance_matrix_complex, g["m_cov_c"][im])
+        assert close(eng.energy["total"], g["m_energy"][im], 1e-11), im
+    assert eng.real_group_sampling_width != eng.complex_group_sampling_width
+    assert eng.step_counter == 1 + M * K // 2                      # only complex-group steps count (ME:450)
+    df = eng.save_time_series()
+    assert close(df["real_group_sampling_width"], g["m_sigma_r"]) and close(df["complex_group_sampling_width"], g["m_sigma_c"])
+
+
+def test_group_wise_stepping_philox_matches_c_oracle():
+    import metropolisengine_b200 as me
+    from oracle import c_oracle as co
+    kw = dict(initial_real_params=np.array([0.3, 0.2]), initial_complex_params=np.array([0.4 - 0.1j]), temp=.1)
+    eng = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5), n_chains=32, seed=8, **kw)
+    o = co.CChain(2, 1, "mixed_well", consts=[1.0, -1.0, 0.5], temp=.1, x0=np.array([0.3, 0.2, 0.4, -0.1]))
+    step = 0
+    for im in range(55):
+        for _ in range(3):
+            eng.step_real_group(2)
+            o.run(1, 2, False, seed=8, chain_id=5, step0=step, group=1); step += 2
+            acc = eng.step_complex_group()
+            o.run(1, 1, False, seed=8, chain_id=5, step0=step, group=2); step += 1
+        eng.measure()
+        o.run(1, 0, True, seed=8, chain_id=5, step0=step)
+    assert acc.shape == (32,)
+    st = eng.state.cpu().numpy()
+    assert close(st[:eng._lay.WORDS - 2, 5], o.state[:eng._lay.WORDS - 2], 2e-9)
+    with pytest.raises(ValueError):
+        me.MetropolisEngine("x2", initial_real_params=[0.0], temp=.1).step_complex_group()

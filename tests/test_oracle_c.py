@@ -60,7 +60,15 @@ def test_c_oracle_injected_matches_reference(name, builtin):
     n_r, n_c, d = ch.n_r, ch.n_c, ch.d
     for im in range(M):
         sl = slice(im * K, (im + 1) * K)
-        acc, ts = ch.run(1, K, True, delta=g["delta"][sl], u=g["u"][sl], want_ts=True)
+        if "group" in g and g["group"].any():          # group-wise schedule: one step at a time, then the measure
+            acc = []
+            for s in range(im * K, (im + 1) * K):
+                a, _ = ch.run(1, 1, False, delta=g["delta"][s:s + 1], u=g["u"][s:s + 1], group=int(g["group"][s]))
+                acc.append(a[0])
+            _, ts = ch.run(1, 0, True, delta=g["delta"][:1], u=g["u"][:1], want_ts=True)
+            acc = np.array(acc)
+        else:
+            acc, ts = ch.run(1, K, True, delta=g["delta"][sl], u=g["u"][sl], want_ts=True)
         assert np.array_equal(acc, g["accept"][sl]), "decisions differ in block %d" % im
         assert rel_close(ch.x, g["step_x"][(im + 1) * K - 1])
         assert rel_close(ch.energy, g["m_energy"][im])
