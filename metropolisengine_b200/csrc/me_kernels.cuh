@@ -15,8 +15,12 @@ struct Cfg {
     using Energy = EnergyT<NR_, NC_>;
 };
 
+/* Small problems are capped at 128 registers: 65,536 chains are 14 warps per SM, which must all be resident in one
+ * wave (<= 146 registers), and multi-million-chain ensembles get 4 warps per SM sub-partition. */
 template <class C>
-__global__ void __launch_bounds__(ME_MAX_BLOCK) k_run(const __grid_constant__ MeParams p) { run_body<C>(p); }
+__global__ void __launch_bounds__(ME_MAX_BLOCK, (C::NR + 2 * C::NC <= 4) ? 2 : 1) k_run(const __grid_constant__ MeParams p) {
+    run_body<C>(p);
+}
 template <class C>
 __global__ void __launch_bounds__(ME_MAX_BLOCK) k_init(const __grid_constant__ MeParams p) { init_body<C>(p); }
 template <class C>

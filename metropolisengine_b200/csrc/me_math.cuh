@@ -59,7 +59,9 @@ __device__ __forceinline__ double neg2log_unit(double u, const MathTables &T) {
     const int e = (hi >> 20) - 1023 + (i >= 53 ? 1 : 0);
     const double rc = T.logt[i][0], l = T.logt[i][1];
     const double r = fma(m, rc, -1.0);
-    /* log1p(r) = r - r^2/2 + r^3/3 - ... - r^8/8 ; |r| <= 2^-7 -> truncation below 2^-66 */
+    /* log1p(r) = r - r^2/2 + r^3/3 - ... - r^8/8 ; |r| <= 2^-7 -> truncation below 2^-66.  Horner on purpose:
+       the Estrin forms of this and of the sin/cos/exp polynomials (dependency depth 4 instead of 8) were measured
+       and are NOT faster here (7.3e10 vs 7.6e10 chain-steps/s, 164 instead of 114 registers uncapped). */
     double p = fma(r, -0.125, me_kc[0]);
     p = fma(r, p, me_kc[1]);
     p = fma(r, p, me_kc[2]);
