@@ -80,22 +80,14 @@ __device__ __forceinline__ U4 philox4x32_10(unsigned c0, unsigned c1, unsigned c
     return o;
 }
 
-/* 53-bit uniform on [0,1): (hi>>5)*2^-27 + (lo>>6)*2^-53 — the bit recipe of CPython's random.random(), the
- * generator behind the reference's accept test (metropolis_engine.py:335).  Integer->double conversion is done
- * with exponent-biased magic numbers (exact, 3 DADD, no I2F). */
-__device__ __forceinline__ double u53(unsigned hi, unsigned lo) {
-    const double a = __hiloint2double(0x43300000 - (27 << 20), (int)(hi >> 5)) - 33554432.0;   /* (hi>>5) * 2^-27 */
-    const double b = __hiloint2double(0x43300000 - (53 << 20), (int)(lo >> 6)) - 0.5;          /* (lo>>6) * 2^-53 */
-    return a + b;
-}
-
 /* Stream definition (identical in oracle/me_oracle.c): per step and chain, Philox call q = 0..ceil(D/2)-1 with
  * counter (chain_lo, chain_hi, step, q), key = seed, output words (x, y, z, w):
- *   radius uniform u1 = u53(x, y) + 2^-53 in (0,1];  angle t = z 2^-31 in [0,2);
+ *   radius uniform  u1 = (K + 1/2) 2^-52 in (0,1),  K = y : x[31:12]  (52 bits);   angle t = z 2^-31 in [0,2);
  *   z_{2q} = sqrt(-2 ln u1) cos(pi t), z_{2q+1} = sqrt(-2 ln u1) sin(pi t);
- *   accept uniform: u53(w_0, w_1) when there are two or more calls, otherwise the 43 bits
- *   w_0 : (x_0 & 31) : (y_0 & 63) — the bits u53 discards.  One Philox call per Gaussian pair, nothing else. */
-struct Spare { unsigned w0, w1, lo11; };
+ *   accept uniform  u = A 2^-44 in [0,1),  A = w_0 : x_0[11:0]  (44 bits of call 0 that the normals do not use).
+ * One Philox call per Gaussian pair, nothing else.  Both uniforms are assembled as the mantissa of a double in
+ * [1,2) and shifted down with ONE exact subtraction (no integer->double conversion, no magic-number pairs). */
+struct Spare { unsigned w0, x0; };
 
 struct Rng {
     unsigned c0, c1;
@@ -106,24 +98,23 @@ struct Rng {
         return philox4x32_10(c0, c1, step, slot, rk);
     }
     template <bool STRICT>
-    __device__ __forceinline__ static void box_muller(const U4 &r, const MathTables &T, double &z0, double &z1) {
-        const double u1 = u53(r.x, r.y) + 1.1102230246251565e-16;                                   /* (0,1] */
-        const double t = __hiloint2double(0x43300000 - (31 << 20), (int)r.z) - 2097152.0;           /* z 2^-31 */
-        const double rad = sqrt(STRICT ? -2.0 * log(u1) : neg2log_unit(u1, T));
+    __device__ __forceinline__ static void box_muller(const U4 &r, const MathTables &T, double &z0, double &z1,
+                                                      const double unit = ME_C_UNIT, const double angle = ME_C_ANGLE) {
+        const double d = __hiloint2double((int)(0x3ff00000u | (r.y >> 12)), (int)((r.y << 20) | (r.x >> 12)));
+        const double u1 = d - unit;                                                     /* d - (1 - 2^-53), exact */
+        const double rad = STRICT ? sqrt(-2.0 * log(u1)) : sqrt_pos(neg2log_unit(u1, T));
         double s, c;
-        sincospi_02(t, s, c);
+        sincospi_bits(r.z, s, c, angle);
         z0 = rad * c;
         z1 = rad * s;
     }
     __device__ __forceinline__ static void keep_spare(const U4 &r, int q, Spare &sp) {
-        if (q == 0) { sp.w0 = r.w; sp.lo11 = ((r.x & 31u) << 6) | (r.y & 63u); }
-        if (q == 1) sp.w1 = r.w;
+        if (q == 0) { sp.w0 = r.w; sp.x0 = r.x; }
     }
-    __device__ __forceinline__ static double accept_uniform(const Spare &sp, int n_calls) {
-        if (n_calls >= 2) return u53(sp.w0, sp.w1);
-        const double a = __hiloint2double(0x43300000 - (32 << 20), (int)sp.w0) - 1048576.0;         /* w0 2^-32 */
-        const double b = __hiloint2double(0x43300000 - (43 << 20), (int)sp.lo11) - 512.0;           /* lo11 2^-43 */
-        return a + b;
+    __device__ __forceinline__ static double accept_uniform(const Spare &sp) {
+        const double d = __hiloint2double((int)(0x3ff00000u | (sp.w0 >> 12)),
+                                          (int)((sp.w0 << 20) | ((sp.x0 & 0xfffu) << 8)));
+        return d - 1.0;
     }
 };
 
@@ -136,6 +127,7 @@ struct Chain {
     double facr[nz(L::NCOVR)];
     double facc[nz(L::NCOVC)];
     double nacc;
+    unsigned nacc_new;      /* acceptances of this launch (integer add in the step loop; folded into nacc on store) */
     int status;
 };
 
@@ -159,6 +151,7 @@ __device__ __forceinline__ void load_chain(Chain<L> &c, const double *st, long l
 #pragma unroll
     for (int i = 0; i < L::NCOVC; i++) c.facc[i] = st[(long long)(L::FACC + i) * ld + ch];
     c.nacc = st[(long long)L::NACC * ld + ch];
+    c.nacc_new = 0u;
     c.status = (int)st[(long long)L::STATUS * ld + ch];
 }
 
@@ -173,7 +166,7 @@ __device__ __forceinline__ void store_chain(const Chain<L> &c, double *st, long 
     for (int i = 0; i < L::NCOVR; i++) st[(long long)(L::FACR + i) * ld + ch] = c.facr[i];
 #pragma unroll
     for (int i = 0; i < L::NCOVC; i++) st[(long long)(L::FACC + i) * ld + ch] = c.facc[i];
-    st[(long long)L::NACC * ld + ch] = c.nacc;
+    st[(long long)L::NACC * ld + ch] = c.nacc + (double)c.nacc_new;
     st[(long long)L::STATUS * ld + ch] = (double)c.status;
 }
 
@@ -267,17 +260,18 @@ struct Draws {                 /* everything random one step consumes; independe
 };
 
 template <class L, bool STRICT>
-__device__ __forceinline__ void gen_draws(const Rng &rng, unsigned step, const MathTables &T, Draws<L> &d) {
+__device__ __forceinline__ void gen_draws(const Rng &rng, unsigned step, const MathTables &T, Draws<L> &d,
+                                          const Pins &pins) {
     constexpr int NQ = (L::D + 1) / 2;
     Spare sp;
-    sp.w0 = sp.w1 = sp.lo11 = 0;
+    sp.w0 = sp.x0 = 0;
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
         const U4 r = rng.bits(step, (unsigned)q);
         Rng::keep_spare(r, q, sp);
-        Rng::box_muller<STRICT>(r, T, d.z[2 * q], d.z[2 * q + 1]);
+        Rng::box_muller<STRICT>(r, T, d.z[2 * q], d.z[2 * q + 1], pins.unit, pins.angle);
     }
-    d.u = Rng::accept_uniform(sp, NQ);
+    d.u = Rng::accept_uniform(sp);
 }
 
 template <class L>
@@ -311,7 +305,9 @@ __device__ __forceinline__ void apply_proposal(const Chain<L> &c, const double *
 /* ------------------------------------------------------------------------------------------ decision + adaptation */
 struct Gains {            /* per measure-block constants of the Robbins-Monro update (ME:429-456) */
     double f;             /* max(n_measure / m, 200) */
-    double up, down;      /* fast mode: ratio (1 - target) / f and ratio target / f */
+    double up, ndown;     /* fast mode: ratio (1 - target) / f and -ratio target / f */
+    double k64;           /* pinned 64/ln2 of exp_nonpos */
+    bool hot;             /* temp != 0 */
 };
 
 __device__ __forceinline__ Gains make_gains(long long n_meas, const MeParams &p) {
@@ -320,24 +316,28 @@ __device__ __forceinline__ Gains make_gains(long long n_meas, const MeParams &p)
     if (!(f > 200.0)) f = 200.0;
     g.f = f;
     g.up = p.ratio * (1 - p.target) / f;
-    g.down = p.ratio * p.target / f;
+    g.ndown = -(p.ratio * p.target / f);
     /* keep the two quotients as values: without this the compiler sinks the division into the step loop
        (select the numerator by `accept`, divide once per step) */
-    asm volatile("" : "+d"(g.up), "+d"(g.down));
+    asm volatile("" : "+d"(g.up), "+d"(g.ndown));
+    g.hot = p.temp != 0;
+    g.k64 = ME_C_64_LN2;
     return g;
 }
 
 /* Metropolis test (ME:319-338): ties accept; T == 0 rejects every uphill move; otherwise u <= exp(-1*diff/T). */
 template <bool STRICT>
-__device__ __forceinline__ bool decide(double diff, double u, const MeParams &p, const MathTables &T) {
+__device__ __forceinline__ bool decide(double diff, double u, const MeParams &p, const MathTables &T, bool hot,
+                                       const double k64 = ME_C_64_LN2) {
     if (STRICT) {
         if (diff <= 0) return true;
         if (p.temp == 0) return false;
         return u <= exp(-1 * diff / p.temp);
     }
-    /* throughput build: branch-free (every lane evaluates the exponential; downhill lanes ignore it) */
-    const double prob = exp_nonpos(fmin(-diff * p.inv_temp, 0.0), T);
-    return (diff <= 0) | ((p.temp != 0) & (u <= prob));
+    /* throughput build: branch-free (every lane evaluates the exponential; downhill lanes ignore its value, which
+       is unspecified for a positive argument) */
+    const double prob = exp_nonpos(-diff * p.inv_temp, T, k64);
+    return (diff <= 0) | (hot & (u <= prob));
 }
 
 template <bool STRICT>
@@ -346,7 +346,7 @@ __device__ __forceinline__ double adapt_sigma(double sig, bool accept, const Gai
         const double c = sig * p.ratio;
         return accept ? sig + (c * (1 - p.target)) / g.f : sig - (c * p.target) / g.f;
     }
-    return accept ? sig + sig * g.up : sig - sig * g.down;
+    return fma(sig, accept ? g.up : g.ndown, sig);
 }
 
 /* ------------------------------------------------------------------------------------------ measure (ME:342-427)
@@ -488,12 +488,12 @@ __device__ __forceinline__ bool finish_step(Chain<Lay<Cfg::NR, Cfg::NC>> &c, dou
         const double e_new = Energy::eval(prop, prop + L::NR, prop + L::NR + L::NC, p.consts);
         if (e_new != e_new) c.status |= ME_STATUS_ENERGY_NAN;
         const double diff = e_new - c.e;
-        accept = decide<STRICT>(diff, u, p, tables);
+        accept = decide<STRICT>(diff, u, p, tables, g.hot, g.k64);
         if (accept) {
             c.e = e_new;
 #pragma unroll
             for (int i = 0; i < D; i++) c.x[i] = prop[i];
-            c.nacc += 1.0;
+            c.nacc_new += 1u;
         }
     }
     if (L::KIND == 0 && group != 0) {       /* ME:440-456: only the stepped group's width adapts */
@@ -555,7 +555,6 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     const bool inject = STRICT && p.inj_delta != nullptr;
     const int group = p.group;
     long long n = p.n_meas0;
-    unsigned long long step = p.step0;
     long long s_local = 0;
     bool accept = false;
 
@@ -564,24 +563,41 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
        the instruction-level parallelism of a warp, which is what limits this kernel when an ensemble gives each
        SM sub-partition only 3-4 warps (65,536 chains on 148 SMs). */
     Draws<L> cur;
-    if (!inject && p.spm > 0) gen_draws<L, STRICT>(rng, (unsigned)step, tables, cur);
+    const Pins pins = load_pins(tables);
+    if (!inject && p.spm > 0) gen_draws<L, STRICT>(rng, (unsigned)p.step0, tables, cur, pins);
     /* (Running the steps in pairs — two independent draw chains in flight — was measured and is NOT faster:
        7.3e10 vs 7.6e10 chain-steps/s on the xy-well at 65,536 chains; one step of look-ahead is the sweet spot.) */
 
-    for (long long b = 0; b < p.n_blocks; b++) {
-        const Gains g = make_gains(n, p);
-        for (long long k = 0; k < p.spm; k++, step++, s_local++) {
-            double prop[D];
-            Draws<L> nxt;
-            if (inject) {
+    /* one step: consumes the draws in `use`, generates the draws of the following step into `make` */
+    unsigned step32 = (unsigned)p.step0;
+    auto one_step = [&](const Gains &g, Draws<L> &use, Draws<L> &make) {
+        double prop[D];
+        if (inject) {
 #pragma unroll
-                for (int i = 0; i < D; i++) prop[i] = p.inj_delta[(s_local * D + i) * ld + ch] + c.x[i];
-                cur.u = p.inj_u[s_local * ld + ch];
-            } else {
-                gen_draws<L, STRICT>(rng, (unsigned)(step + 1), tables, nxt);
-                apply_proposal<L>(c, cur.z, prop);
-            }
-            accept = finish_step<Cfg>(c, prop, cur.u, g, p, tables, group);
+            for (int i = 0; i < D; i++) prop[i] = p.inj_delta[(s_local * D + i) * ld + ch] + c.x[i];
+            use.u = p.inj_u[s_local * ld + ch];
+            s_local++;
+        } else {
+            gen_draws<L, STRICT>(rng, step32 + 1u, tables, make, pins);
+            apply_proposal<L>(c, use.z, prop);
+        }
+        step32++;
+        accept = finish_step<Cfg>(c, prop, use.u, g, p, tables, group);
+    };
+    const unsigned spm = (unsigned)p.spm;
+
+    for (long long b = 0; b < p.n_blocks; b++) {
+        Gains g = make_gains(n, p);
+        g.k64 = pins.k64;
+        /* steps in pairs so that the two draw buffers swap roles by name instead of by register moves */
+        Draws<L> nxt;
+        unsigned k = 0;
+        for (; k + 1 < spm; k += 2) {
+            one_step(g, cur, nxt);
+            one_step(g, nxt, cur);
+        }
+        if (k < spm) {
+            one_step(g, cur, nxt);
             if (!inject) cur = nxt;
         }
         if (p.do_measure) {
@@ -696,6 +712,7 @@ __device__ __forceinline__ void init_body(const MeParams &p) {
     for (int i = 0; i < NR; i++) s.obsm[NR + NC + i] = c.x[i] * c.x[i];
     c.e = p.have_e0 ? p.e_new[ch] : Energy::eval(c.x, c.x + NR, c.x + NR + NC, p.consts);
     c.nacc = 0.0;
+    c.nacc_new = 0u;
     c.status = 0;
     if (c.e != c.e) c.status |= ME_STATUS_ENERGY_NAN;
     if (refactor<L>(s, c)) c.status |= ME_STATUS_NOT_PSD;
@@ -724,7 +741,7 @@ __device__ __forceinline__ void propose_body(const MeParams &p) {
     } else {
         const Rng rng(p, p.chain_offset + (unsigned long long)ch);
         Draws<L> d;
-        gen_draws<L, Cfg::STRICT>(rng, (unsigned)p.step0, tables, d);
+        gen_draws<L, Cfg::STRICT>(rng, (unsigned)p.step0, tables, d, load_pins(tables));
         apply_proposal<L>(c, d.z, prop);
     }
     if (L::KIND == 0 && p.group != 0) {
@@ -765,12 +782,10 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
         else if (diff > 0 && p.temp != 0) {      /* regenerate the spare words of Philox calls 0 (and 1) */
             const Rng rng(p, p.chain_offset + (unsigned long long)ch);
             Spare sp;
-            sp.w1 = 0;
             Rng::keep_spare(rng.bits((unsigned)p.step0, 0u), 0, sp);
-            if ((D + 1) / 2 >= 2) Rng::keep_spare(rng.bits((unsigned)p.step0, 1u), 1, sp);
-            u = Rng::accept_uniform(sp, (D + 1) / 2);
+            u = Rng::accept_uniform(sp);
         }
-        accept = decide<STRICT>(diff, u, p, tables);
+        accept = decide<STRICT>(diff, u, p, tables, g.hot);
         if (accept) {
             st[(long long)L::E * ld + ch] = e_new;
 #pragma unroll

@@ -227,12 +227,10 @@ __global__ void gk_accept(const __grid_constant__ MeParams p) {
         else if (diff > 0 && p.temp != 0) {
             const me::Rng rng(p, p.chain_offset + (unsigned long long)ch);
             me::Spare sp;
-            sp.w1 = 0;
             me::Rng::keep_spare(rng.bits((unsigned)p.step0, 0u), 0, sp);
-            if ((L.d + 1) / 2 >= 2) me::Rng::keep_spare(rng.bits((unsigned)p.step0, 1u), 1, sp);
-            u = me::Rng::accept_uniform(sp, (L.d + 1) / 2);
+            u = me::Rng::accept_uniform(sp);
         }
-        accept = me::decide<true>(diff, u, p, tables);
+        accept = me::decide<true>(diff, u, p, tables, g.hot);
         if (accept) {
             ST(L.E) = e_new;
             for (int i = 0; i < L.d; i++) ST(L.X + i) = p.prop[(long long)i * ld + ch];

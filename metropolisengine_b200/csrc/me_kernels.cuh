@@ -15,12 +15,25 @@ struct Cfg {
     using Energy = EnergyT<NR_, NC_>;
 };
 
-/* Small problems are capped at 128 registers: 65,536 chains are 14 warps per SM, which must all be resident in one
- * wave (<= 146 registers), and multi-million-chain ensembles get 4 warps per SM sub-partition. */
+/* Small problems (D <= 4) are capped at 144 registers: 65,536 chains in CTAs of 32 are 14 warps per SM, which must all
+ * be resident in one wave (14 x 32 x 144 = 64,512 of the SM's 65,536 registers).  Below ~140 ptxas starts to
+ * re-materialise loop invariants (Philox counter words, polynomial constants) inside the step loop. */
+template <class C, bool SMALL = (C::NR + 2 * C::NC <= 4)>
+struct RunKernel;
 template <class C>
-__global__ void __launch_bounds__(ME_MAX_BLOCK, (C::NR + 2 * C::NC <= 4) ? 2 : 1) k_run(const __grid_constant__ MeParams p) {
+__global__ void __maxnreg__(144) k_run_small(const __grid_constant__ MeParams p) {
     run_body<C>(p);
 }
+template <class C>
+__global__ void __launch_bounds__(ME_MAX_BLOCK, 1) k_run(const __grid_constant__ MeParams p) {
+    run_body<C>(p);
+}
+#ifndef ME_NVRTC   /* host-side selection; the run-time compiled kernels (me_api.cu) name their entry points directly */
+template <class C>
+struct RunKernel<C, true> { static const void *get() { return (const void *)&k_run_small<C>; } };
+template <class C>
+struct RunKernel<C, false> { static const void *get() { return (const void *)&k_run<C>; } };
+#endif
 template <class C>
 __global__ void __launch_bounds__(ME_MAX_BLOCK) k_init(const __grid_constant__ MeParams p) { init_body<C>(p); }
 template <class C>
@@ -37,7 +50,7 @@ struct MeAotEntry {
 };
 
 #define ME_AOT_ENTRY(NR, NC, ETMPL, EID, STRICT)                                                        \
-    { NR, NC, EID, STRICT, (const void *)&me::k_run<me::Cfg<NR, NC, ETMPL, STRICT>>,                      \
+    { NR, NC, EID, STRICT, me::RunKernel<me::Cfg<NR, NC, ETMPL, STRICT>>::get(),                          \
       (const void *)&me::k_init<me::Cfg<NR, NC, ETMPL, STRICT>>,                                          \
       (const void *)&me::k_propose<me::Cfg<NR, NC, ETMPL, STRICT>>,                                       \
       (const void *)&me::k_accept<me::Cfg<NR, NC, ETMPL, STRICT>> }

@@ -139,13 +139,9 @@ void meo_philox(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot, uin
     philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), step, slot, (uint32_t)seed, (uint32_t)(seed >> 32), out);
 }
 
-static double u53(uint32_t hi, uint32_t lo) {   /* python random.random() bit recipe: [0,1) on a 2^-53 grid */
-    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
-}
-
 /* sin(pi t), cos(pi t) for t in [0,2): exact octant reduction, then libm on |arg| <= pi/4 */
 static void sincospi_d(double t, double *s, double *c) {
-    double q = floor(2.0 * t + 0.5);           /* nearest multiple of 1/2 */
+    double q = floor(2.0 * t + 0.5);           /* nearest multiple of 1/2 (half-way cases up) */
     double r = t - 0.5 * q;                    /* exact, |r| <= 1/4 */
     double sr = sin(M_PI * r), cr = cos(M_PI * r);
     switch (((int)q) & 3) {
@@ -159,16 +155,16 @@ static void sincospi_d(double t, double *s, double *c) {
 /* Stream definition (shared with the CUDA kernels, me_device.cuh):
  *   per step and chain, Philox call q = 0 .. ceil(D/2)-1 with counter (chain_lo, chain_hi, step, q), key = seed,
  *   output words (x, y, z, w):
- *     radius uniform  u1 = u53(x, y) + 2^-53        in (0,1]
+ *     radius uniform  u1 = (K + 1/2) 2^-52          in (0,1),  K = y : x[31:12]   (52 bits)
  *     angle           t  = z * 2^-31                in [0,2)      (sin/cos of pi*t)
  *     normals         z_{2q} = sqrt(-2 ln u1) cos(pi t),  z_{2q+1} = sqrt(-2 ln u1) sin(pi t)
- *   accept uniform: two or more calls: u = u53(w_0, w_1) (53 bits);
- *                   one call: the 32 bits of w_0 followed by the 5 + 6 low bits of x_0, y_0 that u53 discards
- *                   (43 bits).  All bits used are distinct output bits of the generator. */
+ *   accept uniform    u = A 2^-44 in [0,1),  A = w_0 : x_0[11:0]  (44 bits of call 0 the normals do not use).
+ *   All bits used are distinct output bits of the generator. */
 void meo_normal_pair(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot, double *z0, double *z1) {
     uint32_t r[4];
     meo_philox(seed, chain, step, slot, r);
-    double u1 = u53(r[0], r[1]) + (1.0 / 9007199254740992.0);   /* (0,1] */
+    uint64_t K = ((uint64_t)r[1] << 20) | (uint64_t)(r[0] >> 12);
+    double u1 = ((double)K + 0.5) * (1.0 / 4503599627370496.0);  /* exact: 2K+1 < 2^53 */
     double t = (double)r[2] * (1.0 / 2147483648.0);             /* [0,2) */
     double rad = sqrt(-2.0 * log(u1));
     double s, c;
@@ -179,14 +175,10 @@ void meo_normal_pair(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot
 
 double meo_uniform(uint64_t seed, uint64_t chain, uint32_t step, int n_calls) {
     uint32_t r[4];
+    (void)n_calls;
     meo_philox(seed, chain, step, 0, r);
-    if (n_calls >= 2) {
-        uint32_t r1[4];
-        meo_philox(seed, chain, step, 1, r1);
-        return u53(r[3], r1[3]);
-    }
-    uint64_t bits = ((uint64_t)r[3] << 11) | ((uint64_t)(r[0] & 31u) << 6) | (uint64_t)(r[1] & 63u);
-    return (double)bits * (1.0 / 8796093022208.0);              /* 2^-43 */
+    uint64_t bits = ((uint64_t)r[3] << 12) | (uint64_t)(r[0] & 0xfffu);
+    return (double)bits * (1.0 / 17592186044416.0);             /* 2^-44 */
 }
 
 /* ------------------------------------------------------------------ Cholesky factors of the proposal covariances */

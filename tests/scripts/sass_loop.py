@@ -1,0 +1,40 @@
+"""Instruction histogram of the innermost hot loop of a kernel in libme_b200.so (CPU-side, cuobjdump).
+
+usage: python tests/scripts/sass_loop.py <mangled-name-substring> [--dump]
+The hot loop is the shortest backward-branch body that holds a full Philox call (>= 18 IMAD.WIDE)."""
+import collections, re, subprocess, sys
+
+def main():
+    key = sys.argv[1]
+    lib = "metropolisengine_b200/lib/libme_b200.so"
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    funcs = out.split("Function : ")
+    body = next(f for f in funcs if f.split("\n")[0].find(key) >= 0)
+    ins = []
+    for l in body.split("\n"):
+        m = re.match(r"\s*/\*([0-9a-f]{4,5})\*/\s+(.*?);", l)
+        if m:
+            ins.append((int(m.group(1), 16), m.group(2).strip()))
+    best = None
+    for a, t in ins:
+        m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d,\s*)?(?:P\d,\s*)?0x([0-9a-f]+)", t)
+        if m and int(m.group(1), 16) < a:
+            lo = int(m.group(1), 16)
+            loop = [(x, y) for x, y in ins if lo <= x <= a]
+            nw = sum("IMAD.WIDE" in y for _, y in loop)
+            if nw >= 18 and (best is None or len(loop) < len(best[1])):
+                best = (nw, loop)
+    loop = best[1]
+    c = collections.Counter()
+    for a, t in loop:
+        toks = t.split()
+        op = toks[1] if toks[0].startswith("@") else toks[0]
+        c[op.split(".")[0]] += 1
+    fp64 = sum(v for k, v in c.items() if k in ("DFMA", "DADD", "DMUL", "DSETP"))
+    print(f"loop 0x{loop[0][0]:x}..0x{loop[-1][0]:x}: {len(loop)} instructions, {fp64} FP64, dispatch estimate {len(loop) + fp64}")
+    print(" ".join(f"{k}:{v}" for k, v in c.most_common()))
+    if "--dump" in sys.argv:
+        for a, t in loop:
+            print(f"{a:05x} {t}")
+
+main()
