@@ -25,6 +25,9 @@
 #include "me_math.cuh"
 
 #define ME_MAX_BLOCK 256
+#ifndef ME_BIG_LOOKAHEAD
+#define ME_BIG_LOOKAHEAD 1     /* shapes with D > 4: generate the draws of step s+1 during step s (costs D+2 doubles of registers) */
+#endif
 #define ME_FULL 0xffffffffu
 #define ME_MAX_POOLW 600
 
@@ -259,19 +262,36 @@ struct Draws {                 /* everything random one step consumes; independe
     double u;
 };
 
+template <class L>
+struct Raw {                   /* the generator output one step consumes: one Philox call per Gaussian pair */
+    U4 r[(L::D + 1) / 2];
+};
+
+template <class L>
+__device__ __forceinline__ void gen_bits(const Rng &rng, unsigned step, Raw<L> &raw) {
+#pragma unroll
+    for (int q = 0; q < (L::D + 1) / 2; q++) raw.r[q] = rng.bits(step, (unsigned)q);
+}
+
 template <class L, bool STRICT>
-__device__ __forceinline__ void gen_draws(const Rng &rng, unsigned step, const MathTables &T, Draws<L> &d,
-                                          const Pins &pins) {
+__device__ __forceinline__ void shape_draws(const Raw<L> &raw, const MathTables &T, Draws<L> &d, const Pins &pins) {
     constexpr int NQ = (L::D + 1) / 2;
     Spare sp;
     sp.w0 = sp.x0 = 0;
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-        const U4 r = rng.bits(step, (unsigned)q);
-        Rng::keep_spare(r, q, sp);
-        Rng::box_muller<STRICT>(r, T, d.z[2 * q], d.z[2 * q + 1], pins.unit, pins.angle);
+        Rng::keep_spare(raw.r[q], q, sp);
+        Rng::box_muller<STRICT>(raw.r[q], T, d.z[2 * q], d.z[2 * q + 1], pins.unit, pins.angle);
     }
     d.u = Rng::accept_uniform(sp);
+}
+
+template <class L, bool STRICT>
+__device__ __forceinline__ void gen_draws(const Rng &rng, unsigned step, const MathTables &T, Draws<L> &d,
+                                          const Pins &pins) {
+    Raw<L> raw;
+    gen_bits<L>(rng, step, raw);
+    shape_draws<L, STRICT>(raw, T, d, pins);
 }
 
 template <class L>
@@ -497,7 +517,9 @@ __device__ __forceinline__ bool finish_step(Chain<Lay<Cfg::NR, Cfg::NC>> &c, dou
         }
     }
     if (L::KIND == 0 && group != 0) {       /* ME:440-456: only the stepped group's width adapts */
-        c.sig[group - 1] = adapt_sigma<STRICT>(c.sig[group - 1], accept, g, p);
+        /* (selects, not c.sig[group - 1]: a run-time index would move the whole chain struct to local memory) */
+        const double sg = adapt_sigma<STRICT>(group == 1 ? c.sig[0] : c.sig[1], accept, g, p);
+        if (group == 1) c.sig[0] = sg; else c.sig[1] = sg;
     } else {
         const double sg = adapt_sigma<STRICT>(c.sig[L::SIGIDX], accept, g, p);
         c.sig[L::SIGIDX] = sg;
@@ -558,19 +580,27 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     long long s_local = 0;
     bool accept = false;
 
-    /* Software pipelining: the random draws of step s+1 do not depend on the chain's state, so they are generated
-       while the state-dependent chain of step s (proposal -> energy -> exp -> select) is in flight.  This doubles
-       the instruction-level parallelism of a warp, which is what limits this kernel when an ensemble gives each
-       SM sub-partition only 3-4 warps (65,536 chains on 148 SMs). */
+    /* Software pipelining: the random draws do not depend on the chain's state, so they are produced ahead of the
+       state-dependent chain (proposal -> energy -> exp -> select) of the step that consumes them.  An ensemble of
+       65,536 chains gives each SM sub-partition only 3-4 warps, so the kernel is bound by dependent-issue latency,
+       not by issue slots (tests/scripts/issue_mix.cu: FP64 and integer instructions overlap on sm_100a), and what
+       counts is how many independent dependency chains one warp has in flight.  Small shapes run THREE stages per
+       iteration — Philox rounds of step s+2 (10 dependent IMAD.WIDE/LOP3 rounds, ~180 cycles), Box-Muller of step
+       s+1 (log -> rsqrt -> multiply, ~200 cycles), state update of step s (~190 cycles); larger shapes already
+       have ceil(D/2) independent generator calls per step and keep two stages (registers). */
+    constexpr bool DEEP = L::D <= 4;
+    constexpr bool AHEAD = DEEP || (ME_BIG_LOOKAHEAD != 0);
     Draws<L> cur;
+    Raw<L> raw_a, raw_b;
     const Pins pins = load_pins(tables);
-    if (!inject && p.spm > 0) gen_draws<L, STRICT>(rng, (unsigned)p.step0, tables, cur, pins);
-    /* (Running the steps in pairs — two independent draw chains in flight — was measured and is NOT faster:
-       7.3e10 vs 7.6e10 chain-steps/s on the xy-well at 65,536 chains; one step of look-ahead is the sweet spot.) */
+    if (!inject && p.spm > 0 && AHEAD) {
+        gen_draws<L, STRICT>(rng, (unsigned)p.step0, tables, cur, pins);
+        if (DEEP) gen_bits<L>(rng, (unsigned)p.step0 + 1u, raw_a);
+    }
 
     /* one step: consumes the draws in `use`, generates the draws of the following step into `make` */
     unsigned step32 = (unsigned)p.step0;
-    auto one_step = [&](const Gains &g, Draws<L> &use, Draws<L> &make) {
+    auto one_step = [&](const Gains &g, Draws<L> &use, Draws<L> &make, Raw<L> &raw_in, Raw<L> &raw_out) {
         double prop[D];
         if (inject) {
 #pragma unroll
@@ -578,7 +608,14 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
             use.u = p.inj_u[s_local * ld + ch];
             s_local++;
         } else {
-            gen_draws<L, STRICT>(rng, step32 + 1u, tables, make, pins);
+            if (DEEP) {
+                gen_bits<L>(rng, step32 + 2u, raw_out);
+                shape_draws<L, STRICT>(raw_in, tables, make, pins);
+            } else if (AHEAD) {
+                gen_draws<L, STRICT>(rng, step32 + 1u, tables, make, pins);
+            } else {
+                gen_draws<L, STRICT>(rng, step32, tables, use, pins);
+            }
             apply_proposal<L>(c, use.z, prop);
         }
         step32++;
@@ -593,12 +630,12 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
         Draws<L> nxt;
         unsigned k = 0;
         for (; k + 1 < spm; k += 2) {
-            one_step(g, cur, nxt);
-            one_step(g, nxt, cur);
+            one_step(g, cur, nxt, raw_a, raw_b);
+            one_step(g, nxt, cur, raw_b, raw_a);
         }
         if (k < spm) {
-            one_step(g, cur, nxt);
-            if (!inject) cur = nxt;
+            one_step(g, cur, nxt, raw_a, raw_b);
+            if (!inject) { cur = nxt; if (DEEP) raw_a = raw_b; }
         }
         if (p.do_measure) {
             n += 1;

@@ -24,10 +24,17 @@ template <class C>
 __global__ void __maxnreg__(144) k_run_small(const __grid_constant__ MeParams p) {
     run_body<C>(p);
 }
+#ifdef ME_BIG_MAXNREG
+template <class C>
+__global__ void __maxnreg__(ME_BIG_MAXNREG) k_run(const __grid_constant__ MeParams p) {
+    run_body<C>(p);
+}
+#else
 template <class C>
 __global__ void __launch_bounds__(ME_MAX_BLOCK, 1) k_run(const __grid_constant__ MeParams p) {
     run_body<C>(p);
 }
+#endif
 #ifndef ME_NVRTC   /* host-side selection; the run-time compiled kernels (me_api.cu) name their entry points directly */
 template <class C>
 struct RunKernel<C, true> { static const void *get() { return (const void *)&k_run_small<C>; } };
