@@ -120,7 +120,13 @@ int me_check_energy_source(const char *cuda_source, int32_t n_real, int32_t n_co
 /* Group-wise stepping of mixed engines: subsequent me_run / me_run_injected / me_propose /
  * me_accept calls perform step_real_group (group 1, ME:225-239: only the real block is proposed, only
  * real_group_sampling_width adapts, ME:440-446) or step_complex_group (group 2, ME:209-223, ME:449-456) instead of
- * step_all (group 0).  For all-real / all-complex engines the three coincide (ME:46,56). */
+ * step_all (group 0).  For all-real / all-complex engines the three coincide (ME:46,56).
+ * Groups 3 and 4 are the two halves of step_complex_group under complex_sample_method="magnitude-phase"
+ * (ME:129-130, 168-207, 304-317): 3 = Gaussian move of every modulus at fixed phase
+ * (step_complex_group_magnitude, ME:178-192, draw ME:304-310 — the reference's sigma^2 C_jj is used as the standard
+ * deviation, reproduced), adapts complex_group_sampling_width; 4 = uniform redraw of every phase at fixed modulus
+ * (step_complex_group_phase, ME:194-207, draw ME:312-317), adapts nothing.  In injected (parity) mode the complex
+ * block of the records of groups 3 / 4 holds the ABSOLUTE proposed values, not increments. */
 int me_set_group(me_engine *eng, int32_t group);
 
 /* Launch geometry the handle uses; the pool buffer has grid * POOL_WORDS doubles. */

@@ -40,7 +40,7 @@ struct KernelRef {
     bool valid() const { return rt != nullptr || drv != nullptr; }
 };
 struct KernelSet {
-    KernelRef run, init, propose, accept, energy;
+    KernelRef run, init, propose, accept, energy, run_mp;
     bool valid() const { return run.valid(); }
 };
 
@@ -159,6 +159,9 @@ int nvrtc_compile(int n_real, int n_complex, int energy_id, const std::string &u
     }
     src += std::string("typedef me::Cfg<ME_NR, ME_NC, ") + tmpl + ", (ME_STRICT != 0)> UserCfg;\n";
     src += "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_run(const __grid_constant__ MeParams p) { me::run_body<UserCfg>(p); }\n"
+           "#if ME_NC > 0\n"
+           "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_run_mp(const __grid_constant__ MeParams p) { me::run_body<UserCfg, true>(p); }\n"
+           "#endif\n"
            "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_init(const __grid_constant__ MeParams p) { me::init_body<UserCfg>(p); }\n"
            "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_propose(const __grid_constant__ MeParams p) { me::propose_body<UserCfg>(p); }\n"
            "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_accept(const __grid_constant__ MeParams p) { me::accept_body<UserCfg>(p); }\n";
@@ -309,7 +312,7 @@ int resolve_kernels(me_engine *e, int energy_id, const std::string &user_src) {
         const MeAotEntry *t = strict ? me_aot_strict_table(&n) : me_aot_fast_table(&n);
         for (int i = 0; i < n; i++)
             if (t[i].n_real == nr && t[i].n_complex == nc && t[i].energy_id == energy_id) {
-                e->ks.run.rt = t[i].run; e->ks.init.rt = t[i].init;
+                e->ks.run.rt = t[i].run; e->ks.init.rt = t[i].init; e->ks.run_mp.rt = t[i].run_mp;
                 e->ks.propose.rt = t[i].propose; e->ks.accept.rt = t[i].accept;
                 return ME_OK;
             }
@@ -340,7 +343,8 @@ int resolve_kernels(me_engine *e, int energy_id, const std::string &user_src) {
     if (d.moduleGetFunction(&ks.run.drv, mod, "me_k_run") != CUDA_SUCCESS ||
         d.moduleGetFunction(&ks.init.drv, mod, "me_k_init") != CUDA_SUCCESS ||
         d.moduleGetFunction(&ks.propose.drv, mod, "me_k_propose") != CUDA_SUCCESS ||
-        d.moduleGetFunction(&ks.accept.drv, mod, "me_k_accept") != CUDA_SUCCESS)
+        d.moduleGetFunction(&ks.accept.drv, mod, "me_k_accept") != CUDA_SUCCESS ||
+        (e->cfg.n_complex > 0 && d.moduleGetFunction(&ks.run_mp.drv, mod, "me_k_run_mp") != CUDA_SUCCESS))
         return fail(e, ME_ERR_CUDA, "cuModuleGetFunction failed on the runtime-compiled module");
     g_cache[key] = ks;
     e->ks = ks;
@@ -500,9 +504,12 @@ int me_check_energy_source(const char *src, int32_t nr, int32_t nc, int32_t use_
 
 int me_set_group(me_engine *e, int32_t group) {
     if (!e) return ME_ERR_INVALID;
-    if (group < 0 || group > 2) return fail(e, ME_ERR_INVALID, "group must be 0 (all), 1 (real) or 2 (complex)");
+    if (group < 0 || group > 4)
+        return fail(e, ME_ERR_INVALID, "group must be 0 (all), 1 (real), 2 (complex), 3 (complex magnitudes) or 4 (complex phases)");
     if (group == 1 && e->cfg.n_real == 0) return fail(e, ME_ERR_INVALID, "engine has no real parameters");
-    if (group == 2 && e->cfg.n_complex == 0) return fail(e, ME_ERR_INVALID, "engine has no complex parameters");
+    if (group >= 2 && e->cfg.n_complex == 0) return fail(e, ME_ERR_INVALID, "engine has no complex parameters");
+    if (group >= 3 && e->generic)
+        return fail(e, ME_ERR_UNSUPPORTED, "magnitude-phase moves are built for fused shapes (n_real + 2 n_complex <= 32)");
     e->group = group;
     return ME_OK;
 }
@@ -558,7 +565,9 @@ static int run_common(me_engine *e, int64_t n_blocks, int64_t spm, int do_measur
     p.n_blocks = n_blocks; p.spm = spm; p.do_measure = do_measure ? 1 : 0;
     p.ts = ts; p.ts_row0 = ts_row0; p.record = (ts != nullptr && do_measure) ? 1 : 0;
     p.inj_delta = delta; p.inj_u = u;
-    int rc = launch(e, e->ks.run, p, stream);
+    if (e->group >= 3 && !e->ks.run_mp.valid())
+        return fail(e, ME_ERR_STATE, "no magnitude-phase kernel for this engine");
+    int rc = launch(e, e->group >= 3 ? e->ks.run_mp : e->ks.run, p, stream);
     if (rc != ME_OK) return rc;
     e->step += (unsigned long long)(n_blocks * spm);
     if (do_measure) e->n_measure += n_blocks;

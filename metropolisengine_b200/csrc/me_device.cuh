@@ -322,6 +322,48 @@ __device__ __forceinline__ void apply_proposal(const Chain<L> &c, const double *
     }
 }
 
+/* Magnitude-phase complex moves (complex_sample_method="magnitude-phase", ME:129-130, 168-207, 304-317): the
+ * reference's step_complex_group becomes a Gaussian move of every modulus at fixed phase followed by a uniform redraw of
+ * every phase at fixed modulus, each with its own Metropolis test.  group 3 = magnitudes, group 4 = phases.
+ *   magnitude: |c_j|' = |c_j| + s_j z_j with s_j = sigma_c^2 C_jj — the reference hands this VARIANCE to
+ *              random.gauss as the standard deviation (ME:305,310); reproduced.  C_jj = sum_k |G_jk|^2.
+ *   phase:     c_j' = |c_j| e^{i theta}, theta = pi t - pi, t = 2^-31 x (angle word of Philox call j). */
+template <class L>
+__device__ __forceinline__ void propose_magnitudes(const Chain<L> &c, const double *z, double (&prop)[L::D]) {
+    constexpr int NR = L::NR, NC = L::NC, dg = NC * (NC - 1);
+#pragma unroll
+    for (int i = 0; i < NR; i++) prop[i] = c.x[i];
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        double cjj = c.facc[dg + j] * c.facc[dg + j];
+#pragma unroll
+        for (int k = 0; k < j; k++)
+            cjj += c.facc[herm_lo(j, k)] * c.facc[herm_lo(j, k)] + c.facc[herm_lo(j, k) + 1] * c.facc[herm_lo(j, k) + 1];
+        const double re = c.x[NR + j], im = c.x[NR + NC + j];
+        const double mag = hypot(re, im);
+        const double nm = mag + z[j] * ((c.sig[1] * c.sig[1]) * cjj);
+        const double ratio = nm / mag;
+        prop[NR + j] = mag > 0.0 ? re * ratio : nm;          /* arg 0 = 0 (cmath.polar) */
+        prop[NR + NC + j] = mag > 0.0 ? im * ratio : 0.0;
+    }
+}
+
+template <class L>
+__device__ __forceinline__ void propose_phases(const Chain<L> &c, const Rng &rng, unsigned step, double (&prop)[L::D]) {
+    constexpr int NR = L::NR, NC = L::NC;
+#pragma unroll
+    for (int i = 0; i < NR; i++) prop[i] = c.x[i];
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const U4 r = rng.bits(step, (unsigned)j);
+        double sn, cs;
+        sincospi_bits(r.z, sn, cs);
+        const double mag = hypot(c.x[NR + j], c.x[NR + NC + j]);
+        prop[NR + j] = mag * -cs;
+        prop[NR + NC + j] = mag * -sn;
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ decision + adaptation */
 struct Gains {            /* per measure-block constants of the Robbins-Monro update (ME:429-456) */
     double f;             /* max(n_measure / m, 200) */
@@ -516,7 +558,9 @@ __device__ __forceinline__ bool finish_step(Chain<Lay<Cfg::NR, Cfg::NC>> &c, dou
             c.nacc_new += 1u;
         }
     }
-    if (L::KIND == 0 && group != 0) {       /* ME:440-456: only the stepped group's width adapts */
+    if (L::NC > 0 && group == 4) {
+        /* phase redraw: no width adapts, on the wall or otherwise (ME:194-207) */
+    } else if (L::KIND == 0 && group != 0) {       /* ME:440-456: only the stepped group's width adapts */
         /* (selects, not c.sig[group - 1]: a run-time index would move the whole chain struct to local memory) */
         const double sg = adapt_sigma<STRICT>(group == 1 ? c.sig[0] : c.sig[1], accept, g, p);
         if (group == 1) c.sig[0] = sg; else c.sig[1] = sg;
@@ -530,7 +574,9 @@ __device__ __forceinline__ bool finish_step(Chain<Lay<Cfg::NR, Cfg::NC>> &c, dou
 
 /* ------------------------------------------------------------------------------------------ the fused kernel body
  * Cfg:  NR, NC, Energy (functor with eval / reject), STRICT (reference operation order + draw injection).   */
-template <class Cfg>
+/* MP: instantiation that also serves the magnitude / phase moves (groups 3, 4).  They are kept out of the default
+ * instantiation so that their code (a second set of generator calls, hypot) does not sit in the hot step loop. */
+template <class Cfg, bool MP = false>
 __device__ __forceinline__ void run_body(const MeParams &p) {
     using L = Lay<Cfg::NR, Cfg::NC>;
     using Energy = typename Cfg::Energy;
@@ -603,8 +649,10 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     auto one_step = [&](const Gains &g, Draws<L> &use, Draws<L> &make, Raw<L> &raw_in, Raw<L> &raw_out) {
         double prop[D];
         if (inject) {
+            const bool absolute = MP && L::NC > 0 && group >= 3;      /* magnitude / phase records hold the proposal itself */
 #pragma unroll
-            for (int i = 0; i < D; i++) prop[i] = p.inj_delta[(s_local * D + i) * ld + ch] + c.x[i];
+            for (int i = 0; i < D; i++)
+                prop[i] = p.inj_delta[(s_local * D + i) * ld + ch] + (absolute ? 0.0 : c.x[i]);
             use.u = p.inj_u[s_local * ld + ch];
             s_local++;
         } else {
@@ -617,6 +665,10 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
                 gen_draws<L, STRICT>(rng, step32, tables, use, pins);
             }
             apply_proposal<L>(c, use.z, prop);
+            if (MP && L::NC > 0 && group >= 3) {
+                if (group == 3) propose_magnitudes<L>(c, use.z, prop);
+                else propose_phases<L>(c, rng, step32, prop);
+            }
         }
         step32++;
         accept = finish_step<Cfg>(c, prop, use.u, g, p, tables, group);
@@ -773,13 +825,18 @@ __device__ __forceinline__ void propose_body(const MeParams &p) {
     load_chain<L>(c, p.state, p.ld, ch);
     double prop[D];
     if (Cfg::STRICT && p.inj_delta != nullptr) {
+        const bool absolute = L::NC > 0 && p.group >= 3;
 #pragma unroll
-        for (int i = 0; i < D; i++) prop[i] = p.inj_delta[(long long)i * p.ld + ch] + c.x[i];
+        for (int i = 0; i < D; i++) prop[i] = p.inj_delta[(long long)i * p.ld + ch] + (absolute ? 0.0 : c.x[i]);
     } else {
         const Rng rng(p, p.chain_offset + (unsigned long long)ch);
         Draws<L> d;
         gen_draws<L, Cfg::STRICT>(rng, (unsigned)p.step0, tables, d, load_pins(tables));
         apply_proposal<L>(c, d.z, prop);
+        if (L::NC > 0 && p.group >= 3) {
+            if (p.group == 3) propose_magnitudes<L>(c, d.z, prop);
+            else propose_phases<L>(c, rng, (unsigned)p.step0, prop);
+        }
     }
     if (L::KIND == 0 && p.group != 0) {
 #pragma unroll
@@ -804,7 +861,7 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
     double *st = p.state;
     double e = st[(long long)L::E * ld + ch];
     const bool grouped = L::KIND == 0 && p.group != 0;
-    const int sidx = grouped ? p.group - 1 : L::SIGIDX;
+    const int sidx = grouped ? (p.group == 1 ? 0 : 1) : L::SIGIDX;
     double sg = st[(long long)(L::SIG + sidx) * ld + ch];
     int status = (int)st[(long long)L::STATUS * ld + ch];
     const Gains g = make_gains(p.n_meas0, p);
@@ -830,7 +887,7 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
             st[(long long)L::NACC * ld + ch] += 1.0;
         }
     }
-    sg = adapt_sigma<STRICT>(sg, accept, g, p);
+    if (!(L::NC > 0 && p.group == 4)) sg = adapt_sigma<STRICT>(sg, accept, g, p);     /* phase redraw: ME:194-207 */
     st[(long long)(L::SIG + sidx) * ld + ch] = sg;
     if (L::KIND == 0 && !grouped) {
         st[(long long)(L::SIG + 1) * ld + ch] = sg;

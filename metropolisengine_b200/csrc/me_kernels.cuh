@@ -41,6 +41,17 @@ struct RunKernel<C, true> { static const void *get() { return (const void *)&k_r
 template <class C>
 struct RunKernel<C, false> { static const void *get() { return (const void *)&k_run<C>; } };
 #endif
+/* the instantiation that also performs the magnitude / phase complex moves (me_set_group 3, 4) */
+template <class C>
+__global__ void __launch_bounds__(ME_MAX_BLOCK, 1) k_run_mp(const __grid_constant__ MeParams p) {
+    run_body<C, true>(p);
+}
+#ifndef ME_NVRTC
+template <class C, bool HAS_COMPLEX = (C::NC > 0)>
+struct RunMpKernel { static const void *get() { return (const void *)&k_run_mp<C>; } };
+template <class C>
+struct RunMpKernel<C, false> { static const void *get() { return nullptr; } };
+#endif
 template <class C>
 __global__ void __launch_bounds__(ME_MAX_BLOCK) k_init(const __grid_constant__ MeParams p) { init_body<C>(p); }
 template <class C>
@@ -53,14 +64,15 @@ __global__ void __launch_bounds__(ME_MAX_BLOCK) k_accept(const __grid_constant__
 /* one ahead-of-time instantiation */
 struct MeAotEntry {
     int n_real, n_complex, energy_id, strict;
-    const void *run, *init, *propose, *accept;
+    const void *run, *init, *propose, *accept, *run_mp;
 };
 
 #define ME_AOT_ENTRY(NR, NC, ETMPL, EID, STRICT)                                                        \
     { NR, NC, EID, STRICT, me::RunKernel<me::Cfg<NR, NC, ETMPL, STRICT>>::get(),                          \
       (const void *)&me::k_init<me::Cfg<NR, NC, ETMPL, STRICT>>,                                          \
       (const void *)&me::k_propose<me::Cfg<NR, NC, ETMPL, STRICT>>,                                       \
-      (const void *)&me::k_accept<me::Cfg<NR, NC, ETMPL, STRICT>> }
+      (const void *)&me::k_accept<me::Cfg<NR, NC, ETMPL, STRICT>>,                                        \
+      me::RunMpKernel<me::Cfg<NR, NC, ETMPL, STRICT>>::get() }
 
 /* the shapes of BASELINE.json's configs plus the shapes of the golden fixtures */
 #define ME_AOT_TABLE(STRICT)                                                      \

@@ -92,9 +92,10 @@ class MetropolisEngine:
         if initial_real_params is None and initial_complex_params is None:
             raise ValueError("must give a list containing at least one value for initial real or complex "
                              "parameters")                                                   # ME:37-39
-        if complex_sample_method != "multivariate-gaussian":
-            raise NotImplementedError("only the multivariate-gaussian complex proposal is on the accelerated path "
-                                      "(magnitude-phase is SURVEY.md §8 row f4)")
+        if complex_sample_method not in ("multivariate-gaussian", "magnitude-phase"):
+            # the reference prints a notice and falls back (ME:131-133); nothing is printed here
+            complex_sample_method = "multivariate-gaussian"
+        self.complex_sample_method = complex_sample_method
         if temp is None or not temp >= 0:
             raise AssertionError("temp must be >= 0")                                        # ME:92
         if isinstance(sampling_width, (list, tuple)):
@@ -441,8 +442,10 @@ class MetropolisEngine:
             self.step(k)
         finally:
             self._set_group(0)
-        if group == 2 and self._kind == "mixed":
+        if group in (2, 3) and self._kind == "mixed":
             self.step_counter += int(k)                                                     # ME:450
+        if group == 4 and self._kind == "complex":
+            self.step_counter -= int(k)             # the phase redraw does not go through ME:449-456
         if self.n_chains_total == 1:
             return bool(self._last_accept.item())
         return self._last_accept.bool()
@@ -455,19 +458,46 @@ class MetropolisEngine:
         return self._group_step(1 if self._kind == "mixed" else 0, k)
 
     def step_complex_group(self, k=1):
-        """Propose and decide the complex block only, with its own width (ME:209-223, 449-456)."""
+        """Propose and decide the complex block only, with its own width (ME:209-223, 449-456).  With
+        ``complex_sample_method="magnitude-phase"`` the reference rebinds this method (ME:129-130) to a Gaussian
+        move of the moduli followed by a uniform redraw of the phases (ME:168-176) and returns None; so does this.
+        ``step_all`` keeps the multivariate-Gaussian proposal in either case, as in the reference (ME:46, ME:246)."""
         if not self.num_complex_params:
             raise ValueError("engine has no complex parameters")
+        if self.complex_sample_method == "magnitude-phase":
+            for _ in range(int(k)):
+                self.step_complex_group_magnitude()
+                self.step_complex_group_phase()
+            return None
         return self._group_step(2 if self._kind == "mixed" else 0, k)
 
+    def _require_magnitude_phase_kernels(self):
+        if not self.num_complex_params:
+            raise ValueError("engine has no complex parameters")
+        if self._callable is not None or self._generic:
+            raise NotImplementedError("magnitude-phase moves need a device energy functor and a fused shape "
+                                      "(n_real + 2 n_complex <= 32)")
+
+    def step_complex_group_magnitude(self, k=1):
+        """Gaussian move of every modulus at fixed phase, own Metropolis test, adapts the complex width (ME:178-192;
+        draw ME:304-310, including the reference's use of sigma^2 C_jj as the standard deviation)."""
+        self._require_magnitude_phase_kernels()
+        return self._group_step(3, k)
+
+    def step_complex_group_phase(self, k=1):
+        """Uniform redraw of every phase at fixed modulus, own Metropolis test, adapts nothing (ME:194-207, 312-317)."""
+        self._require_magnitude_phase_kernels()
+        return self._group_step(4, k)
+
     def run_injected_group(self, group, delta, u, k):
-        """Parity mode for group steps: ``k`` injected steps of one group (no measure)."""
-        self._set_group(group if self._kind == "mixed" else 0)
+        """Parity mode for group steps: ``k`` injected steps of one group (no measure).  For groups 3 / 4 (magnitude /
+        phase moves) the complex block of ``delta`` holds the proposed values themselves, not increments."""
+        self._set_group(group if (self._kind == "mixed" or group >= 3) else 0)
         try:
             self.run_injected(delta, u, 1, k, do_measure=False)
         finally:
             self._set_group(0)
-        if group == 2 and self._kind == "mixed":
+        if group in (2, 3) and self._kind == "mixed":
             self.step_counter += int(k)
 
     def _step_external(self, inj_delta=None, inj_u=None):

@@ -339,7 +339,14 @@ int meo_run(const meo_config *c, double *st, int mode, int64_t n_blocks, int64_t
 }
 
 /* group: 0 = step_all; for mixed engines 1 = step_real_group (ME:225-239), 2 = step_complex_group (ME:209-223):
- * only that block is proposed and only that group's width adapts (ME:440-456). */
+ * only that block is proposed and only that group's width adapts (ME:440-456).
+ * 3 / 4 = the two halves of step_complex_group under complex_sample_method="magnitude-phase" (ME:168-207):
+ *   3 magnitude: c'_j = rect(N(|c_j|, s_j), arg c_j), s_j = sigma_c^2 C_jj used as a standard deviation (ME:304-310),
+ *     adapts the complex width like group 2;
+ *   4 phase: c'_j = rect(|c_j|, U(-pi, pi)) (ME:312-317), never adapts a width (ME:194-207).
+ *   Injected mode: the records of these two hold the ABSOLUTE proposed values.
+ *   Philox mode: magnitude j uses the step's normal z_j; phase j uses the angle word of Philox call j,
+ *     theta = pi (word 2^-31) - pi. */
 int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, int64_t spm, int do_measure,
                   int64_t *n_measure, const double *delta, const double *u, uint64_t seed, uint64_t chain_id,
                   uint64_t step0, unsigned char *accept_out, double *ts_out, int group) {
@@ -357,7 +364,32 @@ int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, i
             double prop[MEO_MAX_D];
             const double sr = st[o.SIG], sc = st[o.SIG + 1];
             if (mode == MEO_INJECT) {
-                for (int i = 0; i < d; i++) prop[i] = delta[s * d + i] + x[i];
+                for (int i = 0; i < d; i++) prop[i] = delta[s * d + i] + (group >= 3 ? 0.0 : x[i]);
+            } else if (group >= 3) {
+                const uint32_t step = (uint32_t)(step0 + (uint64_t)s);
+                const double *G = st + o.FACC;
+                const int dg = n_c * (n_c - 1);
+                for (int i = 0; i < n_r; i++) prop[i] = x[i];
+                for (int j = 0; j < n_c; j++) {
+                    const double re = x[n_r + j], im = x[n_r + n_c + j];
+                    const double mag = hypot(re, im), ph = atan2(im, re);
+                    if (group == 3) {
+                        double z[2], cjj = G[dg + j] * G[dg + j];      /* C_jj = sum_k |G_jk|^2 */
+                        for (int k = 0; k < j; k++)
+                            cjj += G[herm_lo(j, k)] * G[herm_lo(j, k)] + G[herm_lo(j, k) + 1] * G[herm_lo(j, k) + 1];
+                        meo_normal_pair(seed, chain_id, step, (uint32_t)(j / 2), &z[0], &z[1]);
+                        const double nm = mag + z[j & 1] * ((sc * sc) * cjj);
+                        prop[n_r + j] = nm * cos(ph);
+                        prop[n_r + n_c + j] = nm * sin(ph);
+                    } else {
+                        uint32_t r[4];
+                        meo_philox(seed, chain_id, step, (uint32_t)j, r);
+                        double sn, cs;
+                        sincospi_d((double)r[2] * (1.0 / 2147483648.0), &sn, &cs);   /* theta = pi t - pi */
+                        prop[n_r + j] = mag * -cs;
+                        prop[n_r + n_c + j] = mag * -sn;
+                    }
+                }
             } else {
                 double z[MEO_MAX_D + 1];
                 const uint32_t step = (uint32_t)(step0 + (uint64_t)s);
@@ -407,9 +439,10 @@ int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, i
             {
                 double f = (double)n / (double)c->m; if (!(f > 200.0)) f = 200.0;
                 const int grouped = (kind == 0 && group != 0);
-                double *sg = grouped ? &st[o.SIG + group - 1] : ((kind == 2) ? &st[o.SIG + 1] : &st[o.SIG]);
+                double *sg = grouped ? &st[o.SIG + (group == 1 ? 0 : 1)] : ((kind == 2) ? &st[o.SIG + 1] : &st[o.SIG]);
                 double cc = (*sg) * c->ratio;
-                if (accept) *sg = *sg + (cc * (1 - p)) / f;
+                if (group == 4) { /* phase redraw: no adaptation */ }
+                else if (accept) *sg = *sg + (cc * (1 - p)) / f;
                 else *sg = *sg - (cc * p) / f;
                 if (kind == 0 && !grouped) { st[o.SIG + 1] = st[o.SIG]; if (!(st[o.SIG] > 0)) st[o.STATUS] = 2.0; }
             }

@@ -71,6 +71,14 @@ def cases():
                             steps_per_measure=8, seed=17, schedule="groups",
                             ctor=dict(initial_real_params=np.array([0.3, 0.2]),
                                       initial_complex_params=np.array([0.4 - 0.1j]), temp=.1)),
+        # complex_sample_method="magnitude-phase" (metropolis_engine.py:129-130, 168-207, 304-317):
+        # the user alternates step_real_group() and step_complex_group(), the latter being a Gaussian magnitude
+        # move followed by a uniform phase redraw
+        "magphase_2r1c": dict(energy=en.demo_2r1c, builtin=("mixed_well", [1.0, -1.0, 0.5]), n_measures=70,
+                              steps_per_measure=9, seed=23, schedule="magphase",
+                              ctor=dict(initial_real_params=np.array([0.3, 0.2]),
+                                        initial_complex_params=np.array([0.4 - 0.1j]), temp=.1,
+                                        complex_sample_method="magnitude-phase")),
         # temp = 0 (the constructor default): greedy descent, no uniform is ever drawn (metropolis_engine.py:331-332)
         "xy_temp0": dict(energy=en.xy_well, builtin=("xy_well", [1.0]), n_measures=60, steps_per_measure=4, seed=7,
                          ctor=dict(initial_real_params=np.array([1.0, -2.0]), temp=0)),

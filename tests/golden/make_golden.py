@@ -25,6 +25,7 @@ import os
 import random
 import sys
 import types
+import warnings
 
 import numpy as np
 
@@ -79,7 +80,8 @@ class Tap:
 
         def uniform(lo, hi):
             val = tap._orig_uniform(lo, hi)
-            tap.uniforms.append(val)
+            if lo == 0:                     # accept test (metropolis_engine.py:335); the phase redraw (ME:317)
+                tap.uniforms.append(val)    # calls uniform(-pi, pi) and is recorded through its proposal instead
             return val
 
         np.random.multivariate_normal = mvn
@@ -117,7 +119,8 @@ def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=Non
     zs = np.zeros((S, d))
     us = np.full(S, np.nan)
     acc = np.zeros(S, dtype=np.bool_)
-    group = np.zeros(S, dtype=np.int32)      # 0 = step_all, 1 = step_real_group, 2 = step_complex_group
+    group = np.zeros(S, dtype=np.int32)      # 0 = step_all, 1 = step_real_group, 2 = step_complex_group,
+                                             # 3 / 4 = magnitude / phase half of the magnitude-phase complex move
     step_x = np.zeros((S, d))
     step_sig = np.zeros((S, 3))
     step_energy = np.zeros(S)
@@ -128,7 +131,7 @@ def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=Non
     def live_energy():
         # all-real / all-complex engines and group steps keep the live energy in eng.energy;
         # the mixed step_all keeps it in eng.energy_total (metropolis_engine.py:255)
-        if mixed and schedule != "groups":
+        if mixed and schedule not in ("groups", "magphase"):
             return float(np.real(eng.energy_total))
         return float(np.real(sum(eng.energy.values())))
 
@@ -137,7 +140,27 @@ def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=Non
         for im in range(n_measures):
             for _ in range(steps_per_measure):
                 nd, nu = len(tap.draws), len(tap.uniforms)
-                if schedule == "groups":       # alternate the two group steps (how the cylinder app drives it)
+                if schedule == "magphase":     # real group, then the two halves of the magnitude-phase complex move
+                    # (metropolis_engine.py:168-207; step_complex_group is rebound to magnitude + phase, ME:129-130)
+                    group[s] = (1, 3, 4)[s % 3]
+                    if group[s] == 1:
+                        a = eng.step_real_group()
+                        (inc, z), = tap.draws[nd:]
+                        delta[s, :n_r] = inc
+                        zs[s, :n_r] = z
+                    else:
+                        name_ = "draw_complex_magnitudes" if group[s] == 3 else "draw_complex_phases"
+                        orig_draw, seen = getattr(eng, name_), []
+                        setattr(eng, name_, lambda o=orig_draw, seen=seen: seen.append(o()) or seen[-1])
+                        with warnings.catch_warnings():
+                            warnings.simplefilter("ignore")        # ComplexWarning at ME:310
+                            a = (eng.step_complex_group_magnitude() if group[s] == 3
+                                 else eng.step_complex_group_phase())
+                        setattr(eng, name_, orig_draw)
+                        (prop,) = seen
+                        delta[s, n_r:n_r + n_c] = np.real(prop)     # ABSOLUTE proposed values, not increments
+                        delta[s, n_r + n_c:] = np.imag(prop)
+                elif schedule == "groups":     # alternate the two group steps (how the cylinder app drives it)
                     group[s] = 1 + (s % 2)
                     a = eng.step_real_group() if group[s] == 1 else eng.step_complex_group()
                     (inc, z), = tap.draws[nd:]
@@ -246,9 +269,11 @@ def check_survey_kats(me):
     print("SURVEY KAT1-3 + constants reproduced bit-for-bit by the live reference")
 
 
-def single_chain_cases(me):
+def single_chain_cases(me, only=None):
     from tests.golden.cases import cases, fresh_ctor
     for name, case in cases().items():
+        if only and name not in only:
+            continue
         run_case(me, name, case["energy"], case["n_measures"], case["steps_per_measure"], seed=case["seed"],
                  reject=case.get("reject"), schedule=case.get("schedule", "all"), **fresh_ctor(case))
 
@@ -313,10 +338,11 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ensembles", action="store_true")
     ap.add_argument("--skip-single", action="store_true")
+    ap.add_argument("--only", nargs="*", help="regenerate only these single-chain cases")
     a = ap.parse_args()
     ref = import_reference()
     if not a.skip_single:
         check_survey_kats(ref)
-        single_chain_cases(ref)
+        single_chain_cases(ref, a.only)
     if a.ensembles:
         ensembles()

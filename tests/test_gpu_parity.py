@@ -405,3 +405,59 @@ def test_group_wise_stepping_philox_matches_c_oracle():
     assert close(st[:eng._lay.WORDS - 2, 5], o.state[:eng._lay.WORDS - 2], 2e-9)
     with pytest.raises(ValueError):
         me.MetropolisEngine("x2", initial_real_params=[0.0], temp=.1).step_complex_group()
+
+
+def test_magnitude_phase_injected_parity():
+    """complex_sample_method="magnitude-phase" (ME:129-130, 168-207, 304-317).  The reference is
+    driven as real group / magnitude move / phase redraw; the recorded proposals are injected into the strict kernel."""
+    import metropolisengine_b200 as me
+    eng, g = make_engine("magphase_2r1c", me, strict=True)
+    assert eng.complex_sample_method == "magnitude-phase"
+    M, K = int(g["n_measures"]), int(g["steps_per_measure"])
+    nacc = 0
+    for im in range(M):
+        for s in range(im * K, (im + 1) * K):
+            eng.run_injected_group(int(g["group"][s]), g["delta"][s:s + 1], g["u"][s:s + 1], 1)
+            nacc += int(g["accept"][s])
+            assert int(eng.accept_count_per_chain.item()) == nacc, s
+        eng.measure()
+        assert close(eng.real_params, g["m_x"][im]) and close(eng.complex_params, g["m_c"][im]), im
+        assert close(eng.real_group_sampling_width, g["m_sigma_r"][im]), im
+        assert close(eng.complex_group_sampling_width, g["m_sigma_c"][im]), im     # phase redraws never adapt it
+        assert close(eng.covariance_matrix_real, g["m_cov_r"][im]) and close(eng.covariance_matrix_complex, g["m_cov_c"][im])
+        assert close(eng.energy["total"], g["m_energy"][im], 1e-11), im
+    assert eng.step_counter == 1 + M * K // 3                      # only the magnitude half counts (ME:450)
+
+
+def test_magnitude_phase_philox_matches_c_oracle():
+    """Device-generated magnitude / phase moves (normal z_j of the step; angle word of Philox call j) against the C
+    oracle running the same streams; step_complex_group() = magnitude + phase and returns None as in the reference."""
+    import metropolisengine_b200 as me
+    from oracle import c_oracle as co
+    x0c = np.array([0.4 - 0.1j, -0.3 + 0.2j])
+    kw = dict(initial_real_params=np.array([0.3, 0.2, 0.1]), initial_complex_params=x0c, temp=.1, sampling_width=0.6,
+              complex_sample_method="magnitude-phase")
+    src = USER_SOURCES["warm_3r2c"]
+    eng = me.MetropolisEngine(me.CudaEnergy(src), n_chains=32, seed=21, **kw)
+
+    def energy(x, n_r, n_c):
+        r, c = x[:n_r], x[n_r:n_r + n_c] + 1j * x[n_r + n_c:]
+        a = (c * c.conjugate()).real
+        return float(np.sum((1 - r) ** 2) + r[0] * r[1] * np.mean(-1 * a + .5 * a ** 2))
+    o = co.CChain(3, 2, lambda x: energy(x, 3, 2), temp=.1, x0=np.array([0.3, 0.2, 0.1, 0.4, -0.3, -0.1, 0.2]),
+                  sampling_width=0.6)
+    step = 0
+    for im in range(56):
+        for _ in range(2):
+            eng.step_real_group()
+            o.run(1, 1, False, seed=21, chain_id=9, step0=step, group=1); step += 1
+            assert eng.step_complex_group() is None
+            o.run(1, 1, False, seed=21, chain_id=9, step0=step, group=3); step += 1
+            o.run(1, 1, False, seed=21, chain_id=9, step0=step, group=4); step += 1
+        eng.measure()
+        o.run(1, 0, True, seed=21, chain_id=9, step0=step)
+    st = eng.state.cpu().numpy()
+    assert close(st[:eng._lay.WORDS - 2, 9], o.state[:eng._lay.WORDS - 2], 2e-9)
+    # phases are redrawn uniformly: the ensemble's arguments of c_0 cover all four quadrants
+    ang = np.angle(eng.complex_params_per_chain.cpu().numpy()[:, 0])
+    assert len(set(np.floor(ang / (np.pi / 2)).astype(int))) == 4

@@ -24,7 +24,7 @@ def _drive(chain, g):
     for im in range(M):
         for _ in range(K):
             grp = int(g["group"][s]) if "group" in g else 0
-            a = chain.step({0: None, 1: "real", 2: "complex"}[grp])
+            a = chain.step({0: None, 1: "real", 2: "complex", 3: "magnitude", 4: "phase"}[grp])
             assert bool(a) == bool(g["accept"][s]), "decision differs at step %d" % s
             got = np.concatenate([chain.real_params, np.real(chain.complex_params), np.imag(chain.complex_params)])
             assert np.array_equal(got, g["step_x"][s]), "state differs at step %d" % s
