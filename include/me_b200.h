@@ -253,6 +253,17 @@ int me_probe_fp64(int32_t device, int64_t iters, double *out, int64_t out_len, v
 int me_statistical_inefficiency(const double *ts, int64_t rows, int64_t row0, int32_t cols, int64_t ld, int32_t col,
                                 int64_t chain0, int64_t n_sel, int64_t max_lag, double *g_out, void *stream);
 
+/* Equilibration detection: for chains [chain0, chain0 + n_sel) and column `col` of the block
+ * ts[row][cols][ld], the start t0 of the production region, its statistical inefficiency g and
+ * Neff_max = max_t0 (rows - t0 + 1) / g(t0) over t0 in range(0, rows - 1, nskip) — what the reference's
+ * save_equilibrium_stats (metropolis_engine.py:481-504) obtains per data-frame column from
+ * pymbar.timeseries.detectEquilibration through statistics.get_equilibration_points (statistics.py:25-48).
+ * fast != 0: pymbar's growing lag increments (its default inside detectEquilibration).  scratch needs
+ * 2 * ceil((rows - 1) / nskip) * n_sel doubles.  t_out / g_out / neff_out: [n_sel] doubles. */
+int me_detect_equilibration(const double *ts, int64_t rows, int32_t cols, int64_t ld, int32_t col, int64_t chain0,
+                            int64_t n_sel, int64_t nskip, int32_t fast, double *scratch, int64_t scratch_doubles,
+                            double *t_out, double *g_out, double *neff_out, void *stream);
+
 const char *me_last_error(me_engine *eng);   /* eng may be NULL: error of the last failing me_create */
 
 #ifdef __cplusplus

@@ -405,6 +405,67 @@ __global__ void k_stat_ineff(const double *ts, long long rows, long long row0, i
     g_out[t_id] = g > 1.0 ? g : 1.0;
 }
 
+/* Equilibration detection: the reference's save_equilibrium_stats (metropolis_engine.py:481-504)
+ * -> statistics.get_equilibration_points (statistics.py:25-48) -> pymbar.timeseries.detectEquilibration, restated in
+ * the oracle (detect_equilibration).  For every candidate start t0 = cand * nskip the statistical inefficiency
+ * g(t0) of rows [t0, T) is computed with pymbar's estimator (C(t) from the mean-removed series, stop at the first
+ * non-positive C(t) beyond `mintime`, optional growing lag increments `fast`), and Neff(t0) = (T - t0 + 1) / g(t0).
+ * One thread per (chain, candidate); consecutive threads are consecutive chains, so every row access is coalesced. */
+__global__ void k_equil_scan(const double *ts, long long rows, int cols, long long ld, int col, long long chain0,
+                             long long n_sel, long long nskip, long long n_cand, int fast, int mintime, double *g_t,
+                             double *neff_t) {
+    const long long t_id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_id >= n_sel) return;
+    const double *x = ts + (long long)col * ld + chain0 + t_id;
+    const long long stride = (long long)cols * ld;
+    for (long long cand = blockIdx.y; cand < n_cand; cand += gridDim.y) {
+        const long long t0 = cand * nskip;
+        const long long N = rows - t0;
+        double mean = 0.0;
+        for (long long i = 0; i < N; i++) mean += x[(t0 + i) * stride];
+        mean /= (double)N;
+        double var = 0.0;
+        for (long long i = 0; i < N; i++) { const double d = x[(t0 + i) * stride] - mean; var += d * d; }
+        var /= (double)N;
+        double g;
+        if (!(var > 0.0)) {
+            g = (double)(rows - t0 + 1);                 /* pymbar: ParameterError -> g = T - t + 1 */
+        } else {
+            g = 1.0;
+            long long t = 1, inc = 1;
+            while (t < N - 1) {
+                double c = 0.0;
+                for (long long i = 0; i + t < N; i++) c += (x[(t0 + i) * stride] - mean) * (x[(t0 + i + t) * stride] - mean);
+                c /= (double)(N - t) * var;
+                if (c <= 0.0 && t > mintime) break;
+                g += 2.0 * c * (1.0 - (double)t / (double)N) * (double)inc;
+                t += inc;
+                if (fast) inc += 1;
+            }
+            if (g < 1.0) g = 1.0;
+        }
+        g_t[cand * n_sel + t_id] = g;
+        /* a series that is constant from its first row is reported as (0, 1, 1) by detectEquilibration: sentinel */
+        neff_t[cand * n_sel + t_id] = (cand == 0 && !(var > 0.0)) ? -1.0 : (double)(rows - t0 + 1) / g;
+    }
+}
+
+__global__ void k_equil_pick(const double *g_t, const double *neff_t, long long n_cand, long long n_sel, long long nskip,
+                             double *t_out, double *g_out, double *neff_out) {
+    const long long t_id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_id >= n_sel) return;
+    if (neff_t[t_id] < 0.0) { t_out[t_id] = 0.0; g_out[t_id] = 1.0; neff_out[t_id] = 1.0; return; }
+    long long best = 0;
+    double bn = neff_t[t_id];
+    for (long long cand = 1; cand < n_cand; cand++) {
+        const double v = neff_t[cand * n_sel + t_id];
+        if (v > bn) { bn = v; best = cand; }              /* first maximum, as numpy.argmax */
+    }
+    t_out[t_id] = (double)(best * nskip);
+    g_out[t_id] = g_t[best * n_sel + t_id];
+    neff_out[t_id] = bn;
+}
+
 }  // namespace
 
 /* ========================================================================================= C ABI */
@@ -671,6 +732,25 @@ int me_statistical_inefficiency(const double *ts, int64_t rows, int64_t row0, in
     const int block = 128;
     k_stat_ineff<<<(unsigned)((n_sel + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
         ts, rows, row0, cols, ld, col, chain0, n_sel, max_lag > 0 ? max_lag : rows, g_out);
+    if (cudaGetLastError() != cudaSuccess) return ME_ERR_CUDA;
+    return ME_OK;
+}
+
+int me_detect_equilibration(const double *ts, int64_t rows, int32_t cols, int64_t ld, int32_t col, int64_t chain0,
+                            int64_t n_sel, int64_t nskip, int32_t fast, double *scratch, int64_t scratch_doubles,
+                            double *t_out, double *g_out, double *neff_out, void *stream) {
+    if (!ts || !scratch || !t_out || !g_out || !neff_out || rows < 3 || cols <= 0 || col < 0 || col >= cols ||
+        n_sel <= 0 || chain0 < 0 || chain0 + n_sel > ld || nskip <= 0)
+        return ME_ERR_INVALID;
+    const long long n_cand = (rows - 1 + nskip - 1) / nskip;        /* t0 in range(0, T - 1, nskip) */
+    if (scratch_doubles < 2 * n_cand * n_sel) return ME_ERR_INVALID;
+    const int block = 128;
+    const unsigned gx = (unsigned)((n_sel + block - 1) / block);
+    const dim3 grid(gx, (unsigned)(n_cand < 65535 ? n_cand : 65535));
+    double *g_t = scratch, *neff_t = scratch + n_cand * n_sel;
+    k_equil_scan<<<grid, block, 0, (cudaStream_t)stream>>>(ts, rows, cols, ld, col, chain0, n_sel, nskip, n_cand, fast ? 1 : 0, 3,
+                                                          g_t, neff_t);
+    k_equil_pick<<<gx, block, 0, (cudaStream_t)stream>>>(g_t, neff_t, n_cand, n_sel, nskip, t_out, g_out, neff_out);
     if (cudaGetLastError() != cudaSuccess) return ME_ERR_CUDA;
     return ME_OK;
 }

@@ -872,6 +872,63 @@ class MetropolisEngine:
             raise ValueError("bad arguments to me_statistical_inefficiency")
         return g
 
+    def _equilibration_kernel(self, block, col, n_sel, nskip, fast=True):
+        """(t0, g, Neff_max) tensors [n_sel] for column ``col`` of a block [rows, cols, ld] on the device."""
+        rows, cols, ld = block.shape
+        n_cand = (rows - 1 + nskip - 1) // nskip
+        scratch = torch.empty(2 * n_cand * n_sel, dtype=torch.float64, device=self.device)
+        out = torch.empty((3, n_sel), dtype=torch.float64, device=self.device)
+        rc = self._lib.me_detect_equilibration(_ptr(block), rows, cols, ld, int(col), 0, n_sel, int(nskip), int(bool(fast)),
+                                               _ptr(scratch), scratch.numel(), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                               self._stream())
+        if rc != 0:
+            raise ValueError("bad arguments to me_detect_equilibration (need at least 3 recorded rows)")
+        return out[0].long(), out[1], out[2]
+
+    def detect_equilibration(self, column=0, n_chains=1024, nskip=1, fast=True):
+        """Per-chain start of the production region ``t0`` (in measures), statistical inefficiency ``g`` and
+        ``Neff_max`` of one stored column for the first ``n_chains`` local chains: pymbar's ``detectEquilibration``
+        (what the reference's ``save_equilibrium_stats`` evaluates per data-frame column, ME:490, statistics.py:25-48)
+        as a device kernel — one thread per (chain, candidate t0).  ``nskip`` thins the candidates (pymbar's own
+        parameter; use ~rows/100 for long series)."""
+        chunks = [(t, used) for t, used in self._ts_chunks if used]
+        if len(chunks) != 1:
+            raise RuntimeError("detect_equilibration needs the series in one storage chunk (raise ts_chunk_bytes)")
+        t, used = chunks[0]
+        return self._equilibration_kernel(t[:used], column, min(int(n_chains), self.n_chains), nskip, fast)
+
+    def save_equilibrium_stats(self, chain=0, nskip=1):
+        """The reference's post-run summary for one chain (ME:481-504 without the ``external_df`` plumbing):
+        ``eq_points`` = {column: [t0, g, Neff_max]} for every non-constant data-frame column (complex ones split into
+        ``_real`` / ``_imag``, statistics.py:25-48), ``global_eq_point`` = the largest t0 among the columns that are
+        not sampling widths (ME:492), ``equilibrated_means`` = column means from that row on (statistics.py:53-64)
+        plus ``"global_cutoff"``.  The series are analysed on the device (me_detect_equilibration)."""
+        df = self.save_time_series(chain)
+        names, series = [], []
+        for name in df.columns.values:
+            col = df[name].to_numpy()
+            if np.iscomplexobj(col):
+                parts = ((name + "_real", col.real), (name + "_imag", col.imag))
+            else:
+                parts = ((name, col.astype(np.float64)),)
+            if df[name].nunique() > 1:                                           # statistics.py:33 "ignore const series"
+                for n_, v in parts:
+                    names.append(n_)
+                    series.append(v)
+        self.eq_points = {}
+        if series:
+            # one block [rows, columns, 1]: every data-frame column is analysed by the same kernel
+            block = torch.tensor(np.stack(series, axis=1)[:, :, None], dtype=torch.float64, device=self.device).contiguous()
+            for k, n_ in enumerate(names):
+                t0, g, neff = self._equilibration_kernel(block, k, 1, nskip)
+                self.eq_points[n_] = [int(t0.item()), float(g.item()), float(neff.item())]
+        cut = [t for key, (t, _g, _n) in self.eq_points.items() if "sampling_width" not in key]
+        self.global_eq_point = max(cut) if cut else 0
+        self.equilibrated_means = {name: np.average(df.loc[self.global_eq_point:, name]) for name in df.columns.values}
+        self.eq_means_error = {}
+        self.equilibrated_means["global_cutoff"] = self.global_eq_point
+        return self.eq_points
+
     # ------------------------------------------------------------------ checkpoint / resume (SURVEY §5)
     def state_dict(self):
         n, s = ctypes.c_int64(), ctypes.c_uint64()

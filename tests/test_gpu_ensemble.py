@@ -164,3 +164,30 @@ def test_pooled_moments_mixed_shape_against_time_series():
     cov_c = cm.T @ cm.conj() / (c.shape[0] - 1)
     assert np.allclose(ps["cov_complex"], cov_c, rtol=1e-9, atol=1e-12)
     assert np.allclose(ps["observables_mean"][3:7], np.abs(c).mean(0), rtol=1e-10)
+
+
+def test_equilibration_detection_matches_oracle():
+    """device detectEquilibration (me_detect_equilibration) against the numpy restatement of
+    pymbar's algorithm (oracle/py_port.py::detect_equilibration), on stored series that start far from equilibrium."""
+    import metropolisengine_b200 as me
+    from oracle.py_port import detect_equilibration, pymbar_statistical_inefficiency
+    eng = me.MetropolisEngine(("xy_well", 1.0), initial_real_params=np.array([3.0, -2.0]), temp=.1, n_chains=64, seed=3)
+    eng.run(400, 2)
+    ts = eng.time_series().cpu().numpy()                      # [rows, cols, chains]
+    for col, nskip in ((0, 1), (1, 7)):
+        t0, g, neff = eng.detect_equilibration(column=col, n_chains=64, nskip=nskip)
+        t0, g, neff = t0.cpu().numpy(), g.cpu().numpy(), neff.cpu().numpy()
+        for ch in (0, 5, 63):
+            ot, og, on = detect_equilibration(ts[:, col, ch], fast=True, nskip=nskip)
+            assert t0[ch] == ot, (col, ch, t0[ch], ot)
+            assert abs(g[ch] - og) <= 1e-9 * og and abs(neff[ch] - on) <= 1e-9 * on
+        assert (t0 > 0).mean() > 0.9                          # the transient from (3, -2) is cut off
+    # the reference-shaped summary for one chain
+    pts = eng.save_equilibrium_stats(chain=5, nskip=4)
+    assert set(pts) >= {"param_0", "param_1", "abs_param_0", "param_0_squared", "total_energy", "real_group_sampling_width"}
+    assert eng.equilibrated_means["global_cutoff"] == eng.global_eq_point == max(
+        t for k, (t, _g, _n) in pts.items() if "sampling_width" not in k)
+    ot, og, on = detect_equilibration(ts[:, 0, 5], fast=True, nskip=4)
+    assert pts["param_0"][0] == ot and abs(pts["param_0"][1] - og) <= 1e-9 * og
+    cut = eng.global_eq_point
+    assert abs(eng.equilibrated_means["param_1"] - ts[cut:, 1, 5].mean()) < 1e-12

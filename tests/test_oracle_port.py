@@ -80,3 +80,24 @@ def test_statistical_inefficiency_ar1():
         x[i] = phi * x[i - 1] + e[i]
     g = statistical_inefficiency(x)
     assert abs(g - (1 + phi) / (1 - phi)) < 0.8   # exact value 9
+
+
+def test_equilibration_detection_on_known_transient():
+    """oracle/py_port.py::detect_equilibration (restated pymbar algorithm, parity unpinned — see its header):
+    AR(1) noise plus an exponential transient of 5 correlation-free time constants must be cut near its end, and
+    the inefficiency of the production region must be the AR(1) value."""
+    from oracle.py_port import detect_equilibration, pymbar_statistical_inefficiency
+    rng = np.random.default_rng(1)
+    phi, n = 0.7, 3000
+    x = np.zeros(n)
+    e = rng.standard_normal(n)
+    for i in range(1, n):
+        x[i] = phi * x[i - 1] + e[i]
+    assert abs(pymbar_statistical_inefficiency(x) - (1 + phi) / (1 - phi)) < 0.5
+    y = x.copy()
+    y[:400] += 8 * np.exp(-np.arange(400) / 60.)
+    t0, g, neff = detect_equilibration(y, nskip=10)
+    assert 60 <= t0 <= 400 and abs(g - (1 + phi) / (1 - phi)) < 1.5 and neff > 300
+    assert detect_equilibration(np.ones(50)) == (0, 1.0, 1.0)
+    t0_flat, _g, _n = detect_equilibration(x, nskip=10)
+    assert t0_flat < 300                                        # no transient: (almost) nothing is discarded
