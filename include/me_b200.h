@@ -215,6 +215,7 @@ typedef struct me_k4_config {
 } me_k4_config;
 typedef struct me_k4_layout {
     int32_t X, E, SIG, MEAN, OBSM, NACC, STATUS, WORDS, D, TS_COLS, N_COMPLEX, TILE, FACTOR_BYTES, MOM_WORDS;
+    int32_t MOM_SCRATCH_PER_SM;   /* doubles of me_k4_moments scratch per SM */
 } me_k4_layout;
 int me_k4_layout_get(me_k4_layout *out);
 int me_k4_create(const me_k4_config *cfg, me_k4 **out);
@@ -229,15 +230,23 @@ int me_k4_step(me_k4 *eng, int64_t n_steps, const double *s_a, float *dbg_z, flo
 int me_k4_measure(me_k4 *eng, double *ts, int64_t ts_row, void *stream);
 /* Pooled moments of the current states of this handle's chains, deterministic (fixed summation order):
  * inc[MOM_WORDS] complex (double pairs) = [chains, sum sigma, sum a, sum a^2, sum c[64], sum c c^H[64x64]] about
- * shift[129] (a, Re c, Im c).  scratch needs n_sm * MOM_WORDS * 2 doubles.  The caller all-reduces `inc` across
- * ranks (NCCL) and adds it to its running moments. */
-int me_k4_moments(me_k4 *eng, const double *shift, double *scratch, int64_t scratch_doubles, double *inc, void *stream);
+ * shift[129] (a, Re c, Im c).  scratch needs (n_sm + 1) * MOM_SCRATCH_PER_SM doubles.  The caller all-reduces `inc` across
+ * ranks (NCCL) and adds it to its running moments.
+ * Single-GPU fast path: mom_accum (may be NULL) = running moments advanced in the same launch (mom[w] += inc[w], w != 1);
+ * snapshot (may be NULL, needs MOM_WORDS + 2 complex) = [mom after the update | inc[0], inc[1]], the input of a factor
+ * refresh that runs later on another stream. */
+int me_k4_moments(me_k4 *eng, const double *shift, double *scratch, int64_t scratch_doubles, double *inc, double *mom_accum,
+                  double *snapshot, void *stream);
 /* Pooled moments -> shared covariance (+ sigma^2/n regulariser, ME:418,425) -> Cholesky -> BF16 operand, one
  * launch, no host sync.  mom / inc are complex (double pairs): mom = [N, -, sum a, sum a^2, sum c[64], sum c c^H
  * [64x64]] about a fixed shift, inc = [chains measured now, sum of their sigma]; cov_c receives the 64x64 complex
  * covariance, cov_a the variance of the real parameter, s_a its square root, status != 0 if not positive definite. */
-int me_k4_refactor(me_k4 *eng, const double *mom, const double *inc, double *cov_c, double *cov_a, void *factor_bf16,
-                   double *s_a, int32_t *status, void *stream);
+int me_k4_refactor(me_k4 *eng, const double *mom, const double *inc, int64_t n_measure, double *cov_c, double *cov_a,
+                   void *factor_bf16, double *s_a, int32_t *status, void *stream);   /* n_measure <= 0: the handle's counter */
+/* The factor the next me_k4_step launches read (double-buffering: a refresh may be writing the other buffer), and the
+ * number of SMs the step kernel leaves idle so that the one-CTA refresh can run beside it on another stream. */
+int me_k4_set_factor(me_k4 *eng, const void *factor_bf16);
+int me_k4_set_reserved_sms(me_k4 *eng, int32_t n);
 int me_k4_get_counters(me_k4 *eng, int64_t *n_measure, uint64_t *step);
 const char *me_k4_last_error(me_k4 *eng);
 

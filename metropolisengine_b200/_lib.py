@@ -46,7 +46,7 @@ class MeK4Config(ctypes.Structure):
 
 class MeK4Layout(ctypes.Structure):
     _fields_ = [(k, _i32) for k in ("X", "E", "SIG", "MEAN", "OBSM", "NACC", "STATUS", "WORDS", "D", "TS_COLS",
-                                    "N_COMPLEX", "TILE", "FACTOR_BYTES", "MOM_WORDS")]
+                                    "N_COMPLEX", "TILE", "FACTOR_BYTES", "MOM_WORDS", "MOM_SCRATCH_PER_SM")]
 
 
 # every symbol include/me_b200.h declares: name -> (restype, argtypes)
@@ -78,8 +78,10 @@ SIGNATURES = {
     "me_k4_init": (ctypes.c_int, [_vp, _vp, _i32, _f64, _vp]),
     "me_k4_step": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "me_k4_measure": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
-    "me_k4_moments": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
-    "me_k4_refactor": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "me_k4_moments": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "me_k4_refactor": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "me_k4_set_factor": (ctypes.c_int, [_vp, _vp]),
+    "me_k4_set_reserved_sms": (ctypes.c_int, [_vp, _i32]),
     "me_k4_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
     "me_k4_last_error": (_cp, [_vp]),
     "me_probe_fp64": (ctypes.c_int, [_i32, _i64, _vp, _i64, _vp, ctypes.POINTER(_i64)]),

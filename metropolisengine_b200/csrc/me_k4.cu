@@ -151,16 +151,33 @@ __device__ __forceinline__ U4 philox(unsigned c0, unsigned c1, unsigned c2, unsi
     U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
     return o;
 }
-/* two normals from 64 random bits: radius from 32 bits, first-quadrant angle from 30 bits, the two signs from 2
- * independent bits -> the pair's law is exactly symmetric whatever the accuracy of the fast intrinsics */
+/* two normals from 64 random bits: radius from the top 23 bits of `a`, angle from 25 bits of `b` (2 quadrant bits +
+ * 23-bit fraction).  Built for the SM's scarcest pipe: no integer->float conversions (the uniforms are assembled
+ * as float mantissas), sin/cos as FP32 polynomials after an integer quadrant reduction, so the only XU operations
+ * left are one MUFU.LG2 and one MUFU.SQRT per PAIR (was five: 2 I2F, LG2, RSQ, SIN, COS).  The two signs and the
+ * sin/cos swap come from independent bits, so the pair's law is exactly symmetric whatever the accuracy of the
+ * approximations (relative error ~1e-6, far below the BF16 rounding of the operand). */
 __device__ __forceinline__ void normal_pair_f32(unsigned a, unsigned b, float &z0, float &z1) {
-    const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   /* (0,1] */
-    const float rad = sqrtf(-2.0f * __logf(fminf(u1, 1.0f)));
-    const float th = __uint2float_rn(b >> 2) * 1.4629180792671596e-09f;                            /* (pi/2) 2^-30 */
-    float s, c;
-    __sincosf(th, &s, &c);
-    z0 = (b & 1u) ? -rad * c : rad * c;
-    z1 = (b & 2u) ? -rad * s : rad * s;
+    const float u = 2.0f - __uint_as_float(0x3f800000u | (a >> 9));                 /* (0, 1], multiples of 2^-23 */
+    const float w = -1.3862943611f * __log2f(u);                                    /* -2 ln u >= 0 */
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(w));
+    const unsigned zz = b + 0x20000000u;                                            /* quadrant = zz >> 30 (rounded) */
+    const float v = __uint_as_float(0x3f800000u | ((zz >> 7) & 0x007fffffu)) - 1.5f;   /* [-1/2, 1/2): angle (pi/2) v */
+    const float q = v * v;
+    float ps = fmaf(q, -0.0046817541f, 0.0796926263f);                              /* sin((pi/2) v) / v */
+    ps = fmaf(q, ps, -0.6459640975f);
+    ps = fmaf(q, ps, 1.5707963268f);
+    const float sr = v * ps;
+    float pc = fmaf(q, 0.0009192603f, -0.0208634807f);                              /* cos((pi/2) v) */
+    pc = fmaf(q, pc, 0.2536695079f);
+    pc = fmaf(q, pc, -1.2337005501f);
+    const float cr = fmaf(q, pc, 1.0f);
+    /* quadrant 0: (cos, sin) = (cr, sr); 1: (-sr, cr); 2: (-cr, -sr); 3: (sr, -cr) */
+    const bool odd = (zz & 0x40000000u) != 0;
+    const float cs = odd ? sr : cr, sn = odd ? cr : sr;
+    z0 = rad * __uint_as_float(__float_as_uint(cs) ^ ((zz + 0x40000000u) & 0x80000000u));
+    z1 = rad * __uint_as_float(__float_as_uint(sn) ^ (zz & 0x80000000u));
 }
 __device__ __forceinline__ double u53(unsigned hi, unsigned lo) {
     const double a = __hiloint2double(0x43300000 - (27 << 20), (int)(hi >> 5)) - 33554432.0;
@@ -217,6 +234,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_d = S.tmem_slot;
     const double s_a = *p.s_a;
+    const double q0 = (double)(16 * g - K4_NC / 2);      /* wavenumber of this thread's first mode */
     const uint32_t zs_addr = smem_u32(S.zs), ls_addr = smem_u32(S.ls);
     uint32_t parity = 0;
 
@@ -306,19 +324,21 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
                 for (int k = 0; k < 32; k++) p.dbg_delta[(long long)(32 * g + k) * ld + ch] = __uint_as_float(raw[k]);
             }
             const double sig = S.sig_s[m];
-            double tot = 0.0, qsum = 0.0;
+            /* sum_j q_j^2 |c_j|^2 with q_j = q0 + jj: three sums with compile-time weights (1, jj, jj^2) and one
+               combination per thread — no integer->double conversion per mode (XU pipe) */
+            double tot = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll
             for (int jj = 0; jj < 16; jj++) {
                 const int j = 16 * g + jj;
                 const double re = fma(sig, (double)__uint_as_float(raw[2 * jj]), S.xs[2 * j][m]);
                 const double im = fma(sig, (double)__uint_as_float(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
                 const double m2 = fma(re, re, im * im);
-                const double q = (double)(j - K4_NC / 2);
                 tot += m2;
-                qsum = fma(q * q, m2, qsum);
+                t1 = fma((double)jj, m2, t1);
+                t2 = fma((double)(jj * jj), m2, t2);
             }
             S.part[g][0][m] = tot;
-            S.part[g][1][m] = qsum;
+            S.part[g][1][m] = fma(q0 * q0, tot, fma(2.0 * q0, t1, t2));
             __syncthreads();
 
             /* ---- decision (one thread per chain): ME:247-258 */
@@ -447,120 +467,185 @@ __global__ void k4_measure(K4Params p) {
 
 /* Pooled moments of the current states, deterministic two-stage reduction (no atomics: the covariance feeds the
  * proposals, so run-to-run bit reproducibility needs a fixed summation order).
- * Stage 1: CTA b sums its slice of chains into part[b][K4_MOMW] (complex): [0] chains, [1] sum sigma, [2] sum a,
- *          [3] sum a^2, [4..68) sum c_i, [68..) sum c_i conj(c_j), all about the shift (shift[0] = a, then Re c, Im c).
- *          256 threads; thread t owns the 4x4 block (i0 = 4 (t / 16), j0 = 4 (t % 16)) of the 64x64 outer product;
- *          chains are staged through shared memory 64 at a time.
- * Stage 2: out[w] = sum_b part[b][w] in CTA order. */
+ *
+ * With Y = [Re c; Im c] (128 rows) about the shift, everything the complex second moment needs is in the LOWER triangle of
+ * the real symmetric S = sum_chains Y Y^T (128 x 128):
+ *     Re (c c^H)_ij = S[i][j] + S[64+i][64+j],    Im (c c^H)_ij = S[64+i][j] - S[64+j][i]
+ * — a rank-k update with half the flops of the full complex outer product (8,256 instead of 16,384 FMAs per chain).
+ * Stage 1: CTA b sums its slice of chains.  Chains are staged 32 at a time in shared memory as Ys[k][row]; thread t < 136
+ *          owns the 8 x 8 register tile (ti, tj), tj <= ti, of S (64 independent FMA chains per thread: the FP64 pipe
+ *          stays full with ~1 warp per sub-partition); threads 136..255 keep the column sums of Y.
+ *          part[b]: [0] chains, [1] sum sigma, [2] sum a, [3] sum a^2, [4..132) sum Y, [132..) S row-major (lower part).
+ * Stage 2: fixed-order sum over the CTAs (2a), emitted in the complex layout the host accumulates (2b):
+ *          out[K4_MOMW] (double2): [0] chains, [1] sum sigma, [2] sum a, [3] sum a^2, [4..68) sum c, [68..) sum c c^H. */
 constexpr int K4_MOMW = 4 + K4_NC + K4_NC * K4_NC;
 constexpr int K4_MOM_CHUNK = 32;
+constexpr int K4_PARTW = 4 + K4_N + K4_N * K4_N;        /* doubles per CTA partial */
 
-__global__ void __launch_bounds__(256) k4_moments_stage1(K4Params p, const double *shift, double2 *part,
+__global__ void __launch_bounds__(256) k4_moments_stage1(K4Params p, const double *shift, double *part,
                                                          long long chains_per_cta) {
-    /* thread t: half h = t / 128 of each staged chunk of chains, 8x4 block (i0 = 8 (u / 16), j0 = 4 (u % 16)),
-       u = t % 128, of the 64x64 outer product; the two halves are combined through shared memory at the end */
-    __shared__ double cr[K4_NC][K4_MOM_CHUNK + 1], ci[K4_NC][K4_MOM_CHUNK + 1];
+    /* Ys[k][pos(row)]: every block of 8 rows is followed by 2 pad doubles, so that the 16-byte reads of lanes that own
+       neighbouring tiles (80 B apart) fall into distinct banks; the row length 162 keeps the staging stores (same
+       row, consecutive k) at 4-way instead of 32-way conflicts. */
+    constexpr int YLD = K4_N + 2 * (K4_N / 8) + 2;       /* 162 */
+    __shared__ __align__(16) double Ys[K4_MOM_CHUNK][YLD];   /* 41 KB */
+    auto pos = [](int row) { return row + 2 * (row >> 3); };
     __shared__ double red[256];
-    const int tid = threadIdx.x, h = tid >> 7, u = tid & 127;
+    const int tid = threadIdx.x;
     const long long lo = (long long)blockIdx.x * chains_per_cta;
     long long hi = lo + chains_per_cta;
     if (hi > p.n_chains) hi = p.n_chains;
     const long long ld = p.ld;
-    const int i0 = 8 * (u / 16), j0 = 4 * (u % 16);
-    double ar[8][4], ai[8][4];
+    /* tile of thread t < 136: row-major enumeration of the lower triangle of the 16 x 16 tile grid */
+    int ti = 0, tj = 0;
+    {
+        int t = tid < 136 ? tid : 0;
+        while (t > ti) { t -= ti + 1; ti++; }
+        tj = t;
+    }
+    const bool tile_thread = tid < 136;
+    double acc[8][8];
 #pragma unroll
     for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) ar[a][b] = ai[a][b] = 0.0;
-    double s1r = 0.0, s1i = 0.0;          /* thread t < 64: sum of c_t */
-    double sa = 0.0, sa2 = 0.0, ssig = 0.0;
+        for (int b = 0; b < 8; b++) acc[a][b] = 0.0;
+    double colsum = 0.0, colsum2 = 0.0;                   /* thread 136 + r: sum of Y[r] (and of Y[120 + r] for r < 8) */
+    double sa = 0.0, sa2 = 0.0, ssig = 0.0;               /* threads < 32 */
     for (long long base = lo; base < hi; base += K4_MOM_CHUNK) {
         const int cnt = (int)((hi - base) < K4_MOM_CHUNK ? (hi - base) : K4_MOM_CHUNK);
         __syncthreads();
-        for (int e = tid; e < K4_NC * K4_MOM_CHUNK; e += 256) {
-            const int j = e / K4_MOM_CHUNK, c = e % K4_MOM_CHUNK;
-            const bool ok = c < cnt;
-            cr[j][c] = ok ? p.state[(long long)(K4_X + 1 + j) * ld + base + c] - shift[1 + j] : 0.0;
-            ci[j][c] = ok ? p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + base + c] - shift[1 + K4_NC + j] : 0.0;
+        /* stage: consecutive threads read consecutive chains of one state word (coalesced), write Ys[k][row] */
+        for (int e = tid; e < K4_N * K4_MOM_CHUNK; e += 256) {
+            const int row = e / K4_MOM_CHUNK, k = e % K4_MOM_CHUNK;
+            Ys[k][pos(row)] = k < cnt ? p.state[(long long)(K4_X + 1 + row) * ld + base + k] - shift[1 + row] : 0.0;
         }
         if (tid < cnt) {
             const double a = p.state[(long long)K4_X * ld + base + tid] - shift[0];
             sa += a; sa2 += a * a; ssig += p.state[(long long)K4_SIG * ld + base + tid];
         }
         __syncthreads();
-#pragma unroll 2
-        for (int c = h * (K4_MOM_CHUNK / 2); c < (h + 1) * (K4_MOM_CHUNK / 2); c++) {
-            double xr[8], xi[8], yr[4], yi[4];
+        if (tile_thread) {
+#pragma unroll 4
+            for (int k = 0; k < K4_MOM_CHUNK; k++) {
+                double ya[8], yb[8];
+                const double2 *pa = reinterpret_cast<const double2 *>(&Ys[k][10 * ti]);     /* pos(8 ti) */
+                const double2 *pb = reinterpret_cast<const double2 *>(&Ys[k][10 * tj]);
 #pragma unroll
-            for (int a = 0; a < 8; a++) { xr[a] = cr[i0 + a][c]; xi[a] = ci[i0 + a][c]; }
-#pragma unroll
-            for (int b = 0; b < 4; b++) { yr[b] = cr[j0 + b][c]; yi[b] = ci[j0 + b][c]; }
-#pragma unroll
-            for (int a = 0; a < 8; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) {     /* x conj(y) */
-                    ar[a][b] = fma(xr[a], yr[b], fma(xi[a], yi[b], ar[a][b]));
-                    ai[a][b] = fma(xi[a], yr[b], fma(-xr[a], yi[b], ai[a][b]));
+                for (int q = 0; q < 4; q++) {
+                    const double2 va = pa[q], vb = pb[q];
+                    ya[2 * q] = va.x; ya[2 * q + 1] = va.y; yb[2 * q] = vb.x; yb[2 * q + 1] = vb.y;
                 }
-        }
-        if (tid < K4_NC)
-            for (int c = 0; c < K4_MOM_CHUNK; c++) { s1r += cr[tid][c]; s1i += ci[tid][c]; }
-    }
-    double2 *out = part + (long long)blockIdx.x * K4_MOMW;
-    /* combine the two chain halves in a fixed order: half 1 writes, half 0 adds */
-    if (h == 1) {
 #pragma unroll
-        for (int a = 0; a < 8; a++)
+                for (int a = 0; a < 8; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) out[4 + K4_NC + (i0 + a) * K4_NC + (j0 + b)] = make_double2(ar[a][b], ai[a][b]);
-    }
-    __syncthreads();
-    if (h == 0) {
-#pragma unroll
-        for (int a = 0; a < 8; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                double2 *o = &out[4 + K4_NC + (i0 + a) * K4_NC + (j0 + b)];
-                *o = make_double2(ar[a][b] + o->x, ai[a][b] + o->y);
+                    for (int b = 0; b < 8; b++) acc[a][b] = fma(ya[a], yb[b], acc[a][b]);
             }
+        } else {
+            const int r = tid - 136;
+            for (int k = 0; k < K4_MOM_CHUNK; k++) colsum += Ys[k][pos(r)];
+            if (r < 8)
+                for (int k = 0; k < K4_MOM_CHUNK; k++) colsum2 += Ys[k][pos(120 + r)];
+        }
     }
-    if (tid < K4_NC) out[4 + tid] = make_double2(s1r, s1i);
-    /* the three scalar sums: fixed-order tree over the staging threads */
+    double *out = part + (long long)blockIdx.x * K4_PARTW;
+    if (tile_thread) {
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 8; b++) out[4 + K4_N + (8 * ti + a) * K4_N + (8 * tj + b)] = acc[a][b];
+    }
+    if (!tile_thread) {
+        out[4 + (tid - 136)] = colsum;
+        if (tid - 136 < 8) out[4 + 120 + (tid - 136)] = colsum2;
+    }
+    /* the three scalar sums: fixed-order trees */
     for (int which = 0; which < 3; which++) {
         __syncthreads();
         red[tid] = (tid < K4_MOM_CHUNK) ? (which == 0 ? ssig : (which == 1 ? sa : sa2)) : 0.0;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-        if (tid == 0) out[1 + which] = make_double2(red[0], 0.0);
+        if (tid == 0) out[1 + which] = red[0];
     }
-    if (tid == 0) out[0] = make_double2((double)(hi > lo ? hi - lo : 0), 0.0);
+    if (tid == 0) out[0] = (double)(hi > lo ? hi - lo : 0);
 }
 
-__global__ void k4_moments_stage2(const double2 *part, int n_parts, double2 *out) {
+/* stage 2a: total[idx] = sum over the CTA partials in CTA order (one thread per word, coalesced across threads;
+ * the upper triangle of S is never read, its threads idle) */
+__global__ void k4_moments_stage2a(const double *part, int n_parts, double *total) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K4_PARTW) return;
+    if (idx >= 4 + K4_N) {
+        const int e = idx - 4 - K4_N;
+        if (e / K4_N < e % K4_N) return;
+    }
+    /* loads in batches of 16 (independent), adds in CTA order (fixed summation order) */
+    double t = 0.0;
+    int b = 0;
+    for (; b + 16 <= n_parts; b += 16) {
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) v[q] = part[(long long)(b + q) * K4_PARTW + idx];
+#pragma unroll
+        for (int q = 0; q < 16; q++) t += v[q];
+    }
+    for (; b < n_parts; b++) t += part[(long long)b * K4_PARTW + idx];
+    total[idx] = t;
+}
+/* stage 2b: the complex layout the host accumulates.  Optionally (single-GPU fast path) the running moments are
+ * advanced here, mom[w] += inc[w] for w != 1, and a snapshot [mom (MOMW) | inc[0], inc[1]] is written for a factor
+ * refresh that runs asynchronously on another stream. */
+__global__ void k4_moments_stage2b(const double *total, double2 *out, double2 *mom, double2 *snap) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= K4_MOMW) return;
-    double re = 0.0, im = 0.0;
-    for (int b = 0; b < n_parts; b++) { re += part[(long long)b * K4_MOMW + w].x; im += part[(long long)b * K4_MOMW + w].y; }
-    out[w] = make_double2(re, im);
+    double2 v;
+    if (w < 4) v = make_double2(total[w], 0.0);
+    else if (w < 4 + K4_NC) { const int i = w - 4; v = make_double2(total[4 + i], total[4 + K4_NC + i]); }
+    else {
+        const int e = w - 4 - K4_NC, i = e / K4_NC, j = e % K4_NC;
+        auto S = [&](int r, int c) { return total[4 + K4_N + (r >= c ? r * K4_N + c : c * K4_N + r)]; };   /* symmetric */
+        v = make_double2(S(i, j) + S(K4_NC + i, K4_NC + j), S(K4_NC + i, j) - S(K4_NC + j, i));
+    }
+    out[w] = v;
+    if (mom != nullptr) {
+        double2 m = mom[w];
+        if (w != 1) { m.x += v.x; m.y += v.y; mom[w] = m; }
+        if (snap != nullptr) {
+            snap[w] = m;
+            if (w < 2) snap[K4_MOMW + w] = v;
+        }
+    }
+}
+
+/* 1 / sqrt(d) for a normal positive d: MUFU.RSQ64H seed + two Newton steps (relative error ~1e-16) */
+__device__ __forceinline__ double k4_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y * y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-d, y * y, 1.0);
+    return fma(0.5 * y, e, y);
 }
 
 /* Pooled covariance -> shared proposal factor, one CTA (runs once per measure after the 50th, ME:389,396).
  * mom (complex, as double pairs): [0] sample count N, [2] sum a, [3] sum a^2, [4..68) sum c, [68..) sum c c^H
  * (about a fixed shift); inc: [0] chains measured now, [1] sum of their sigma.  Computes
  *   C_c = (S2 - S1 S1^H / N)/(N-1) + small I,  small = mean(sigma)^2 / n   (the regulariser of ME:418,425),
- * its Cholesky factor G (right-looking, in shared memory), the BF16 UMMA operand of me_k4_step, and the same for
- * the real parameter.  status: nonzero if a pivot was not positive. */
+ * its Cholesky factor G, the BF16 UMMA operand of me_k4_step, and the same for the real parameter.
+ * Cholesky: left-looking by columns, 4 threads per row splitting the dot product (fixed order + shuffle tree), two
+ * barriers per column, pivot through one reciprocal square root.  status: nonzero if a pivot was not positive. */
 __global__ void __launch_bounds__(256) k4_refactor(const double2 *mom, const double2 *inc, long long n_meas,
                                                    double2 *cov_c, double *cov_a, __nv_bfloat16 *factor, double *s_a,
                                                    int *status) {
+    constexpr int LDA = K4_NC + 1;                       /* padded row length (double2) */
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    double2(*A)[K4_NC] = reinterpret_cast<double2(*)[K4_NC]>(smem_raw);
-    __shared__ double piv;
+    double2 *A = reinterpret_cast<double2 *>(smem_raw);  /* A[i * LDA + j] */
+    __shared__ double2 col[K4_NC];
     __shared__ int bad;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, row = tid >> 2, part = tid & 3;
     const double N = mom[0].x;
     const double sm = inc[1].x / inc[0].x;
     const double small = sm * sm / (double)n_meas;
+    const double inv_n = 1.0 / N, inv_n1 = 1.0 / (N - 1.0);
     const double2 *s1 = mom + 4, *s2 = mom + 4 + K4_NC;
     if (tid == 0) bad = 0;
     for (int e = tid; e < K4_NC * K4_NC; e += blockDim.x) {
@@ -568,36 +653,40 @@ __global__ void __launch_bounds__(256) k4_refactor(const double2 *mom, const dou
         /* s1_i conj(s1_j) */
         const double pr = s1[i].x * s1[j].x + s1[i].y * s1[j].y, pi = s1[i].y * s1[j].x - s1[i].x * s1[j].y;
         double2 v;
-        v.x = (s2[e].x - pr / N) / (N - 1.0) + (i == j ? small : 0.0);
-        v.y = (s2[e].y - pi / N) / (N - 1.0);
-        A[i][j] = v;
+        v.x = (s2[e].x - pr * inv_n) * inv_n1 + (i == j ? small : 0.0);
+        v.y = (s2[e].y - pi * inv_n) * inv_n1;
+        A[i * LDA + j] = v;
         cov_c[e] = v;
     }
     if (tid == 0) {
-        const double va = (mom[3].x - mom[2].x * mom[2].x / N) / (N - 1.0) + small;
+        const double va = (mom[3].x - mom[2].x * mom[2].x * inv_n) * inv_n1 + small;
         *cov_a = va;
         *s_a = sqrt(va);
     }
     __syncthreads();
     for (int j = 0; j < K4_NC; j++) {
-        if (tid == 0) {
-            double d = A[j][j].x;
-            if (!(d > 0.0)) { bad = 1; d = small > 0.0 ? small : 1e-300; }
-            piv = sqrt(d);
-            A[j][j].x = piv; A[j][j].y = 0.0;
+        /* v_i = A_ij - sum_{k<j} G_ik conj(G_jk), rows i >= j; the four parts of a row are adjacent lanes */
+        double ar = 0.0, ai = 0.0;
+        if (row >= j) {
+            for (int k = part; k < j; k += 4) {
+                const double2 pq = A[row * LDA + k], q = A[j * LDA + k];
+                ar = fma(pq.x, q.x, fma(pq.y, q.y, ar));
+                ai = fma(pq.y, q.x, fma(-pq.x, q.y, ai));
+            }
+        }
+        ar += __shfl_xor_sync(0xffffffffu, ar, 1); ai += __shfl_xor_sync(0xffffffffu, ai, 1);
+        ar += __shfl_xor_sync(0xffffffffu, ar, 2); ai += __shfl_xor_sync(0xffffffffu, ai, 2);
+        if (part == 0 && row >= j) {
+            const double2 a0 = A[row * LDA + j];
+            col[row] = make_double2(a0.x - ar, a0.y - ai);
         }
         __syncthreads();
-        const double inv = 1.0 / piv;
-        for (int i = j + 1 + tid; i < K4_NC; i += blockDim.x) { A[i][j].x *= inv; A[i][j].y *= inv; }
-        __syncthreads();
-        const int rem = K4_NC - 1 - j;              /* trailing (i, k), j < k <= i */
-        for (int e = tid; e < rem * rem; e += blockDim.x) {
-            const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-            if (k <= i) {                           /* A_ik -= G_ij conj(G_kj) */
-                const double2 p = A[i][j], q = A[k][j];
-                A[i][k].x -= p.x * q.x + p.y * q.y;
-                A[i][k].y -= p.y * q.x - p.x * q.y;
-            }
+        double d = col[j].x;
+        if (!(d > 0.0)) { if (tid == 0) bad = 1; d = small > 0.0 ? small : 1e-300; }
+        const double inv = k4_rsqrt(d);
+        if (part == 0 && row >= j) {
+            const double2 v = col[row];
+            A[row * LDA + j] = row == j ? make_double2(d * inv, 0.0) : make_double2(v.x * inv, v.y * inv);
         }
         __syncthreads();
     }
@@ -609,7 +698,7 @@ __global__ void __launch_bounds__(256) k4_refactor(const double2 *mom, const dou
         const int i = nrow >> 1, jj = k >> 1;
         double v = 0.0;
         if (jj <= i) {
-            const double2 gij = A[i][jj];
+            const double2 gij = A[i * LDA + jj];
             const bool ro = nrow & 1, ko = k & 1;
             v = (ro == ko) ? gij.x : (ro ? -gij.y : gij.y);
             if (jj == i && ro != ko) v = 0.0;       /* diagonal of G is real */
@@ -630,6 +719,7 @@ struct me_k4 {
     long long n_measure = 1;
     unsigned long long step = 0;
     int n_sm = 148;
+    int reserved_sms = 0;          /* SMs the step kernel leaves free (for a concurrent factor refresh) */
     std::string err;
 };
 
@@ -669,6 +759,7 @@ int me_k4_layout_get(me_k4_layout *o) {
     o->X = K4_X; o->E = K4_E; o->SIG = K4_SIG; o->MEAN = K4_MEAN; o->OBSM = K4_OBSM; o->NACC = K4_NACC;
     o->STATUS = K4_STATUS; o->WORDS = K4_WORDS; o->D = K4_D; o->TS_COLS = K4_D + 2; o->N_COMPLEX = K4_NC;
     o->TILE = K4_TILE; o->FACTOR_BYTES = K4_N * K4_N * 2; o->MOM_WORDS = K4_MOMW;
+    o->MOM_SCRATCH_PER_SM = K4_PARTW;
     return ME_OK;
 }
 
@@ -693,6 +784,18 @@ int me_k4_destroy(me_k4 *e) { delete e; return ME_OK; }
 int me_k4_bind(me_k4 *e, double *state, const void *factor_bf16, unsigned char *last_accept) {
     if (!e || !state || !factor_bf16) return ME_ERR_INVALID;
     e->state = state; e->factor = factor_bf16; e->last_accept = last_accept;
+    return ME_OK;
+}
+
+int me_k4_set_factor(me_k4 *e, const void *factor_bf16) {
+    if (!e || !factor_bf16) return ME_ERR_INVALID;
+    e->factor = factor_bf16;
+    return ME_OK;
+}
+
+int me_k4_set_reserved_sms(me_k4 *e, int32_t n) {
+    if (!e || n < 0) return ME_ERR_INVALID;
+    e->reserved_sms = n;
     return ME_OK;
 }
 
@@ -726,7 +829,8 @@ int me_k4_step(me_k4 *e, int64_t n_steps, const double *s_a, float *dbg_z, float
     }
     if (ce == cudaSuccess) {
         const long long n_tiles = e->cfg.n_chains / K4_TILE;
-        const int grid = (int)(n_tiles < e->n_sm ? n_tiles : e->n_sm);
+        const int avail = e->n_sm - e->reserved_sms > 0 ? e->n_sm - e->reserved_sms : 1;
+        const int grid = (int)(n_tiles < avail ? n_tiles : avail);
         k4_steps<<<grid, K4_THREADS, sizeof(K4Smem), (cudaStream_t)stream>>>(p);
         ce = cudaGetLastError();
     }
@@ -752,29 +856,34 @@ int me_k4_measure(me_k4 *e, double *ts, int64_t ts_row, void *stream) {
     return ME_OK;
 }
 
-int me_k4_moments(me_k4 *e, const double *shift, double *scratch, int64_t scratch_doubles, double *inc, void *stream) {
+int me_k4_moments(me_k4 *e, const double *shift, double *scratch, int64_t scratch_doubles, double *inc, double *mom_accum,
+                  double *snapshot, void *stream) {
     if (!e || !e->state || !shift || !scratch || !inc) return ME_ERR_INVALID;
     const int n_parts = e->n_sm < 1 ? 1 : e->n_sm;
-    if (scratch_doubles < (int64_t)n_parts * K4_MOMW * 2) return k4_fail(e, ME_ERR_INVALID, "moments scratch too small");
+    if (scratch_doubles < (int64_t)(n_parts + 1) * K4_PARTW) return k4_fail(e, ME_ERR_INVALID, "moments scratch too small");
     K4Params p;
     k4_base(e, p);
     const long long per = (e->cfg.n_chains + n_parts - 1) / n_parts;
     int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    k4_moments_stage1<<<n_parts, 256, 0, (cudaStream_t)stream>>>(p, shift, reinterpret_cast<double2 *>(scratch), per);
-    k4_moments_stage2<<<(K4_MOMW + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2 *>(scratch),
-                                                                            n_parts, reinterpret_cast<double2 *>(inc));
+    k4_moments_stage1<<<n_parts, 256, 0, (cudaStream_t)stream>>>(p, shift, scratch, per);
+    double *total = scratch + (long long)n_parts * K4_PARTW;
+    k4_moments_stage2a<<<(K4_PARTW + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, n_parts, total);
+    k4_moments_stage2b<<<(K4_MOMW + 127) / 128, 128, 0, (cudaStream_t)stream>>>(total, reinterpret_cast<double2 *>(inc),
+                                                                             reinterpret_cast<double2 *>(mom_accum),
+                                                                             reinterpret_cast<double2 *>(snapshot));
     cudaError_t ce = cudaGetLastError();
     cudaSetDevice(prev);
     if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_moments: ") + cudaGetErrorString(ce));
     return ME_OK;
 }
 
-int me_k4_refactor(me_k4 *e, const double *mom, const double *inc, double *cov_c, double *cov_a, void *factor_bf16,
-                   double *s_a, int32_t *status, void *stream) {
+int me_k4_refactor(me_k4 *e, const double *mom, const double *inc, int64_t n_measure, double *cov_c, double *cov_a,
+                   void *factor_bf16, double *s_a, int32_t *status, void *stream) {
     if (!e || !mom || !inc || !cov_c || !cov_a || !factor_bf16 || !s_a) return ME_ERR_INVALID;
+    if (n_measure <= 0) n_measure = e->n_measure;
     int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
     static bool attr_set = false;
-    const int smem = K4_NC * K4_NC * (int)sizeof(double2);
+    const int smem = K4_NC * (K4_NC + 1) * (int)sizeof(double2);
     cudaError_t ce = cudaSuccess;
     if (!attr_set) {
         ce = cudaFuncSetAttribute(k4_refactor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -782,7 +891,7 @@ int me_k4_refactor(me_k4 *e, const double *mom, const double *inc, double *cov_c
     }
     if (ce == cudaSuccess) {
         k4_refactor<<<1, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const double2 *>(mom),
-                                                            reinterpret_cast<const double2 *>(inc), e->n_measure,
+                                                            reinterpret_cast<const double2 *>(inc), n_measure,
                                                             reinterpret_cast<double2 *>(cov_c), cov_a,
                                                             reinterpret_cast<__nv_bfloat16 *>(factor_bf16), s_a, status);
         ce = cudaGetLastError();

@@ -8,9 +8,12 @@ block is *pooled over the ensemble* and shared by all chains.  It is the running
 sample so far plus the reference's ``sigma^2/n`` regulariser (ME:418,425), used from the 50th measure on (ME:389,396);
 across GPUs its moments are summed with one NCCL all-reduce per measure (the path's only collective).
 
-Host work per measure (all stream-ordered, no host sync): per-chain means / observable means / time-series row in
-libme_b200 (me_k4_measure); pooled moments with one complex GEMM (torch -> cuBLAS, a plain library GEMM), 64x64
-Cholesky, and the BF16 re-packing of the factor into the UMMA operand layout (tensor plumbing).
+Work per measure (all stream-ordered, no host sync): per-chain means / observable means / time-series row
+(me_k4_measure); pooled moments as a symmetric rank-k update (me_k4_moments); covariance + 64x64 complex Cholesky + BF16
+re-packing of the factor into the UMMA operand layout (me_k4_refactor).  The factor refresh is a one-CTA kernel, so by
+default it runs on a SIDE stream beside the next block of steps (the step kernel leaves one SM free): the steps after
+measure b use the factor of measure b-1.  The lag is deterministic and only shapes the (symmetric) proposal;
+``async_refresh=False`` gives the strictly sequential schedule.
 """
 import ctypes
 import math
@@ -29,7 +32,7 @@ class SharedCovarianceEngine:
     def __init__(self, energy_consts=(10.0, -1.0, 0.05, 1.0), reject_condition=True, initial_real_params=None,
                  initial_complex_params=None, sampling_width=0.05, covariance_matrix_real=None,
                  covariance_matrix_complex=None, params_names=None, target_acceptance=.3, temp=0, *, n_chains=128,
-                 seed=0, device=None, record=True, distributed=False, ts_chunk_rows=64):
+                 seed=0, device=None, record=True, distributed=False, ts_chunk_rows=64, async_refresh=True):
         """``energy_consts`` = (kappa, alpha, gamma, beta) of the cylinder-style energy (SURVEY.md §8d C4);
         ``reject_condition=True`` enables its hard wall ``|a| >= 1`` (legacy metropolis_engine.py:103,139)."""
         if not torch.cuda.is_available():
@@ -72,8 +75,17 @@ class SharedCovarianceEngine:
         self._h = h
         dev, f64 = self.device, torch.float64
         self.state = torch.zeros((lay.WORDS, self.n_chains), dtype=f64, device=dev)
-        self._factor = torch.zeros((16, 128, 8), dtype=torch.bfloat16, device=dev)
-        self._s_a = torch.ones(1, dtype=f64, device=dev)
+        # factor / s_a are triple-buffered: one pair is read by the step kernel, one holds the finished refresh that the
+        # next launch adopts, one is being written by the refresh in flight
+        self._factors = [torch.zeros((16, 128, 8), dtype=torch.bfloat16, device=dev) for _ in range(3)]
+        self._s_as = [torch.ones(1, dtype=f64, device=dev) for _ in range(3)]
+        self._cur = 0
+        self._factor, self._s_a = self._factors[0], self._s_as[0]
+        self._async = bool(async_refresh)
+        self._side = torch.cuda.Stream(device=dev) if self._async else None
+        self._in_flight = None          # (event, buffer index) of the refresh launched at the last measure
+        self._ready = None              # ... of the one before: adopted by the next step launch
+        self._refresh_count = 0
         self._last_accept = torch.zeros(self.n_chains, dtype=torch.uint8, device=dev)
         self._check(self._lib.me_k4_bind(self._h, _ptr(self.state), _ptr(self._factor), _ptr(self._last_accept)))
         # shared covariances (ME:63-70): identity unless given
@@ -88,9 +100,13 @@ class SharedCovarianceEngine:
                              (xc if xc.ndim == 1 else xc.mean(0)).real, (xc if xc.ndim == 1 else xc.mean(0)).imag])
         self._shift = torch.as_tensor(np.ascontiguousarray(x0), dtype=f64, device=dev)
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        self._scratch = torch.zeros(n_sm * lay.MOM_WORDS * 2, dtype=f64, device=dev)
+        self._scratch = torch.zeros((n_sm + 1) * lay.MOM_SCRATCH_PER_SM, dtype=f64, device=dev)
         self._inc_full = torch.zeros(lay.MOM_WORDS, dtype=torch.complex128, device=dev)
         self._mom = torch.zeros(4 + N_C + N_C * N_C, dtype=torch.complex128, device=dev)   # count, -, sum a, sum a^2, sum c, sum c c^H
+        self._snaps = [torch.zeros(lay.MOM_WORDS + 2, dtype=torch.complex128, device=dev) for _ in range(2)]
+        self._snap_events = [None, None]
+        if self._async:
+            self._check(self._lib.me_k4_set_reserved_sms(self._h, 1))
         self._inc = torch.zeros(2, dtype=torch.complex128, device=dev)
         self._psd_status = torch.zeros(1, dtype=torch.int32, device=dev)
         per_chain = xr.ndim == 2 or xc.ndim == 2
@@ -138,8 +154,9 @@ class SharedCovarianceEngine:
         B[1::2, 0::2] = -gi
         B[1::2, 1::2] = gr
         self._B = B
-        self._factor.copy_(B.view(128, 16, 8).permute(1, 0, 2).to(torch.bfloat16))
-        self._s_a.copy_(torch.sqrt(self._cov_a))
+        for f, sa in zip(self._factors, self._s_as):
+            f.copy_(B.view(128, 16, 8).permute(1, 0, 2).to(torch.bfloat16))
+            sa.copy_(torch.sqrt(self._cov_a))
 
     @property
     def measure_step_counter(self):
@@ -154,11 +171,30 @@ class SharedCovarianceEngine:
         return s.value
 
     # ------------------------------------------------------------------ hot path
+    def _adopt_refresh(self):
+        """Switch the step kernel to the most recent factor whose refresh was launched at least one measure ago."""
+        if self._ready is not None:
+            ev, idx = self._ready
+            torch.cuda.current_stream(self.device).wait_event(ev)      # finished long ago: no stall
+            self._cur = idx
+            self._factor, self._s_a = self._factors[idx], self._s_as[idx]
+            self._check(self._lib.me_k4_set_factor(self._h, _ptr(self._factor)))
+            self._ready = None
+
+    def synchronize_refresh(self):
+        """Wait for the factor refresh in flight and make it the current one (reads of the shared covariance, tests)."""
+        if self._in_flight is not None:
+            self._ready, self._in_flight = self._in_flight, None
+        self._adopt_refresh()
+
     def step(self, k=1, _dbg=None):
         dz = dd = None
         if _dbg is not None:
             dz, dd = _dbg
+        self._adopt_refresh()
         self._launch(self._lib.me_k4_step(self._h, int(k), _ptr(self._s_a), _ptr(dz), _ptr(dd), self._stream()))
+        if self._in_flight is not None:           # the refresh launched at the last measure becomes adoptable
+            self._ready, self._in_flight = self._in_flight, None
 
     def step_all(self):
         self.step(1)
@@ -183,17 +219,47 @@ class SharedCovarianceEngine:
             self._launch(self._lib.me_k4_measure(self._h, None, 0, self._stream()))
         n = self.measure_step_counter
         inc = self._inc_full
+        parity = self._refresh_count % 2
+        snap = self._snaps[parity]
+        if self._snap_events[parity] is not None:      # the refresh that read this snapshot two measures ago
+            torch.cuda.current_stream(self.device).wait_event(self._snap_events[parity])
+            self._snap_events[parity] = None
+        fused = not self._distributed            # single GPU: the moments kernel advances mom and writes the snapshot
         self._launch(self._lib.me_k4_moments(self._h, _ptr(self._shift), _ptr(self._scratch), self._scratch.numel(),
-                                             _ptr(inc), self._stream()))
-        self.launch_count += 1
-        if self._distributed:
+                                             _ptr(inc), _ptr(self._mom) if fused else None,
+                                             _ptr(snap) if fused else None, self._stream()))
+        self.launch_count += 2
+        if not fused:
             parallel.allreduce_sum_(torch.view_as_real(inc))
-        self._mom[0] += inc[0]
-        self._mom[2:] += inc[2:]
+            self._mom[0] += inc[0]
+            self._mom[2:] += inc[2:]
+            snap[:-2].copy_(self._mom)
+            snap[-2:].copy_(inc[:2])
         if n > 50:                                                                            # ME:389,396
-            self._launch(self._lib.me_k4_refactor(self._h, _ptr(self._mom), _ptr(inc), _ptr(self._cov_c),
-                                                  _ptr(self._cov_a), _ptr(self._factor), _ptr(self._s_a),
-                                                  _ptr(self._psd_status), self._stream()))
+            mw = self._lay.MOM_WORDS
+            if not self._async:
+                self._launch(self._lib.me_k4_refactor(self._h, _ptr(snap), _ptr(snap[mw:]), n, _ptr(self._cov_c),
+                                                      _ptr(self._cov_a), _ptr(self._factor), _ptr(self._s_a),
+                                                      _ptr(self._psd_status), self._stream()))
+            else:
+                # refresh into a buffer that is neither read by the step kernel nor waiting to be adopted, on the side
+                # stream, behind this measure
+                if self._in_flight is not None:   # two measures without a step in between: the older refresh (finished
+                    self._ready, self._in_flight = self._in_flight, None     # before this one starts) becomes adoptable
+                busy = {self._cur} | ({self._ready[1]} if self._ready is not None else set())
+                idx = min(i for i in range(3) if i not in busy)
+                main = torch.cuda.current_stream(self.device)
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self._launch(self._lib.me_k4_refactor(self._h, _ptr(snap), _ptr(snap[mw:]), n, _ptr(self._cov_c),
+                                                          _ptr(self._cov_a), _ptr(self._factors[idx]),
+                                                          _ptr(self._s_as[idx]), _ptr(self._psd_status),
+                                                          ctypes.c_void_p(self._side.cuda_stream)))
+                    ev = torch.cuda.Event()
+                    ev.record(self._side)
+                self._snap_events[parity] = ev
+                self._in_flight = (ev, idx)
+            self._refresh_count += 1
 
     def run(self, n_measures, steps_per_measure):
         for _ in range(int(n_measures)):
@@ -243,10 +309,14 @@ class SharedCovarianceEngine:
 
     @property
     def covariance_matrix_real(self):
+        if self._side is not None:
+            self._side.synchronize()
         return self._cov_a.reshape(1, 1).cpu().numpy()
 
     @property
     def covariance_matrix_complex(self):
+        if self._side is not None:
+            self._side.synchronize()
         return self._cov_c.cpu().numpy()
 
     @property

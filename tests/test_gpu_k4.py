@@ -151,3 +151,67 @@ def test_quartic_energy_satisfies_the_virial_identity_per_mode():
     assert np.max(np.abs(z)) < 5.0, (int(np.argmax(np.abs(z))), float(np.max(np.abs(z))), v.mean(0)[:4])
     assert abs(v.mean() - 2 * T) < 5 * v.mean(1).std(ddof=1) / np.sqrt(n)
     assert np.all(np.abs(eng.real_params_per_chain.cpu().numpy()) < 1.0)
+
+
+def test_pooled_moments_and_factor_match_float64_linear_algebra():
+    """me_k4_moments (symmetric rank-k update of [Re c; Im c]) and me_k4_refactor (left-looking complex Cholesky)
+    against torch float64: the increment of one measure, then the covariance and the BF16 factor built from it."""
+    import metropolisengine_b200 as me
+    n = 128 * 37 + 128                              # uneven split over the moment CTAs
+    eng = me.SharedCovarianceEngine(temp=.1, n_chains=n, seed=4, record=False, sampling_width=0.05)
+    eng.run(52, 4)                                  # crosses n > 50: the factor has been rebuilt from pooled moments
+    eng.synchronize_refresh()                       # adopt the refresh of the last measure (it runs on a side stream)
+    torch.cuda.synchronize()
+    lay = eng._lay
+    x = eng.state[lay.X:lay.X + lay.D].clone()      # [129, chains] as seen by the LAST measure
+    a = x[0] - eng._shift[0]
+    c = torch.complex(x[1:65] - eng._shift[1:65, None], x[65:129] - eng._shift[65:129, None])    # [64, chains]
+    inc = eng._inc_full.clone()                     # increment of the last measure
+    assert inc[0].real.item() == n
+    assert torch.allclose(inc[2].real, a.sum(), rtol=1e-12, atol=1e-12)
+    assert torch.allclose(inc[3].real, (a * a).sum(), rtol=1e-12)
+    assert torch.allclose(inc[1].real, eng.state[lay.SIG].sum(), rtol=1e-12)
+    assert torch.allclose(inc[4:68], c.sum(dim=1), rtol=1e-11, atol=1e-11)
+    s2 = (c @ c.conj().t()).reshape(-1)
+    assert torch.allclose(inc[68:], s2, rtol=1e-11, atol=1e-11 * s2.abs().max().item())
+    # covariance from the accumulated moments and its factor
+    mom = eng._mom
+    N = mom[0].real
+    s1 = mom[4:68]
+    small = (inc[1].real / inc[0].real) ** 2 / eng.measure_step_counter
+    cov = (mom[68:].reshape(64, 64) - torch.outer(s1, s1.conj()) / N) / (N - 1) + small * torch.eye(64, dtype=torch.complex128, device=x.device)
+    assert torch.allclose(eng._cov_c, cov, rtol=1e-10, atol=1e-14)
+    G = torch.linalg.cholesky(cov)
+    gr, gi = G.real / 2 ** .5, G.imag / 2 ** .5
+    B = torch.zeros((128, 128), dtype=torch.float64, device=x.device)
+    B[0::2, 0::2] = gr; B[0::2, 1::2] = gi; B[1::2, 0::2] = -gi; B[1::2, 1::2] = gr
+    want = B.view(128, 16, 8).permute(1, 0, 2).to(torch.bfloat16).float()
+    got = eng._factor.float()
+    assert (got - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()      # equal up to one BF16 rounding
+    assert int(eng._psd_status.item()) == 0
+
+
+def test_asynchronous_factor_refresh_is_deterministic_and_lags_by_one_measure():
+    """The factor refresh runs on a side stream beside the next block of steps; the block after measure b steps with
+    the factor of measure b-1.  The schedule is fixed by the host, so two runs are bit-identical, and the sequential
+    schedule (async_refresh=False) differs from it only through that one-measure lag."""
+    import metropolisengine_b200 as me
+    kw = dict(energy_consts=(10.0, -1.0, 0.05, 1.0), temp=.1, seed=33, record=False, n_chains=1024,
+              sampling_width=0.004)      # small enough that the identity-covariance proposals are accepted from the start
+    a = me.SharedCovarianceEngine(**kw)
+    b = me.SharedCovarianceEngine(**kw)
+    a.run(56, 3)
+    b.run(56, 3)
+    torch.cuda.synchronize()
+    assert float(a.acceptance_rate) > 0.1
+    assert torch.equal(a.state, b.state)
+    assert np.array_equal(a.covariance_matrix_complex, b.covariance_matrix_complex)
+    s = me.SharedCovarianceEngine(async_refresh=False, **kw)
+    c = me.SharedCovarianceEngine(**kw)
+    s.run(50, 3)                  # the first refresh happens at the 50th measure (n = 51 > 50, ME:389,396): up to and
+    c.run(50, 3)                  # including it both schedules have stepped with the initial factor
+    torch.cuda.synchronize()
+    assert torch.equal(s.state, c.state)
+    s.run(1, 3); c.run(1, 3)      # the next block uses the new factor only in the sequential schedule
+    torch.cuda.synchronize()
+    assert not torch.equal(s.state[:129], c.state[:129])
