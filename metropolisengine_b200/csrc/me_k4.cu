@@ -32,6 +32,10 @@
 
 namespace {
 
+#ifndef K4_INT_CVT
+#define K4_INT_CVT 0       /* 1: FP32->FP64 with integer instructions instead of F2F (XU pipe); measured: no gain (115.0 vs
+                              113.0 us per 10 steps at 32,768 chains) — the kernel is bound by its barrier/MMA-wait structure */
+#endif
 constexpr int K4_NC = 64;
 constexpr int K4_N = 2 * K4_NC;          /* embedded real dimension = MMA N = MMA K */
 constexpr int K4_TILE = 128;             /* chains per tile = MMA M = TMEM lanes */
@@ -151,18 +155,23 @@ __device__ __forceinline__ U4 philox(unsigned c0, unsigned c1, unsigned c2, unsi
     U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
     return o;
 }
-/* two normals from 64 random bits: radius from the top 23 bits of `a`, angle from 25 bits of `b` (2 quadrant bits +
- * 23-bit fraction).  Built for the SM's scarcest pipe: no integer->float conversions (the uniforms are assembled
- * as float mantissas), sin/cos as FP32 polynomials after an integer quadrant reduction, so the only XU operations
- * left are one MUFU.LG2 and one MUFU.SQRT per PAIR (was five: 2 I2F, LG2, RSQ, SIN, COS).  The two signs and the
- * sin/cos swap come from independent bits, so the pair's law is exactly symmetric whatever the accuracy of the
- * approximations (relative error ~1e-6, far below the BF16 rounding of the operand). */
-__device__ __forceinline__ void normal_pair_f32(unsigned a, unsigned b, float &z0, float &z1) {
-    const float u = 2.0f - __uint_as_float(0x3f800000u | (a >> 9));                 /* (0, 1], multiples of 2^-23 */
-    const float w = -1.3862943611f * __log2f(u);                                    /* -2 ln u >= 0 */
+/* two normals from 32 random bits: radius uniform from the high 16 bits, angle from the low 16 (2 quadrant bits + 14-bit
+ * fraction).  The operand these normals feed is BF16 (8 significant bits), so a 2^-16 grid for the radius uniform and a
+ * 1e-4 rad grid for the angle are already below its rounding; the radius is capped at sqrt(2 ln 2^16) = 4.7.  Half the
+ * Philox calls of a 64-bit recipe — the generator's IMAD.WIDE rounds are the largest single cost of the step kernel.
+ * Built for the SM's scarcest pipe: no integer->float conversions (the uniforms are assembled as float mantissas),
+ * sin/cos as FP32 polynomials after an integer quadrant reduction, so the only XU operations left are one MUFU.LG2 and
+ * one MUFU.SQRT per PAIR (was five: 2 I2F, LG2, RSQ, SIN, COS).  The two signs and the sin/cos swap come from
+ * independent bits, so the pair's law is exactly symmetric whatever the accuracy of the approximations: the proposal
+ * stays symmetric and detailed balance exact. */
+__device__ __forceinline__ void normal_pair_f32(unsigned bits, float &z0, float &z1) {
+    const float u = 2.0f - __uint_as_float(0x3f800000u | ((bits >> 16) << 7));     /* (0, 1], multiples of 2^-16 */
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));                         /* u >= 2^-16: no denormal path */
+    const float w = -1.3862943611f * lg;                                            /* -2 ln u >= 0 */
     float rad;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(w));
-    const unsigned zz = b + 0x20000000u;                                            /* quadrant = zz >> 30 (rounded) */
+    const unsigned zz = (bits << 16) + 0x20000000u;                                 /* quadrant = zz >> 30 (rounded) */
     const float v = __uint_as_float(0x3f800000u | ((zz >> 7) & 0x007fffffu)) - 1.5f;   /* [-1/2, 1/2): angle (pi/2) v */
     const float q = v * v;
     float ps = fmaf(q, -0.0046817541f, 0.0796926263f);                              /* sin((pi/2) v) / v */
@@ -187,6 +196,18 @@ __device__ __forceinline__ double u53(unsigned hi, unsigned lo) {
 __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const unsigned *>(&v);
+}
+
+/* FP32 bit pattern -> double, exact for normal values, with integer instructions only (F2F.F64.F32 runs on the XU pipe
+ * at a quarter of a warp per cycle, and the epilogues convert 64 increments per thread and step).  +-0 and denormals map
+ * to +-2^-126-sized values, which are added to O(1) coordinates. */
+__device__ __forceinline__ double f32_bits_to_f64(uint32_t f) {
+#if K4_INT_CVT
+    const uint32_t hi = ((((f << 1) >> 4) + 0x38000000u) | (f & 0x80000000u));
+    return __hiloint2double((int)hi, (int)(f << 29));
+#else
+    return (double)__uint_as_float(f);
+#endif
 }
 
 /* cylinder-style energy from its sufficient statistics (same functional form as me::EnergyCylinder) */
@@ -270,10 +291,12 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
                     kc*2048 + m*16: consecutive lanes write consecutive 16 B) */
             float dz[32];
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const U4 r = philox(c0, c1, step, (unsigned)(8 * g + i), p.rk);
-                normal_pair_f32(r.x, r.y, dz[4 * i], dz[4 * i + 1]);
-                normal_pair_f32(r.z, r.w, dz[4 * i + 2], dz[4 * i + 3]);
+            for (int i = 0; i < 4; i++) {
+                const U4 r = philox(c0, c1, step, (unsigned)(4 * g + i), p.rk);
+                normal_pair_f32(r.x, dz[8 * i], dz[8 * i + 1]);
+                normal_pair_f32(r.y, dz[8 * i + 2], dz[8 * i + 3]);
+                normal_pair_f32(r.z, dz[8 * i + 4], dz[8 * i + 5]);
+                normal_pair_f32(r.w, dz[8 * i + 6], dz[8 * i + 7]);
             }
 #pragma unroll
             for (int c = 0; c < 4; c++) {
@@ -292,7 +315,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
             if (g == 0) {            /* draws of the real parameter and of the accept test */
                 const U4 r = philox(c0, c1, step, 32u, p.rk);
                 float za, zb;
-                normal_pair_f32(r.x, r.y, za, zb);
+                normal_pair_f32(r.x, za, zb);
                 S.za_s[m] = (double)za;
                 S.u_s[m] = u53(r.z, r.w);
             }
@@ -330,8 +353,8 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
 #pragma unroll
             for (int jj = 0; jj < 16; jj++) {
                 const int j = 16 * g + jj;
-                const double re = fma(sig, (double)__uint_as_float(raw[2 * jj]), S.xs[2 * j][m]);
-                const double im = fma(sig, (double)__uint_as_float(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
+                const double re = fma(sig, f32_bits_to_f64(raw[2 * jj]), S.xs[2 * j][m]);
+                const double im = fma(sig, f32_bits_to_f64(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
                 const double m2 = fma(re, re, im * im);
                 tot += m2;
                 t1 = fma((double)jj, m2, t1);
@@ -368,8 +391,8 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
 #pragma unroll
                 for (int jj = 0; jj < 16; jj++) {
                     const int j = 16 * g + jj;
-                    S.xs[2 * j][m] = fma(sig, (double)__uint_as_float(raw[2 * jj]), S.xs[2 * j][m]);
-                    S.xs[2 * j + 1][m] = fma(sig, (double)__uint_as_float(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
+                    S.xs[2 * j][m] = fma(sig, f32_bits_to_f64(raw[2 * jj]), S.xs[2 * j][m]);
+                    S.xs[2 * j + 1][m] = fma(sig, f32_bits_to_f64(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
                 }
             }
         }
