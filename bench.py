@@ -31,31 +31,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# algorithmic work per chain-step / bytes per chain-measure (x[D], E, sigma stored in FP64)
+# algorithmic work per chain-step / bytes per chain-measure (x[D], E, sigma stored in FP64).
+# fp64_inst / wide_inst: FP64 and IMAD.WIDE instructions per chain-step in the SASS of the step loop
+# (tests/scripts/sass_loop.py on the shipped library) — the inputs of the pipe-level roofline below.
 WORKLOADS = {
     "c1": dict(name="README x^2: 1 real param, T=0.01, measure every step", energy=("x2",), n_r=1, n_c=0, temp=0.01,
-               chains=65536, measures=10000, spm=1, flop=10, sf=3),
+               chains=65536, measures=10000, spm=1, flop=10, sf=3, fp64_inst=58.0, wide_inst=18.0),
     "c2": dict(name="demo/toymodel_xypotentialwell: 2 real params, E=x^2+y^2, T=0.1, 65,536 chains x 1e5 steps, "
                     "measure every 10", energy=("xy_well", 1.0), n_r=2, n_c=0, temp=0.1, chains=65536,
-               measures=10000, spm=10, flop=20, sf=5),
+               measures=10000, spm=10, flop=20, sf=5, fp64_inst=64.5, wide_inst=18.0),
     "c3": dict(name="mixed 3 real + 4 complex (bounded demo-style well), T=0.1, 262,144 chains, measure every 10",
                energy=("mixed_well", 1.0, -1.0, 0.5, 1.0), n_r=3, n_c=4, temp=0.1, chains=262144, measures=100, spm=10,
-               flop=170, sf=23),
+               flop=170, sf=23, fp64_inst=347.0, wide_inst=88.0),
 }
 
 
 def _ncu_traffic_per_chain_measure():
     """DRAM bytes per chain-measure of the step kernel from the committed ncu --set full capture
-    (profiles/r01_ncu_c2_k_run.csv: a launch of 1000 measures x 65,536 chains)."""
+    (profiles/r01_ncu_c2_k_run_v3.csv: a launch of 300 measures x 65,536 chains)."""
     try:
         rd = wr = None
-        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_c2_k_run.csv")):
+        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_c2_k_run_v3.csv")):
             f = line.strip().split(",")
             if f[0] == "dram__bytes_read.sum":
                 rd = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
             if f[0] == "dram__bytes_write.sum":
                 wr = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
-        return (rd + wr) / (1000.0 * 65536.0)
+        return (rd + wr) / (300.0 * 65536.0)
     except Exception:
         return None
 
@@ -409,6 +411,30 @@ def run_ours(args):
     per_launch_steps = chains * M * spm
     achieved_tf = per_launch_steps * wl["flop"] / (ker_ms * 1e-3) / 1e12
     ts_gbs = ts_bytes / (ker_ms * 1e-3) / 1e9
+    # Pipe-level roofline of the step kernel.  A warp-wide FP64 instruction holds the FP64 pipe of its SM
+    # sub-partition for 2 cycles and an IMAD.WIDE (Philox round) the FMA-heavy pipe for ~3.5; the two contend
+    # (tests/scripts/issue_mix.cu, profiles/r01_microbench_issue_mix.txt), so a warp-step costs at least
+    # 2 * fp64_inst + 3.5 * wide_inst cycles of its sub-partition, and the kernel cannot finish before the most loaded
+    # sub-partition has done that for all of its warps.
+    clk = clocks.summary()
+    sm_hz = 1e6 * (clk.get("sm_mhz") or 1965)
+    n_smsp = 4 * n_sm
+    warps = -(-chains // 32)
+    # one wave (every warp resident from the start): the busiest sub-partition holds ceil(warps / n_smsp) of them;
+    # several waves: the CTA scheduler balances the waves, use the average
+    warps_busiest = -(-warps // n_smsp) if warps <= 4 * n_smsp else warps / n_smsp
+    cyc_step = 2.0 * wl["fp64_inst"] + 3.5 * wl["wide_inst"]
+    pipe_bound_ms = 1e3 * warps_busiest * M * spm * cyc_step / sm_hz
+    pipe = {"fp64_inst_per_chain_step": wl["fp64_inst"], "imad_wide_per_chain_step": wl["wide_inst"],
+            "cycles_per_warp_step_lower_bound": cyc_step, "warps_on_busiest_subpartition": warps_busiest,
+            "bound_ms": pipe_bound_ms, "frac": pipe_bound_ms / ker_ms,
+            "balanced_frac": 1e3 * (warps / n_smsp) * M * spm * cyc_step / sm_hz / ker_ms,
+            "how": "FP64-pipe + FMA-heavy-pipe cycles the SASS of the step loop needs (2 per FP64 instruction, 3.5 per "
+                   "IMAD.WIDE; the pipes contend) on the most loaded SM sub-partition / measured kernel time; "
+                   "balanced_frac uses the average warps per sub-partition instead",
+            "ncu": ("profiles/r01_ncu_c2_k_run_v3.csv: FP64 pipe 38 % + FMA-heavy 27 % of elapsed cycles (46 % / 32 % "
+                    "of active), issue slots 59 % busy, sub-partitions active 83 % of the kernel"
+                    if args.workload == "c2" else None)}
     line = {
         "metric": "ensemble chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -427,9 +453,9 @@ def run_ours(args):
                      "frac": achieved_tf / fp64_peak,
                      "traffic": (tpm * chains * M) if tpm else None,
                      "traffic_note": "DRAM read+write bytes per launch: per chain-measure figure of the committed ncu "
-                                     "--set full capture (profiles/r01_ncu_c2_k_run.csv) x this launch's "
+                                     "--set full capture (profiles/r01_ncu_c2_k_run_v3.csv) x this launch's "
                                      "chain-measures; algorithmic %d B per chain-measure" % (8 * ts_cols),
-                     "fp64_pipe_busy_ncu": 0.40 if args.workload == "c2" else None,
+                     "pipe": pipe,
                      "kernel": "me::k_run", "kernel_ms": ker_ms,
                      "algorithmic": "%d flop + %d special functions per chain-step (SURVEY.md §8d); special functions "
                                     "and Philox integer work are NOT counted in achieved" % (wl["flop"], wl["sf"]),
