@@ -101,7 +101,9 @@ class SharedCovarianceEngine:
         self._shift = torch.as_tensor(np.ascontiguousarray(x0), dtype=f64, device=dev)
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         self._scratch = torch.zeros((n_sm + 1) * lay.MOM_SCRATCH_PER_SM, dtype=f64, device=dev)
-        self._inc_full = torch.zeros(lay.MOM_WORDS, dtype=torch.complex128, device=dev)
+        self._incs = [torch.zeros(lay.MOM_WORDS, dtype=torch.complex128, device=dev) for _ in range(2)]
+        self._inc_full = self._incs[0]          # increment of the latest measure
+        self._measure_count = 0
         self._mom = torch.zeros(4 + N_C + N_C * N_C, dtype=torch.complex128, device=dev)   # count, -, sum a, sum a^2, sum c, sum c c^H
         self._snaps = [torch.zeros(lay.MOM_WORDS + 2, dtype=torch.complex128, device=dev) for _ in range(2)]
         self._snap_events = [None, None]
@@ -186,6 +188,8 @@ class SharedCovarianceEngine:
         if self._in_flight is not None:
             self._ready, self._in_flight = self._in_flight, None
         self._adopt_refresh()
+        if self._side is not None:
+            self._side.synchronize()
 
     def step(self, k=1, _dbg=None):
         dz = dd = None
@@ -218,48 +222,57 @@ class SharedCovarianceEngine:
         else:
             self._launch(self._lib.me_k4_measure(self._h, None, 0, self._stream()))
         n = self.measure_step_counter
-        inc = self._inc_full
-        parity = self._refresh_count % 2
-        snap = self._snaps[parity]
-        if self._snap_events[parity] is not None:      # the refresh that read this snapshot two measures ago
-            torch.cuda.current_stream(self.device).wait_event(self._snap_events[parity])
+        parity = self._measure_count % 2
+        self._measure_count += 1
+        inc, snap = self._incs[parity], self._snaps[parity]
+        self._inc_full = inc
+        main = torch.cuda.current_stream(self.device)
+        if self._snap_events[parity] is not None:      # side-stream work of two measures ago that used these buffers
+            main.wait_event(self._snap_events[parity])
             self._snap_events[parity] = None
         fused = not self._distributed            # single GPU: the moments kernel advances mom and writes the snapshot
         self._launch(self._lib.me_k4_moments(self._h, _ptr(self._shift), _ptr(self._scratch), self._scratch.numel(),
                                              _ptr(inc), _ptr(self._mom) if fused else None,
                                              _ptr(snap) if fused else None, self._stream()))
         self.launch_count += 2
-        if not fused:
-            parallel.allreduce_sum_(torch.view_as_real(inc))
-            self._mom[0] += inc[0]
-            self._mom[2:] += inc[2:]
-            snap[:-2].copy_(self._mom)
-            snap[-2:].copy_(inc[:2])
-        if n > 50:                                                                            # ME:389,396
-            mw = self._lay.MOM_WORDS
-            if not self._async:
+        refresh = n > 50                                                                      # ME:389,396
+        if fused and not refresh:
+            return
+        mw = self._lay.MOM_WORDS
+
+        def tail(stream, idx):
+            """all-reduce + accumulation (multi-GPU) and the factor refresh, all stream-ordered on `stream`"""
+            if not fused:
+                parallel.allreduce_sum_(torch.view_as_real(inc))        # the path's only collective (NCCL)
+                self._mom[0] += inc[0]
+                self._mom[2:] += inc[2:]
+                snap[:-2].copy_(self._mom)
+                snap[-2:].copy_(inc[:2])
+            if refresh:
                 self._launch(self._lib.me_k4_refactor(self._h, _ptr(snap), _ptr(snap[mw:]), n, _ptr(self._cov_c),
-                                                      _ptr(self._cov_a), _ptr(self._factor), _ptr(self._s_a),
-                                                      _ptr(self._psd_status), self._stream()))
-            else:
-                # refresh into a buffer that is neither read by the step kernel nor waiting to be adopted, on the side
-                # stream, behind this measure
-                if self._in_flight is not None:   # two measures without a step in between: the older refresh (finished
-                    self._ready, self._in_flight = self._in_flight, None     # before this one starts) becomes adoptable
-                busy = {self._cur} | ({self._ready[1]} if self._ready is not None else set())
-                idx = min(i for i in range(3) if i not in busy)
-                main = torch.cuda.current_stream(self.device)
-                self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):
-                    self._launch(self._lib.me_k4_refactor(self._h, _ptr(snap), _ptr(snap[mw:]), n, _ptr(self._cov_c),
-                                                          _ptr(self._cov_a), _ptr(self._factors[idx]),
-                                                          _ptr(self._s_as[idx]), _ptr(self._psd_status),
-                                                          ctypes.c_void_p(self._side.cuda_stream)))
-                    ev = torch.cuda.Event()
-                    ev.record(self._side)
-                self._snap_events[parity] = ev
-                self._in_flight = (ev, idx)
-            self._refresh_count += 1
+                                                      _ptr(self._cov_a), _ptr(self._factors[idx]),
+                                                      _ptr(self._s_as[idx]), _ptr(self._psd_status),
+                                                      ctypes.c_void_p(stream.cuda_stream)))
+
+        if not self._async:
+            tail(main, self._cur)
+            return
+        # side stream, behind this measure: the collective, the accumulation and the one-CTA refresh run beside the next
+        # block of steps; the refresh writes a buffer that is neither read by the step kernel nor waiting to be adopted
+        idx = None
+        if refresh:
+            if self._in_flight is not None:       # two measures without a step in between: the older refresh (finished
+                self._ready, self._in_flight = self._in_flight, None     # before this one starts) becomes adoptable
+            busy = {self._cur} | ({self._ready[1]} if self._ready is not None else set())
+            idx = min(i for i in range(3) if i not in busy)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            tail(self._side, idx)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._snap_events[parity] = ev
+        if refresh:
+            self._in_flight = (ev, idx)
 
     def run(self, n_measures, steps_per_measure):
         for _ in range(int(n_measures)):
