@@ -201,9 +201,12 @@ __device__ __forceinline__ void store_stats(const Stats<L> &s, double *st, long 
  * Replaces the SVD hidden inside np.random.multivariate_normal (metropolis_engine.py:268,300): the factor only
  * changes when measure() changes the covariance, so it is recomputed there, not per step.
  * Real block C_r = L L^T; complex block C_c = G G^H.  Returns nonzero if a pivot was not positive. */
-template <class L>
+template <class L, bool FAST = false>
 __device__ __forceinline__ int refactor(const Stats<L> &s, Chain<L> &c) {
     int bad = 0;
+    /* FAST (throughput build): one reciprocal square root per pivot — L_ii = a r, L_ij = a_ij r_j with r = a^-1/2 —
+       instead of a libdevice sqrt plus a division per off-diagonal entry */
+    double rinv[nz(L::NR)];
 #pragma unroll
     for (int i = 0; i < L::NR; i++) {
 #pragma unroll
@@ -212,8 +215,18 @@ __device__ __forceinline__ int refactor(const Stats<L> &s, Chain<L> &c) {
 #pragma unroll
             for (int k = 0; k < j; k++) a -= c.facr[tri(i, k)] * c.facr[tri(j, k)];
             if (i == j) {
-                if (!(a > 0.0)) { bad = 1; a = 0.0; }
-                c.facr[tri(i, i)] = sqrt(a);
+                if (FAST) {
+                    const bool ok = a > 0.0;
+                    if (!ok) bad = 1;
+                    const double r = rsqrt_pos(ok ? a : 1.0);
+                    rinv[i] = ok ? r : 0.0;
+                    c.facr[tri(i, i)] = ok ? a * r : 0.0;
+                } else {
+                    if (!(a > 0.0)) { bad = 1; a = 0.0; }
+                    c.facr[tri(i, i)] = sqrt(a);
+                }
+            } else if (FAST) {
+                c.facr[tri(i, j)] = a * rinv[j];
             } else {
                 const double piv = c.facr[tri(j, j)];
                 c.facr[tri(i, j)] = piv > 0.0 ? a / piv : 0.0;
@@ -221,6 +234,7 @@ __device__ __forceinline__ int refactor(const Stats<L> &s, Chain<L> &c) {
         }
     }
     constexpr int dg = L::NC * (L::NC - 1);
+    double cinv[nz(L::NC)];
 #pragma unroll
     for (int i = 0; i < L::NC; i++) {
 #pragma unroll
@@ -232,8 +246,16 @@ __device__ __forceinline__ int refactor(const Stats<L> &s, Chain<L> &c) {
                     const double re = c.facc[herm_lo(i, k)], im = c.facc[herm_lo(i, k) + 1];
                     a -= re * re + im * im;
                 }
-                if (!(a > 0.0)) { bad = 1; a = 0.0; }
-                c.facc[dg + i] = sqrt(a);
+                if (FAST) {
+                    const bool ok = a > 0.0;
+                    if (!ok) bad = 1;
+                    const double r = rsqrt_pos(ok ? a : 1.0);
+                    cinv[i] = ok ? r : 0.0;
+                    c.facc[dg + i] = ok ? a * r : 0.0;
+                } else {
+                    if (!(a > 0.0)) { bad = 1; a = 0.0; }
+                    c.facc[dg + i] = sqrt(a);
+                }
             } else {
                 double are = s.covc[herm_lo(i, j)], aim = s.covc[herm_lo(i, j) + 1];
 #pragma unroll
@@ -243,9 +265,14 @@ __device__ __forceinline__ int refactor(const Stats<L> &s, Chain<L> &c) {
                     are -= pr * qr + pi * qi;
                     aim -= pi * qr - pr * qi;
                 }
-                const double piv = c.facc[dg + j];
-                c.facc[herm_lo(i, j)] = piv > 0.0 ? are / piv : 0.0;
-                c.facc[herm_lo(i, j) + 1] = piv > 0.0 ? aim / piv : 0.0;
+                if (FAST) {
+                    c.facc[herm_lo(i, j)] = are * cinv[j];
+                    c.facc[herm_lo(i, j) + 1] = aim * cinv[j];
+                } else {
+                    const double piv = c.facc[dg + j];
+                    c.facc[herm_lo(i, j)] = piv > 0.0 ? are / piv : 0.0;
+                    c.facc[herm_lo(i, j) + 1] = piv > 0.0 ? aim / piv : 0.0;
+                }
             }
         }
     }
@@ -372,8 +399,21 @@ struct Gains {            /* per measure-block constants of the Robbins-Monro up
     bool hot;             /* temp != 0 */
 };
 
-__device__ __forceinline__ Gains make_gains(long long n_meas, const MeParams &p) {
+template <bool FAST = false>
+__device__ __forceinline__ Gains make_gains(long long n_meas, const MeParams &p, double inv_n = 0.0) {
     Gains g;
+    if (FAST) {
+        /* 1/f = min(m / n, 1/200): no FP64 division (the measure block runs once per few steps; three divisions with
+           their slow-path calls were a tenth of the C2 step cost); inv_n = 1/n from the measure clock */
+        const double invf = n_meas > 200LL * p.m ? (double)p.m * inv_n : 0.005;
+        g.f = 0.0;
+        g.up = (p.ratio * (1 - p.target)) * invf;
+        g.ndown = -((p.ratio * p.target) * invf);
+        asm volatile("" : "+d"(g.up), "+d"(g.ndown));
+        g.hot = p.temp != 0;
+        g.k64 = ME_C_64_LN2;
+        return g;
+    }
     double f = (double)n_meas / (double)p.m;
     if (!(f > 200.0)) f = 200.0;
     g.f = f;
@@ -416,12 +456,29 @@ __device__ __forceinline__ double adapt_sigma(double sig, bool accept, const Gai
  * the reference.  numpy divides a complex array by a real as multiplication by the reciprocal,
  * so the complex block uses inv_n / inv_n1 where the real block divides (strict build); the throughput build
  * uses the reciprocals everywhere. */
+/* Counter of the measure loop as the throughput build wants it: n as a double and its reciprocal.  The reciprocals of
+ * consecutive counters are all the measure block needs (1/n, 1/(n-1), and m/n for the Robbins-Monro gain), so ONE
+ * reciprocal is computed per measure and the previous one is kept; the counter itself is advanced in floating point
+ * (exact below 2^53) instead of three 64-bit integer->double conversions. */
+struct MeasureClock {
+    double dn, inv_dn;
+    __device__ __forceinline__ void start(long long n) { dn = (double)n; inv_dn = __drcp_rn(dn); }
+};
+
 template <class L, bool STRICT>
-__device__ __forceinline__ void measure_update(Chain<L> &c, Stats<L> &s, long long n) {
+__device__ __forceinline__ void measure_update(Chain<L> &c, Stats<L> &s, long long n, MeasureClock *clk = nullptr) {
     constexpr int NR = L::NR, NC = L::NC;
-    const double dn = (double)n, dn1 = (double)(n - 1), dn2 = (double)(n - 2);
-    /* throughput build: two reciprocals per measure instead of a division per element */
-    const double inv_n = STRICT ? 1.0 / dn : __drcp_rn(dn), inv_n1 = STRICT ? 1.0 / dn1 : __drcp_rn(dn1);
+    double dn, dn1, dn2, inv_n, inv_n1;
+    if (!STRICT && clk != nullptr) {          /* clk holds the counter before this measure (n - 1) */
+        dn1 = clk->dn; inv_n1 = clk->inv_dn;
+        dn = dn1 + 1.0; dn2 = dn1 - 1.0;
+        inv_n = __drcp_rn(dn);
+        clk->dn = dn; clk->inv_dn = inv_n;
+    } else {
+        dn = (double)n; dn1 = (double)(n - 1); dn2 = (double)(n - 2);
+        /* throughput build: two reciprocals per measure instead of a division per element */
+        inv_n = STRICT ? 1.0 / dn : __drcp_rn(dn); inv_n1 = STRICT ? 1.0 / dn1 : __drcp_rn(dn1);
+    }
     const double shrink = STRICT ? dn1 / dn : dn1 * inv_n;
     const bool adapt_cov = n > 50;
     const double decay = STRICT ? dn2 / dn1 : dn2 * inv_n1, grow = STRICT ? dn / dn1 : dn * inv_n1;
@@ -492,7 +549,7 @@ __device__ __forceinline__ void measure_update(Chain<L> &c, Stats<L> &s, long lo
         const double q = c.x[i] * c.x[i];
         s.obsm[NR + NC + i] = s.obsm[NR + NC + i] * shrink + (STRICT ? q / dn : q * inv_n);
     }
-    if (adapt_cov && refactor<L>(s, c)) c.status |= ME_STATUS_NOT_PSD;
+    if (adapt_cov && refactor<L, !STRICT>(s, c)) c.status |= ME_STATUS_NOT_PSD;
 }
 
 /* ------------------------------------------------------------------------------------------ pooled moments
@@ -674,9 +731,14 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
         accept = finish_step<Cfg>(c, prop, use.u, g, p, tables, group);
     };
     const unsigned spm = (unsigned)p.spm;
+    MeasureClock clk;
+    clk.start(n);
+    /* running row pointer of the time series (one 64-bit add per measure instead of the full index arithmetic) */
+    double *row = p.record ? p.ts + p.ts_row0 * (long long)L::TSCOLS * ld + ch : nullptr;
+    const long long row_stride = (long long)L::TSCOLS * ld;
 
     for (long long b = 0; b < p.n_blocks; b++) {
-        Gains g = make_gains(n, p);
+        Gains g = make_gains<!STRICT>(n, p, clk.inv_dn);
         g.k64 = pins.k64;
         /* steps in pairs so that the two draw buffers swap roles by name instead of by register moves */
         Draws<L> nxt;
@@ -692,15 +754,14 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
         if (p.do_measure) {
             n += 1;
             if (STATS_REG) {
-                measure_update<L, STRICT>(c, sreg, n);
+                measure_update<L, STRICT>(c, sreg, n, &clk);
             } else {
                 Stats<L> s;
                 load_stats<L>(s, st, ld, ch);
-                measure_update<L, STRICT>(c, s, n);
+                measure_update<L, STRICT>(c, s, n, &clk);
                 if (active) store_stats<L>(s, st, ld, ch);
             }
             if (p.record && active) {
-                double *row = p.ts + (p.ts_row0 + b) * (long long)L::TSCOLS * ld + ch;
 #pragma unroll
                 for (int i = 0; i < D; i++) __stcs(row + (long long)i * ld, c.x[i]);
                 __stcs(row + (long long)D * ld, c.e);
@@ -711,6 +772,7 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
                     __stcs(row + (long long)(D + 1) * ld, c.sig[L::SIGIDX]);
                 }
             }
+            if (p.record) row += row_stride;
             if (pooling) {
                 if (POOL_REG) {
 for_each_pool_word<L>(c, shift, [&](int w, double v) { pacc[w] += v; });

@@ -120,6 +120,17 @@ __device__ __forceinline__ double sqrt_pos(double w) {
     return fma(fma(-s, s, w), y1h, s);
 }
 
+/* 1 / sqrt(d) for a normal, strictly positive d: MUFU.RSQ64H seed + two Newton steps (relative error ~1e-16).  Used by
+ * the throughput build's Cholesky refactorisation, where it replaces a libdevice sqrt and a division per pivot. */
+__device__ __forceinline__ double rsqrt_pos(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y * y, 1.0);
+    y = fma(__hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y)), e, y);
+    e = fma(-d, y * y, 1.0);
+    return fma(__hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y)), e, y);
+}
+
 /* e^x for x <= 0 (clamped at -700: the result is only compared with a uniform on a 2^-44 grid).  x > 0 or NaN
  * gives an unspecified value without trapping (the caller ignores it: a downhill move is accepted anyway).
  * k = round(64 x / ln2), x = k ln2/64 + r, |r| <= ln2/128; e^x = 2^(k>>6) 2^((k&63)/64) e^r. */
