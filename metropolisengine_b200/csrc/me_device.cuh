@@ -87,7 +87,10 @@ __device__ __forceinline__ U4 philox4x32_10(unsigned c0, unsigned c1, unsigned c
  * counter (chain_lo, chain_hi, step, q), key = seed, output words (x, y, z, w):
  *   radius uniform  u1 = (K + 1/2) 2^-52 in (0,1),  K = y : x[31:12]  (52 bits);   angle t = z 2^-31 in [0,2);
  *   z_{2q} = sqrt(-2 ln u1) cos(pi t), z_{2q+1} = sqrt(-2 ln u1) sin(pi t);
- *   accept uniform  u = A 2^-44 in [0,1),  A = w_0 : x_0[11:0]  (44 bits of call 0 that the normals do not use).
+ *   accept uniform  u = (A + 1/2) 2^-44 in (0,1),  A = w_0 : x_0[11:0]  (44 bits of call 0 the normals do not use).
+ *   The throughput build never exponentiates: u <= exp(-dE/T)  <=>  dE <= -T ln u, and the threshold -T ln u does not
+ *   depend on the chain's state, so it is computed in the draw stage (one table-driven log, off the critical path)
+ *   and the Metropolis test of the state-dependent chain is a single comparison.
  * One Philox call per Gaussian pair, nothing else.  Both uniforms are assembled as the mantissa of a double in
  * [1,2) and shifted down with ONE exact subtraction (no integer->double conversion, no magic-number pairs). */
 struct Spare { unsigned w0, x0; };
@@ -116,8 +119,12 @@ struct Rng {
     }
     __device__ __forceinline__ static double accept_uniform(const Spare &sp) {
         const double d = __hiloint2double((int)(0x3ff00000u | (sp.w0 >> 12)),
-                                          (int)((sp.w0 << 20) | ((sp.x0 & 0xfffu) << 8)));
+                                          (int)((sp.w0 << 20) | ((sp.x0 & 0xfffu) << 8) | 0x80u));
         return d - 1.0;
+    }
+    /* -T ln u = (T/2) (-2 ln u) >= 0; T == 0 gives 0: only moves with dE <= 0 are accepted (ME:331-332) */
+    __device__ __forceinline__ static double accept_threshold(const Spare &sp, const MathTables &T, double half_temp) {
+        return half_temp * neg2log_unit(accept_uniform(sp), T);
     }
 };
 
@@ -301,7 +308,8 @@ __device__ __forceinline__ void gen_bits(const Rng &rng, unsigned step, Raw<L> &
 }
 
 template <class L, bool STRICT>
-__device__ __forceinline__ void shape_draws(const Raw<L> &raw, const MathTables &T, Draws<L> &d, const Pins &pins) {
+__device__ __forceinline__ void shape_draws(const Raw<L> &raw, const MathTables &T, Draws<L> &d, const Pins &pins,
+                                            double half_temp) {
     constexpr int NQ = (L::D + 1) / 2;
     Spare sp;
     sp.w0 = sp.x0 = 0;
@@ -310,15 +318,16 @@ __device__ __forceinline__ void shape_draws(const Raw<L> &raw, const MathTables 
         Rng::keep_spare(raw.r[q], q, sp);
         Rng::box_muller<STRICT>(raw.r[q], T, d.z[2 * q], d.z[2 * q + 1], pins.unit, pins.angle);
     }
-    d.u = Rng::accept_uniform(sp);
+    /* strict build: the uniform itself; throughput build: the energy threshold -T ln u */
+    d.u = STRICT ? Rng::accept_uniform(sp) : Rng::accept_threshold(sp, T, half_temp);
 }
 
 template <class L, bool STRICT>
 __device__ __forceinline__ void gen_draws(const Rng &rng, unsigned step, const MathTables &T, Draws<L> &d,
-                                          const Pins &pins) {
+                                          const Pins &pins, double half_temp) {
     Raw<L> raw;
     gen_bits<L>(rng, step, raw);
-    shape_draws<L, STRICT>(raw, T, d, pins);
+    shape_draws<L, STRICT>(raw, T, d, pins, half_temp);
 }
 
 template <class L>
@@ -436,10 +445,9 @@ __device__ __forceinline__ bool decide(double diff, double u, const MeParams &p,
         if (p.temp == 0) return false;
         return u <= exp(-1 * diff / p.temp);
     }
-    /* throughput build: branch-free (every lane evaluates the exponential; downhill lanes ignore its value, which
-       is unspecified for a positive argument) */
-    const double prob = exp_nonpos(-diff * p.inv_temp, T, k64);
-    return (diff <= 0) | (hot & (u <= prob));
+    /* throughput build: `u` is the precomputed threshold -T ln u >= 0 (see the stream definition): one comparison;
+       ties accept, NaN rejects, T == 0 accepts only dE <= 0 */
+    return diff <= u;
 }
 
 template <bool STRICT>
@@ -696,8 +704,9 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     Draws<L> cur;
     Raw<L> raw_a, raw_b;
     const Pins pins = load_pins(tables);
+    const double half_temp = 0.5 * p.temp;
     if (!inject && p.spm > 0 && AHEAD) {
-        gen_draws<L, STRICT>(rng, (unsigned)p.step0, tables, cur, pins);
+        gen_draws<L, STRICT>(rng, (unsigned)p.step0, tables, cur, pins, half_temp);
         if (DEEP) gen_bits<L>(rng, (unsigned)p.step0 + 1u, raw_a);
     }
 
@@ -715,11 +724,11 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
         } else {
             if (DEEP) {
                 gen_bits<L>(rng, step32 + 2u, raw_out);
-                shape_draws<L, STRICT>(raw_in, tables, make, pins);
+                shape_draws<L, STRICT>(raw_in, tables, make, pins, half_temp);
             } else if (AHEAD) {
-                gen_draws<L, STRICT>(rng, step32 + 1u, tables, make, pins);
+                gen_draws<L, STRICT>(rng, step32 + 1u, tables, make, pins, half_temp);
             } else {
-                gen_draws<L, STRICT>(rng, step32, tables, use, pins);
+                gen_draws<L, STRICT>(rng, step32, tables, use, pins, half_temp);
             }
             apply_proposal<L>(c, use.z, prop);
             if (MP && L::NC > 0 && group >= 3) {
@@ -893,7 +902,7 @@ __device__ __forceinline__ void propose_body(const MeParams &p) {
     } else {
         const Rng rng(p, p.chain_offset + (unsigned long long)ch);
         Draws<L> d;
-        gen_draws<L, Cfg::STRICT>(rng, (unsigned)p.step0, tables, d, load_pins(tables));
+        gen_draws<L, Cfg::STRICT>(rng, (unsigned)p.step0, tables, d, load_pins(tables), 0.5 * p.temp);
         apply_proposal<L>(c, d.z, prop);
         if (L::NC > 0 && p.group >= 3) {
             if (p.group == 3) propose_magnitudes<L>(c, d.z, prop);
@@ -939,7 +948,7 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
             const Rng rng(p, p.chain_offset + (unsigned long long)ch);
             Spare sp;
             Rng::keep_spare(rng.bits((unsigned)p.step0, 0u), 0, sp);
-            u = Rng::accept_uniform(sp);
+            u = STRICT ? Rng::accept_uniform(sp) : Rng::accept_threshold(sp, tables, 0.5 * p.temp);
         }
         accept = decide<STRICT>(diff, u, p, tables, g.hot);
         if (accept) {

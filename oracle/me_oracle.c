@@ -158,7 +158,7 @@ static void sincospi_d(double t, double *s, double *c) {
  *     radius uniform  u1 = (K + 1/2) 2^-52          in (0,1),  K = y : x[31:12]   (52 bits)
  *     angle           t  = z * 2^-31                in [0,2)      (sin/cos of pi*t)
  *     normals         z_{2q} = sqrt(-2 ln u1) cos(pi t),  z_{2q+1} = sqrt(-2 ln u1) sin(pi t)
- *   accept uniform    u = A 2^-44 in [0,1),  A = w_0 : x_0[11:0]  (44 bits of call 0 the normals do not use).
+ *   accept uniform    u = (A + 1/2) 2^-44 in (0,1),  A = w_0 : x_0[11:0]  (44 bits of call 0 the normals do not use).
  *   All bits used are distinct output bits of the generator. */
 void meo_normal_pair(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot, double *z0, double *z1) {
     uint32_t r[4];
@@ -178,7 +178,7 @@ double meo_uniform(uint64_t seed, uint64_t chain, uint32_t step, int n_calls) {
     (void)n_calls;
     meo_philox(seed, chain, step, 0, r);
     uint64_t bits = ((uint64_t)r[3] << 12) | (uint64_t)(r[0] & 0xfffu);
-    return (double)bits * (1.0 / 17592186044416.0);             /* 2^-44 */
+    return ((double)bits + 0.5) * (1.0 / 17592186044416.0);     /* 2^-44 */
 }
 
 /* ------------------------------------------------------------------ Cholesky factors of the proposal covariances */
