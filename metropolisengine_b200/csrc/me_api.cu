@@ -215,6 +215,12 @@ struct me_engine {
     int n_sm = 148;
     bool generic = false;              /* large shape: runtime-shape kernels, unfused step */
     int group = 0;                     /* 0 step_all, 1 real group, 2 complex group (mixed engines) */
+    /* time segmentation of fused launches (me_device.cuh, run_body) */
+    unsigned long long *seg_flags = nullptr;   /* work queue (tickets, pushes, ring) followed by its initial image; device
+                                                  memory owned by the handle */
+    unsigned long long seg_base = 0;           /* ring capacity */
+    int seg_workers = 0;                       /* CTAs of a segmented launch */
+    int run_slots = -1;                        /* CTAs of the fused kernel resident on the device at once (-1: unknown) */
     std::string err;
 };
 
@@ -231,16 +237,17 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-int launch(me_engine *e, const KernelRef &k, MeParams &p, void *stream) {
+int launch(me_engine *e, const KernelRef &k, MeParams &p, void *stream, int grid_mult = 1, int grid_override = 0) {
     if (!k.valid()) return fail(e, ME_ERR_STATE, "no energy functor registered (call me_set_energy_* first)");
     DeviceGuard g(e->cfg.device);
     void *args[] = {&p};
+    const unsigned grid = grid_override > 0 ? (unsigned)grid_override : (unsigned)e->grid * (unsigned)grid_mult;
     if (k.rt) {
-        cudaError_t ce = cudaLaunchKernel(k.rt, dim3(e->grid), dim3(e->block), args, 0, (cudaStream_t)stream);
+        cudaError_t ce = cudaLaunchKernel(k.rt, dim3(grid), dim3(e->block), args, 0, (cudaStream_t)stream);
         if (ce != cudaSuccess) return fail(e, ME_ERR_CUDA, std::string("cudaLaunchKernel: ") + cudaGetErrorString(ce));
     } else {
         Driver &d = driver();
-        CUresult r = d.launchKernel(k.drv, e->grid, 1, 1, e->block, 1, 1, 0, (CUstream)stream, args, nullptr);
+        CUresult r = d.launchKernel(k.drv, grid, 1, 1, e->block, 1, 1, 0, (CUstream)stream, args, nullptr);
         if (r != CUDA_SUCCESS) {
             const char *s = nullptr;
             d.getErrorString(r, &s);
@@ -278,6 +285,66 @@ void base_params(me_engine *e, MeParams &p) {
     p.energy_id = e->energy_id;
     p.scratch = e->buf.scratch;
     p.group = e->group;
+}
+
+/* Time segmentation of a fused launch (me_device.cuh, run_body): when the whole grid is resident in one wave the
+ * launch is cut into time segments per chain group and the CTAs become workers on a FIFO of ready segments, which
+ * balances the SM sub-partitions (65,536 chains are 3 or 4 warps per sub-partition, and a sub-partition saturates at
+ * 2-3).  Returns the segment count (1 = off), -1 on a CUDA error.  ME_SEGMENTS=<n> overrides (0 / 1 = off). */
+int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long long spm, bool injected, void *stream) {
+    if (injected || e->generic || e->cfg.strict || !k.rt) return 1;      /* runtime-compiled kernels: not segmented */
+    int want = -1;
+    if (const char *env = getenv("ME_SEGMENTS")) want = atoi(env);
+    if (want == 0 || want == 1) return 1;
+    DeviceGuard g(e->cfg.device);
+    if (e->run_slots < 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.rt, e->block, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+        e->run_slots = per_sm * e->n_sm;
+    }
+    if (e->run_slots <= 0) return 1;
+    /* workers: full waves only, i.e. the same number of CTAs on every SM sub-partition; segmentation pays when the
+       groups do not fill an integer number of such waves exactly and there are only a few waves */
+    const int n_smsp = 4 * e->n_sm;
+    int workers = (int)((e->grid < e->run_slots ? e->grid : e->run_slots) / n_smsp) * n_smsp;
+    if (workers <= 0 || e->grid % workers == 0 || e->grid > 4LL * e->run_slots) return 1;
+    const long long steps = n_blocks * (spm > 0 ? spm : 1);
+    const long long min_steps = 1500;                                    /* per segment: hand-over cost stays < 1 % */
+    long long segs = want > 1 ? want : steps / min_steps;
+    if (segs > 16) segs = 16;
+    if (segs > n_blocks) segs = n_blocks;
+    if (segs < 2) return 1;
+    if (!e->seg_flags) {
+        unsigned long long cap = 2;
+        while (cap < 2ull * (unsigned long long)e->grid) cap <<= 1;
+        const size_t words = (size_t)(cap + 2);
+        if (cudaMallocAsync((void **)&e->seg_flags, sizeof(unsigned long long) * 2 * words, (cudaStream_t)stream) != cudaSuccess) {
+            fail(e, ME_ERR_CUDA, "allocating the segment queue failed");
+            return -1;
+        }
+        /* initial image behind the live queue: no ticket handed out, segment 0 of every group pushed */
+        std::vector<unsigned long long> img(words, 0ull);
+        img[1] = (unsigned long long)e->grid;
+        for (long long gidx = 0; gidx < e->grid; gidx++) img[2 + gidx] = (unsigned long long)gidx + 1ull;
+        if (cudaMemcpyAsync(e->seg_flags + words, img.data(), sizeof(unsigned long long) * words, cudaMemcpyHostToDevice,
+                            (cudaStream_t)stream) != cudaSuccess ||
+            cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {     /* img is a stack-lifetime host buffer */
+            fail(e, ME_ERR_CUDA, "initialising the segment queue failed");
+            return -1;
+        }
+        e->seg_base = cap;
+    }
+    e->seg_workers = workers;
+    if (getenv("ME_DEBUG"))
+        fprintf(stderr, "[me_b200] segmented launch: %lld groups x %lld segments on %d workers (%d slots)\n",
+                (long long)e->grid, segs, workers, e->run_slots);
+    const size_t words = (size_t)(e->seg_base + 2);
+    if (cudaMemcpyAsync(e->seg_flags, e->seg_flags + words, sizeof(unsigned long long) * words, cudaMemcpyDeviceToDevice,
+                        (cudaStream_t)stream) != cudaSuccess) {
+        fail(e, ME_ERR_CUDA, "resetting the segment queue failed");
+        return -1;
+    }
+    return (int)segs;
 }
 
 /* Launch geometry.  One thread per chain, so the CTA size only trades scheduling granularity against the
@@ -520,6 +587,10 @@ int me_create(const me_config *cfg, me_engine **out) {
 }
 
 int me_destroy(me_engine *e) {
+    if (e && e->seg_flags) {
+        DeviceGuard g(e->cfg.device);
+        cudaFree(e->seg_flags);
+    }
     delete e;
     return ME_OK;
 }
@@ -628,7 +699,13 @@ static int run_common(me_engine *e, int64_t n_blocks, int64_t spm, int do_measur
     p.inj_delta = delta; p.inj_u = u;
     if (e->group >= 3 && !e->ks.run_mp.valid())
         return fail(e, ME_ERR_STATE, "no magnitude-phase kernel for this engine");
-    int rc = launch(e, e->group >= 3 ? e->ks.run_mp : e->ks.run, p, stream);
+    const KernelRef &kr = e->group >= 3 ? e->ks.run_mp : e->ks.run;
+    const int segs = plan_segments(e, kr, n_blocks, spm, delta != nullptr, stream);
+    if (segs < 0) return ME_ERR_CUDA;
+    if (segs > 1) {
+        p.seg_count = segs; p.seg_groups = e->grid; p.seg_base = e->seg_base; p.seg_flags = e->seg_flags;
+    }
+    int rc = launch(e, kr, p, stream, 1, segs > 1 ? e->seg_workers : 0);
     if (rc != ME_OK) return rc;
     e->step += (unsigned long long)(n_blocks * spm);
     if (do_measure) e->n_measure += n_blocks;

@@ -149,20 +149,22 @@ struct Stats {
     double obsm[L::NOBS];
 };
 
+/* State loads bypass L1 (__ldcg): consecutive time segments of one chain group run as different CTAs, possibly on
+ * different SMs, and hand the state over through global memory (see run_body). */
 template <class L>
 __device__ __forceinline__ void load_chain(Chain<L> &c, const double *st, long long ld, long long ch) {
 #pragma unroll
-    for (int i = 0; i < L::D; i++) c.x[i] = st[(long long)(L::X + i) * ld + ch];
-    c.e = st[(long long)L::E * ld + ch];
-    c.sig[0] = st[(long long)L::SIG * ld + ch];
-    c.sig[1] = st[(long long)(L::SIG + 1) * ld + ch];
+    for (int i = 0; i < L::D; i++) c.x[i] = __ldcg(st + (long long)(L::X + i) * ld + ch);
+    c.e = __ldcg(st + (long long)L::E * ld + ch);
+    c.sig[0] = __ldcg(st + (long long)L::SIG * ld + ch);
+    c.sig[1] = __ldcg(st + (long long)(L::SIG + 1) * ld + ch);
 #pragma unroll
-    for (int i = 0; i < L::NCOVR; i++) c.facr[i] = st[(long long)(L::FACR + i) * ld + ch];
+    for (int i = 0; i < L::NCOVR; i++) c.facr[i] = __ldcg(st + (long long)(L::FACR + i) * ld + ch);
 #pragma unroll
-    for (int i = 0; i < L::NCOVC; i++) c.facc[i] = st[(long long)(L::FACC + i) * ld + ch];
-    c.nacc = st[(long long)L::NACC * ld + ch];
+    for (int i = 0; i < L::NCOVC; i++) c.facc[i] = __ldcg(st + (long long)(L::FACC + i) * ld + ch);
+    c.nacc = __ldcg(st + (long long)L::NACC * ld + ch);
     c.nacc_new = 0u;
-    c.status = (int)st[(long long)L::STATUS * ld + ch];
+    c.status = (int)__ldcg(st + (long long)L::STATUS * ld + ch);
 }
 
 template <class L>
@@ -183,13 +185,13 @@ __device__ __forceinline__ void store_chain(const Chain<L> &c, double *st, long 
 template <class L>
 __device__ __forceinline__ void load_stats(Stats<L> &s, const double *st, long long ld, long long ch) {
 #pragma unroll
-    for (int i = 0; i < L::D; i++) s.mean[i] = st[(long long)(L::MEAN + i) * ld + ch];
+    for (int i = 0; i < L::D; i++) s.mean[i] = __ldcg(st + (long long)(L::MEAN + i) * ld + ch);
 #pragma unroll
-    for (int i = 0; i < L::NCOVR; i++) s.covr[i] = st[(long long)(L::COVR + i) * ld + ch];
+    for (int i = 0; i < L::NCOVR; i++) s.covr[i] = __ldcg(st + (long long)(L::COVR + i) * ld + ch);
 #pragma unroll
-    for (int i = 0; i < L::NCOVC; i++) s.covc[i] = st[(long long)(L::COVC + i) * ld + ch];
+    for (int i = 0; i < L::NCOVC; i++) s.covc[i] = __ldcg(st + (long long)(L::COVC + i) * ld + ch);
 #pragma unroll
-    for (int i = 0; i < L::NOBS; i++) s.obsm[i] = st[(long long)(L::OBSM + i) * ld + ch];
+    for (int i = 0; i < L::NOBS; i++) s.obsm[i] = __ldcg(st + (long long)(L::OBSM + i) * ld + ch);
 }
 
 template <class L>
@@ -660,7 +662,56 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     init_math_tables(tables);
     __syncthreads();
 
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    /* Time segmentation with a work queue (p.seg_count > 1).  A fused launch of an ensemble that fits the device in
+       about one wave is badly balanced: the CTAs that are resident at once are an integer number per SM sub-partition
+       (1-warp CTAs at 129..160 registers: 12 per SM = 3 per sub-partition), 65,536 chains are 2048 of them against
+       1776 slots, so a static launch runs a full first wave and then a second one at a sixth of the occupancy
+       (tests/scripts/scale_probe.py: 3 warps per sub-partition saturate its pipes).  Instead the launch is cut into
+       seg_count time segments per chain group (= the 32..128 chains of one CTA), the grid is exactly one full wave of
+       persistent workers, and the workers serve a FIFO of ready (group, segment) items: a worker pops the oldest item,
+       loads that group's state, runs the segment, stores the state and pushes the group's next segment.  All groups
+       advance at the same rate, every slot is busy until the work runs out (work-conserving), and the last, partly
+       filled round costs 1/seg_count of the launch instead of a whole wave.
+       Results do not depend on the schedule: a segment is a pure function of the group's stored state.
+       Queue memory (p.seg_flags, written by the host before the launch): [0] tickets handed out, [1] pushes made,
+       [2 .. 2 + cap) ring of entries (segment << 32 | group) + 1, 0 = empty, pre-filled with segment 0 of every group;
+       cap = p.seg_base is a power of two >= 2 x groups, so a slot is never reused before it was consumed. */
+    __shared__ unsigned long long next_item;
+    long long cgroup = blockIdx.x;
+    int seg = 0;
+  for (;;) {                                       /* one iteration per work item (exactly one when seg_count <= 1) */
+    long long b_first = 0, n_blocks = p.n_blocks;
+    if (p.seg_count > 1) {
+        if (threadIdx.x == 0) {
+            unsigned long long *q = p.seg_flags;
+            const unsigned long long cap = p.seg_base, total = (unsigned long long)p.seg_groups * (unsigned long long)p.seg_count;
+            const unsigned long long ticket = atomicAdd(q, 1ull);
+            unsigned long long got = 0;
+            if (ticket < total) {
+                unsigned long long *entry = q + 2 + (ticket & (cap - 1));
+                unsigned spin = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(entry) : "memory");
+                    if (got != 0) break;
+                    __nanosleep(200);
+                    if (++spin > (1u << 27)) __trap();   /* ~30 s: a broken queue must not hang the GPU */
+                }
+                atomicExch(entry, 0ull);
+            }
+            next_item = got;
+        }
+        __syncthreads();
+        const unsigned long long it = next_item;
+        if (it == 0) break;                        /* every item has been handed out */
+        cgroup = (long long)((it - 1ull) & 0xffffffffull);
+        seg = (int)((it - 1ull) >> 32);
+        __syncthreads();                           /* next_item may be rewritten only after everyone has read it */
+        const long long per = (p.n_blocks + p.seg_count - 1) / p.seg_count;
+        b_first = seg * per;
+        n_blocks = p.n_blocks - b_first < per ? p.n_blocks - b_first : per;
+        if (n_blocks < 0) n_blocks = 0;
+    }
+    const long long tid = cgroup * blockDim.x + threadIdx.x;
     const bool active = tid < p.n_chains;
     const long long ch = active ? tid : p.n_chains - 1;
     const long long ld = p.ld;
@@ -687,7 +738,8 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     const Rng rng(p, p.chain_offset + (unsigned long long)ch);
     const bool inject = STRICT && p.inj_delta != nullptr;
     const int group = p.group;
-    long long n = p.n_meas0;
+    long long n = p.n_meas0 + (p.do_measure ? b_first : 0);
+    const unsigned step_first = (unsigned)(p.step0 + (unsigned long long)(b_first * p.spm));
     long long s_local = 0;
     bool accept = false;
 
@@ -706,12 +758,12 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     const Pins pins = load_pins(tables);
     const double half_temp = 0.5 * p.temp;
     if (!inject && p.spm > 0 && AHEAD) {
-        gen_draws<L, STRICT>(rng, (unsigned)p.step0, tables, cur, pins, half_temp);
-        if (DEEP) gen_bits<L>(rng, (unsigned)p.step0 + 1u, raw_a);
+        gen_draws<L, STRICT>(rng, step_first, tables, cur, pins, half_temp);
+        if (DEEP) gen_bits<L>(rng, step_first + 1u, raw_a);
     }
 
     /* one step: consumes the draws in `use`, generates the draws of the following step into `make` */
-    unsigned step32 = (unsigned)p.step0;
+    unsigned step32 = step_first;
     auto one_step = [&](const Gains &g, Draws<L> &use, Draws<L> &make, Raw<L> &raw_in, Raw<L> &raw_out) {
         double prop[D];
         if (inject) {
@@ -743,10 +795,10 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     MeasureClock clk;
     clk.start(n);
     /* running row pointer of the time series (one 64-bit add per measure instead of the full index arithmetic) */
-    double *row = p.record ? p.ts + p.ts_row0 * (long long)L::TSCOLS * ld + ch : nullptr;
+    double *row = p.record ? p.ts + (p.ts_row0 + b_first) * (long long)L::TSCOLS * ld + ch : nullptr;
     const long long row_stride = (long long)L::TSCOLS * ld;
 
-    for (long long b = 0; b < p.n_blocks; b++) {
+    for (long long b = 0; b < n_blocks; b++) {
         Gains g = make_gains<!STRICT>(n, p, clk.inv_dn);
         g.k64 = pins.k64;
         /* steps in pairs so that the two draw buffers swap roles by name instead of by register moves */
@@ -807,7 +859,7 @@ for_each_pool_word<L>(c, shift, [&](int w, double v) { pacc[w] += v; });
     if (active) {
         store_chain<L>(c, st, ld, ch);
         if (STATS_REG && p.do_measure) store_stats<L>(sreg, st, ld, ch);
-        if (p.last_accept && p.spm > 0 && p.n_blocks > 0) p.last_accept[ch] = (unsigned char)accept;
+        if (p.last_accept && p.spm > 0 && n_blocks > 0) p.last_accept[ch] = (unsigned char)accept;
     }
     if (pooling) {
         if (POOL_REG) {
@@ -822,13 +874,24 @@ for_each_pool_word<L>(c, shift, [&](int w, double v) { pacc[w] += v; });
             for (int w = threadIdx.x; w < L::POOLW; w += blockDim.x) {
                 double t = 0.0;
                 for (int q = 0; q < nw; q++) t += pool_warp[q][w];
-                p.pool[(long long)blockIdx.x * L::POOLW + w] += t;
+                p.pool[cgroup * L::POOLW + w] = __ldcg(p.pool + cgroup * L::POOLW + w) + t;
             }
         } else {
             for (int w = threadIdx.x; w < L::POOLW; w += blockDim.x)
-                p.pool[(long long)blockIdx.x * L::POOLW + w] += pool_cta[w];
+                p.pool[cgroup * L::POOLW + w] = __ldcg(p.pool + cgroup * L::POOLW + w) + pool_cta[w];
         }
     }
+    if (p.seg_count <= 1) break;
+    /* hand the chain group over: publish its next segment */
+    __syncthreads();
+    if (threadIdx.x == 0 && seg + 1 < p.seg_count) {
+        unsigned long long *q = p.seg_flags;
+        __threadfence();                           /* the group's state is visible before its next segment is */
+        const unsigned long long slot = atomicAdd(q + 1, 1ull);
+        const unsigned long long item = (((unsigned long long)(seg + 1) << 32) | (unsigned long long)cgroup) + 1ull;
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(q + 2 + (slot & (p.seg_base - 1))), "l"(item) : "memory");
+    }
+  }
 }
 
 /* ------------------------------------------------------------------------------------------ initialisation (ME:40-125)

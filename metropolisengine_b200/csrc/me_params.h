@@ -5,7 +5,7 @@
 #ifndef ME_PARAMS_H
 #define ME_PARAMS_H
 
-#define ME_PARAMS_VERSION 6
+#define ME_PARAMS_VERSION 7
 #define ME_MAX_CONSTS 16
 
 /* status bits written to the per-chain STATUS word (SURVEY §5 "failure detection") */
@@ -57,7 +57,14 @@ struct MeParams {
     double *scratch;               /* [D][ld] per-chain scratch (old means during measure) */
     double *e_out;                 /* [ld] gk_energy output */
     unsigned char *rej_out;        /* [ld] gk_energy hard-wall output (may be NULL) */
-    int group;                     /* mixed engines: 0 = step_all (ME:241), 1 = step_real_group (ME:225), 2 = step_complex_group (ME:209) */
+    int group;                     /* mixed engines: 0 = step_all (ME:241), 1 = step_real_group (ME:225), 2 = step_complex_group (ME:209),
+                                      3 / 4 = magnitude / phase half of the magnitude-phase complex move (ME:178-207) */
+    /* time segmentation of a launch with a work queue (me_device.cuh, run_body) */
+    int seg_count;                 /* segments per chain group; <= 1: off */
+    long long seg_groups;          /* chain groups (the launch's CTAs are workers: at most one full wave) */
+    unsigned long long seg_base;   /* ring capacity (a power of two >= 2 x seg_groups) */
+    unsigned long long *seg_flags; /* queue: [0] tickets, [1] pushes, [2 .. 2 + capacity) ring; the host writes the initial
+                                      image (segment 0 of every group ready) before the launch */
 };
 
 #endif

@@ -1,17 +1,27 @@
-import sys, time, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+"""Throughput of the C2 step kernel as a function of the warps per SM sub-partition:
+592 sub-partitions x {1, 2, 3, 4} warps exactly, plus the BASELINE count (65,536 chains = 3.46 warps on average)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import metropolisengine_b200 as me
-for n in (65536, 262144, 1048576, 4194304, 16777216):
-    for wl in ("c2", "c3"):
-        if wl == "c2":
-            eng = me.MetropolisEngine(("xy_well", 1.0), initial_real_params=np.zeros(2), temp=.1, n_chains=n, record=False)
-        else:
-            if n > 4194304: continue
-            eng = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5, 1.0), initial_real_params=np.zeros(3), initial_complex_params=np.zeros(4, dtype=complex), temp=.1, n_chains=n, record=False)
-        steps = max(200, int(2e9 // n // 10 * 10)) if wl == "c2" else max(100, int(3e8 // n // 10 * 10))
-        eng.run(5, 10); torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); eng.run(steps // 10, 10); b.record(); torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
-        print("%s n=%9d block=%3d grid=%7d steps=%6d  %.3e chain-steps/s" % (wl, n, eng._block, eng._grid, steps, n * steps / ms * 1e3), flush=True)
-        del eng
+
+n_smsp = 4 * torch.cuda.get_device_properties(0).multi_processor_count
+for label, chains in [("1 warp / SMSP", n_smsp * 32), ("2 warps / SMSP", n_smsp * 64), ("3 warps / SMSP", n_smsp * 96),
+                      ("4 warps / SMSP", n_smsp * 128), ("65,536 chains", 65536), ("8 warps worth / SMSP", n_smsp * 256)]:
+    eng = me.MetropolisEngine(("xy_well", 1.0), initial_real_params=np.zeros(2), temp=.1, n_chains=chains, seed=3,
+                              record=False)
+    eng.run(300, 10)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    eng.run(3000, 10)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    print("%-22s chains=%8d grid=%5d block=%3d  %8.2f ms  %.3e chain-steps/s  (%.1f cycles per warp-step per SMSP-warp)"
+          % (label, chains, eng._grid, eng._block, ms, chains * 30000 / ms * 1e3,
+             ms * 1e-3 * 1.965e9 / 30000))

@@ -191,3 +191,39 @@ def test_equilibration_detection_matches_oracle():
     assert pts["param_0"][0] == ot and abs(pts["param_0"][1] - og) <= 1e-9 * og
     cut = eng.global_eq_point
     assert abs(eng.equilibrated_means["param_1"] - ts[cut:, 1, 5].mean()) < 1e-12
+
+
+def test_time_segmented_launch_is_bit_identical_to_the_plain_one():
+    """Work-queue time segmentation of single-wave launches (me_device.cuh run_body, me_api.cu plan_segments): a segment
+    is a pure function of the chain group's stored state, so states, time series and pooled moments must not depend on
+    it.  ME_SEGMENTS=1 switches it off."""
+    import os
+    import metropolisengine_b200 as me
+
+    def run(segments):
+        old = os.environ.get("ME_SEGMENTS")
+        if segments is None:
+            os.environ.pop("ME_SEGMENTS", None)
+        else:
+            os.environ["ME_SEGMENTS"] = str(segments)
+        try:
+            eng = me.MetropolisEngine(("xy_well", 1.0), initial_real_params=np.array([0.5, -0.5]), temp=.1,
+                                      n_chains=4096 + 17, seed=12)
+            eng.run(400, 10)                      # 4000 steps: segmented by default (>= 2 x 1500 steps, one wave)
+            eng.run(7, 3)                         # too short: plain launch
+            ps = eng.pooled_statistics()
+            torch.cuda.synchronize()
+            return eng.state.clone(), eng.time_series().clone(), ps
+        finally:
+            if old is None:
+                os.environ.pop("ME_SEGMENTS", None)
+            else:
+                os.environ["ME_SEGMENTS"] = old
+    s0, t0, p0 = run(1)
+    for segs in (None, 5, 16):
+        s1, t1, p1 = run(segs)
+        assert torch.equal(s0, s1), segs
+        assert torch.equal(t0, t1), segs
+        # pooled moments are summed per segment instead of per launch: equal up to the rounding of that regrouping
+        assert np.allclose(p0["cov_real"], p1["cov_real"], rtol=1e-12, atol=0), segs
+        assert np.allclose(p0["mean_real"], p1["mean_real"], rtol=1e-12, atol=1e-15), segs
