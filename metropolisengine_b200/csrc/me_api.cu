@@ -293,6 +293,7 @@ void base_params(me_engine *e, MeParams &p) {
  * 2-3).  Returns the segment count (1 = off), -1 on a CUDA error.  ME_SEGMENTS=<n> overrides (0 / 1 = off). */
 int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long long spm, bool injected, void *stream) {
     if (injected || e->generic || e->cfg.strict || !k.rt) return 1;      /* runtime-compiled kernels: not segmented */
+    if (e->lay.D > ME_SEG_MAX_D) return 1;                               /* compiled out for larger shapes (me_device.cuh) */
     int want = -1;
     if (const char *env = getenv("ME_SEGMENTS")) want = atoi(env);
     if (want == 0 || want == 1) return 1;
@@ -303,11 +304,8 @@ int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long lon
         e->run_slots = per_sm * e->n_sm;
     }
     if (e->run_slots <= 0) return 1;
-    /* workers: full waves only, i.e. the same number of CTAs on every SM sub-partition; segmentation pays when the
-       groups do not fill an integer number of such waves exactly and there are only a few waves */
-    const int n_smsp = 4 * e->n_sm;
-    int workers = (int)((e->grid < e->run_slots ? e->grid : e->run_slots) / n_smsp) * n_smsp;
-    if (workers <= 0 || e->grid % workers == 0 || e->grid > 4LL * e->run_slots) return 1;
+    /* segmentation pays when the groups do not fill an integer number of waves and there are only a few waves */
+    if (e->grid % e->run_slots == 0 || e->grid > 4LL * e->run_slots) return 1;
     const long long steps = n_blocks * (spm > 0 ? spm : 1);
     const long long min_steps = 1500;                                    /* per segment: hand-over cost stays < 1 % */
     long long segs = want > 1 ? want : steps / min_steps;
@@ -316,7 +314,9 @@ int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long lon
     if (segs < 2) return 1;
     if (!e->seg_flags) {
         unsigned long long cap = 2;
-        while (cap < 2ull * (unsigned long long)e->grid) cap <<= 1;
+        /* one ring slot per item of the largest launch (16 segments): every CTA takes its ticket as soon as it starts,
+           long before the matching push, so a slot must never be shared by two tickets of one launch */
+        while (cap < 16ull * (unsigned long long)e->grid) cap <<= 1;
         const size_t words = (size_t)(cap + 2);
         if (cudaMallocAsync((void **)&e->seg_flags, sizeof(unsigned long long) * 2 * words, (cudaStream_t)stream) != cudaSuccess) {
             fail(e, ME_ERR_CUDA, "allocating the segment queue failed");
@@ -334,10 +334,9 @@ int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long lon
         }
         e->seg_base = cap;
     }
-    e->seg_workers = workers;
     if (getenv("ME_DEBUG"))
-        fprintf(stderr, "[me_b200] segmented launch: %lld groups x %lld segments on %d workers (%d slots)\n",
-                (long long)e->grid, segs, workers, e->run_slots);
+        fprintf(stderr, "[me_b200] segmented launch: %lld groups x %lld segments (%d resident slots)\n",
+                (long long)e->grid, segs, e->run_slots);
     const size_t words = (size_t)(e->seg_base + 2);
     if (cudaMemcpyAsync(e->seg_flags, e->seg_flags + words, sizeof(unsigned long long) * words, cudaMemcpyDeviceToDevice,
                         (cudaStream_t)stream) != cudaSuccess) {
@@ -705,7 +704,7 @@ static int run_common(me_engine *e, int64_t n_blocks, int64_t spm, int do_measur
     if (segs > 1) {
         p.seg_count = segs; p.seg_groups = e->grid; p.seg_base = e->seg_base; p.seg_flags = e->seg_flags;
     }
-    int rc = launch(e, kr, p, stream, 1, segs > 1 ? e->seg_workers : 0);
+    int rc = launch(e, kr, p, stream, segs > 1 ? segs : 1);
     if (rc != ME_OK) return rc;
     e->step += (unsigned long long)(n_blocks * spm);
     if (do_measure) e->n_measure += n_blocks;

@@ -29,6 +29,7 @@
 #define ME_BIG_LOOKAHEAD 1     /* shapes with D > 4: generate the draws of step s+1 during step s (costs D+2 doubles of registers) */
 #endif
 #define ME_FULL 0xffffffffu
+#define ME_SEG_MAX_D 4         /* shapes up to this D = n_real + 2 n_complex support work-queue time segmentation */
 #define ME_MAX_POOLW 600
 
 namespace me {
@@ -667,45 +668,44 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
        (1-warp CTAs at 129..160 registers: 12 per SM = 3 per sub-partition), 65,536 chains are 2048 of them against
        1776 slots, so a static launch runs a full first wave and then a second one at a sixth of the occupancy
        (tests/scripts/scale_probe.py: 3 warps per sub-partition saturate its pipes).  Instead the launch is cut into
-       seg_count time segments per chain group (= the 32..128 chains of one CTA), the grid is exactly one full wave of
-       persistent workers, and the workers serve a FIFO of ready (group, segment) items: a worker pops the oldest item,
-       loads that group's state, runs the segment, stores the state and pushes the group's next segment.  All groups
-       advance at the same rate, every slot is busy until the work runs out (work-conserving), and the last, partly
-       filled round costs 1/seg_count of the launch instead of a whole wave.
+       seg_count time segments per chain group (= the 32..128 chains of one CTA) and launched as groups x seg_count
+       CTAs, each of which takes ONE item from a FIFO of ready (group, segment) items when it starts: it loads that
+       group's state, runs the segment, stores the state and pushes the group's next segment.  Which CTA index runs which
+       item is decided at run time, so the hardware CTA scheduler — which refills a slot the moment it frees — becomes
+       a work-conserving scheduler: every slot is busy until the work runs out, all groups advance at the same rate,
+       and the last, partly filled round costs 1/seg_count of the launch instead of a whole wave.  Progress: an item is
+       only ever pushed by a CTA that already holds its own item (resident or finished), so the CTA holding the lowest
+       unserved ticket never waits on an undispatched CTA.
        Results do not depend on the schedule: a segment is a pure function of the group's stored state.
        Queue memory (p.seg_flags, written by the host before the launch): [0] tickets handed out, [1] pushes made,
        [2 .. 2 + cap) ring of entries (segment << 32 | group) + 1, 0 = empty, pre-filled with segment 0 of every group;
-       cap = p.seg_base is a power of two >= 2 x groups, so a slot is never reused before it was consumed. */
+       cap = p.seg_base is a power of two >= groups x 16 >= the number of items, so no two tickets share a slot.
+       (A persistent-worker loop around this body was measured first: it costs 7 % in the step loop, because the
+       compiler no longer proves the control flow uniform and reloads its uniform-register operands every iteration.) */
+    constexpr bool SEGMENTED = L::D <= ME_SEG_MAX_D;     /* larger shapes run at 255 registers: not worth the pressure */
     __shared__ unsigned long long next_item;
-    long long cgroup = blockIdx.x;
+    long long cgroup = blockIdx.x, b_first = 0, n_blocks = p.n_blocks;
     int seg = 0;
-  for (;;) {                                       /* one iteration per work item (exactly one when seg_count <= 1) */
-    long long b_first = 0, n_blocks = p.n_blocks;
-    if (p.seg_count > 1) {
+    if (SEGMENTED && p.seg_count > 1) {
         if (threadIdx.x == 0) {
             unsigned long long *q = p.seg_flags;
-            const unsigned long long cap = p.seg_base, total = (unsigned long long)p.seg_groups * (unsigned long long)p.seg_count;
-            const unsigned long long ticket = atomicAdd(q, 1ull);
+            const unsigned long long ticket = atomicAdd(q, 1ull);       /* < groups x seg_count = the grid size */
+            unsigned long long *entry = q + 2 + (ticket & (p.seg_base - 1));
             unsigned long long got = 0;
-            if (ticket < total) {
-                unsigned long long *entry = q + 2 + (ticket & (cap - 1));
-                unsigned spin = 0;
-                for (;;) {
-                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(entry) : "memory");
-                    if (got != 0) break;
-                    __nanosleep(200);
-                    if (++spin > (1u << 27)) __trap();   /* ~30 s: a broken queue must not hang the GPU */
-                }
-                atomicExch(entry, 0ull);
+            unsigned spin = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(entry) : "memory");
+                if (got != 0) break;
+                __nanosleep(200);
+                if (++spin > (1u << 27)) __trap();       /* ~30 s: a broken queue must not hang the GPU */
             }
+            atomicExch(entry, 0ull);
             next_item = got;
         }
         __syncthreads();
         const unsigned long long it = next_item;
-        if (it == 0) break;                        /* every item has been handed out */
         cgroup = (long long)((it - 1ull) & 0xffffffffull);
         seg = (int)((it - 1ull) >> 32);
-        __syncthreads();                           /* next_item may be rewritten only after everyone has read it */
         const long long per = (p.n_blocks + p.seg_count - 1) / p.seg_count;
         b_first = seg * per;
         n_blocks = p.n_blocks - b_first < per ? p.n_blocks - b_first : per;
@@ -881,17 +881,16 @@ for_each_pool_word<L>(c, shift, [&](int w, double v) { pacc[w] += v; });
                 p.pool[cgroup * L::POOLW + w] = __ldcg(p.pool + cgroup * L::POOLW + w) + pool_cta[w];
         }
     }
-    if (p.seg_count <= 1) break;
-    /* hand the chain group over: publish its next segment */
-    __syncthreads();
-    if (threadIdx.x == 0 && seg + 1 < p.seg_count) {
-        unsigned long long *q = p.seg_flags;
-        __threadfence();                           /* the group's state is visible before its next segment is */
-        const unsigned long long slot = atomicAdd(q + 1, 1ull);
-        const unsigned long long item = (((unsigned long long)(seg + 1) << 32) | (unsigned long long)cgroup) + 1ull;
-        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(q + 2 + (slot & (p.seg_base - 1))), "l"(item) : "memory");
+    if (SEGMENTED && p.seg_count > 1 && seg + 1 < p.seg_count) {      /* hand the chain group over: publish its next segment */
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long *q = p.seg_flags;
+            __threadfence();                           /* the group's state is visible before its next segment is */
+            const unsigned long long slot = atomicAdd(q + 1, 1ull);
+            const unsigned long long item = (((unsigned long long)(seg + 1) << 32) | (unsigned long long)cgroup) + 1ull;
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(q + 2 + (slot & (p.seg_base - 1))), "l"(item) : "memory");
+        }
     }
-  }
 }
 
 /* ------------------------------------------------------------------------------------------ initialisation (ME:40-125)

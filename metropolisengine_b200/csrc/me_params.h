@@ -61,8 +61,8 @@ struct MeParams {
                                       3 / 4 = magnitude / phase half of the magnitude-phase complex move (ME:178-207) */
     /* time segmentation of a launch with a work queue (me_device.cuh, run_body) */
     int seg_count;                 /* segments per chain group; <= 1: off */
-    long long seg_groups;          /* chain groups (the launch's CTAs are workers: at most one full wave) */
-    unsigned long long seg_base;   /* ring capacity (a power of two >= 2 x seg_groups) */
+    long long seg_groups;          /* chain groups; the launch has seg_groups x seg_count CTAs, one work item each */
+    unsigned long long seg_base;   /* ring capacity (a power of two >= seg_groups x seg_count) */
     unsigned long long *seg_flags; /* queue: [0] tickets, [1] pushes, [2 .. 2 + capacity) ring; the host writes the initial
                                       image (segment 0 of every group ready) before the launch */
 };
