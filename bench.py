@@ -48,10 +48,10 @@ WORKLOADS = {
 
 def _ncu_traffic_per_chain_measure():
     """DRAM bytes per chain-measure of the step kernel from the committed ncu --set full capture
-    (profiles/r01_ncu_c2_k_run_v3.csv: a launch of 300 measures x 65,536 chains)."""
+    (profiles/r01_ncu_c2_k_run_v4.csv: a launch of 300 measures x 65,536 chains)."""
     try:
         rd = wr = None
-        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_c2_k_run_v3.csv")):
+        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_c2_k_run_v4.csv")):
             f = line.strip().split(",")
             if f[0] == "dram__bytes_read.sum":
                 rd = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
@@ -414,26 +414,23 @@ def run_ours(args):
     # Pipe-level roofline of the step kernel.  A warp-wide FP64 instruction holds the FP64 pipe of its SM
     # sub-partition for 2 cycles and an IMAD.WIDE (Philox round) the FMA-heavy pipe for ~3.5; the two contend
     # (tests/scripts/issue_mix.cu, profiles/r01_microbench_issue_mix.txt), so a warp-step costs at least
-    # 2 * fp64_inst + 3.5 * wide_inst cycles of its sub-partition, and the kernel cannot finish before the most loaded
-    # sub-partition has done that for all of its warps.
+    # 2 * fp64_inst + 3.5 * wide_inst cycles of its sub-partition.  Launches are balanced over the sub-partitions
+    # (several waves, or the work-queue time segmentation of me_device.cuh for ensembles of about one wave), so the
+    # bound is that cost times the average number of warps per sub-partition.
     clk = clocks.summary()
     sm_hz = 1e6 * (clk.get("sm_mhz") or 1965)
     n_smsp = 4 * n_sm
     warps = -(-chains // 32)
-    # one wave (every warp resident from the start): the busiest sub-partition holds ceil(warps / n_smsp) of them;
-    # several waves: the CTA scheduler balances the waves, use the average
-    warps_busiest = -(-warps // n_smsp) if warps <= 4 * n_smsp else warps / n_smsp
+    warps_busiest = warps / n_smsp
     cyc_step = 2.0 * wl["fp64_inst"] + 3.5 * wl["wide_inst"]
     pipe_bound_ms = 1e3 * warps_busiest * M * spm * cyc_step / sm_hz
     pipe = {"fp64_inst_per_chain_step": wl["fp64_inst"], "imad_wide_per_chain_step": wl["wide_inst"],
-            "cycles_per_warp_step_lower_bound": cyc_step, "warps_on_busiest_subpartition": warps_busiest,
+            "cycles_per_warp_step_lower_bound": cyc_step, "warps_per_subpartition": warps_busiest,
             "bound_ms": pipe_bound_ms, "frac": pipe_bound_ms / ker_ms,
-            "balanced_frac": 1e3 * (warps / n_smsp) * M * spm * cyc_step / sm_hz / ker_ms,
             "how": "FP64-pipe + FMA-heavy-pipe cycles the SASS of the step loop needs (2 per FP64 instruction, 3.5 per "
-                   "IMAD.WIDE; the pipes contend) on the most loaded SM sub-partition / measured kernel time; "
-                   "balanced_frac uses the average warps per sub-partition instead",
-            "ncu": ("profiles/r01_ncu_c2_k_run_v3.csv: FP64 pipe 38 % + FMA-heavy 27 % of elapsed cycles (46 % / 32 % "
-                    "of active), issue slots 59 % busy, sub-partitions active 83 % of the kernel"
+                   "IMAD.WIDE; the pipes contend) x average warps per SM sub-partition / measured kernel time",
+            "ncu": ("profiles/r01_ncu_c2_k_run_v4.csv: FP64 pipe 46 % + FMA-heavy pipe 42 % of elapsed cycles (the "
+                    "FMA-heavy pipe also runs the IMAD.MOV / IMAD.SHL the compiler uses as moves), issue slots 61 % busy"
                     if args.workload == "c2" else None)}
     line = {
         "metric": "ensemble chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
@@ -453,7 +450,7 @@ def run_ours(args):
                      "frac": achieved_tf / fp64_peak,
                      "traffic": (tpm * chains * M) if tpm else None,
                      "traffic_note": "DRAM read+write bytes per launch: per chain-measure figure of the committed ncu "
-                                     "--set full capture (profiles/r01_ncu_c2_k_run_v3.csv) x this launch's "
+                                     "--set full capture (profiles/r01_ncu_c2_k_run_v4.csv) x this launch's "
                                      "chain-measures; algorithmic %d B per chain-measure" % (8 * ts_cols),
                      "pipe": pipe,
                      "kernel": "me::k_run", "kernel_ms": ker_ms,
