@@ -50,12 +50,14 @@ typedef CUresult (*cuModuleGetFunction_t)(CUfunction *, CUmodule, const char *);
 typedef CUresult (*cuLaunchKernel_t)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                                      CUstream, void **, void **);
 typedef CUresult (*cuGetErrorString_t)(CUresult, const char **);
+typedef CUresult (*cuOccupancy_t)(int *, CUfunction, int, size_t);
 
 struct Driver {
     cuModuleLoadData_t moduleLoadData = nullptr;
     cuModuleGetFunction_t moduleGetFunction = nullptr;
     cuLaunchKernel_t launchKernel = nullptr;
     cuGetErrorString_t getErrorString = nullptr;
+    cuOccupancy_t occupancy = nullptr;          /* optional: only the launch balancing of runtime-compiled kernels needs it */
     bool ok = false;
     std::string err;
 };
@@ -77,6 +79,10 @@ Driver &driver() {
         d.ok = get("cuModuleLoadData", (void **)&d.moduleLoadData) &&
                get("cuModuleGetFunction", (void **)&d.moduleGetFunction) &&
                get("cuLaunchKernel", (void **)&d.launchKernel) && get("cuGetErrorString", (void **)&d.getErrorString);
+        if (d.ok) {
+            const std::string keep = d.err;
+            if (!get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void **)&d.occupancy)) { d.occupancy = nullptr; d.err = keep; }
+        }
     });
     return d;
 }
@@ -292,7 +298,7 @@ void base_params(me_engine *e, MeParams &p) {
  * balances the SM sub-partitions (65,536 chains are 3 or 4 warps per sub-partition, and a sub-partition saturates at
  * 2-3).  Returns the segment count (1 = off), -1 on a CUDA error.  ME_SEGMENTS=<n> overrides (0 / 1 = off). */
 int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long long spm, bool injected, void *stream) {
-    if (injected || e->generic || e->cfg.strict || !k.rt) return 1;      /* runtime-compiled kernels: not segmented */
+    if (injected || e->generic || e->cfg.strict || !k.valid()) return 1;
     if (e->lay.D > ME_SEG_MAX_D) return 1;                               /* compiled out for larger shapes (me_device.cuh) */
     int want = -1;
     if (const char *env = getenv("ME_SEGMENTS")) want = atoi(env);
@@ -300,7 +306,12 @@ int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long lon
     DeviceGuard g(e->cfg.device);
     if (e->run_slots < 0) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.rt, e->block, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+        if (k.rt) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.rt, e->block, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+        } else {                                  /* runtime-compiled (NVRTC) kernel: driver API */
+            Driver &d = driver();
+            if (!d.ok || !d.occupancy || d.occupancy(&per_sm, k.drv, e->block, 0) != CUDA_SUCCESS) per_sm = 0;
+        }
         e->run_slots = per_sm * e->n_sm;
     }
     if (e->run_slots <= 0) return 1;
@@ -602,6 +613,7 @@ static int set_energy(me_engine *e, int id, const char *src, const double *const
     for (int i = 0; i < n_consts; i++) e->consts[i] = consts[i];
     e->use_reject = use_reject ? 1 : 0;
     e->ks = KernelSet();
+    e->run_slots = -1;
     const int prev_id = e->energy_id;
     e->energy_id = id;
     int rc = resolve_kernels(e, id, src ? std::string(src) : std::string());

@@ -696,8 +696,8 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
             for (;;) {
                 asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(entry) : "memory");
                 if (got != 0) break;
-                __nanosleep(200);
-                if (++spin > (1u << 27)) __trap();       /* ~30 s: a broken queue must not hang the GPU */
+                __nanosleep(spin < 4096u ? 200u : 2000u);
+                if (++spin > (1u << 28)) __trap();       /* > 8 minutes: a broken queue must not hang the GPU for good */
             }
             atomicExch(entry, 0ull);
             next_item = got;

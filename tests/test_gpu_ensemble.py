@@ -227,3 +227,28 @@ def test_time_segmented_launch_is_bit_identical_to_the_plain_one():
         # pooled moments are summed per segment instead of per launch: equal up to the rounding of that regrouping
         assert np.allclose(p0["cov_real"], p1["cov_real"], rtol=1e-12, atol=0), segs
         assert np.allclose(p0["mean_real"], p1["mean_real"], rtol=1e-12, atol=1e-15), segs
+
+
+def test_time_segmentation_also_serves_runtime_compiled_functors():
+    """A user functor compiled through NVRTC gets the same work-queue launch (occupancy through the driver API) and the
+    same bit-identical results."""
+    import os
+    import metropolisengine_b200 as me
+    src = """__device__ double me_user_energy(const double* x, const double* cr, const double* ci, const double* k) {
+        return k[0] * (x[0] * x[0] + x[1] * x[1]); }"""
+
+    def run(segments):
+        old = os.environ.get("ME_SEGMENTS")
+        os.environ["ME_SEGMENTS"] = str(segments)
+        try:
+            eng = me.MetropolisEngine(me.CudaEnergy(src, consts=[1.0]), initial_real_params=np.array([0.5, -0.5]), temp=.1,
+                                      n_chains=2048 + 5, seed=12, record=False)
+            eng.run(300, 10)
+            torch.cuda.synchronize()
+            return eng.state.clone()
+        finally:
+            if old is None:
+                os.environ.pop("ME_SEGMENTS", None)
+            else:
+                os.environ["ME_SEGMENTS"] = old
+    assert torch.equal(run(1), run(4))
