@@ -297,6 +297,7 @@ void base_params(me_engine *e, MeParams &p) {
  * launch is cut into time segments per chain group and the CTAs become workers on a FIFO of ready segments, which
  * balances the SM sub-partitions (65,536 chains are 3 or 4 warps per sub-partition, and a sub-partition saturates at
  * 2-3).  Returns the segment count (1 = off), -1 on a CUDA error.  ME_SEGMENTS=<n> overrides (0 / 1 = off). */
+#define ME_MAX_SEGMENTS 64      /* the last, partly filled round of items costs ~1/(2 x rounds) of the launch */
 int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long long spm, bool injected, void *stream) {
     if (injected || e->generic || e->cfg.strict || !k.valid()) return 1;
     if (e->lay.D > ME_SEG_MAX_D) return 1;                               /* compiled out for larger shapes (me_device.cuh) */
@@ -320,14 +321,14 @@ int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long lon
     const long long steps = n_blocks * (spm > 0 ? spm : 1);
     const long long min_steps = 1500;                                    /* per segment: hand-over cost stays < 1 % */
     long long segs = want > 1 ? want : steps / min_steps;
-    if (segs > 16) segs = 16;
+    if (segs > ME_MAX_SEGMENTS) segs = ME_MAX_SEGMENTS;
     if (segs > n_blocks) segs = n_blocks;
     if (segs < 2) return 1;
     if (!e->seg_flags) {
         unsigned long long cap = 2;
-        /* one ring slot per item of the largest launch (16 segments): every CTA takes its ticket as soon as it starts,
-           long before the matching push, so a slot must never be shared by two tickets of one launch */
-        while (cap < 16ull * (unsigned long long)e->grid) cap <<= 1;
+        /* one ring slot per item of the largest launch: every CTA takes its ticket as soon as it starts, long before the
+           matching push, so a slot must never be shared by two tickets of one launch */
+        while (cap < (unsigned long long)ME_MAX_SEGMENTS * (unsigned long long)e->grid) cap <<= 1;
         const size_t words = (size_t)(cap + 2);
         if (cudaMallocAsync((void **)&e->seg_flags, sizeof(unsigned long long) * 2 * words, (cudaStream_t)stream) != cudaSuccess) {
             fail(e, ME_ERR_CUDA, "allocating the segment queue failed");

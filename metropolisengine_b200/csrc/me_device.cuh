@@ -668,7 +668,7 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
        (1-warp CTAs at 129..160 registers: 12 per SM = 3 per sub-partition), 65,536 chains are 2048 of them against
        1776 slots, so a static launch runs a full first wave and then a second one at a sixth of the occupancy
        (tests/scripts/scale_probe.py: 3 warps per sub-partition saturate its pipes).  Instead the launch is cut into
-       seg_count time segments per chain group (= the 32..128 chains of one CTA) and launched as groups x seg_count
+       seg_count (<= 64) time segments per chain group (= the 32..128 chains of one CTA) and launched as groups x seg_count
        CTAs, each of which takes ONE item from a FIFO of ready (group, segment) items when it starts: it loads that
        group's state, runs the segment, stores the state and pushes the group's next segment.  Which CTA index runs which
        item is decided at run time, so the hardware CTA scheduler — which refills a slot the moment it frees — becomes
@@ -679,7 +679,7 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
        Results do not depend on the schedule: a segment is a pure function of the group's stored state.
        Queue memory (p.seg_flags, written by the host before the launch): [0] tickets handed out, [1] pushes made,
        [2 .. 2 + cap) ring of entries (segment << 32 | group) + 1, 0 = empty, pre-filled with segment 0 of every group;
-       cap = p.seg_base is a power of two >= groups x 16 >= the number of items, so no two tickets share a slot.
+       cap = p.seg_base is a power of two >= groups x 64 >= the number of items, so no two tickets share a slot.
        (A persistent-worker loop around this body was measured first: it costs 7 % in the step loop, because the
        compiler no longer proves the control flow uniform and reloads its uniform-register operands every iteration.) */
     constexpr bool SEGMENTED = L::D <= ME_SEG_MAX_D;     /* larger shapes run at 255 registers: not worth the pressure */

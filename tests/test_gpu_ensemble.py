@@ -220,7 +220,7 @@ def test_time_segmented_launch_is_bit_identical_to_the_plain_one():
             else:
                 os.environ["ME_SEGMENTS"] = old
     s0, t0, p0 = run(1)
-    for segs in (None, 5, 16):
+    for segs in (None, 5, 16, 64):
         s1, t1, p1 = run(segs)
         assert torch.equal(s0, s1), segs
         assert torch.equal(t0, t1), segs
