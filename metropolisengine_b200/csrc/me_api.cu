@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <dlfcn.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -227,6 +228,7 @@ struct me_engine {
     unsigned long long seg_base = 0;           /* ring capacity */
     int seg_workers = 0;                       /* CTAs of a segmented launch */
     int run_slots = -1;                        /* CTAs of the fused kernel resident on the device at once (-1: unknown) */
+    const double *logtab = nullptr;            /* me_math.cuh log table on this engine's device */
     std::string err;
 };
 
@@ -263,8 +265,35 @@ int launch(me_engine *e, const KernelRef &k, MeParams &p, void *stream, int grid
     return ME_OK;
 }
 
+/* The log table of me_math.cuh: computed once per device in long double and kept for the life of the process. */
+const double *log_table(int device) {
+    static std::mutex mu;
+    static std::map<int, double *> tabs;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = tabs.find(device);
+    if (it != tabs.end()) return it->second;
+    std::vector<double> host(2 * ME_LOGTAB_ENTRIES);
+    const int fold = (int)(0.4142135623730951 * ME_LOGTAB_ENTRIES);          /* first interval whose upper edge exceeds sqrt 2 */
+    for (int i = 0; i < ME_LOGTAB_ENTRIES; i++) {
+        const double c = 1.0 + (double)(i + 1) / (double)ME_LOGTAB_ENTRIES;
+        const double rc = (double)(float)(1.0 / c);
+        host[2 * i] = rc;
+        host[2 * i + 1] = (double)(2.0L * logl(i >= fold ? (long double)rc * 2.0L : (long double)rc));
+    }
+    DeviceGuard g(device);
+    double *dev = nullptr;
+    if (cudaMalloc((void **)&dev, host.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    tabs[device] = dev;
+    return dev;
+}
+
 void base_params(me_engine *e, MeParams &p) {
     memset(&p, 0, sizeof(p));
+    p.logtab = e->logtab;
     p.state = e->buf.state;
     p.ld = e->cfg.n_chains;
     p.n_chains = e->cfg.n_chains;
@@ -672,6 +701,10 @@ int me_bind(me_engine *e, const me_buffers *b) {
     if (e->generic && !b->scratch) return fail(e, ME_ERR_INVALID, "large parameter spaces need the scratch buffer");
     e->buf = *b;
     e->bound = true;
+    if (!e->logtab) {
+        e->logtab = log_table(e->cfg.device);
+        if (!e->logtab) return fail(e, ME_ERR_CUDA, "allocating the log table failed");
+    }
     return ME_OK;
 }
 

@@ -34,6 +34,9 @@
 
 namespace me {
 
+template <bool SMEM> struct TabSelect { typedef LogTabGlobal type; };
+template <> struct TabSelect<true> { typedef LogTabShared type; };
+
 template <int NR_, int NC_>
 struct Lay {
     static constexpr int NR = NR_, NC = NC_;
@@ -104,12 +107,13 @@ struct Rng {
     __device__ __forceinline__ U4 bits(unsigned step, unsigned slot) const {
         return philox4x32_10(c0, c1, step, slot, rk);
     }
-    template <bool STRICT>
+    template <bool STRICT, class Tab = LogTabGlobal>
     __device__ __forceinline__ static void box_muller(const U4 &r, const MathTables &T, double &z0, double &z1,
-                                                      const double unit = ME_C_UNIT, const double angle = ME_C_ANGLE) {
+                                                      const double unit = ME_C_UNIT, const double angle = ME_C_ANGLE,
+                                                      const Tab logtab = Tab{nullptr}) {
         const double d = __hiloint2double((int)(0x3ff00000u | (r.y >> 12)), (int)((r.y << 20) | (r.x >> 12)));
         const double u1 = d - unit;                                                     /* d - (1 - 2^-53), exact */
-        const double rad = STRICT ? sqrt(-2.0 * log(u1)) : sqrt_pos(neg2log_unit(u1, T));
+        const double rad = STRICT ? sqrt(-2.0 * log(u1)) : sqrt_pos(neg2log_unit(u1, logtab));
         double s, c;
         sincospi_bits(r.z, s, c, angle);
         z0 = rad * c;
@@ -124,8 +128,9 @@ struct Rng {
         return d - 1.0;
     }
     /* -T ln u = (T/2) (-2 ln u) >= 0; T == 0 gives 0: only moves with dE <= 0 are accepted (ME:331-332) */
-    __device__ __forceinline__ static double accept_threshold(const Spare &sp, const MathTables &T, double half_temp) {
-        return half_temp * neg2log_unit(accept_uniform(sp), T);
+    template <class Tab>
+    __device__ __forceinline__ static double accept_threshold(const Spare &sp, const Tab &logtab, double half_temp) {
+        return half_temp * neg2log_unit(accept_uniform(sp), logtab);
     }
 };
 
@@ -310,27 +315,27 @@ __device__ __forceinline__ void gen_bits(const Rng &rng, unsigned step, Raw<L> &
     for (int q = 0; q < (L::D + 1) / 2; q++) raw.r[q] = rng.bits(step, (unsigned)q);
 }
 
-template <class L, bool STRICT>
+template <class L, bool STRICT, class Tab>
 __device__ __forceinline__ void shape_draws(const Raw<L> &raw, const MathTables &T, Draws<L> &d, const Pins &pins,
-                                            double half_temp) {
+                                            double half_temp, const Tab &logtab) {
     constexpr int NQ = (L::D + 1) / 2;
     Spare sp;
     sp.w0 = sp.x0 = 0;
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
         Rng::keep_spare(raw.r[q], q, sp);
-        Rng::box_muller<STRICT>(raw.r[q], T, d.z[2 * q], d.z[2 * q + 1], pins.unit, pins.angle);
+        Rng::box_muller<STRICT, Tab>(raw.r[q], T, d.z[2 * q], d.z[2 * q + 1], pins.unit, pins.angle, logtab);
     }
     /* strict build: the uniform itself; throughput build: the energy threshold -T ln u */
-    d.u = STRICT ? Rng::accept_uniform(sp) : Rng::accept_threshold(sp, T, half_temp);
+    d.u = STRICT ? Rng::accept_uniform(sp) : Rng::accept_threshold(sp, logtab, half_temp);
 }
 
-template <class L, bool STRICT>
+template <class L, bool STRICT, class Tab>
 __device__ __forceinline__ void gen_draws(const Rng &rng, unsigned step, const MathTables &T, Draws<L> &d,
-                                          const Pins &pins, double half_temp) {
+                                          const Pins &pins, double half_temp, const Tab &logtab) {
     Raw<L> raw;
     gen_bits<L>(rng, step, raw);
-    shape_draws<L, STRICT>(raw, T, d, pins, half_temp);
+    shape_draws<L, STRICT, Tab>(raw, T, d, pins, half_temp, logtab);
 }
 
 template <class L>
@@ -757,8 +762,18 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     Raw<L> raw_a, raw_b;
     const Pins pins = load_pins(tables);
     const double half_temp = 0.5 * p.temp;
+    /* log table: read-only global path for small shapes, per-CTA shared copy for larger ones (see me_math.cuh) */
+    constexpr bool TAB_SMEM = !STRICT && L::D > ME_SEG_MAX_D;
+    __shared__ double2 logtab_s[TAB_SMEM ? ME_LOGTAB_ENTRIES : 1];
+    if (TAB_SMEM) {
+        for (int i = threadIdx.x; i < ME_LOGTAB_ENTRIES; i += blockDim.x)
+            logtab_s[i] = __ldg(reinterpret_cast<const double2 *>(p.logtab) + i);
+        __syncthreads();
+    }
+    typedef typename TabSelect<TAB_SMEM>::type Tab;
+    const Tab logtab{TAB_SMEM ? logtab_s : reinterpret_cast<const double2 *>(p.logtab)};
     if (!inject && p.spm > 0 && AHEAD) {
-        gen_draws<L, STRICT>(rng, step_first, tables, cur, pins, half_temp);
+        gen_draws<L, STRICT, Tab>(rng, step_first, tables, cur, pins, half_temp, logtab);
         if (DEEP) gen_bits<L>(rng, step_first + 1u, raw_a);
     }
 
@@ -776,11 +791,11 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
         } else {
             if (DEEP) {
                 gen_bits<L>(rng, step32 + 2u, raw_out);
-                shape_draws<L, STRICT>(raw_in, tables, make, pins, half_temp);
+                shape_draws<L, STRICT, Tab>(raw_in, tables, make, pins, half_temp, logtab);
             } else if (AHEAD) {
-                gen_draws<L, STRICT>(rng, step32 + 1u, tables, make, pins, half_temp);
+                gen_draws<L, STRICT, Tab>(rng, step32 + 1u, tables, make, pins, half_temp, logtab);
             } else {
-                gen_draws<L, STRICT>(rng, step32, tables, use, pins, half_temp);
+                gen_draws<L, STRICT, Tab>(rng, step32, tables, use, pins, half_temp, logtab);
             }
             apply_proposal<L>(c, use.z, prop);
             if (MP && L::NC > 0 && group >= 3) {
@@ -964,7 +979,8 @@ __device__ __forceinline__ void propose_body(const MeParams &p) {
     } else {
         const Rng rng(p, p.chain_offset + (unsigned long long)ch);
         Draws<L> d;
-        gen_draws<L, Cfg::STRICT>(rng, (unsigned)p.step0, tables, d, load_pins(tables), 0.5 * p.temp);
+        gen_draws<L, Cfg::STRICT, LogTabGlobal>(rng, (unsigned)p.step0, tables, d, load_pins(tables), 0.5 * p.temp,
+                                                LogTabGlobal{reinterpret_cast<const double2 *>(p.logtab)});
         apply_proposal<L>(c, d.z, prop);
         if (L::NC > 0 && p.group >= 3) {
             if (p.group == 3) propose_magnitudes<L>(c, d.z, prop);
@@ -1010,7 +1026,8 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
             const Rng rng(p, p.chain_offset + (unsigned long long)ch);
             Spare sp;
             Rng::keep_spare(rng.bits((unsigned)p.step0, 0u), 0, sp);
-            u = STRICT ? Rng::accept_uniform(sp) : Rng::accept_threshold(sp, tables, 0.5 * p.temp);
+            u = STRICT ? Rng::accept_uniform(sp)
+                       : Rng::accept_threshold(sp, LogTabGlobal{reinterpret_cast<const double2 *>(p.logtab)}, 0.5 * p.temp);
         }
         accept = decide<STRICT>(diff, u, p, tables, g.hot);
         if (accept) {

@@ -33,6 +33,12 @@ namespace me {
 struct Pins {
     double unit, angle, k64;
 };
+
+/* Table of the table-driven log: 1024 intervals of the mantissa [1 + i/1024, 1 + (i+1)/1024): {rc_i, -2 l_i} with
+ * rc_i = float(1 / upper edge), l_i = -ln(rc_i * (i >= 424 ? 2 : 1)).  16 KB, computed once per device by the host
+ * library in long double (me_api.cu) and read through the L1 / read-only path: no per-CTA initialisation, and the finer
+ * intervals (|r| <= 2^-10) cut the log1p polynomial from degree 8 to degree 5. */
+#define ME_LOGTAB_ENTRIES 1024
 __constant__ double me_kc[32] = {
     /* 0..4  log1p series coefficients that are not exact binary fractions: 1/7, -1/6, 1/5, 1/3, (unused) */
     0.14285714285714285, -0.16666666666666666, 0.2, 0.33333333333333331, 0.0,
@@ -50,20 +56,12 @@ __constant__ double me_kc[32] = {
     0.0, 0.0, 0.0, 0.0};
 
 struct MathTables {
-    double logt[128][2];   /* interval i of the mantissa [1 + i/128, 1 + (i+1)/128): {rc_i, -2 l_i} with
-                              rc_i = float(1 / upper edge), l_i = -ln(rc_i * (i >= 53 ? 2 : 1)) */
     double exp2t[64];      /* 2^(j/64) */
     double pins[4];        /* ME_C_UNIT, ME_C_ANGLE, ME_C_64_LN2 (see Pins) */
 };
 
 /* Called by every thread of the CTA before any use; the caller synchronises afterwards. */
 __device__ __forceinline__ void init_math_tables(MathTables &T) {
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-        const double c = 1.0 + (double)(i + 1) * 0.0078125;
-        const double rc = (double)(float)(1.0 / c);
-        T.logt[i][0] = rc;
-        T.logt[i][1] = 2.0 * log(i >= 53 ? rc * 2.0 : rc);
-    }
     for (int j = threadIdx.x; j < 64; j += blockDim.x) T.exp2t[j] = exp2((double)j * 0.015625);
     if (threadIdx.x == 0) { T.pins[0] = ME_C_UNIT; T.pins[1] = ME_C_ANGLE; T.pins[2] = ME_C_64_LN2; T.pins[3] = 0.0; }
 }
@@ -76,33 +74,47 @@ __device__ __forceinline__ Pins load_pins(const MathTables &T) {
     return c;
 }
 
-/* -2 ln(u), u in [2^-53, 1).  u = 2^e m, m in [1,2); interval i = top 7 mantissa bits; r = m rc_i - 1 in
- * [-2^-7, 2^-24]; ln m = l_i + ln2 [i >= 53] + log1p(r) with the mantissa range folded to [0.71, 1.42) so that
+/* -2 ln(u), u in [2^-53, 1).  u = 2^e m, m in [1,2); interval i = top 10 mantissa bits; r = m rc_i - 1 in
+ * [-2^-10, 2^-24]; ln m = l_i + ln2 [i >= 424] + log1p(r) with the mantissa range folded to [0.71, 1.42) so that
  * u -> 1 keeps full relative accuracy (top interval has rc = 1/2, l = 0 exactly).  The fold is an integer carry:
- * adding 75 to the 7-bit interval field of the high word overflows into the exponent field exactly when i >= 53.
- * The result is > 0 for every u < 1 (|.| only clears a sign that rounding could set for u within 2^-50 of 1). */
-__device__ __forceinline__ double neg2log_unit(double u, const MathTables &T) {
+ * adding 600 to the 10-bit interval field of the high word overflows into the exponent field exactly when i >= 424.
+ * The result is > 0 for every u < 1 (|.| only clears a sign that rounding could set for u within 2^-50 of 1).
+ * Max error 1.5 ulp (checked against long-double log over 2e7 arguments incl. u -> 1 and u -> 2^-53). */
+/* Where the log table is read from: global memory through the read-only path (small shapes: one-warp CTAs that live for
+ * one work item), or a per-CTA copy in shared memory (larger shapes: few, long-lived CTAs with two warps per
+ * sub-partition, where the shorter LDS latency matters). */
+struct LogTabGlobal {
+    const double2 *base;
+    __device__ __forceinline__ double2 at(unsigned byte_off) const {
+        return __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(base) + byte_off));
+    }
+};
+struct LogTabShared {
+    const double2 *base;          /* points into a __shared__ array */
+    __device__ __forceinline__ double2 at(unsigned byte_off) const {
+        return *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(base) + byte_off);
+    }
+};
+
+template <class Tab>
+__device__ __forceinline__ double neg2log_unit(double u, const Tab &logtab) {
     const int hi = __double2hiint(u), lo = __double2loint(u);
-    const int i = (hi >> 13) & 127;
+    /* {rc, -2 l}; byte offset added as a 32-bit quantity (a 64-bit index would be scaled with IMAD.WIDE on the pipe the
+       Philox rounds need) */
+    const double2 e = logtab.at((unsigned)((hi >> 6) & ((ME_LOGTAB_ENTRIES - 1) << 4)));
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    /* n = 1023 - (biased exponent + [i >= 53]) >= 0: minus the exponent of the folded mantissa, as one subtract+shift */
+    /* n = 1023 - (biased exponent + [i >= 424]) >= 0: minus the exponent of the folded mantissa, as one subtract+shift */
     const int n = (int)((unsigned)(0x3ff69fff - hi) >> 20);
-    const double rc = T.logt[i][0], l2 = T.logt[i][1];
-    const double r = fma(m, rc, -1.0);
-    /* log1p(r) = r - r^2/2 + r^3/3 - ... - r^8/8 ; |r| <= 2^-7 -> truncation below 2^-66.  Horner on purpose:
-       the Estrin forms of this and of the sin/cos/exp polynomials (dependency depth 4 instead of 8) were measured
-       and are NOT faster here (7.3e10 vs 7.6e10 chain-steps/s, 164 instead of 114 registers uncapped). */
-    double p = fma(r, -0.125, me_kc[0]);
-    p = fma(r, p, me_kc[1]);
-    p = fma(r, p, me_kc[2]);
-    p = fma(r, p, -0.25);
+    const double r = fma(m, e.x, -1.0);
+    /* log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5 ; |r| <= 2^-10 -> truncation r^6/6 < 2^-62 */
+    double p = fma(r, 0.2, -0.25);
     p = fma(r, p, me_kc[3]);
     p = fma(r, p, -0.5);
     p = fma(r * r, p, r);
     const double nd = __hiloint2double(0x43300000, n) - 4503599627370496.0;              /* (double)n */
     /* -2 ln u = n (2 ln2_hi) + (-2 l + -2 (p - n ln2_lo)) */
     const double q = fma(nd, me_kc[5], p);                         /* -ln2_lo */
-    const double t = fma(q, -2.0, l2);
+    const double t = fma(q, -2.0, e.y);
     const double w = fma(nd, ME_C_2LN2HI, t);                      /* exact product (11 x 21 bits) */
     return __hiloint2double(__double2hiint(w) & 0x7fffffff, __double2loint(w));
 }
