@@ -336,6 +336,14 @@ def run_ours(args):
     chain_steps_per_pass = chains * world * M * spm
     value = chain_steps_per_pass * args.steps / (ms_total * 1e-3)
     ker_ms = sum(a.elapsed_time(b) for a, b in ker_ev) / len(ker_ev)
+    # per-rank view of the timed region (a straggler GPU — e.g. one that is power-capped when all eight run FP64 flat
+    # out — sets the job's time through the per-step all-reduce): kernel time and clocks of every rank
+    rank_view = None
+    if world > 1:
+        mine = {"rank": rank, "kernel_ms": ker_ms, "clocks": clocks.summary()}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        rank_view = gathered
 
     # ---- e2e: public API with host buffers, copies inside the timed region
     pin_r = torch.zeros((chains, n_r), dtype=torch.float64).pin_memory() if n_r else None
@@ -460,6 +468,7 @@ def run_ours(args):
                      "hbm": {"achieved": ts_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ts_gbs / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}},
         "clocks": clocks.summary(),
+        "ranks": rank_view,
         "check": {"acceptance_rate": acc_rate, "pooled_var_x0": float(ps["cov_real"][0, 0]) if n_r else None},
         "ess": {"g_steps": g_steps, "ess_per_sec": value / g_steps if g_steps else None,
                 "how": "statistical inefficiency per step (pymbar's definition, worst coordinate, median of 1024 "
