@@ -42,7 +42,7 @@ WORKLOADS = {
                measures=10000, spm=10, flop=20, sf=5, fp64_inst=59.0, wide_inst=18.0),
     "c3": dict(name="mixed 3 real + 4 complex (bounded demo-style well), T=0.1, 262,144 chains, measure every 10",
                energy=("mixed_well", 1.0, -1.0, 0.5, 1.0), n_r=3, n_c=4, temp=0.1, chains=262144, measures=100, spm=10,
-               flop=170, sf=23, fp64_inst=327.0, wide_inst=91.0),
+               flop=170, sf=23, fp64_inst=328.0, wide_inst=94.0),
 }
 
 

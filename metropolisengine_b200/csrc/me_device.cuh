@@ -25,8 +25,15 @@
 #include "me_math.cuh"
 
 #define ME_MAX_BLOCK 256
+#ifndef ME_PAIR_BIG
+#define ME_PAIR_BIG 0          /* shapes with D > 4: 1 = process the steps in pairs too (see run_body) */
+#endif
 #ifndef ME_BIG_LOOKAHEAD
-#define ME_BIG_LOOKAHEAD 1     /* shapes with D > 4: generate the draws of step s+1 during step s (costs D+2 doubles of registers) */
+#define ME_BIG_LOOKAHEAD 0     /* shapes with D > 4: 1 = generate the draws of step s+1 during step s (costs D+2 doubles of
+                                  registers).  Measured on the 3r+4c shape, 262,144 chains: pairs + look-ahead 1.51e10,
+                                  single steps + look-ahead 1.55e10, single steps without look-ahead 1.70e10 chain-steps/s
+                                  (ceil(D/2) independent generator calls per step already give the warp its ILP; the
+                                  27 KB pair-unrolled loop stalls on instruction fetch) */
 #endif
 #define ME_FULL 0xffffffffu
 #define ME_SEG_MAX_D 4         /* shapes up to this D = n_real + 2 n_complex support work-queue time segmentation */
@@ -819,13 +826,22 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
         /* steps in pairs so that the two draw buffers swap roles by name instead of by register moves */
         Draws<L> nxt;
         unsigned k = 0;
-        for (; k + 1 < spm; k += 2) {
-            one_step(g, cur, nxt, raw_a, raw_b);
-            one_step(g, nxt, cur, raw_b, raw_a);
-        }
-        if (k < spm) {
-            one_step(g, cur, nxt, raw_a, raw_b);
-            if (!inject) { cur = nxt; if (DEEP) raw_a = raw_b; }
+        if (ME_PAIR_BIG || DEEP) {
+            for (; k + 1 < spm; k += 2) {
+                one_step(g, cur, nxt, raw_a, raw_b);
+                one_step(g, nxt, cur, raw_b, raw_a);
+            }
+            if (k < spm) {
+                one_step(g, cur, nxt, raw_a, raw_b);
+                if (!inject) { cur = nxt; if (DEEP) raw_a = raw_b; }
+            }
+        } else {
+            /* larger shapes: one step per iteration (the pair-unrolled loop of a 3r+4c shape is 27 KB of code) */
+#pragma unroll 1
+            for (; k < spm; k++) {
+                one_step(g, cur, nxt, raw_a, raw_b);
+                if (!inject && AHEAD) cur = nxt;
+            }
         }
         if (p.do_measure) {
             n += 1;
