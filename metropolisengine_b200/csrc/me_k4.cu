@@ -53,6 +53,7 @@ struct K4Params {
     unsigned rk[20];
     unsigned long long step0;
     long long n_steps;
+    long long chains_per_cta;      /* step kernel: contiguous chains per CTA (a multiple of 32) */
     long long n_meas;              /* measure_step_counter (for the Robbins-Monro gain) */
     double temp, inv_temp, target, ratio;
     int m;
@@ -263,19 +264,28 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
     if (!(f > 200.0)) f = 200.0;
     const double g_up = p.ratio * (1 - p.target) / f, g_down = p.ratio * p.target / f;
 
-    const long long n_tiles = p.n_chains / K4_TILE;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long ch = tile * K4_TILE + m;
+    /* Each CTA owns a contiguous range of chains (a multiple of 32) and walks it in tiles of up to 128: 32,768 chains on
+       147 CTAs are 224 chains each = one full tile and one with 96 active rows, whose fourth row of warps skips the
+       generator and the epilogues (1.75 tile-times instead of the 2 that whole tiles dealt round-robin cost).  The MMA
+       always runs M = 128; the accumulator rows of inactive chains are never read. */
+    const long long range_lo = (long long)blockIdx.x * p.chains_per_cta;
+    const long long range_hi = range_lo + p.chains_per_cta < p.n_chains ? range_lo + p.chains_per_cta : p.n_chains;
+    for (long long base = range_lo; base < range_hi; base += K4_TILE) {
+        const int cnt = (int)(range_hi - base < K4_TILE ? range_hi - base : K4_TILE);      /* multiple of 32 */
+        const bool act = m < cnt;                                                          /* warp-uniform */
+        const long long ch = act ? base + m : base;
         const unsigned long long gch = p.chain_offset + (unsigned long long)ch;
         const unsigned c0 = (unsigned)gch, c1 = (unsigned)(gch >> 32);
         /* load the tile's state */
+        if (act) {
 #pragma unroll 4
-        for (int jj = 0; jj < 16; jj++) {
-            const int j = 16 * g + jj;
-            S.xs[2 * j][m] = p.state[(long long)(K4_X + 1 + j) * ld + ch];
-            S.xs[2 * j + 1][m] = p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch];
+            for (int jj = 0; jj < 16; jj++) {
+                const int j = 16 * g + jj;
+                S.xs[2 * j][m] = p.state[(long long)(K4_X + 1 + j) * ld + ch];
+                S.xs[2 * j + 1][m] = p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch];
+            }
         }
-        if (g == 0) {
+        if (g == 0 && act) {
             S.a_s[m] = p.state[(long long)K4_X * ld + ch];
             S.e_s[m] = p.state[(long long)K4_E * ld + ch];
             S.sig_s[m] = p.state[(long long)K4_SIG * ld + ch];
@@ -289,6 +299,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
             const unsigned step = (unsigned)(p.step0 + (unsigned long long)s);
             /* ---- Z tile: 32 normals per thread, BF16, canonical K-major layout (16-byte chunk kc of row m at
                     kc*2048 + m*16: consecutive lanes write consecutive 16 B) */
+            if (act) {
             float dz[32];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -312,7 +323,8 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
                 for (int k = 0; k < 32; k++)
                     p.dbg_z[(long long)(32 * g + k) * ld + ch] = __bfloat162float(__float2bfloat16_rn(dz[k]));
             }
-            if (g == 0) {            /* draws of the real parameter and of the accept test */
+            }
+            if (g == 0 && act) {     /* draws of the real parameter and of the accept test */
                 const U4 r = philox(c0, c1, step, 32u, p.rk);
                 float za, zb;
                 normal_pair_f32(r.x, za, zb);
@@ -340,9 +352,9 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
 
             /* ---- epilogue 1: thread (m, g) owns 32 increments of chain m; partial energy statistics */
             uint32_t raw[32];
-            tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(32 * g), raw);
+            if (act) tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(32 * g), raw);
             tc_fence_before();
-            if (p.dbg_delta != nullptr && s == 0) {
+            if (act && p.dbg_delta != nullptr && s == 0) {
 #pragma unroll
                 for (int k = 0; k < 32; k++) p.dbg_delta[(long long)(32 * g + k) * ld + ch] = __uint_as_float(raw[k]);
             }
@@ -350,6 +362,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
             /* sum_j q_j^2 |c_j|^2 with q_j = q0 + jj: three sums with compile-time weights (1, jj, jj^2) and one
                combination per thread — no integer->double conversion per mode (XU pipe) */
             double tot = 0.0, t1 = 0.0, t2 = 0.0;
+            if (act) {
 #pragma unroll
             for (int jj = 0; jj < 16; jj++) {
                 const int j = 16 * g + jj;
@@ -362,10 +375,11 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
             }
             S.part[g][0][m] = tot;
             S.part[g][1][m] = fma(q0 * q0, tot, fma(2.0 * q0, t1, t2));
+            }
             __syncthreads();
 
             /* ---- decision (one thread per chain): ME:247-258 */
-            if (g == 0) {
+            if (g == 0 && act) {
                 const double t_all = (S.part[0][0][m] + S.part[1][0][m]) + (S.part[2][0][m] + S.part[3][0][m]);
                 const double q_all = (S.part[0][1][m] + S.part[1][1][m]) + (S.part[2][1][m] + S.part[3][1][m]);
                 const double a_new = fma(sig * s_a, S.za_s[m], S.a_s[m]);
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
             __syncthreads();
 
             /* ---- epilogue 2: accepted chains take the increments (still in registers) */
-            if (S.acc_s[m]) {
+            if (act && S.acc_s[m]) {
 #pragma unroll
                 for (int jj = 0; jj < 16; jj++) {
                     const int j = 16 * g + jj;
@@ -399,13 +413,15 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
 
         /* store the tile's state */
         __syncthreads();
+        if (act) {
 #pragma unroll 4
-        for (int jj = 0; jj < 16; jj++) {
-            const int j = 16 * g + jj;
-            p.state[(long long)(K4_X + 1 + j) * ld + ch] = S.xs[2 * j][m];
-            p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch] = S.xs[2 * j + 1][m];
+            for (int jj = 0; jj < 16; jj++) {
+                const int j = 16 * g + jj;
+                p.state[(long long)(K4_X + 1 + j) * ld + ch] = S.xs[2 * j][m];
+                p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch] = S.xs[2 * j + 1][m];
+            }
         }
-        if (g == 0) {
+        if (g == 0 && act) {
             p.state[(long long)K4_X * ld + ch] = S.a_s[m];
             p.state[(long long)K4_E * ld + ch] = S.e_s[m];
             p.state[(long long)K4_SIG * ld + ch] = S.sig_s[m];
@@ -851,9 +867,11 @@ int me_k4_step(me_k4 *e, int64_t n_steps, const double *s_a, float *dbg_z, float
         attr_set = (ce == cudaSuccess);
     }
     if (ce == cudaSuccess) {
-        const long long n_tiles = e->cfg.n_chains / K4_TILE;
         const int avail = e->n_sm - e->reserved_sms > 0 ? e->n_sm - e->reserved_sms : 1;
-        const int grid = (int)(n_tiles < avail ? n_tiles : avail);
+        long long per = (e->cfg.n_chains + avail - 1) / avail;
+        per = (per + 31) / 32 * 32;
+        p.chains_per_cta = per;
+        const int grid = (int)((e->cfg.n_chains + per - 1) / per);
         k4_steps<<<grid, K4_THREADS, sizeof(K4Smem), (cudaStream_t)stream>>>(p);
         ce = cudaGetLastError();
     }
