@@ -314,7 +314,8 @@ def run_ours(args):
     ker_ev = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
-        ev0.record(stream)
+        barrier()          # the sampler's NVML start-up takes milliseconds and differs per process: line the ranks up
+        ev0.record(stream) # again so that no rank's timed region contains another rank's start-up
         for _ in range(args.steps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             eng.clear_time_series(keep_storage=True)
@@ -525,6 +526,7 @@ def run_c4(args):
     l0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        barrier()          # see run_ours: the sampler's start-up must not leak into another rank's timed region
         ev0.record(stream)
         for _ in range(args.steps):
             eng.run(M, spm)
