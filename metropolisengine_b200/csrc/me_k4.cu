@@ -223,7 +223,7 @@ struct K4Smem {
     alignas(1024) unsigned char zs[K4_TILE * K4_N * 2];   /* A operand (normals), BF16           32 KB */
     alignas(1024) unsigned char ls[K4_N * K4_N * 2];      /* B operand (factor), BF16            32 KB */
     double part[4][2][K4_TILE];
-    double a_s[K4_TILE], e_s[K4_TILE], sig_s[K4_TILE], za_s[K4_TILE], u_s[K4_TILE], nacc_s[K4_TILE];
+    double a_s[K4_TILE], e_s[K4_TILE], sig_s[K4_TILE], za_s[2][K4_TILE], u_s[2][K4_TILE], nacc_s[K4_TILE];
     int acc_s[K4_TILE];
     int status_s[K4_TILE];
     me::MathTables tables;
@@ -295,46 +295,45 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
         }
         __syncthreads();
 
-        for (long long s = 0; s < p.n_steps; s++) {
-            const unsigned step = (unsigned)(p.step0 + (unsigned long long)s);
-            /* ---- Z tile: 32 normals per thread, BF16, canonical K-major layout (16-byte chunk kc of row m at
-                    kc*2048 + m*16: consecutive lanes write consecutive 16 B) */
+        /* One step = generator (Z tile + scalars) -> MMA -> epilogue 1 (energy statistics) -> decision -> epilogue 2.
+           The phases are skewed so that the pipes overlap: the Z tile of step s+1 is generated right after the MMA of
+           step s has finished with the operand buffer — in the same barrier interval as epilogue 1 of step s, so the
+           integer-heavy generator and the FP64-heavy epilogue of different warps run side by side — and the MMA of step
+           s+1 is issued before the decision and epilogue 2 of step s, which hide its latency.  Two barriers per step. */
+        auto generate = [&](unsigned step, int slot, bool first) {
             if (act) {
-            float dz[32];
+                /* Z tile: 32 normals per thread, BF16, canonical K-major layout (16-byte chunk kc of row m at
+                   kc*2048 + m*16: consecutive lanes write consecutive 16 B); one Philox call = 8 normals = one chunk */
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const U4 r = philox(c0, c1, step, (unsigned)(4 * g + i), p.rk);
-                normal_pair_f32(r.x, dz[8 * i], dz[8 * i + 1]);
-                normal_pair_f32(r.y, dz[8 * i + 2], dz[8 * i + 3]);
-                normal_pair_f32(r.z, dz[8 * i + 4], dz[8 * i + 5]);
-                normal_pair_f32(r.w, dz[8 * i + 6], dz[8 * i + 7]);
-            }
+                for (int i = 0; i < 4; i++) {
+                    float dz[8];
+                    const U4 r = philox(c0, c1, step, (unsigned)(4 * g + i), p.rk);
+                    normal_pair_f32(r.x, dz[0], dz[1]);
+                    normal_pair_f32(r.y, dz[2], dz[3]);
+                    normal_pair_f32(r.z, dz[4], dz[5]);
+                    normal_pair_f32(r.w, dz[6], dz[7]);
+                    uint4 v;
+                    v.x = pack_bf16(dz[0], dz[1]);
+                    v.y = pack_bf16(dz[2], dz[3]);
+                    v.z = pack_bf16(dz[4], dz[5]);
+                    v.w = pack_bf16(dz[6], dz[7]);
+                    *reinterpret_cast<uint4 *>(S.zs + (4 * g + i) * 2048 + m * 16) = v;
+                    if (first && p.dbg_z != nullptr) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint4 v;
-                v.x = pack_bf16(dz[8 * c], dz[8 * c + 1]);
-                v.y = pack_bf16(dz[8 * c + 2], dz[8 * c + 3]);
-                v.z = pack_bf16(dz[8 * c + 4], dz[8 * c + 5]);
-                v.w = pack_bf16(dz[8 * c + 6], dz[8 * c + 7]);
-                *reinterpret_cast<uint4 *>(S.zs + (4 * g + c) * 2048 + m * 16) = v;
+                        for (int k = 0; k < 8; k++)
+                            p.dbg_z[(long long)(32 * g + 8 * i + k) * ld + ch] = __bfloat162float(__float2bfloat16_rn(dz[k]));
+                    }
+                }
+                if (g == 0) {        /* draws of the real parameter and of the accept test */
+                    const U4 r = philox(c0, c1, step, 32u, p.rk);
+                    float za, zb;
+                    normal_pair_f32(r.x, za, zb);
+                    S.za_s[slot][m] = (double)za;
+                    S.u_s[slot][m] = u53(r.z, r.w);
+                }
             }
-            if (p.dbg_z != nullptr && s == 0) {
-#pragma unroll
-                for (int k = 0; k < 32; k++)
-                    p.dbg_z[(long long)(32 * g + k) * ld + ch] = __bfloat162float(__float2bfloat16_rn(dz[k]));
-            }
-            }
-            if (g == 0 && act) {     /* draws of the real parameter and of the accept test */
-                const U4 r = philox(c0, c1, step, 32u, p.rk);
-                float za, zb;
-                normal_pair_f32(r.x, za, zb);
-                S.za_s[m] = (double)za;
-                S.u_s[m] = u53(r.z, r.w);
-            }
-            fence_async_smem();          /* generic-proxy stores -> visible to the tensor-core (async) proxy */
-            __syncthreads();
-
-            /* ---- Delta = Z . B^T on the tensor cores: 8 x (M128 N128 K16), accumulator in TMEM */
+        };
+        auto issue_mma = [&]() {     /* Delta = Z . B^T on the tensor cores: 8 x (M128 N128 K16), accumulator in TMEM */
             if (warp == 0) {
                 tc_fence_after();
                 if (lane == 0) {
@@ -346,6 +345,16 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
                 }
                 __syncwarp();
             }
+        };
+        if (p.n_steps > 0) {
+            generate((unsigned)p.step0, 0, true);
+            fence_async_smem();          /* generic-proxy stores -> visible to the tensor-core (async) proxy */
+            __syncthreads();
+            issue_mma();
+        }
+        for (long long s = 0; s < p.n_steps; s++) {
+            const unsigned step = (unsigned)(p.step0 + (unsigned long long)s);
+            const int slot = (int)(s & 1);
             mbar_wait(&S.mbar, parity);
             parity ^= 1u;
             tc_fence_after();
@@ -354,6 +363,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
             uint32_t raw[32];
             if (act) tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(32 * g), raw);
             tc_fence_before();
+            if (s + 1 < p.n_steps) generate(step + 1u, slot ^ 1, false);     /* the MMA is done with the operand buffer */
             if (act && p.dbg_delta != nullptr && s == 0) {
 #pragma unroll
                 for (int k = 0; k < 32; k++) p.dbg_delta[(long long)(32 * g + k) * ld + ch] = __uint_as_float(raw[k]);
@@ -361,28 +371,30 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
             const double sig = S.sig_s[m];
             /* sum_j q_j^2 |c_j|^2 with q_j = q0 + jj: three sums with compile-time weights (1, jj, jj^2) and one
                combination per thread — no integer->double conversion per mode (XU pipe) */
-            double tot = 0.0, t1 = 0.0, t2 = 0.0;
             if (act) {
+                double tot = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll
-            for (int jj = 0; jj < 16; jj++) {
-                const int j = 16 * g + jj;
-                const double re = fma(sig, f32_bits_to_f64(raw[2 * jj]), S.xs[2 * j][m]);
-                const double im = fma(sig, f32_bits_to_f64(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
-                const double m2 = fma(re, re, im * im);
-                tot += m2;
-                t1 = fma((double)jj, m2, t1);
-                t2 = fma((double)(jj * jj), m2, t2);
+                for (int jj = 0; jj < 16; jj++) {
+                    const int j = 16 * g + jj;
+                    const double re = fma(sig, f32_bits_to_f64(raw[2 * jj]), S.xs[2 * j][m]);
+                    const double im = fma(sig, f32_bits_to_f64(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
+                    const double m2 = fma(re, re, im * im);
+                    tot += m2;
+                    t1 = fma((double)jj, m2, t1);
+                    t2 = fma((double)(jj * jj), m2, t2);
+                }
+                S.part[g][0][m] = tot;
+                S.part[g][1][m] = fma(q0 * q0, tot, fma(2.0 * q0, t1, t2));
             }
-            S.part[g][0][m] = tot;
-            S.part[g][1][m] = fma(q0 * q0, tot, fma(2.0 * q0, t1, t2));
-            }
-            __syncthreads();
+            fence_async_smem();
+            __syncthreads();             /* A: statistics ready, next Z tile visible, accumulator read by everyone */
+            if (s + 1 < p.n_steps) issue_mma();
 
             /* ---- decision (one thread per chain): ME:247-258 */
             if (g == 0 && act) {
                 const double t_all = (S.part[0][0][m] + S.part[1][0][m]) + (S.part[2][0][m] + S.part[3][0][m]);
                 const double q_all = (S.part[0][1][m] + S.part[1][1][m]) + (S.part[2][1][m] + S.part[3][1][m]);
-                const double a_new = fma(sig * s_a, S.za_s[m], S.a_s[m]);
+                const double a_new = fma(sig * s_a, S.za_s[slot][m], S.a_s[m]);
                 bool accept = false;
                 const bool wall = p.use_wall && fabs(a_new) >= 1.0;
                 if (!wall) {
@@ -390,7 +402,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
                     if (e_new != e_new) S.status_s[m] |= ME_STATUS_ENERGY_NAN;
                     const double diff = e_new - S.e_s[m];
                     const double prob = me::exp_nonpos(fmin(-diff * p.inv_temp, 0.0), S.tables);
-                    accept = (diff <= 0) | ((p.temp != 0) & (S.u_s[m] <= prob));
+                    accept = (diff <= 0) | ((p.temp != 0) & (S.u_s[slot][m] <= prob));
                     if (accept) { S.e_s[m] = e_new; S.a_s[m] = a_new; S.nacc_s[m] += 1.0; }
                 }
                 const double sg = accept ? fma(sig, g_up, sig) : fma(sig, -g_down, sig);
@@ -398,7 +410,7 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
                 if (!(sg > 0)) S.status_s[m] |= ME_STATUS_SIGMA_NONPOS;
                 S.acc_s[m] = accept ? 1 : 0;
             }
-            __syncthreads();
+            __syncthreads();             /* B */
 
             /* ---- epilogue 2: accepted chains take the increments (still in registers) */
             if (act && S.acc_s[m]) {
