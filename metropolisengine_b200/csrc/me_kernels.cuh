@@ -15,13 +15,15 @@ struct Cfg {
     using Energy = EnergyT<NR_, NC_>;
 };
 
-/* Small problems (D <= 4) are capped at 144 registers: 65,536 chains in CTAs of 32 are 14 warps per SM, which must all
- * be resident in one wave (14 x 32 x 144 = 64,512 of the SM's 65,536 registers).  Below ~140 ptxas starts to
- * re-materialise loop invariants (Philox counter words, polynomial constants) inside the step loop. */
+/* Small problems (D <= 4) are capped at 160 registers.  The register file holds one-warp CTAs in steps: 16 per SM up to
+ * 128 registers per thread, 12 from 129 to 160, 10 beyond; three warps per SM sub-partition (12 per SM) already saturate
+ * its pipes, and below ~140 registers ptxas starts to re-materialise loop invariants (Philox counter words, polynomial
+ * constants) inside the step loop.  Ensembles that do not fill whole waves of those 12 x 148 slots are balanced by the
+ * work-queue time segmentation of run_body. */
 template <class C, bool SMALL = (C::NR + 2 * C::NC <= 4)>
 struct RunKernel;
 template <class C>
-__global__ void __maxnreg__(144) k_run_small(const __grid_constant__ MeParams p) {
+__global__ void __maxnreg__(160) k_run_small(const __grid_constant__ MeParams p) {
     run_body<C>(p);
 }
 #ifdef ME_BIG_MAXNREG
