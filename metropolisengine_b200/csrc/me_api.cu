@@ -165,7 +165,12 @@ int nvrtc_compile(int n_real, int n_complex, int energy_id, const std::string &u
         src += "};\n}\n";
     }
     src += std::string("typedef me::Cfg<ME_NR, ME_NC, ") + tmpl + ", (ME_STRICT != 0)> UserCfg;\n";
-    src += "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_run(const __grid_constant__ MeParams p) { me::run_body<UserCfg>(p); }\n"
+    /* same register policy as the ahead-of-time kernels (me_kernels.cuh): small shapes at most 160 registers */
+    src += "#if ME_NR + 2 * ME_NC <= 4\n"
+           "extern \"C\" __global__ void __maxnreg__(160) me_k_run(const __grid_constant__ MeParams p) { me::run_body<UserCfg>(p); }\n"
+           "#else\n"
+           "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_run(const __grid_constant__ MeParams p) { me::run_body<UserCfg>(p); }\n"
+           "#endif\n"
            "#if ME_NC > 0\n"
            "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_run_mp(const __grid_constant__ MeParams p) { me::run_body<UserCfg, true>(p); }\n"
            "#endif\n"

@@ -98,6 +98,10 @@ __device__ bool me_user_reject(const double* x, const double* cr, const double* 
     for strict in (False, True):
         ok, log = lib.check_energy_source(src, 1, 3, use_reject=True, strict=strict)
         assert ok, log
+    # small shape (D <= 4): compiled under the 160-register cap of the ahead-of-time small kernels
+    src2 = "__device__ double me_user_energy(const double* x, const double* cr, const double* ci, const double* k) { return k[0] * (x[0] * x[0] + x[1] * x[1]); }"
+    ok, log = lib.check_energy_source(src2, 2, 0, use_reject=False, strict=False)
+    assert ok, log
     ok, log = lib.check_energy_source("__device__ double me_user_energy(const double* x) { return 0; }", 1, 0)
     assert not ok and "me_user_energy" in log
     # shapes that are not instantiated ahead of time compile at run time too (built-in functor, arbitrary shape)
