@@ -231,7 +231,6 @@ struct me_engine {
     unsigned long long *seg_flags = nullptr;   /* work queue (tickets, pushes, ring) followed by its initial image; device
                                                   memory owned by the handle */
     unsigned long long seg_base = 0;           /* ring capacity */
-    int seg_workers = 0;                       /* CTAs of a segmented launch */
     int run_slots = -1;                        /* CTAs of the fused kernel resident on the device at once (-1: unknown) */
     const double *logtab = nullptr;            /* me_math.cuh log table on this engine's device */
     std::string err;
