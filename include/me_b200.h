@@ -117,6 +117,13 @@ int me_set_energy_external(me_engine *eng);
 int me_check_energy_source(const char *cuda_source, int32_t n_real, int32_t n_complex, int32_t use_reject,
                            int32_t strict, char *log, int64_t log_cap);
 
+/* CUDA-graph replay of the unfused step (me_propose -> caller's energy -> me_accept).  Kernel parameters are frozen
+ * when a graph is captured, so with enable != 0 the step index and the measure counter are read from a device copy
+ * that me_accept advances itself; the call (re)loads that copy from the handle's counters, so call it again before a
+ * replay whenever the handle's counters moved outside the graph (me_run measure, me_set_counters), and advance the
+ * handle's own counters with me_set_counters after a replay.  Fused shapes (D <= 32) only. */
+int me_device_counters(me_engine *eng, int32_t enable, void *stream);
+
 /* Group-wise stepping of mixed engines: subsequent me_run / me_run_injected / me_propose /
  * me_accept calls perform step_real_group (group 1, ME:225-239: only the real block is proposed, only
  * real_group_sampling_width adapts, ME:440-446) or step_complex_group (group 2, ME:209-223, ME:449-456) instead of

@@ -85,6 +85,7 @@ SIGNATURES = {
     "me_k4_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
     "me_k4_last_error": (_cp, [_vp]),
     "me_probe_fp64": (ctypes.c_int, [_i32, _i64, _vp, _i64, _vp, ctypes.POINTER(_i64)]),
+    "me_device_counters": (ctypes.c_int, [_vp, _i32, _vp]),
     "me_statistical_inefficiency": (ctypes.c_int, [_vp, _i64, _i64, _i32, _i64, _i32, _i64, _i64, _i64, _vp, _vp]),
     "me_detect_equilibration": (ctypes.c_int, [_vp, _i64, _i32, _i64, _i32, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp,
                                                _vp, _vp]),

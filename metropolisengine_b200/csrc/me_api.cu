@@ -233,6 +233,8 @@ struct me_engine {
     unsigned long long seg_base = 0;           /* ring capacity */
     int run_slots = -1;                        /* CTAs of the fused kernel resident on the device at once (-1: unknown) */
     const double *logtab = nullptr;            /* me_math.cuh log table on this engine's device */
+    unsigned long long *ctr_dev = nullptr;     /* device copy of (step, n_measure) for CUDA-graph replay of the unfused step */
+    bool use_ctr = false;
     std::string err;
 };
 
@@ -298,6 +300,7 @@ const double *log_table(int device) {
 void base_params(me_engine *e, MeParams &p) {
     memset(&p, 0, sizeof(p));
     p.logtab = e->logtab;
+    p.ctr_dev = e->use_ctr ? e->ctr_dev : nullptr;
     p.state = e->buf.state;
     p.ld = e->cfg.n_chains;
     p.n_chains = e->cfg.n_chains;
@@ -482,6 +485,12 @@ __global__ void __launch_bounds__(256) k_pool_reduce(double *pool, double *out, 
     if (t == 0) out[w] = part[0];
 }
 
+/* device copy of the step / measure counters (see MeParams::ctr_dev) */
+__global__ void k_ctr_set(unsigned long long *ctr, unsigned long long step, unsigned long long n_meas) {
+    ctr[0] = step; ctr[1] = n_meas;
+}
+__global__ void k_ctr_advance(unsigned long long *ctr, unsigned long long dstep) { ctr[0] += dstep; }
+
 /* FP64 FMA throughput probe: 8 independent dependent-FMA streams per thread.  The roofline denominator of the
  * step kernels (MEASURED_PEAKS.json carries HBM and bf16 figures only). */
 __global__ void __launch_bounds__(256) k_probe_fp64(double *out, long long iters) {
@@ -640,9 +649,10 @@ int me_create(const me_config *cfg, me_engine **out) {
 }
 
 int me_destroy(me_engine *e) {
-    if (e && e->seg_flags) {
+    if (e && (e->seg_flags || e->ctr_dev)) {
         DeviceGuard g(e->cfg.device);
-        cudaFree(e->seg_flags);
+        if (e->seg_flags) cudaFree(e->seg_flags);
+        if (e->ctr_dev) cudaFree(e->ctr_dev);
     }
     delete e;
     return ME_OK;
@@ -803,8 +813,30 @@ int me_accept(me_engine *e, const double *prop, const double *e_new, const unsig
     base_params(e, p);
     p.prop = const_cast<double *>(prop); p.e_new = e_new; p.rej = rej; p.inj_u = inj_u;
     int rc = launch(e, e->ks.accept, p, stream);
-    if (rc == ME_OK) e->step += 1;
+    if (rc == ME_OK) {
+        e->step += 1;
+        if (e->use_ctr) {           /* keeps the device counter in step, also when this call is replayed from a graph */
+            DeviceGuard g(e->cfg.device);
+            k_ctr_advance<<<1, 1, 0, (cudaStream_t)stream>>>(e->ctr_dev, 1ull);
+            if (cudaGetLastError() != cudaSuccess) return fail(e, ME_ERR_CUDA, "advancing the device counters failed");
+        }
+    }
     return rc;
+}
+
+int me_device_counters(me_engine *e, int32_t enable, void *stream) {
+    if (!e) return ME_ERR_INVALID;
+    if (e->generic) return fail(e, ME_ERR_UNSUPPORTED, "device counters serve the fused-shape unfused path (D <= 32)");
+    DeviceGuard g(e->cfg.device);
+    if (enable) {
+        if (!e->ctr_dev &&
+            cudaMallocAsync((void **)&e->ctr_dev, 2 * sizeof(unsigned long long), (cudaStream_t)stream) != cudaSuccess)
+            return fail(e, ME_ERR_CUDA, "allocating the device counters failed");
+        k_ctr_set<<<1, 1, 0, (cudaStream_t)stream>>>(e->ctr_dev, e->step, (unsigned long long)e->n_measure);
+        if (cudaGetLastError() != cudaSuccess) return fail(e, ME_ERR_CUDA, "setting the device counters failed");
+    }
+    e->use_ctr = enable != 0;
+    return ME_OK;
 }
 
 int me_energy_builtin(me_engine *e, const double *prop, double *e_out, unsigned char *rej_out, void *stream) {

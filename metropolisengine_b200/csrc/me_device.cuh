@@ -995,12 +995,13 @@ __device__ __forceinline__ void propose_body(const MeParams &p) {
     } else {
         const Rng rng(p, p.chain_offset + (unsigned long long)ch);
         Draws<L> d;
-        gen_draws<L, Cfg::STRICT, LogTabGlobal>(rng, (unsigned)p.step0, tables, d, load_pins(tables), 0.5 * p.temp,
+        const unsigned step = p.ctr_dev ? (unsigned)p.ctr_dev[0] : (unsigned)p.step0;
+        gen_draws<L, Cfg::STRICT, LogTabGlobal>(rng, step, tables, d, load_pins(tables), 0.5 * p.temp,
                                                 LogTabGlobal{reinterpret_cast<const double2 *>(p.logtab)});
         apply_proposal<L>(c, d.z, prop);
         if (L::NC > 0 && p.group >= 3) {
             if (p.group == 3) propose_magnitudes<L>(c, d.z, prop);
-            else propose_phases<L>(c, rng, (unsigned)p.step0, prop);
+            else propose_phases<L>(c, rng, step, prop);
         }
     }
     if (L::KIND == 0 && p.group != 0) {
@@ -1029,7 +1030,7 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
     const int sidx = grouped ? (p.group == 1 ? 0 : 1) : L::SIGIDX;
     double sg = st[(long long)(L::SIG + sidx) * ld + ch];
     int status = (int)st[(long long)L::STATUS * ld + ch];
-    const Gains g = make_gains(p.n_meas0, p);
+    const Gains g = make_gains(p.ctr_dev ? (long long)p.ctr_dev[1] : p.n_meas0, p);
     bool accept = false;
     const bool wall = p.rej != nullptr && p.rej[ch] != 0;
     if (!wall) {
@@ -1041,7 +1042,7 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
         else if (diff > 0 && p.temp != 0) {      /* regenerate the spare words of Philox calls 0 (and 1) */
             const Rng rng(p, p.chain_offset + (unsigned long long)ch);
             Spare sp;
-            Rng::keep_spare(rng.bits((unsigned)p.step0, 0u), 0, sp);
+            Rng::keep_spare(rng.bits(p.ctr_dev ? (unsigned)p.ctr_dev[0] : (unsigned)p.step0, 0u), 0, sp);
             u = STRICT ? Rng::accept_uniform(sp)
                        : Rng::accept_threshold(sp, LogTabGlobal{reinterpret_cast<const double2 *>(p.logtab)}, 0.5 * p.temp);
         }

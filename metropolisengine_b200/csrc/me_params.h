@@ -5,7 +5,7 @@
 #ifndef ME_PARAMS_H
 #define ME_PARAMS_H
 
-#define ME_PARAMS_VERSION 8
+#define ME_PARAMS_VERSION 9
 #define ME_MAX_CONSTS 16
 
 /* status bits written to the per-chain STATUS word (SURVEY §5 "failure detection") */
@@ -59,6 +59,9 @@ struct MeParams {
     unsigned char *rej_out;        /* [ld] gk_energy hard-wall output (may be NULL) */
     int group;                     /* mixed engines: 0 = step_all (ME:241), 1 = step_real_group (ME:225), 2 = step_complex_group (ME:209),
                                       3 / 4 = magnitude / phase half of the magnitude-phase complex move (ME:178-207) */
+    const unsigned long long *ctr_dev; /* unfused path under CUDA-graph replay: [0] index of the step, [1] measure counter,
+                                      read by k_propose / k_accept INSTEAD of step0 / n_meas0 (kernel parameters are
+                                      frozen at capture; NULL = use the parameters) */
     const double *logtab;          /* [1024][2] table of the table-driven log (me_math.cuh), device memory owned by the library */
     /* time segmentation of a launch with a work queue (me_device.cuh, run_body) */
     int seg_count;                 /* segments per chain group; <= 1: off */

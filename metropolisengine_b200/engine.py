@@ -81,6 +81,9 @@ class MetropolisEngine:
                       ([chains, n_params], default) or ``"params_first"`` ([n_params, chains], so reference-style
                       bodies such as ``real_params[0]**2`` vectorise unchanged)
     distributed       shard ``n_chains`` over the ranks of the default torch.distributed group
+    graph_callable    python energy callables only: capture the ``steps_per_measure`` steps between two measures
+                      (propose -> callable -> accept, each) in a CUDA graph on first use and replay it in ``run()``;
+                      the callable must then be capture-safe (static shapes, no host synchronisation)
     """
 
     def __init__(self, energy_functions, reject_condition=None, initial_real_params=None,
@@ -88,7 +91,7 @@ class MetropolisEngine:
                  covariance_matrix_complex=None, params_names=None, target_acceptance=.3, temp=0,
                  complex_sample_method="multivariate-gaussian", *, n_chains=1, seed=0, device=None, strict=False,
                  record=True, callable_layout="chains_first", distributed=False, ts_chunk_bytes=1 << 30,
-                 _shard=None):
+                 graph_callable=False, _shard=None):
         if initial_real_params is None and initial_complex_params is None:
             raise ValueError("must give a list containing at least one value for initial real or complex "
                              "parameters")                                                   # ME:37-39
@@ -104,6 +107,8 @@ class MetropolisEngine:
             raise RuntimeError("MetropolisEngine needs a CUDA device: the hot path is CUDA-only (no CPU fallback)")
         self._lib = _lib.load()
         self.launch_count = 0
+        self._graph_callable = bool(graph_callable)
+        self._graphs = {}               # steps per measure -> captured torch.cuda.CUDAGraph
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -398,9 +403,13 @@ class MetropolisEngine:
         if n_measures <= 0:
             return
         if self._callable is not None or self._generic:
+            graphed = self._graph_callable and self._callable is not None and not self._generic and steps_per_measure > 0
             for _ in range(n_measures):
-                for _ in range(steps_per_measure):
-                    self._step_external()
+                if graphed:
+                    self._replay_steps(steps_per_measure)
+                else:
+                    for _ in range(steps_per_measure):
+                        self._step_external()
                 self.measure()
             return
         if self.record:
@@ -517,6 +526,30 @@ class MetropolisEngine:
             e_new = self._eval_callable(prop)
         self._launch(self._lib.me_accept(self._h, _ptr(prop), _ptr(e_new), _ptr(rej), _ptr(inj_u), self._stream()))
         self.step_counter += 1 if self._kind == "complex" else 0
+
+    def _replay_steps(self, k):
+        """``k`` unfused steps as one CUDA-graph launch.  Kernel parameters are frozen at capture, so the step index
+        and the measure counter live in a device copy (``me_device_counters``) that the accept kernel advances; the
+        handle's own counters are moved by hand after each replay."""
+        n, s0 = ctypes.c_int64(), ctypes.c_uint64()
+        self._lib.me_get_counters(self._h, ctypes.byref(n), ctypes.byref(s0))
+        g = self._graphs.get(k)
+        if g is None:
+            self._check(self._lib.me_device_counters(self._h, 1, self._stream()))
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(k):
+                    self._step_external()                    # recorded, not executed
+            self._graphs[k] = g
+            self._check(self._lib.me_set_counters(self._h, n.value, s0.value))      # capture moved the host counters
+            self.step_counter -= k if self._kind == "complex" else 0
+        self._check(self._lib.me_device_counters(self._h, 1, self._stream()))         # device copy <- (step, n_measure)
+        g.replay()
+        self.launch_count += 1
+        self._check(self._lib.me_set_counters(self._h, n.value, s0.value + k))
+        self._check(self._lib.me_device_counters(self._h, 0, self._stream()))
+        self.step_counter += k if self._kind == "complex" else 0
 
     def measure(self):
         """Running means, covariance recursion, observable means and one time-series row (ME:342-427)."""

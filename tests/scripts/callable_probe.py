@@ -10,14 +10,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import metropolisengine_b200 as me
 
 n = 65536
-eng = me.MetropolisEngine(lambda r, c: (r * r).sum(dim=1), initial_real_params=np.zeros(2), temp=.1, n_chains=n, seed=3,
-                          record=False)
-eng.run(5, 10)
-torch.cuda.synchronize()
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-eng.run(50, 10)
-b.record()
-torch.cuda.synchronize()
-ms = a.elapsed_time(b)
-print("torch callable (3 launches + torch ops per step): %.3e chain-steps/s, %.1f us per ensemble step" % (n * 500 / ms * 1e3, ms * 1e3 / 500))
+for graph in (False, True):
+    eng = me.MetropolisEngine(lambda r, c: (r * r).sum(dim=1), initial_real_params=np.zeros(2), temp=.1, n_chains=n, seed=3,
+                              record=False, graph_callable=graph)
+    eng.run(5, 10)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    eng.run(50, 10)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    print("torch callable, graph_callable=%-5s: %.3e chain-steps/s, %.1f us per ensemble step"
+          % (graph, n * 500 / ms * 1e3, ms * 1e3 / 500))
