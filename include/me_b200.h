@@ -161,7 +161,10 @@ int me_init(me_engine *eng, const double *x0, int32_t x0_broadcast, double sigma
  *   measure    ME:342-427: running means, covariance recursion (+ refactorisation), observable means, and, when
  *              ts != NULL, one time-series row per chain at ts[((ts_row0 + block) * TS_COLS + col) * n_chains + chain]
  *              (the lists of ME:31-35,350-356).
- *   me_run(e, 1, k, 0, ...) is k plain step_all() calls; me_run(e, 1, 0, 1, ...) is one measure(). */
+ *   me_run(e, 1, k, 0, ...) is k plain step_all() calls; me_run(e, 1, 0, 1, ...) is one measure().
+ * Scheduling is internal and does not change results: when the ensemble is about one wave of CTAs the launch is cut
+ * into time segments per chain group served from a work queue (bit-identical to the plain launch; ME_SEGMENTS=1 in the
+ * environment switches it off).  The call is asynchronous on `stream`. */
 int me_run(me_engine *eng, int64_t n_blocks, int64_t steps_per_measure, int32_t do_measure, double *ts,
            int64_t ts_row0, void *stream);
 
