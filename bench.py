@@ -48,10 +48,10 @@ WORKLOADS = {
 
 def _ncu_traffic_per_chain_measure():
     """DRAM bytes per chain-measure of the step kernel from the committed ncu --set full capture
-    (profiles/r01_ncu_c2_k_run_v4.csv: a launch of 300 measures x 65,536 chains)."""
+    (profiles/r01_ncu_c2_k_run_v5.csv: a launch of 300 measures x 65,536 chains)."""
     try:
         rd = wr = None
-        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_c2_k_run_v4.csv")):
+        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_c2_k_run_v5.csv")):
             f = line.strip().split(",")
             if f[0] == "dram__bytes_read.sum":
                 rd = float(f[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[1]]
@@ -438,8 +438,8 @@ def run_ours(args):
             "bound_ms": pipe_bound_ms, "frac": pipe_bound_ms / ker_ms,
             "how": "FP64-pipe + FMA-heavy-pipe cycles the SASS of the step loop needs (2 per FP64 instruction, 3.5 per "
                    "IMAD.WIDE; the pipes contend) x average warps per SM sub-partition / measured kernel time",
-            "ncu": ("profiles/r01_ncu_c2_k_run_v4.csv: FP64 pipe 46 % + FMA-heavy pipe 42 % of elapsed cycles (the "
-                    "FMA-heavy pipe also runs the IMAD.MOV / IMAD.SHL the compiler uses as moves), issue slots 61 % busy"
+            "ncu": ("profiles/r01_ncu_c2_k_run_v5.csv: FP64 pipe 43 % + FMA-heavy pipe 45 % of elapsed cycles (the "
+                    "FMA-heavy pipe also runs the IMAD.MOV / IMAD.SHL the compiler uses as moves), issue slots 60 % busy"
                     if args.workload == "c2" else None)}
     line = {
         "metric": "ensemble chain-steps/sec", "value": value, "unit": "chain-steps/s", "n_gpus": world,
@@ -459,7 +459,7 @@ def run_ours(args):
                      "frac": achieved_tf / fp64_peak,
                      "traffic": (tpm * chains * M) if tpm else None,
                      "traffic_note": "DRAM read+write bytes per launch: per chain-measure figure of the committed ncu "
-                                     "--set full capture (profiles/r01_ncu_c2_k_run_v4.csv) x this launch's "
+                                     "--set full capture (profiles/r01_ncu_c2_k_run_v5.csv) x this launch's "
                                      "chain-measures; algorithmic %d B per chain-measure" % (8 * ts_cols),
                      "pipe": pipe,
                      "kernel": "me::k_run", "kernel_ms": ker_ms,
