@@ -233,6 +233,7 @@ struct me_engine {
     unsigned long long seg_base = 0;           /* ring capacity */
     int run_slots = -1;                        /* CTAs of the fused kernel resident on the device at once (-1: unknown) */
     const double *logtab = nullptr;            /* me_math.cuh log table on this engine's device */
+    double *pool_partial = nullptr;            /* first-stage rows of the pooled-moment reduction (large ensembles) */
     unsigned long long *ctr_dev = nullptr;     /* device copy of (step, n_measure) for CUDA-graph replay of the unfused step */
     bool use_ctr = false;
     std::string err;
@@ -485,6 +486,31 @@ __global__ void __launch_bounds__(256) k_pool_reduce(double *pool, double *out, 
     if (t == 0) out[w] = part[0];
 }
 
+/* First stage for very large ensembles (10^7-10^8 chains: millions of per-CTA moment rows).  The pool is read as the
+ * flat array it is: thread t of a CTA owns word (t % words) of row offset (t / words) inside a slab of `rpb` rows, so
+ * consecutive threads read consecutive doubles; the slabs of one CTA are `gridDim.x` slabs apart.  The per-thread sums
+ * are folded over the row offsets in fixed order, so the result depends on (grid, words, gridDim.x) only. */
+#define ME_POOL_STAGE_CTAS 592
+__global__ void __launch_bounds__(256) k_pool_partial(double *pool, double *partial, long long grid, int words, int reset) {
+    __shared__ double part[256];
+    const int rpb = 256 / words, t = threadIdx.x;
+    const int ro = t / words, w = t - ro * words;
+    double acc = 0.0;
+    if (ro < rpb) {
+        for (long long r = (long long)blockIdx.x * rpb + ro; r < grid; r += (long long)gridDim.x * rpb) {
+            acc += pool[r * words + w];
+            if (reset) pool[r * words + w] = 0.0;
+        }
+    }
+    part[t] = acc;
+    __syncthreads();
+    if (t < words) {
+        double a = part[t];
+        for (int k = 1; k < rpb; k++) a += part[k * words + t];
+        partial[(long long)blockIdx.x * words + t] = a;
+    }
+}
+
 /* device copy of the step / measure counters (see MeParams::ctr_dev) */
 __global__ void k_ctr_set(unsigned long long *ctr, unsigned long long step, unsigned long long n_meas) {
     ctr[0] = step; ctr[1] = n_meas;
@@ -649,10 +675,11 @@ int me_create(const me_config *cfg, me_engine **out) {
 }
 
 int me_destroy(me_engine *e) {
-    if (e && (e->seg_flags || e->ctr_dev)) {
+    if (e && (e->seg_flags || e->ctr_dev || e->pool_partial)) {
         DeviceGuard g(e->cfg.device);
         if (e->seg_flags) cudaFree(e->seg_flags);
         if (e->ctr_dev) cudaFree(e->ctr_dev);
+        if (e->pool_partial) cudaFree(e->pool_partial);
     }
     delete e;
     return ME_OK;
@@ -855,7 +882,19 @@ int me_pool_reduce(me_engine *e, double *out, int32_t reset, void *stream) {
     if (!e->bound || !e->buf.pool || e->lay.POOL_WORDS == 0) return fail(e, ME_ERR_STATE, "no pool buffer bound");
     DeviceGuard g(e->cfg.device);
     const int words = e->lay.POOL_WORDS;
-    k_pool_reduce<<<words, 256, 0, (cudaStream_t)stream>>>(e->buf.pool, out, e->grid, words, reset);
+    if (e->grid > 4096 && words <= 256) {
+        /* millions of rows: coalesced first stage into ME_POOL_STAGE_CTAS partial rows, then the fixed-order tree */
+        if (!e->pool_partial &&
+            cudaMalloc(&e->pool_partial, sizeof(double) * ME_POOL_STAGE_CTAS * words) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(e, ME_ERR_CUDA, "pool reduce: cannot allocate the partial-sum rows");
+        }
+        k_pool_partial<<<ME_POOL_STAGE_CTAS, 256, 0, (cudaStream_t)stream>>>(e->buf.pool, e->pool_partial, e->grid, words,
+                                                                           reset);
+        k_pool_reduce<<<words, 256, 0, (cudaStream_t)stream>>>(e->pool_partial, out, ME_POOL_STAGE_CTAS, words, 0);
+    } else {
+        k_pool_reduce<<<words, 256, 0, (cudaStream_t)stream>>>(e->buf.pool, out, e->grid, words, reset);
+    }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(e, ME_ERR_CUDA, std::string("pool reduce: ") + cudaGetErrorString(ce));
     return ME_OK;

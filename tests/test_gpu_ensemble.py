@@ -2,6 +2,8 @@
 (i) ensembles of the unmodified reference run as independent seeded processes (tests/golden/ensemble_*.npz,
 two-sample KS on per-chain end-of-run quantities and z-tests on their means) and (ii) exact facts about the
 stationary law exp(-E/T) (SURVEY §8c "pins available" (2)).  Tolerances are stated per assertion."""
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -164,6 +166,42 @@ def test_pooled_moments_mixed_shape_against_time_series():
     cov_c = cm.T @ cm.conj() / (c.shape[0] - 1)
     assert np.allclose(ps["cov_complex"], cov_c, rtol=1e-9, atol=1e-12)
     assert np.allclose(ps["observables_mean"][3:7], np.abs(c).mean(0), rtol=1e-10)
+
+
+@pytest.mark.parametrize("shape", ["real2", "mixed"])
+def test_pooled_moments_of_a_million_chain_ensemble_use_the_two_stage_reduction(shape):
+    """SURVEY §8(d) C5 sizes: beyond 4,096 CTAs of per-CTA moment rows the pooled reduction goes through a coalesced
+    first stage (k_pool_partial).  Its result must equal the moments recomputed from the stored rows, and two
+    reductions of the same rows must be bit-identical (fixed summation order)."""
+    import metropolisengine_b200 as me
+    n = 1_200_000 + 17                      # ragged: the last CTA is partial
+    if shape == "real2":
+        eng = me.MetropolisEngine(("xy_well", 1.0), initial_real_params=np.array([0.3, -0.2]), temp=.1, n_chains=n,
+                                  seed=11)
+        d = 2
+    else:
+        eng = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5), initial_real_params=np.zeros(3),
+                                  initial_complex_params=np.zeros(4, dtype=complex), temp=.1, n_chains=n, seed=11)
+        d = 11
+    assert eng._grid > 4096
+    eng.run(3, 4)
+    raw = []
+    for _ in range(2):                     # reset=0 reductions of the same rows
+        out = torch.zeros(eng._lay.POOL_WORDS, dtype=torch.float64, device=eng.device)
+        eng._launch(eng._lib.me_pool_reduce(eng._h, ctypes.c_void_p(out.data_ptr()), 0, eng._stream()))
+        raw.append(out.cpu().numpy())
+    assert np.array_equal(raw[0], raw[1])
+    ps = eng.pooled_statistics()
+    assert ps["count"] == 3 * n
+    ts = eng.time_series()
+    x = ts[:, :d, :].permute(0, 2, 1).reshape(-1, d).cpu().numpy()
+    nr = eng.num_real_params
+    assert np.allclose(ps["mean_real"], x[:, :nr].mean(0), rtol=0, atol=1e-12)
+    assert np.allclose(ps["cov_real"], np.cov(x[:, :nr].T), rtol=1e-9, atol=1e-13)
+    # a second reduction after the reset sees empty rows
+    out = torch.zeros(eng._lay.POOL_WORDS, dtype=torch.float64, device=eng.device)
+    eng._launch(eng._lib.me_pool_reduce(eng._h, ctypes.c_void_p(out.data_ptr()), 0, eng._stream()))
+    assert float(out.abs().max()) == 0.0
 
 
 def test_equilibration_detection_matches_oracle():
