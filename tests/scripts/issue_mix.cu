@@ -20,7 +20,8 @@ __global__ void mix(double *out, long long iters, long long *cycles) {
             if (i < NI) {
                 if (KIND == 0) { unsigned long long p = (unsigned long long)b[i] * 0xD2511F53u; b[i] = (unsigned)(p >> 32) + (unsigned)p; }
                 else if (KIND == 1) b[i] = (b[i] ^ 0x9E3779B9u) + (b[i] >> 3);          // LOP3 + SHF/IADD
-                else b[i] = b[i] * 0xCD9E8D57u + 12345u;                                // IMAD (32-bit)
+                else if (KIND == 2) b[i] = b[i] * 0xCD9E8D57u + 12345u;                 // IMAD (32-bit), affine: ptxas composes it
+                else b[i] = b[i] * b[i] + 12345u;                                       // IMAD (32-bit), quadratic: stays in the loop
             }
         }
     }
@@ -35,7 +36,7 @@ template <int ND, int NI, int KIND> void run(int warps_per_sm) {
     long long iters = 20000;
     for (int r = 0; r < 2; r++) { mix<ND, NI, KIND><<<148, 32 * warps_per_sm>>>(out, iters, cyc); cudaDeviceSynchronize(); }
     long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
-    const char *kn = KIND == 0 ? "IMAD.WIDE+IADD" : (KIND == 1 ? "LOP3+SHF+IADD" : "IMAD32");
+    const char *kn = KIND == 0 ? "IMAD.WIDE+IADD" : (KIND == 1 ? "LOP3+SHF+IADD" : (KIND == 2 ? "IMAD32" : "IMAD32 x*x+c"));
     printf("ND=%2d DFMA + NI=%2d %-15s warps/SM=%2d: %7.2f cycles/iter/warp -> %.2f cycles per SMSP-iteration\n", ND, NI, kn,
            warps_per_sm, (double)h / iters, (double)h / iters / (warps_per_sm / 4.0) );
     cudaFree(out); cudaFree(cyc);
@@ -45,5 +46,6 @@ int main() {
     run<0, 8, 0>(16); run<8, 8, 0>(16);
     run<0, 8, 1>(16); run<8, 8, 1>(16);
     run<8, 8, 2>(8); run<8, 8, 2>(12);
+    run<0, 16, 3>(16); run<8, 16, 3>(16); run<8, 8, 3>(16); run<8, 32, 3>(16); run<0, 32, 3>(16);
     return 0;
 }
