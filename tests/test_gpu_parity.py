@@ -463,6 +463,33 @@ def test_magnitude_phase_philox_matches_c_oracle():
     assert len(set(np.floor(ang / (np.pi / 2)).astype(int))) == 4
 
 
+def test_magnitude_phase_with_a_torch_callable_matches_the_device_functor():
+    """Magnitude / phase moves on the unfused propose / torch-callable / accept path (me_propose and me_accept with
+    groups 3 / 4) consume the same Philox words as the fused kernel: same decisions, same states."""
+    import metropolisengine_b200 as me
+    kw = dict(initial_real_params=np.array([0.3, 0.2, 0.1]), initial_complex_params=np.array([0.4 - 0.1j, -0.3 + 0.2j]),
+              temp=.1, sampling_width=0.6, complex_sample_method="magnitude-phase", n_chains=64, seed=5)
+
+    def energy(r, c):
+        a = (c * c.conj()).real
+        return ((1 - r) ** 2).sum(dim=1) + r[:, 0] * r[:, 1] * (-a + 0.5 * a * a).mean(dim=1)
+
+    engines = [me.MetropolisEngine(me.CudaEnergy(USER_SOURCES["warm_3r2c"]), **kw), me.MetropolisEngine(energy, **kw)]
+    for eng in engines:
+        for _ in range(54):
+            eng.step_real_group()
+            assert eng.step_complex_group() is None           # magnitude move + phase redraw (ME:168-176)
+            eng.step_complex_group_magnitude()
+            eng.measure()
+    a, b = engines
+    assert torch.equal(a.accept_count_per_chain, b.accept_count_per_chain)
+    assert int(a.accept_count_per_chain.sum()) > 0
+    assert torch.allclose(a.state, b.state, rtol=1e-10, atol=1e-13)
+    assert a.step_counter == b.step_counter
+    assert torch.equal(a.time_series(), a.time_series()) and torch.allclose(a.time_series(), b.time_series(), rtol=1e-10,
+                                                                            atol=1e-13)
+
+
 def test_graph_replay_of_callable_steps_is_bit_identical():
     """graph_callable=True: the steps between two measures of a torch-callable engine are captured once in a CUDA graph
     (device-resident step / measure counters, me_device_counters) and replayed; states and series must equal the
