@@ -731,8 +731,6 @@ int me_set_group(me_engine *e, int32_t group) {
         return fail(e, ME_ERR_INVALID, "group must be 0 (all), 1 (real), 2 (complex), 3 (complex magnitudes) or 4 (complex phases)");
     if (group == 1 && e->cfg.n_real == 0) return fail(e, ME_ERR_INVALID, "engine has no real parameters");
     if (group >= 2 && e->cfg.n_complex == 0) return fail(e, ME_ERR_INVALID, "engine has no complex parameters");
-    if (group >= 3 && e->generic)
-        return fail(e, ME_ERR_UNSUPPORTED, "magnitude-phase moves are built for fused shapes (n_real + 2 n_complex <= 32)");
     e->group = group;
     return ME_OK;
 }

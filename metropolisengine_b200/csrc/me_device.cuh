@@ -394,8 +394,11 @@ __device__ __forceinline__ void propose_magnitudes(const Chain<L> &c, const doub
         const double mag = hypot(re, im);
         const double nm = mag + z[j] * ((c.sig[1] * c.sig[1]) * cjj);
         const double ratio = nm / mag;
-        prop[NR + j] = mag > 0.0 ? re * ratio : nm;          /* arg 0 = 0 (cmath.polar) */
-        prop[NR + NC + j] = mag > 0.0 ? im * ratio : 0.0;
+        /* zero modulus: cmath.polar keeps atan2's signed zeros — arg(+0 +-0i) = +-0, arg(-0 +-0i) = +-pi (a rejected
+         * first move followed by a phase redraw leaves 0 x -cos(theta) = -0 behind) */
+        const bool neg0 = __double2hiint(re) < 0;
+        prop[NR + j] = mag > 0.0 ? re * ratio : (neg0 ? -nm : nm);
+        prop[NR + NC + j] = mag > 0.0 ? im * ratio : nm * copysign(neg0 ? 1.2246467991473532e-16 : 0.0, im);
     }
 }
 

@@ -159,7 +159,9 @@ __global__ void gk_propose(const __grid_constant__ MeParams p) {
     double *pr = p.prop + ch;
     const int nr = L.nr, nc = L.nc, d = L.d;
     if (p.inj_delta != nullptr) {
-        for (int i = 0; i < d; i++) pr[(long long)i * ld] = p.inj_delta[(long long)i * ld + ch] + ST(L.X + i);
+        const bool absolute = nc > 0 && p.group >= 3;     /* magnitude / phase records hold the proposal itself */
+        for (int i = 0; i < d; i++)
+            pr[(long long)i * ld] = p.inj_delta[(long long)i * ld + ch] + (absolute ? 0.0 : ST(L.X + i));
         if (nr > 0 && nc > 0 && p.group != 0)
             for (int i = 0; i < d; i++)
                 if ((i < nr) != (p.group == 1)) pr[(long long)i * ld] = ST(L.X + i);
@@ -174,6 +176,37 @@ __global__ void gk_propose(const __grid_constant__ MeParams p) {
         me::Rng::box_muller<true>(r, tables, z0, z1);
         z[(long long)(2 * q) * ld] = z0;
         if (2 * q + 1 < d) z[(long long)(2 * q + 1) * ld] = z1;
+    }
+    if (nc > 0 && p.group >= 3) {
+        /* magnitude-phase moves (ME:168-207, 304-317; same arithmetic as me::propose_magnitudes / propose_phases):
+         * 3: |c_j|' = |c_j| + z_j sigma_c^2 C_jj (the reference's variance-as-deviation, ME:305,310),
+         *    C_jj = sum_k |G_jk|^2;  4: c_j' = |c_j| e^{i theta}, theta from the angle word of Philox call j. */
+        const int dg = nc * (nc - 1);
+        const double sc2 = ST(L.SIG + 1) * ST(L.SIG + 1);
+        for (int i = 0; i < nr; i++) pr[(long long)i * ld] = ST(L.X + i);
+        for (int j = 0; j < nc; j++) {
+            const double re = ST(L.X + nr + j), im = ST(L.X + nr + nc + j);
+            const double mag = hypot(re, im);
+            if (p.group == 3) {
+                double cjj = ST(L.FACC + dg + j) * ST(L.FACC + dg + j);
+                for (int k = 0; k < j; k++)
+                    cjj += ST(L.FACC + g_hlo(j, k)) * ST(L.FACC + g_hlo(j, k))
+                         + ST(L.FACC + g_hlo(j, k) + 1) * ST(L.FACC + g_hlo(j, k) + 1);
+                const double nm = mag + z[(long long)j * ld] * (sc2 * cjj);
+                const double ratio = nm / mag;
+                const bool neg0 = __double2hiint(re) < 0;      /* zero modulus: atan2's signed zeros (see me_device.cuh) */
+                pr[(long long)(nr + j) * ld] = mag > 0.0 ? re * ratio : (neg0 ? -nm : nm);
+                pr[(long long)(nr + nc + j) * ld] = mag > 0.0 ? im * ratio
+                                                              : nm * copysign(neg0 ? 1.2246467991473532e-16 : 0.0, im);
+            } else {
+                const me::U4 r = rng.bits((unsigned)p.step0, (unsigned)j);
+                double sn, cs;
+                me::sincospi_bits(r.z, sn, cs);
+                pr[(long long)(nr + j) * ld] = mag * -cs;
+                pr[(long long)(nr + nc + j) * ld] = mag * -sn;
+            }
+        }
+        return;
     }
     const double sr = ST(L.SIG), sc = ST(L.SIG + 1) * 0.70710678118654752440;
     for (int i = 0; i < nr; i++) {
@@ -212,7 +245,7 @@ __global__ void gk_accept(const __grid_constant__ MeParams p) {
     double *st = p.state;
     const int kind = (L.nr > 0 && L.nc > 0) ? 0 : (L.nr > 0 ? 1 : 2);
     const bool grouped = kind == 0 && p.group != 0;
-    const int sidx = grouped ? p.group - 1 : (kind == 2 ? 1 : 0);
+    const int sidx = grouped ? (p.group == 1 ? 0 : 1) : (kind == 2 ? 1 : 0);
     double sg = ST(L.SIG + sidx);
     int status = (int)ST(L.STATUS);
     const me::Gains g = me::make_gains(p.n_meas0, p);
@@ -237,7 +270,7 @@ __global__ void gk_accept(const __grid_constant__ MeParams p) {
             ST(L.NACC) += 1.0;
         }
     }
-    sg = me::adapt_sigma<true>(sg, accept, g, p);
+    if (!(L.nc > 0 && p.group == 4)) sg = me::adapt_sigma<true>(sg, accept, g, p);     /* phase redraw: ME:194-207 */
     ST(L.SIG + sidx) = sg;
     if (kind == 0 && !grouped) {
         ST(L.SIG + 1) = sg;

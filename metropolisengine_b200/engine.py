@@ -483,8 +483,6 @@ class MetropolisEngine:
     def _require_magnitude_phase_kernels(self):
         if not self.num_complex_params:
             raise ValueError("engine has no complex parameters")
-        if self._generic:
-            raise NotImplementedError("magnitude-phase moves are built for fused shapes (n_real + 2 n_complex <= 32)")
 
     def step_complex_group_magnitude(self, k=1):
         """Gaussian move of every modulus at fixed phase, own Metropolis test, adapts the complex width (ME:178-192;

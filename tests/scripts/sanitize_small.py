@@ -1,5 +1,6 @@
 """Small end-to-end exercise of every kernel family for compute-sanitizer (memcheck):
-   compute-sanitizer --tool memcheck python tests/scripts/sanitize_small.py"""
+   compute-sanitizer --tool memcheck python tests/scripts/sanitize_small.py
+   (compute-sanitizer is closed on the round-1 GPU pool; the script also runs bare as an end-to-end smoke.)"""
 import os
 import sys
 

@@ -463,6 +463,46 @@ def test_magnitude_phase_philox_matches_c_oracle():
     assert len(set(np.floor(ang / (np.pi / 2)).astype(int))) == 4
 
 
+def test_magnitude_phase_large_shape_philox_matches_c_oracle():
+    """Magnitude / phase moves of a runtime-shape engine (1 real + 16 complex: 33 words, me_generic.cu gk_propose /
+    gk_accept with groups 3 / 4) against the C oracle on the same Philox streams.  Half of the coefficients start at
+    zero modulus (cmath.polar's arg 0 = 0 branch)."""
+    import metropolisengine_b200 as me
+    from oracle import c_oracle as co
+    consts = [10.0, -1.0, 0.05, 1.0]
+    c0 = np.concatenate([np.full(8, 0.05 + 0.02j), np.zeros(8, dtype=complex)])
+    eng = me.MetropolisEngine(me.BuiltinEnergy("cylinder", *consts, reject=True), initial_real_params=np.array([0.2]),
+                              initial_complex_params=c0, temp=.1, sampling_width=0.3, n_chains=48, seed=31,
+                              complex_sample_method="magnitude-phase")
+    assert eng._generic
+    oracles = {ch: co.CChain(1, 16, "cylinder", consts=consts, temp=.1, sampling_width=0.3,
+                             x0=np.concatenate([[0.2], c0.real, c0.imag]), use_reject=True) for ch in (0, 17, 47)}
+    step, nacc = 0, {ch: 0 for ch in oracles}
+    for im in range(54):                                       # crosses n > 50: adapted C_jj enter the magnitude width
+        for grp in (1, 3, 4, 3):
+            if grp == 1:
+                eng.step_real_group()
+            elif grp == 3:
+                eng.step_complex_group_magnitude()
+            else:
+                eng.step_complex_group_phase()
+            for ch, o in oracles.items():
+                acc, _ = o.run(1, 1, False, seed=31, chain_id=ch, step0=step, group=grp)
+                nacc[ch] += int(acc.sum())
+            step += 1
+        eng.measure()
+        for ch, o in oracles.items():
+            o.run(1, 0, True, seed=31, chain_id=ch, step0=step)
+    eng.check_status()
+    st = eng.state.cpu().numpy()
+    lay = eng._lay
+    assert sum(nacc.values()) > 0
+    for ch, o in oracles.items():
+        assert st[lay.NACC, ch] == nacc[ch], ch
+        assert close(st[:lay.WORDS - 2, ch], o.state[:lay.WORDS - 2], 2e-9), ch
+    assert eng.step_counter == 1 + 54 * 2                       # the two magnitude halves per block count (ME:450)
+
+
 def test_magnitude_phase_with_a_torch_callable_matches_the_device_functor():
     """Magnitude / phase moves on the unfused propose / torch-callable / accept path (me_propose and me_accept with
     groups 3 / 4) consume the same Philox words as the fused kernel: same decisions, same states."""
