@@ -429,12 +429,15 @@ def test_magnitude_phase_injected_parity():
     assert eng.step_counter == 1 + M * K // 3                      # only the magnitude half counts (ME:450)
 
 
-def test_magnitude_phase_philox_matches_c_oracle():
+@pytest.mark.parametrize("x0c", [np.array([0.4 - 0.1j, -0.3 + 0.2j]), np.array([0j, -0.3 + 0.2j])],
+                         ids=["nonzero", "zero_modulus"])
+def test_magnitude_phase_philox_matches_c_oracle(x0c):
     """Device-generated magnitude / phase moves (normal z_j of the step; angle word of Philox call j) against the C
-    oracle running the same streams; step_complex_group() = magnitude + phase and returns None as in the reference."""
+    oracle running the same streams; step_complex_group() = magnitude + phase and returns None as in the reference.
+    zero_modulus: a coefficient starting at 0 takes cmath.polar's signed-zero argument (arg(-0) = pi) until a move is
+    accepted (tests/test_oracle_c.py pins the oracle to cmath for this)."""
     import metropolisengine_b200 as me
     from oracle import c_oracle as co
-    x0c = np.array([0.4 - 0.1j, -0.3 + 0.2j])
     kw = dict(initial_real_params=np.array([0.3, 0.2, 0.1]), initial_complex_params=x0c, temp=.1, sampling_width=0.6,
               complex_sample_method="magnitude-phase")
     src = USER_SOURCES["warm_3r2c"]
@@ -444,7 +447,7 @@ def test_magnitude_phase_philox_matches_c_oracle():
         r, c = x[:n_r], x[n_r:n_r + n_c] + 1j * x[n_r + n_c:]
         a = (c * c.conjugate()).real
         return float(np.sum((1 - r) ** 2) + r[0] * r[1] * np.mean(-1 * a + .5 * a ** 2))
-    o = co.CChain(3, 2, lambda x: energy(x, 3, 2), temp=.1, x0=np.array([0.3, 0.2, 0.1, 0.4, -0.3, -0.1, 0.2]),
+    o = co.CChain(3, 2, lambda x: energy(x, 3, 2), temp=.1, x0=np.concatenate([[0.3, 0.2, 0.1], x0c.real, x0c.imag]),
                   sampling_width=0.6)
     step = 0
     for im in range(56):

@@ -170,3 +170,26 @@ def test_philox_proposals_have_reference_covariance():
     assert np.allclose(emp_r, sig ** 2 * Cr, atol=se * sig ** 2)
     assert np.allclose(emp_c, sig ** 2 * np.conj(Cc), atol=se * sig ** 2)
     assert np.allclose(pseudo, 0, atol=se * sig ** 2)
+
+
+@pytest.mark.parametrize("re0, im0", [(0.0, 0.0), (-0.0, 0.0), (-0.0, -0.0), (0.0, -0.0)])
+def test_magnitude_move_from_zero_modulus_follows_cmath_polar(re0, im0):
+    """The reference's magnitude move is cmath.rect(gauss(|c|, s), phase(c)) (ME:304-310).  At zero modulus the phase
+    is atan2 of signed zeros (arg(-0) = +-pi), which a rejected first move plus a phase redraw does produce; the C
+    oracle (and through it the kernels) must give what cmath gives."""
+    import cmath
+    import ctypes
+    import math
+    o = co.CChain(0, 1, lambda x: 0.0, temp=.1, sampling_width=0.5, x0=np.array([re0, im0]))
+    lay = co.layout(0, 1)
+    o.state[lay.X], o.state[lay.X + 1] = re0, im0          # np.array keeps the sign of zero; make sure of it
+    z0, z1 = ctypes.c_double(), ctypes.c_double()
+    co.lib().meo_normal_pair(ctypes.c_uint64(3), ctypes.c_uint64(11), ctypes.c_uint32(0), ctypes.c_uint32(0),
+                             ctypes.byref(z0), ctypes.byref(z1))
+    acc, _ = o.run(1, 1, False, seed=3, chain_id=11, step0=0, group=3)
+    assert acc.sum() == 1                                   # flat energy: always accepted
+    modulus, phase = cmath.polar(complex(re0, im0))
+    want = cmath.rect(modulus + z0.value * (0.5 * 0.5 * 1.0), phase)      # s = sigma^2 C_jj, C = identity
+    got = complex(o.state[lay.X], o.state[lay.X + 1])
+    assert got.real == pytest.approx(want.real, rel=1e-15, abs=0) and math.copysign(1, got.real) == math.copysign(1, want.real)
+    assert got.imag == pytest.approx(want.imag, rel=1e-12, abs=1e-300)
