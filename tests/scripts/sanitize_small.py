@@ -35,6 +35,10 @@ eng.run(8, 5)
 eng = me.MetropolisEngine(me.BuiltinEnergy("cylinder", 10.0, -1.0, 0.05, 1.0, reject=True), initial_real_params=np.array([0.2]),
                           initial_complex_params=np.zeros(64, dtype=complex), temp=.1, sampling_width=0.012, n_chains=64, seed=6)
 eng.run(3, 2)
+eng.step_complex_group_magnitude()
+eng.step_complex_group_phase()
+eng.measure()
+eng.check_status()
 # shared-covariance tcgen05 path with the asynchronous factor refresh
 eng = me.SharedCovarianceEngine(temp=.1, n_chains=128 * 5, seed=7, sampling_width=0.004)
 eng.run(54, 2)
