@@ -79,6 +79,15 @@ def cases():
                               ctor=dict(initial_real_params=np.array([0.3, 0.2]),
                                         initial_complex_params=np.array([0.4 - 0.1j]), temp=.1,
                                         complex_sample_method="magnitude-phase")),
+        # the same schedule on a large parameter space (1 real + 16 complex = 33 words: runtime-shape kernels); half of
+        # the coefficients start at zero modulus, where cmath.polar's argument is atan2 of signed zeros
+        "magphase_1r16c": dict(energy=en.make_cylinder(16), builtin=("cylinder", [10.0, -1.0, 0.05, 1.0]),
+                               reject=en.cylinder_reject, n_measures=54, steps_per_measure=6, seed=29,
+                               schedule="magphase",
+                               ctor=dict(initial_real_params=np.array([0.2]),
+                                         initial_complex_params=np.concatenate([np.full(8, 0.05 + 0.02j),
+                                                                                np.zeros(8, dtype=complex)]),
+                                         temp=.1, sampling_width=0.3, complex_sample_method="magnitude-phase")),
         # temp = 0 (the constructor default): greedy descent, no uniform is ever drawn (metropolis_engine.py:331-332)
         "xy_temp0": dict(energy=en.xy_well, builtin=("xy_well", [1.0]), n_measures=60, steps_per_measure=4, seed=7,
                          ctor=dict(initial_real_params=np.array([1.0, -2.0]), temp=0)),

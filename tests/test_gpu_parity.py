@@ -407,11 +407,14 @@ def test_group_wise_stepping_philox_matches_c_oracle():
         me.MetropolisEngine("x2", initial_real_params=[0.0], temp=.1).step_complex_group()
 
 
-def test_magnitude_phase_injected_parity():
+@pytest.mark.parametrize("name", ["magphase_2r1c", "magphase_1r16c"])
+def test_magnitude_phase_injected_parity(name):
     """complex_sample_method="magnitude-phase" (ME:129-130, 168-207, 304-317).  The reference is
-    driven as real group / magnitude move / phase redraw; the recorded proposals are injected into the strict kernel."""
+    driven as real group / magnitude move / phase redraw; the recorded proposals are injected into the strict kernel.
+    magphase_1r16c: the same on a large parameter space (runtime-shape kernels, hard wall, zero-modulus starts)."""
     import metropolisengine_b200 as me
-    eng, g = make_engine("magphase_2r1c", me, strict=True)
+    eng, g = make_engine(name, me, strict=True)
+    assert eng._generic == (name == "magphase_1r16c")
     assert eng.complex_sample_method == "magnitude-phase"
     M, K = int(g["n_measures"]), int(g["steps_per_measure"])
     nacc = 0
