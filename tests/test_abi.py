@@ -129,3 +129,24 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), "%s uses the oracle" % f
+
+
+def test_set_group_validation(lib):
+    """me_set_group (include/me_b200.h; ME:209-239 group steps, ME:168-207 magnitude / phase halves): argument checks
+    need no GPU.  Groups 3 / 4 are available on every shape, large parameter spaces (D > 32) included."""
+    L = lib.load()
+    h = ctypes.c_void_p()
+    cfg = lib.MeConfig(2, 0, 64, 0, 0.1, 0.3, 3.49, 0, 0, 0)                # all-real: no complex group of any kind
+    assert L.me_create(ctypes.byref(cfg), ctypes.byref(h)) == lib.ME_OK
+    assert L.me_set_group(h, 1) == lib.ME_OK
+    for g in (2, 3, 4):
+        assert L.me_set_group(h, g) == lib.ME_ERR_INVALID
+    assert L.me_set_group(h, 5) == lib.ME_ERR_INVALID and L.me_set_group(h, -1) == lib.ME_ERR_INVALID
+    assert L.me_destroy(h) == lib.ME_OK
+    for n_r, n_c in ((3, 4), (1, 16), (0, 20)):                              # fused mixed, runtime-shape mixed / complex
+        cfg = lib.MeConfig(n_r, n_c, 64, 0, 0.1, 0.3, 1.0, 0, 0, 0)
+        assert L.me_create(ctypes.byref(cfg), ctypes.byref(h)) == lib.ME_OK
+        for g in (0, 2, 3, 4):
+            assert L.me_set_group(h, g) == lib.ME_OK, (n_r, n_c, g)
+        assert L.me_set_group(h, 1) == (lib.ME_OK if n_r else lib.ME_ERR_INVALID)
+        assert L.me_destroy(h) == lib.ME_OK
