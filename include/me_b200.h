@@ -185,9 +185,11 @@ int me_accept(me_engine *eng, const double *prop, const double *e_new, const uns
 
 /* Large parameter spaces (D > 32, e.g. 1 real + 64 complex with per-chain covariance — the reference's own
  * algorithm at the cylinder shape): the step is always unfused, me_propose -> energy -> me_accept, with runtime-shape
- * kernels whose state stays in global memory (csrc/me_generic.cu); me_run then only serves measure().  For built-in
- * functors this entry point evaluates the energy (and the functor's hard wall) of a proposal block:
- * e_out[n_chains], rej_out[n_chains] (may be NULL). */
+ * kernels whose state stays in global memory (csrc/me_generic.cu); me_run then only serves measure().
+ * me_energy_builtin evaluates the handle's DEVICE functor (built-in, or user CUDA text on fused shapes) and its hard
+ * wall on a proposal block: e_out[n_chains], rej_out[n_chains] (may be NULL).  Besides the large-shape step it lets a
+ * host-side predicate — the reference's python reject_condition (ME:142-146) — sit between me_propose and me_accept
+ * of a functor engine of any shape. */
 int me_energy_builtin(me_engine *eng, const double *prop, double *e_out, unsigned char *rej_out, void *stream);
 
 /* Pooled ensemble moments: out[POOL_WORDS] = sum over CTAs (fixed order, deterministic) of the accumulators

@@ -176,7 +176,8 @@ int nvrtc_compile(int n_real, int n_complex, int energy_id, const std::string &u
            "#endif\n"
            "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_init(const __grid_constant__ MeParams p) { me::init_body<UserCfg>(p); }\n"
            "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_propose(const __grid_constant__ MeParams p) { me::propose_body<UserCfg>(p); }\n"
-           "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_accept(const __grid_constant__ MeParams p) { me::accept_body<UserCfg>(p); }\n";
+           "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_accept(const __grid_constant__ MeParams p) { me::accept_body<UserCfg>(p); }\n"
+           "extern \"C\" __global__ void __launch_bounds__(ME_MAX_BLOCK) me_k_energy(const __grid_constant__ MeParams p) { me::energy_body<UserCfg>(p); }\n";
     const char *hdr_names[] = {"me_params.h", "me_math.cuh", "me_device.cuh", "me_energies.cuh", "me_kernels.cuh"};
     const char *hdr_src[] = {me_src_params_h, me_src_math_cuh, me_src_device_cuh, me_src_energies_cuh,
                              me_src_kernels_cuh};
@@ -232,6 +233,7 @@ struct me_engine {
                                                   memory owned by the handle */
     unsigned long long seg_base = 0;           /* ring capacity */
     int run_slots = -1;                        /* CTAs of the fused kernel resident on the device at once (-1: unknown) */
+    const void *run_slots_of = nullptr;        /* the kernel run_slots was measured for (run and run_mp have different register caps) */
     const double *logtab = nullptr;            /* me_math.cuh log table on this engine's device */
     double *pool_partial = nullptr;            /* first-stage rows of the pooled-moment reduction (large ensembles) */
     unsigned long long *ctr_dev = nullptr;     /* device copy of (step, n_measure) for CUDA-graph replay of the unfused step */
@@ -342,7 +344,9 @@ int plan_segments(me_engine *e, const KernelRef &k, long long n_blocks, long lon
     if (const char *env = getenv("ME_SEGMENTS")) want = atoi(env);
     if (want == 0 || want == 1) return 1;
     DeviceGuard g(e->cfg.device);
-    if (e->run_slots < 0) {
+    const void *kid = k.rt ? k.rt : (const void *)k.drv;
+    if (e->run_slots < 0 || e->run_slots_of != kid) {
+        e->run_slots_of = kid;
         int per_sm = 0;
         if (k.rt) {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.rt, e->block, 0) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
@@ -428,7 +432,7 @@ int resolve_kernels(me_engine *e, int energy_id, const std::string &user_src) {
         for (int i = 0; i < n; i++)
             if (t[i].n_real == nr && t[i].n_complex == nc && t[i].energy_id == energy_id) {
                 e->ks.run.rt = t[i].run; e->ks.init.rt = t[i].init; e->ks.run_mp.rt = t[i].run_mp;
-                e->ks.propose.rt = t[i].propose; e->ks.accept.rt = t[i].accept;
+                e->ks.propose.rt = t[i].propose; e->ks.accept.rt = t[i].accept; e->ks.energy.rt = t[i].energy;
                 return ME_OK;
             }
     }
@@ -459,6 +463,7 @@ int resolve_kernels(me_engine *e, int energy_id, const std::string &user_src) {
         d.moduleGetFunction(&ks.init.drv, mod, "me_k_init") != CUDA_SUCCESS ||
         d.moduleGetFunction(&ks.propose.drv, mod, "me_k_propose") != CUDA_SUCCESS ||
         d.moduleGetFunction(&ks.accept.drv, mod, "me_k_accept") != CUDA_SUCCESS ||
+        d.moduleGetFunction(&ks.energy.drv, mod, "me_k_energy") != CUDA_SUCCESS ||
         (e->cfg.n_complex > 0 && d.moduleGetFunction(&ks.run_mp.drv, mod, "me_k_run_mp") != CUDA_SUCCESS))
         return fail(e, ME_ERR_CUDA, "cuModuleGetFunction failed on the runtime-compiled module");
     g_cache[key] = ks;
@@ -834,6 +839,7 @@ int me_accept(me_engine *e, const double *prop, const double *e_new, const unsig
     if (!e->bound) return fail(e, ME_ERR_STATE, "me_bind first");
     if (!prop || !e_new) return fail(e, ME_ERR_INVALID, "prop and e_new are required");
     if (inj_u && !e->cfg.strict) return fail(e, ME_ERR_STATE, "draw injection needs a strict handle");
+    if (e->step + 1ull >= 0xffffffffull) return fail(e, ME_ERR_INVALID, "step index exceeds the 32-bit Philox counter word");
     MeParams p;
     base_params(e, p);
     p.prop = const_cast<double *>(prop); p.e_new = e_new; p.rej = rej; p.inj_u = inj_u;
@@ -866,9 +872,9 @@ int me_device_counters(me_engine *e, int32_t enable, void *stream) {
 
 int me_energy_builtin(me_engine *e, const double *prop, double *e_out, unsigned char *rej_out, void *stream) {
     if (!e) return ME_ERR_INVALID;
-    if (!e->generic) return fail(e, ME_ERR_STATE, "me_energy_builtin serves the large-shape unfused path only");
+    if (!e->bound) return fail(e, ME_ERR_STATE, "me_bind first");
     if (!prop || !e_out) return fail(e, ME_ERR_INVALID, "prop and e_out are required");
-    if (e->energy_id < 0 || e->energy_id == ME_ENERGY_EXTERNAL) return fail(e, ME_ERR_STATE, "no built-in functor registered");
+    if (e->energy_id < 0 || e->energy_id == ME_ENERGY_EXTERNAL) return fail(e, ME_ERR_STATE, "no device functor registered");
     MeParams p;
     base_params(e, p);
     p.prop = const_cast<double *>(prop); p.e_out = e_out; p.rej_out = rej_out;

@@ -773,7 +773,10 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     const Pins pins = load_pins(tables);
     const double half_temp = 0.5 * p.temp;
     /* log table: read-only global path for small shapes, per-CTA shared copy for larger ones (see me_math.cuh) */
-    constexpr bool TAB_SMEM = !STRICT && L::D > ME_SEG_MAX_D;
+    /* static shared-memory budget (48 KB): the pooled-moment staging of a large shape (9 x POOLW doubles, up to 43 KB at
+       ME_MAX_POOLW) and the 16 KB table copy do not both fit; such shapes read the table through the read-only path */
+    constexpr bool TAB_FITS = (ME_MAX_BLOCK / 32 + 1) * PW * 8 + ME_LOGTAB_ENTRIES * 16 + 1024 <= 48 * 1024;
+    constexpr bool TAB_SMEM = !STRICT && L::D > ME_SEG_MAX_D && TAB_FITS;
     __shared__ double2 logtab_s[TAB_SMEM ? ME_LOGTAB_ENTRIES : 1];
     if (TAB_SMEM) {
         for (int i = threadIdx.x; i < ME_LOGTAB_ENTRIES; i += blockDim.x)
@@ -1014,6 +1017,23 @@ __device__ __forceinline__ void propose_body(const MeParams &p) {
     }
 #pragma unroll
     for (int i = 0; i < D; i++) p.prop[(long long)i * p.ld + ch] = prop[i];
+}
+
+/* Energy (and hard wall) of a proposal block with the engine's device functor: lets a host-side predicate (a python
+ * reject_condition, ME:142-146) sit between the proposal and the decision of a functor engine. */
+template <class Cfg>
+__device__ __forceinline__ void energy_body(const MeParams &p) {
+    using L = Lay<Cfg::NR, Cfg::NC>;
+    using Energy = typename Cfg::Energy;
+    constexpr int D = L::D;
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_chains) return;
+    double x[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) x[i] = p.prop[(long long)i * p.ld + ch];
+    p.e_out[ch] = Energy::eval(x, x + L::NR, x + L::NR + L::NC, p.consts);
+    if (p.rej_out)
+        p.rej_out[ch] = (p.use_reject && Energy::reject(x, x + L::NR, x + L::NR + L::NC, p.consts)) ? 1 : 0;
 }
 
 template <class Cfg>

@@ -402,7 +402,9 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
                     if (e_new != e_new) S.status_s[m] |= ME_STATUS_ENERGY_NAN;
                     const double diff = e_new - S.e_s[m];
                     const double prob = me::exp_nonpos(fmin(-diff * p.inv_temp, 0.0), S.tables);
-                    accept = (diff <= 0) | ((p.temp != 0) & (S.u_s[slot][m] <= prob));
+                    /* a NaN difference rejects, as in the reference (`uniform <= exp(nan)` is False, ME:327-338): fmin
+                       would turn it into prob = 1 */
+                    accept = (diff <= 0) | ((p.temp != 0) & (diff == diff) & (S.u_s[slot][m] <= prob));
                     if (accept) { S.e_s[m] = e_new; S.a_s[m] = a_new; S.nacc_s[m] += 1.0; }
                 }
                 const double sg = accept ? fma(sig, g_up, sig) : fma(sig, -g_down, sig);
@@ -872,12 +874,8 @@ int me_k4_step(me_k4 *e, int64_t n_steps, const double *s_a, float *dbg_z, float
     k4_base(e, p);
     p.n_steps = n_steps; p.s_a = s_a; p.dbg_z = dbg_z; p.dbg_delta = dbg_delta;
     int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    static bool attr_set = false;
-    cudaError_t ce = cudaSuccess;
-    if (!attr_set) {
-        ce = cudaFuncSetAttribute(k4_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
-        attr_set = (ce == cudaSuccess);
-    }
+    /* the attribute is per device: set it before every launch (a host-side table write, no device work) */
+    cudaError_t ce = cudaFuncSetAttribute(k4_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
     if (ce == cudaSuccess) {
         const int avail = e->n_sm - e->reserved_sms > 0 ? e->n_sm - e->reserved_sms : 1;
         long long per = (e->cfg.n_chains + avail - 1) / avail;
@@ -935,13 +933,8 @@ int me_k4_refactor(me_k4 *e, const double *mom, const double *inc, int64_t n_mea
     if (!e || !mom || !inc || !cov_c || !cov_a || !factor_bf16 || !s_a) return ME_ERR_INVALID;
     if (n_measure <= 0) n_measure = e->n_measure;
     int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    static bool attr_set = false;
     const int smem = K4_NC * (K4_NC + 1) * (int)sizeof(double2);
-    cudaError_t ce = cudaSuccess;
-    if (!attr_set) {
-        ce = cudaFuncSetAttribute(k4_refactor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = (ce == cudaSuccess);
-    }
+    cudaError_t ce = cudaFuncSetAttribute(k4_refactor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (ce == cudaSuccess) {
         k4_refactor<<<1, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const double2 *>(mom),
                                                             reinterpret_cast<const double2 *>(inc), n_measure,

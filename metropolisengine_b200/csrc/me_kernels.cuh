@@ -60,13 +60,15 @@ template <class C>
 __global__ void __launch_bounds__(ME_MAX_BLOCK) k_propose(const __grid_constant__ MeParams p) { propose_body<C>(p); }
 template <class C>
 __global__ void __launch_bounds__(ME_MAX_BLOCK) k_accept(const __grid_constant__ MeParams p) { accept_body<C>(p); }
+template <class C>
+__global__ void __launch_bounds__(ME_MAX_BLOCK) k_energy(const __grid_constant__ MeParams p) { energy_body<C>(p); }
 
 }  // namespace me
 
 /* one ahead-of-time instantiation */
 struct MeAotEntry {
     int n_real, n_complex, energy_id, strict;
-    const void *run, *init, *propose, *accept, *run_mp;
+    const void *run, *init, *propose, *accept, *run_mp, *energy;
 };
 
 #define ME_AOT_ENTRY(NR, NC, ETMPL, EID, STRICT)                                                        \
@@ -74,7 +76,8 @@ struct MeAotEntry {
       (const void *)&me::k_init<me::Cfg<NR, NC, ETMPL, STRICT>>,                                          \
       (const void *)&me::k_propose<me::Cfg<NR, NC, ETMPL, STRICT>>,                                       \
       (const void *)&me::k_accept<me::Cfg<NR, NC, ETMPL, STRICT>>,                                        \
-      me::RunMpKernel<me::Cfg<NR, NC, ETMPL, STRICT>>::get() }
+      me::RunMpKernel<me::Cfg<NR, NC, ETMPL, STRICT>>::get(),                                             \
+      (const void *)&me::k_energy<me::Cfg<NR, NC, ETMPL, STRICT>> }
 
 /* the shapes of BASELINE.json's configs plus the shapes of the golden fixtures */
 #define ME_AOT_TABLE(STRICT)                                                      \

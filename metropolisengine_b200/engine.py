@@ -86,12 +86,22 @@ class MetropolisEngine:
                       the callable must then be capture-safe (static shapes, no host synchronisation)
     """
 
+    def __new__(cls, *args, adapt="per_chain", **kw):
+        """One front door: ``adapt="pooled"`` builds the shared-covariance engine (the proposal
+        covariance of the complex block pooled over the ensemble, L.Z on the tensor cores) from the same arguments."""
+        if adapt == "pooled" and cls is MetropolisEngine:
+            from .engine_shared import SharedCovarianceEngine
+            return SharedCovarianceEngine.from_reference_arguments(*args, **kw)
+        if adapt not in ("per_chain", "pooled"):
+            raise ValueError("adapt must be 'per_chain' (the reference's algorithm) or 'pooled'")
+        return super().__new__(cls)
+
     def __init__(self, energy_functions, reject_condition=None, initial_real_params=None,
                  initial_complex_params=None, sampling_width=0.05, covariance_matrix_real=None,
                  covariance_matrix_complex=None, params_names=None, target_acceptance=.3, temp=0,
                  complex_sample_method="multivariate-gaussian", *, n_chains=1, seed=0, device=None, strict=False,
                  record=True, callable_layout="chains_first", distributed=False, ts_chunk_bytes=1 << 30,
-                 graph_callable=False, _shard=None):
+                 graph_callable=False, adapt="per_chain", _shard=None):
         if initial_real_params is None and initial_complex_params is None:
             raise ValueError("must give a list containing at least one value for initial real or complex "
                              "parameters")                                                   # ME:37-39
@@ -101,8 +111,14 @@ class MetropolisEngine:
         self.complex_sample_method = complex_sample_method
         if temp is None or not temp >= 0:
             raise AssertionError("temp must be >= 0")                                        # ME:92
-        if isinstance(sampling_width, (list, tuple)):
-            raise NotImplementedError("per-group sampling widths belong to group-wise stepping (SURVEY §8 row f1)")
+        self._width_pair = None
+        if isinstance(sampling_width, (list, tuple)):                                        # ME:93-95
+            if len(sampling_width) != 2:
+                raise ValueError("sampling_width as a list is [sigma_real, sigma_complex]")
+            self._width_pair = (float(sampling_width[0]), float(sampling_width[1]))
+            # the reference leaves self.sampling_width undefined in this form and its mixed step_all() then fails at
+            # ME:431; here a mixed step_all() continues from the real group's width
+            sampling_width = self._width_pair[0]
         if not torch.cuda.is_available():
             raise RuntimeError("MetropolisEngine needs a CUDA device: the hot path is CUDA-only (no CPU fallback)")
         self._lib = _lib.load()
@@ -190,6 +206,7 @@ class MetropolisEngine:
         # ---- energy plugin (ME:110-120) and hard-wall predicate (ME:126-127, 142-146)
         self._callable = None
         self._terms = None
+        self.reject_condition = None
         self._callable_layout = callable_layout
         if callable_layout not in ("chains_first", "params_first"):
             raise ValueError("callable_layout must be 'chains_first' or 'params_first'")
@@ -217,6 +234,7 @@ class MetropolisEngine:
             e0 = self._eval_callable(full)
         self._launch(self._lib.me_init(self._h, _ptr(x0_dev), 0 if per_chain_init else 1, self._sampling_width0,
                                       _ptr(cov_r), _ptr(cov_c_re), _ptr(cov_c_im), _ptr(e0), self._stream()))
+        self._apply_width_pair()
         self._energy0 = self.state[self._lay.E].clone()
         self._term_energy0 = None
         if self._terms is not None:
@@ -251,6 +269,12 @@ class MetropolisEngine:
         if h is not None and getattr(self, "_lib", None) is not None:
             self._lib.me_destroy(h)
             self._h = None
+
+    def _apply_width_pair(self):
+        """sampling_width=[sigma_real, sigma_complex] (ME:93-95): the two group widths start apart."""
+        if self._width_pair is not None:
+            self.state[self._lay.SIG].fill_(self._width_pair[0])
+            self.state[self._lay.SIG + 1].fill_(self._width_pair[1])
 
     def _install_energy(self, energy):
         if isinstance(energy, str):
@@ -293,13 +317,12 @@ class MetropolisEngine:
         self.reject_condition = reject_fct
 
     def _check_reject_supported(self, reject_fct):
-        """A python predicate can only run on the unfused (python-callable energy) path; fused device functors
-        carry their hard wall inside the functor (``BuiltinEnergy(..., reject=True)`` / ``CudaEnergy(...,
-        has_reject=True)``).  Refuse instead of silently ignoring the constraint."""
-        if reject_fct is not None and self._callable is None:
-            raise NotImplementedError("reject_condition as a python callable needs a python-callable energy; for "
-                                      "device functors put the wall in the functor (BuiltinEnergy(reject=True) or "
-                                      "CudaEnergy(has_reject=True))")
+        """A python predicate (ME:142-146) is evaluated on the proposal block between the proposal and the decision,
+        so an engine that has one steps unfused: me_propose -> device functor (me_energy_builtin) or python energy ->
+        predicate -> me_accept.  The fast form of a hard wall is inside the functor (``BuiltinEnergy(...,
+        reject=True)`` / ``CudaEnergy(..., has_reject=True)``), which keeps the step fused."""
+        if reject_fct is not None and not callable(reject_fct):
+            raise TypeError("reject_condition must be callable: (real_params, complex_params) -> bool per chain")
 
     def _split(self, block):
         """[D, chains] block -> (real, complex) tensors in the callable's layout."""
@@ -388,8 +411,14 @@ class MetropolisEngine:
             x0[nr:nr + nc] = c.real.t() if c.dim() == 2 else c.real[:, None]
             x0[nr + nc:] = c.imag.t() if c.dim() == 2 else c.imag[:, None]
         e0 = self._eval_callable(x0) if self._callable is not None else None
+        if isinstance(sampling_width, (list, tuple)):
+            self._width_pair = (float(sampling_width[0]), float(sampling_width[1]))
+            sampling_width = self._width_pair[0]
+        elif sampling_width is not None:
+            self._width_pair = None
         sw = self._sampling_width0 if sampling_width is None else float(sampling_width)
         self._launch(self._lib.me_init(self._h, _ptr(x0), 0, sw, None, None, None, _ptr(e0), self._stream()))
+        self._apply_width_pair()
         self._energy0 = self.state[self._lay.E].clone()
         self.reset_pooled_statistics()
         self.clear_time_series()
@@ -402,8 +431,9 @@ class MetropolisEngine:
         n_measures, steps_per_measure = int(n_measures), int(steps_per_measure)
         if n_measures <= 0:
             return
-        if self._callable is not None or self._generic:
-            graphed = self._graph_callable and self._callable is not None and not self._generic and steps_per_measure > 0
+        if self._unfused():
+            graphed = (self._graph_callable and self._callable is not None and not self._generic
+                       and steps_per_measure > 0)
             for _ in range(n_measures):
                 if graphed:
                     self._replay_steps(steps_per_measure)
@@ -423,7 +453,7 @@ class MetropolisEngine:
     def step(self, k=1):
         """``k`` calls of ``step_all()`` in one launch (no measure)."""
         k = int(k)
-        if self._callable is not None or self._generic:
+        if self._unfused():
             for _ in range(k):
                 self._step_external()
             return
@@ -506,20 +536,26 @@ class MetropolisEngine:
         if group in (2, 3) and self._kind == "mixed":
             self.step_counter += int(k)
 
+    def _unfused(self):
+        """True when a step is propose -> energy -> accept instead of the fused kernel: python energies, large shapes,
+        and any engine carrying a python reject_condition."""
+        return self._callable is not None or self._generic or self.reject_condition is not None
+
     def _step_external(self, inj_delta=None, inj_u=None):
         prop = torch.empty((self._d, self.n_chains), dtype=torch.float64, device=self.device)
         self._launch(self._lib.me_propose(self._h, _ptr(prop), _ptr(inj_delta), self._stream()))
         rej = None
-        if self._callable is None:              # large shape with a built-in functor: energy + wall on the device
+        if self._callable is None:              # device functor (large shape, or a python predicate): energy + wall
             e_new = torch.empty(self.n_chains, dtype=torch.float64, device=self.device)
             rej = torch.empty(self.n_chains, dtype=torch.uint8, device=self.device)
             self._launch(self._lib.me_energy_builtin(self._h, _ptr(prop), _ptr(e_new), _ptr(rej), self._stream()))
-        else:
-            if self.reject_condition is not None:
-                r, c = self._split(prop)
-                rej = torch.as_tensor(self.reject_condition(r, c), device=self.device)
-                rej = (rej.to(torch.uint8).expand(self.n_chains).contiguous() if rej.dim() == 0
-                       else rej.to(torch.uint8).contiguous())
+        if self.reject_condition is not None:                                               # ME:227, ME:247
+            r, c = self._split(prop)
+            mask = torch.as_tensor(self.reject_condition(r, c), device=self.device)
+            mask = (mask.to(torch.uint8).expand(self.n_chains).contiguous() if mask.dim() == 0
+                    else mask.to(torch.uint8).contiguous())
+            rej = mask if rej is None else torch.maximum(rej, mask)
+        if self._callable is not None:
             e_new = self._eval_callable(prop)
         self._launch(self._lib.me_accept(self._h, _ptr(prop), _ptr(e_new), _ptr(rej), _ptr(inj_u), self._stream()))
         self.step_counter += 1 if self._kind == "complex" else 0
@@ -574,7 +610,7 @@ class MetropolisEngine:
             u = u[:, None].expand(S, self.n_chains)
         delta, u = delta.contiguous(), u.contiguous()
         assert delta.shape == (S, self._d, self.n_chains) and u.shape == (S, self.n_chains)
-        if self._callable is not None or self._generic:
+        if self._unfused():
             s = 0
             for _ in range(int(n_measures)):
                 for _ in range(int(steps_per_measure)):
@@ -767,6 +803,9 @@ class MetropolisEngine:
         group width and leave it at its initial value."""
         if self._kind == "mixed":
             return self.real_group_sampling_width
+        if self._width_pair is not None:
+            raise AttributeError("sampling_width is undefined when the widths were given as [sigma_real, "
+                                 "sigma_complex] (ME:93-95); read the group widths")
         return self._sampling_width0
 
     @property
@@ -927,13 +966,22 @@ class MetropolisEngine:
         t, used = chunks[0]
         return self._equilibration_kernel(t[:used], column, min(int(n_chains), self.n_chains), nskip, fast)
 
-    def save_equilibrium_stats(self, chain=0, nskip=1):
-        """The reference's post-run summary for one chain (ME:481-504 without the ``external_df`` plumbing):
+    def save_equilibrium_stats(self, external_df=None, chain=0, nskip=1):
+        """The reference's post-run summary for one chain (ME:481-504).  ``external_df``: a list of data frames of
+        external observables recorded alongside the run (the cylinder app's field profiles); those whose first entry is
+        a float or int join the equilibration analysis (ME:485-487), and every one of them is re-averaged from the
+        global cut-off (ME:494-502: ``field_profile`` / ``field_abs_profile`` are the first two).  ``eq_means_error`` is
+        the empty dict the reference's ``get_equilibrated_means`` returns (statistics.py:59,64: never filled).
         ``eq_points`` = {column: [t0, g, Neff_max]} for every non-constant data-frame column (complex ones split into
         ``_real`` / ``_imag``, statistics.py:25-48), ``global_eq_point`` = the largest t0 among the columns that are
         not sampling widths (ME:492), ``equilibrated_means`` = column means from that row on (statistics.py:53-64)
         plus ``"global_cutoff"``.  The series are analysed on the device (me_detect_equilibration)."""
-        df = self.save_time_series(chain)
+        import pandas
+        own = self.save_time_series(chain)
+        df = own
+        if external_df is not None:                                                          # ME:485-487
+            keep = [own] + [e for e in external_df if isinstance(e.iloc[0, 0], (float, int, np.floating, np.integer))]
+            df = pandas.concat(keep, axis=1)
         names, series = [], []
         for name in df.columns.values:
             col = df[name].to_numpy()
@@ -954,8 +1002,14 @@ class MetropolisEngine:
                 self.eq_points[n_] = [int(t0.item()), float(g.item()), float(neff.item())]
         cut = [t for key, (t, _g, _n) in self.eq_points.items() if "sampling_width" not in key]
         self.global_eq_point = max(cut) if cut else 0
-        self.equilibrated_means = {name: np.average(df.loc[self.global_eq_point:, name]) for name in df.columns.values}
-        self.eq_means_error = {}
+        def means_from(frame):                                                              # statistics.py:53-64
+            return {name: np.average(frame.loc[self.global_eq_point:, name]) for name in frame.columns.values}
+
+        self.equilibrated_means, self.eq_means_error = means_from(own), {}                  # ME:494
+        if external_df is not None:                                                          # ME:495-502
+            profiles = [means_from(e) for e in external_df]
+            self.field_profile = profiles[0] if len(profiles) > 0 else None
+            self.field_abs_profile = profiles[1] if len(profiles) > 1 else None
         self.equilibrated_means["global_cutoff"] = self.global_eq_point
         return self.eq_points
 

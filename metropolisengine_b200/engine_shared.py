@@ -126,6 +126,33 @@ class SharedCovarianceEngine:
         self.record = bool(record)
         self._ts_chunks, self._ts_chunk_rows = [], int(ts_chunk_rows)
 
+    @classmethod
+    def from_reference_arguments(cls, energy_functions, reject_condition=None, initial_real_params=None,
+                                 initial_complex_params=None, sampling_width=0.05, covariance_matrix_real=None,
+                                 covariance_matrix_complex=None, params_names=None, target_acceptance=.3, temp=0,
+                                 complex_sample_method="multivariate-gaussian", **kw):
+        """``MetropolisEngine(..., adapt="pooled")``: the reference's constructor arguments (ME:17) mapped onto this
+        engine.  The energy must be the cylinder-style device functor (``("cylinder", kappa, alpha, gamma, beta)`` or
+        ``BuiltinEnergy("cylinder", ...)``); its hard wall is switched on by ``BuiltinEnergy(..., reject=True)``."""
+        from .engine import BuiltinEnergy
+        e = energy_functions
+        if isinstance(e, str):
+            e = BuiltinEnergy(e)
+        elif isinstance(e, tuple) and e and isinstance(e[0], str):
+            e = BuiltinEnergy(e[0], *e[1:])
+        if not isinstance(e, BuiltinEnergy) or e.name != "cylinder":
+            raise NotImplementedError("adapt='pooled' (shared proposal covariance on the tensor cores) serves the "
+                                      "cylinder-style device functor; other energies use adapt='per_chain'")
+        if reject_condition is not None:
+            raise NotImplementedError("adapt='pooled': put the hard wall in the functor (BuiltinEnergy(reject=True))")
+        for k in ("strict", "callable_layout", "graph_callable", "ts_chunk_bytes", "_shard"):
+            kw.pop(k, None)
+        consts = e.consts if len(e.consts) == 4 else (10.0, -1.0, 0.05, 1.0)
+        return cls(energy_consts=consts, reject_condition=e.reject, initial_real_params=initial_real_params,
+                   initial_complex_params=initial_complex_params, sampling_width=sampling_width,
+                   covariance_matrix_real=covariance_matrix_real, covariance_matrix_complex=covariance_matrix_complex,
+                   params_names=params_names, target_acceptance=target_acceptance, temp=temp, **kw)
+
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

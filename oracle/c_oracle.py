@@ -102,8 +102,11 @@ class CChain:
         if cov_c is not None:
             cre = np.ascontiguousarray(np.real(cov_c), dtype=np.float64)
             cim = np.ascontiguousarray(np.imag(cov_c), dtype=np.float64)
-        lib().meo_init(ctypes.byref(self.cfg), _dp(self.state), _dp(x0), ctypes.c_double(sampling_width),
+        widths = np.atleast_1d(np.asarray(sampling_width, dtype=np.float64))
+        lib().meo_init(ctypes.byref(self.cfg), _dp(self.state), _dp(x0), ctypes.c_double(widths[0]),
                        _dp(cr), _dp(cre), _dp(cim))
+        if widths.size == 2:                       # sampling_width=[sigma_real, sigma_complex] (ME:93-95)
+            self.state[self.off.SIG], self.state[self.off.SIG + 1] = widths[0], widths[1]
 
     def run(self, n_blocks, spm, do_measure=True, delta=None, u=None, seed=0, chain_id=0, step0=0, want_ts=False,
             group=0):

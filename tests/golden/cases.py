@@ -71,6 +71,13 @@ def cases():
                             steps_per_measure=8, seed=17, schedule="groups",
                             ctor=dict(initial_real_params=np.array([0.3, 0.2]),
                                       initial_complex_params=np.array([0.4 - 0.1j]), temp=.1)),
+        # the same schedule started from sampling_width=[sigma_real, sigma_complex] (metropolis_engine.py:93-95): the
+        # list form sets the two group widths only (the reference's step_all would raise AttributeError at ME:431)
+        "groups_widths_2r1c": dict(energy=en.demo_2r1c, builtin=("mixed_well", [1.0, -1.0, 0.5]), n_measures=60,
+                                   steps_per_measure=6, seed=19, schedule="groups",
+                                   ctor=dict(initial_real_params=np.array([0.3, 0.2]),
+                                             initial_complex_params=np.array([0.4 - 0.1j]), temp=.1,
+                                             sampling_width=[0.21, 0.04])),
         # complex_sample_method="magnitude-phase" (metropolis_engine.py:129-130, 168-207, 304-317):
         # the user alternates step_real_group() and step_complex_group(), the latter being a Gaussian magnitude
         # move followed by a uniform phase redraw

@@ -107,7 +107,7 @@ def run_case(me, name, energy, n_measures, steps_per_measure, seed=0, reject=Non
     rec = dict(
         n_r=n_r, n_c=n_c, n_measures=n_measures, steps_per_measure=steps_per_measure, seed=seed,
         temp=float(eng.temp), target_acceptance=float(eng.target_acceptance),
-        sampling_width0=float(ctor.get("sampling_width", 0.05)),
+        sampling_width0=np.asarray(ctor.get("sampling_width", 0.05), dtype=np.float64),   # scalar, or [sigma_r, sigma_c]
         alpha=float(eng.alpha), ratio=float(eng.ratio), m=int(eng.m),
         x0=np.array(eng.real_params, dtype=np.float64),
         c0=np.array(eng.complex_params, dtype=np.complex128),

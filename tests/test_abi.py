@@ -150,3 +150,22 @@ def test_set_group_validation(lib):
             assert L.me_set_group(h, g) == lib.ME_OK, (n_r, n_c, g)
         assert L.me_set_group(h, 1) == (lib.ME_OK if n_r else lib.ME_ERR_INVALID)
         assert L.me_destroy(h) == lib.ME_OK
+
+
+def test_reference_import_name_resolves_to_this_package():
+    """`import metropolisengine as me` (reference README.md:15,33) is a one-file shim over metropolisengine_b200."""
+    import metropolisengine
+    import metropolisengine_b200
+    assert metropolisengine.MetropolisEngine is metropolisengine_b200.MetropolisEngine
+    assert metropolisengine.__file__.startswith(ROOT)
+
+
+@pytest.mark.parametrize("nr,nc", [(27, 0), (0, 14)])
+def test_large_fused_shapes_fit_the_static_shared_memory_budget(lib, nr, nc):
+    """Fused shapes whose pooled-moment staging approaches 48 KB (POOLW 448..600) must still compile in the
+    throughput build: the log table then stays in global memory instead of a 16 KB shared copy.  Compile-only (NVRTC,
+    no GPU); the two shapes are the ones ptxas used to reject with 'uses too much shared data'."""
+    lay = lib.layout(nr, nc)
+    assert 447 < lay.POOL_WORDS <= 600
+    ok, log = lib.check_energy_source(None, nr, nc, use_reject=False, strict=False)
+    assert ok, log[-400:]

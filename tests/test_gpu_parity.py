@@ -361,11 +361,15 @@ def test_on_disk_time_series_formats(tmp_path):
     assert np.allclose(z["rows"][:, 0, 2], back["param_0"], rtol=1e-15)
 
 
-def test_group_wise_stepping_injected_parity():
+@pytest.mark.parametrize("name", ["groups_2r1c", "groups_widths_2r1c"])
+def test_group_wise_stepping_injected_parity(name):
     """step_real_group / step_complex_group on a mixed engine, each with its own width
-    (ME:209-239, 440-456), alternating as the cylinder app drives them; draw-injected against the reference."""
+    (ME:209-239, 440-456), alternating as the cylinder app drives them; draw-injected against the reference.
+    groups_widths_2r1c starts from sampling_width=[sigma_real, sigma_complex] (ME:93-95)."""
     import metropolisengine_b200 as me
-    eng, g = make_engine("groups_2r1c", me, strict=True)
+    eng, g = make_engine(name, me, strict=True)
+    if name == "groups_widths_2r1c":
+        assert eng.real_group_sampling_width == 0.21 and eng.complex_group_sampling_width == 0.04
     M, K = int(g["n_measures"]), int(g["steps_per_measure"])
     nacc = 0
     for im in range(M):
@@ -559,3 +563,71 @@ def test_graph_replay_of_callable_steps_is_bit_identical():
     s1, t1, l1 = run(True)
     assert torch.equal(s0, s1) and torch.equal(t0, t1)
     assert l1 < l0 / 2                    # one graph launch per block instead of two kernel launches per step
+
+
+def test_python_reject_condition_on_a_device_functor_engine():
+    """ME:142-146: a python predicate on an engine whose energy is a device functor.  The engine then steps unfused
+    (me_propose -> me_energy_builtin -> predicate -> me_accept); the chain must equal the one whose wall sits inside
+    the functor (same Philox slots, same decisions), on a fused shape and on a runtime-compiled user functor."""
+    import metropolisengine_b200 as me
+    kw = dict(initial_real_params=np.array([0.9]), initial_complex_params=np.zeros(8, dtype=complex), temp=.1,
+              sampling_width=0.2, n_chains=64, seed=31)
+    consts = (10.0, -1.0, 0.05, 1.0)
+    a = me.MetropolisEngine(me.BuiltinEnergy("cylinder", *consts, reject=True), **kw)
+    a.run(55, 4)
+    b = me.MetropolisEngine(me.BuiltinEnergy("cylinder", *consts), **kw)
+    b.set_reject_condition(lambda r, c: r[:, 0].abs() >= 1.0)
+    b.run(55, 4)
+    assert torch.equal(a.accept_count_per_chain, b.accept_count_per_chain)
+    assert torch.allclose(a.state, b.state, rtol=1e-11, atol=1e-13)
+    assert float(a.real_params_per_chain.abs().max()) < 1.0
+    # constructor argument form (the reference drops it, SURVEY App. B-3; honoured here) with a user CUDA functor
+    src = """
+__device__ double me_user_energy(const double* x, const double* cr, const double* ci, const double* k) {
+    return x[0] * x[0] + x[1] * x[1];
+}"""
+    kw2 = dict(initial_real_params=np.array([0., 0.]), temp=.1, n_chains=64, seed=3)
+    c = me.MetropolisEngine(me.CudaEnergy(src), reject_condition=lambda r, c_: r[:, 0] > 0.3, **kw2)
+    c.run(60, 5)
+    assert float(c.real_params_per_chain[:, 0].max()) <= 0.3
+    d = me.MetropolisEngine(me.CudaEnergy(src + """
+__device__ bool me_user_reject(const double* x, const double* cr, const double* ci, const double* k) { return x[0] > 0.3; }
+""", has_reject=True), **kw2)
+    d.run(60, 5)
+    assert torch.equal(c.accept_count_per_chain, d.accept_count_per_chain)
+    assert torch.allclose(c.state, d.state, rtol=1e-11, atol=1e-13)
+
+
+def test_reference_import_name_front_door_and_equilibrium_stats_with_external_frames():
+    """`import metropolisengine as me` (reference README.md:15); adapt="pooled" picks the shared-covariance engine;
+    save_equilibrium_stats(external_df=...) (ME:481-504) re-averages external frames from the global cut-off and
+    leaves eq_means_error empty exactly like statistics.py:59,64."""
+    import pandas
+    import metropolisengine as ref_name
+    import metropolisengine_b200 as me
+    assert ref_name.MetropolisEngine is me.MetropolisEngine
+    eng = ref_name.MetropolisEngine("x2", initial_real_params=[0.5], temp=.01, n_chains=4, seed=1)
+    eng.run(300, 2)
+    rows = 300
+    ext = [pandas.DataFrame({"profile_a": np.linspace(0., 1., rows), "profile_b": np.ones(rows)}),
+           pandas.DataFrame({"abs_a": np.arange(rows, dtype=float)}),
+           pandas.DataFrame({"label": ["x"] * rows})]
+    eq = eng.save_equilibrium_stats(external_df=ext)
+    assert "profile_a" in eq and "abs_a" in eq and "label" not in eq and "profile_b" not in eq   # constant / string columns
+    cut = eng.global_eq_point
+    assert eng.eq_means_error == {}
+    assert eng.field_profile["profile_a"] == pytest.approx(np.linspace(0., 1., rows)[cut:].mean())
+    assert eng.field_abs_profile["abs_a"] == pytest.approx(np.arange(rows)[cut:].mean())
+    assert eng.equilibrated_means["global_cutoff"] == cut and "param_0" in eng.equilibrated_means
+    pooled = me.MetropolisEngine(me.BuiltinEnergy("cylinder", 10.0, -1.0, 0.05, 1.0, reject=True),
+                                 initial_real_params=np.array([0.1]), initial_complex_params=np.zeros(64, dtype=complex),
+                                 temp=.1, n_chains=256, seed=2, adapt="pooled")
+    assert isinstance(pooled, me.SharedCovarianceEngine)
+    pooled.run(2, 3)
+    assert pooled.complex_mean.shape == (64,)
+    with pytest.raises(NotImplementedError):
+        me.MetropolisEngine("x2", initial_real_params=[0.0], temp=.1, adapt="pooled")
+    lst = me.MetropolisEngine("x2", initial_real_params=[0.0], temp=.1, sampling_width=[0.3, 0.1])
+    assert lst.real_group_sampling_width == 0.3
+    with pytest.raises(AttributeError):
+        lst.sampling_width

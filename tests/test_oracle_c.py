@@ -30,7 +30,7 @@ def make_c_chain(name, use_builtin=True):
     n_r, n_c = int(g["n_r"]), int(g["n_c"])
     ctor = fresh_ctor(case)
     x0 = np.concatenate([g["x0"], np.real(g["c0"]), np.imag(g["c0"])])
-    kw = dict(temp=float(g["temp"]), sampling_width=float(g["sampling_width0"]), x0=x0,
+    kw = dict(temp=float(g["temp"]), sampling_width=g["sampling_width0"], x0=x0,
               cov_r=ctor.get("covariance_matrix_real"), cov_c=ctor.get("covariance_matrix_complex"))
     if use_builtin and case["builtin"] is not None:
         bname, consts = case["builtin"]
