@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ME_ABI_VERSION 3
+#define ME_ABI_VERSION 4
 
 enum me_status_code {
     ME_OK = 0,
@@ -117,11 +117,12 @@ int me_set_energy_external(me_engine *eng);
 int me_check_energy_source(const char *cuda_source, int32_t n_real, int32_t n_complex, int32_t use_reject,
                            int32_t strict, char *log, int64_t log_cap);
 
-/* CUDA-graph replay of the unfused step (me_propose -> caller's energy -> me_accept).  Kernel parameters are frozen
- * when a graph is captured, so with enable != 0 the step index and the measure counter are read from a device copy
- * that me_accept advances itself; the call (re)loads that copy from the handle's counters, so call it again before a
- * replay whenever the handle's counters moved outside the graph (me_run measure, me_set_counters), and advance the
- * handle's own counters with me_set_counters after a replay.  Fused shapes (D <= 32) only. */
+/* CUDA-graph replay of me_run (fused launches) and of the unfused step (me_propose -> caller's energy -> me_accept).
+ * Kernel parameters are frozen when a graph is captured, so with enable != 0 the step index and the measure counter
+ * are read from a device copy that me_run / me_accept advance themselves in-stream; the call (re)loads that copy from
+ * the handle's counters, so call it again before a replay whenever the handle's counters moved outside the graph
+ * (me_set_counters, launches made with enable == 0), and advance the handle's own counters with me_set_counters after a
+ * replay.  Fused shapes (D <= 32) only. */
 int me_device_counters(me_engine *eng, int32_t enable, void *stream);
 
 /* Group-wise stepping of mixed engines: subsequent me_run / me_run_injected / me_propose /
@@ -196,6 +197,26 @@ int me_energy_builtin(me_engine *eng, const double *prop, double *e_out, unsigne
  * filled at every measure; reset != 0 zeroes the accumulators afterwards.  The caller all-reduces `out` across
  * ranks (NCCL) — the only collective of the path.  No reference counterpart. */
 int me_pool_reduce(me_engine *eng, double *out, int32_t reset, void *stream);
+
+/* Pooled statistics across GPUs inside the library — the path's only collective.
+ * me_comm wraps an NCCL communicator: either one the library creates (rank 0 obtains a 128-byte id with
+ * me_comm_unique_id, distributes it by any means — the Python host broadcasts it through torch.distributed — and every
+ * rank calls me_comm_create), or an existing ncclComm_t of the host application (me_comm_adopt; not destroyed by
+ * me_comm_destroy).  NCCL itself is loaded at run time (the copy already in the process, else ME_NCCL_PATH /
+ * me_comm_set_library).
+ * me_allreduce_stats, all stream-ordered and without host synchronisation (so it can be captured in a CUDA graph
+ * together with me_run):  inc[0..POOL_WORDS) = fixed-order sum of this handle's per-CTA accumulators (which are
+ * reset), inc[POOL_WORDS] = n_samples (the (chain, measure) samples pooled since the previous call);  inc is summed
+ * over the ranks of `comm` in place (comm == NULL or one rank: no collective);  totals[0..POOL_WORDS] += inc.
+ * `totals` is the device-resident running moment vector the host reads once when statistics are wanted. */
+typedef struct me_comm me_comm;
+int me_comm_set_library(const char *libnccl_path);
+int me_comm_unique_id(unsigned char *id128);
+int me_comm_create(const unsigned char *id128, int32_t world, int32_t rank, int32_t device, me_comm **out);
+int me_comm_adopt(void *nccl_comm, int32_t world, int32_t rank, int32_t device, me_comm **out);
+int me_comm_destroy(me_comm *comm);
+const char *me_comm_last_error(void);
+int me_allreduce_stats(me_engine *eng, me_comm *comm, double *inc, double *totals, int64_t n_samples, void *stream);
 
 /* measure_step_counter (ME:73) and the global step index (Philox counter); for checkpoint / resume. */
 int me_get_counters(me_engine *eng, int64_t *n_measure, uint64_t *step);

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ME_B200_LIB") or os.path.join(HERE, "lib", "libme_b200.so")   # override: kernel experiments
 
-ME_ABI_VERSION = 3
+ME_ABI_VERSION = 4
 
 ME_OK, ME_ERR_INVALID, ME_ERR_CUDA, ME_ERR_COMPILE, ME_ERR_UNSUPPORTED, ME_ERR_STATE = range(6)
 
@@ -69,6 +69,13 @@ SIGNATURES = {
     "me_accept": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "me_energy_builtin": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "me_pool_reduce": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
+    "me_comm_set_library": (ctypes.c_int, [_cp]),
+    "me_comm_unique_id": (ctypes.c_int, [_vp]),
+    "me_comm_create": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(_vp)]),
+    "me_comm_adopt": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(_vp)]),
+    "me_comm_destroy": (ctypes.c_int, [_vp]),
+    "me_comm_last_error": (_cp, []),
+    "me_allreduce_stats": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "me_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
     "me_set_counters": (ctypes.c_int, [_vp, _i64, _u64]),
     "me_k4_layout_get": (ctypes.c_int, [ctypes.POINTER(MeK4Layout)]),

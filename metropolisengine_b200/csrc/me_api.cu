@@ -474,9 +474,14 @@ int resolve_kernels(me_engine *e, int energy_id, const std::string &user_src) {
 /* out[w] = sum over the per-CTA slots pool[b][w] in a fixed order (deterministic): one CTA per word, thread t sums the
  * slots t, t + 256, ... and a shared-memory tree combines the 256 partial sums.  (One thread per word walking all slots
  * serially cost 0.5 ms per call at 2048 slots — pure L2 latency.) */
-__global__ void __launch_bounds__(256) k_pool_reduce(double *pool, double *out, int grid, int words, int reset) {
+__global__ void __launch_bounds__(256) k_pool_reduce(double *pool, double *out, int grid, int words, int reset,
+                                                     int has_extra = 0, double extra = 0.0) {
     __shared__ double part[256];
     const int w = blockIdx.x, t = threadIdx.x;
+    if (w == words) {                           /* me_allreduce_stats: the sample count travels with the moments */
+        if (has_extra && t == 0) out[words] = extra;
+        return;
+    }
     double acc = 0.0;
     for (int b = t; b < grid; b += 256) {
         acc += pool[(long long)b * words + w];
@@ -521,6 +526,14 @@ __global__ void k_ctr_set(unsigned long long *ctr, unsigned long long step, unsi
     ctr[0] = step; ctr[1] = n_meas;
 }
 __global__ void k_ctr_advance(unsigned long long *ctr, unsigned long long dstep) { ctr[0] += dstep; }
+__global__ void k_ctr_advance2(unsigned long long *ctr, unsigned long long dstep, unsigned long long dmeas) {
+    ctr[0] += dstep; ctr[1] += dmeas;
+}
+/* totals[w] += inc[w]: the device-resident running moments of me_allreduce_stats */
+__global__ void k_accumulate(double *totals, const double *inc, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) totals[i] += inc[i];
+}
 
 /* FP64 FMA throughput probe: 8 independent dependent-FMA streams per thread.  The roofline denominator of the
  * step kernels (MEASURED_PEAKS.json carries HBM and bf16 figures only). */
@@ -807,6 +820,12 @@ static int run_common(me_engine *e, int64_t n_blocks, int64_t spm, int do_measur
     if (rc != ME_OK) return rc;
     e->step += (unsigned long long)(n_blocks * spm);
     if (do_measure) e->n_measure += n_blocks;
+    if (e->use_ctr) {            /* the device copy follows, also when this launch is replayed from a CUDA graph */
+        DeviceGuard g(e->cfg.device);
+        k_ctr_advance2<<<1, 1, 0, (cudaStream_t)stream>>>(e->ctr_dev, (unsigned long long)(n_blocks * spm),
+                                                         do_measure ? (unsigned long long)n_blocks : 0ull);
+        if (cudaGetLastError() != cudaSuccess) return fail(e, ME_ERR_CUDA, "advancing the device counters failed");
+    }
     return ME_OK;
 }
 
@@ -901,6 +920,142 @@ int me_pool_reduce(me_engine *e, double *out, int32_t reset, void *stream) {
     }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(e, ME_ERR_CUDA, std::string("pool reduce: ") + cudaGetErrorString(ce));
+    return ME_OK;
+}
+
+}  // extern "C"
+
+/* ----------------------------------------------------------------------------------------- NCCL, loaded lazily
+ * The library does not link NCCL: the Python host already carries torch's copy, a C host names one with
+ * me_comm_set_library() or ME_NCCL_PATH. */
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    int (*getUniqueId)(NcclId *) = nullptr;
+    int (*commInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*commDestroy)(void *) = nullptr;
+    int (*allReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*getErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string err, path;
+};
+std::string g_nccl_path;
+NcclApi &nccl_api() {
+    static NcclApi n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::vector<std::string> names;
+        if (!g_nccl_path.empty()) names.push_back(g_nccl_path);
+        if (const char *env = getenv("ME_NCCL_PATH")) names.push_back(env);
+        names.push_back("libnccl.so.2");
+        names.push_back("libnccl.so");
+        void *h = nullptr;
+        for (auto &nm : names) {
+            h = dlopen(nm.c_str(), RTLD_NOW | RTLD_NOLOAD);          /* the copy the host process already loaded */
+            if (!h) h = dlopen(nm.c_str(), RTLD_NOW | RTLD_GLOBAL);
+            if (h) { n.path = nm; break; }
+        }
+        if (!h) { n.err = "libnccl.so.2 not found (me_comm_set_library / ME_NCCL_PATH)"; return; }
+        bool all = true;
+        auto sym = [&](const char *sname, void **fn) { *fn = dlsym(h, sname); if (!*fn) all = false; };
+        sym("ncclGetUniqueId", (void **)&n.getUniqueId);
+        sym("ncclCommInitRank", (void **)&n.commInitRank);
+        sym("ncclCommDestroy", (void **)&n.commDestroy);
+        sym("ncclAllReduce", (void **)&n.allReduce);
+        sym("ncclGetErrorString", (void **)&n.getErrorString);
+        n.ok = all;
+        if (!all) n.err = "libnccl is missing required symbols";
+    });
+    return n;
+}
+std::string g_comm_error;
+}  // namespace
+
+struct me_comm {
+    void *nccl = nullptr;      /* ncclComm_t */
+    int world = 1, rank = 0, device = 0;
+    bool owned = false;
+};
+
+extern "C" {
+
+int me_comm_set_library(const char *path) {
+    if (!path) return ME_ERR_INVALID;
+    g_nccl_path = path;
+    return ME_OK;
+}
+
+int me_comm_unique_id(unsigned char *id128) {
+    if (!id128) return ME_ERR_INVALID;
+    NcclApi &n = nccl_api();
+    if (!n.ok) { g_comm_error = n.err; return ME_ERR_UNSUPPORTED; }
+    NcclId id;
+    const int rc = n.getUniqueId(&id);
+    if (rc != 0) { g_comm_error = std::string("ncclGetUniqueId: ") + n.getErrorString(rc); return ME_ERR_CUDA; }
+    memcpy(id128, id.internal, 128);
+    return ME_OK;
+}
+
+int me_comm_create(const unsigned char *id128, int32_t world, int32_t rank, int32_t device, me_comm **out) {
+    if (!id128 || !out || world < 1 || rank < 0 || rank >= world) return ME_ERR_INVALID;
+    NcclApi &n = nccl_api();
+    if (!n.ok) { g_comm_error = n.err; return ME_ERR_UNSUPPORTED; }
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    DeviceGuard g(device);
+    void *comm = nullptr;
+    const int rc = n.commInitRank(&comm, world, id, rank);
+    if (rc != 0) { g_comm_error = std::string("ncclCommInitRank: ") + n.getErrorString(rc); return ME_ERR_CUDA; }
+    me_comm *c = new me_comm();
+    c->nccl = comm; c->world = world; c->rank = rank; c->device = device; c->owned = true;
+    *out = c;
+    return ME_OK;
+}
+
+int me_comm_adopt(void *nccl_comm, int32_t world, int32_t rank, int32_t device, me_comm **out) {
+    if (!nccl_comm || !out || world < 1 || rank < 0 || rank >= world) return ME_ERR_INVALID;
+    NcclApi &n = nccl_api();
+    if (!n.ok) { g_comm_error = n.err; return ME_ERR_UNSUPPORTED; }
+    me_comm *c = new me_comm();
+    c->nccl = nccl_comm; c->world = world; c->rank = rank; c->device = device; c->owned = false;
+    *out = c;
+    return ME_OK;
+}
+
+int me_comm_destroy(me_comm *c) {
+    if (!c) return ME_OK;
+    if (c->owned && c->nccl) nccl_api().commDestroy(c->nccl);
+    delete c;
+    return ME_OK;
+}
+
+const char *me_comm_last_error(void) { return g_comm_error.c_str(); }
+
+int me_allreduce_stats(me_engine *e, me_comm *comm, double *inc, double *totals, int64_t n_samples, void *stream) {
+    if (!e || !inc || !totals || n_samples < 0) return ME_ERR_INVALID;
+    if (!e->bound || !e->buf.pool || e->lay.POOL_WORDS == 0) return fail(e, ME_ERR_STATE, "no pool buffer bound");
+    DeviceGuard g(e->cfg.device);
+    const int words = e->lay.POOL_WORDS;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e->grid > 4096 && words <= 256) {
+        if (!e->pool_partial &&
+            cudaMalloc(&e->pool_partial, sizeof(double) * ME_POOL_STAGE_CTAS * words) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(e, ME_ERR_CUDA, "pool reduce: cannot allocate the partial-sum rows");
+        }
+        k_pool_partial<<<ME_POOL_STAGE_CTAS, 256, 0, st>>>(e->buf.pool, e->pool_partial, e->grid, words, 1);
+        k_pool_reduce<<<words + 1, 256, 0, st>>>(e->pool_partial, inc, ME_POOL_STAGE_CTAS, words, 0, 1, (double)n_samples);
+    } else {
+        k_pool_reduce<<<words + 1, 256, 0, st>>>(e->buf.pool, inc, e->grid, words, 1, 1, (double)n_samples);
+    }
+    if (comm && comm->world > 1) {
+        NcclApi &n = nccl_api();
+        const int rc = n.allReduce(inc, inc, (size_t)(words + 1), 8 /* ncclDouble */, 0 /* ncclSum */, comm->nccl, st);
+        if (rc != 0) return fail(e, ME_ERR_CUDA, std::string("ncclAllReduce: ") + n.getErrorString(rc));
+    }
+    k_accumulate<<<(words + 1 + 127) / 128, 128, 0, st>>>(totals, inc, words + 1);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return fail(e, ME_ERR_CUDA, std::string("me_allreduce_stats: ") + cudaGetErrorString(ce));
     return ME_OK;
 }
 

@@ -753,8 +753,13 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     const Rng rng(p, p.chain_offset + (unsigned long long)ch);
     const bool inject = STRICT && p.inj_delta != nullptr;
     const int group = p.group;
-    long long n = p.n_meas0 + (p.do_measure ? b_first : 0);
-    const unsigned step_first = (unsigned)(p.step0 + (unsigned long long)(b_first * p.spm));
+    /* under CUDA-graph replay the kernel parameters are frozen: the step index and the measure counter then come from
+       the device copy that the library advances in-stream after every launch (MeParams::ctr_dev) */
+    unsigned long long step0 = p.step0;
+    long long n_meas0 = p.n_meas0;
+    if (p.ctr_dev != nullptr) { step0 = __ldcg(p.ctr_dev); n_meas0 = (long long)__ldcg(p.ctr_dev + 1); }
+    long long n = n_meas0 + (p.do_measure ? b_first : 0);
+    const unsigned step_first = (unsigned)(step0 + (unsigned long long)(b_first * p.spm));
     long long s_local = 0;
     bool accept = false;
 

@@ -195,8 +195,13 @@ class MetropolisEngine:
         self._shift = torch.tensor(self._shift_host, dtype=f64, device=dev)
         self._last_accept = torch.zeros(self.n_chains, dtype=torch.uint8, device=dev)
         self._pool_out = torch.zeros(max(pw, 1), dtype=f64, device=dev)
-        self._pool_sum = np.zeros(max(pw, 1))
-        self._pool_count = 0
+        # pooled moments live on the device: [POOL_WORDS sums | sample count], summed over ranks inside the library
+        # (me_allreduce_stats); the host reads them once, when statistics are asked for
+        self._pool_inc = torch.zeros(pw + 1, dtype=f64, device=dev)
+        self._pool_tot = torch.zeros(pw + 1, dtype=f64, device=dev)
+        self._pool_pending = 0          # local (chain, measure) samples accumulated since the last reduction
+        self._comm = None
+        self._ctr_on = False
         self._generic = self._d > 32          # large shapes: runtime-shape kernels, unfused step (me_generic.cu)
         self._scratch = torch.zeros((self._d, self.n_chains), dtype=f64, device=dev) if self._generic else None
         bufs = _lib.MeBuffers(_ptr(self.state), _ptr(self._pool), _ptr(self._shift), _ptr(self._last_accept),
@@ -447,7 +452,48 @@ class MetropolisEngine:
                 self._launch(self._lib.me_run(self._h, rows, steps_per_measure, 1, _ptr(t), row0, self._stream()))
         else:
             self._launch(self._lib.me_run(self._h, n_measures, steps_per_measure, 1, None, 0, self._stream()))
-        self._pool_count += n_measures * self.n_chains
+        self._pool_pending += n_measures * self.n_chains
+        self.step_counter += n_measures * steps_per_measure if self._kind == "complex" else 0
+
+    def run_graphed(self, n_measures, steps_per_measure):
+        """``run()`` followed by the pooled-moment reduction and its all-reduce across ranks, as ONE CUDA-graph launch
+        (fused device-functor engines, ``record=False``): for ensembles whose launch lasts only a fraction of a
+        millisecond the per-launch host work otherwise bounds the job.  The first call runs eagerly (it makes every
+        allocation), the second captures, later ones replay; the Philox step index and the measure counter come from
+        the device copy of the counters, so a replay continues the chains exactly like an eager call
+        (``test_graph_replay_of_fused_runs_is_bit_identical``)."""
+        n_measures, steps_per_measure = int(n_measures), int(steps_per_measure)
+        if self._unfused() or self.record:
+            raise RuntimeError("run_graphed serves fused device-functor engines with record=False")
+        key = ("fused", n_measures, steps_per_measure)
+        seen = self._graphs.get(key)
+        if seen is None:                        # first use: eager, so that no allocation happens under capture
+            self.run(n_measures, steps_per_measure)
+            self._flush_pool()
+            self._graphs[key] = "warm"
+            return
+        n, s0 = ctypes.c_int64(), ctypes.c_uint64()
+        self._lib.me_get_counters(self._h, ctypes.byref(n), ctypes.byref(s0))
+        if not self._ctr_on:
+            self._check(self._lib.me_device_counters(self._h, 1, self._stream()))
+            self._ctr_on = True
+        if seen == "warm":
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            pending = self._pool_pending
+            with torch.cuda.graph(g):
+                self._launch(self._lib.me_run(self._h, n_measures, steps_per_measure, 1, None, 0, self._stream()))
+                self._launch(self._lib.me_allreduce_stats(self._h, self._library_comm(), _ptr(self._pool_inc),
+                                                          _ptr(self._pool_tot), n_measures * self.n_chains,
+                                                          self._stream()))
+            self._check(self._lib.me_set_counters(self._h, n.value, s0.value))     # capture moved the host counters
+            self._pool_pending = pending
+            self._graphs[key] = seen = g
+        if self._pool_pending:
+            self._flush_pool()                  # samples of earlier eager runs go in before the graph's own
+        seen.replay()
+        self.launch_count += 3
+        self._check(self._lib.me_set_counters(self._h, n.value + n_measures, s0.value + n_measures * steps_per_measure))
         self.step_counter += n_measures * steps_per_measure if self._kind == "complex" else 0
 
     def step(self, k=1):
@@ -591,7 +637,7 @@ class MetropolisEngine:
             self._launch(self._lib.me_run(self._h, 1, 0, 1, _ptr(t), row0, self._stream()))
         else:
             self._launch(self._lib.me_run(self._h, 1, 0, 1, None, 0, self._stream()))
-        self._pool_count += self.n_chains
+        self._pool_pending += self.n_chains
         if self._term_series is not None and self.record:
             full = self.state[:self._d]
             for tname, fn in self._terms["all"].items():
@@ -628,7 +674,7 @@ class MetropolisEngine:
         self._launch(self._lib.me_run_injected(self._h, int(n_measures), int(steps_per_measure), int(bool(do_measure)),
                                               _ptr(delta), _ptr(u), _ptr(ts), row0, self._stream()))
         if do_measure:
-            self._pool_count += int(n_measures) * self.n_chains
+            self._pool_pending += int(n_measures) * self.n_chains
         self.step_counter += S if self._kind == "complex" else 0
 
     # ------------------------------------------------------------------ counters
@@ -832,20 +878,34 @@ class MetropolisEngine:
         return float(self._pooled(self.accept_count_per_chain[:, None])[0]) / steps
 
     # ------------------------------------------------------------------ clean pooled ensemble statistics
+    def _library_comm(self):
+        if self._distributed and self._comm is None:
+            self._comm = parallel.library_comm(self._lib, self.device.index, self._group)
+        return self._comm if self._distributed else None
+
+    def _flush_pool(self):
+        """Per-CTA accumulators -> fixed-order sum -> all-reduce across ranks (NCCL, inside the library) -> device
+        totals.  Stream-ordered, no host synchronisation."""
+        self._launch(self._lib.me_allreduce_stats(self._h, self._library_comm(), _ptr(self._pool_inc),
+                                                  _ptr(self._pool_tot), int(self._pool_pending), self._stream()))
+        self._pool_pending = 0
+
     def pooled_statistics(self):
         """Ensemble mean / covariance / observable means over every (chain, measure) sample of the whole job,
-        from the in-kernel shifted moments; across ranks this is the path's one all-reduce."""
+        from the in-kernel shifted moments; across ranks this is the path's one all-reduce, issued inside
+        the library (``me_allreduce_stats``).  The moments stay on the device; this call is their one read-back."""
         pw = self._lay.POOL_WORDS
         if pw == 0:
             raise NotImplementedError("parameter space too large for in-kernel pooled moments")
-        self._launch(self._lib.me_pool_reduce(self._h, _ptr(self._pool_out), 1, self._stream()))
-        # running totals live on the host in f64; the all-reduce sums them across ranks
-        self._pool_sum[:pw] += self._pool_out[:pw].cpu().numpy()
-        tot = torch.tensor(np.concatenate([self._pool_sum[:pw], [float(self._pool_count)]]), dtype=torch.float64,
-                           device=self.device)
-        if self._distributed:
-            parallel.allreduce_sum_(tot, self._group)
-        tot = tot.cpu().numpy()
+        if self._distributed and self._library_comm() is None:
+            # no NCCL group (e.g. gloo on a CPU-only rendezvous): reduce locally, sum across ranks through torch
+            self._launch(self._lib.me_allreduce_stats(self._h, None, _ptr(self._pool_inc), _ptr(self._pool_tot),
+                                                      int(self._pool_pending), self._stream()))
+            self._pool_pending = 0
+            tot = parallel.allreduce_sum_(self._pool_tot.clone(), self._group).cpu().numpy()
+        else:
+            self._flush_pool()
+            tot = self._pool_tot.cpu().numpy()
         if tot[-1] < 2:
             raise RuntimeError("pooled statistics need at least two measured samples")
         return parallel.finalize_pooled(tot[:pw], tot[-1], self._shift_host, self.num_real_params,
@@ -855,8 +915,8 @@ class MetropolisEngine:
         """Forget the pooled moments accumulated so far (e.g. after burn-in)."""
         if self._lay.POOL_WORDS:
             self._launch(self._lib.me_pool_reduce(self._h, _ptr(self._pool_out), 1, self._stream()))
-        self._pool_sum[:] = 0.0
-        self._pool_count = 0
+        self._pool_tot.zero_()
+        self._pool_pending = 0
 
     # ------------------------------------------------------------------ output (ME:466-479)
     def time_series(self):
@@ -1019,7 +1079,7 @@ class MetropolisEngine:
         self._lib.me_get_counters(self._h, ctypes.byref(n), ctypes.byref(s))
         return dict(state=self.state.clone(), n_measure=n.value, step=s.value, seed=self.seed,
                     chain_offset=self.chain_offset, pool=None if self._pool is None else self._pool.clone(),
-                    pool_sum=self._pool_sum.copy(), pool_count=self._pool_count)
+                    pool_tot=self._pool_tot.clone(), pool_pending=self._pool_pending)
 
     def load_state_dict(self, sd):
         if sd["state"].shape != self.state.shape:
@@ -1028,6 +1088,8 @@ class MetropolisEngine:
         self.state.copy_(sd["state"])
         if self._pool is not None and sd.get("pool") is not None:
             self._pool.copy_(sd["pool"])
-        self._pool_sum = np.array(sd["pool_sum"], dtype=np.float64)
-        self._pool_count = int(sd["pool_count"])
+        self._pool_tot.copy_(sd["pool_tot"])
+        self._pool_pending = int(sd["pool_pending"])
         self._check(self._lib.me_set_counters(self._h, int(sd["n_measure"]), int(sd["step"])))
+        if self._ctr_on:
+            self._check(self._lib.me_device_counters(self._h, 1, self._stream()))

@@ -79,3 +79,53 @@ def finalize_pooled(sums, count, shift, n_real, n_complex):
     cov_c = (cov[re, re] + cov[im, im]) + 1j * (cov[im, re] - cov[re, im])
     return dict(mean_real=mean[:nr].copy(), mean_complex=mean[re] + 1j * mean[im], cov_real=cov[:nr, :nr].copy(),
                 cov_complex=cov_c, observables_mean=obs / n, count=int(count))
+
+
+_LIBRARY_COMMS = {}
+
+
+def nccl_library_path():
+    """The NCCL shared object the process already carries (torch's bundled copy), for me_comm_set_library."""
+    import os
+    try:
+        import nvidia.nccl as nv
+        base = list(nv.__path__)[0]
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except Exception:
+        pass
+    return None
+
+
+def library_comm(lib, device_index, group=None):
+    """The library-side NCCL communicator (``me_comm``, include/me_b200.h) of this rank, created once per device:
+    rank 0 draws the NCCL unique id inside the library, torch.distributed carries the 128 bytes to the other ranks,
+    every rank joins with ``me_comm_create``.  Returns a ctypes handle (None when there is one rank or no CUDA
+    process group) — ``me_allreduce_stats`` then runs the collective inside the library, stream-ordered, with no host
+    round trip."""
+    import ctypes
+    import torch.distributed as dist
+    rank, world_size = world(group)
+    if world_size <= 1 or dist.get_backend(group) != "nccl":
+        return None
+    key = (device_index, id(group))
+    if key in _LIBRARY_COMMS:
+        return _LIBRARY_COMMS[key]
+    path = nccl_library_path()
+    if path:
+        lib.me_comm_set_library(path.encode())
+    buf = (ctypes.c_ubyte * 128)()
+    if rank == 0:
+        rc = lib.me_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError("me_comm_unique_id: " + lib.me_comm_last_error().decode())
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ident = (ctypes.c_ubyte * 128).from_buffer_copy(box[0])
+    comm = ctypes.c_void_p()
+    rc = lib.me_comm_create(ident, world_size, rank, device_index, ctypes.byref(comm))
+    if rc != 0:
+        raise RuntimeError("me_comm_create: " + lib.me_comm_last_error().decode())
+    _LIBRARY_COMMS[key] = comm
+    return comm

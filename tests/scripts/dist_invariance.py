@@ -44,6 +44,20 @@ def main():
             ok = ok and np.allclose(ps[k], rps[k], rtol=1e-11, atol=1e-13)
         ok = ok and ps["count"] == rps["count"] == 70 * n
         ok = ok and np.allclose(mean_attr, ref.real_mean, rtol=1e-12) and np.allclose(cov_attr, ref.covariance_matrix_complex, rtol=1e-12)
+    # the same collective from inside a CUDA graph: [fused run -> reduce -> NCCL all-reduce (library) -> accumulate]
+    kw2 = dict(initial_real_params=np.zeros(2), temp=.1, seed=78, record=False)
+    g = me.MetropolisEngine(("xy_well", 1.0), n_chains=n, distributed=True, **kw2)
+    for _ in range(4):
+        g.run_graphed(25, 4)
+    gps = g.pooled_statistics()
+    if rank == 0:
+        ref2 = me.MetropolisEngine(("xy_well", 1.0), n_chains=n, **kw2)
+        for _ in range(4):
+            ref2.run(25, 4)
+        r2 = ref2.pooled_statistics()
+        ok = ok and gps["count"] == r2["count"] == 100 * n
+        for k in ("mean_real", "cov_real", "observables_mean"):
+            ok = ok and np.allclose(gps[k], r2[k], rtol=1e-11, atol=1e-13)
     # every rank must hold the same pooled numbers
     v = torch.tensor(np.concatenate([ps["mean_real"], np.diag(ps["cov_real"])]), device="cuda")
     lo, hi = v.clone(), v.clone()

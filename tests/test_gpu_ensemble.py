@@ -290,3 +290,32 @@ def test_time_segmentation_also_serves_runtime_compiled_functors():
             else:
                 os.environ["ME_SEGMENTS"] = old
     assert torch.equal(run(1), run(4))
+
+
+@pytest.mark.parametrize("shape", ["c2_segmented", "c3"])
+def test_graph_replay_of_fused_runs_is_bit_identical(shape):
+    """run_graphed(): [fused run -> pooled-moment reduction -> (all-reduce) -> accumulate] as one CUDA-graph launch.  The
+    step index and measure counter come from the device copy of the counters, so replays continue the chains exactly
+    like eager launches: same state, same pooled moments (device-resident totals, me_allreduce_stats)."""
+    import metropolisengine_b200 as me
+    if shape == "c3":
+        kw = dict(initial_real_params=np.zeros(3), initial_complex_params=np.zeros(4, dtype=complex), temp=.1,
+                  n_chains=8192, seed=5, record=False)
+        energy, M, K = ("mixed_well", 1.0, -1.0, 0.5, 1.0), 12, 5
+    else:                           # 65,536 chains x 3,200 steps: the work-queue time segmentation is active
+        kw = dict(initial_real_params=np.array([0., 0.]), temp=.1, n_chains=65536, seed=5, record=False)
+        energy, M, K = ("xy_well", 1.0), 320, 10
+    a = me.MetropolisEngine(energy, **kw)
+    b = me.MetropolisEngine(energy, **kw)
+    for _ in range(5):
+        a.run(M, K)
+        b.run_graphed(M, K)
+    b.run(3, 2)                     # an eager launch after replays continues from the same counters
+    a.run(3, 2)
+    torch.cuda.synchronize()
+    assert a.measure_step_counter == b.measure_step_counter and a.steps_done == b.steps_done
+    assert torch.equal(a.state, b.state)
+    pa, pb = a.pooled_statistics(), b.pooled_statistics()
+    assert pa["count"] == pb["count"] == (5 * M + 3) * kw["n_chains"]
+    for k in ("mean_real", "cov_real", "observables_mean"):
+        assert np.allclose(pa[k], pb[k], rtol=1e-12, atol=1e-15), k
