@@ -281,13 +281,24 @@ const double *log_table(int device) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = tabs.find(device);
     if (it != tabs.end()) return it->second;
-    std::vector<double> host(2 * ME_LOGTAB_ENTRIES);
+    std::vector<double> host(2 * (ME_LOGTAB_ENTRIES + ME_SINTAB_ENTRIES));
     const int fold = (int)(0.4142135623730951 * ME_LOGTAB_ENTRIES);          /* first interval whose upper edge exceeds sqrt 2 */
     for (int i = 0; i < ME_LOGTAB_ENTRIES; i++) {
         const double c = 1.0 + (double)(i + 1) / (double)ME_LOGTAB_ENTRIES;
         const double rc = (double)(float)(1.0 / c);
         host[2 * i] = rc;
         host[2 * i + 1] = (double)(2.0L * logl(i >= fold ? (long double)rc * 2.0L : (long double)rc));
+    }
+    /* sin/cos of the interval midpoints (me_math.cuh, sincospi_tab); the second half of the circle is the exact negative
+       of the first, so that opposite angle words give exactly opposite normals */
+    double *sc = host.data() + 2 * ME_LOGTAB_ENTRIES;
+    const long double two_pi = 6.283185307179586476925286766559L;
+    for (int i = 0; i < ME_SINTAB_ENTRIES / 2; i++) {
+        const long double a = ((long double)i + 0.5L) * two_pi / (long double)ME_SINTAB_ENTRIES;
+        sc[2 * i] = (double)sinl(a);
+        sc[2 * i + 1] = (double)cosl(a);
+        sc[2 * (i + ME_SINTAB_ENTRIES / 2)] = -sc[2 * i];
+        sc[2 * (i + ME_SINTAB_ENTRIES / 2) + 1] = -sc[2 * i + 1];
     }
     DeviceGuard g(device);
     double *dev = nullptr;
