@@ -1,5 +1,7 @@
-/* me_k4.cu — shared-covariance step kernel for large parameter spaces (BASELINE config 4: 1 real + 64 complex
- * Fourier-mode coefficients, 32,768 chains), tcgen05 tensor cores.
+/* me_k4_v1.cu — FIRST version of the shared-covariance step kernel (1 real + 64 complex only), kept as the measured
+ * baseline of the warp-specialised pipeline in me_k4_device.cuh: every warp of the CTA generates, waits for the MMA and runs
+ * the epilogue in lock step (two CTA-wide barriers per step).  Selected with ME_K4_V1=1 in the environment; its random
+ * stream (Philox4x32-10, scalar slot 32) is not the one the oracle restates.
  *
  * Same Metropolis step as me_device.cuh (reference metropolis_engine.py:241-259: proposal, hard wall ME:247, energy
  * ME:250, decision ME:319-338, Robbins-Monro width ME:429-438), but the proposal covariance of the complex block is
@@ -451,509 +453,33 @@ __global__ void __launch_bounds__(K4_THREADS, 1) k4_steps(const __grid_constant_
     if (warp == 0) tmem_dealloc(tmem_d, K4_N);
 }
 
-/* -------------------------------------------------------------------------------------------- init / measure */
-__global__ void k4_init(K4Params p, const double *x0, int broadcast, double sigma0) {
-    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= p.n_chains) return;
-    const long long ld = p.ld;
-    double tot = 0.0, qsum = 0.0;
-    const double a = broadcast ? x0[0] : x0[ch];
-    p.state[(long long)K4_X * ld + ch] = a;
-    p.state[(long long)K4_MEAN * ld + ch] = a;
-    for (int j = 0; j < K4_NC; j++) {
-        const double re = broadcast ? x0[1 + j] : x0[(long long)(1 + j) * ld + ch];
-        const double im = broadcast ? x0[1 + K4_NC + j] : x0[(long long)(1 + K4_NC + j) * ld + ch];
-        p.state[(long long)(K4_X + 1 + j) * ld + ch] = re;
-        p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch] = im;
-        p.state[(long long)(K4_MEAN + 1 + j) * ld + ch] = re;
-        p.state[(long long)(K4_MEAN + 1 + K4_NC + j) * ld + ch] = im;
-        const double m2 = re * re + im * im, q = (double)(j - K4_NC / 2);
-        tot += m2;
-        qsum += q * q * m2;
-        p.state[(long long)(K4_OBSM + 1 + j) * ld + ch] = hypot(re, im);
-    }
-    p.state[(long long)K4_OBSM * ld + ch] = fabs(a);
-    p.state[(long long)(K4_OBSM + 1 + K4_NC) * ld + ch] = a * a;
-    p.state[(long long)K4_E * ld + ch] = k4_energy(a, tot, qsum, p);
-    p.state[(long long)K4_SIG * ld + ch] = sigma0;
-    p.state[(long long)K4_NACC * ld + ch] = 0.0;
-    p.state[(long long)K4_STATUS * ld + ch] = 0.0;
-}
-
-/* measure (ME:342-356 without the per-chain covariance, which is shared): running means (ME:404-410), observable
- * means (ME:412-414, 458-463), one time-series row [129 params, E, sigma].  n = counter after the increment. */
-__global__ void k4_measure(K4Params p) {
-    /* one thread per (slot, chain): slot j < 64 = complex mode j, slot 64 = real parameter + energy + sigma */
-    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (ch >= p.n_chains) return;
-    const long long ld = p.ld;
-    const double dn = (double)p.n_meas, inv_n = 1.0 / dn, shrink = (dn - 1.0) * inv_n;
-    double *row = p.record ? p.ts + p.ts_row * (long long)(K4_D + 2) * ld + ch : nullptr;
-    if (j == K4_NC) {
-        const double a = p.state[(long long)K4_X * ld + ch];
-        double *mp = &p.state[(long long)K4_MEAN * ld + ch];
-        *mp = *mp * shrink + a * inv_n;
-        double *o0 = &p.state[(long long)K4_OBSM * ld + ch], *o1 = &p.state[(long long)(K4_OBSM + 1 + K4_NC) * ld + ch];
-        *o0 = *o0 * shrink + fabs(a) * inv_n;
-        *o1 = *o1 * shrink + (a * a) * inv_n;
-        if (row) {
-            __stcs(row, a);
-            __stcs(row + (long long)K4_D * ld, p.state[(long long)K4_E * ld + ch]);
-            __stcs(row + (long long)(K4_D + 1) * ld, p.state[(long long)K4_SIG * ld + ch]);
-        }
-        return;
-    }
-    const double re = p.state[(long long)(K4_X + 1 + j) * ld + ch];
-    const double im = p.state[(long long)(K4_X + 1 + K4_NC + j) * ld + ch];
-    double *mr = &p.state[(long long)(K4_MEAN + 1 + j) * ld + ch];
-    double *mi = &p.state[(long long)(K4_MEAN + 1 + K4_NC + j) * ld + ch];
-    *mr = *mr * shrink + re * inv_n;
-    *mi = *mi * shrink + im * inv_n;
-    double *ob = &p.state[(long long)(K4_OBSM + 1 + j) * ld + ch];
-    *ob = *ob * shrink + hypot(re, im) * inv_n;
-    if (row) {
-        __stcs(row + (long long)(1 + j) * ld, re);
-        __stcs(row + (long long)(1 + K4_NC + j) * ld, im);
-    }
-}
-
-/* Pooled moments of the current states, deterministic two-stage reduction (no atomics: the covariance feeds the
- * proposals, so run-to-run bit reproducibility needs a fixed summation order).
- *
- * With Y = [Re c; Im c] (128 rows) about the shift, everything the complex second moment needs is in the LOWER triangle of
- * the real symmetric S = sum_chains Y Y^T (128 x 128):
- *     Re (c c^H)_ij = S[i][j] + S[64+i][64+j],    Im (c c^H)_ij = S[64+i][j] - S[64+j][i]
- * — a rank-k update with half the flops of the full complex outer product (8,256 instead of 16,384 FMAs per chain).
- * Stage 1: CTA b sums its slice of chains.  Chains are staged 32 at a time in shared memory as Ys[k][row]; thread t < 136
- *          owns the 8 x 8 register tile (ti, tj), tj <= ti, of S (64 independent FMA chains per thread: the FP64 pipe
- *          stays full with ~1 warp per sub-partition); threads 136..255 keep the column sums of Y.
- *          part[b]: [0] chains, [1] sum sigma, [2] sum a, [3] sum a^2, [4..132) sum Y, [132..) S row-major (lower part).
- * Stage 2: fixed-order sum over the CTAs (2a), emitted in the complex layout the host accumulates (2b):
- *          out[K4_MOMW] (double2): [0] chains, [1] sum sigma, [2] sum a, [3] sum a^2, [4..68) sum c, [68..) sum c c^H. */
-constexpr int K4_MOMW = 4 + K4_NC + K4_NC * K4_NC;
-constexpr int K4_MOM_CHUNK = 32;
-constexpr int K4_PARTW = 4 + K4_N + K4_N * K4_N;        /* doubles per CTA partial */
-
-__global__ void __launch_bounds__(256) k4_moments_stage1(K4Params p, const double *shift, double *part,
-                                                         long long chains_per_cta) {
-    /* Ys[k][pos(row)]: every block of 8 rows is followed by 2 pad doubles, so that the 16-byte reads of lanes that own
-       neighbouring tiles (80 B apart) fall into distinct banks; the row length 162 keeps the staging stores (same
-       row, consecutive k) at 4-way instead of 32-way conflicts. */
-    constexpr int YLD = K4_N + 2 * (K4_N / 8) + 2;       /* 162 */
-    __shared__ __align__(16) double Ys[K4_MOM_CHUNK][YLD];   /* 41 KB */
-    auto pos = [](int row) { return row + 2 * (row >> 3); };
-    __shared__ double red[256];
-    const int tid = threadIdx.x;
-    const long long lo = (long long)blockIdx.x * chains_per_cta;
-    long long hi = lo + chains_per_cta;
-    if (hi > p.n_chains) hi = p.n_chains;
-    const long long ld = p.ld;
-    /* tile of thread t < 136: row-major enumeration of the lower triangle of the 16 x 16 tile grid */
-    int ti = 0, tj = 0;
-    {
-        int t = tid < 136 ? tid : 0;
-        while (t > ti) { t -= ti + 1; ti++; }
-        tj = t;
-    }
-    const bool tile_thread = tid < 136;
-    double acc[8][8];
-#pragma unroll
-    for (int a = 0; a < 8; a++)
-#pragma unroll
-        for (int b = 0; b < 8; b++) acc[a][b] = 0.0;
-    double colsum = 0.0, colsum2 = 0.0;                   /* thread 136 + r: sum of Y[r] (and of Y[120 + r] for r < 8) */
-    double sa = 0.0, sa2 = 0.0, ssig = 0.0;               /* threads < 32 */
-    for (long long base = lo; base < hi; base += K4_MOM_CHUNK) {
-        const int cnt = (int)((hi - base) < K4_MOM_CHUNK ? (hi - base) : K4_MOM_CHUNK);
-        __syncthreads();
-        /* stage: consecutive threads read consecutive chains of one state word (coalesced), write Ys[k][row] */
-        for (int e = tid; e < K4_N * K4_MOM_CHUNK; e += 256) {
-            const int row = e / K4_MOM_CHUNK, k = e % K4_MOM_CHUNK;
-            Ys[k][pos(row)] = k < cnt ? p.state[(long long)(K4_X + 1 + row) * ld + base + k] - shift[1 + row] : 0.0;
-        }
-        if (tid < cnt) {
-            const double a = p.state[(long long)K4_X * ld + base + tid] - shift[0];
-            sa += a; sa2 += a * a; ssig += p.state[(long long)K4_SIG * ld + base + tid];
-        }
-        __syncthreads();
-        if (tile_thread) {
-#pragma unroll 4
-            for (int k = 0; k < K4_MOM_CHUNK; k++) {
-                double ya[8], yb[8];
-                const double2 *pa = reinterpret_cast<const double2 *>(&Ys[k][10 * ti]);     /* pos(8 ti) */
-                const double2 *pb = reinterpret_cast<const double2 *>(&Ys[k][10 * tj]);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const double2 va = pa[q], vb = pb[q];
-                    ya[2 * q] = va.x; ya[2 * q + 1] = va.y; yb[2 * q] = vb.x; yb[2 * q + 1] = vb.y;
-                }
-#pragma unroll
-                for (int a = 0; a < 8; a++)
-#pragma unroll
-                    for (int b = 0; b < 8; b++) acc[a][b] = fma(ya[a], yb[b], acc[a][b]);
-            }
-        } else {
-            const int r = tid - 136;
-            for (int k = 0; k < K4_MOM_CHUNK; k++) colsum += Ys[k][pos(r)];
-            if (r < 8)
-                for (int k = 0; k < K4_MOM_CHUNK; k++) colsum2 += Ys[k][pos(120 + r)];
-        }
-    }
-    double *out = part + (long long)blockIdx.x * K4_PARTW;
-    if (tile_thread) {
-#pragma unroll
-        for (int a = 0; a < 8; a++)
-#pragma unroll
-            for (int b = 0; b < 8; b++) out[4 + K4_N + (8 * ti + a) * K4_N + (8 * tj + b)] = acc[a][b];
-    }
-    if (!tile_thread) {
-        out[4 + (tid - 136)] = colsum;
-        if (tid - 136 < 8) out[4 + 120 + (tid - 136)] = colsum2;
-    }
-    /* the three scalar sums: fixed-order trees */
-    for (int which = 0; which < 3; which++) {
-        __syncthreads();
-        red[tid] = (tid < K4_MOM_CHUNK) ? (which == 0 ? ssig : (which == 1 ? sa : sa2)) : 0.0;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-        if (tid == 0) out[1 + which] = red[0];
-    }
-    if (tid == 0) out[0] = (double)(hi > lo ? hi - lo : 0);
-}
-
-/* stage 2a: total[idx] = sum over the CTA partials in CTA order (one thread per word, coalesced across threads;
- * the upper triangle of S is never read, its threads idle) */
-__global__ void k4_moments_stage2a(const double *part, int n_parts, double *total) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= K4_PARTW) return;
-    if (idx >= 4 + K4_N) {
-        const int e = idx - 4 - K4_N;
-        if (e / K4_N < e % K4_N) return;
-    }
-    /* loads in batches of 16 (independent), adds in CTA order (fixed summation order) */
-    double t = 0.0;
-    int b = 0;
-    for (; b + 16 <= n_parts; b += 16) {
-        double v[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) v[q] = part[(long long)(b + q) * K4_PARTW + idx];
-#pragma unroll
-        for (int q = 0; q < 16; q++) t += v[q];
-    }
-    for (; b < n_parts; b++) t += part[(long long)b * K4_PARTW + idx];
-    total[idx] = t;
-}
-/* stage 2b: the complex layout the host accumulates.  Optionally (single-GPU fast path) the running moments are
- * advanced here, mom[w] += inc[w] for w != 1, and a snapshot [mom (MOMW) | inc[0], inc[1]] is written for a factor
- * refresh that runs asynchronously on another stream. */
-__global__ void k4_moments_stage2b(const double *total, double2 *out, double2 *mom, double2 *snap) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= K4_MOMW) return;
-    double2 v;
-    if (w < 4) v = make_double2(total[w], 0.0);
-    else if (w < 4 + K4_NC) { const int i = w - 4; v = make_double2(total[4 + i], total[4 + K4_NC + i]); }
-    else {
-        const int e = w - 4 - K4_NC, i = e / K4_NC, j = e % K4_NC;
-        auto S = [&](int r, int c) { return total[4 + K4_N + (r >= c ? r * K4_N + c : c * K4_N + r)]; };   /* symmetric */
-        v = make_double2(S(i, j) + S(K4_NC + i, K4_NC + j), S(K4_NC + i, j) - S(K4_NC + j, i));
-    }
-    out[w] = v;
-    if (mom != nullptr) {
-        double2 m = mom[w];
-        if (w != 1) { m.x += v.x; m.y += v.y; mom[w] = m; }
-        if (snap != nullptr) {
-            snap[w] = m;
-            if (w < 2) snap[K4_MOMW + w] = v;
-        }
-    }
-}
-
-/* 1 / sqrt(d) for a normal positive d: MUFU.RSQ64H seed + two Newton steps (relative error ~1e-16) */
-__device__ __forceinline__ double k4_rsqrt(double d) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e = fma(-d, y * y, 1.0);
-    y = fma(0.5 * y, e, y);
-    e = fma(-d, y * y, 1.0);
-    return fma(0.5 * y, e, y);
-}
-
-/* Pooled covariance -> shared proposal factor, one CTA (runs once per measure after the 50th, ME:389,396).
- * mom (complex, as double pairs): [0] sample count N, [2] sum a, [3] sum a^2, [4..68) sum c, [68..) sum c c^H
- * (about a fixed shift); inc: [0] chains measured now, [1] sum of their sigma.  Computes
- *   C_c = (S2 - S1 S1^H / N)/(N-1) + small I,  small = mean(sigma)^2 / n   (the regulariser of ME:418,425),
- * its Cholesky factor G, the BF16 UMMA operand of me_k4_step, and the same for the real parameter.
- * Cholesky: left-looking by columns, 4 threads per row splitting the dot product (fixed order + shuffle tree), two
- * barriers per column, pivot through one reciprocal square root.  status: nonzero if a pivot was not positive. */
-__global__ void __launch_bounds__(256) k4_refactor(const double2 *mom, const double2 *inc, long long n_meas,
-                                                   double2 *cov_c, double *cov_a, __nv_bfloat16 *factor, double *s_a,
-                                                   int *status) {
-    constexpr int LDA = K4_NC + 1;                       /* padded row length (double2) */
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    double2 *A = reinterpret_cast<double2 *>(smem_raw);  /* A[i * LDA + j] */
-    __shared__ double2 col[K4_NC];
-    __shared__ int bad;
-    const int tid = threadIdx.x, row = tid >> 2, part = tid & 3;
-    const double N = mom[0].x;
-    const double sm = inc[1].x / inc[0].x;
-    const double small = sm * sm / (double)n_meas;
-    const double inv_n = 1.0 / N, inv_n1 = 1.0 / (N - 1.0);
-    const double2 *s1 = mom + 4, *s2 = mom + 4 + K4_NC;
-    if (tid == 0) bad = 0;
-    for (int e = tid; e < K4_NC * K4_NC; e += blockDim.x) {
-        const int i = e / K4_NC, j = e % K4_NC;
-        /* s1_i conj(s1_j) */
-        const double pr = s1[i].x * s1[j].x + s1[i].y * s1[j].y, pi = s1[i].y * s1[j].x - s1[i].x * s1[j].y;
-        double2 v;
-        v.x = (s2[e].x - pr * inv_n) * inv_n1 + (i == j ? small : 0.0);
-        v.y = (s2[e].y - pi * inv_n) * inv_n1;
-        A[i * LDA + j] = v;
-        cov_c[e] = v;
-    }
-    if (tid == 0) {
-        const double va = (mom[3].x - mom[2].x * mom[2].x * inv_n) * inv_n1 + small;
-        *cov_a = va;
-        *s_a = sqrt(va);
-    }
-    __syncthreads();
-    for (int j = 0; j < K4_NC; j++) {
-        /* v_i = A_ij - sum_{k<j} G_ik conj(G_jk), rows i >= j; the four parts of a row are adjacent lanes */
-        double ar = 0.0, ai = 0.0;
-        if (row >= j) {
-            for (int k = part; k < j; k += 4) {
-                const double2 pq = A[row * LDA + k], q = A[j * LDA + k];
-                ar = fma(pq.x, q.x, fma(pq.y, q.y, ar));
-                ai = fma(pq.y, q.x, fma(-pq.x, q.y, ai));
-            }
-        }
-        ar += __shfl_xor_sync(0xffffffffu, ar, 1); ai += __shfl_xor_sync(0xffffffffu, ai, 1);
-        ar += __shfl_xor_sync(0xffffffffu, ar, 2); ai += __shfl_xor_sync(0xffffffffu, ai, 2);
-        if (part == 0 && row >= j) {
-            const double2 a0 = A[row * LDA + j];
-            col[row] = make_double2(a0.x - ar, a0.y - ai);
-        }
-        __syncthreads();
-        double d = col[j].x;
-        if (!(d > 0.0)) { if (tid == 0) bad = 1; d = small > 0.0 ? small : 1e-300; }
-        const double inv = k4_rsqrt(d);
-        if (part == 0 && row >= j) {
-            const double2 v = col[row];
-            A[row * LDA + j] = row == j ? make_double2(d * inv, 0.0) : make_double2(v.x * inv, v.y * inv);
-        }
-        __syncthreads();
-    }
-    /* B[2i][2j] = Gr/sqrt2, B[2i][2j+1] = Gi/sqrt2, B[2i+1][2j] = -Gi/sqrt2, B[2i+1][2j+1] = Gr/sqrt2; stored
-       BF16 at [k/8][n][k%8] */
-    const double rs = 0.70710678118654752440;
-    for (int e = tid; e < K4_N * K4_N; e += blockDim.x) {
-        const int nrow = e / K4_N, k = e % K4_N;
-        const int i = nrow >> 1, jj = k >> 1;
-        double v = 0.0;
-        if (jj <= i) {
-            const double2 gij = A[i * LDA + jj];
-            const bool ro = nrow & 1, ko = k & 1;
-            v = (ro == ko) ? gij.x : (ro ? -gij.y : gij.y);
-            if (jj == i && ro != ko) v = 0.0;       /* diagonal of G is real */
-        }
-        factor[(k >> 3) * (K4_N * 8) + nrow * 8 + (k & 7)] = __double2bfloat16(v * rs);
-    }
-    if (tid == 0 && status) *status = bad;
-}
 
 }  // namespace
 
-/* ============================================================================================ C ABI */
-struct me_k4 {
-    me_k4_config cfg;
-    double *state = nullptr;
-    const void *factor = nullptr;
-    unsigned char *last_accept = nullptr;
-    long long n_measure = 1;
-    unsigned long long step = 0;
-    int n_sm = 148;
-    int reserved_sms = 0;          /* SMs the step kernel leaves free (for a concurrent factor refresh) */
-    std::string err;
-};
-
-static std::string g_k4_create_error;
-static int k4_fail(me_k4 *e, int code, const std::string &msg) {
-    if (e) e->err = msg; else g_k4_create_error = msg;
-    return code;
-}
-
-static void k4_base(me_k4 *e, K4Params &p) {
+/* launcher used by me_k4.cu when ME_K4_V1=1 */
+extern "C" int me_k4v1_steps(double *state, long long ld, long long n_chains, unsigned long long chain_offset,
+                             unsigned long long seed, unsigned long long step0, long long n_steps, int n_sm_avail,
+                             long long n_meas, double temp, double target, double ratio, const double *consts4, int use_wall,
+                             const void *factor, const double *s_a, unsigned char *last_accept, float *dbg_z,
+                             float *dbg_delta, void *stream) {
+    K4Params p;
     memset(&p, 0, sizeof(p));
-    p.state = e->state;
-    p.ld = e->cfg.n_chains;
-    p.n_chains = e->cfg.n_chains;
-    p.chain_offset = (unsigned long long)e->cfg.chain_offset;
+    p.state = state; p.ld = ld; p.n_chains = n_chains; p.chain_offset = chain_offset;
     for (int r = 0; r < 10; r++) {
-        p.rk[2 * r] = (unsigned)e->cfg.seed + (unsigned)r * 0x9E3779B9u;
-        p.rk[2 * r + 1] = (unsigned)(e->cfg.seed >> 32) + (unsigned)r * 0xBB67AE85u;
+        p.rk[2 * r] = (unsigned)seed + (unsigned)r * 0x9E3779B9u;
+        p.rk[2 * r + 1] = (unsigned)(seed >> 32) + (unsigned)r * 0xBB67AE85u;
     }
-    p.step0 = e->step;
-    p.n_meas = e->n_measure;
-    p.temp = e->cfg.temp;
-    p.inv_temp = e->cfg.temp != 0 ? 1.0 / e->cfg.temp : 0.0;
-    p.target = e->cfg.target_acceptance;
-    p.ratio = e->cfg.ratio;
-    p.m = 1 + K4_NC;
-    p.kappa = e->cfg.consts[0]; p.alpha = e->cfg.consts[1]; p.gamma = e->cfg.consts[2]; p.beta = e->cfg.consts[3];
-    p.use_wall = e->cfg.use_reject;
-    p.factor = e->factor;
-    p.last_accept = e->last_accept;
-}
-
-extern "C" {
-
-int me_k4_layout_get(me_k4_layout *o) {
-    if (!o) return ME_ERR_INVALID;
-    o->X = K4_X; o->E = K4_E; o->SIG = K4_SIG; o->MEAN = K4_MEAN; o->OBSM = K4_OBSM; o->NACC = K4_NACC;
-    o->STATUS = K4_STATUS; o->WORDS = K4_WORDS; o->D = K4_D; o->TS_COLS = K4_D + 2; o->N_COMPLEX = K4_NC;
-    o->TILE = K4_TILE; o->FACTOR_BYTES = K4_N * K4_N * 2; o->MOM_WORDS = K4_MOMW;
-    o->MOM_SCRATCH_PER_SM = K4_PARTW;
-    return ME_OK;
-}
-
-int me_k4_create(const me_k4_config *cfg, me_k4 **out) {
-    if (!cfg || !out) return k4_fail(nullptr, ME_ERR_INVALID, "null argument");
-    if (cfg->n_real != 1 || cfg->n_complex != K4_NC)
-        return k4_fail(nullptr, ME_ERR_UNSUPPORTED, "the shared-covariance tensor-core path is built for 1 real + 64 complex parameters");
-    if (cfg->n_chains <= 0 || cfg->n_chains % K4_TILE != 0)
-        return k4_fail(nullptr, ME_ERR_INVALID, "n_chains must be a positive multiple of 128 (one MMA tile = 128 chains)");
-    if (!(cfg->temp >= 0)) return k4_fail(nullptr, ME_ERR_INVALID, "temp must be >= 0 (reference: assert, ME:92)");
-    me_k4 *e = new me_k4();
-    e->cfg = *cfg;
-    int n_sm = 0;
-    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) e->n_sm = n_sm;
-    else cudaGetLastError();
-    *out = e;
-    return ME_OK;
-}
-
-int me_k4_destroy(me_k4 *e) { delete e; return ME_OK; }
-
-int me_k4_bind(me_k4 *e, double *state, const void *factor_bf16, unsigned char *last_accept) {
-    if (!e || !state || !factor_bf16) return ME_ERR_INVALID;
-    e->state = state; e->factor = factor_bf16; e->last_accept = last_accept;
-    return ME_OK;
-}
-
-int me_k4_set_factor(me_k4 *e, const void *factor_bf16) {
-    if (!e || !factor_bf16) return ME_ERR_INVALID;
-    e->factor = factor_bf16;
-    return ME_OK;
-}
-
-int me_k4_set_reserved_sms(me_k4 *e, int32_t n) {
-    if (!e || n < 0) return ME_ERR_INVALID;
-    e->reserved_sms = n;
-    return ME_OK;
-}
-
-int me_k4_init(me_k4 *e, const double *x0, int32_t broadcast, double sigma0, void *stream) {
-    if (!e || !e->state || !x0) return ME_ERR_INVALID;
-    K4Params p;
-    k4_base(e, p);
-    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    const int block = 128, grid = (int)((e->cfg.n_chains + block - 1) / block);
-    k4_init<<<grid, block, 0, (cudaStream_t)stream>>>(p, x0, broadcast, sigma0);
-    cudaError_t ce = cudaGetLastError();
-    cudaSetDevice(prev);
-    e->n_measure = 1; e->step = 0;
-    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_init: ") + cudaGetErrorString(ce));
-    return ME_OK;
-}
-
-int me_k4_step(me_k4 *e, int64_t n_steps, const double *s_a, float *dbg_z, float *dbg_delta, void *stream) {
-    if (!e || !e->state || !s_a) return ME_ERR_INVALID;
-    if (n_steps <= 0) return ME_OK;
-    if (e->step + (unsigned long long)n_steps >= 0xffffffffull) return k4_fail(e, ME_ERR_INVALID, "step counter overflow");
-    K4Params p;
-    k4_base(e, p);
-    p.n_steps = n_steps; p.s_a = s_a; p.dbg_z = dbg_z; p.dbg_delta = dbg_delta;
-    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    /* the attribute is per device: set it before every launch (a host-side table write, no device work) */
+    p.step0 = step0; p.n_steps = n_steps; p.n_meas = n_meas;
+    p.temp = temp; p.inv_temp = temp != 0 ? 1.0 / temp : 0.0; p.target = target; p.ratio = ratio; p.m = 1 + K4_NC;
+    p.kappa = consts4[0]; p.alpha = consts4[1]; p.gamma = consts4[2]; p.beta = consts4[3];
+    p.use_wall = use_wall; p.factor = factor; p.s_a = s_a; p.last_accept = last_accept; p.dbg_z = dbg_z; p.dbg_delta = dbg_delta;
     cudaError_t ce = cudaFuncSetAttribute(k4_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K4Smem));
-    if (ce == cudaSuccess) {
-        const int avail = e->n_sm - e->reserved_sms > 0 ? e->n_sm - e->reserved_sms : 1;
-        long long per = (e->cfg.n_chains + avail - 1) / avail;
-        per = (per + 31) / 32 * 32;
-        p.chains_per_cta = per;
-        const int grid = (int)((e->cfg.n_chains + per - 1) / per);
-        k4_steps<<<grid, K4_THREADS, sizeof(K4Smem), (cudaStream_t)stream>>>(p);
-        ce = cudaGetLastError();
-    }
-    cudaSetDevice(prev);
-    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_steps: ") + cudaGetErrorString(ce));
-    e->step += (unsigned long long)n_steps;
-    return ME_OK;
+    if (ce != cudaSuccess) return (int)ce;
+    const int avail = n_sm_avail > 0 ? n_sm_avail : 1;
+    long long per = (n_chains + avail - 1) / avail;
+    per = (per + 31) / 32 * 32;
+    p.chains_per_cta = per;
+    const int grid = (int)((n_chains + per - 1) / per);
+    k4_steps<<<grid, K4_THREADS, sizeof(K4Smem), (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
 }
-
-int me_k4_measure(me_k4 *e, double *ts, int64_t ts_row, void *stream) {
-    if (!e || !e->state) return ME_ERR_INVALID;
-    e->n_measure += 1;
-    K4Params p;
-    k4_base(e, p);
-    p.ts = ts; p.ts_row = ts_row; p.record = ts != nullptr;
-    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    const int block = 256;
-    const dim3 grid((unsigned)((e->cfg.n_chains + block - 1) / block), K4_NC + 1);
-    k4_measure<<<grid, block, 0, (cudaStream_t)stream>>>(p);
-    cudaError_t ce = cudaGetLastError();
-    cudaSetDevice(prev);
-    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_measure: ") + cudaGetErrorString(ce));
-    return ME_OK;
-}
-
-int me_k4_moments(me_k4 *e, const double *shift, double *scratch, int64_t scratch_doubles, double *inc, double *mom_accum,
-                  double *snapshot, void *stream) {
-    if (!e || !e->state || !shift || !scratch || !inc) return ME_ERR_INVALID;
-    const int n_parts = e->n_sm < 1 ? 1 : e->n_sm;
-    if (scratch_doubles < (int64_t)(n_parts + 1) * K4_PARTW) return k4_fail(e, ME_ERR_INVALID, "moments scratch too small");
-    K4Params p;
-    k4_base(e, p);
-    const long long per = (e->cfg.n_chains + n_parts - 1) / n_parts;
-    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    k4_moments_stage1<<<n_parts, 256, 0, (cudaStream_t)stream>>>(p, shift, scratch, per);
-    double *total = scratch + (long long)n_parts * K4_PARTW;
-    k4_moments_stage2a<<<(K4_PARTW + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, n_parts, total);
-    k4_moments_stage2b<<<(K4_MOMW + 127) / 128, 128, 0, (cudaStream_t)stream>>>(total, reinterpret_cast<double2 *>(inc),
-                                                                             reinterpret_cast<double2 *>(mom_accum),
-                                                                             reinterpret_cast<double2 *>(snapshot));
-    cudaError_t ce = cudaGetLastError();
-    cudaSetDevice(prev);
-    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_moments: ") + cudaGetErrorString(ce));
-    return ME_OK;
-}
-
-int me_k4_refactor(me_k4 *e, const double *mom, const double *inc, int64_t n_measure, double *cov_c, double *cov_a,
-                   void *factor_bf16, double *s_a, int32_t *status, void *stream) {
-    if (!e || !mom || !inc || !cov_c || !cov_a || !factor_bf16 || !s_a) return ME_ERR_INVALID;
-    if (n_measure <= 0) n_measure = e->n_measure;
-    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    const int smem = K4_NC * (K4_NC + 1) * (int)sizeof(double2);
-    cudaError_t ce = cudaFuncSetAttribute(k4_refactor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (ce == cudaSuccess) {
-        k4_refactor<<<1, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const double2 *>(mom),
-                                                            reinterpret_cast<const double2 *>(inc), n_measure,
-                                                            reinterpret_cast<double2 *>(cov_c), cov_a,
-                                                            reinterpret_cast<__nv_bfloat16 *>(factor_bf16), s_a, status);
-        ce = cudaGetLastError();
-    }
-    cudaSetDevice(prev);
-    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_refactor: ") + cudaGetErrorString(ce));
-    return ME_OK;
-}
-
-int me_k4_get_counters(me_k4 *e, int64_t *n_measure, uint64_t *step) {
-    if (!e) return ME_ERR_INVALID;
-    if (n_measure) *n_measure = e->n_measure;
-    if (step) *step = e->step;
-    return ME_OK;
-}
-
-const char *me_k4_last_error(me_k4 *e) { return e ? e->err.c_str() : g_k4_create_error.c_str(); }
-
-}  // extern "C"
