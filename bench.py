@@ -43,13 +43,13 @@ if ROOT not in sys.path:
 # (tests/scripts/sass_loop.py on the shipped library) — the inputs of the pipe-level roofline below.
 WORKLOADS = {
     "c1": dict(name="README x^2: 1 real param, T=0.01, measure every step", energy=("x2",), n_r=1, n_c=0, temp=0.01,
-               chains=65536, measures=10000, short_measures=10000, spm=1, flop=10, sf=3, fp64_inst=52.5, wide_inst=18.0),
+               chains=65536, measures=10000, short_measures=10000, spm=1, flop=10, sf=3, fp64_inst=30.5, wide_inst=12.0),
     "c2": dict(name="demo/toymodel_xypotentialwell: 2 real params, E=x^2+y^2, T=0.1, 65,536 chains x 1e5 steps, "
                     "measure every 10", energy=("xy_well", 1.0), n_r=2, n_c=0, temp=0.1, chains=65536,
-               measures=10000, short_measures=2000, spm=10, flop=20, sf=5, fp64_inst=59.0, wide_inst=18.0),
+               measures=10000, short_measures=2000, spm=10, flop=20, sf=5, fp64_inst=39.5, wide_inst=12.0),
     "c3": dict(name="mixed 3 real + 4 complex (bounded demo-style well), T=0.1, 262,144 chains, measure every 10",
                energy=("mixed_well", 1.0, -1.0, 0.5, 1.0), n_r=3, n_c=4, temp=0.1, chains=262144, measures=100,
-               short_measures=100, spm=10, flop=170, sf=23, fp64_inst=328.0, wide_inst=94.0),
+               short_measures=100, spm=10, flop=170, sf=23, fp64_inst=257.0, wide_inst=60.0),
 }
 # the CPU arm also knows config 4 (1 real + 64 complex, the reference's own per-chain covariance: 128x128 SVD per step)
 CPU_WORKLOADS = dict(WORKLOADS)

@@ -223,41 +223,54 @@ int me_get_counters(me_engine *eng, int64_t *n_measure, uint64_t *step);
 int me_set_counters(me_engine *eng, int64_t n_measure, uint64_t step);
 
 /* ------------------------------------------------------------------------------------------------------------
- * Shared-covariance tensor-core path (BASELINE config 4: 1 real + 64 complex Fourier-mode coefficients).
- * Same step as me_run (ME:241-259), but the complex block's proposal covariance is pooled over the ensemble at
+ * Shared-covariance tensor-core path (BASELINE config 4: 1 real + n_c complex Fourier-mode coefficients, n_c = 8, 16, 32
+ * or 64).  Same step as me_run (ME:241-259), but the complex block's proposal covariance is pooled over the ensemble at
  * measure boundaries and shared by all chains, so the proposal increments of 128 chains are one BF16 tcgen05
- * contraction  Delta = Z . B^T  with the FP32 accumulator in TMEM (csrc/me_k4.cu).  The caller owns the pooled
- * covariance / Cholesky factor (host side: engine_shared.py) and hands the factor over in `factor_bf16`:
+ * contraction  Delta = Z . B^T  with the FP32 accumulator in TMEM (csrc/me_k4_device.cuh: warp-specialised pipeline of
+ * generator warps, one MMA-issuing warp and epilogue warps; B arrives by TMA).  The caller owns the pooled covariance /
+ * Cholesky factor (host side: engine_shared.py) and hands the factor over in `factor_bf16`:
  *   B[2i][2j] = Re G_ij / sqrt2, B[2i][2j+1] = Im G_ij / sqrt2, B[2i+1][2j] = -Im G_ij / sqrt2, B[2i+1][2j+1] = Re G_ij / sqrt2
- *   (C_c = G G^H; ME:288-302 samples CN(0, sigma^2 conj(C_c))), stored BF16 as [16 k-chunks][128 n][8] (UMMA
+ *   (C_c = G G^H; ME:288-302 samples CN(0, sigma^2 conj(C_c))), stored BF16 as [K/8 k-chunks][N n][8], N = K = 2 n_c (UMMA
  *   canonical K-major, no swizzle).
- * State block (me_k4_layout): X 129 (a, Re c, Im c) | E | SIG | MEAN 129 | OBSM 66 | NACC | STATUS. */
+ * State block (me_k4_layout_for): X 1+2n_c (a, Re c, Im c) | E | SIG | MEAN 1+2n_c | OBSM 2+n_c | NACC | STATUS.
+ * Energy plugin (ME:20, 110-120): the built-in cylinder-style functor (consts: kappa, alpha, gamma, beta; hard wall
+ * |a| >= 1, legacy metropolis_engine.py:103,139), or CUDA text through me_k4_set_energy_source defining
+ *     __device__ void   me_k4_mode(double q, double re, double im, const double *k, double &s0, double &s1);   q = j - n_c/2
+ *     __device__ double me_k4_total(double a, double s0, double s1, const double *k, int n_c);
+ *     __device__ bool   me_k4_reject(double a, const double *k);                  (only when use_reject != 0)
+ * i.e. energies of the form E = total(a, sum_j f0_j(c_j), sum_j f1_j(c_j)); the per-mode sums are accumulated by the
+ * epilogue threads in mode order (first half of the modes, second half, then added). */
 typedef struct me_k4 me_k4;
 typedef struct me_k4_config {
     int32_t n_real;             /* must be 1  */
-    int32_t n_complex;          /* must be 64 */
+    int32_t n_complex;          /* 8, 16, 32 or 64 */
     int64_t n_chains;           /* multiple of 128 */
     int64_t chain_offset;
     double temp;
     double target_acceptance;
-    double ratio;               /* ME:105-107 with m = 65 */
+    double ratio;               /* ME:105-107 with m = 1 + n_complex */
     uint64_t seed;
     int32_t device;
-    int32_t use_reject;         /* hard wall |a| >= 1 (legacy metropolis_engine.py:103,139) */
-    double consts[4];           /* cylinder energy: kappa, alpha, gamma, beta */
+    int32_t use_reject;         /* hard wall of the functor */
+    double consts[4];           /* built-in cylinder energy: kappa, alpha, gamma, beta */
 } me_k4_config;
 typedef struct me_k4_layout {
     int32_t X, E, SIG, MEAN, OBSM, NACC, STATUS, WORDS, D, TS_COLS, N_COMPLEX, TILE, FACTOR_BYTES, MOM_WORDS;
     int32_t MOM_SCRATCH_PER_SM;   /* doubles of me_k4_moments scratch per SM */
 } me_k4_layout;
-int me_k4_layout_get(me_k4_layout *out);
+int me_k4_layout_get(me_k4_layout *out);                       /* n_complex = 64 */
+int me_k4_layout_for(int32_t n_complex, me_k4_layout *out);
 int me_k4_create(const me_k4_config *cfg, me_k4 **out);
 int me_k4_destroy(me_k4 *eng);
+int me_k4_set_energy_source(me_k4 *eng, const char *cuda_source, const double *consts, int32_t n_consts, int32_t use_reject);
+int me_k4_check_energy_source(const char *cuda_source, int32_t n_complex, int32_t use_reject, char *log, int64_t log_cap);
 int me_k4_bind(me_k4 *eng, double *state, const void *factor_bf16, unsigned char *last_accept);
 int me_k4_init(me_k4 *eng, const double *x0, int32_t x0_broadcast, double sigma0, void *stream);
-/* n_steps x step_all(); s_a = DEVICE scalar, shared proposal std of the real parameter; dbg_z / dbg_delta (may be NULL) receive
- * the normals [128][n_chains] and tensor-core increments [128][n_chains] of the first step (tests). */
-int me_k4_step(me_k4 *eng, int64_t n_steps, const double *s_a, float *dbg_z, float *dbg_delta, void *stream);
+/* n_steps x step_all(); s_a = DEVICE scalar, shared proposal std of the real parameter.  Taps of the FIRST step of the launch
+ * (may be NULL; tests and the oracle's injection protocol): dbg_z [2 n_c][n_chains] normals (BF16 values), dbg_delta
+ * [2 n_c][n_chains] tensor-core increments (interleaved Re, Im), dbg_scal [2][n_chains] the real parameter's normal and
+ * the accept uniform. */
+int me_k4_step(me_k4 *eng, int64_t n_steps, const double *s_a, float *dbg_z, float *dbg_delta, double *dbg_scal, void *stream);
 /* measure() without the covariance recursion (the caller pools it): means, observable means, one row
  * ts[(row * TS_COLS + col) * n_chains + chain]. */
 int me_k4_measure(me_k4 *eng, double *ts, int64_t ts_row, void *stream);

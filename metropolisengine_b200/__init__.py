@@ -4,6 +4,6 @@
 reference (README.md:15,33; package surface metropolisengine/__init__.py:1).
 """
 from .engine import BuiltinEnergy, CudaEnergy, MetropolisEngine, adaptation_constants  # noqa: F401
-from .engine_shared import SharedCovarianceEngine  # noqa: F401
+from .engine_shared import SharedCovarianceEngine, SharedEnergy  # noqa: F401
 
-__all__ = ["MetropolisEngine", "SharedCovarianceEngine", "BuiltinEnergy", "CudaEnergy", "adaptation_constants"]
+__all__ = ["MetropolisEngine", "SharedCovarianceEngine", "SharedEnergy", "BuiltinEnergy", "CudaEnergy", "adaptation_constants"]

@@ -20,6 +20,7 @@
 
 #include "../../include/me_b200.h"
 #include "me_kernels.cuh"
+#include "me_rt.h"
 #include "me_embedded.inc"   /* generated: the kernel headers as string constants for NVRTC */
 
 extern "C" const MeAotEntry *me_aot_fast_table(int *n);
@@ -52,6 +53,10 @@ typedef CUresult (*cuLaunchKernel_t)(CUfunction, unsigned, unsigned, unsigned, u
                                      CUstream, void **, void **);
 typedef CUresult (*cuGetErrorString_t)(CUresult, const char **);
 typedef CUresult (*cuOccupancy_t)(int *, CUfunction, int, size_t);
+typedef CUresult (*cuFuncSetAttribute_t)(CUfunction, CUfunction_attribute, int);
+typedef CUresult (*cuTensorMapEncodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                             const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct Driver {
     cuModuleLoadData_t moduleLoadData = nullptr;
@@ -59,6 +64,8 @@ struct Driver {
     cuLaunchKernel_t launchKernel = nullptr;
     cuGetErrorString_t getErrorString = nullptr;
     cuOccupancy_t occupancy = nullptr;          /* optional: only the launch balancing of runtime-compiled kernels needs it */
+    cuFuncSetAttribute_t funcSetAttribute = nullptr;        /* optional: > 48 KB dynamic shared memory of runtime-compiled kernels */
+    cuTensorMapEncodeTiled_t tensorMapEncodeTiled = nullptr; /* optional: TMA tensor maps */
     bool ok = false;
     std::string err;
 };
@@ -83,6 +90,8 @@ Driver &driver() {
         if (d.ok) {
             const std::string keep = d.err;
             if (!get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void **)&d.occupancy)) { d.occupancy = nullptr; d.err = keep; }
+            if (!get("cuFuncSetAttribute", (void **)&d.funcSetAttribute)) { d.funcSetAttribute = nullptr; d.err = keep; }
+            if (!get("cuTensorMapEncodeTiled", (void **)&d.tensorMapEncodeTiled)) { d.tensorMapEncodeTiled = nullptr; d.err = keep; }
         }
     });
     return d;
@@ -206,6 +215,104 @@ int nvrtc_compile(int n_real, int n_complex, int energy_id, const std::string &u
     return ME_OK;
 }
 
+}  // namespace
+
+/* ----------------------------------------------------------------------------------------- me_rt.h */
+int me_rt_compile(const std::string &src, const char *name, const std::vector<std::string> &extra, std::vector<char> &cubin,
+                  std::string &log) {
+    Nvrtc &n = nvrtc();
+    if (!n.ok) { log = n.err; return ME_ERR_UNSUPPORTED; }
+    const char *hdr_names[] = {"me_params.h", "me_math.cuh", "me_device.cuh", "me_energies.cuh", "me_kernels.cuh",
+                               "me_k4_device.cuh"};
+    const char *hdr_src[] = {me_src_params_h, me_src_math_cuh, me_src_device_cuh, me_src_energies_cuh, me_src_kernels_cuh,
+                             me_src_k4_device_cuh};
+    nvrtcProgram prog = nullptr;
+    int rc = n.createProgram(&prog, src.c_str(), name, 6, hdr_src, hdr_names);
+    if (rc != 0) { log = std::string("nvrtcCreateProgram: ") + n.getErrorString(rc); return ME_ERR_COMPILE; }
+    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DME_NVRTC=1"};
+    for (auto &o : extra) opts.push_back(o.c_str());
+    rc = n.compileProgram(prog, (int)opts.size(), opts.data());
+    size_t lsz = 0;
+    n.getProgramLogSize(prog, &lsz);
+    if (lsz > 1) { log.resize(lsz); n.getProgramLog(prog, &log[0]); }
+    if (rc != 0) {
+        log = std::string("NVRTC: ") + n.getErrorString(rc) + "\n" + log;
+        n.destroyProgram(&prog);
+        return ME_ERR_COMPILE;
+    }
+    size_t csz = 0;
+    n.getCUBINSize(prog, &csz);
+    cubin.resize(csz);
+    n.getCUBIN(prog, cubin.data());
+    n.destroyProgram(&prog);
+    return ME_OK;
+}
+
+int me_rt_load(int device, const std::vector<char> &cubin, const char *const *names, int cnt, CUfunction *out, std::string &err) {
+    Driver &d = driver();
+    if (!d.ok) { err = d.err; return ME_ERR_UNSUPPORTED; }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    cudaFree(0);   /* make sure the primary context exists and is current */
+    CUmodule mod = nullptr;
+    CUresult r = d.moduleLoadData(&mod, cubin.data());
+    int rc = ME_OK;
+    if (r != CUDA_SUCCESS) {
+        const char *s = nullptr;
+        d.getErrorString(r, &s);
+        err = std::string("cuModuleLoadData: ") + (s ? s : "?");
+        rc = ME_ERR_CUDA;
+    }
+    for (int i = 0; rc == ME_OK && i < cnt; i++)
+        if (d.moduleGetFunction(&out[i], mod, names[i]) != CUDA_SUCCESS) {
+            err = std::string("cuModuleGetFunction: ") + names[i];
+            rc = ME_ERR_CUDA;
+        }
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}
+
+int me_rt_launch(CUfunction f, unsigned grid, unsigned block, unsigned smem, void *stream, void **args, std::string &err) {
+    Driver &d = driver();
+    if (!d.ok) { err = d.err; return ME_ERR_UNSUPPORTED; }
+    CUresult r = d.launchKernel(f, grid, 1, 1, block, 1, 1, smem, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) {
+        const char *s = nullptr;
+        d.getErrorString(r, &s);
+        err = std::string("cuLaunchKernel: ") + (s ? s : "?");
+        return ME_ERR_CUDA;
+    }
+    return ME_OK;
+}
+
+int me_rt_set_dynamic_smem(CUfunction f, int bytes, std::string &err) {
+    Driver &d = driver();
+    if (!d.ok || !d.funcSetAttribute) { err = "cuFuncSetAttribute not available"; return ME_ERR_UNSUPPORTED; }
+    if (d.funcSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, bytes) != CUDA_SUCCESS) {
+        err = "cuFuncSetAttribute(MAX_DYNAMIC_SHARED_SIZE_BYTES) failed";
+        return ME_ERR_CUDA;
+    }
+    return ME_OK;
+}
+
+int me_rt_tensor_map_2d_bf16(void *map_out, const void *gaddr, unsigned long long inner, unsigned long long rows,
+                             unsigned box_inner, unsigned box_rows) {
+    Driver &d = driver();
+    if (!d.ok || !d.tensorMapEncodeTiled) return ME_ERR_UNSUPPORTED;
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {inner * 2};            /* bytes between rows */
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = d.tensorMapEncodeTiled(reinterpret_cast<CUtensorMap *>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                                        const_cast<void *>(gaddr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ME_OK : ME_ERR_CUDA;
+}
+
+namespace {
+
 /* process-wide cache of loaded runtime-compiled kernel sets */
 std::mutex g_cache_mu;
 std::map<std::string, KernelSet> g_cache;
@@ -281,13 +388,24 @@ const double *log_table(int device) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = tabs.find(device);
     if (it != tabs.end()) return it->second;
-    std::vector<double> host(2 * ME_LOGTAB_ENTRIES);
+    std::vector<double> host(2 * (ME_LOGTAB_ENTRIES + ME_SINTAB_ENTRIES));
     const int fold = (int)(0.4142135623730951 * ME_LOGTAB_ENTRIES);          /* first interval whose upper edge exceeds sqrt 2 */
     for (int i = 0; i < ME_LOGTAB_ENTRIES; i++) {
         const double c = 1.0 + (double)(i + 1) / (double)ME_LOGTAB_ENTRIES;
         const double rc = (double)(float)(1.0 / c);
         host[2 * i] = rc;
         host[2 * i + 1] = (double)(2.0L * logl(i >= fold ? (long double)rc * 2.0L : (long double)rc));
+    }
+    /* sin/cos of the interval midpoints (me_math.cuh, sincospi_tab); the second half of the circle is the exact negative
+       of the first, so that opposite angle words give exactly opposite normals */
+    double *sc = host.data() + 2 * ME_LOGTAB_ENTRIES;
+    const long double two_pi = 6.283185307179586476925286766559L;
+    for (int i = 0; i < ME_SINTAB_ENTRIES / 2; i++) {
+        const long double a = ((long double)i + 0.5L) * two_pi / (long double)ME_SINTAB_ENTRIES;
+        sc[2 * i] = (double)sinl(a);
+        sc[2 * i + 1] = (double)cosl(a);
+        sc[2 * (i + ME_SINTAB_ENTRIES / 2)] = -sc[2 * i];
+        sc[2 * (i + ME_SINTAB_ENTRIES / 2) + 1] = -sc[2 * i + 1];
     }
     DeviceGuard g(device);
     double *dev = nullptr;

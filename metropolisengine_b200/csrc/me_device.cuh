@@ -74,15 +74,21 @@ __host__ __device__ constexpr int nz(int n) { return n > 0 ? n : 1; }
 __device__ __forceinline__ constexpr int herm_lo(int i, int j) { return 2 * (i * (i - 1) / 2 + j); }
 __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-/* ------------------------------------------------------------------------------------------ Philox4x32-10 */
+/* ------------------------------------------------------------------------------------------ Philox4x32-7 */
 struct U4 { unsigned x, y, z, w; };
 
-/* rk: the 10 round-key pairs (k0 + r*0x9E3779B9, k1 + r*0xBB67AE85), precomputed on the host: they are the same
+/* Philox4x32 with ME_PHILOX_ROUNDS = 7 rounds: the smallest round count Random123 (Salmon et al., SC'11, table 2) reports
+ * as passing the full BigCrush battery ("Crush-resistant"); 10 is that library's default with a safety margin.  The
+ * generator's IMAD.WIDE rounds contend with the FP64 pipe (profiles/r01_microbench_issue_mix.txt), so three rounds less
+ * are six quarter-rate instructions less per Gaussian pair.  The C oracle uses the same count and is pinned against the
+ * Random123 known-answer vectors for both 7 and 10 rounds.
+ * rk: the round-key pairs (k0 + r*0x9E3779B9, k1 + r*0xBB67AE85), precomputed on the host: they are the same
  * for every chain and step, and as kernel parameters they are constant-bank operands of the XORs. */
-__device__ __forceinline__ U4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
-                                            const unsigned *rk) {
+#define ME_PHILOX_ROUNDS 7
+__device__ __forceinline__ U4 philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                         const unsigned *rk) {
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < ME_PHILOX_ROUNDS; r++) {
         const unsigned k0 = rk[2 * r], k1 = rk[2 * r + 1];
         const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;   /* one IMAD.WIDE each */
         const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
@@ -112,17 +118,22 @@ struct Rng {
     __device__ __forceinline__ Rng(const MeParams &p, unsigned long long gchain)
         : c0((unsigned)gchain), c1((unsigned)(gchain >> 32)), rk(p.rk) {}
     __device__ __forceinline__ U4 bits(unsigned step, unsigned slot) const {
-        return philox4x32_10(c0, c1, step, slot, rk);
+        return philox4x32(c0, c1, step, slot, rk);
     }
     template <bool STRICT, class Tab = LogTabGlobal>
     __device__ __forceinline__ static void box_muller(const U4 &r, const MathTables &T, double &z0, double &z1,
-                                                      const double unit = ME_C_UNIT, const double angle = ME_C_ANGLE,
+                                                      const double unit = ME_C_UNIT, const double angle = ME_C_ANGLE_TAB,
                                                       const Tab logtab = Tab{nullptr}) {
         const double d = __hiloint2double((int)(0x3ff00000u | (r.y >> 12)), (int)((r.y << 20) | (r.x >> 12)));
         const double u1 = d - unit;                                                     /* d - (1 - 2^-53), exact */
-        const double rad = STRICT ? sqrt(-2.0 * log(u1)) : sqrt_pos(neg2log_unit(u1, logtab));
-        double s, c;
-        sincospi_bits(r.z, s, c, angle);
+        double s, c, rad;
+        if (STRICT) {           /* parity build: libdevice log / sqrt and the full-accuracy polynomial sin/cos */
+            rad = sqrt(-2.0 * log(u1));
+            sincospi_bits(r.z, s, c);
+        } else {                /* throughput build: table-driven log and sin/cos, accuracy budget 1e-10 */
+            rad = sqrt_pos(neg2log_unit(u1, logtab));
+            sincospi_tab(r.z, s, c, logtab, angle);
+        }
         z0 = rad * c;
         z1 = rad * s;
     }
@@ -138,6 +149,22 @@ struct Rng {
     template <class Tab>
     __device__ __forceinline__ static double accept_threshold(const Spare &sp, const Tab &logtab, double half_temp) {
         return half_temp * neg2log_unit(accept_uniform(sp), logtab);
+    }
+    /* A window [lo, hi] around the threshold -T ln u, from FP32 arithmetic only: the FP64 pipe is what bounds the step
+     * kernel and the exact threshold costs it 12 instructions per step, while almost every decision is far from the
+     * threshold.  u 2^32 lies in [w0, w0 + 1); with w0 >= 2^18 the estimate ln u ~ ln((w0 + 1/2) 2^-32) is off by at most
+     * 1.9e-6, MUFU.LG2 by 2^-22 relative of |log2 u| <= 14 (7.7e-6 ln2 in ln u at worst over the full range), the
+     * conversion and the FP32 FMA / adds by < 4e-6 T: |estimate - (-T ln u)| < 1.1e-5 T; the window half-width is 4e-5 T.
+     * dE <= lo accepts, dE > hi rejects, in between (probability ~2e-5 per step) the caller computes the exact threshold.
+     * w0 < 2^18 (probability 2^-14): window [0, inf), i.e. always the exact path for uphill moves.  T == 0: lo = hi = 0. */
+    __device__ __forceinline__ static void accept_window(unsigned w0, float t_ln2, float t_band, double &lo, double &hi) {
+        float lg;
+        const float f = __uint2float_rn(w0) + 0.5f;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(f));
+        const float thr = (32.0f - lg) * t_ln2;                   /* T ln2 (32 - log2(w0 + 1/2)) */
+        const bool wide = w0 < 0x40000u;
+        lo = (double)(wide ? 0.0f : thr - t_band);
+        hi = (double)(wide ? __int_as_float(0x7f800000) : thr + t_band);
     }
 };
 
@@ -308,7 +335,8 @@ __device__ __forceinline__ int refactor(const Stats<L> &s, Chain<L> &c) {
 template <class L>
 struct Draws {                 /* everything random one step consumes; independent of the chain's state */
     double z[(L::D + 1) / 2 * 2];
-    double u;
+    double u;                  /* parity build: the accept uniform; throughput build: lower edge of the threshold window */
+    double uhi;                /* throughput build: upper edge of the threshold window (Rng::accept_window) */
 };
 
 template <class L>
@@ -333,8 +361,14 @@ __device__ __forceinline__ void shape_draws(const Raw<L> &raw, const MathTables 
         Rng::keep_spare(raw.r[q], q, sp);
         Rng::box_muller<STRICT, Tab>(raw.r[q], T, d.z[2 * q], d.z[2 * q + 1], pins.unit, pins.angle, logtab);
     }
-    /* strict build: the uniform itself; throughput build: the energy threshold -T ln u */
-    d.u = STRICT ? Rng::accept_uniform(sp) : Rng::accept_threshold(sp, logtab, half_temp);
+    /* strict build: the uniform itself; throughput build: a window around the energy threshold -T ln u */
+    if (STRICT) {
+        d.u = Rng::accept_uniform(sp);
+        d.uhi = 0.0;
+    } else {
+        const float t2 = (float)(2.0 * half_temp);
+        Rng::accept_window(sp.w0, t2 * 0.69314718f, t2 * 4e-5f, d.u, d.uhi);
+    }
 }
 
 template <class L, bool STRICT, class Tab>
@@ -612,10 +646,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 /* ------------------------------------------------------------------------------------------ one state-dependent step
  * proposal (already formed in `prop`) -> hard wall (ME:247) -> energy (ME:250) -> decision (ME:252) -> select
  * (ME:253-257) -> width adaptation (ME:258 / group variants ME:440-456). */
-template <class Cfg>
+template <class Cfg, class Tab = LogTabGlobal>
 __device__ __forceinline__ bool finish_step(Chain<Lay<Cfg::NR, Cfg::NC>> &c, double (&prop)[Lay<Cfg::NR, Cfg::NC>::D],
                                             double u, const Gains &g, const MeParams &p, const MathTables &tables,
-                                            int group) {
+                                            int group, double uhi = 0.0, const Rng *rng = nullptr, unsigned step = 0u,
+                                            const Tab *logtab = nullptr, double half_temp = 0.0) {
     using L = Lay<Cfg::NR, Cfg::NC>;
     using Energy = typename Cfg::Energy;
     constexpr bool STRICT = Cfg::STRICT;
@@ -634,6 +669,12 @@ __device__ __forceinline__ bool finish_step(Chain<Lay<Cfg::NR, Cfg::NC>> &c, dou
         if (e_new != e_new) c.status |= ME_STATUS_ENERGY_NAN;
         const double diff = e_new - c.e;
         accept = decide<STRICT>(diff, u, p, tables, g.hot, g.k64);
+        if (!STRICT && rng != nullptr && !accept && diff <= uhi) {
+            /* inside the FP32 window (about 2 steps in 10^5): the exact threshold from the same random bits */
+            Spare sp;
+            Rng::keep_spare(rng->bits(step, 0u), 0, sp);
+            accept = diff <= Rng::accept_threshold(sp, *logtab, half_temp);
+        }
         if (accept) {
             c.e = e_new;
 #pragma unroll
@@ -780,11 +821,12 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     /* log table: read-only global path for small shapes, per-CTA shared copy for larger ones (see me_math.cuh) */
     /* static shared-memory budget (48 KB): the pooled-moment staging of a large shape (9 x POOLW doubles, up to 43 KB at
        ME_MAX_POOLW) and the 16 KB table copy do not both fit; such shapes read the table through the read-only path */
-    constexpr bool TAB_FITS = (ME_MAX_BLOCK / 32 + 1) * PW * 8 + ME_LOGTAB_ENTRIES * 16 + 1024 <= 48 * 1024;
+    constexpr int TAB_ENTRIES = ME_LOGTAB_ENTRIES + ME_SINTAB_ENTRIES;       /* log table, then the sin/cos table */
+    constexpr bool TAB_FITS = (ME_MAX_BLOCK / 32 + 1) * PW * 8 + TAB_ENTRIES * 16 + 1024 <= 48 * 1024;
     constexpr bool TAB_SMEM = !STRICT && L::D > ME_SEG_MAX_D && TAB_FITS;
-    __shared__ double2 logtab_s[TAB_SMEM ? ME_LOGTAB_ENTRIES : 1];
+    __shared__ double2 logtab_s[TAB_SMEM ? TAB_ENTRIES : 1];
     if (TAB_SMEM) {
-        for (int i = threadIdx.x; i < ME_LOGTAB_ENTRIES; i += blockDim.x)
+        for (int i = threadIdx.x; i < TAB_ENTRIES; i += blockDim.x)
             logtab_s[i] = __ldg(reinterpret_cast<const double2 *>(p.logtab) + i);
         __syncthreads();
     }
@@ -821,8 +863,9 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
                 else propose_phases<L>(c, rng, step32, prop);
             }
         }
+        accept = finish_step<Cfg, Tab>(c, prop, use.u, g, p, tables, group, use.uhi, inject ? nullptr : &rng, step32,
+                                       &logtab, half_temp);
         step32++;
-        accept = finish_step<Cfg>(c, prop, use.u, g, p, tables, group);
     };
     const unsigned spm = (unsigned)p.spm;
     MeasureClock clk;

@@ -1,0 +1,589 @@
+/* me_k4_device.cuh — shared-covariance step kernel, version 2: a warp-specialised tcgen05 pipeline (sm_100a).
+ *
+ * One Metropolis step of an ensemble whose complex block shares ONE proposal covariance (pooled over the chains at
+ * measure boundaries; reference step: metropolis_engine.py:241-259, proposal law ME:274-302, hard wall ME:247, decision
+ * ME:319-338, Robbins-Monro width ME:429-438).  For a tile of 128 chains the proposal increments are one contraction
+ *        Delta[128 chains x N] = Z[128 x K normals] . B^T[K x N],     N = K = 2 n_c,
+ * B the real embedding of conj(G)/sqrt2 in interleaved (Re, Im) coordinates, C_c = G G^H.
+ *
+ * Roles inside a CTA of 17 warps (no CTA-wide barrier in the step loop):
+ *   warps 8..15  GENERATORS  Philox4x32-7 -> FP32 Box-Muller -> BF16, written straight into the UMMA canonical K-major
+ *                            operand layout.  The K dimension is produced in two halves, each its own pipeline stage
+ *                            (mbarriers z_full / z_empty), so the generators of step s+1 start as soon as the MMAs of step
+ *                            s have consumed the FIRST half of the operand: they never wait for the epilogue.
+ *   warp  16     MMA ISSUER  one elected lane: K/16 x tcgen05.mma (M128, N, K16, kind::f16) per step into one of TWO FP32
+ *                            accumulators in TMEM (lane = chain), tcgen05.commit -> mbarriers.  The shared factor B is
+ *                            brought in once per CTA by TMA (cp.async.bulk.tensor through a tensor map).
+ *   warps 0..7   EPILOGUE    thread (chain m, half h) owns the coordinates [h N/2, (h+1) N/2) of chain m for the whole launch:
+ *                            tcgen05.ld -> x' = x + sigma Delta (FP64) -> the energy functor's per-mode sums -> ONE
+ *                            64-thread named barrier with the thread of the other half -> both evaluate the (identical)
+ *                            Metropolis decision -> accepted chains write x' (their own words of the shared-memory state
+ *                            tile).  Chain scalars (a, E, sigma, count) live in registers of both threads.
+ * The only serial dependency is the state inside the epilogue; generation and contraction run ahead of it.
+ *
+ * Stream definition (restated by oracle/me_oracle_k4.c): chain g, step s —
+ *   normals 8c .. 8c+7 of the chain's row of Z: Philox4x32-7(counter (g_lo, g_hi, s, c), key seed) -> words x, y, z, w -> one
+ *   pair each through normal_pair_f32 (32 random bits per pair), rounded to BF16;
+ *   scalar draws: Philox call with slot 0x10000: word x -> pair -> first normal = the real parameter's, words z, w -> the
+ *   accept uniform (53 bits).
+ * Energy plugin: the functor supplies per-mode contributions to two sums and the total, i.e. energies of the form
+ *   E = total(a, sum_j f0_j(c_j), sum_j f1_j(c_j)) — the Fourier-mode field energies this path is for:
+ *     static void   mode(double q, double re, double im, const double *k, double &s0, double &s1);   q = j - n_c/2
+ *     static double total(double a, double s0, double s1, const double *k, int n_c);
+ *     static bool   reject(double a, const double *k);
+ * Fed to NVRTC as text for user functors: no #include of anything but the sibling headers.
+ */
+#ifndef ME_K4_DEVICE_CUH
+#define ME_K4_DEVICE_CUH
+
+#include "me_params.h"
+#include "me_math.cuh"
+
+namespace k4 {
+
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+constexpr int TILE = 128;               /* chains per tile = MMA M = TMEM lanes */
+constexpr int EPI_WARPS = 8, GEN_WARPS = 8;
+constexpr int GEN_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + GEN_WARPS;
+constexpr int THREADS = 32 * (EPI_WARPS + GEN_WARPS + 1);
+constexpr u32 SCALAR_SLOT = 0x10000u;   /* Philox slot of the per-chain scalar draws (beyond any operand chunk) */
+constexpr int PHILOX_ROUNDS = 7;
+
+struct TensorMap { alignas(64) u64 opaque[16]; };      /* a CUtensorMap, opaque to device code */
+
+struct StepParams {
+    double *state;
+    long long ld, n_chains;
+    u64 chain_offset;
+    u32 rk[20];
+    u64 step0;
+    long long n_steps;
+    long long chains_per_cta;      /* contiguous chains per CTA (a multiple of 32) */
+    long long n_meas;              /* measure_step_counter (for the Robbins-Monro gain) */
+    double temp, inv_temp, target, ratio;
+    int m;                         /* n_real + n_complex */
+    int n_c;
+    double consts[ME_MAX_CONSTS];  /* energy functor constants */
+    int use_wall;
+    int use_tma;                   /* 1: B arrives through the tensor map; 0: plain loads from `factor` */
+    const void *factor;            /* B operand, BF16, UMMA canonical K-major layout [K/8 chunks][N rows][8] */
+    const double *s_a;             /* device scalar: shared proposal std of the real parameter */
+    unsigned char *last_accept;
+    float *dbg_z;                  /* optional [K][ld]: the normals of the FIRST step of the launch (tests / oracle taps) */
+    float *dbg_delta;              /* optional [N][ld]: the tensor-core increments of the first step */
+    double *dbg_scal;              /* optional [2][ld]: real-parameter normal and accept uniform of the first step */
+};
+
+/* state-block word offsets for n_c complex parameters: X (1 + 2 n_c) | E | SIG | MEAN (1 + 2 n_c) | OBSM (2 + n_c) | NACC | STATUS */
+struct Layout {
+    int D, X, E, SIG, MEAN, OBSM, NOBS, NACC, STATUS, WORDS;
+    __host__ __device__ explicit Layout(int nc) {
+        D = 1 + 2 * nc; X = 0; E = D; SIG = D + 1; MEAN = D + 2; OBSM = MEAN + D; NOBS = 2 + nc; NACC = OBSM + NOBS;
+        STATUS = NACC + 1; WORDS = STATUS + 1;
+    }
+};
+
+/* -------------------------------------------------------------------------------------------- PTX helpers */
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
+    u32 ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+/* bounded wait: a protocol error must not hang the GPU — trap instead */
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    for (u32 spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const TensorMap *map, u64 *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((u64)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(u32 *slot, u32 cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(u32 addr, u32 cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+/* D[tmem] (+)= A[smem] . B[smem]^T, BF16 inputs, FP32 accumulate, M = 128, K = 16 */
+__device__ __forceinline__ void umma_bf16(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(u64 *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+/* K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; row groups 128 B apart (SBO); the two 16-byte K chunks of
+ * one K=16 MMA `lbo` bytes apart; descriptor fields in 16-byte units; version 1 (Blackwell). */
+__device__ __forceinline__ u64 umma_desc(u32 smem_addr, u32 lbo) {
+    return (u64)((smem_addr & 0x3ffffu) >> 4) | ((u64)(lbo >> 4) << 16) | ((u64)(128 >> 4) << 32) | (1ull << 46);
+}
+/* instruction descriptor: D = F32, A = B = BF16, both K-major, N, M = 128 */
+__host__ __device__ constexpr u32 umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(n >> 3) << 17) | ((u32)(TILE >> 4) << 24);
+}
+
+template <int CNT> struct TmemLd;
+template <> struct TmemLd<8> {
+    __device__ __forceinline__ static void ld(u32 taddr, u32 *r) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr) : "memory");
+    }
+};
+template <> struct TmemLd<16> {
+    __device__ __forceinline__ static void ld(u32 taddr, u32 *r) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr) : "memory");
+    }
+};
+template <> struct TmemLd<32> {
+    __device__ __forceinline__ static void ld(u32 taddr, u32 *r) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr) : "memory");
+    }
+};
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+/* -------------------------------------------------------------------------------------------- RNG (FP32 path) */
+struct U4 { u32 x, y, z, w; };
+__device__ __forceinline__ U4 philox(u32 c0, u32 c1, u32 c2, u32 c3, const u32 *rk) {
+#pragma unroll
+    for (int r = 0; r < PHILOX_ROUNDS; r++) {
+        const u64 p0 = (u64)0xD2511F53u * c0;
+        const u64 p1 = (u64)0xCD9E8D57u * c2;
+        const u32 n0 = (u32)(p1 >> 32) ^ c1 ^ rk[2 * r];
+        const u32 n2 = (u32)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = (u32)p1; c2 = n2; c3 = (u32)p0;
+    }
+    U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+/* two normals from 32 random bits: radius uniform from the high 16 bits, angle from the low 16 (2 quadrant bits + 14-bit
+ * fraction).  The operand these normals feed is BF16 (8 significant bits), so a 2^-16 grid for the radius uniform and a
+ * 1e-4 rad grid for the angle are already below its rounding; the radius is capped at sqrt(2 ln 2^16) = 4.7.
+ * Built for the SM's scarcest pipe: no integer->float conversions (the uniforms are assembled as float mantissas),
+ * sin/cos as FP32 polynomials after an integer quadrant reduction, so the only XU operations are one MUFU.LG2 and one
+ * MUFU.SQRT per PAIR.  The two signs and the sin/cos swap come from independent bits, so the pair's law is exactly
+ * symmetric whatever the accuracy of the approximations: the proposal stays symmetric and detailed balance exact. */
+__device__ __forceinline__ void normal_pair_f32(u32 bits, float &z0, float &z1) {
+    const float u = 2.0f - __uint_as_float(0x3f800000u | ((bits >> 16) << 7));     /* (0, 1], multiples of 2^-16 */
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));                         /* u >= 2^-16: no denormal path */
+    const float w = -1.3862943611f * lg;                                            /* -2 ln u >= 0 */
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(w));
+    const u32 zz = (bits << 16) + 0x20000000u;                                      /* quadrant = zz >> 30 (rounded) */
+    const float v = __uint_as_float(0x3f800000u | ((zz >> 7) & 0x007fffffu)) - 1.5f;   /* [-1/2, 1/2): angle (pi/2) v */
+    const float q = v * v;
+    float ps = fmaf(q, -0.0046817541f, 0.0796926263f);                              /* sin((pi/2) v) / v */
+    ps = fmaf(q, ps, -0.6459640975f);
+    ps = fmaf(q, ps, 1.5707963268f);
+    const float sr = v * ps;
+    float pc = fmaf(q, 0.0009192603f, -0.0208634807f);                              /* cos((pi/2) v) */
+    pc = fmaf(q, pc, 0.2536695079f);
+    pc = fmaf(q, pc, -1.2337005501f);
+    const float cr = fmaf(q, pc, 1.0f);
+    /* quadrant 0: (cos, sin) = (cr, sr); 1: (-sr, cr); 2: (-cr, -sr); 3: (sr, -cr) */
+    const bool odd = (zz & 0x40000000u) != 0;
+    const float cs = odd ? sr : cr, sn = odd ? cr : sr;
+    z0 = rad * __uint_as_float(__float_as_uint(cs) ^ ((zz + 0x40000000u) & 0x80000000u));
+    z1 = rad * __uint_as_float(__float_as_uint(sn) ^ (zz & 0x80000000u));
+}
+__device__ __forceinline__ double u53(u32 hi, u32 lo) {
+    const double a = __hiloint2double(0x43300000 - (27 << 20), (int)(hi >> 5)) - 33554432.0;
+    const double b = __hiloint2double(0x43300000 - (53 << 20), (int)(lo >> 6)) - 0.5;
+    return a + b;
+}
+__device__ __forceinline__ u32 pack_bf16(float lo, float hi) {
+    u32 r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float bf16_round(float v) { return __uint_as_float(pack_bf16(v, 0.0f) << 16); }
+
+/* FP32 accumulator word -> double (F2F.F64.F32, exact) */
+__device__ __forceinline__ double f32_bits_to_f64(u32 f) { return (double)__uint_as_float(f); }
+
+/* -------------------------------------------------------------------------------------------- built-in functor */
+/* cylinder-style Fourier-mode field (shape from legacy metropolis_engine.py:103,139-143):
+ * E = k0 a^2 + sum_q (k1 + k2 q^2 (1+a^2)) |c_q|^2 + (k3/(2 n_c)) (sum_q |c_q|^2)^2, q = j - n_c/2; hard wall |a| >= 1 */
+struct EnergyCylinder {
+    __device__ __forceinline__ static void mode(double q, double re, double im, const double *, double &s0, double &s1) {
+        const double m2 = fma(re, re, im * im);
+        s0 += m2;
+        s1 = fma(q * q, m2, s1);
+    }
+    /* written with explicit fma so that the compiler's contraction choices cannot change the bits (the C oracle
+       restates exactly this sequence) */
+    __device__ __forceinline__ static double total(double a, double s0, double s1, const double *k, int nc) {
+        const double a2 = a * a;
+        const double inner = fma(k[1], s0, (k[2] * (1.0 + a2)) * s1);
+        const double quad = fma(k[0], a2, inner);
+        return fma(k[3] / (2.0 * (double)nc), s0 * s0, quad);
+    }
+    __device__ __forceinline__ static bool reject(double a, const double *) { return fabs(a) >= 1.0; }
+};
+
+/* -------------------------------------------------------------------------------------------- shared memory */
+template <int NC>
+struct Smem {
+    static constexpr int N = 2 * NC;
+    static constexpr int HALVES = (N >= 32) ? 2 : 1;
+    double xs[N][TILE];                                     /* complex block, interleaved [n][chain]      N KB   */
+    alignas(1024) unsigned char zs[TILE * N * 2];           /* A operand (normals), BF16, HALVES stages            */
+    alignas(1024) unsigned char ls[N * N * 2];              /* B operand (factor), BF16                            */
+    double part[2][2][2][TILE];                             /* [step parity][half][sum][chain] partial energy sums */
+    me::MathTables tables;
+    u64 z_full[2], z_empty[2], acc_full[2], acc_empty[2], b_full;
+    u32 tmem_slot;
+};
+
+/* -------------------------------------------------------------------------------------------- the step kernel */
+template <int NC, class Energy>
+__device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap *bmap) {
+    typedef Smem<NC> S_t;
+    constexpr int N = S_t::N, K = N, HALVES = S_t::HALVES;
+    constexpr int CHUNKS = K / 8;                 /* 16-byte K chunks per operand row */
+    constexpr int CH_HALF = CHUNKS / HALVES;      /* chunks per pipeline stage */
+    constexpr u32 A_LBO = TILE * 16, B_LBO = N * 16;
+    constexpr u32 TCOLS = N < 32 ? 32 : N;        /* TMEM columns per accumulator */
+    constexpr u32 IDESC = umma_idesc(N);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    S_t &S = *reinterpret_cast<S_t *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ld = p.ld;
+    const Layout L(NC);
+
+    me::init_math_tables(S.tables);
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&S.z_full[i], GEN_WARPS);
+            mbar_init(&S.z_empty[i], 1);
+            mbar_init(&S.acc_full[i], 1);
+            mbar_init(&S.acc_empty[i], EPI_WARPS);
+        }
+        mbar_init(&S.b_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) tmem_alloc(&S.tmem_slot, 2 * TCOLS);
+    if (!p.use_tma) {                             /* plain staging of the factor (tensor map not available) */
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.factor);
+        uint4 *dst = reinterpret_cast<uint4 *>(S.ls);
+        for (int i = tid; i < N * N * 2 / 16; i += THREADS) dst[i] = src[i];
+        fence_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem_base = S.tmem_slot;
+
+    /* the chains of this CTA, walked in tiles of up to 128; iteration it = tile * n_steps + s */
+    const long long range_lo = (long long)blockIdx.x * p.chains_per_cta;
+    const long long range_hi = range_lo + p.chains_per_cta < p.n_chains ? range_lo + p.chains_per_cta : p.n_chains;
+    const long long n_tiles = range_hi > range_lo ? (range_hi - range_lo + TILE - 1) / TILE : 0;
+    const long long n_steps = p.n_steps;
+
+    if (warp == MMA_WARP) {
+        /* ================================================================== MMA issuer (+ the factor's TMA load) */
+        if (lane == 0) {
+            if (p.use_tma) {
+                constexpr int ROWS = CHUNKS * N;                 /* rows of 16 bytes */
+                constexpr int BOX = ROWS < 256 ? ROWS : 256;
+                mbar_expect_tx(&S.b_full, (u32)(N * N * 2));
+                for (int r = 0; r < ROWS; r += BOX) tma_load_2d(S.ls + r * 16, bmap, &S.b_full, 0, r);
+                mbar_wait(&S.b_full, 0);
+            }
+            const u32 zs_addr = smem_u32(S.zs), ls_addr = smem_u32(S.ls);
+            long long it = 0;
+            for (long long t = 0; t < n_tiles; t++) {
+                for (long long s = 0; s < n_steps; s++, it++) {
+                    const u32 a = (u32)(it & 1);
+                    if (it >= 2) mbar_wait(&S.acc_empty[a], (u32)(((it >> 1) - 1) & 1));
+                    for (int h = 0; h < HALVES; h++) {
+                        mbar_wait(&S.z_full[h], (u32)(it & 1));
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < CH_HALF / 2; k++) {
+                            const int c = h * CH_HALF + 2 * k;       /* first of the two K chunks of this MMA */
+                            umma_bf16(tmem_base + a * TCOLS, umma_desc(zs_addr + c * A_LBO, A_LBO),
+                                      umma_desc(ls_addr + c * B_LBO, B_LBO), IDESC, (h > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&S.z_empty[h]);                  /* the operand stage may be overwritten */
+                    }
+                    umma_commit(&S.acc_full[a]);                     /* the accumulator is complete */
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= GEN_WARP0) {
+        /* ================================================================== generators */
+        const int gt = tid - 32 * GEN_WARP0;          /* 0..255 */
+        const int m = gt & (TILE - 1);                /* operand row = chain within the tile */
+        const int c_par = gt >> 7;                    /* this thread's chunk parity */
+        long long it = 0;
+        for (long long t = 0; t < n_tiles; t++) {
+            const long long base = range_lo + t * TILE;
+            const int cnt = (int)(range_hi - base < TILE ? range_hi - base : TILE);      /* multiple of 32 */
+            const bool act = m < cnt;                                                    /* warp-uniform */
+            const u64 gch = p.chain_offset + (u64)(act ? base + m : base);
+            const u32 c0 = (u32)gch, c1 = (u32)(gch >> 32);
+            for (long long s = 0; s < n_steps; s++, it++) {
+                const u32 step = (u32)(p.step0 + (u64)s);
+                for (int h = 0; h < HALVES; h++) {
+                    if (it >= 1) mbar_wait(&S.z_empty[h], (u32)((it - 1) & 1));
+                    if (act) {
+#pragma unroll
+                        for (int i = 0; i < CH_HALF / 2; i++) {
+                            const int c = h * CH_HALF + c_par + 2 * i;      /* CH_HALF is even: both parities are used */
+                            float dz[8];
+                            const U4 r = philox(c0, c1, step, (u32)c, p.rk);
+                            normal_pair_f32(r.x, dz[0], dz[1]);
+                            normal_pair_f32(r.y, dz[2], dz[3]);
+                            normal_pair_f32(r.z, dz[4], dz[5]);
+                            normal_pair_f32(r.w, dz[6], dz[7]);
+                            uint4 v;
+                            v.x = pack_bf16(dz[0], dz[1]);
+                            v.y = pack_bf16(dz[2], dz[3]);
+                            v.z = pack_bf16(dz[4], dz[5]);
+                            v.w = pack_bf16(dz[6], dz[7]);
+                            *reinterpret_cast<uint4 *>(S.zs + c * A_LBO + m * 16) = v;
+                            if (s == 0 && p.dbg_z != nullptr) {
+#pragma unroll
+                                for (int k = 0; k < 8; k++)
+                                    p.dbg_z[(long long)(8 * c + k) * ld + base + m] = bf16_round(dz[k]);
+                            }
+                        }
+                    }
+                    fence_async_smem();          /* generic-proxy stores -> visible to the tensor-core (async) proxy */
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.z_full[h]);
+                }
+            }
+        }
+    } else {
+        /* ================================================================== epilogue */
+        const int q4 = warp & 3, h = warp >> 2;        /* lane quarter (TMEM lanes 32 q4 ..), coordinate half */
+        const int m = 32 * q4 + lane;                  /* chain within the tile = TMEM lane */
+        constexpr int MODES = NC / 2;                  /* modes per thread */
+        constexpr int LDCH = NC < 32 ? NC : 32;        /* columns per tcgen05.ld */
+        const double s_a = *p.s_a;
+        double f = (double)p.n_meas / (double)p.m;
+        if (!(f > 200.0)) f = 200.0;
+        const double g_up = p.ratio * (1 - p.target) / f, g_down = p.ratio * p.target / f;
+        const double q_first = (double)(h * MODES - NC / 2);     /* wavenumber of this thread's first mode */
+        long long it = 0;
+        for (long long t = 0; t < n_tiles; t++) {
+            const long long base = range_lo + t * TILE;
+            const int cnt = (int)(range_hi - base < TILE ? range_hi - base : TILE);
+            const bool act = 32 * q4 < cnt;                                              /* warp-uniform */
+            const long long ch = act ? base + m : base;
+            const u64 gch = p.chain_offset + (u64)ch;
+            const u32 c0 = (u32)gch, c1 = (u32)(gch >> 32);
+            /* this thread's words of the tile's state, and (both halves redundantly) the chain's scalars */
+            double a = 0, e = 0, sig = 0, nacc = 0;
+            int status = 0, accepted_last = 0;
+            if (act) {
+#pragma unroll 4
+                for (int jj = 0; jj < MODES; jj++) {
+                    const int j = h * MODES + jj;
+                    S.xs[2 * j][m] = p.state[(long long)(L.X + 1 + j) * ld + ch];
+                    S.xs[2 * j + 1][m] = p.state[(long long)(L.X + 1 + NC + j) * ld + ch];
+                }
+                a = p.state[(long long)L.X * ld + ch];
+                e = p.state[(long long)L.E * ld + ch];
+                sig = p.state[(long long)L.SIG * ld + ch];
+                nacc = p.state[(long long)L.NACC * ld + ch];
+                status = (int)p.state[(long long)L.STATUS * ld + ch];
+            }
+            for (long long s = 0; s < n_steps; s++, it++) {
+                const u32 step = (u32)(p.step0 + (u64)s);
+                const u32 acc = (u32)(it & 1);
+                /* scalar draws of this (chain, step): independent of the state, computed while the MMA is in flight */
+                double za = 0.0, u = 0.0;
+                if (act) {
+                    const U4 r = philox(c0, c1, step, SCALAR_SLOT, p.rk);
+                    float f0, f1;
+                    normal_pair_f32(r.x, f0, f1);
+                    za = (double)f0;
+                    u = u53(r.z, r.w);
+                }
+                mbar_wait(&S.acc_full[acc], (u32)((it >> 1) & 1));
+                tc_fence_after();
+                const u32 tcol = tmem_base + acc * TCOLS + ((u32)(32 * q4) << 16) + (u32)(h * NC);
+                bool accept = false;
+                double sg = sig;
+                if (act) {
+                    /* ---- pass 1: proposed coordinates of this half, the functor's two sums.  The increments are read
+                       from TMEM in chunks of LDCH columns (and read again in pass 2) instead of being held in 2 n_c / 2
+                       registers across the decision */
+                    double s0 = 0.0, s1 = 0.0, q = q_first;
+#pragma unroll
+                    for (int c = 0; c < NC; c += LDCH) {
+                        u32 raw[LDCH];
+                        TmemLd<LDCH>::ld(tcol + (u32)c, raw);
+                        tmem_ld_wait();
+                        if (s == 0 && p.dbg_delta != nullptr) {
+#pragma unroll
+                            for (int k = 0; k < LDCH; k++)
+                                p.dbg_delta[(long long)(h * NC + c + k) * ld + ch] = __uint_as_float(raw[k]);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < LDCH / 2; jj++) {
+                            const int j = h * MODES + c / 2 + jj;
+                            const double re = fma(sig, f32_bits_to_f64(raw[2 * jj]), S.xs[2 * j][m]);
+                            const double im = fma(sig, f32_bits_to_f64(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
+                            Energy::mode(q, re, im, p.consts, s0, s1);
+                            q += 1.0;
+                        }
+                    }
+                    S.part[it & 1][h][0][m] = s0;
+                    S.part[it & 1][h][1][m] = s1;
+                }
+                named_barrier(1 + q4, 64);           /* the two halves of this lane quarter exchange their sums */
+                if (act) {
+                    /* ---- decision, evaluated identically by both halves (ME:247-258) */
+                    const double t0 = S.part[it & 1][0][0][m] + S.part[it & 1][1][0][m];
+                    const double t1 = S.part[it & 1][0][1][m] + S.part[it & 1][1][1][m];
+                    const double a_new = fma(sig * s_a, za, a);
+                    const bool wall = p.use_wall && Energy::reject(a_new, p.consts);
+                    if (!wall) {
+                        const double e_new = Energy::total(a_new, t0, t1, p.consts, NC);
+                        if (e_new != e_new) status |= ME_STATUS_ENERGY_NAN;
+                        const double diff = e_new - e;
+                        const double prob = me::exp_nonpos(fmin(-diff * p.inv_temp, 0.0), S.tables);
+                        /* a NaN difference rejects, as in the reference (`uniform <= exp(nan)` is False, ME:327-338) */
+                        accept = (diff <= 0) | ((p.temp != 0) & (diff == diff) & (u <= prob));
+                        if (accept) { e = e_new; a = a_new; nacc += 1.0; }
+                    }
+                    sg = accept ? fma(sig, g_up, sig) : fma(sig, -g_down, sig);
+                    if (!(sg > 0)) status |= ME_STATUS_SIGMA_NONPOS;
+                    if (s == 0 && h == 0 && p.dbg_scal != nullptr) { p.dbg_scal[ch] = za; p.dbg_scal[ld + ch] = u; }
+                    /* ---- pass 2: accepted chains take the proposal (the same fma as pass 1: the accepted state is
+                       bit-for-bit the one whose energy was evaluated) */
+                    if (__any_sync(0xffffffffu, accept)) {
+#pragma unroll
+                        for (int c = 0; c < NC; c += LDCH) {
+                            u32 raw[LDCH];
+                            TmemLd<LDCH>::ld(tcol + (u32)c, raw);
+                            tmem_ld_wait();
+                            if (accept) {
+#pragma unroll
+                                for (int jj = 0; jj < LDCH / 2; jj++) {
+                                    const int j = h * MODES + c / 2 + jj;
+                                    S.xs[2 * j][m] = fma(sig, f32_bits_to_f64(raw[2 * jj]), S.xs[2 * j][m]);
+                                    S.xs[2 * j + 1][m] = fma(sig, f32_bits_to_f64(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.acc_empty[acc]);       /* this warp is done with the accumulator */
+                if (act) {
+                    sig = sg;
+                    accepted_last = accept ? 1 : 0;
+                }
+            }
+            /* store this thread's words of the tile */
+            if (act) {
+#pragma unroll 4
+                for (int jj = 0; jj < MODES; jj++) {
+                    const int j = h * MODES + jj;
+                    p.state[(long long)(L.X + 1 + j) * ld + ch] = S.xs[2 * j][m];
+                    p.state[(long long)(L.X + 1 + NC + j) * ld + ch] = S.xs[2 * j + 1][m];
+                }
+                if (h == 0) {
+                    p.state[(long long)L.X * ld + ch] = a;
+                    p.state[(long long)L.E * ld + ch] = e;
+                    p.state[(long long)L.SIG * ld + ch] = sig;
+                    p.state[(long long)L.NACC * ld + ch] = nacc;
+                    p.state[(long long)L.STATUS * ld + ch] = (double)status;
+                    if (p.last_accept && n_steps > 0) p.last_accept[ch] = (unsigned char)accepted_last;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 2 * TCOLS);
+}
+
+/* -------------------------------------------------------------------------------------------- initialisation (ME:40-125) */
+template <class Energy>
+__device__ __forceinline__ void init_body(const StepParams &p, const double *x0, int broadcast, double sigma0) {
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_chains) return;
+    const long long ld = p.ld;
+    const int nc = p.n_c;
+    const Layout L(nc);
+    double s0 = 0.0, s1 = 0.0;
+    const double a = broadcast ? x0[0] : x0[ch];
+    p.state[(long long)L.X * ld + ch] = a;
+    p.state[(long long)L.MEAN * ld + ch] = a;
+    for (int j = 0; j < nc; j++) {
+        const double re = broadcast ? x0[1 + j] : x0[(long long)(1 + j) * ld + ch];
+        const double im = broadcast ? x0[1 + nc + j] : x0[(long long)(1 + nc + j) * ld + ch];
+        p.state[(long long)(L.X + 1 + j) * ld + ch] = re;
+        p.state[(long long)(L.X + 1 + nc + j) * ld + ch] = im;
+        p.state[(long long)(L.MEAN + 1 + j) * ld + ch] = re;
+        p.state[(long long)(L.MEAN + 1 + nc + j) * ld + ch] = im;
+        Energy::mode((double)(j - nc / 2), re, im, p.consts, s0, s1);
+        p.state[(long long)(L.OBSM + 1 + j) * ld + ch] = hypot(re, im);
+    }
+    p.state[(long long)L.OBSM * ld + ch] = fabs(a);
+    p.state[(long long)(L.OBSM + 1 + nc) * ld + ch] = a * a;
+    p.state[(long long)L.E * ld + ch] = Energy::total(a, s0, s1, p.consts, nc);
+    p.state[(long long)L.SIG * ld + ch] = sigma0;
+    p.state[(long long)L.NACC * ld + ch] = 0.0;
+    p.state[(long long)L.STATUS * ld + ch] = 0.0;
+}
+
+}  // namespace k4
+
+#endif

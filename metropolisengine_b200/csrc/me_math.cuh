@@ -25,7 +25,8 @@ namespace me {
 #define ME_C_EXP5 0x1.11111p-7         /* 1/120 truncated; effect on e^r < 1e-20 */
 #define ME_C_2LN2HI 0x1.62e42p+0       /* 2 ln2_hi */
 #define ME_C_64_LN2 0x1.71547p+6       /* 64/ln2, leading 21 bits (the reduction uses the k it produced, so only |r| grows, by 3e-7) */
-#define ME_C_ANGLE 2097152.25          /* 2^21 + 1/4: bias of the integer angle reduction */
+#define ME_C_ANGLE 2097152.25          /* 2^21 + 1/4: bias of the integer angle reduction (polynomial sin/cos, parity build) */
+#define ME_C_ANGLE_TAB 4503599629467648.0   /* 2^52 + 2^21: bias of the table-driven sin/cos residual (throughput build) */
 #define ME_C_UNIT 0.99999999999999988898   /* 1 - 2^-53: bias of the radius uniform */
 
 /* Constants that cannot be immediates (non-zero low word) and would otherwise be re-materialised inside the step loop
@@ -33,6 +34,12 @@ namespace me {
 struct Pins {
     double unit, angle, k64;
 };
+
+/* Table of the table-driven sin/cos (throughput build): 1024 intervals of the angle pi t, t = z 2^-31 in [0, 2):
+ * {sin a_i, cos a_i} at the interval midpoints a_i = (i + 1/2) 2 pi / 1024, computed by the host library in long double
+ * with entry i + 512 = -entry i EXACTLY (so that z and z ^ 0x80000000 give exactly opposite normals: the proposal is
+ * symmetric bit for bit).  16 KB, stored right behind the log table. */
+#define ME_SINTAB_ENTRIES 1024
 
 /* Table of the table-driven log: 1024 intervals of the mantissa [1 + i/1024, 1 + (i+1)/1024): {rc_i, -2 l_i} with
  * rc_i = float(1 / upper edge), l_i = -ln(rc_i * (i >= 424 ? 2 : 1)).  16 KB, computed once per device by the host
@@ -53,7 +60,9 @@ __constant__ double me_kc[32] = {
     /* 20..27 cos(pi r) in s (rel. error 2e-17); [27] is ME_C_COS7 */
     1.0, -4.934802200544679, 4.058712126416747, -1.3352627688519174, 0.23533063019088787, -0.025806885652951306,
     0.0019294657440800042, -0.00010356747255199479,
-    0.0, 0.0, 0.0, 0.0};
+    /* 28..31 residual rotation of the table-driven sin/cos in the INTEGER residual v = (z mod 2^22) - 2^21 (angle
+       b = kappa v, kappa = 2 pi / 2^32): kappa, -kappa^3/6, -kappa^2/2, kappa^4/24 */
+    1.4629180792671596e-09, -5.218056424438286e-28, -1.0700646533233578e-18, 1.90839727048673e-37};
 
 struct MathTables {
     double exp2t[64];      /* 2^(j/64) */
@@ -63,7 +72,7 @@ struct MathTables {
 /* Called by every thread of the CTA before any use; the caller synchronises afterwards. */
 __device__ __forceinline__ void init_math_tables(MathTables &T) {
     for (int j = threadIdx.x; j < 64; j += blockDim.x) T.exp2t[j] = exp2((double)j * 0.015625);
-    if (threadIdx.x == 0) { T.pins[0] = ME_C_UNIT; T.pins[1] = ME_C_ANGLE; T.pins[2] = ME_C_64_LN2; T.pins[3] = 0.0; }
+    if (threadIdx.x == 0) { T.pins[0] = ME_C_UNIT; T.pins[1] = ME_C_ANGLE_TAB; T.pins[2] = ME_C_64_LN2; T.pins[3] = ME_C_ANGLE; }
 }
 
 /* After the table barrier: the pinned constants as register values.  Coming from shared memory they are opaque to
@@ -79,21 +88,23 @@ __device__ __forceinline__ Pins load_pins(const MathTables &T) {
  * u -> 1 keeps full relative accuracy (top interval has rc = 1/2, l = 0 exactly).  The fold is an integer carry:
  * adding 600 to the 10-bit interval field of the high word overflows into the exponent field exactly when i >= 424.
  * The result is > 0 for every u < 1 (|.| only clears a sign that rounding could set for u within 2^-50 of 1).
- * Max error 1.5 ulp (checked against long-double log over 2e7 arguments incl. u -> 1 and u -> 2^-53). */
+ * Absolute error < 5e-13 (relative < 2.4e-10 where -2 ln u < 2^-9; checked against long-double log). */
 /* Where the log table is read from: global memory through the read-only path (small shapes: one-warp CTAs that live for
  * one work item), or a per-CTA copy in shared memory (larger shapes: few, long-lived CTAs with two warps per
  * sub-partition, where the shorter LDS latency matters). */
 struct LogTabGlobal {
-    const double2 *base;
+    const double2 *base;          /* log table, followed by the sin/cos table */
     __device__ __forceinline__ double2 at(unsigned byte_off) const {
         return __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(base) + byte_off));
     }
+    __device__ __forceinline__ double2 sincos_at(unsigned byte_off) const { return at(byte_off + ME_LOGTAB_ENTRIES * 16u); }
 };
 struct LogTabShared {
-    const double2 *base;          /* points into a __shared__ array */
+    const double2 *base;          /* points into a __shared__ array holding both tables */
     __device__ __forceinline__ double2 at(unsigned byte_off) const {
         return *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(base) + byte_off);
     }
+    __device__ __forceinline__ double2 sincos_at(unsigned byte_off) const { return at(byte_off + ME_LOGTAB_ENTRIES * 16u); }
 };
 
 template <class Tab>
@@ -106,10 +117,10 @@ __device__ __forceinline__ double neg2log_unit(double u, const Tab &logtab) {
     /* n = 1023 - (biased exponent + [i >= 424]) >= 0: minus the exponent of the folded mantissa, as one subtract+shift */
     const int n = (int)((unsigned)(0x3ff69fff - hi) >> 20);
     const double r = fma(m, e.x, -1.0);
-    /* log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5 ; |r| <= 2^-10 -> truncation r^6/6 < 2^-62 */
-    double p = fma(r, 0.2, -0.25);
-    p = fma(r, p, me_kc[3]);
-    p = fma(r, p, -0.5);
+    /* log1p(r) = r - r^2/2 + r^3/3 ; |r| <= 2^-10 -> truncation r^4/4 < 2.3e-13 absolute (accuracy budget of the draw
+       stage: 1e-10 — the proposal is symmetric whatever the accuracy, and the Metropolis threshold is only trusted to
+       4e-5 T before the exact fallback, see accept_window) */
+    double p = fma(r, me_kc[3], -0.5);
     p = fma(r * r, p, r);
     const double nd = __hiloint2double(0x43300000, n) - 4503599627370496.0;              /* (double)n */
     /* -2 ln u = n (2 ln2_hi) + (-2 l + -2 (p - n ln2_lo)) */
@@ -119,13 +130,23 @@ __device__ __forceinline__ double neg2log_unit(double u, const Tab &logtab) {
     return __hiloint2double(__double2hiint(w) & 0x7fffffff, __double2loint(w));
 }
 
-/* sqrt(w) for a normal, strictly positive w: MUFU.RSQ64H seed (2^-22), one coupled Newton step for 1/sqrt and one for
- * the root (relative error < 2^-52.5; no range check, no slow path — the Box-Muller argument is in [2e-16, 74]). */
+/* sqrt(w) for a normal, strictly positive w: MUFU.RSQ64H seed (2^-22) and one Newton step for 1/sqrt (no range check,
+ * no slow path — the Box-Muller argument is in [2e-16, 74]). */
 __device__ __forceinline__ double sqrt_pos(double w) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
     const double e = fma(-w, y * y, 1.0);
     const double yh = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));       /* y / 2 */
+    const double y1 = fma(yh, e, y);
+    return w * y1;                     /* relative error (3/8) e^2 < 1e-13: inside the draw stage's accuracy budget */
+}
+
+/* the same with the final correction step (relative error < 2^-52.5) */
+__device__ __forceinline__ double sqrt_pos_full(double w) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(w));
+    const double e = fma(-w, y * y, 1.0);
+    const double yh = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
     const double y1 = fma(yh, e, y);
     const double s = w * y1;
     const double y1h = __hiloint2double(__double2hiint(y1) - 0x00100000, __double2loint(y1));
@@ -188,6 +209,25 @@ __device__ __forceinline__ void sincospi_bits(unsigned z, double &sn, double &cs
     const double a = odd ? cr : sr, b = odd ? sr : cr;
     sn = __hiloint2double(__double2hiint(a) ^ (int)(zz & 0x80000000u), __double2loint(a));
     cs = __hiloint2double(__double2hiint(b) ^ (int)((zz + 0x40000000u) & 0x80000000u), __double2loint(b));
+}
+
+/* sin(pi t), cos(pi t) for t = z 2^-31, table-driven (throughput build): interval i = z >> 22 of 1024, midpoint values
+ * {sin a_i, cos a_i} from the table, residual angle b = kappa v with the exact integer v = (z mod 2^22) - 2^21 in
+ * [-2^21, 2^21) (one DADD on a mantissa-assembled double), |b| <= pi/1024:
+ *     sin b = v (kappa - kappa^3/6 v^2)          (b^5/120 < 2.3e-15)
+ *     cos b - 1 = v^2 (-kappa^2/2 + kappa^4/24 v^2)  (b^6/720 < 2e-18)
+ *     sin(a + b) = sa + (sa (cos b - 1) + ca sin b),   cos(a + b) = ca + (ca (cos b - 1) - sa sin b).
+ * 10 FP64 instructions and no quadrant fix-up (the table covers the full circle), against 17 + 8 integer ones for the
+ * polynomial version; absolute error < 1e-14. */
+template <class Tab>
+__device__ __forceinline__ void sincospi_tab(unsigned z, double &sn, double &cs, const Tab &tab, const double bias) {
+    const double2 e = tab.sincos_at((z >> 18) & ((ME_SINTAB_ENTRIES - 1) << 4));        /* {sin a_i, cos a_i} */
+    const double v = __hiloint2double(0x43300000, (int)(z & 0x003fffffu)) - bias;        /* exact */
+    const double v2 = v * v;
+    const double sb = v * fma(v2, me_kc[29], me_kc[28]);
+    const double cm = v2 * fma(v2, me_kc[31], me_kc[30]);
+    sn = fma(e.x, cm, fma(e.y, sb, e.x));
+    cs = fma(e.y, cm, fma(-e.x, sb, e.y));
 }
 
 }  // namespace me

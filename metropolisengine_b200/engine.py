@@ -1063,7 +1063,9 @@ class MetropolisEngine:
         cut = [t for key, (t, _g, _n) in self.eq_points.items() if "sampling_width" not in key]
         self.global_eq_point = max(cut) if cut else 0
         def means_from(frame):                                                              # statistics.py:53-64
-            return {name: np.average(frame.loc[self.global_eq_point:, name]) for name in frame.columns.values}
+            # (the reference averages every column and would raise on a string-valued external frame; those are skipped)
+            return {name: np.average(frame.loc[self.global_eq_point:, name]) for name in frame.columns.values
+                    if np.issubdtype(frame[name].dtype, np.number)}
 
         self.equilibrated_means, self.eq_means_error = means_from(own), {}                  # ME:494
         if external_df is not None:                                                          # ME:495-502

@@ -1,5 +1,6 @@
 """Shared-covariance ensemble engine for large parameter spaces (BASELINE config 4: cylinder-style field with 1 real
-amplitude + 64 complex Fourier coefficients), driving the tcgen05 kernel of csrc/me_k4.cu.
+amplitude + n_c complex Fourier coefficients, n_c = 8, 16, 32 or 64), driving the warp-specialised tcgen05 kernel of
+csrc/me_k4_device.cuh.
 
 Same public surface as ``MetropolisEngine`` (reference metropolisengine/metropolis_engine.py: ``step_all`` ME:241-259,
 ``measure`` ME:342-356, ``real_mean`` / ``complex_mean`` / ``covariance_matrix_*`` / ``observables_mean`` /
@@ -25,16 +26,33 @@ from . import _lib
 from . import parallel
 from .engine import adaptation_constants, _ptr
 
-N_C = 64
+N_C = 64          # default number of complex parameters (BASELINE config 4)
+
+
+class SharedEnergy:
+    """User energy functor of the shared-covariance path (the reference's plugin surface, ME:20, 110-120).  ``source``
+    is CUDA C++ defining the per-mode contributions to two sums and the total (include/me_b200.h, me_k4_set_energy_source)::
+
+        __device__ void   me_k4_mode(double q, double re, double im, const double* k, double& s0, double& s1);  // q = j - n_c/2
+        __device__ double me_k4_total(double a, double s0, double s1, const double* k, int n_c);
+        __device__ bool   me_k4_reject(double a, const double* k);          // only when has_reject=True
+
+    i.e. energies E = total(a, sum_j f0_j(c_j), sum_j f1_j(c_j)); compiled by NVRTC into the same tcgen05 step kernel."""
+
+    def __init__(self, source, consts=(), has_reject=False):
+        self.source, self.consts, self.has_reject = source, tuple(float(c) for c in consts), bool(has_reject)
 
 
 class SharedCovarianceEngine:
     def __init__(self, energy_consts=(10.0, -1.0, 0.05, 1.0), reject_condition=True, initial_real_params=None,
                  initial_complex_params=None, sampling_width=0.05, covariance_matrix_real=None,
                  covariance_matrix_complex=None, params_names=None, target_acceptance=.3, temp=0, *, n_chains=128,
-                 seed=0, device=None, record=True, distributed=False, ts_chunk_rows=64, async_refresh=True):
-        """``energy_consts`` = (kappa, alpha, gamma, beta) of the cylinder-style energy (SURVEY.md §8d C4);
-        ``reject_condition=True`` enables its hard wall ``|a| >= 1`` (legacy metropolis_engine.py:103,139)."""
+                 seed=0, device=None, record=True, distributed=False, ts_chunk_rows=64, async_refresh=True,
+                 energy=None, n_complex=None):
+        """``energy_consts`` = (kappa, alpha, gamma, beta) of the built-in cylinder-style energy (SURVEY.md §8d C4);
+        ``reject_condition=True`` enables its hard wall ``|a| >= 1`` (legacy metropolis_engine.py:103,139).
+        ``energy``: a ``SharedEnergy`` (user CUDA functor) instead of the built-in one.  The number of complex parameters
+        (8, 16, 32 or 64) is taken from ``initial_complex_params`` (or ``n_complex``; default 64)."""
         if not torch.cuda.is_available():
             raise RuntimeError("SharedCovarianceEngine needs a CUDA device: the hot path is CUDA-only (no CPU fallback)")
         if temp is None or not temp >= 0:
@@ -44,27 +62,30 @@ class SharedCovarianceEngine:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        lay = _lib.MeK4Layout()
-        self._lib.me_k4_layout_get(ctypes.byref(lay))
-        self._lay = lay
-        self.num_real_params, self.num_complex_params = 1, N_C
         xr = np.zeros(1) if initial_real_params is None else np.asarray(initial_real_params, dtype=np.float64)
-        xc = (np.zeros(N_C, dtype=np.complex128) if initial_complex_params is None
+        nc = int(n_complex) if n_complex is not None else (N_C if initial_complex_params is None
+                                                           else np.asarray(initial_complex_params).shape[-1])
+        xc = (np.zeros(nc, dtype=np.complex128) if initial_complex_params is None
               else np.asarray(initial_complex_params, dtype=np.complex128))
-        if xr.shape[-1] != 1 or xc.shape[-1] != N_C:
-            raise ValueError("the shared-covariance path is built for 1 real + 64 complex parameters")
+        if xr.shape[-1] != 1 or xc.shape[-1] != nc or nc not in (8, 16, 32, 64):
+            raise ValueError("the shared-covariance path serves 1 real + 8 / 16 / 32 / 64 complex parameters")
+        self._nc = nc
+        lay = _lib.MeK4Layout()
+        self._lib.me_k4_layout_for(nc, ctypes.byref(lay))
+        self._lay = lay
+        self.num_real_params, self.num_complex_params = 1, nc
         self.n_chains_total = int(n_chains)
         self._rank, self._world = (parallel.world() if distributed else (0, 1))
         lo, hi = parallel.shard_range(self.n_chains_total, self._rank, self._world)
         self.chain_offset, self.n_chains = lo, hi - lo
         self._distributed = bool(distributed) and self._world > 1
         self.temp, self.target_acceptance = temp, target_acceptance
-        self.alpha, self.m, self.ratio = adaptation_constants(1, N_C, target_acceptance)
-        self.params_names = list(params_names) if params_names else ["param_" + str(i) for i in range(1 + N_C)]
-        self.observables_names = ["abs_param_" + str(i) for i in range(1 + N_C)] + ["param_0_squared"]
+        self.alpha, self.m, self.ratio = adaptation_constants(1, nc, target_acceptance)
+        self.params_names = list(params_names) if params_names else ["param_" + str(i) for i in range(1 + nc)]
+        self.observables_names = ["abs_param_" + str(i) for i in range(1 + nc)] + ["param_0_squared"]
         self.seed = int(seed)
         self.df = None
-        cfg = _lib.MeK4Config(1, N_C, self.n_chains, self.chain_offset, float(temp), float(target_acceptance),
+        cfg = _lib.MeK4Config(1, nc, self.n_chains, self.chain_offset, float(temp), float(target_acceptance),
                               self.ratio, self.seed, self.device.index, int(bool(reject_condition)),
                               (ctypes.c_double * 4)(*[float(c) for c in energy_consts]))
         h = ctypes.c_void_p()
@@ -73,11 +94,17 @@ class SharedCovarianceEngine:
             msg = self._lib.me_k4_last_error(None).decode()
             raise ValueError(msg) if rc == _lib.ME_ERR_INVALID else _lib.MeError(msg)
         self._h = h
+        if energy is not None:
+            if not isinstance(energy, SharedEnergy):
+                raise TypeError("energy must be a SharedEnergy (CUDA functor of the shared-covariance path)")
+            consts = (ctypes.c_double * max(len(energy.consts), 1))(*energy.consts)
+            self._check(self._lib.me_k4_set_energy_source(self._h, energy.source.encode(), consts, len(energy.consts),
+                                                          int(energy.has_reject)))
         dev, f64 = self.device, torch.float64
         self.state = torch.zeros((lay.WORDS, self.n_chains), dtype=f64, device=dev)
         # factor / s_a are triple-buffered: one pair is read by the step kernel, one holds the finished refresh that the
         # next launch adopts, one is being written by the refresh in flight
-        self._factors = [torch.zeros((16, 128, 8), dtype=torch.bfloat16, device=dev) for _ in range(3)]
+        self._factors = [torch.zeros((2 * nc // 8, 2 * nc, 8), dtype=torch.bfloat16, device=dev) for _ in range(3)]
         self._s_as = [torch.ones(1, dtype=f64, device=dev) for _ in range(3)]
         self._cur = 0
         self._factor, self._s_a = self._factors[0], self._s_as[0]
@@ -89,7 +116,7 @@ class SharedCovarianceEngine:
         self._last_accept = torch.zeros(self.n_chains, dtype=torch.uint8, device=dev)
         self._check(self._lib.me_k4_bind(self._h, _ptr(self.state), _ptr(self._factor), _ptr(self._last_accept)))
         # shared covariances (ME:63-70): identity unless given
-        self._cov_c = (torch.eye(N_C, dtype=torch.complex128, device=dev) if covariance_matrix_complex is None
+        self._cov_c = (torch.eye(nc, dtype=torch.complex128, device=dev) if covariance_matrix_complex is None
                        else torch.as_tensor(np.asarray(covariance_matrix_complex, dtype=np.complex128),
                                             device=dev).contiguous())
         self._cov_a = torch.ones(1, dtype=f64, device=dev) if covariance_matrix_real is None else \
@@ -104,7 +131,7 @@ class SharedCovarianceEngine:
         self._incs = [torch.zeros(lay.MOM_WORDS, dtype=torch.complex128, device=dev) for _ in range(2)]
         self._inc_full = self._incs[0]          # increment of the latest measure
         self._measure_count = 0
-        self._mom = torch.zeros(4 + N_C + N_C * N_C, dtype=torch.complex128, device=dev)   # count, -, sum a, sum a^2, sum c, sum c c^H
+        self._mom = torch.zeros(4 + nc + nc * nc, dtype=torch.complex128, device=dev)   # count, -, sum a, sum a^2, sum c, sum c c^H
         self._snaps = [torch.zeros(lay.MOM_WORDS + 2, dtype=torch.complex128, device=dev) for _ in range(2)]
         self._snap_events = [None, None]
         if self._async:
@@ -115,8 +142,8 @@ class SharedCovarianceEngine:
         if per_chain:
             full = np.zeros((lay.D, self.n_chains_total))
             full[0] = xr[:, 0] if xr.ndim == 2 else xr[0]
-            full[1:1 + N_C] = xc.real.T if xc.ndim == 2 else xc.real[:, None]
-            full[1 + N_C:] = xc.imag.T if xc.ndim == 2 else xc.imag[:, None]
+            full[1:1 + nc] = xc.real.T if xc.ndim == 2 else xc.real[:, None]
+            full[1 + nc:] = xc.imag.T if xc.ndim == 2 else xc.imag[:, None]
             x0_dev = torch.tensor(np.ascontiguousarray(full[:, lo:hi]), dtype=f64, device=dev)
         else:
             x0_dev = torch.tensor(x0, dtype=f64, device=dev)
@@ -140,13 +167,20 @@ class SharedCovarianceEngine:
             e = BuiltinEnergy(e)
         elif isinstance(e, tuple) and e and isinstance(e[0], str):
             e = BuiltinEnergy(e[0], *e[1:])
-        if not isinstance(e, BuiltinEnergy) or e.name != "cylinder":
-            raise NotImplementedError("adapt='pooled' (shared proposal covariance on the tensor cores) serves the "
-                                      "cylinder-style device functor; other energies use adapt='per_chain'")
         if reject_condition is not None:
-            raise NotImplementedError("adapt='pooled': put the hard wall in the functor (BuiltinEnergy(reject=True))")
+            raise NotImplementedError("adapt='pooled': put the hard wall in the functor (BuiltinEnergy(reject=True) / "
+                                      "SharedEnergy(has_reject=True))")
         for k in ("strict", "callable_layout", "graph_callable", "ts_chunk_bytes", "_shard"):
             kw.pop(k, None)
+        if isinstance(e, SharedEnergy):
+            return cls(energy=e, reject_condition=e.has_reject, initial_real_params=initial_real_params,
+                       initial_complex_params=initial_complex_params, sampling_width=sampling_width,
+                       covariance_matrix_real=covariance_matrix_real, covariance_matrix_complex=covariance_matrix_complex,
+                       params_names=params_names, target_acceptance=target_acceptance, temp=temp, **kw)
+        if not isinstance(e, BuiltinEnergy) or e.name != "cylinder":
+            raise NotImplementedError("adapt='pooled' (shared proposal covariance on the tensor cores) serves the "
+                                      "cylinder-style device functor or a SharedEnergy; other energies use "
+                                      "adapt='per_chain'")
         consts = e.consts if len(e.consts) == 4 else (10.0, -1.0, 0.05, 1.0)
         return cls(energy_consts=consts, reject_condition=e.reject, initial_real_params=initial_real_params,
                    initial_complex_params=initial_complex_params, sampling_width=sampling_width,
@@ -177,14 +211,15 @@ class SharedCovarianceEngine:
         canonical K-major layout [k-chunk][n][8]; s_a = sqrt(C_a).  Stream-ordered, no host sync."""
         G = torch.linalg.cholesky_ex(self._cov_c)[0]
         gr, gi = G.real / math.sqrt(2.0), G.imag / math.sqrt(2.0)
-        B = torch.zeros((2 * N_C, 2 * N_C), dtype=torch.float64, device=self.device)
+        n2 = 2 * self._nc
+        B = torch.zeros((n2, n2), dtype=torch.float64, device=self.device)
         B[0::2, 0::2] = gr
         B[0::2, 1::2] = gi
         B[1::2, 0::2] = -gi
         B[1::2, 1::2] = gr
         self._B = B
         for f, sa in zip(self._factors, self._s_as):
-            f.copy_(B.view(128, 16, 8).permute(1, 0, 2).to(torch.bfloat16))
+            f.copy_(B.view(n2, n2 // 8, 8).permute(1, 0, 2).to(torch.bfloat16))
             sa.copy_(torch.sqrt(self._cov_a))
 
     @property
@@ -219,11 +254,14 @@ class SharedCovarianceEngine:
             self._side.synchronize()
 
     def step(self, k=1, _dbg=None):
-        dz = dd = None
+        """``k`` x step_all() in one launch.  ``_dbg``: (normals [2 n_c, chains] f32, increments [2 n_c, chains] f32[,
+        scalar draws [2, chains] f64]) taps of the first step of the launch (tests, oracle injection)."""
+        dz = dd = ds = None
         if _dbg is not None:
-            dz, dd = _dbg
+            dz, dd = _dbg[0], _dbg[1]
+            ds = _dbg[2] if len(_dbg) > 2 else None
         self._adopt_refresh()
-        self._launch(self._lib.me_k4_step(self._h, int(k), _ptr(self._s_a), _ptr(dz), _ptr(dd), self._stream()))
+        self._launch(self._lib.me_k4_step(self._h, int(k), _ptr(self._s_a), _ptr(dz), _ptr(dd), _ptr(ds), self._stream()))
         if self._in_flight is not None:           # the refresh launched at the last measure becomes adoptable
             self._ready, self._in_flight = self._in_flight, None
 
@@ -320,7 +358,8 @@ class SharedCovarianceEngine:
     @property
     def complex_params_per_chain(self):
         x = self._lay.X
-        return torch.complex(self.state[x + 1:x + 1 + N_C], self.state[x + 1 + N_C:x + 1 + 2 * N_C]).t()
+        nc = self._nc
+        return torch.complex(self.state[x + 1:x + 1 + nc], self.state[x + 1 + nc:x + 1 + 2 * nc]).t()
 
     @property
     def sampling_width_per_chain(self):
@@ -341,11 +380,12 @@ class SharedCovarianceEngine:
     @property
     def complex_mean(self):
         m = self._lay.MEAN
-        return self._pooled(torch.complex(self.state[m + 1:m + 1 + N_C], self.state[m + 1 + N_C:m + 1 + 2 * N_C]))
+        nc = self._nc
+        return self._pooled(torch.complex(self.state[m + 1:m + 1 + nc], self.state[m + 1 + nc:m + 1 + 2 * nc]))
 
     @property
     def observables_mean(self):
-        return self._pooled(self.state[self._lay.OBSM:self._lay.OBSM + 2 + N_C])
+        return self._pooled(self.state[self._lay.OBSM:self._lay.OBSM + 2 + self._nc])
 
     @property
     def covariance_matrix_real(self):
@@ -384,16 +424,16 @@ class SharedCovarianceEngine:
         """``self.df`` for one chain, reference column order (ME:466-478)."""
         import pandas
         rows = self.time_series()[:, :, chain].cpu().numpy()
-        d = self._lay.D
-        a, c = rows[:, 0], rows[:, 1:1 + N_C] + 1j * rows[:, 1 + N_C:d]
+        d, nc = self._lay.D, self._nc
+        a, c = rows[:, 0], rows[:, 1:1 + nc] + 1j * rows[:, 1 + nc:d]
         cols = {self.observables_names[0]: np.abs(a)}
-        for j in range(N_C):
+        for j in range(nc):
             cols[self.observables_names[1 + j]] = np.abs(c[:, j])
-        cols[self.observables_names[1 + N_C]] = a * a
+        cols[self.observables_names[1 + nc]] = a * a
         cols["total_energy"] = rows[:, d]
         cols[self.params_names[0]] = a
         cols["real_group_sampling_width"] = rows[:, d + 1]
-        for j in range(N_C):
+        for j in range(nc):
             cols[self.params_names[1 + j]] = c[:, j]
         cols["complex_group_sampling_width"] = rows[:, d + 1]
         self.df = pandas.DataFrame.from_dict(cols)

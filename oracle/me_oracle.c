@@ -17,7 +17,7 @@
  *   observables ME:458-463     |x_i|, |c_j|, x_i^2
  * Two draw sources:
  *   MEO_INJECT  recorded increments delta[step][d] and uniforms u[step] (NaN = none drawn)  — parity level L-A
- *   MEO_PHILOX  Philox4x32-10 + Box-Muller + per-chain Cholesky factors — the SAME stream definition the CUDA
+ *   MEO_PHILOX  Philox4x32-7 + Box-Muller + per-chain Cholesky factors — the SAME stream definition the CUDA
  *               kernels use (key = seed, counter = (chain_lo, chain_hi, step, slot)), so a CUDA ensemble can be
  *               checked chain by chain.  (This part has no reference counterpart: the reference draws from
  *               numpy's global MT19937, ME:268,300.)
@@ -119,10 +119,12 @@ static int reject_eval(const meo_config *c, const double *x) {
     return 0;
 }
 
-/* ------------------------------------------------------------------ Philox4x32-10 + Gaussian pairs */
-static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                          uint32_t out[4]) {
-    for (int r = 0; r < 10; r++) {
+/* ------------------------------------------------------------------ Philox4x32-7 + Gaussian pairs */
+#define MEO_PHILOX_ROUNDS 7      /* the stream definition of the CUDA kernels (me_device.cuh, ME_PHILOX_ROUNDS) */
+
+static void philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, int rounds,
+                         uint32_t out[4]) {
+    for (int r = 0; r < rounds; r++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -136,7 +138,13 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 }
 
 void meo_philox(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot, uint32_t out[4]) {
-    philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), step, slot, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+    philox4x32_r((uint32_t)chain, (uint32_t)(chain >> 32), step, slot, (uint32_t)seed, (uint32_t)(seed >> 32),
+                 MEO_PHILOX_ROUNDS, out);
+}
+
+/* any round count, for the Random123 known-answer vectors (7 and 10 rounds) */
+void meo_philox_rounds(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot, int rounds, uint32_t out[4]) {
+    philox4x32_r((uint32_t)chain, (uint32_t)(chain >> 32), step, slot, (uint32_t)seed, (uint32_t)(seed >> 32), rounds, out);
 }
 
 /* sin(pi t), cos(pi t) for t in [0,2): exact octant reduction, then libm on |arg| <= pi/4 */

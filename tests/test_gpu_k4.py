@@ -1,10 +1,12 @@
 """Shared-covariance tensor-core path (BASELINE config 4 shape: 1 real + 64 complex), csrc/me_k4.cu.
 
-The reference has no shared-covariance mode (it is one chain), so parity here is: (i) the tensor-core contraction
-equals B.z computed in float64 from the same BF16 operands (FP32 accumulation tolerance 2e-5 relative to |B||z|);
-(ii) the in-kernel normals are standard; (iii) ensembles sample the exact stationary law of decoupled Gaussian
-modes (z-tests, tolerance stated per assertion) and agree with the per-chain FP64 C oracle of the same energy;
-(iv) hard wall, adaptation target, sharding invariance."""
+The reference has no shared-covariance mode (it is one chain), so parity here is: (i) the C restatement of this path
+(oracle/me_oracle_k4.c + oracle/k4_oracle.py) run beside the kernel on a whole 256-chain ensemble: generator stream,
+tensor-core increments (tolerance, then injected), identical accept decisions, bit-identical FP64 state, pooled
+covariance, Cholesky factor and its one-measure lag; (ii) an ensemble cross-check against the per-chain engine (pinned by
+goldens recorded from the live reference) on the full quartic energy; (iii) the tensor-core contraction equals B.z computed in
+float64 from the same BF16 operands; the in-kernel normals are standard; ensembles sample the exact stationary law of
+decoupled Gaussian modes; virial identity; hard wall, adaptation target, sharding invariance; user CUDA functors."""
 import numpy as np
 import pytest
 import torch
@@ -215,3 +217,163 @@ def test_asynchronous_factor_refresh_is_deterministic_and_lags_by_one_measure():
     s.run(1, 3); c.run(1, 3)      # the next block uses the new factor only in the sequential schedule
     torch.cuda.synchronize()
     assert not torch.equal(s.state[:129], c.state[:129])
+
+
+@pytest.mark.parametrize("nc,async_refresh", [(64, True), (16, True), (32, False)])
+def test_oracle_runs_beside_the_kernel_with_identical_decisions(nc, async_refresh):
+    """Level L-A of SURVEY §8c applied to the shared-covariance path.  A 256-chain ensemble is stepped one step per launch
+    with the taps on; the C oracle holds the same ensemble.  Per step: (1) the oracle's own Philox / Box-Muller / BF16
+    operand equals the kernel's except where MUFU.LG2 / MUFU.SQRT put a normal across a BF16 rounding boundary (<= 1 BF16
+    ulp there, and in < 0.5 % of the entries); (2) the oracle's B.z in float64 equals the tensor-core increments within the
+    FP32 accumulation tolerance 2e-5 |B||z|; (3) with the kernel's increments injected, every accept decision is identical
+    and the FP64 state (parameters, energy, width, count) is BIT-identical over 56 measures x 4 steps — across the
+    covariance switch-on at the 50th measure and the one-measure lag of the asynchronous factor refresh; (4) the pooled
+    covariance and the BF16 factor the engine computes equal the oracle's."""
+    import metropolisengine_b200 as me
+    from oracle import k4_oracle as ko
+    n, M, K = 256, 56, 4
+    consts, T, seed = (10.0, -1.0, 0.05, 1.0), 0.1, 41
+    x0c = 0.05 * np.exp(1j * np.arange(nc))
+    eng = me.SharedCovarianceEngine(energy_consts=consts, temp=T, n_chains=n, seed=seed, record=False,
+                                    initial_real_params=np.array([0.1]), initial_complex_params=x0c,
+                                    sampling_width=0.02, async_refresh=async_refresh)
+    x0 = np.concatenate([[0.1], x0c.real, x0c.imag])
+    orc = ko.K4Ensemble(nc, n, consts, T, eng.ratio, seed=seed, use_wall=True, sampling_width=0.02, x0=x0,
+                        async_refresh=async_refresh)
+    lay = eng._lay
+    N = 2 * nc
+    dz = torch.zeros((N, n), dtype=torch.float32, device="cuda")
+    dd = torch.zeros((N, n), dtype=torch.float32, device="cuda")
+    ds = torch.zeros((2, n), dtype=torch.float64, device="cuda")
+    assert np.array_equal(eng.state.cpu().numpy().T[:, :lay.NACC], orc.state[:, :lay.NACC])       # same initial state
+    flips = total = 0
+    nacc = np.zeros(n)
+    for im in range(M):
+        for k in range(K):
+            step = im * K + k
+            eng.step(1, _dbg=(dz, dd, ds))
+            torch.cuda.synchronize()
+            zg, dg, sg = dz.cpu().numpy().T, dd.cpu().numpy().T, ds.cpu().numpy()
+            orc.begin_step_launch()
+            # (1) generator stream
+            _z, zb = orc.normals(step)
+            neq = zb != zg
+            flips += int(neq.sum()); total += zb.size
+            assert np.all(np.abs(zb - zg)[neq] <= 2.0 ** -7 * np.abs(zg[neq]) + 1e-30), step
+            za_o, u_o = orc.scalars(step)
+            assert np.array_equal(u_o, sg[1]) and np.allclose(za_o, sg[0], rtol=3e-6, atol=1e-7), step
+            # the factor in use is the oracle's own (after the switch-on it came through the engine's refresh kernel)
+            Bg = eng._factor.float().permute(1, 0, 2).reshape(N, N).cpu().numpy()
+            assert np.mean(Bg != orc.B_now) < 2e-3 and np.allclose(Bg, orc.B_now, rtol=2.0 ** -7, atol=1e-12), step
+            orc.B_now = Bg
+            assert np.isclose(float(eng._s_a.item()), orc.s_a_now, rtol=1e-12)
+            orc.s_a_now = float(eng._s_a.item())
+            # (2) tensor-core increments
+            d_o, scale = orc.delta(zg)
+            assert np.all(np.abs(d_o - dg) <= 2e-5 * scale + 1e-30), step
+            # (3) injected step
+            acc = orc.step_injected(dg, sg[0], sg[1])
+            orc.end_step_launch()
+            nacc += acc
+            st = eng.state.cpu().numpy().T
+            assert np.array_equal(st[:, lay.NACC], nacc), "accept/reject decisions differ at step %d" % step
+            assert np.array_equal(st[:, lay.X:lay.SIG + 1], orc.state[:, lay.X:lay.SIG + 1]), step     # x, E, sigma
+        eng.measure()
+        orc.measure()
+        st = eng.state.cpu().numpy().T
+        assert np.allclose(st[:, lay.MEAN:lay.NACC], orc.state[:, lay.MEAN:lay.NACC], rtol=1e-12, atol=1e-15), im
+        if orc.n_measure > 50:
+            assert np.allclose(eng.covariance_matrix_complex, orc.cov_c, rtol=1e-9, atol=1e-14), im
+            assert np.isclose(float(eng.covariance_matrix_real[0, 0]), orc.cov_a, rtol=1e-9), im
+    assert flips / total < 5e-3, flips / total
+    assert 0.05 < nacc.sum() / (n * M * K) < 0.95
+    assert eng.measure_step_counter == orc.n_measure == M + 1
+
+
+def test_user_functor_on_the_tensor_core_path_matches_the_builtin_one():
+    """The energy plugin on the shared-covariance path: CUDA text with the sufficient-statistics contract
+    (me_k4_set_energy_source), compiled by NVRTC into the same warp-specialised kernel.  Restating the cylinder energy
+    must reproduce the built-in functor's chains; a different energy (no quartic term, no wall) must sample its exact law."""
+    import metropolisengine_b200 as me
+    src = """
+__device__ void me_k4_mode(double q, double re, double im, const double* k, double& s0, double& s1) {
+    const double m2 = fma(re, re, im * im);
+    s0 += m2;
+    s1 = fma(q * q, m2, s1);
+}
+__device__ double me_k4_total(double a, double s0, double s1, const double* k, int nc) {
+    const double a2 = a * a;
+    const double inner = fma(k[1], s0, (k[2] * (1.0 + a2)) * s1);
+    return fma(k[3] / (2.0 * (double)nc), s0 * s0, fma(k[0], a2, inner));
+}
+__device__ bool me_k4_reject(double a, const double* k) { return fabs(a) >= 1.0; }
+"""
+    consts = (10.0, -1.0, 0.05, 1.0)
+    kw = dict(temp=.1, n_chains=512, seed=6, record=False, n_complex=32)
+    a = me.SharedCovarianceEngine(energy_consts=consts, **kw)
+    b = me.SharedCovarianceEngine(energy=me.SharedEnergy(src, consts=consts, has_reject=True), **kw)
+    a.run(53, 5)
+    b.run(53, 5)
+    torch.cuda.synchronize()
+    assert torch.equal(a.accept_count_per_chain, b.accept_count_per_chain)
+    assert torch.equal(a.state, b.state)
+    # a functor of its own: independent modes with stiffness k0 + k1 q^4, harmonic amplitude, no wall
+    src2 = """
+__device__ void me_k4_mode(double q, double re, double im, const double* k, double& s0, double& s1) {
+    const double m2 = re * re + im * im;
+    s0 += m2;
+    s1 += (q * q) * (q * q) * m2;
+}
+__device__ double me_k4_total(double a, double s0, double s1, const double* k, int nc) {
+    return k[2] * a * a + k[0] * s0 + k[1] * s1;
+}
+"""
+    T, k0, k1, k2 = 0.2, 1.0, 0.01, 4.0
+    c = me.SharedCovarianceEngine(energy=me.SharedEnergy(src2, consts=(k0, k1, k2)), reject_condition=False, temp=T,
+                                  n_chains=4096, seed=8, record=False, n_complex=8)
+    c.run(500, 10)
+    v = c.complex_params_per_chain.cpu().numpy()
+    q = np.arange(8) - 4.0
+    exact = T / (2.0 * (k0 + k1 * q ** 4))
+    for part in (v.real, v.imag):
+        z = (part.var(axis=0) - exact) / (exact * np.sqrt(2.0 / 4096))
+        assert np.max(np.abs(z)) < 5.0, z
+    av = c.real_params_per_chain.cpu().numpy()[:, 0].var()
+    assert abs(av - T / (2 * k2)) < 5 * (T / (2 * k2)) * np.sqrt(2.0 / 4096)
+    with pytest.raises(Exception):
+        me.SharedCovarianceEngine(energy=me.SharedEnergy("not CUDA"), temp=T, n_chains=128, n_complex=8)
+
+
+def test_pooled_engine_matches_the_per_chain_engine_on_the_quartic_energy():
+    """Ensemble cross-check: the shared-covariance engine against the per-chain engine (the reference's own algorithm,
+    pinned at this kind of shape by the goldens cyl_1r64c / magphase_1r16c recorded from the live reference) on the
+    full cylinder energy with its wall, 1 real + 16 complex.  Both sample the same law: two-sample KS on the marginals of
+    the amplitude, of the softest and the stiffest mode, z-test on <sum |c|^2>, acceptance near the target."""
+    import metropolisengine_b200 as me
+    nc, n, T = 16, 4096, 0.1
+    consts = (10.0, -1.0, 0.05, 1.0)
+    pooled = me.MetropolisEngine(me.BuiltinEnergy("cylinder", *consts, reject=True), initial_real_params=np.array([0.0]),
+                                 initial_complex_params=np.zeros(nc, dtype=complex), temp=T, n_chains=n, seed=12,
+                                 record=False, adapt="pooled")
+    per = me.MetropolisEngine(me.BuiltinEnergy("cylinder", *consts, reject=True), initial_real_params=np.array([0.0]),
+                              initial_complex_params=np.zeros(nc, dtype=complex), temp=T, n_chains=n, seed=13,
+                              record=False)
+    assert isinstance(pooled, me.SharedCovarianceEngine) and per._generic
+    pooled.run(500, 10)
+    per.run(500, 10)
+    a0, a1 = pooled.accept_count_per_chain.clone(), per.accept_count_per_chain.clone()
+    pooled.run(40, 10)
+    per.run(40, 10)
+    for eng, acc0 in ((pooled, a0), (per, a1)):
+        acc = ((eng.accept_count_per_chain - acc0).sum() / (400.0 * n)).item()
+        assert 0.22 < acc < 0.40, acc
+    cp, cq = pooled.complex_params_per_chain.cpu().numpy(), per.complex_params_per_chain.cpu().numpy()
+    ap, aq = pooled.real_params_per_chain.cpu().numpy()[:, 0], per.real_params_per_chain.cpu().numpy()[:, 0]
+    assert stats.ks_2samp(ap, aq).pvalue > 1e-3
+    for j in (0, nc // 2, nc - 1):                     # q = -8 (stiff), 0 (soft: alpha < 0, held by the quartic term), 7
+        assert stats.ks_2samp(np.abs(cp[:, j]), np.abs(cq[:, j])).pvalue > 1e-3, j
+        assert stats.ks_2samp(cp[:, j].real, cq[:, j].real).pvalue > 1e-3, j
+    tp, tq = (np.abs(cp) ** 2).sum(1), (np.abs(cq) ** 2).sum(1)
+    z = (tp.mean() - tq.mean()) / np.sqrt(tp.var() / n + tq.var() / n)
+    assert abs(z) < 5.0, z
+    assert np.all(np.abs(ap) < 1.0) and np.all(np.abs(aq) < 1.0)

@@ -108,19 +108,28 @@ def test_c_oracle_is_bit_identical_where_arithmetic_coincides(name):
 
 
 def test_philox_known_answer():
-    """Philox4x32-10 known-answer vectors from the Random123 distribution (kat_vectors): zero and all-ones
-    counter/key, and the pi-digits vector."""
+    """Philox4x32 known-answer vectors from the Random123 distribution (kat_vectors): zero and all-ones
+    counter/key and the pi-digits vector, for the 10-round default and for the 7 rounds of this stream definition."""
     import ctypes
     out = (ctypes.c_uint32 * 4)()
     L = co.lib()
+
+    def run(seed, chain, step, slot, rounds):
+        L.meo_philox_rounds(ctypes.c_uint64(seed), ctypes.c_uint64(chain), ctypes.c_uint32(step), ctypes.c_uint32(slot),
+                            ctypes.c_int(rounds), out)
+        return [hex(v) for v in out]
+
+    ones64, ones32 = 0xffffffffffffffff, 0xffffffff
+    pi = (0x299f31d0a4093822, 0x85a308d3243f6a88, 0x13198a2e, 0x03707344)
+    assert run(0, 0, 0, 0, 10) == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    assert run(ones64, ones64, ones32, ones32, 10) == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    assert run(*pi, 10) == ['0xd16cfe09', '0x94fdcceb', '0x5001e420', '0x24126ea1']
+    assert run(0, 0, 0, 0, 7) == ['0x5f6fb709', '0xd893f64', '0x4f121f81', '0x4f730a48']
+    assert run(ones64, ones64, ones32, ones32, 7) == ['0x5207ddc2', '0x45165e59', '0x4d8ee751', '0x8c52f662']
+    assert run(*pi, 7) == ['0x4dfccaba', '0x190a87f0', '0xc47362ba', '0xb6b5242a']
+    # the stream itself uses 7 rounds
     L.meo_philox(ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint32(0), ctypes.c_uint32(0), out)
-    assert [hex(v) for v in out] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
-    L.meo_philox(ctypes.c_uint64(0xffffffffffffffff), ctypes.c_uint64(0xffffffffffffffff),
-                 ctypes.c_uint32(0xffffffff), ctypes.c_uint32(0xffffffff), out)
-    assert [hex(v) for v in out] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
-    L.meo_philox(ctypes.c_uint64(0x299f31d0a4093822), ctypes.c_uint64(0x85a308d3243f6a88),
-                 ctypes.c_uint32(0x13198a2e), ctypes.c_uint32(0x03707344), out)
-    assert [hex(v) for v in out] == ['0xd16cfe09', '0x94fdcceb', '0x5001e420', '0x24126ea1']
+    assert [hex(v) for v in out] == ['0x5f6fb709', '0xd893f64', '0x4f121f81', '0x4f730a48']
 
 
 def test_philox_normals_are_standard():
