@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libme_oracle.so")
 
 ENERGY_IDS = {"x2": 0, "xy_well": 1, "mixed_well": 2, "cylinder": 3}
 E_CALLBACK = 100
-INJECT, PHILOX = 0, 1
+INJECT, PHILOX, XOSHIRO = 0, 1, 2
 
 _ENERGY_CB = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int)
 _REJECT_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int)
@@ -22,7 +22,7 @@ class Config(ctypes.Structure):
     _fields_ = [("n_r", ctypes.c_int), ("n_c", ctypes.c_int), ("energy_id", ctypes.c_int),
                 ("use_reject", ctypes.c_int), ("consts", ctypes.c_double * 16), ("temp", ctypes.c_double),
                 ("target", ctypes.c_double), ("ratio", ctypes.c_double), ("m", ctypes.c_int),
-                ("energy_cb", _ENERGY_CB), ("reject_cb", _REJECT_CB)]
+                ("energy_cb", _ENERGY_CB), ("reject_cb", _REJECT_CB), ("frozen", ctypes.c_int)]
 
 
 class Offsets(ctypes.Structure):
@@ -109,7 +109,7 @@ class CChain:
             self.state[self.off.SIG], self.state[self.off.SIG + 1] = widths[0], widths[1]
 
     def run(self, n_blocks, spm, do_measure=True, delta=None, u=None, seed=0, chain_id=0, step0=0, want_ts=False,
-            group=0):
+            group=0, generator="philox"):
         S = n_blocks * spm
         acc = np.zeros(max(S, 1), dtype=np.uint8)
         ts = np.zeros((max(n_blocks, 1), self.d + 3)) if want_ts else None
@@ -118,7 +118,7 @@ class CChain:
             u = np.ascontiguousarray(u, dtype=np.float64)
             mode = INJECT
         else:
-            mode = PHILOX
+            mode = XOSHIRO if generator == "xoshiro" else PHILOX
         rc = lib().meo_run_group(ctypes.byref(self.cfg), _dp(self.state), mode, ctypes.c_int64(n_blocks),
                                  ctypes.c_int64(spm), int(do_measure), ctypes.byref(self.n_measure), _dp(delta), _dp(u),
                                  ctypes.c_uint64(seed), ctypes.c_uint64(chain_id), ctypes.c_uint64(step0),

@@ -39,6 +39,8 @@
 #define MEO_MAX_D 160
 #define MEO_INJECT 0
 #define MEO_PHILOX 1
+#define MEO_XOSHIRO 2        /* an unrelated generator (xoshiro256++, sequential per chain) feeding the same Box-Muller and
+                                proposal code: shows which properties of a run belong to the algorithm, not to Philox */
 
 enum { MEO_E_X2 = 0, MEO_E_XY = 1, MEO_E_MIXED = 2, MEO_E_CYL = 3, MEO_E_CALLBACK = 100 };
 
@@ -54,6 +56,8 @@ typedef struct {
     int m;
     meo_energy_cb energy_cb;
     meo_reject_cb reject_cb;
+    int frozen;              /* experiment switch (tests/scripts/pooled_variance_offset.py): 1 = no width adaptation and no
+                                covariance recursion from now on (means / observable means still run) */
 } meo_config;
 
 typedef struct {
@@ -189,6 +193,37 @@ double meo_uniform(uint64_t seed, uint64_t chain, uint32_t step, int n_calls) {
     return ((double)bits + 0.5) * (1.0 / 17592186044416.0);     /* 2^-44 */
 }
 
+/* xoshiro256++ (Blackman & Vigna), state seeded by splitmix64 of (seed, chain); one stream per chain, kept in a small
+ * table keyed by the caller (the experiment driver runs one chain per object, sequentially) */
+static uint64_t xo_s[4];
+static uint64_t xo_rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+void meo_xoshiro_seed(uint64_t seed, uint64_t chain) {
+    uint64_t z = seed * 0x9E3779B97F4A7C15ull + chain * 0xD1B54A32D192ED03ull + 0x2545F4914F6CDD1Dull;
+    for (int i = 0; i < 4; i++) {
+        z += 0x9E3779B97F4A7C15ull;
+        uint64_t t = z;
+        t = (t ^ (t >> 30)) * 0xBF58476D1CE4E5B9ull;
+        t = (t ^ (t >> 27)) * 0x94D049BB133111EBull;
+        xo_s[i] = t ^ (t >> 31);
+    }
+}
+void meo_xoshiro_state(uint64_t *io, int set) { for (int i = 0; i < 4; i++) { if (set) xo_s[i] = io[i]; else io[i] = xo_s[i]; } }
+static uint64_t xo_next(void) {
+    const uint64_t r = xo_rotl(xo_s[0] + xo_s[3], 23) + xo_s[0];
+    const uint64_t t = xo_s[1] << 17;
+    xo_s[2] ^= xo_s[0]; xo_s[3] ^= xo_s[1]; xo_s[1] ^= xo_s[2]; xo_s[0] ^= xo_s[3];
+    xo_s[2] ^= t; xo_s[3] = xo_rotl(xo_s[3], 45);
+    return r;
+}
+static double xo_uniform(void) { return ((double)(xo_next() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+static void xo_normal_pair(double *z0, double *z1) {
+    const double u1 = xo_uniform(), t = 2.0 * xo_uniform();
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi_d(t, &s, &c);
+    *z0 = rad * c; *z1 = rad * s;
+}
+
 /* ------------------------------------------------------------------ Cholesky factors of the proposal covariances */
 static int herm_lo(int i, int j) { return 2 * (i * (i - 1) / 2 + j); }   /* j < i */
 
@@ -274,7 +309,7 @@ static void measure(const meo_config *c, double *st, const meo_offsets *o, int64
     if (n_r) {
         for (int i = 0; i < n_r; i++) old[i] = mean[i];
         for (int i = 0; i < n_r; i++) { mean[i] = mean[i] * shrink; mean[i] = mean[i] + x[i] / dn; }
-        if (n > 50) {
+        if (n > 50 && !c->frozen) {
             const double sig = st[o->SIG];
             const double small = (sig * sig) / dn;
             const double decay = dn2 / dn1, grow = dn / dn1;
@@ -298,7 +333,7 @@ static void measure(const meo_config *c, double *st, const meo_offsets *o, int64
             mr[j] = mr[j] * shrink; mi[j] = mi[j] * shrink;
             mr[j] = mr[j] + xr[j] * inv_n; mi[j] = mi[j] + xi[j] * inv_n;
         }
-        if (n > 50) {
+        if (n > 50 && !c->frozen) {
             const double sig = st[o->SIG + 1];
             const double small = (sig * sig) / dn;
             const double decay = dn2 / dn1, grow = dn / dn1;
@@ -325,7 +360,7 @@ static void measure(const meo_config *c, double *st, const meo_offsets *o, int64
     for (int i = 0; i < n_r; i++) om[i] = om[i] * shrink + fabs(x[i]) / dn;
     for (int j = 0; j < n_c; j++) om[n_r + j] = om[n_r + j] * shrink + hypot(x[n_r + j], x[n_r + n_c + j]) / dn;
     for (int i = 0; i < n_r; i++) om[n_r + n_c + i] = om[n_r + n_c + i] * shrink + (x[i] * x[i]) / dn;
-    if (n > 50 && meo_refactor(n_r, n_c, st, o)) st[o->STATUS] = 1.0;
+    if (n > 50 && !c->frozen && meo_refactor(n_r, n_c, st, o)) st[o->STATUS] = 1.0;
 }
 
 /* ------------------------------------------------------------------ the driver
@@ -401,7 +436,10 @@ int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, i
             } else {
                 double z[MEO_MAX_D + 1];
                 const uint32_t step = (uint32_t)(step0 + (uint64_t)s);
-                for (int q = 0; q < (d + 1) / 2; q++) meo_normal_pair(seed, chain_id, step, (uint32_t)q, &z[2 * q], &z[2 * q + 1]);
+                for (int q = 0; q < (d + 1) / 2; q++) {
+                    if (mode == MEO_XOSHIRO) xo_normal_pair(&z[2 * q], &z[2 * q + 1]);
+                    else meo_normal_pair(seed, chain_id, step, (uint32_t)q, &z[2 * q], &z[2 * q + 1]);
+                }
                 /* real block: sigma_r * (L z) ; z[0..n_r) */
                 const double *L = st + o.FACR;
                 for (int i = 0; i < n_r; i++) {
@@ -437,7 +475,7 @@ int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, i
                 if (diff <= 0) accept = 1;
                 else if (c->temp == 0) accept = 0;
                 else {
-                    double uu = (mode == MEO_INJECT) ? u[s]
+                    double uu = (mode == MEO_INJECT) ? u[s] : (mode == MEO_XOSHIRO) ? xo_uniform()
                               : meo_uniform(seed, chain_id, (uint32_t)(step0 + (uint64_t)s), (d + 1) / 2);
                     accept = uu <= exp(-1 * diff / c->temp);
                 }
@@ -449,7 +487,7 @@ int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, i
                 const int grouped = (kind == 0 && group != 0);
                 double *sg = grouped ? &st[o.SIG + (group == 1 ? 0 : 1)] : ((kind == 2) ? &st[o.SIG + 1] : &st[o.SIG]);
                 double cc = (*sg) * c->ratio;
-                if (group == 4) { /* phase redraw: no adaptation */ }
+                if (group == 4 || c->frozen) { /* phase redraw: no adaptation; frozen: experiment switch */ }
                 else if (accept) *sg = *sg + (cc * (1 - p)) / f;
                 else *sg = *sg - (cc * p) / f;
                 if (kind == 0 && !grouped) { st[o.SIG + 1] = st[o.SIG]; if (!(st[o.SIG] > 0)) st[o.STATUS] = 2.0; }

@@ -288,9 +288,9 @@ def _ensemble_worker(args):
         kw = dict(initial_real_params=[0.0], temp=.01); fn = en.x2; M, K = 1000, 1
     elif cfg == "c2":
         kw = dict(initial_real_params=np.array([0., 0.]), temp=.1); fn = en.xy_well; M, K = 1000, 10
-    else:
+    else:                 # "c3": the demo-style energy; "c3b": its bounded |x0 x1| variant — the one bench.py runs
         kw = dict(initial_real_params=np.zeros(3), initial_complex_params=np.zeros(4, dtype=complex), temp=.1)
-        fn = en.mixed_3r4c; M, K = 300, 10
+        fn = en.mixed_3r4c_bounded if cfg == "c3b" else en.mixed_3r4c; M, K = 300, 10
     with contextlib.redirect_stdout(io.StringIO()):
         e = me.MetropolisEngine(fn, **kw)
     acc = np.zeros(M * K, dtype=np.bool_)
@@ -309,11 +309,13 @@ def _ensemble_worker(args):
     return row
 
 
-def ensembles():
+def ensembles(only=None):
     """Per-chain end-of-run quantities of M independent reference chains (seed = chain index); the GPU
     ensemble tests compare distributions against these (two-sample KS, z-tests).  SURVEY.md §4."""
     import multiprocessing as mp
-    for cfg, M in (("c1", 512), ("c2", 256), ("c3", 96)):
+    for cfg, M in (("c1", 512), ("c2", 256), ("c3", 96), ("c3b", 192)):
+        if only and cfg not in only:
+            continue
         with mp.get_context("fork").Pool(os.cpu_count()) as pool:
             rows = pool.map(_ensemble_worker, [(cfg, s) for s in range(M)], chunksize=4)
         rows = np.array(rows, dtype=np.float64)
@@ -345,4 +347,4 @@ if __name__ == "__main__":
         check_survey_kats(ref)
         single_chain_cases(ref, a.only)
     if a.ensembles:
-        ensembles()
+        ensembles(a.only)

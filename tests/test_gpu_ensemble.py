@@ -117,6 +117,63 @@ def test_c3_mixed_ensemble_matches_reference_ensemble():
     _ks_and_z(om[:, -1], cols["obs_sq2"], "<x2^2>")
 
 
+def test_c3_benchmarked_energy_matches_reference_ensemble():
+    """The energy variant bench.py runs for config 3 (bounded |x0 x1| coupling) against a reference ensemble
+    of that same variant: M = 192 unmodified-reference chains, 300 x (10 steps + measure) (tests/golden/ensemble_c3b.npz)."""
+    import metropolisengine_b200 as me
+    ref = load_golden("ensemble_c3b")
+    cols = {str(c): ref["rows"][:, i] for i, c in enumerate(ref["columns"])}
+    eng = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5, 1.0), initial_real_params=np.zeros(3),
+                              initial_complex_params=np.zeros(4, dtype=complex), temp=.1, n_chains=4096, seed=404,
+                              record=False)
+    acc_all, acc_half2 = _run_with_half_acceptance(eng, 300, 10)
+    eng.check_status()
+    _ks_and_z(eng.sampling_width_per_chain.cpu().numpy(), cols["sigma"], "sigma")
+    _ks_and_z(acc_all, cols["acc_all"], "acceptance(all)")
+    _ks_and_z(acc_half2, cols["acc_half2"], "acceptance(2nd half)")
+    x = eng.real_params_per_chain.cpu().numpy()
+    m = eng.real_mean_per_chain.cpu().numpy()
+    cv = eng.covariance_matrix_real_per_chain.cpu().numpy()
+    for i in range(3):
+        _ks_and_z(x[:, i], cols["x%d" % i], "x%d" % i)
+        _ks_and_z(m[:, i], cols["mean%d" % i], "mean%d" % i)
+        _ks_and_z(cv[:, i, i], cols["cov%d%d" % (i, i)], "cov%d%d" % (i, i))
+    cabs = eng.complex_params_per_chain.abs().cpu().numpy()
+    cc = eng.covariance_matrix_complex_per_chain.cpu().numpy()
+    for j in range(4):
+        _ks_and_z(cabs[:, j], cols["absc%d" % j], "|c%d|" % j)
+        _ks_and_z(cc[:, j, j].real, cols["covc%d%d" % (j, j)], "covC%d%d" % (j, j))
+
+
+def test_full_size_c3_pooled_moments_and_acceptance():
+    """BASELINE config 3 at its full size (262,144 chains, the bench.py workload): the in-kernel pooled moments (warp
+    shuffles + shared memory + per-CTA slots + fixed-order reduction) must equal the moments recomputed from the stored
+    time-series rows, no chain may raise a status flag, and the acceptance over the second half sits at the target."""
+    import metropolisengine_b200 as me
+    n, M, K = 262144, 40, 10
+    eng = me.MetropolisEngine(("mixed_well", 1.0, -1.0, 0.5, 1.0), initial_real_params=np.zeros(3),
+                              initial_complex_params=np.zeros(4, dtype=complex), temp=.1, n_chains=n, seed=2024,
+                              ts_chunk_bytes=M * 14 * n * 8)
+    eng.run(M // 2, K)
+    a0 = eng.accept_count_per_chain.clone()
+    eng.run(M // 2, K)
+    eng.check_status()
+    acc = ((eng.accept_count_per_chain - a0).sum() / (n * (M // 2) * K)).item()
+    assert 0.3 < acc < 0.45, acc                      # 400 steps in: the width is still growing towards the 0.3 target
+    ps = eng.pooled_statistics()
+    ts = eng.time_series()                              # [M, 14, n]
+    assert ts.shape == (M, 14, n) and ps["count"] == M * n
+    x = ts[:, :11, :].permute(0, 2, 1).reshape(-1, 11)
+    mean = x.mean(dim=0).cpu().numpy()
+    cov = torch.cov(x.t()).cpu().numpy()
+    assert np.allclose(ps["mean_real"], mean[:3], rtol=1e-10, atol=1e-12)
+    assert np.allclose(ps["cov_real"], cov[:3, :3], rtol=1e-9, atol=1e-12)
+    cre = cov[3:7, 3:7] + cov[7:11, 7:11]
+    assert np.allclose(ps["cov_complex"].real, cre, rtol=1e-9, atol=1e-12)
+    # every stored row is a state the chain visited: the last row is the current state
+    assert torch.equal(ts[-1, :11, :], eng.state[:11])
+
+
 def test_full_size_c2_pooled_statistics_are_exact():
     """BASELINE config 2 chain count (65,536 chains) through size-independent properties: pooled mean 0, pooled
     variance T/2, zero correlation, <|x|> = sqrt(T/pi), acceptance -> target 0.3; and the pooled moments equal
