@@ -1065,7 +1065,7 @@ class MetropolisEngine:
         def means_from(frame):                                                              # statistics.py:53-64
             # (the reference averages every column and would raise on a string-valued external frame; those are skipped)
             return {name: np.average(frame.loc[self.global_eq_point:, name]) for name in frame.columns.values
-                    if np.issubdtype(frame[name].dtype, np.number)}
+                    if pandas.api.types.is_numeric_dtype(frame[name])}
 
         self.equilibrated_means, self.eq_means_error = means_from(own), {}                  # ME:494
         if external_df is not None:                                                          # ME:495-502
