@@ -39,11 +39,8 @@ constexpr int MAX_NC = 64;
 constexpr int MAX_N = 2 * MAX_NC;
 
 /* -------------------------------------------------------------------------------------------- step / init entry points */
-/* 17 warps x 32 x 112 registers = 60,928 of the SM's 65,536: registers are allocated per warp in units of 512, so 120
-   (3,840 -> 4,096 per warp) no longer fits 17 warps, and a __launch_bounds__ of 544 threads makes ptxas settle on 96 and
-   spill the epilogue */
 template <int NC, class Energy>
-__global__ void __maxnreg__(112) k4_steps(const __grid_constant__ StepParams p,
+__global__ void __launch_bounds__(k4::THREADS, 1) k4_steps(const __grid_constant__ StepParams p,
                                                            const __grid_constant__ k4::TensorMap bmap) {
     k4::steps_body<NC, Energy>(p, &bmap);
 }
@@ -482,7 +479,7 @@ int me_k4_set_energy_source(me_k4 *e, const char *src, const double *consts, int
             "  __device__ __forceinline__ static bool reject(double a, const double *k) {\n";
     text += use_reject ? "    return me_k4_reject(a, k); }\n" : "    return false; }\n";
     text += "};\n"
-            "extern \"C\" __global__ void __maxnreg__(112) me_k4_steps(const __grid_constant__ k4::StepParams p,\n"
+            "extern \"C\" __global__ void __launch_bounds__(k4::THREADS, 1) me_k4_steps(const __grid_constant__ k4::StepParams p,\n"
             "    const __grid_constant__ k4::TensorMap bmap) { k4::steps_body<ME_K4_NC, K4UserEnergy>(p, &bmap); }\n"
             "extern \"C\" __global__ void me_k4_init(const __grid_constant__ k4::StepParams p, const double *x0, int broadcast,\n"
             "    double sigma0) { k4::init_body<K4UserEnergy>(p, x0, broadcast, sigma0); }\n";
@@ -525,7 +522,7 @@ int me_k4_check_energy_source(const char *src, int32_t nc, int32_t use_reject, c
             "  __device__ __forceinline__ static bool reject(double a, const double *k) {\n";
     text += use_reject ? "    return me_k4_reject(a, k); }\n" : "    return false; }\n";
     text += "};\n"
-            "extern \"C\" __global__ void __maxnreg__(112) me_k4_steps(const __grid_constant__ k4::StepParams p,\n"
+            "extern \"C\" __global__ void __launch_bounds__(k4::THREADS, 1) me_k4_steps(const __grid_constant__ k4::StepParams p,\n"
             "    const __grid_constant__ k4::TensorMap bmap) { k4::steps_body<ME_K4_NC, K4UserEnergy>(p, &bmap); }\n";
     std::vector<std::string> opts = {"-DME_K4_NC=" + std::to_string(nc)};
     std::vector<char> cubin;

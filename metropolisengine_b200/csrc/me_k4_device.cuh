@@ -6,14 +6,15 @@
  *        Delta[128 chains x N] = Z[128 x K normals] . B^T[K x N],     N = K = 2 n_c,
  * B the real embedding of conj(G)/sqrt2 in interleaved (Re, Im) coordinates, C_c = G G^H.
  *
- * Roles inside a CTA of 17 warps (no CTA-wide barrier in the step loop):
+ * Roles inside a CTA of 16 warps (no CTA-wide barrier in the step loop):
  *   warps 8..15  GENERATORS  Philox4x32-7 -> FP32 Box-Muller -> BF16, written straight into the UMMA canonical K-major
  *                            operand layout.  The K dimension is produced in two halves, each its own pipeline stage
  *                            (mbarriers z_full / z_empty), so the generators of step s+1 start as soon as the MMAs of step
  *                            s have consumed the FIRST half of the operand: they never wait for the epilogue.
- *   warp  16     MMA ISSUER  one elected lane: K/16 x tcgen05.mma (M128, N, K16, kind::f16) per step into one of TWO FP32
- *                            accumulators in TMEM (lane = chain), tcgen05.commit -> mbarriers.  The shared factor B is
- *                            brought in once per CTA by TMA (cp.async.bulk.tensor through a tensor map).
+ *   warp 8 lane 0 MMA ISSUER after its warp's share of an operand half: K/32 x tcgen05.mma (M128, N, K16, kind::f16) into one
+ *                            of TWO FP32 accumulators in TMEM (lane = chain), tcgen05.commit -> mbarriers.  The shared
+ *                            factor B is brought in once per CTA by TMA (cp.async.bulk.tensor through a tensor map).
+ *                            (A 17th warp for this role would cost four warps of registers: they are granted in fours.)
  *   warps 0..7   EPILOGUE    thread (chain m, half h) owns the coordinates [h N/2, (h+1) N/2) of chain m for the whole launch:
  *                            tcgen05.ld -> x' = x + sigma Delta (FP64) -> the energy functor's per-mode sums -> ONE
  *                            64-thread named barrier with the thread of the other half -> both evaluate the (identical)
@@ -46,8 +47,9 @@ typedef unsigned long long u64;
 
 constexpr int TILE = 128;               /* chains per tile = MMA M = TMEM lanes */
 constexpr int EPI_WARPS = 8, GEN_WARPS = 8;
-constexpr int GEN_WARP0 = EPI_WARPS, MMA_WARP = EPI_WARPS + GEN_WARPS;
-constexpr int THREADS = 32 * (EPI_WARPS + GEN_WARPS + 1);
+constexpr int GEN_WARP0 = EPI_WARPS, MMA_WARP = GEN_WARP0;     /* lane 0 of the first generator warp also issues the MMAs */
+constexpr int THREADS = 32 * (EPI_WARPS + GEN_WARPS);          /* 16 warps: registers are granted to a CTA in groups of four
+                                                                  warps, so a 17th warp would cost as much as four */
 constexpr u32 SCALAR_SLOT = 0x10000u;   /* Philox slot of the per-chain scalar draws (beyond any operand chunk) */
 constexpr int PHILOX_ROUNDS = 7;
 
@@ -327,40 +329,17 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
     const long long n_tiles = range_hi > range_lo ? (range_hi - range_lo + TILE - 1) / TILE : 0;
     const long long n_steps = p.n_steps;
 
-    if (warp == MMA_WARP) {
-        /* ================================================================== MMA issuer (+ the factor's TMA load) */
-        if (lane == 0) {
-            if (p.use_tma) {
-                constexpr int ROWS = CHUNKS * N;                 /* rows of 16 bytes */
-                constexpr int BOX = ROWS < 256 ? ROWS : 256;
-                mbar_expect_tx(&S.b_full, (u32)(N * N * 2));
-                for (int r = 0; r < ROWS; r += BOX) tma_load_2d(S.ls + r * 16, bmap, &S.b_full, 0, r);
-                mbar_wait(&S.b_full, 0);
-            }
-            const u32 zs_addr = smem_u32(S.zs), ls_addr = smem_u32(S.ls);
-            long long it = 0;
-            for (long long t = 0; t < n_tiles; t++) {
-                for (long long s = 0; s < n_steps; s++, it++) {
-                    const u32 a = (u32)(it & 1);
-                    if (it >= 2) mbar_wait(&S.acc_empty[a], (u32)(((it >> 1) - 1) & 1));
-                    for (int h = 0; h < HALVES; h++) {
-                        mbar_wait(&S.z_full[h], (u32)(it & 1));
-                        tc_fence_after();
-#pragma unroll
-                        for (int k = 0; k < CH_HALF / 2; k++) {
-                            const int c = h * CH_HALF + 2 * k;       /* first of the two K chunks of this MMA */
-                            umma_bf16(tmem_base + a * TCOLS, umma_desc(zs_addr + c * A_LBO, A_LBO),
-                                      umma_desc(ls_addr + c * B_LBO, B_LBO), IDESC, (h > 0 || k > 0) ? 1u : 0u);
-                        }
-                        umma_commit(&S.z_empty[h]);                  /* the operand stage may be overwritten */
-                    }
-                    umma_commit(&S.acc_full[a]);                     /* the accumulator is complete */
-                }
-            }
+    if (warp >= GEN_WARP0) {
+        /* ================================================================== generators (+ the MMA issuer) */
+        const bool issuer = warp == MMA_WARP && lane == 0;
+        if (issuer && p.use_tma) {
+            constexpr int ROWS = CHUNKS * N;                 /* rows of 16 bytes */
+            constexpr int BOX = ROWS < 256 ? ROWS : 256;
+            mbar_expect_tx(&S.b_full, (u32)(N * N * 2));
+            for (int r = 0; r < ROWS; r += BOX) tma_load_2d(S.ls + r * 16, bmap, &S.b_full, 0, r);
+            mbar_wait(&S.b_full, 0);
         }
-        __syncwarp();
-    } else if (warp >= GEN_WARP0) {
-        /* ================================================================== generators */
+        const u32 zs_addr = smem_u32(S.zs), ls_addr = smem_u32(S.ls);
         const int gt = tid - 32 * GEN_WARP0;          /* 0..255 */
         const int m = gt & (TILE - 1);                /* operand row = chain within the tile */
         const int c_par = gt >> 7;                    /* this thread's chunk parity */
@@ -373,6 +352,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
             const u32 c0 = (u32)gch, c1 = (u32)(gch >> 32);
             for (long long s = 0; s < n_steps; s++, it++) {
                 const u32 step = (u32)(p.step0 + (u64)s);
+                const u32 a = (u32)(it & 1);
                 for (int h = 0; h < HALVES; h++) {
                     if (it >= 1) mbar_wait(&S.z_empty[h], (u32)((it - 1) & 1));
                     if (act) {
@@ -401,6 +381,21 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     fence_async_smem();          /* generic-proxy stores -> visible to the tensor-core (async) proxy */
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.z_full[h]);
+                    if (issuer) {
+                        /* Delta (+)= Z_half . B_half^T: CH_HALF / 2 x (M128, N, K16), accumulator `a` in TMEM */
+                        if (h == 0 && it >= 2) mbar_wait(&S.acc_empty[a], (u32)(((it >> 1) - 1) & 1));
+                        mbar_wait(&S.z_full[h], (u32)(it & 1));
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < CH_HALF / 2; k++) {
+                            const int c = h * CH_HALF + 2 * k;       /* first of the two K chunks of this MMA */
+                            umma_bf16(tmem_base + a * TCOLS, umma_desc(zs_addr + c * A_LBO, A_LBO),
+                                      umma_desc(ls_addr + c * B_LBO, B_LBO), IDESC, (h > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&S.z_empty[h]);                  /* the operand stage may be overwritten */
+                        if (h == HALVES - 1) umma_commit(&S.acc_full[a]);   /* the accumulator is complete */
+                    }
+                    __syncwarp();
                 }
             }
         }

@@ -22,8 +22,11 @@ struct Cfg {
  * work-queue time segmentation of run_body. */
 template <class C, bool SMALL = (C::NR + 2 * C::NC <= 4)>
 struct RunKernel;
+#ifndef ME_SMALL_MAXNREG
+#define ME_SMALL_MAXNREG 160     /* build-time experiment knob (make SMALL_NREG=...): see tests/scripts/nreg_probe.py */
+#endif
 template <class C>
-__global__ void __maxnreg__(160) k_run_small(const __grid_constant__ MeParams p) {
+__global__ void __maxnreg__(ME_SMALL_MAXNREG) k_run_small(const __grid_constant__ MeParams p) {
     run_body<C>(p);
 }
 #ifdef ME_BIG_MAXNREG

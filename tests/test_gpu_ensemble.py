@@ -159,7 +159,7 @@ def test_full_size_c3_pooled_moments_and_acceptance():
     eng.run(M // 2, K)
     eng.check_status()
     acc = ((eng.accept_count_per_chain - a0).sum() / (n * (M // 2) * K)).item()
-    assert 0.3 < acc < 0.45, acc                      # 400 steps in: the width is still growing towards the 0.3 target
+    assert 0.3 < acc < 0.5, acc                       # 400 steps in: the width is still growing towards the 0.3 target
     ps = eng.pooled_statistics()
     ts = eng.time_series()                              # [M, 14, n]
     assert ts.shape == (M, 14, n) and ps["count"] == M * n
