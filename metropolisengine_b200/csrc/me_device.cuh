@@ -669,17 +669,32 @@ __device__ __forceinline__ bool finish_step(Chain<Lay<Cfg::NR, Cfg::NC>> &c, dou
         if (e_new != e_new) c.status |= ME_STATUS_ENERGY_NAN;
         const double diff = e_new - c.e;
         accept = decide<STRICT>(diff, u, p, tables, g.hot, g.k64);
-        if (!STRICT && rng != nullptr && !accept && diff <= uhi) {
-            /* inside the FP32 window (about 2 steps in 10^5): the exact threshold from the same random bits */
-            Spare sp;
-            Rng::keep_spare(rng->bits(step, 0u), 0, sp);
-            accept = diff <= Rng::accept_threshold(sp, *logtab, half_temp);
+        if (!STRICT && rng != nullptr) {
+            /* inside the FP32 window (about 2 steps in 10^5): the exact threshold from the same random bits.  The branch
+               is taken by the whole (converged part of the) warp on a vote, so the common path stays straight-line code
+               that the compiler can interleave with the draw stages of the following steps */
+            const bool inside = !accept && diff <= uhi;
+            if (__any_sync(__activemask(), inside)) {
+                Spare sp;
+                Rng::keep_spare(rng->bits(step, 0u), 0, sp);
+                const double thr = Rng::accept_threshold(sp, *logtab, half_temp);
+                accept = accept | (inside & (diff <= thr));
+            }
         }
-        if (accept) {
-            c.e = e_new;
+        if (STRICT) {
+            if (accept) {
+                c.e = e_new;
 #pragma unroll
-            for (int i = 0; i < D; i++) c.x[i] = prop[i];
-            c.nacc_new += 1u;
+                for (int i = 0; i < D; i++) c.x[i] = prop[i];
+                c.nacc_new += 1u;
+            }
+        } else {
+            /* throughput build: selects, not a divergent branch — a reconvergence region in the middle of the step would
+               stop the compiler from interleaving the state update with the draw stages of the following steps */
+            c.e = accept ? e_new : c.e;
+#pragma unroll
+            for (int i = 0; i < D; i++) c.x[i] = accept ? prop[i] : c.x[i];
+            c.nacc_new += accept ? 1u : 0u;
         }
     }
     if (L::NC > 0 && group == 4) {
