@@ -723,8 +723,14 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     constexpr int D = L::D;
     /* small problems keep running statistics and pooled accumulators in registers for the whole launch;
        larger ones touch them in global memory at measure time only */
-    constexpr bool STATS_REG = (L::D + L::NCOVR + L::NCOVC + L::NOBS) <= 12;
-    constexpr bool POOL_REG = L::POOLW <= 9;
+#ifndef ME_STATS_REG_MAX
+#define ME_STATS_REG_MAX 12      /* build-time experiment knobs (tests/scripts/nreg_probe.py) */
+#endif
+#ifndef ME_POOL_REG_MAX
+#define ME_POOL_REG_MAX 9
+#endif
+    constexpr bool STATS_REG = (L::D + L::NCOVR + L::NCOVC + L::NOBS) <= ME_STATS_REG_MAX;
+    constexpr bool POOL_REG = L::POOLW <= ME_POOL_REG_MAX;
     constexpr bool POOL_OK = L::POOLW <= ME_MAX_POOLW;        /* static shared-memory budget */
     constexpr int PW = POOL_OK ? L::POOLW : 1;
 

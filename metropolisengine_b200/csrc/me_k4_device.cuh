@@ -6,20 +6,20 @@
  *        Delta[128 chains x N] = Z[128 x K normals] . B^T[K x N],     N = K = 2 n_c,
  * B the real embedding of conj(G)/sqrt2 in interleaved (Re, Im) coordinates, C_c = G G^H.
  *
- * Roles inside a CTA of 16 warps (no CTA-wide barrier in the step loop):
- *   warps 8..15  GENERATORS  Philox4x32-7 -> FP32 Box-Muller -> BF16, written straight into the UMMA canonical K-major
+ * Roles inside a CTA of 32 warps (no CTA-wide barrier in the step loop):
+ *   warps 16..31 GENERATORS  Philox4x32-7 -> FP32 Box-Muller -> BF16, written straight into the UMMA canonical K-major
  *                            operand layout.  The K dimension is produced in two halves, each its own pipeline stage
  *                            (mbarriers z_full / z_empty), so the generators of step s+1 start as soon as the MMAs of step
  *                            s have consumed the FIRST half of the operand: they never wait for the epilogue.
- *   warp 8 lane 0 MMA ISSUER after its warp's share of an operand half: K/32 x tcgen05.mma (M128, N, K16, kind::f16) into one
+ *   warp 16 lane 0 MMA ISSUER after its warp's share of an operand half: K/32 x tcgen05.mma (M128, N, K16, kind::f16) into one
  *                            of TWO FP32 accumulators in TMEM (lane = chain), tcgen05.commit -> mbarriers.  The shared
  *                            factor B is brought in once per CTA by TMA (cp.async.bulk.tensor through a tensor map).
  *                            (A 17th warp for this role would cost four warps of registers: they are granted in fours.)
- *   warps 0..7   EPILOGUE    thread (chain m, half h) owns the coordinates [h N/2, (h+1) N/2) of chain m for the whole launch:
- *                            tcgen05.ld -> x' = x + sigma Delta (FP64) -> the energy functor's per-mode sums -> ONE
- *                            64-thread named barrier with the thread of the other half -> both evaluate the (identical)
+ *   warps 0..15  EPILOGUE    thread (chain m, column group g) owns the coordinates [g N/4, (g+1) N/4) of chain m for the whole
+ *                            launch: tcgen05.ld -> x' = x + sigma Delta (FP64) -> the energy functor's per-mode sums -> ONE
+ *                            128-thread named barrier with the other column groups -> all four evaluate the (identical)
  *                            Metropolis decision -> accepted chains write x' (their own words of the shared-memory state
- *                            tile).  Chain scalars (a, E, sigma, count) live in registers of both threads.
+ *                            tile).  Chain scalars (a, E, sigma, count) live in registers of all four threads.
  * The only serial dependency is the state inside the epilogue; generation and contraction run ahead of it.
  *
  * Stream definition (restated by oracle/me_oracle_k4.c): chain g, step s —
@@ -46,10 +46,21 @@ typedef unsigned int u32;
 typedef unsigned long long u64;
 
 constexpr int TILE = 128;               /* chains per tile = MMA M = TMEM lanes */
-constexpr int EPI_WARPS = 8, GEN_WARPS = 8;
-constexpr int GEN_WARP0 = EPI_WARPS, MMA_WARP = GEN_WARP0;     /* lane 0 of the first generator warp also issues the MMAs */
-constexpr int THREADS = 32 * (EPI_WARPS + GEN_WARPS);          /* 16 warps: registers are granted to a CTA in groups of four
-                                                                  warps, so a 17th warp would cost as much as four */
+/* CTA shape: 32 warps = 16 epilogue warps (4 column groups x 4 lane quarters) + 16 generator warps.  Both roles are chains
+ * of dependent instructions (FP64 / XU / shared-memory latencies), so what they need is warps: with 8 + 8 warps the SM sat
+ * at 48 % issue utilisation, a quarter of it spent polling mbarriers (profiles/r02_ncu_c4_k4_steps_v2_16warps.csv).  Registers
+ * are granted per warpgroup: the kernel is launched at 64 per thread and the epilogue warpgroups grow to 80 while the
+ * generator warpgroups shrink to 48 (setmaxnreg).  K4_WIDE=0 builds the 8 + 8 warp variant (128 registers each). */
+#ifndef K4_WIDE
+#define K4_WIDE 1
+#endif
+constexpr int EPI_GROUPS = K4_WIDE ? 4 : 2;                 /* threads per chain in the epilogue (column groups) */
+constexpr int EPI_WARPS = 4 * EPI_GROUPS, GEN_WARPS = K4_WIDE ? 16 : 8;
+constexpr int GEN_PAR = GEN_WARPS * 32 / TILE;              /* generator threads per operand row */
+constexpr int GEN_WARP0 = EPI_WARPS, MMA_WARP = GEN_WARP0;  /* lane 0 of the first generator warp also issues the MMAs: registers
+                                                               are granted in groups of four warps, a 33rd warp would cost four */
+constexpr int THREADS = 32 * (EPI_WARPS + GEN_WARPS);
+constexpr int EPI_REGS = 80, GEN_REGS = 48;                 /* setmaxnreg targets (K4_WIDE) */
 constexpr u32 SCALAR_SLOT = 0x10000u;   /* Philox slot of the per-chain scalar draws (beyond any operand chunk) */
 constexpr int PHILOX_ROUNDS = 7;
 
@@ -159,6 +170,12 @@ __host__ __device__ constexpr u32 umma_idesc(int n) {
 }
 
 template <int CNT> struct TmemLd;
+template <> struct TmemLd<4> {
+    __device__ __forceinline__ static void ld(u32 taddr, u32 *r) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+    }
+};
 template <> struct TmemLd<8> {
     __device__ __forceinline__ static void ld(u32 taddr, u32 *r) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -274,23 +291,28 @@ struct EnergyCylinder {
 template <int NC>
 struct Smem {
     static constexpr int N = 2 * NC;
-    static constexpr int HALVES = (N >= 32) ? 2 : 1;
+    static constexpr int CHUNKS = N / 8;                                   /* 16-byte K chunks per operand row */
+    static constexpr int HALVES = (CHUNKS >= 2 * GEN_PAR) ? 2 : 1;         /* operand pipeline stages */
     double xs[N][TILE];                                     /* complex block, interleaved [n][chain]      N KB   */
     alignas(1024) unsigned char zs[TILE * N * 2];           /* A operand (normals), BF16, HALVES stages            */
     alignas(1024) unsigned char ls[N * N * 2];              /* B operand (factor), BF16                            */
-    double part[2][2][2][TILE];                             /* [step parity][half][sum][chain] partial energy sums */
+    double part[2][EPI_GROUPS][2][TILE];                    /* [step parity][column group][sum][chain] partial sums */
     me::MathTables tables;
     u64 z_full[2], z_empty[2], acc_full[2], acc_empty[2], b_full;
     u32 tmem_slot;
 };
 
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 /* -------------------------------------------------------------------------------------------- the step kernel */
 template <int NC, class Energy>
 __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap *bmap) {
     typedef Smem<NC> S_t;
-    constexpr int N = S_t::N, K = N, HALVES = S_t::HALVES;
-    constexpr int CHUNKS = K / 8;                 /* 16-byte K chunks per operand row */
-    constexpr int CH_HALF = CHUNKS / HALVES;      /* chunks per pipeline stage */
+    constexpr int N = S_t::N, K = N, HALVES = S_t::HALVES, CHUNKS = S_t::CHUNKS;
+    constexpr int CS = CHUNKS / HALVES;           /* chunks per pipeline stage (even) */
     constexpr u32 A_LBO = TILE * 16, B_LBO = N * 16;
     constexpr u32 TCOLS = N < 32 ? 32 : N;        /* TMEM columns per accumulator */
     constexpr u32 IDESC = umma_idesc(N);
@@ -331,6 +353,9 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
 
     if (warp >= GEN_WARP0) {
         /* ================================================================== generators (+ the MMA issuer) */
+#if K4_WIDE
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEN_REGS));
+#endif
         const bool issuer = warp == MMA_WARP && lane == 0;
         if (issuer && p.use_tma) {
             constexpr int ROWS = CHUNKS * N;                 /* rows of 16 bytes */
@@ -340,9 +365,9 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
             mbar_wait(&S.b_full, 0);
         }
         const u32 zs_addr = smem_u32(S.zs), ls_addr = smem_u32(S.ls);
-        const int gt = tid - 32 * GEN_WARP0;          /* 0..255 */
+        const int gt = tid - 32 * GEN_WARP0;
         const int m = gt & (TILE - 1);                /* operand row = chain within the tile */
-        const int c_par = gt >> 7;                    /* this thread's chunk parity */
+        const int c_par = gt >> 7;                    /* this thread takes the chunks c_par, c_par + GEN_PAR, ... of a stage */
         long long it = 0;
         for (long long t = 0; t < n_tiles; t++) {
             const long long base = range_lo + t * TILE;
@@ -357,24 +382,26 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     if (it >= 1) mbar_wait(&S.z_empty[h], (u32)((it - 1) & 1));
                     if (act) {
 #pragma unroll
-                        for (int i = 0; i < CH_HALF / 2; i++) {
-                            const int c = h * CH_HALF + c_par + 2 * i;      /* CH_HALF is even: both parities are used */
-                            float dz[8];
-                            const U4 r = philox(c0, c1, step, (u32)c, p.rk);
-                            normal_pair_f32(r.x, dz[0], dz[1]);
-                            normal_pair_f32(r.y, dz[2], dz[3]);
-                            normal_pair_f32(r.z, dz[4], dz[5]);
-                            normal_pair_f32(r.w, dz[6], dz[7]);
-                            uint4 v;
-                            v.x = pack_bf16(dz[0], dz[1]);
-                            v.y = pack_bf16(dz[2], dz[3]);
-                            v.z = pack_bf16(dz[4], dz[5]);
-                            v.w = pack_bf16(dz[6], dz[7]);
-                            *reinterpret_cast<uint4 *>(S.zs + c * A_LBO + m * 16) = v;
-                            if (s == 0 && p.dbg_z != nullptr) {
+                        for (int cc = 0; cc < CS; cc += GEN_PAR) {
+                            if (cc + c_par < CS) {
+                                const int c = h * CS + cc + c_par;
+                                float dz[8];
+                                const U4 r = philox(c0, c1, step, (u32)c, p.rk);
+                                normal_pair_f32(r.x, dz[0], dz[1]);
+                                normal_pair_f32(r.y, dz[2], dz[3]);
+                                normal_pair_f32(r.z, dz[4], dz[5]);
+                                normal_pair_f32(r.w, dz[6], dz[7]);
+                                uint4 v;
+                                v.x = pack_bf16(dz[0], dz[1]);
+                                v.y = pack_bf16(dz[2], dz[3]);
+                                v.z = pack_bf16(dz[4], dz[5]);
+                                v.w = pack_bf16(dz[6], dz[7]);
+                                *reinterpret_cast<uint4 *>(S.zs + c * A_LBO + m * 16) = v;
+                                if (s == 0 && p.dbg_z != nullptr) {
 #pragma unroll
-                                for (int k = 0; k < 8; k++)
-                                    p.dbg_z[(long long)(8 * c + k) * ld + base + m] = bf16_round(dz[k]);
+                                    for (int k = 0; k < 8; k++)
+                                        p.dbg_z[(long long)(8 * c + k) * ld + base + m] = bf16_round(dz[k]);
+                                }
                             }
                         }
                     }
@@ -382,13 +409,13 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.z_full[h]);
                     if (issuer) {
-                        /* Delta (+)= Z_half . B_half^T: CH_HALF / 2 x (M128, N, K16), accumulator `a` in TMEM */
+                        /* Delta (+)= Z_stage . B_stage^T: CS / 2 x (M128, N, K16), accumulator `a` in TMEM */
                         if (h == 0 && it >= 2) mbar_wait(&S.acc_empty[a], (u32)(((it >> 1) - 1) & 1));
                         mbar_wait(&S.z_full[h], (u32)(it & 1));
                         tc_fence_after();
 #pragma unroll
-                        for (int k = 0; k < CH_HALF / 2; k++) {
-                            const int c = h * CH_HALF + 2 * k;       /* first of the two K chunks of this MMA */
+                        for (int k = 0; k < CS / 2; k++) {
+                            const int c = h * CS + 2 * k;            /* first of the two K chunks of this MMA */
                             umma_bf16(tmem_base + a * TCOLS, umma_desc(zs_addr + c * A_LBO, A_LBO),
                                       umma_desc(ls_addr + c * B_LBO, B_LBO), IDESC, (h > 0 || k > 0) ? 1u : 0u);
                         }
@@ -401,15 +428,19 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
         }
     } else {
         /* ================================================================== epilogue */
-        const int q4 = warp & 3, h = warp >> 2;        /* lane quarter (TMEM lanes 32 q4 ..), coordinate half */
+#if K4_WIDE
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+#endif
+        const int q4 = warp & 3, g = warp >> 2;        /* lane quarter (TMEM lanes 32 q4 ..), column group */
         const int m = 32 * q4 + lane;                  /* chain within the tile = TMEM lane */
-        constexpr int MODES = NC / 2;                  /* modes per thread */
-        constexpr int LDCH = NC < 32 ? NC : 32;        /* columns per tcgen05.ld */
+        constexpr int MODES = NC / EPI_GROUPS;         /* modes per thread */
+        constexpr int COLS = 2 * MODES;                /* accumulator columns per thread */
+        constexpr int LDCH = COLS < 32 ? COLS : 32;    /* columns per tcgen05.ld */
         const double s_a = *p.s_a;
         double f = (double)p.n_meas / (double)p.m;
         if (!(f > 200.0)) f = 200.0;
         const double g_up = p.ratio * (1 - p.target) / f, g_down = p.ratio * p.target / f;
-        const double q_first = (double)(h * MODES - NC / 2);     /* wavenumber of this thread's first mode */
+        const double q_first = (double)(g * MODES - NC / 2);     /* wavenumber of this thread's first mode */
         long long it = 0;
         for (long long t = 0; t < n_tiles; t++) {
             const long long base = range_lo + t * TILE;
@@ -418,21 +449,23 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
             const long long ch = act ? base + m : base;
             const u64 gch = p.chain_offset + (u64)ch;
             const u32 c0 = (u32)gch, c1 = (u32)(gch >> 32);
-            /* this thread's words of the tile's state, and (both halves redundantly) the chain's scalars */
+            /* this thread's words of the tile's state (asynchronous copies: all of them in flight at once), and — every
+               thread of the chain redundantly — the chain's scalars */
             double a = 0, e = 0, sig = 0, nacc = 0;
             int status = 0, accepted_last = 0;
             if (act) {
-#pragma unroll 4
+#pragma unroll
                 for (int jj = 0; jj < MODES; jj++) {
-                    const int j = h * MODES + jj;
-                    S.xs[2 * j][m] = p.state[(long long)(L.X + 1 + j) * ld + ch];
-                    S.xs[2 * j + 1][m] = p.state[(long long)(L.X + 1 + NC + j) * ld + ch];
+                    const int j = g * MODES + jj;
+                    cp_async_8(&S.xs[2 * j][m], p.state + (long long)(L.X + 1 + j) * ld + ch);
+                    cp_async_8(&S.xs[2 * j + 1][m], p.state + (long long)(L.X + 1 + NC + j) * ld + ch);
                 }
                 a = p.state[(long long)L.X * ld + ch];
                 e = p.state[(long long)L.E * ld + ch];
                 sig = p.state[(long long)L.SIG * ld + ch];
                 nacc = p.state[(long long)L.NACC * ld + ch];
                 status = (int)p.state[(long long)L.STATUS * ld + ch];
+                cp_async_wait_all();
             }
             for (long long s = 0; s < n_steps; s++, it++) {
                 const u32 step = (u32)(p.step0 + (u64)s);
@@ -448,41 +481,47 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                 }
                 mbar_wait(&S.acc_full[acc], (u32)((it >> 1) & 1));
                 tc_fence_after();
-                const u32 tcol = tmem_base + acc * TCOLS + ((u32)(32 * q4) << 16) + (u32)(h * NC);
+                const u32 tcol = tmem_base + acc * TCOLS + ((u32)(32 * q4) << 16) + (u32)(g * COLS);
                 bool accept = false;
                 double sg = sig;
                 if (act) {
-                    /* ---- pass 1: proposed coordinates of this half, the functor's two sums.  The increments are read
-                       from TMEM in chunks of LDCH columns (and read again in pass 2) instead of being held in 2 n_c / 2
+                    /* ---- pass 1: proposed coordinates of this column group, the functor's two sums.  The increments are
+                       read from TMEM in chunks of LDCH columns (and read again in pass 2) instead of being held in
                        registers across the decision */
                     double s0 = 0.0, s1 = 0.0, q = q_first;
 #pragma unroll
-                    for (int c = 0; c < NC; c += LDCH) {
+                    for (int c = 0; c < COLS; c += LDCH) {
                         u32 raw[LDCH];
                         TmemLd<LDCH>::ld(tcol + (u32)c, raw);
                         tmem_ld_wait();
                         if (s == 0 && p.dbg_delta != nullptr) {
 #pragma unroll
                             for (int k = 0; k < LDCH; k++)
-                                p.dbg_delta[(long long)(h * NC + c + k) * ld + ch] = __uint_as_float(raw[k]);
+                                p.dbg_delta[(long long)(g * COLS + c + k) * ld + ch] = __uint_as_float(raw[k]);
                         }
 #pragma unroll
                         for (int jj = 0; jj < LDCH / 2; jj++) {
-                            const int j = h * MODES + c / 2 + jj;
+                            const int j = g * MODES + c / 2 + jj;
                             const double re = fma(sig, f32_bits_to_f64(raw[2 * jj]), S.xs[2 * j][m]);
                             const double im = fma(sig, f32_bits_to_f64(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
                             Energy::mode(q, re, im, p.consts, s0, s1);
                             q += 1.0;
                         }
                     }
-                    S.part[it & 1][h][0][m] = s0;
-                    S.part[it & 1][h][1][m] = s1;
+                    S.part[it & 1][g][0][m] = s0;
+                    S.part[it & 1][g][1][m] = s1;
                 }
-                named_barrier(1 + q4, 64);           /* the two halves of this lane quarter exchange their sums */
+                named_barrier(1 + q4, 32 * EPI_GROUPS);      /* the column groups of this lane quarter exchange their sums */
                 if (act) {
-                    /* ---- decision, evaluated identically by both halves (ME:247-258) */
-                    const double t0 = S.part[it & 1][0][0][m] + S.part[it & 1][1][0][m];
-                    const double t1 = S.part[it & 1][0][1][m] + S.part[it & 1][1][1][m];
+                    /* ---- decision, evaluated identically by every thread of the chain (ME:247-258) */
+                    double t0, t1;
+                    if (EPI_GROUPS == 4) {
+                        t0 = (S.part[it & 1][0][0][m] + S.part[it & 1][1][0][m]) + (S.part[it & 1][2][0][m] + S.part[it & 1][3][0][m]);
+                        t1 = (S.part[it & 1][0][1][m] + S.part[it & 1][1][1][m]) + (S.part[it & 1][2][1][m] + S.part[it & 1][3][1][m]);
+                    } else {
+                        t0 = S.part[it & 1][0][0][m] + S.part[it & 1][1][0][m];
+                        t1 = S.part[it & 1][0][1][m] + S.part[it & 1][1][1][m];
+                    }
                     const double a_new = fma(sig * s_a, za, a);
                     const bool wall = p.use_wall && Energy::reject(a_new, p.consts);
                     if (!wall) {
@@ -496,19 +535,19 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     }
                     sg = accept ? fma(sig, g_up, sig) : fma(sig, -g_down, sig);
                     if (!(sg > 0)) status |= ME_STATUS_SIGMA_NONPOS;
-                    if (s == 0 && h == 0 && p.dbg_scal != nullptr) { p.dbg_scal[ch] = za; p.dbg_scal[ld + ch] = u; }
+                    if (s == 0 && g == 0 && p.dbg_scal != nullptr) { p.dbg_scal[ch] = za; p.dbg_scal[ld + ch] = u; }
                     /* ---- pass 2: accepted chains take the proposal (the same fma as pass 1: the accepted state is
                        bit-for-bit the one whose energy was evaluated) */
                     if (__any_sync(0xffffffffu, accept)) {
 #pragma unroll
-                        for (int c = 0; c < NC; c += LDCH) {
+                        for (int c = 0; c < COLS; c += LDCH) {
                             u32 raw[LDCH];
                             TmemLd<LDCH>::ld(tcol + (u32)c, raw);
                             tmem_ld_wait();
                             if (accept) {
 #pragma unroll
                                 for (int jj = 0; jj < LDCH / 2; jj++) {
-                                    const int j = h * MODES + c / 2 + jj;
+                                    const int j = g * MODES + c / 2 + jj;
                                     S.xs[2 * j][m] = fma(sig, f32_bits_to_f64(raw[2 * jj]), S.xs[2 * j][m]);
                                     S.xs[2 * j + 1][m] = fma(sig, f32_bits_to_f64(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
                                 }
@@ -526,13 +565,13 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
             }
             /* store this thread's words of the tile */
             if (act) {
-#pragma unroll 4
+#pragma unroll 8
                 for (int jj = 0; jj < MODES; jj++) {
-                    const int j = h * MODES + jj;
+                    const int j = g * MODES + jj;
                     p.state[(long long)(L.X + 1 + j) * ld + ch] = S.xs[2 * j][m];
                     p.state[(long long)(L.X + 1 + NC + j) * ld + ch] = S.xs[2 * j + 1][m];
                 }
-                if (h == 0) {
+                if (g == 0) {
                     p.state[(long long)L.X * ld + ch] = a;
                     p.state[(long long)L.E * ld + ch] = e;
                     p.state[(long long)L.SIG * ld + ch] = sig;

@@ -17,7 +17,8 @@
  *   increments  Delta_n = sum_k bf16(Z_k) bf16(B_nk), accumulated in double and rounded to float (the tensor core
  *               accumulates in FP32 in an order of its own: compared with a tolerance, then INJECTED — level L-A of
  *               SURVEY §8c applied to this path)
- *   step        x'_n = fma(sigma, (double)Delta_n, x_n); per-half mode sums in mode order; a' = fma(sigma s_a, za, a);
+ *   step        x'_n = fma(sigma, (double)Delta_n, x_n); mode sums per quarter of the modes, in mode order, combined as
+ *               (p0 + p1) + (p2 + p3); a' = fma(sigma s_a, za, a);
  *               wall; E' = total(a', s0, s1); accept = dE <= 0 or (T != 0 and u <= exp(-dE / T)); sigma update by fma
  * MUFU.LG2 / MUFU.SQRT of the generator are hardware approximations: the normals restated here (log2f / sqrtf, fmaf
  * polynomials) agree with the kernel's to a BF16 rounding boundary, which is what the test asserts before injecting the
@@ -201,24 +202,24 @@ void k4o_init(const k4o_config *c, double *st, const double *x0, double sigma0) 
 int k4o_step(const k4o_config *c, double *st, const float *delta, double za, double u, double s_a, int64_t n_meas) {
     k4o_layout L;
     k4o_layout_for(c->nc, &L);
-    const int nc = c->nc, half = nc / 2;
+    const int nc = c->nc, quarter = nc / 4;      /* the kernel's four column groups per chain (k4::EPI_GROUPS) */
     const double sig = st[L.SIG];
     double f = (double)n_meas / (double)(1 + nc);
     if (!(f > 200.0)) f = 200.0;
     const double g_up = c->ratio * (1 - c->target) / f, g_down = c->ratio * c->target / f;
-    double xr[K4O_MAX_NC], xi[K4O_MAX_NC], part0[2], part1[2];
-    for (int h = 0; h < 2; h++) {
-        double s0 = 0.0, s1 = 0.0, q = (double)(h * half - nc / 2);
-        for (int jj = 0; jj < half; jj++) {
-            const int j = h * half + jj;
+    double xr[K4O_MAX_NC], xi[K4O_MAX_NC], part0[4], part1[4];
+    for (int g = 0; g < 4; g++) {
+        double s0 = 0.0, s1 = 0.0, q = (double)(g * quarter - nc / 2);
+        for (int jj = 0; jj < quarter; jj++) {
+            const int j = g * quarter + jj;
             xr[j] = fma(sig, (double)delta[2 * j], st[L.X + 1 + j]);
             xi[j] = fma(sig, (double)delta[2 * j + 1], st[L.X + 1 + nc + j]);
             mode(q, xr[j], xi[j], &s0, &s1);
             q += 1.0;
         }
-        part0[h] = s0; part1[h] = s1;
+        part0[g] = s0; part1[g] = s1;
     }
-    const double t0 = part0[0] + part0[1], t1 = part1[0] + part1[1];
+    const double t0 = (part0[0] + part0[1]) + (part0[2] + part0[3]), t1 = (part1[0] + part1[1]) + (part1[2] + part1[3]);
     const double a_new = fma(sig * s_a, za, st[L.X]);
     int accept = 0;
     const int wall = c->use_wall && fabs(a_new) >= 1.0;

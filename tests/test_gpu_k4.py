@@ -245,7 +245,10 @@ def test_oracle_runs_beside_the_kernel_with_identical_decisions(nc, async_refres
     dz = torch.zeros((N, n), dtype=torch.float32, device="cuda")
     dd = torch.zeros((N, n), dtype=torch.float32, device="cuda")
     ds = torch.zeros((2, n), dtype=torch.float64, device="cuda")
-    assert np.array_equal(eng.state.cpu().numpy().T[:, :lay.NACC], orc.state[:, :lay.NACC])       # same initial state
+    st0 = eng.state.cpu().numpy().T
+    assert np.array_equal(st0[:, lay.X:lay.E], orc.state[:, lay.X:lay.E])                         # same initial parameters
+    assert np.allclose(st0[:, :lay.NACC], orc.state[:, :lay.NACC], rtol=1e-14, atol=1e-16)        # (hypot, one-pass energy)
+    orc.state[:, lay.E] = st0[:, lay.E]
     flips = total = 0
     nacc = np.zeros(n)
     for im in range(M):
