@@ -293,6 +293,9 @@ int me_k4_refactor(me_k4 *eng, const double *mom, const double *inc, int64_t n_m
  * number of SMs the step kernel leaves idle so that the one-CTA refresh can run beside it on another stream. */
 int me_k4_set_factor(me_k4 *eng, const void *factor_bf16);
 int me_k4_set_reserved_sms(me_k4 *eng, int32_t n);
+/* The generator's quantile table (host copy): out[4096] BF16 bit patterns of Phi^-1(1/2 + (i + 1/2) / 8192); n must be 4096.
+ * The kernel draws its BF16 normals by inverse CDF from it (12 index bits + 1 sign bit of a Philox half-word each). */
+int me_k4_normal_table(uint16_t *out, int32_t n);
 int me_k4_get_counters(me_k4 *eng, int64_t *n_measure, uint64_t *step);
 const char *me_k4_last_error(me_k4 *eng);
 

@@ -92,6 +92,7 @@ SIGNATURES = {
     "me_k4_refactor": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "me_k4_set_factor": (ctypes.c_int, [_vp, _vp]),
     "me_k4_set_reserved_sms": (ctypes.c_int, [_vp, _i32]),
+    "me_k4_normal_table": (ctypes.c_int, [_vp, _i32]),
     "me_k4_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
     "me_k4_last_error": (_cp, [_vp]),
     "me_probe_fp64": (ctypes.c_int, [_i32, _i64, _vp, _i64, _vp, ctypes.POINTER(_i64)]),

@@ -14,6 +14,7 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -345,6 +346,50 @@ __global__ void __launch_bounds__(256) k4_refactor(const double2 *mom, const dou
     if (tid == 0 && status) *status = bad;
 }
 
+/* The generator's table (me_k4_device.cuh): BF16 bits of Phi^-1(1/2 + (i + 1/2) / 8192), i < 4096, by bisection on erfc
+ * (monotone, no series to trust), rounded to nearest even.  Host copy + one device copy per device for the process. */
+const unsigned short *k4_host_ztab() {
+    static unsigned short tab[k4::ZTAB_ENTRIES];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (int i = 0; i < k4::ZTAB_ENTRIES; i++) {
+            const double pr = 0.5 + ((double)i + 0.5) / (2.0 * k4::ZTAB_ENTRIES);
+            double lo = 0.0, hi = 8.0;
+            for (int it = 0; it < 200; it++) {
+                const double mid = 0.5 * (lo + hi);
+                if (mid == lo || mid == hi) break;
+                if (0.5 * erfc(-mid * 0.70710678118654752440) < pr) lo = mid; else hi = mid;
+            }
+            const float f = (float)(0.5 * (lo + hi));
+            unsigned int b;
+            memcpy(&b, &f, 4);
+            b += 0x7fffu + ((b >> 16) & 1u);
+            tab[i] = (unsigned short)(b >> 16);
+        }
+    });
+    return tab;
+}
+const unsigned short *k4_device_ztab(int device) {
+    static std::mutex mu;
+    static std::map<int, unsigned short *> tabs;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = tabs.find(device);
+    if (it != tabs.end()) return it->second;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    unsigned short *dev = nullptr;
+    const size_t bytes = sizeof(unsigned short) * k4::ZTAB_ENTRIES;
+    if (cudaMalloc((void **)&dev, bytes) != cudaSuccess ||
+        cudaMemcpy(dev, k4_host_ztab(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        dev = nullptr;
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    if (dev) tabs[device] = dev;
+    return dev;
+}
+
 /* ahead-of-time step kernels for the built-in functor */
 struct AotEntry { int nc; const void *steps; int smem; };
 template <int NC> AotEntry aot_entry() {
@@ -361,6 +406,7 @@ struct me_k4 {
     int use_reject = 0;
     double *state = nullptr;
     const void *factor = nullptr;
+    const unsigned short *ztab = nullptr;   /* generator table on cfg.device (owned by the library) */
     unsigned char *last_accept = nullptr;
     long long n_measure = 1;
     unsigned long long step = 0;
@@ -402,6 +448,7 @@ static void k4_base(me_k4 *e, StepParams &p) {
     memcpy(p.consts, e->consts, sizeof(p.consts));
     p.use_wall = e->use_reject;
     p.factor = e->factor;
+    p.ztab = e->ztab;
     p.last_accept = e->last_accept;
 }
 
@@ -538,6 +585,10 @@ int me_k4_check_energy_source(const char *src, int32_t nc, int32_t use_reject, c
 int me_k4_bind(me_k4 *e, double *state, const void *factor_bf16, unsigned char *last_accept) {
     if (!e || !state || !factor_bf16) return ME_ERR_INVALID;
     e->state = state; e->factor = factor_bf16; e->last_accept = last_accept;
+    if (!e->ztab) {
+        e->ztab = k4_device_ztab(e->cfg.device);
+        if (!e->ztab) return k4_fail(e, ME_ERR_CUDA, "allocating the generator table failed");
+    }
     return ME_OK;
 }
 
@@ -677,6 +728,13 @@ int me_k4_refactor(me_k4 *e, const double *mom, const double *inc, int64_t n_mea
     }
     cudaSetDevice(prev);
     if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_refactor: ") + cudaGetErrorString(ce));
+    return ME_OK;
+}
+
+/* the generator's table (host copy): 4096 BF16 bit patterns, Phi^-1(1/2 + (i + 1/2) / 8192) */
+int me_k4_normal_table(uint16_t *out, int32_t n) {
+    if (!out || n != k4::ZTAB_ENTRIES) return ME_ERR_INVALID;
+    memcpy(out, k4_host_ztab(), sizeof(uint16_t) * k4::ZTAB_ENTRIES);
     return ME_OK;
 }
 

@@ -7,7 +7,7 @@
  * B the real embedding of conj(G)/sqrt2 in interleaved (Re, Im) coordinates, C_c = G G^H.
  *
  * Roles inside a CTA of 32 warps (no CTA-wide barrier in the step loop):
- *   warps 16..31 GENERATORS  Philox4x32-7 -> FP32 Box-Muller -> BF16, written straight into the UMMA canonical K-major
+ *   warps 16..31 GENERATORS  Philox4x32-7 -> BF16 normals by table (inverse CDF), written straight into the UMMA canonical K-major
  *                            operand layout.  The K dimension is produced in two halves, each its own pipeline stage
  *                            (mbarriers z_full / z_empty), so the generators of step s+1 start as soon as the MMAs of step
  *                            s have consumed the FIRST half of the operand: they never wait for the epilogue.
@@ -23,10 +23,14 @@
  * The only serial dependency is the state inside the epilogue; generation and contraction run ahead of it.
  *
  * Stream definition (restated by oracle/me_oracle_k4.c): chain g, step s —
- *   normals 8c .. 8c+7 of the chain's row of Z: Philox4x32-7(counter (g_lo, g_hi, s, c), key seed) -> words x, y, z, w -> one
- *   pair each through normal_pair_f32 (32 random bits per pair), rounded to BF16;
- *   scalar draws: Philox call with slot 0x10000: word x -> pair -> first normal = the real parameter's, words z, w -> the
- *   accept uniform (53 bits).
+ *   normals 8c .. 8c+7 of the chain's row of Z: Philox4x32-7(counter (g_lo, g_hi, s, c), key seed) -> words x, y, z, w; each
+ *   word gives two normals, from its low and its high half: 12 bits index a table of the 4096 quantiles
+ *   Phi^-1(1/2 + (i + 1/2) / 8192) of the half-normal law (rounded to BF16 — the operand's own format, which resolves only
+ *   ~900 magnitudes anyway), bit 15 of the half is the sign.  Inverse-CDF sampling straight in the operand's precision: 8
+ *   instructions per pair instead of the ~30 of an FP32 Box-Muller (the generator was more than half of the kernel's
+ *   instructions), exactly symmetric, |z| <= 3.84.
+ *   scalar draws: Philox call with slot 0x10000: low half of word x -> the real parameter's normal (same table), words z, w ->
+ *   the accept uniform (53 bits).
  * Energy plugin: the functor supplies per-mode contributions to two sums and the total, i.e. energies of the form
  *   E = total(a, sum_j f0_j(c_j), sum_j f1_j(c_j)) — the Fourier-mode field energies this path is for:
  *     static void   mode(double q, double re, double im, const double *k, double &s0, double &s1);   q = j - n_c/2
@@ -82,6 +86,7 @@ struct StepParams {
     int use_wall;
     int use_tma;                   /* 1: B arrives through the tensor map; 0: plain loads from `factor` */
     const void *factor;            /* B operand, BF16, UMMA canonical K-major layout [K/8 chunks][N rows][8] */
+    const unsigned short *ztab;    /* [4096] BF16 quantiles of the half-normal law (device memory owned by the library) */
     const double *s_a;             /* device scalar: shared proposal std of the real parameter */
     unsigned char *last_accept;
     float *dbg_z;                  /* optional [K][ld]: the normals of the FIRST step of the launch (tests / oracle taps) */
@@ -221,49 +226,20 @@ __device__ __forceinline__ U4 philox(u32 c0, u32 c1, u32 c2, u32 c3, const u32 *
     U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
     return o;
 }
-/* two normals from 32 random bits: radius uniform from the high 16 bits, angle from the low 16 (2 quadrant bits + 14-bit
- * fraction).  The operand these normals feed is BF16 (8 significant bits), so a 2^-16 grid for the radius uniform and a
- * 1e-4 rad grid for the angle are already below its rounding; the radius is capped at sqrt(2 ln 2^16) = 4.7.
- * Built for the SM's scarcest pipe: no integer->float conversions (the uniforms are assembled as float mantissas),
- * sin/cos as FP32 polynomials after an integer quadrant reduction, so the only XU operations are one MUFU.LG2 and one
- * MUFU.SQRT per PAIR.  The two signs and the sin/cos swap come from independent bits, so the pair's law is exactly
- * symmetric whatever the accuracy of the approximations: the proposal stays symmetric and detailed balance exact. */
-__device__ __forceinline__ void normal_pair_f32(u32 bits, float &z0, float &z1) {
-    const float u = 2.0f - __uint_as_float(0x3f800000u | ((bits >> 16) << 7));     /* (0, 1], multiples of 2^-16 */
-    float lg;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));                         /* u >= 2^-16: no denormal path */
-    const float w = -1.3862943611f * lg;                                            /* -2 ln u >= 0 */
-    float rad;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(w));
-    const u32 zz = (bits << 16) + 0x20000000u;                                      /* quadrant = zz >> 30 (rounded) */
-    const float v = __uint_as_float(0x3f800000u | ((zz >> 7) & 0x007fffffu)) - 1.5f;   /* [-1/2, 1/2): angle (pi/2) v */
-    const float q = v * v;
-    float ps = fmaf(q, -0.0046817541f, 0.0796926263f);                              /* sin((pi/2) v) / v */
-    ps = fmaf(q, ps, -0.6459640975f);
-    ps = fmaf(q, ps, 1.5707963268f);
-    const float sr = v * ps;
-    float pc = fmaf(q, 0.0009192603f, -0.0208634807f);                              /* cos((pi/2) v) */
-    pc = fmaf(q, pc, 0.2536695079f);
-    pc = fmaf(q, pc, -1.2337005501f);
-    const float cr = fmaf(q, pc, 1.0f);
-    /* quadrant 0: (cos, sin) = (cr, sr); 1: (-sr, cr); 2: (-cr, -sr); 3: (sr, -cr) */
-    const bool odd = (zz & 0x40000000u) != 0;
-    const float cs = odd ? sr : cr, sn = odd ? cr : sr;
-    z0 = rad * __uint_as_float(__float_as_uint(cs) ^ ((zz + 0x40000000u) & 0x80000000u));
-    z1 = rad * __uint_as_float(__float_as_uint(sn) ^ (zz & 0x80000000u));
+constexpr int ZTAB_ENTRIES = 4096;
+/* two BF16 normals (packed: low half = first) from one 32-bit random word and the quantile table in shared memory */
+__device__ __forceinline__ u32 normal_pair_bf16(u32 w, const unsigned short *ztab) {
+    const u32 t0 = *reinterpret_cast<const unsigned short *>(reinterpret_cast<const char *>(ztab) + ((w << 1) & 0x1ffeu));
+    const u32 t1 = *reinterpret_cast<const unsigned short *>(reinterpret_cast<const char *>(ztab) + ((w >> 15) & 0x1ffeu));
+    return (t0 | (t1 << 16)) | (w & 0x80008000u);
 }
+__device__ __forceinline__ float bf16_lo_to_float(u32 packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi_to_float(u32 packed) { return __uint_as_float(packed & 0xffff0000u); }
 __device__ __forceinline__ double u53(u32 hi, u32 lo) {
     const double a = __hiloint2double(0x43300000 - (27 << 20), (int)(hi >> 5)) - 33554432.0;
     const double b = __hiloint2double(0x43300000 - (53 << 20), (int)(lo >> 6)) - 0.5;
     return a + b;
 }
-__device__ __forceinline__ u32 pack_bf16(float lo, float hi) {
-    u32 r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-__device__ __forceinline__ float bf16_round(float v) { return __uint_as_float(pack_bf16(v, 0.0f) << 16); }
-
 /* FP32 accumulator word -> double (F2F.F64.F32, exact) */
 __device__ __forceinline__ double f32_bits_to_f64(u32 f) { return (double)__uint_as_float(f); }
 
@@ -297,10 +273,13 @@ struct Smem {
     alignas(1024) unsigned char zs[TILE * N * 2];           /* A operand (normals), BF16, HALVES stages            */
     alignas(1024) unsigned char ls[N * N * 2];              /* B operand (factor), BF16                            */
     double part[2][EPI_GROUPS][2][TILE];                    /* [step parity][column group][sum][chain] partial sums */
+    alignas(16) unsigned short ztab[ZTAB_ENTRIES];          /* BF16 quantile table of the generator               8 KB   */
     me::MathTables tables;
     u64 z_full[2], z_empty[2], acc_full[2], acc_empty[2], b_full;
     u32 tmem_slot;
 };
+
+static_assert(sizeof(Smem<64>) + 1024 <= 227 * 1024, "the 1 real + 64 complex tile must fit the 227 KB of one SM");
 
 __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -334,6 +313,11 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) tmem_alloc(&S.tmem_slot, 2 * TCOLS);
+    {                                             /* the generator's quantile table */
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.ztab);
+        uint4 *dst = reinterpret_cast<uint4 *>(S.ztab);
+        for (int i = tid; i < ZTAB_ENTRIES * 2 / 16; i += THREADS) dst[i] = src[i];
+    }
     if (!p.use_tma) {                             /* plain staging of the factor (tensor map not available) */
         const uint4 *src = reinterpret_cast<const uint4 *>(p.factor);
         uint4 *dst = reinterpret_cast<uint4 *>(S.ls);
@@ -385,22 +369,20 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                         for (int cc = 0; cc < CS; cc += GEN_PAR) {
                             if (cc + c_par < CS) {
                                 const int c = h * CS + cc + c_par;
-                                float dz[8];
                                 const U4 r = philox(c0, c1, step, (u32)c, p.rk);
-                                normal_pair_f32(r.x, dz[0], dz[1]);
-                                normal_pair_f32(r.y, dz[2], dz[3]);
-                                normal_pair_f32(r.z, dz[4], dz[5]);
-                                normal_pair_f32(r.w, dz[6], dz[7]);
                                 uint4 v;
-                                v.x = pack_bf16(dz[0], dz[1]);
-                                v.y = pack_bf16(dz[2], dz[3]);
-                                v.z = pack_bf16(dz[4], dz[5]);
-                                v.w = pack_bf16(dz[6], dz[7]);
+                                v.x = normal_pair_bf16(r.x, S.ztab);
+                                v.y = normal_pair_bf16(r.y, S.ztab);
+                                v.z = normal_pair_bf16(r.z, S.ztab);
+                                v.w = normal_pair_bf16(r.w, S.ztab);
                                 *reinterpret_cast<uint4 *>(S.zs + c * A_LBO + m * 16) = v;
                                 if (s == 0 && p.dbg_z != nullptr) {
+                                    const u32 w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                                    for (int k = 0; k < 8; k++)
-                                        p.dbg_z[(long long)(8 * c + k) * ld + base + m] = bf16_round(dz[k]);
+                                    for (int k = 0; k < 4; k++) {
+                                        p.dbg_z[(long long)(8 * c + 2 * k) * ld + base + m] = bf16_lo_to_float(w4[k]);
+                                        p.dbg_z[(long long)(8 * c + 2 * k + 1) * ld + base + m] = bf16_hi_to_float(w4[k]);
+                                    }
                                 }
                             }
                         }
@@ -474,9 +456,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                 double za = 0.0, u = 0.0;
                 if (act) {
                     const U4 r = philox(c0, c1, step, SCALAR_SLOT, p.rk);
-                    float f0, f1;
-                    normal_pair_f32(r.x, f0, f1);
-                    za = (double)f0;
+                    za = (double)bf16_lo_to_float(normal_pair_bf16(r.x, S.ztab));
                     u = u53(r.z, r.w);
                 }
                 mbar_wait(&S.acc_full[acc], (u32)((it >> 1) & 1));

@@ -11,18 +11,16 @@
  *
  * What is restated, in the kernel's own operation order (explicit fma where the kernel uses fma, so an FP64 chain is
  * reproduced bit for bit once the tensor-core increments are given):
- *   stream      chain g, step s: normals 8c..8c+7 of the operand row from Philox4x32-7(counter (g_lo, g_hi, s, c)), one
- *               pair per output word through normal_pair (32 bits per pair), rounded to BF16; scalar draws from slot
- *               0x10000: word x -> pair -> first normal = the real parameter's, words z, w -> accept uniform (53 bits)
+ *   stream      chain g, step s: normals 8c..8c+7 of the operand row from Philox4x32-7(counter (g_lo, g_hi, s, c)), two per
+ *               output word by inverse CDF from a 4096-entry BF16 quantile table (12 index bits + sign per half-word);
+ *               scalar draws from slot 0x10000: low half of word x -> the real parameter's normal, words z, w -> accept
+ *               uniform (53 bits).  Integer arithmetic and table look-ups only: the operand is reproduced EXACTLY
  *   increments  Delta_n = sum_k bf16(Z_k) bf16(B_nk), accumulated in double and rounded to float (the tensor core
  *               accumulates in FP32 in an order of its own: compared with a tolerance, then INJECTED — level L-A of
  *               SURVEY §8c applied to this path)
  *   step        x'_n = fma(sigma, (double)Delta_n, x_n); mode sums per quarter of the modes, in mode order, combined as
  *               (p0 + p1) + (p2 + p3); a' = fma(sigma s_a, za, a);
  *               wall; E' = total(a', s0, s1); accept = dE <= 0 or (T != 0 and u <= exp(-dE / T)); sigma update by fma
- * MUFU.LG2 / MUFU.SQRT of the generator are hardware approximations: the normals restated here (log2f / sqrtf, fmaf
- * polynomials) agree with the kernel's to a BF16 rounding boundary, which is what the test asserts before injecting the
- * kernel's own operand.
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared
  */
@@ -82,52 +80,34 @@ float k4o_bf16_from_double(double v) {
     return k4o_bf16(f);
 }
 
-/* the kernel's normal_pair_f32 with exact log2 / sqrt in place of the MUFU approximations */
-static void normal_pair(uint32_t bits, float *z0, float *z1) {
-    const float u = 2.0f - as_float(0x3f800000u | ((bits >> 16) << 7));
-    const float lg = log2f(u);
-    const float w = -1.3862943611f * lg;
-    const float rad = sqrtf(w);
-    const uint32_t zz = (bits << 16) + 0x20000000u;
-    const float v = as_float(0x3f800000u | ((zz >> 7) & 0x007fffffu)) - 1.5f;
-    const float q = v * v;
-    float ps = fmaf(q, -0.0046817541f, 0.0796926263f);
-    ps = fmaf(q, ps, -0.6459640975f);
-    ps = fmaf(q, ps, 1.5707963268f);
-    const float sr = v * ps;
-    float pc = fmaf(q, 0.0009192603f, -0.0208634807f);
-    pc = fmaf(q, pc, 0.2536695079f);
-    pc = fmaf(q, pc, -1.2337005501f);
-    const float cr = fmaf(q, pc, 1.0f);
-    const int odd = (zz & 0x40000000u) != 0;
-    const float cs = odd ? sr : cr, sn = odd ? cr : sr;
-    *z0 = rad * as_float(as_u32(cs) ^ ((zz + 0x40000000u) & 0x80000000u));
-    *z1 = rad * as_float(as_u32(sn) ^ (zz & 0x80000000u));
+/* Two BF16 normals from one 32-bit random word (k4::normal_pair_bf16): the low and the high half each give one normal —
+ * 12 bits index the table of the 4096 half-normal quantiles Phi^-1(1/2 + (i + 1/2) / 8192) (BF16 bit patterns), bit 15 of
+ * the half is the sign.  The table is an INPUT here: the test builds it independently (scipy's inverse normal CDF) and
+ * checks it against the library's before use. */
+static void normal_pair(uint32_t w, const uint16_t *tab, float *z0, float *z1) {
+    const uint32_t t0 = tab[w & 0xfffu], t1 = tab[(w >> 16) & 0xfffu];
+    *z0 = as_float((t0 | (w & 0x8000u)) << 16);
+    *z1 = as_float(((t1 << 16) | (w & 0x80000000u)));
 }
 
-/* normals of one chain and step: z[K] (K = 2 n_c), unrounded floats; zb[K] the BF16 values the operand holds */
-void k4o_normals(uint64_t seed, uint64_t chain, uint32_t step, int K, float *z, float *zb) {
+/* normals of one chain and step: zb[K] (K = 2 n_c), the BF16 values the operand holds */
+void k4o_normals(uint64_t seed, uint64_t chain, uint32_t step, int K, const uint16_t *tab, float *zb) {
     for (int c = 0; c < K / 8; c++) {
         uint32_t r[4];
         philox7((uint32_t)chain, (uint32_t)(chain >> 32), step, (uint32_t)c, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-        for (int w = 0; w < 4; w++) {
-            float a, b;
-            normal_pair(r[w], &a, &b);
-            z[8 * c + 2 * w] = a; z[8 * c + 2 * w + 1] = b;
-            zb[8 * c + 2 * w] = k4o_bf16(a); zb[8 * c + 2 * w + 1] = k4o_bf16(b);
-        }
+        for (int w = 0; w < 4; w++) normal_pair(r[w], tab, &zb[8 * c + 2 * w], &zb[8 * c + 2 * w + 1]);
     }
 }
 
-/* scalar draws of one chain and step: the real parameter's normal (FP32 value as double) and the accept uniform */
-void k4o_scalars(uint64_t seed, uint64_t chain, uint32_t step, double *za, double *u) {
+/* scalar draws of one chain and step: the real parameter's normal (table, low half of word x) and the accept uniform */
+void k4o_scalars(uint64_t seed, uint64_t chain, uint32_t step, const uint16_t *tab, double *za, double *u) {
     uint32_t r[4];
     philox7((uint32_t)chain, (uint32_t)(chain >> 32), step, 0x10000u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
     float a, b;
-    normal_pair(r[0], &a, &b);
+    normal_pair(r[0], tab, &a, &b);
     *za = (double)a;
-    /* u53: (hi >> 5) 2^-27 + ((lo >> 6) + 1/2) 2^-53 */
-    *u = (double)(r[2] >> 5) * (1.0 / 134217728.0) + ((double)(r[3] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+    /* u53: (hi >> 5) 2^-27 + (lo >> 6) 2^-53, a 53-bit uniform in [0, 1) (both terms and their sum are exact) */
+    *u = (double)(r[2] >> 5) * (1.0 / 134217728.0) + (double)(r[3] >> 6) * (1.0 / 9007199254740992.0);
 }
 
 /* Delta[n] = sum_k B[n][k] z[k] for n < N (B row-major [N][K], BF16 values as floats), double accumulation -> float;

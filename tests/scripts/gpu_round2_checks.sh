@@ -10,7 +10,7 @@ timeout 300 python tests/scripts/k4_probe.py > gpurun_out/${T}_k4_probe_v2.txt 2
 ME_K4_NO_TMA=1 timeout 300 python tests/scripts/k4_probe.py > gpurun_out/${T}_k4_probe_v2_notma.txt 2>&1
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${T}_bench.log 2> gpurun_out/${T}_bench.err; echo "bench rc=$?" >> gpurun_out/${T}_bench.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k4_steps -s 10 -c 1 -o gpurun_out/${T}_ncu_k4 python tests/scripts/k4_probe.py > gpurun_out/${T}_ncu_k4.log 2>&1
-timeout 600 python tests/scripts/nreg_probe.py > gpurun_out/${T}_nreg_probe.txt 2>&1
+# (register-cap variants: profiles/r02_nreg_probe_small_shapes.txt)
 ME_B200_LIB=$PWD/metropolisengine_b200/lib/variants/k4narrow_libme_b200.so timeout 300 python tests/scripts/k4_probe.py > gpurun_out/${T}_k4_probe_16warps.txt 2>&1
 timeout 300 python tests/scripts/scale_probe.py > gpurun_out/${T}_scale_probe.txt 2>&1
 tail -3 gpurun_out/${T}_k4tests.log; tail -3 gpurun_out/${T}_gputests.log; tail -2 gpurun_out/${T}_smoke.log; head -3 gpurun_out/${T}_k4_probe_v2.txt; tail -1 gpurun_out/${T}_bench.err

@@ -63,7 +63,7 @@ def test_in_kernel_normals_are_standard_and_symmetric():
     z = dz.double().cpu().numpy()
     flat = z.reshape(-1)
     assert abs(flat.mean()) < 5 / np.sqrt(flat.size)
-    assert abs(flat.var() - 1.0) < 5 * np.sqrt(2.0 / flat.size) + 2e-5
+    assert abs(flat.var() - 0.99984) < 5 * np.sqrt(2.0 / flat.size) + 2e-5        # variance of the 4096-quantile BF16 table
     assert stats.kstest(flat[::7], "norm").pvalue > 1e-4          # BF16 rounding is far below the KS resolution here
     cm = np.corrcoef(z[:16])                                        # different coordinates are uncorrelated
     assert np.max(np.abs(cm - np.eye(16))) < 6 / np.sqrt(n)
@@ -222,9 +222,9 @@ def test_asynchronous_factor_refresh_is_deterministic_and_lags_by_one_measure():
 @pytest.mark.parametrize("nc,async_refresh", [(64, True), (16, True), (32, False)])
 def test_oracle_runs_beside_the_kernel_with_identical_decisions(nc, async_refresh):
     """Level L-A of SURVEY §8c applied to the shared-covariance path.  A 256-chain ensemble is stepped one step per launch
-    with the taps on; the C oracle holds the same ensemble.  Per step: (1) the oracle's own Philox / Box-Muller / BF16
-    operand equals the kernel's except where MUFU.LG2 / MUFU.SQRT put a normal across a BF16 rounding boundary (<= 1 BF16
-    ulp there, and in < 0.5 % of the entries); (2) the oracle's B.z in float64 equals the tensor-core increments within the
+    with the taps on; the C oracle holds the same ensemble.  Per step: (1) the oracle's own Philox / inverse-CDF BF16
+    operand, real-parameter normal and accept uniform equal the kernel's EXACTLY (its quantile table is built independently
+    with scipy); (2) the oracle's B.z in float64 equals the tensor-core increments within the
     FP32 accumulation tolerance 2e-5 |B||z|; (3) with the kernel's increments injected, every accept decision is identical
     and the FP64 state (parameters, energy, width, count) is BIT-identical over 56 measures x 4 steps — across the
     covariance switch-on at the 50th measure and the one-measure lag of the asynchronous factor refresh; (4) the pooled
@@ -249,7 +249,6 @@ def test_oracle_runs_beside_the_kernel_with_identical_decisions(nc, async_refres
     assert np.array_equal(st0[:, lay.X:lay.E], orc.state[:, lay.X:lay.E])                         # same initial parameters
     assert np.allclose(st0[:, :lay.NACC], orc.state[:, :lay.NACC], rtol=1e-14, atol=1e-16)        # (hypot, one-pass energy)
     orc.state[:, lay.E] = st0[:, lay.E]
-    flips = total = 0
     nacc = np.zeros(n)
     for im in range(M):
         for k in range(K):
@@ -258,13 +257,10 @@ def test_oracle_runs_beside_the_kernel_with_identical_decisions(nc, async_refres
             torch.cuda.synchronize()
             zg, dg, sg = dz.cpu().numpy().T, dd.cpu().numpy().T, ds.cpu().numpy()
             orc.begin_step_launch()
-            # (1) generator stream
-            _z, zb = orc.normals(step)
-            neq = zb != zg
-            flips += int(neq.sum()); total += zb.size
-            assert np.all(np.abs(zb - zg)[neq] <= 2.0 ** -7 * np.abs(zg[neq]) + 1e-30), step
+            # (1) generator stream: integer arithmetic and table look-ups only — the operand is reproduced exactly
+            assert np.array_equal(orc.normals(step), zg), step
             za_o, u_o = orc.scalars(step)
-            assert np.array_equal(u_o, sg[1]) and np.allclose(za_o, sg[0], rtol=3e-6, atol=1e-7), step
+            assert np.array_equal(u_o, sg[1]) and np.array_equal(za_o, sg[0]), step
             # the factor in use is the oracle's own (after the switch-on it came through the engine's refresh kernel)
             Bg = eng._factor.float().permute(1, 0, 2).reshape(N, N).cpu().numpy()
             assert np.mean(Bg != orc.B_now) < 2e-3 and np.allclose(Bg, orc.B_now, rtol=2.0 ** -7, atol=1e-12), step
@@ -288,7 +284,6 @@ def test_oracle_runs_beside_the_kernel_with_identical_decisions(nc, async_refres
         if orc.n_measure > 50:
             assert np.allclose(eng.covariance_matrix_complex, orc.cov_c, rtol=1e-9, atol=1e-14), im
             assert np.isclose(float(eng.covariance_matrix_real[0, 0]), orc.cov_a, rtol=1e-9), im
-    assert flips / total < 5e-3, flips / total
     assert 0.05 < nacc.sum() / (n * M * K) < 0.95
     assert eng.measure_step_counter == orc.n_measure == M + 1
 
