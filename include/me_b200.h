@@ -257,6 +257,8 @@ typedef struct me_k4_config {
 typedef struct me_k4_layout {
     int32_t X, E, SIG, MEAN, OBSM, NACC, STATUS, WORDS, D, TS_COLS, N_COMPLEX, TILE, FACTOR_BYTES, MOM_WORDS;
     int32_t MOM_SCRATCH_PER_SM;   /* doubles of me_k4_moments scratch per SM */
+    int32_t SUM_GROUPS;           /* the functor's per-mode sums are accumulated over this many groups of consecutive modes
+                                     (2: a + b; 4: (a + b) + (c + d)) — part of the arithmetic the oracle restates */
 } me_k4_layout;
 int me_k4_layout_get(me_k4_layout *out);                       /* n_complex = 64 */
 int me_k4_layout_for(int32_t n_complex, me_k4_layout *out);

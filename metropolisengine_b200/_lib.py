@@ -46,7 +46,7 @@ class MeK4Config(ctypes.Structure):
 
 class MeK4Layout(ctypes.Structure):
     _fields_ = [(k, _i32) for k in ("X", "E", "SIG", "MEAN", "OBSM", "NACC", "STATUS", "WORDS", "D", "TS_COLS",
-                                    "N_COMPLEX", "TILE", "FACTOR_BYTES", "MOM_WORDS", "MOM_SCRATCH_PER_SM")]
+                                    "N_COMPLEX", "TILE", "FACTOR_BYTES", "MOM_WORDS", "MOM_SCRATCH_PER_SM", "SUM_GROUPS")]
 
 
 # every symbol include/me_b200.h declares: name -> (restype, argtypes)

@@ -476,6 +476,7 @@ int me_k4_layout_for(int32_t nc, me_k4_layout *o) {
     o->STATUS = L.STATUS; o->WORDS = L.WORDS; o->D = L.D; o->TS_COLS = L.D + 2; o->N_COMPLEX = nc;
     o->TILE = k4::TILE; o->FACTOR_BYTES = 4 * nc * nc * 2; o->MOM_WORDS = momw(nc);
     o->MOM_SCRATCH_PER_SM = partw(nc);
+    o->SUM_GROUPS = k4::EPI_GROUPS;
     return ME_OK;
 }
 int me_k4_layout_get(me_k4_layout *o) { return me_k4_layout_for(64, o); }

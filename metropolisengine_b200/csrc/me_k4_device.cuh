@@ -6,20 +6,20 @@
  *        Delta[128 chains x N] = Z[128 x K normals] . B^T[K x N],     N = K = 2 n_c,
  * B the real embedding of conj(G)/sqrt2 in interleaved (Re, Im) coordinates, C_c = G G^H.
  *
- * Roles inside a CTA of 32 warps (no CTA-wide barrier in the step loop):
- *   warps 16..31 GENERATORS  Philox4x32-7 -> BF16 normals by table (inverse CDF), written straight into the UMMA canonical K-major
+ * Roles inside a CTA of 16 warps (no CTA-wide barrier in the step loop; K4_WIDE=1 doubles both roles):
+ *   warps 8..15  GENERATORS  Philox4x32-7 -> BF16 normals by table (inverse CDF), written straight into the UMMA canonical K-major
  *                            operand layout.  The K dimension is produced in two halves, each its own pipeline stage
  *                            (mbarriers z_full / z_empty), so the generators of step s+1 start as soon as the MMAs of step
  *                            s have consumed the FIRST half of the operand: they never wait for the epilogue.
- *   warp 16 lane 0 MMA ISSUER after its warp's share of an operand half: K/32 x tcgen05.mma (M128, N, K16, kind::f16) into one
+ *   warp 8 lane 0 MMA ISSUER after its warp's share of an operand half: K/32 x tcgen05.mma (M128, N, K16, kind::f16) into one
  *                            of TWO FP32 accumulators in TMEM (lane = chain), tcgen05.commit -> mbarriers.  The shared
  *                            factor B is brought in once per CTA by TMA (cp.async.bulk.tensor through a tensor map).
  *                            (A 17th warp for this role would cost four warps of registers: they are granted in fours.)
- *   warps 0..15  EPILOGUE    thread (chain m, column group g) owns the coordinates [g N/4, (g+1) N/4) of chain m for the whole
+ *   warps 0..7   EPILOGUE    thread (chain m, column group g) owns the coordinates [g N/2, (g+1) N/2) of chain m for the whole
  *                            launch: tcgen05.ld -> x' = x + sigma Delta (FP64) -> the energy functor's per-mode sums -> ONE
- *                            128-thread named barrier with the other column groups -> all four evaluate the (identical)
+ *                            64-thread named barrier with the other column group -> both evaluate the (identical)
  *                            Metropolis decision -> accepted chains write x' (their own words of the shared-memory state
- *                            tile).  Chain scalars (a, E, sigma, count) live in registers of all four threads.
+ *                            tile).  Chain scalars (a, E, sigma, count) live in registers of both threads.
  * The only serial dependency is the state inside the epilogue; generation and contraction run ahead of it.
  *
  * Stream definition (restated by oracle/me_oracle_k4.c): chain g, step s —
@@ -50,13 +50,14 @@ typedef unsigned int u32;
 typedef unsigned long long u64;
 
 constexpr int TILE = 128;               /* chains per tile = MMA M = TMEM lanes */
-/* CTA shape: 32 warps = 16 epilogue warps (4 column groups x 4 lane quarters) + 16 generator warps.  Both roles are chains
- * of dependent instructions (FP64 / XU / shared-memory latencies), so what they need is warps: with 8 + 8 warps the SM sat
- * at 48 % issue utilisation, a quarter of it spent polling mbarriers (profiles/r02_ncu_c4_k4_steps_v2_16warps.csv).  Registers
- * are granted per warpgroup: the kernel is launched at 64 per thread and the epilogue warpgroups grow to 80 while the
- * generator warpgroups shrink to 48 (setmaxnreg).  K4_WIDE=0 builds the 8 + 8 warp variant (128 registers each). */
+/* CTA shape.  Default: 16 warps = 8 epilogue warps (2 column groups x 4 lane quarters) + 8 generator warps, 128 registers
+ * each.  K4_WIDE=1 builds 32 warps (16 + 16, launched at 64 registers, epilogue warpgroups grown to 80 and generator
+ * warpgroups shrunk to 48 with setmaxnreg).  Measured on B200 (profiles/r02_k4_probe_*.txt, 32,768 chains, 10 / 100 steps per
+ * launch): 16 warps 90.5 / 766 us, 32 warps 96.2 / 832 us — with twice the warps the issue slots fill up (52 -> 58 %) but
+ * the four threads of a chain repeat the decision and the scalar draws, the mbarrier polls double, and the shared-memory
+ * pipe (state tile, partial sums, the generator's table) becomes the limiter (51 % of its cycles, MIO-throttle stalls). */
 #ifndef K4_WIDE
-#define K4_WIDE 1
+#define K4_WIDE 0
 #endif
 constexpr int EPI_GROUPS = K4_WIDE ? 4 : 2;                 /* threads per chain in the epilogue (column groups) */
 constexpr int EPI_WARPS = 4 * EPI_GROUPS, GEN_WARPS = K4_WIDE ? 16 : 8;

@@ -17,7 +17,8 @@ LIB = os.path.join(HERE, "libme_oracle_k4.so")
 
 class Config(ctypes.Structure):
     _fields_ = [("nc", ctypes.c_int), ("use_wall", ctypes.c_int), ("consts", ctypes.c_double * 16),
-                ("temp", ctypes.c_double), ("target", ctypes.c_double), ("ratio", ctypes.c_double)]
+                ("temp", ctypes.c_double), ("target", ctypes.c_double), ("ratio", ctypes.c_double),
+                ("groups", ctypes.c_int)]
 
 
 class Layout(ctypes.Structure):
@@ -89,13 +90,14 @@ def embed_factor(cov_c):
 
 class K4Ensemble:
     def __init__(self, nc, n_chains, consts, temp, ratio, seed=0, use_wall=True, target=0.3, sampling_width=0.05,
-                 x0=None, chain_offset=0, async_refresh=True):
+                 x0=None, chain_offset=0, async_refresh=True, groups=2):
         self.nc, self.n, self.seed, self.chain_offset = nc, n_chains, int(seed), int(chain_offset)
         self.cfg = Config()
         self.cfg.nc, self.cfg.use_wall = nc, int(use_wall)
         for i, v in enumerate(consts):
             self.cfg.consts[i] = float(v)
         self.cfg.temp, self.cfg.target, self.cfg.ratio = float(temp), float(target), float(ratio)
+        self.cfg.groups = int(groups)
         self.L = Layout()
         lib().k4o_layout_for(nc, ctypes.byref(self.L))
         x0 = np.zeros(1 + 2 * nc) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)

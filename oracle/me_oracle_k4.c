@@ -18,8 +18,8 @@
  *   increments  Delta_n = sum_k bf16(Z_k) bf16(B_nk), accumulated in double and rounded to float (the tensor core
  *               accumulates in FP32 in an order of its own: compared with a tolerance, then INJECTED — level L-A of
  *               SURVEY §8c applied to this path)
- *   step        x'_n = fma(sigma, (double)Delta_n, x_n); mode sums per quarter of the modes, in mode order, combined as
- *               (p0 + p1) + (p2 + p3); a' = fma(sigma s_a, za, a);
+ *   step        x'_n = fma(sigma, (double)Delta_n, x_n); mode sums per group of consecutive modes (2 groups: p0 + p1;
+ *               4 groups: (p0 + p1) + (p2 + p3) — the kernel's build says which, me_k4_layout.SUM_GROUPS); a' = fma(sigma s_a, za, a);
  *               wall; E' = total(a', s0, s1); accept = dE <= 0 or (T != 0 and u <= exp(-dE / T)); sigma update by fma
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared
@@ -35,6 +35,7 @@ typedef struct {
     int use_wall;
     double consts[16];        /* cylinder functor: kappa, alpha, gamma, beta */
     double temp, target, ratio;
+    int groups;               /* groups of consecutive modes the per-mode sums are accumulated over (me_k4_layout.SUM_GROUPS) */
 } k4o_config;
 
 typedef struct { int D, X, E, SIG, MEAN, OBSM, NOBS, NACC, STATUS, WORDS; } k4o_layout;
@@ -182,13 +183,15 @@ void k4o_init(const k4o_config *c, double *st, const double *x0, double sigma0) 
 int k4o_step(const k4o_config *c, double *st, const float *delta, double za, double u, double s_a, int64_t n_meas) {
     k4o_layout L;
     k4o_layout_for(c->nc, &L);
-    const int nc = c->nc, quarter = nc / 4;      /* the kernel's four column groups per chain (k4::EPI_GROUPS) */
+    const int groups = c->groups == 4 ? 4 : 2;   /* the kernel's column groups per chain (k4::EPI_GROUPS) */
+    const int nc = c->nc, quarter = nc / groups;
     const double sig = st[L.SIG];
     double f = (double)n_meas / (double)(1 + nc);
     if (!(f > 200.0)) f = 200.0;
     const double g_up = c->ratio * (1 - c->target) / f, g_down = c->ratio * c->target / f;
     double xr[K4O_MAX_NC], xi[K4O_MAX_NC], part0[4], part1[4];
-    for (int g = 0; g < 4; g++) {
+    part0[2] = part0[3] = part1[2] = part1[3] = 0.0;
+    for (int g = 0; g < groups; g++) {
         double s0 = 0.0, s1 = 0.0, q = (double)(g * quarter - nc / 2);
         for (int jj = 0; jj < quarter; jj++) {
             const int j = g * quarter + jj;
@@ -199,7 +202,8 @@ int k4o_step(const k4o_config *c, double *st, const float *delta, double za, dou
         }
         part0[g] = s0; part1[g] = s1;
     }
-    const double t0 = (part0[0] + part0[1]) + (part0[2] + part0[3]), t1 = (part1[0] + part1[1]) + (part1[2] + part1[3]);
+    const double t0 = groups == 4 ? (part0[0] + part0[1]) + (part0[2] + part0[3]) : part0[0] + part0[1];
+    const double t1 = groups == 4 ? (part1[0] + part1[1]) + (part1[2] + part1[3]) : part1[0] + part1[1];
     const double a_new = fma(sig * s_a, za, st[L.X]);
     int accept = 0;
     const int wall = c->use_wall && fabs(a_new) >= 1.0;

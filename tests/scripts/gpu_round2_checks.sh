@@ -11,6 +11,7 @@ ME_K4_NO_TMA=1 timeout 300 python tests/scripts/k4_probe.py > gpurun_out/${T}_k4
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${T}_bench.log 2> gpurun_out/${T}_bench.err; echo "bench rc=$?" >> gpurun_out/${T}_bench.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k4_steps -s 10 -c 1 -o gpurun_out/${T}_ncu_k4 python tests/scripts/k4_probe.py > gpurun_out/${T}_ncu_k4.log 2>&1
 # (register-cap variants: profiles/r02_nreg_probe_small_shapes.txt)
-ME_B200_LIB=$PWD/metropolisengine_b200/lib/variants/k4narrow_libme_b200.so timeout 300 python tests/scripts/k4_probe.py > gpurun_out/${T}_k4_probe_16warps.txt 2>&1
+ME_B200_LIB=$PWD/metropolisengine_b200/lib/variants/k4wide_libme_b200.so timeout 300 python tests/scripts/k4_probe.py > gpurun_out/${T}_k4_probe_32warps.txt 2>&1
+ME_B200_LIB=$PWD/metropolisengine_b200/lib/variants/k4wide_libme_b200.so timeout 600 python -m pytest tests/test_gpu_k4.py -q --timeout 600 -k oracle > gpurun_out/${T}_k4tests_32warps.log 2>&1
 timeout 300 python tests/scripts/scale_probe.py > gpurun_out/${T}_scale_probe.txt 2>&1
 tail -3 gpurun_out/${T}_k4tests.log; tail -3 gpurun_out/${T}_gputests.log; tail -2 gpurun_out/${T}_smoke.log; head -3 gpurun_out/${T}_k4_probe_v2.txt; tail -1 gpurun_out/${T}_bench.err

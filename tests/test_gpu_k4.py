@@ -239,7 +239,7 @@ def test_oracle_runs_beside_the_kernel_with_identical_decisions(nc, async_refres
                                     sampling_width=0.02, async_refresh=async_refresh)
     x0 = np.concatenate([[0.1], x0c.real, x0c.imag])
     orc = ko.K4Ensemble(nc, n, consts, T, eng.ratio, seed=seed, use_wall=True, sampling_width=0.02, x0=x0,
-                        async_refresh=async_refresh)
+                        async_refresh=async_refresh, groups=eng._lay.SUM_GROUPS)
     lay = eng._lay
     N = 2 * nc
     dz = torch.zeros((N, n), dtype=torch.float32, device="cuda")
