@@ -43,19 +43,19 @@ if ROOT not in sys.path:
 # (tests/scripts/sass_loop.py on the shipped library) — the inputs of the pipe-level roofline below.
 WORKLOADS = {
     "c1": dict(name="README x^2: 1 real param, T=0.01, measure every step", energy=("x2",), n_r=1, n_c=0, temp=0.01,
-               chains=65536, measures=10000, short_measures=10000, spm=1, flop=10, sf=3, fp64_inst=30.5, wide_inst=12.0),
+               chains=65536, measures=10000, short_measures=10000, spm=1, flop=10, sf=3, inst=111.0, fp64_inst=31.0, wide_inst=12.0),
     "c2": dict(name="demo/toymodel_xypotentialwell: 2 real params, E=x^2+y^2, T=0.1, 65,536 chains x 1e5 steps, "
                     "measure every 10", energy=("xy_well", 1.0), n_r=2, n_c=0, temp=0.1, chains=65536,
-               measures=10000, short_measures=2000, spm=10, flop=20, sf=5, fp64_inst=39.5, wide_inst=12.0),
+               measures=10000, short_measures=2000, spm=10, flop=20, sf=5, inst=126.5, fp64_inst=40.0, wide_inst=12.0),
     "c3": dict(name="mixed 3 real + 4 complex (bounded demo-style well), T=0.1, 262,144 chains, measure every 10",
                energy=("mixed_well", 1.0, -1.0, 0.5, 1.0), n_r=3, n_c=4, temp=0.1, chains=262144, measures=100,
-               short_measures=100, spm=10, flop=170, sf=23, fp64_inst=257.0, wide_inst=60.0),
+               short_measures=100, spm=10, flop=170, sf=23, inst=658.0, fp64_inst=257.0, wide_inst=60.0),
 }
 # the CPU arm also knows config 4 (1 real + 64 complex, the reference's own per-chain covariance: 128x128 SVD per step)
 CPU_WORKLOADS = dict(WORKLOADS)
 CPU_WORKLOADS["c4"] = dict(name="cylinder-style Fourier-mode field: 1 real + 64 complex (reference: per-chain covariance)",
                            temp=0.1, spm=10)
-NCU_C2_CAPTURE = "profiles/r01_ncu_c2_k_run_v5.csv"
+NCU_C2_CAPTURE = "profiles/r02_ncu_c2_k_run_stream_v3.csv"
 
 
 C4_NAME = ("cylinder-style Fourier-mode field: 1 real + 64 complex, shared proposal covariance (tensor-core L.Z), "
@@ -379,20 +379,26 @@ class Ctx:
 
 
 def pipe_model(wl, chains, steps_per_chain, ker_ms, sm_hz, n_sm):
-    """Pipe-level roofline of the fused step kernel.  A warp-wide FP64 instruction holds the FP64 pipe of its SM
-    sub-partition for 2 cycles and an IMAD.WIDE (Philox round) the FMA-heavy pipe for ~3.5; the two contend
-    (tests/scripts/issue_mix.cu, profiles/r01_microbench_issue_mix.txt), so a warp-step costs at least
-    2 * fp64_inst + 3.5 * wide_inst cycles of its sub-partition; launches are balanced over the sub-partitions, so the
-    bound is that cost times the average number of warps per sub-partition."""
+    """Issue-port roofline of the fused step kernel (DESIGN.md §3 "What bounds the step kernel").  Measured on B200: once an
+    SM sub-partition holds >= 3 warps of this kernel its throughput no longer grows with the warp count
+    (tests/scripts/scale_probe.py) and the time per warp-step follows   inst + fp64_inst + 2.5 * wide_inst   cycles of the
+    sub-partition's issue port — every instruction takes one issue cycle, a warp-wide FP64 instruction holds the port a
+    second cycle (64 FP64 lanes per clock and SM = 2 cycles per warp) and an IMAD.WIDE (Philox round) about 3.5 cycles in
+    all (tests/scripts/issue_mix.cu).  The model reproduces both stream definitions of this kernel: v2 (164 / 59 / 18
+    instructions per step) predicts 268 cycles against 295 measured, v3 (this build) 196 against 228.  The bound is that
+    cost (step loop only; the measure block is not counted) times the average number of warps per sub-partition."""
     warps = -(-chains // 32) / (4.0 * n_sm)
-    cyc = 2.0 * wl["fp64_inst"] + 3.5 * wl["wide_inst"]
+    cyc = wl["inst"] + wl["fp64_inst"] + 2.5 * wl["wide_inst"]
     bound_ms = 1e3 * warps * steps_per_chain * cyc / sm_hz
-    return {"fp64_inst_per_chain_step": wl["fp64_inst"], "imad_wide_per_chain_step": wl["wide_inst"],
-            "cycles_per_warp_step_lower_bound": cyc, "warps_per_subpartition": warps, "bound_ms": bound_ms,
-            "frac": bound_ms / ker_ms,
-            "how": "FP64-pipe + FMA-heavy-pipe cycles the SASS of the step loop needs (2 per FP64 instruction, 3.5 per "
-                   "IMAD.WIDE; instruction counts from tests/scripts/sass_loop.py on the shipped library) x average warps "
-                   "per SM sub-partition / measured kernel time"}
+    return {"inst_per_chain_step": wl["inst"], "fp64_inst_per_chain_step": wl["fp64_inst"],
+            "imad_wide_per_chain_step": wl["wide_inst"], "issue_cycles_per_warp_step_lower_bound": cyc,
+            "warps_per_subpartition": warps, "bound_ms": bound_ms, "frac": bound_ms / ker_ms,
+            "fp64_pipe_frac": 1e3 * warps * steps_per_chain * 2.0 * wl["fp64_inst"] / sm_hz / ker_ms,
+            "how": "issue-port cycles the SASS of the step loop needs (1 per instruction + 1 more per FP64 instruction + 2.5 "
+                   "more per IMAD.WIDE; counts from tests/scripts/sass_loop.py on the shipped library, main path of the "
+                   "loop) x average warps per SM sub-partition / measured kernel time; fp64_pipe_frac = FP64-pipe cycles "
+                   "(2 per FP64 instruction) / measured kernel time, the quantity ncu reports as "
+                   "sm__pipe_fp64_cycles_active"}
 
 
 def fp64_peak_tflops(ctx, lib):
