@@ -473,6 +473,37 @@ def short_fused_pass(ctx, wl_key, fp64_peak, hbm_peak, sm_hz, steps=3, warmup=3)
     return rec
 
 
+def per_chain_large_pass(ctx, hbm_peak, steps=3, warmup=3, chains=8192, measures=20):
+    """The reference's OWN algorithm at the cylinder shape: 1 real + 64 complex with a covariance per chain (ME:274-302), the
+    runtime-shape kernel (me_generic.cu, gk_run: one launch per schedule).  HBM-bound: every step streams the chain's 64 x 64
+    complex factor (8 n_c^2 = 32,768 B) plus the parameter / proposal / normal vectors."""
+    import numpy as np
+    import metropolisengine_b200 as me
+    spm, nc = 10, 64
+    eng = me.MetropolisEngine(me.BuiltinEnergy("cylinder", 10.0, -1.0, 0.05, 1.0, reject=True),
+                              initial_real_params=np.array([0.0]), initial_complex_params=np.zeros(nc, dtype=complex),
+                              temp=.1, n_chains=chains * ctx.world, seed=5, record=False, distributed=(ctx.world > 1),
+                              device=ctx.dev, sampling_width=0.02)
+    eng.run(55, 2)                       # past the 50th measure: per-chain covariances and their Cholesky factors are live
+    ms = ctx.timed(lambda: eng.run(measures, spm), steps, warmup)
+    value = chains * ctx.world * measures * spm * steps / (ms * 1e-3)
+    d = 1 + 2 * nc
+    bytes_step = 8.0 * (nc * nc + 7 * d)             # factor + x, z (w+r), proposal (w+r+r), state write-back on accept
+    gbs = chains * measures * spm * steps * bytes_step / (ms * 1e-3) / 1e9
+    rec = {"workload": "1 real + 64 complex, PER-CHAIN covariance (the reference's algorithm at the cylinder shape), %d chains "
+                       "per GPU, measure (64 x 64 complex Cholesky per chain) every 10 steps" % chains,
+           "value": value, "unit": "chain-steps/s", "ms_per_pass": ms / steps, "kernel": "gk_run",
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                        "traffic": None,
+                        "algorithmic": "%d B per chain-step (8 n_c^2 factor stream + 7 vectors of D doubles); the per-measure "
+                                       "Cholesky (O(n_c^3) per chain, operands in global memory) is inside the timed pass"
+                                       % int(bytes_step)},
+           "acceptance_rate": eng.acceptance_rate}
+    del eng
+    ctx.torch.cuda.empty_cache()
+    return rec
+
+
 def c4_pass(ctx, peaks, steps=3, warmup=3, measures=100):
     """BASELINE config 4: 1 real + 64 complex, shared proposal covariance, 32,768 chains per GPU; tcgen05 path.  One pass =
     `measures` x (10 x step_all() + measure()), the pooled-covariance update (and, for N > 1, its moment all-reduce)
@@ -688,6 +719,7 @@ def run_ours(args):
             if key != args.workload:
                 sub[key] = short_fused_pass(ctx, key, fp64_peak, hbm_peak, sm_hz)
         sub["c4"] = c4_pass(ctx, peaks)
+        sub["c4_per_chain_covariance"] = per_chain_large_pass(ctx, hbm_peak)
         sub["c5_2^20_chains_total"] = c5_pass(ctx)
 
     if rank != 0:

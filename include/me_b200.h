@@ -146,6 +146,8 @@ typedef struct me_buffers {
     double *shift;              /* [D] shift of the pooled moments (required when pool != NULL) */
     unsigned char *last_accept; /* [n_chains] accept flag of the most recent step — the return value of step_all() (ME:259) */
     double *scratch;            /* [D][n_chains] work space, required when D = n_real + 2 n_complex > 32 (may be NULL otherwise) */
+    double *prop;               /* [D][n_chains] proposal block of the one-launch schedule of large shapes (me_run with steps on
+                                   a D > 32 handle); may be NULL: such handles then step through me_propose / me_accept only */
 } me_buffers;
 int me_bind(me_engine *eng, const me_buffers *buffers);
 
@@ -185,8 +187,10 @@ int me_accept(me_engine *eng, const double *prop, const double *e_new, const uns
               const double *inj_u, void *stream);
 
 /* Large parameter spaces (D > 32, e.g. 1 real + 64 complex with per-chain covariance — the reference's own
- * algorithm at the cylinder shape): the step is always unfused, me_propose -> energy -> me_accept, with runtime-shape
- * kernels whose state stays in global memory (csrc/me_generic.cu); me_run then only serves measure().
+ * algorithm at the cylinder shape): runtime-shape kernels whose state stays in global memory (csrc/me_generic.cu).  With a
+ * built-in functor me_run performs the whole schedule in one launch (me_buffers.prop required); with a caller-evaluated
+ * energy, a host-side predicate, magnitude / phase moves or injected draws the step is me_propose -> energy -> me_accept
+ * and me_run serves measure().
  * me_energy_builtin evaluates the handle's DEVICE functor (built-in, or user CUDA text on fused shapes) and its hard
  * wall on a proposal block: e_out[n_chains], rej_out[n_chains] (may be NULL).  Besides the large-shape step it lets a
  * host-side predicate — the reference's python reject_condition (ME:142-146) — sit between me_propose and me_accept

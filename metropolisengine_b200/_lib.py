@@ -35,7 +35,7 @@ class MeLayout(ctypes.Structure):
 
 
 class MeBuffers(ctypes.Structure):
-    _fields_ = [("state", _vp), ("pool", _vp), ("shift", _vp), ("last_accept", _vp), ("scratch", _vp)]
+    _fields_ = [("state", _vp), ("pool", _vp), ("shift", _vp), ("last_accept", _vp), ("scratch", _vp), ("prop", _vp)]
 
 
 class MeK4Config(ctypes.Structure):

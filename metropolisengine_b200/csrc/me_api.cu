@@ -447,6 +447,7 @@ void base_params(me_engine *e, MeParams &p) {
     p.n_complex = e->cfg.n_complex;
     p.energy_id = e->energy_id;
     p.scratch = e->buf.scratch;
+    p.prop = e->buf.prop;
     p.group = e->group;
 }
 
@@ -916,9 +917,11 @@ static int run_common(me_engine *e, int64_t n_blocks, int64_t spm, int do_measur
     if (n_blocks == 0 || (spm == 0 && !do_measure)) return ME_OK;
     if (spm > 0 && e->energy_id == ME_ENERGY_EXTERNAL)
         return fail(e, ME_ERR_STATE, "external energies step through me_propose / me_accept");
-    if (e->generic && (spm > 0 || n_blocks != 1))
-        return fail(e, ME_ERR_STATE, "large parameter spaces step through me_propose / me_energy_builtin / me_accept "
-                                     "and measure one block at a time");
+    if (e->generic && spm > 0 &&
+        (delta != nullptr || e->energy_id < 0 || e->energy_id >= ME_ENERGY_EXTERNAL || !e->buf.prop || e->group >= 3))
+        return fail(e, ME_ERR_STATE, "large parameter spaces run whole schedules in one launch only with a built-in functor "
+                                     "(and me_buffers.prop bound); otherwise step through me_propose / me_energy_builtin / "
+                                     "me_accept and let me_run measure");
     if (e->step + (unsigned long long)(n_blocks * spm) >= 0xffffffffull)
         return fail(e, ME_ERR_INVALID, "step index exceeds the 32-bit Philox counter word");
     MeParams p;

@@ -147,12 +147,7 @@ __global__ void gk_init(const __grid_constant__ MeParams p) {
 }
 
 /* proposal (ME:261-302): x' = x + sigma_r L z ; c' = c + sigma_c conj(G) xi, xi = (z + i z')/sqrt2 */
-__global__ void gk_propose(const __grid_constant__ MeParams p) {
-    __shared__ me::MathTables tables;
-    me::init_math_tables(tables);
-    __syncthreads();
-    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= p.n_chains) return;
+__device__ void g_propose(const MeParams &p, const me::MathTables &tables, long long ch, unsigned step) {
     const GLay L(p.n_real, p.n_complex);
     const long long ld = p.ld;
     double *st = p.state;
@@ -171,7 +166,7 @@ __global__ void gk_propose(const __grid_constant__ MeParams p) {
     double *z = p.scratch + ch;
     const me::Rng rng(p, p.chain_offset + (unsigned long long)ch);
     for (int q = 0; q < (d + 1) / 2; q++) {
-        const me::U4 r = rng.bits((unsigned)p.step0, (unsigned)q);
+        const me::U4 r = rng.bits(step, (unsigned)q);
         double z0, z1;
         me::Rng::box_muller<true>(r, tables, z0, z1);
         z[(long long)(2 * q) * ld] = z0;
@@ -199,7 +194,7 @@ __global__ void gk_propose(const __grid_constant__ MeParams p) {
                 pr[(long long)(nr + nc + j) * ld] = mag > 0.0 ? im * ratio
                                                               : nm * copysign(neg0 ? 1.2246467991473532e-16 : 0.0, im);
             } else {
-                const me::U4 r = rng.bits((unsigned)p.step0, (unsigned)j);
+                const me::U4 r = rng.bits(step, (unsigned)j);
                 double sn, cs;
                 me::sincospi_bits(r.z, sn, cs);
                 pr[(long long)(nr + j) * ld] = mag * -cs;
@@ -232,14 +227,18 @@ __global__ void gk_propose(const __grid_constant__ MeParams p) {
         for (int i = 0; i < d; i++)
             if ((i < nr) != (p.group == 1)) pr[(long long)i * ld] = ST(L.X + i);
 }
-
-/* decision + sigma adaptation (ME:247-258, 319-338, 429-456) */
-__global__ void gk_accept(const __grid_constant__ MeParams p) {
+__global__ void gk_propose(const __grid_constant__ MeParams p) {
     __shared__ me::MathTables tables;
     me::init_math_tables(tables);
     __syncthreads();
     const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= p.n_chains) return;
+    g_propose(p, tables, ch, (unsigned)p.step0);
+}
+
+/* decision + sigma adaptation (ME:247-258, 319-338, 429-456); e_new / wall of THIS chain are passed in */
+__device__ void g_accept(const MeParams &p, const me::MathTables &tables, long long ch, unsigned step, long long n_meas,
+                         double e_new, bool wall) {
     const GLay L(p.n_real, p.n_complex);
     const long long ld = p.ld;
     double *st = p.state;
@@ -248,11 +247,9 @@ __global__ void gk_accept(const __grid_constant__ MeParams p) {
     const int sidx = grouped ? (p.group == 1 ? 0 : 1) : (kind == 2 ? 1 : 0);
     double sg = ST(L.SIG + sidx);
     int status = (int)ST(L.STATUS);
-    const me::Gains g = me::make_gains(p.n_meas0, p);
+    const me::Gains g = me::make_gains(n_meas, p);
     bool accept = false;
-    const bool wall = p.rej != nullptr && p.rej[ch] != 0;
     if (!wall) {
-        const double e_new = p.e_new[ch];
         if (e_new != e_new) status |= ME_STATUS_ENERGY_NAN;
         const double diff = e_new - ST(L.E);
         double u = 0.0;
@@ -260,7 +257,7 @@ __global__ void gk_accept(const __grid_constant__ MeParams p) {
         else if (diff > 0 && p.temp != 0) {
             const me::Rng rng(p, p.chain_offset + (unsigned long long)ch);
             me::Spare sp;
-            me::Rng::keep_spare(rng.bits((unsigned)p.step0, 0u), 0, sp);
+            me::Rng::keep_spare(rng.bits(step, 0u), 0, sp);
             u = me::Rng::accept_uniform(sp);
         }
         accept = me::decide<true>(diff, u, p, tables, g.hot);
@@ -279,18 +276,23 @@ __global__ void gk_accept(const __grid_constant__ MeParams p) {
     ST(L.STATUS) = (double)status;
     if (p.last_accept) p.last_accept[ch] = (unsigned char)accept;
 }
-
-/* measure (ME:342-427): the strict-order arithmetic of me::measure_update for runtime shapes.  Launched through
- * me_run(1, 0, 1, ...): n = n_meas0 + 1. */
-__global__ void gk_measure(const __grid_constant__ MeParams p) {
+__global__ void gk_accept(const __grid_constant__ MeParams p) {
+    __shared__ me::MathTables tables;
+    me::init_math_tables(tables);
+    __syncthreads();
     const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= p.n_chains) return;
+    g_accept(p, tables, ch, (unsigned)p.step0, p.n_meas0, p.e_new[ch], p.rej != nullptr && p.rej[ch] != 0);
+}
+
+/* measure (ME:342-427): the strict-order arithmetic of me::measure_update for runtime shapes; n = the counter AFTER the
+ * increment, ts_row = the time-series row this measure writes. */
+__device__ void g_measure(const MeParams &p, long long ch, long long n, long long ts_row) {
     const GLay L(p.n_real, p.n_complex);
     const long long ld = p.ld;
     double *st = p.state;
     double *old = p.scratch + ch;          /* old[i] at scratch[i][ch] */
     const int nr = L.nr, nc = L.nc, d = L.d;
-    const long long n = p.n_meas0 + 1;
     const double dn = (double)n, dn1 = (double)(n - 1), dn2 = (double)(n - 2);
     const double inv_n = 1.0 / dn, inv_n1 = 1.0 / dn1;
     const double shrink = dn1 / dn, decay = dn2 / dn1, grow = dn / dn1;
@@ -358,7 +360,7 @@ __global__ void gk_measure(const __grid_constant__ MeParams p) {
     if (p.record) {
         const int kind = (nr > 0 && nc > 0) ? 0 : (nr > 0 ? 1 : 2);
         const int tscols = d + (kind == 0 ? 3 : 2);
-        double *row = p.ts + p.ts_row0 * (long long)tscols * ld + ch;
+        double *row = p.ts + ts_row * (long long)tscols * ld + ch;
         for (int i = 0; i < d; i++) __stcs(row + (long long)i * ld, ST(L.X + i));
         __stcs(row + (long long)d * ld, ST(L.E));
         if (kind == 0) {
@@ -370,11 +372,38 @@ __global__ void gk_measure(const __grid_constant__ MeParams p) {
     }
 }
 
+/* The whole schedule of a runtime-shape engine with a built-in functor in ONE launch (the fused kernel's counterpart for
+ * D > 32): n_blocks x (spm x [propose -> energy + wall -> decide] [+ measure]).  One thread per chain; the chain's state, its
+ * 64 x 64 factor, the proposal and the normals stay in global memory (chain-minor: every word access of a warp is one
+ * coalesced 256-byte line), so a step streams the factor once: 8 (n_r(n_r+1)/2 + n_c^2) bytes per chain-step — HBM bound. */
+__global__ void gk_run(const __grid_constant__ MeParams p) {
+    __shared__ me::MathTables tables;
+    me::init_math_tables(tables);
+    __syncthreads();
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_chains) return;
+    long long n = p.n_meas0;
+    unsigned step = (unsigned)p.step0;
+    for (long long b = 0; b < p.n_blocks; b++) {
+        for (long long k = 0; k < p.spm; k++, step++) {
+            g_propose(p, tables, ch, step);
+            const double *v = p.prop + ch;
+            const bool wall = p.use_reject && p.energy_id == ME_ENERGY_CYLINDER && fabs(v[0]) >= 1.0;
+            const double e_new = wall ? 0.0 : g_energy(p.energy_id, v, p.ld, p.n_real, p.n_complex, p.consts);
+            g_accept(p, tables, ch, step, n, e_new, wall);
+        }
+        if (p.do_measure) {
+            n += 1;
+            g_measure(p, ch, n, p.ts_row0 + b);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" void me_generic_kernels(const void **run_measure, const void **init, const void **propose, const void **accept,
                                    const void **energy) {
-    *run_measure = (const void *)&gk_measure;
+    *run_measure = (const void *)&gk_run;
     *init = (const void *)&gk_init;
     *propose = (const void *)&gk_propose;
     *accept = (const void *)&gk_accept;

@@ -204,14 +204,16 @@ class MetropolisEngine:
         self._ctr_on = False
         self._generic = self._d > 32          # large shapes: runtime-shape kernels, unfused step (me_generic.cu)
         self._scratch = torch.zeros((self._d, self.n_chains), dtype=f64, device=dev) if self._generic else None
+        self._prop = torch.zeros((self._d, self.n_chains), dtype=f64, device=dev) if self._generic else None
         bufs = _lib.MeBuffers(_ptr(self.state), _ptr(self._pool), _ptr(self._shift), _ptr(self._last_accept),
-                              _ptr(self._scratch))
+                              _ptr(self._scratch), _ptr(self._prop))
         self._check(self._lib.me_bind(self._h, ctypes.byref(bufs)))
 
         # ---- energy plugin (ME:110-120) and hard-wall predicate (ME:126-127, 142-146)
         self._callable = None
         self._terms = None
         self.reject_condition = None
+        self._group_mode = 0
         self._callable_layout = callable_layout
         if callable_layout not in ("chains_first", "params_first"):
             raise ValueError("callable_layout must be 'chains_first' or 'params_first'")
@@ -463,8 +465,8 @@ class MetropolisEngine:
         the device copy of the counters, so a replay continues the chains exactly like an eager call
         (``test_graph_replay_of_fused_runs_is_bit_identical``)."""
         n_measures, steps_per_measure = int(n_measures), int(steps_per_measure)
-        if self._unfused() or self.record:
-            raise RuntimeError("run_graphed serves fused device-functor engines with record=False")
+        if self._unfused() or self._generic or self.record:
+            raise RuntimeError("run_graphed serves fused device-functor engines (D <= 32) with record=False")
         key = ("fused", n_measures, steps_per_measure)
         seen = self._graphs.get(key)
         if seen is None:                        # first use: eager, so that no allocation happens under capture
@@ -583,9 +585,11 @@ class MetropolisEngine:
             self.step_counter += int(k)
 
     def _unfused(self):
-        """True when a step is propose -> energy -> accept instead of the fused kernel: python energies, large shapes,
-        and any engine carrying a python reject_condition."""
-        return self._callable is not None or self._generic or self.reject_condition is not None
+        """True when a step is propose -> energy -> accept (separate launches) instead of one kernel: python energies,
+        any engine carrying a python reject_condition, and large shapes doing magnitude / phase moves.  Large shapes
+        (D > 32) with a device functor run whole schedules in one launch of the runtime-shape kernel (gk_run)."""
+        return (self._callable is not None or self.reject_condition is not None
+                or (self._generic and self._group_mode >= 3))
 
     def _step_external(self, inj_delta=None, inj_u=None):
         prop = torch.empty((self._d, self.n_chains), dtype=torch.float64, device=self.device)
@@ -656,7 +660,7 @@ class MetropolisEngine:
             u = u[:, None].expand(S, self.n_chains)
         delta, u = delta.contiguous(), u.contiguous()
         assert delta.shape == (S, self._d, self.n_chains) and u.shape == (S, self.n_chains)
-        if self._unfused():
+        if self._unfused() or self._generic:      # runtime shapes inject one step at a time (me_propose / me_accept)
             s = 0
             for _ in range(int(n_measures)):
                 for _ in range(int(steps_per_measure)):

@@ -120,6 +120,31 @@ def test_large_shape_philox_matches_c_oracle():
         assert close(st[:lay.WORDS - 2, ch], o.state[:lay.WORDS - 2], 1e-9), ch
 
 
+def test_large_shape_one_launch_schedule_equals_the_step_by_step_path():
+    """Runtime shapes (D > 32) with a built-in functor run a whole schedule in one launch (gk_run: propose -> energy + wall
+    -> decide per step, measure per block, all inside the kernel).  It must equal the three-launches-per-step path bit
+    for bit (same device functions, same Philox slots) — forced here by an always-false python predicate — including the
+    stored rows, and group-wise steps."""
+    import metropolisengine_b200 as me
+    kw = dict(initial_real_params=np.array([0.2]), initial_complex_params=np.zeros(16, dtype=complex), temp=.1,
+              sampling_width=0.05, n_chains=96, seed=17)
+    consts = (10.0, -1.0, 0.05, 1.0)
+    a = me.MetropolisEngine(me.BuiltinEnergy("cylinder", *consts, reject=True), **kw)
+    b = me.MetropolisEngine(me.BuiltinEnergy("cylinder", *consts, reject=True), **kw)
+    b.set_reject_condition(lambda r, c: torch.zeros(r.shape[0], dtype=torch.bool, device=r.device))
+    assert a._generic and not a._unfused() and b._unfused()
+    l0 = a.launch_count
+    a.run(55, 4)
+    assert a.launch_count - l0 == 1                                   # the whole schedule: one launch
+    b.run(55, 4)
+    a.step_real_group(3); b.step_real_group(3)
+    a.step_complex_group(2); b.step_complex_group(2)
+    torch.cuda.synchronize()
+    assert torch.equal(a.state, b.state)
+    assert torch.equal(a.time_series(), b.time_series()) and a.time_series().shape[0] == 55
+    assert a.measure_step_counter == b.measure_step_counter == 56 and a.steps_done == b.steps_done == 225
+
+
 @pytest.mark.parametrize("name", ["pure_2c", "warm_3r2c"])
 def test_injected_parity_user_functor_nvrtc(name):
     """User CUDA functors compiled at run time (NVRTC, --fmad=false) and fused into the step kernel."""
