@@ -295,6 +295,15 @@ int me_k4_moments(me_k4 *eng, const double *shift, double *scratch, int64_t scra
  * covariance, cov_a the variance of the real parameter, s_a its square root, status != 0 if not positive definite. */
 int me_k4_refactor(me_k4 *eng, const double *mom, const double *inc, int64_t n_measure, double *cov_c, double *cov_a,
                    void *factor_bf16, double *s_a, int32_t *status, void *stream);   /* n_measure <= 0: the handle's counter */
+/* The block a sampling loop repeats — n_steps x step_all(), then measure() (reference README loop; ME:241-259, 342-356)
+ * — as ONE launch of the step kernel plus the two small reduction kernels of the pooled moments.  The per-chain
+ * measurement equals me_k4_measure bit for bit.  The second moments sum Y Y^T are formed on the tensor cores from Y split
+ * into two BF16 words (products accurate to ~2^-16 relative, FP32 accumulation per CTA, FP64 across CTAs); first moments
+ * and scalar sums are FP64.  me_k4_measure + me_k4_moments remain the all-FP64 route.  Arguments as in me_k4_step,
+ * me_k4_measure (ts may be NULL) and me_k4_moments; n_steps >= 1. */
+int me_k4_step_measure(me_k4 *eng, int64_t n_steps, const double *s_a, double *ts, int64_t ts_row, const double *shift,
+                       double *scratch, int64_t scratch_doubles, double *inc, double *mom_accum, double *snapshot,
+                       void *stream);
 /* The factor the next me_k4_step launches read (double-buffering: a refresh may be writing the other buffer), and the
  * number of SMs the step kernel leaves idle so that the one-CTA refresh can run beside it on another stream. */
 int me_k4_set_factor(me_k4 *eng, const void *factor_bf16);

@@ -87,6 +87,7 @@ SIGNATURES = {
     "me_k4_set_energy_source": (ctypes.c_int, [_vp, _cp, ctypes.POINTER(_f64), _i32, _i32]),
     "me_k4_check_energy_source": (ctypes.c_int, [_cp, _i32, _i32, _cp, _i64]),
     "me_k4_step": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "me_k4_step_measure": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "me_k4_measure": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     "me_k4_moments": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "me_k4_refactor": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -73,10 +73,10 @@ __global__ void k4_measure(MeasureParams p) {
     if (j == nc) {
         const double a = p.state[(long long)L.X * ld + ch];
         double *mp = &p.state[(long long)L.MEAN * ld + ch];
-        *mp = *mp * shrink + a * inv_n;
+        *mp = fma(a, inv_n, *mp * shrink);
         double *o0 = &p.state[(long long)L.OBSM * ld + ch], *o1 = &p.state[(long long)(L.OBSM + 1 + nc) * ld + ch];
-        *o0 = *o0 * shrink + fabs(a) * inv_n;
-        *o1 = *o1 * shrink + (a * a) * inv_n;
+        *o0 = fma(fabs(a), inv_n, *o0 * shrink);
+        *o1 = fma(a * a, inv_n, *o1 * shrink);
         if (row) {
             __stcs(row, a);
             __stcs(row + (long long)L.D * ld, p.state[(long long)L.E * ld + ch]);
@@ -88,10 +88,10 @@ __global__ void k4_measure(MeasureParams p) {
     const double im = p.state[(long long)(L.X + 1 + nc + j) * ld + ch];
     double *mr = &p.state[(long long)(L.MEAN + 1 + j) * ld + ch];
     double *mi = &p.state[(long long)(L.MEAN + 1 + nc + j) * ld + ch];
-    *mr = *mr * shrink + re * inv_n;
-    *mi = *mi * shrink + im * inv_n;
+    *mr = fma(re, inv_n, *mr * shrink);
+    *mi = fma(im, inv_n, *mi * shrink);
     double *ob = &p.state[(long long)(L.OBSM + 1 + j) * ld + ch];
-    *ob = *ob * shrink + hypot(re, im) * inv_n;
+    *ob = fma(hypot(re, im), inv_n, *ob * shrink);
     if (row) {
         __stcs(row + (long long)(1 + j) * ld, re);
         __stcs(row + (long long)(1 + nc + j) * ld, im);
@@ -627,51 +627,107 @@ int me_k4_init(me_k4 *e, const double *x0, int32_t broadcast, double sigma0, voi
     return ME_OK;
 }
 
+/* one launch of the step kernel; `tail` != nullptr adds the fused measure (see StepParams) */
+struct K4Tail { double *ts; long long ts_row; const double *shift; double *mom_part; };
+static int k4_launch_steps(me_k4 *e, int64_t n_steps, const double *s_a, float *dbg_z, float *dbg_delta, double *dbg_scal,
+                           const K4Tail *tail, int *grid_out, void *stream) {
+    const int avail = e->n_sm - e->reserved_sms > 0 ? e->n_sm - e->reserved_sms : 1;
+    int rc = ME_OK;
+    std::string err;
+    StepParams p;
+    k4_base(e, p);
+    p.n_steps = n_steps; p.s_a = s_a; p.dbg_z = dbg_z; p.dbg_delta = dbg_delta; p.dbg_scal = dbg_scal;
+    if (tail) {
+        p.do_measure = 1; p.record = tail->ts != nullptr; p.n_meas_after = e->n_measure + 1;
+        p.ts = tail->ts; p.ts_row = tail->ts_row; p.shift = tail->shift; p.mom_part = tail->mom_part;
+    }
+    long long per = (e->cfg.n_chains + avail - 1) / avail;
+    per = (per + 31) / 32 * 32;
+    p.chains_per_cta = per;
+    const int grid = (int)((e->cfg.n_chains + per - 1) / per);
+    if (grid_out) *grid_out = grid;
+    /* tensor map of the factor: rows of 16 bytes, [K/8 chunks x N rows][8 bf16] */
+    k4::TensorMap bmap;
+    memset(&bmap, 0, sizeof(bmap));
+    p.use_tma = 0;
+    if (!e->no_tma) {
+        const int N = 2 * e->nc, rows = (N / 8) * N;
+        if (me_rt_tensor_map_2d_bf16(&bmap, e->factor, 8, rows, 8, rows < 256 ? rows : 256) == ME_OK) p.use_tma = 1;
+        else e->no_tma = true;                 /* driver without tensor maps: plain staging from now on */
+    }
+    void *args[] = {&p, &bmap};
+    if (e->steps_drv) {
+        rc = me_rt_launch(e->steps_drv, grid, k4::THREADS, e->steps_smem, stream, args, err);
+    } else {
+        /* the attribute is per device: set it before every launch (a host-side table write, no device work) */
+        cudaError_t ce = cudaFuncSetAttribute(e->steps_rt, cudaFuncAttributeMaxDynamicSharedMemorySize, e->steps_smem);
+        if (ce == cudaSuccess)
+            ce = cudaLaunchKernel(e->steps_rt, dim3(grid), dim3(k4::THREADS), args, (size_t)e->steps_smem, (cudaStream_t)stream);
+        if (ce != cudaSuccess) { rc = ME_ERR_CUDA; err = cudaGetErrorString(ce); }
+    }
+    if (rc != ME_OK) return k4_fail(e, rc, "k4_steps: " + err);
+    return ME_OK;
+}
+
 int me_k4_step(me_k4 *e, int64_t n_steps, const double *s_a, float *dbg_z, float *dbg_delta, double *dbg_scal, void *stream) {
     if (!e || !e->state || !s_a) return ME_ERR_INVALID;
     if (n_steps <= 0) return ME_OK;
     if (e->step + (unsigned long long)n_steps >= 0xffffffffull) return k4_fail(e, ME_ERR_INVALID, "step counter overflow");
     int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
-    const int avail = e->n_sm - e->reserved_sms > 0 ? e->n_sm - e->reserved_sms : 1;
     int rc = ME_OK;
-    std::string err;
     if (e->use_v1) {
+        const int avail = e->n_sm - e->reserved_sms > 0 ? e->n_sm - e->reserved_sms : 1;
         const int ce = me_k4v1_steps(e->state, e->cfg.n_chains, e->cfg.n_chains, (unsigned long long)e->cfg.chain_offset,
                                      e->cfg.seed, e->step, n_steps, avail, e->n_measure, e->cfg.temp,
                                      e->cfg.target_acceptance, e->cfg.ratio, e->consts, e->use_reject, e->factor, s_a,
                                      e->last_accept, dbg_z, dbg_delta, stream);
-        if (ce != 0) { rc = ME_ERR_CUDA; err = cudaGetErrorString((cudaError_t)ce); }
+        if (ce != 0) rc = k4_fail(e, ME_ERR_CUDA, std::string("k4_steps: ") + cudaGetErrorString((cudaError_t)ce));
     } else {
-        StepParams p;
-        k4_base(e, p);
-        p.n_steps = n_steps; p.s_a = s_a; p.dbg_z = dbg_z; p.dbg_delta = dbg_delta; p.dbg_scal = dbg_scal;
-        long long per = (e->cfg.n_chains + avail - 1) / avail;
-        per = (per + 31) / 32 * 32;
-        p.chains_per_cta = per;
-        const int grid = (int)((e->cfg.n_chains + per - 1) / per);
-        /* tensor map of the factor: rows of 16 bytes, [K/8 chunks x N rows][8 bf16] */
-        k4::TensorMap bmap;
-        memset(&bmap, 0, sizeof(bmap));
-        p.use_tma = 0;
-        if (!e->no_tma) {
-            const int N = 2 * e->nc, rows = (N / 8) * N;
-            if (me_rt_tensor_map_2d_bf16(&bmap, e->factor, 8, rows, 8, rows < 256 ? rows : 256) == ME_OK) p.use_tma = 1;
-            else e->no_tma = true;                 /* driver without tensor maps: plain staging from now on */
-        }
-        void *args[] = {&p, &bmap};
-        if (e->steps_drv) {
-            rc = me_rt_launch(e->steps_drv, grid, k4::THREADS, e->steps_smem, stream, args, err);
-        } else {
-            /* the attribute is per device: set it before every launch (a host-side table write, no device work) */
-            cudaError_t ce = cudaFuncSetAttribute(e->steps_rt, cudaFuncAttributeMaxDynamicSharedMemorySize, e->steps_smem);
-            if (ce == cudaSuccess)
-                ce = cudaLaunchKernel(e->steps_rt, dim3(grid), dim3(k4::THREADS), args, (size_t)e->steps_smem, (cudaStream_t)stream);
-            if (ce != cudaSuccess) { rc = ME_ERR_CUDA; err = cudaGetErrorString(ce); }
-        }
+        rc = k4_launch_steps(e, n_steps, s_a, dbg_z, dbg_delta, dbg_scal, nullptr, nullptr, stream);
     }
     cudaSetDevice(prev);
-    if (rc != ME_OK) return k4_fail(e, rc, "k4_steps: " + err);
+    if (rc != ME_OK) return rc;
     e->step += (unsigned long long)n_steps;
+    return ME_OK;
+}
+
+static void k4_moments_finish(me_k4 *e, double *scratch, int n_parts, double *inc, double *mom_accum, double *snapshot,
+                              void *stream) {
+    const int nc = e->nc, pw = partw(nc), mw = momw(nc);
+    double *total = scratch + (long long)n_parts * pw;
+    k4_moments_stage2a<<<(pw + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, n_parts, total, nc);
+    k4_moments_stage2b<<<(mw + 127) / 128, 128, 0, (cudaStream_t)stream>>>(total, reinterpret_cast<double2 *>(inc),
+                                                                       reinterpret_cast<double2 *>(mom_accum),
+                                                                       reinterpret_cast<double2 *>(snapshot), nc);
+}
+
+/* n_steps x step_all() + measure() in ONE launch of the step kernel, then the two small reduction kernels of the pooled
+ * moments: the block a sampling loop repeats (ME README loop: step_all x k, measure).  The per-chain measurement is the
+ * one of me_k4_measure bit for bit; the second moments S = sum Y Y^T are formed on the tensor cores from Y split into two
+ * BF16 words (relative error of a product ~2^-16, FP32 accumulation per CTA, FP64 across CTAs), the first moments and the
+ * scalar sums in FP64.  me_k4_measure + me_k4_moments remain the all-FP64 route. */
+int me_k4_step_measure(me_k4 *e, int64_t n_steps, const double *s_a, double *ts, int64_t ts_row, const double *shift,
+                       double *scratch, int64_t scratch_doubles, double *inc, double *mom_accum, double *snapshot,
+                       void *stream) {
+    if (!e || !e->state || !s_a || !shift || !scratch || !inc) return ME_ERR_INVALID;
+    if (n_steps <= 0) return k4_fail(e, ME_ERR_INVALID, "me_k4_step_measure needs at least one step");
+    if (e->use_v1) return k4_fail(e, ME_ERR_UNSUPPORTED, "the first-version step kernel has no fused measure");
+    if (e->step + (unsigned long long)n_steps >= 0xffffffffull) return k4_fail(e, ME_ERR_INVALID, "step counter overflow");
+    const int max_parts = e->n_sm < 1 ? 1 : e->n_sm;
+    if (scratch_doubles < (int64_t)(max_parts + 1) * partw(e->nc)) return k4_fail(e, ME_ERR_INVALID, "moments scratch too small");
+    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
+    K4Tail tail{ts, (long long)ts_row, shift, scratch};
+    int grid = 0;
+    int rc = k4_launch_steps(e, n_steps, s_a, nullptr, nullptr, nullptr, &tail, &grid, stream);
+    if (rc == ME_OK) {
+        k4_moments_finish(e, scratch, grid, inc, mom_accum, snapshot, stream);
+        cudaError_t ce = cudaGetLastError();
+        if (ce != cudaSuccess) rc = k4_fail(e, ME_ERR_CUDA, std::string("k4_moments: ") + cudaGetErrorString(ce));
+    }
+    cudaSetDevice(prev);
+    if (rc != ME_OK) return rc;
+    e->step += (unsigned long long)n_steps;
+    e->n_measure += 1;
     return ME_OK;
 }
 
@@ -701,11 +757,7 @@ int me_k4_moments(me_k4 *e, const double *shift, double *scratch, int64_t scratc
     int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
     k4_moments_stage1<<<n_parts, 256, 0, (cudaStream_t)stream>>>(e->state, e->cfg.n_chains, e->cfg.n_chains, nc, shift,
                                                                  scratch, per);
-    double *total = scratch + (long long)n_parts * pw;
-    k4_moments_stage2a<<<(pw + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, n_parts, total, nc);
-    k4_moments_stage2b<<<(mw + 127) / 128, 128, 0, (cudaStream_t)stream>>>(total, reinterpret_cast<double2 *>(inc),
-                                                                       reinterpret_cast<double2 *>(mom_accum),
-                                                                       reinterpret_cast<double2 *>(snapshot), nc);
+    k4_moments_finish(e, scratch, n_parts, inc, mom_accum, snapshot, stream);
     cudaError_t ce = cudaGetLastError();
     cudaSetDevice(prev);
     if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_moments: ") + cudaGetErrorString(ce));

@@ -93,6 +93,15 @@ struct StepParams {
     float *dbg_z;                  /* optional [K][ld]: the normals of the FIRST step of the launch (tests / oracle taps) */
     float *dbg_delta;              /* optional [N][ld]: the tensor-core increments of the first step */
     double *dbg_scal;              /* optional [2][ld]: real-parameter normal and accept uniform of the first step */
+    /* fused measure tail (do_measure != 0): after the last step of every tile the epilogue warps take the measurement
+       (means, observable means, time-series row: ME:342-356, 404-414) and the CTA leaves its partial of the pooled moments
+       in mom_part[blockIdx.x] (layout of k4_moments_stage1 in me_k4.cu) */
+    int do_measure, record;
+    long long n_meas_after;        /* measure_step_counter after the increment */
+    double *ts;                    /* time-series block [rows][D + 2][ld] (record != 0) */
+    long long ts_row;
+    const double *shift;           /* [1 + 2 n_c] fixed shift of the pooled moments */
+    double *mom_part;              /* [gridDim.x][4 + N + N N] */
 };
 
 /* state-block word offsets for n_c complex parameters: X (1 + 2 n_c) | E | SIG | MEAN (1 + 2 n_c) | OBSM (2 + n_c) | NACC | STATUS */
@@ -241,6 +250,11 @@ __device__ __forceinline__ double u53(u32 hi, u32 lo) {
     const double b = __hiloint2double(0x43300000 - (53 << 20), (int)(lo >> 6)) - 0.5;
     return a + b;
 }
+/* round-to-nearest-even BF16 bits of a finite float */
+__device__ __forceinline__ u32 bf16_bits_rn(float f) {
+    const u32 b = __float_as_uint(f);
+    return (b + 0x7fffu + ((b >> 16) & 1u)) >> 16;
+}
 /* FP32 accumulator word -> double (F2F.F64.F32, exact) */
 __device__ __forceinline__ double f32_bits_to_f64(u32 f) { return (double)__uint_as_float(f); }
 
@@ -274,9 +288,12 @@ struct Smem {
     alignas(1024) unsigned char zs[TILE * N * 2];           /* A operand (normals), BF16, HALVES stages            */
     alignas(1024) unsigned char ls[N * N * 2];              /* B operand (factor), BF16                            */
     double part[2][EPI_GROUPS][2][TILE];                    /* [step parity][column group][sum][chain] partial sums */
+    double csum[4][N];                                      /* measure tail: per lane quarter, sums over 32 chains of Y     */
+    double cscal[4][4];                                     /*               ... of a, a^2, sigma                            */
     alignas(16) unsigned short ztab[ZTAB_ENTRIES];          /* BF16 quantile table of the generator               8 KB   */
     me::MathTables tables;
     u64 z_full[2], z_empty[2], acc_full[2], acc_empty[2], b_full;
+    u64 y_full, s_done;                                     /* measure tail: moment operands written / moment MMAs complete */
     u32 tmem_slot;
 };
 
@@ -296,6 +313,9 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
     constexpr u32 A_LBO = TILE * 16, B_LBO = N * 16;
     constexpr u32 TCOLS = N < 32 ? 32 : N;        /* TMEM columns per accumulator */
     constexpr u32 IDESC = umma_idesc(N);
+    /* TMEM: two step accumulators + the moment accumulator S of the measure tail (N columns), a power of two in total */
+    constexpr u32 TALLOC = 3 * TCOLS <= 128 ? 128 : (3 * TCOLS <= 256 ? 256 : 512);
+    constexpr u32 Y_LBO = N * 16;                 /* moment operands: [TILE / 8 chain chunks][N rows][8 chains] */
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     S_t &S = *reinterpret_cast<S_t *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -311,9 +331,11 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
             mbar_init(&S.acc_empty[i], EPI_WARPS);
         }
         mbar_init(&S.b_full, 1);
+        mbar_init(&S.y_full, EPI_WARPS);
+        mbar_init(&S.s_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == MMA_WARP) tmem_alloc(&S.tmem_slot, 2 * TCOLS);
+    if (warp == MMA_WARP) tmem_alloc(&S.tmem_slot, TALLOC);
     {                                             /* the generator's quantile table */
         const uint4 *src = reinterpret_cast<const uint4 *>(p.ztab);
         uint4 *dst = reinterpret_cast<uint4 *>(S.ztab);
@@ -408,6 +430,31 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     __syncwarp();
                 }
             }
+            if (p.do_measure) {
+                /* measure tail: S (+)= Yh Yh^T + Yh Yl^T + Yl Yh^T over the 128 chains of the tile (Y = state - shift split
+                   into two BF16 words by the epilogue warps; Yh sits in the normals' buffer, Yl in the state tile, both
+                   free now).  Nobody touches either buffer again before the MMAs have completed (s_done). */
+                if (issuer) {
+                    mbar_wait(&S.y_full, (u32)(t & 1));
+                    tc_fence_after();
+                    const u32 yh = zs_addr, yl = smem_u32(S.xs);
+#pragma unroll
+                    for (int k = 0; k < TILE / 16; k++)
+                        umma_bf16(tmem_base + 2 * TCOLS, umma_desc(yh + 2 * k * Y_LBO, Y_LBO), umma_desc(yh + 2 * k * Y_LBO, Y_LBO),
+                                  IDESC, (t > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < TILE / 16; k++)
+                        umma_bf16(tmem_base + 2 * TCOLS, umma_desc(yh + 2 * k * Y_LBO, Y_LBO), umma_desc(yl + 2 * k * Y_LBO, Y_LBO),
+                                  IDESC, 1u);
+#pragma unroll
+                    for (int k = 0; k < TILE / 16; k++)
+                        umma_bf16(tmem_base + 2 * TCOLS, umma_desc(yl + 2 * k * Y_LBO, Y_LBO), umma_desc(yh + 2 * k * Y_LBO, Y_LBO),
+                                  IDESC, 1u);
+                    umma_commit(&S.s_done);
+                }
+                __syncwarp();
+                mbar_wait(&S.s_done, (u32)(t & 1));
+            }
         }
     } else {
         /* ================================================================== epilogue */
@@ -424,6 +471,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
         if (!(f > 200.0)) f = 200.0;
         const double g_up = p.ratio * (1 - p.target) / f, g_down = p.ratio * p.target / f;
         const double q_first = (double)(g * MODES - NC / 2);     /* wavenumber of this thread's first mode */
+        double col_acc = 0.0, sc_acc[4] = {0.0, 0.0, 0.0, 0.0};  /* measure tail: sums over this CTA's tiles */
         long long it = 0;
         for (long long t = 0; t < n_tiles; t++) {
             const long long base = range_lo + t * TILE;
@@ -561,12 +609,133 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     if (p.last_accept && n_steps > 0) p.last_accept[ch] = (unsigned char)accepted_last;
                 }
             }
+            if (p.do_measure) {
+                /* ---------------------------------------------------------------- measure tail of this tile */
+                const double dn = (double)p.n_meas_after, inv_n = 1.0 / dn, shrink = (dn - 1.0) * inv_n;
+                double *row = p.record ? p.ts + p.ts_row * (long long)(L.D + 2) * ld + ch : nullptr;
+                u32 ylp[COLS / 2];                            /* low BF16 words of this thread's Y, two per register */
+                double keep[(COLS + 31) / 32];
+#pragma unroll
+                for (int i = 0; i < (COLS + 31) / 32; i++) keep[i] = 0.0;
+                unsigned char *yh_row = S.zs + (m >> 3) * Y_LBO + (m & 7) * 2;
+#pragma unroll
+                for (int jj = 0; jj < MODES; jj++) {
+                    const int j = g * MODES + jj;
+                    double y[2] = {0.0, 0.0};
+                    if (act) {
+                        const double re = S.xs[2 * j][m], im = S.xs[2 * j + 1][m];
+                        /* running means and observable means (ME:404-414), this chain's words */
+                        double *mr = &p.state[(long long)(L.MEAN + 1 + j) * ld + ch];
+                        double *mi = &p.state[(long long)(L.MEAN + 1 + NC + j) * ld + ch];
+                        double *ob = &p.state[(long long)(L.OBSM + 1 + j) * ld + ch];
+                        *mr = fma(re, inv_n, *mr * shrink);
+                        *mi = fma(im, inv_n, *mi * shrink);
+                        *ob = fma(hypot(re, im), inv_n, *ob * shrink);
+                        if (row) {
+                            __stcs(row + (long long)(1 + j) * ld, re);
+                            __stcs(row + (long long)(1 + NC + j) * ld, im);
+                        }
+                        y[0] = re - p.shift[1 + j];
+                        y[1] = im - p.shift[1 + NC + j];
+                    }
+                    u32 lo_pair = 0;
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int n = 2 * j + r;                 /* interleaved coordinate = operand row */
+                        const u32 hb = bf16_bits_rn((float)y[r]);
+                        const double rest = y[r] - (double)__uint_as_float(hb << 16);
+                        const u32 lb = bf16_bits_rn((float)rest);
+                        *reinterpret_cast<unsigned short *>(yh_row + n * 16) = (unsigned short)hb;
+                        lo_pair |= lb << (16 * r);
+                        /* column sum over the 32 chains of this warp: butterfly, every lane ends with the total */
+                        double v = y[r];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        const int c = 2 * jj + r;
+                        if ((c & 31) == lane) keep[c >> 5] = v;
+                    }
+                    ylp[jj] = lo_pair;
+                }
+#pragma unroll
+                for (int i = 0; i < (COLS + 31) / 32; i++)
+                    if (32 * i + lane < COLS) S.csum[q4][g * COLS + 32 * i + lane] = keep[i];
+                if (g == 0) {
+                    double va = 0.0, va2 = 0.0, vs = 0.0;
+                    if (act) {
+                        double *mp = &p.state[(long long)L.MEAN * ld + ch];
+                        double *o0 = &p.state[(long long)L.OBSM * ld + ch], *o1 = &p.state[(long long)(L.OBSM + 1 + NC) * ld + ch];
+                        *mp = fma(a, inv_n, *mp * shrink);
+                        *o0 = fma(fabs(a), inv_n, *o0 * shrink);
+                        *o1 = fma(a * a, inv_n, *o1 * shrink);
+                        if (row) {
+                            __stcs(row, a);
+                            __stcs(row + (long long)L.D * ld, e);
+                            __stcs(row + (long long)(L.D + 1) * ld, sig);
+                        }
+                        va = a - p.shift[0]; va2 = va * va; vs = sig;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        va += __shfl_xor_sync(0xffffffffu, va, o);
+                        va2 += __shfl_xor_sync(0xffffffffu, va2, o);
+                        vs += __shfl_xor_sync(0xffffffffu, vs, o);
+                    }
+                    if (lane == 0) { S.cscal[q4][0] = va; S.cscal[q4][1] = va2; S.cscal[q4][2] = vs; }
+                }
+                named_barrier(6, 32 * EPI_WARPS);            /* every epilogue thread is done with the state tile */
+                /* low words into the (now free) state tile, same operand layout as the high words */
+                unsigned char *yl_row = reinterpret_cast<unsigned char *>(&S.xs[0][0]) + (m >> 3) * Y_LBO + (m & 7) * 2;
+#pragma unroll
+                for (int jj = 0; jj < MODES; jj++) {
+                    const int j = g * MODES + jj;
+                    *reinterpret_cast<unsigned short *>(yl_row + (2 * j) * 16) = (unsigned short)(ylp[jj] & 0xffffu);
+                    *reinterpret_cast<unsigned short *>(yl_row + (2 * j + 1) * 16) = (unsigned short)(ylp[jj] >> 16);
+                }
+                /* the CTA's running sums: thread n < N owns coordinate n, thread 0 the scalars (fixed order) */
+                if (tid < N) col_acc += (S.csum[0][tid] + S.csum[1][tid]) + (S.csum[2][tid] + S.csum[3][tid]);
+                if (tid == 0) {
+                    sc_acc[0] += (double)cnt;
+                    sc_acc[1] += (S.cscal[0][2] + S.cscal[1][2]) + (S.cscal[2][2] + S.cscal[3][2]);
+                    sc_acc[2] += (S.cscal[0][0] + S.cscal[1][0]) + (S.cscal[2][0] + S.cscal[3][0]);
+                    sc_acc[3] += (S.cscal[0][1] + S.cscal[1][1]) + (S.cscal[2][1] + S.cscal[3][1]);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.y_full);
+                mbar_wait(&S.s_done, (u32)(t & 1));           /* the moment MMAs have read both operand buffers */
+            }
+        }
+        if (p.do_measure) {
+            /* ------------------------------------------------------------ this CTA's partial of the pooled moments */
+            double *out = p.mom_part + (long long)blockIdx.x * (4 + N + N * N);
+            auto stage_row = [](int i) { return (i & 1) ? NC + (i >> 1) : (i >> 1); };   /* interleaved -> [Re; Im] order */
+            if (tid == 0) { out[0] = sc_acc[0]; out[1] = sc_acc[1]; out[2] = sc_acc[2]; out[3] = sc_acc[3]; }
+            if (tid < N) out[4 + stage_row(tid)] = col_acc;
+            tc_fence_after();
+            const int n_row = 32 * q4 + lane;                  /* TMEM lane = row of S (interleaved coordinate) */
+            if (32 * q4 < N) {
+                const u32 scol = tmem_base + 2 * TCOLS + ((u32)(32 * q4) << 16) + (u32)(g * COLS);
+#pragma unroll
+                for (int c = 0; c < COLS; c += LDCH) {
+                    u32 raw[LDCH];
+                    if (n_tiles > 0) { TmemLd<LDCH>::ld(scol + (u32)c, raw); tmem_ld_wait(); }
+                    else {
+#pragma unroll
+                        for (int k = 0; k < LDCH; k++) raw[k] = 0u;
+                    }
+                    if (n_row < N) {
+#pragma unroll
+                        for (int k = 0; k < LDCH; k++)
+                            out[4 + N + stage_row(n_row) * N + stage_row(g * COLS + c + k)] = f32_bits_to_f64(raw[k]);
+                    }
+                }
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 2 * TCOLS);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, TALLOC);
 }
 
 /* -------------------------------------------------------------------------------------------- initialisation (ME:40-125) */

@@ -17,6 +17,7 @@ measure b use the factor of measure b-1.  The lag is deterministic and only shap
 ``async_refresh=False`` gives the strictly sequential schedule.
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -152,6 +153,8 @@ class SharedCovarianceEngine:
                                           self._stream()))
         self.record = bool(record)
         self._ts_chunks, self._ts_chunk_rows = [], int(ts_chunk_rows)
+        self._fused_measure = not (os.environ.get("ME_K4_SPLIT_MEASURE", "0") not in ("", "0")
+                                   or os.environ.get("ME_K4_V1", "0") not in ("", "0"))
 
     @classmethod
     def from_reference_arguments(cls, energy_functions, reject_condition=None, initial_real_params=None,
@@ -286,7 +289,31 @@ class SharedCovarianceEngine:
             self._launch(self._lib.me_k4_measure(self._h, _ptr(t), row, self._stream()))
         else:
             self._launch(self._lib.me_k4_measure(self._h, None, 0, self._stream()))
-        n = self.measure_step_counter
+        inc, snap, parity, fused = self._moment_buffers()
+        self._launch(self._lib.me_k4_moments(self._h, _ptr(self._shift), _ptr(self._scratch), self._scratch.numel(),
+                                             _ptr(inc), _ptr(self._mom) if fused else None,
+                                             _ptr(snap) if fused else None, self._stream()))
+        self.launch_count += 2
+        self._after_moments(inc, snap, parity, fused)
+
+    def step_measure(self, k):
+        """``k`` x step_all() then measure() as ONE launch of the step kernel (+ the two small reductions of the pooled
+        moments): the measurement and this CTA's share of the pooled moments are taken by the epilogue warps while the
+        chain states are still in shared memory, the second moments on the tensor cores (include/me_b200.h,
+        me_k4_step_measure).  step(k); measure() is the same schedule with all-FP64 moments."""
+        self._adopt_refresh()
+        t, row = self._ts_slot() if self.record else (None, 0)
+        inc, snap, parity, fused = self._moment_buffers()
+        self._launch(self._lib.me_k4_step_measure(self._h, int(k), _ptr(self._s_a), _ptr(t), row, _ptr(self._shift),
+                                                  _ptr(self._scratch), self._scratch.numel(), _ptr(inc),
+                                                  _ptr(self._mom) if fused else None, _ptr(snap) if fused else None,
+                                                  self._stream()))
+        self.launch_count += 2
+        if self._in_flight is not None:           # the refresh launched at the last measure becomes adoptable
+            self._ready, self._in_flight = self._in_flight, None
+        self._after_moments(inc, snap, parity, fused)
+
+    def _moment_buffers(self):
         parity = self._measure_count % 2
         self._measure_count += 1
         inc, snap = self._incs[parity], self._snaps[parity]
@@ -296,10 +323,11 @@ class SharedCovarianceEngine:
             main.wait_event(self._snap_events[parity])
             self._snap_events[parity] = None
         fused = not self._distributed            # single GPU: the moments kernel advances mom and writes the snapshot
-        self._launch(self._lib.me_k4_moments(self._h, _ptr(self._shift), _ptr(self._scratch), self._scratch.numel(),
-                                             _ptr(inc), _ptr(self._mom) if fused else None,
-                                             _ptr(snap) if fused else None, self._stream()))
-        self.launch_count += 2
+        return inc, snap, parity, fused
+
+    def _after_moments(self, inc, snap, parity, fused):
+        n = self.measure_step_counter
+        main = torch.cuda.current_stream(self.device)
         refresh = n > 50                                                                      # ME:389,396
         if fused and not refresh:
             return
@@ -339,10 +367,18 @@ class SharedCovarianceEngine:
         if refresh:
             self._in_flight = (ev, idx)
 
-    def run(self, n_measures, steps_per_measure):
+    def run(self, n_measures, steps_per_measure, fused_measure=None):
+        """``n_measures`` x [``steps_per_measure`` x step_all(), measure()].  By default every block is one step_measure()
+        launch; ``fused_measure=False`` (or ME_K4_SPLIT_MEASURE=1) keeps step() and measure() as separate kernels with
+        all-FP64 pooled moments."""
+        if fused_measure is None:
+            fused_measure = self._fused_measure
         for _ in range(int(n_measures)):
-            self.step(int(steps_per_measure))
-            self.measure()
+            if fused_measure and steps_per_measure >= 1:
+                self.step_measure(int(steps_per_measure))
+            else:
+                self.step(int(steps_per_measure))
+                self.measure()
 
     # ------------------------------------------------------------------ reads (reference attribute names)
     def _pooled(self, t):

@@ -44,7 +44,13 @@ spare = torch.zeros_like(eng._factors[0])
 spare_sa = torch.ones(1, dtype=torch.float64, device=eng.device)
 timed("k4_refactor", lambda: L.me_k4_refactor(eng._h, _ptr(eng._mom), _ptr(eng._inc_full), 0, _ptr(eng._cov_c), _ptr(eng._cov_a),
                                               _ptr(spare), _ptr(spare_sa), _ptr(eng._psd_status), eng._stream()))
-us = timed("run(1, 10): steps + measure + adaptation", lambda: eng.run(1, 10))
+if hasattr(L, "me_k4_step_measure"):
+    timed("k4_steps x10 + measure tail + stage 2a/2b", lambda: L.me_k4_step_measure(
+        eng._h, 10, _ptr(eng._s_a), None, 0, _ptr(eng._shift), _ptr(eng._scratch), eng._scratch.numel(), _ptr(eng._inc_full),
+        None, None, eng._stream()))
+us = timed("run(1, 10), separate measure / FP64 moments kernels", lambda: eng.run(1, 10, fused_measure=False))
+print("   -> %.3e chain-steps/s" % (n * 10 / us * 1e6))
+us = timed("run(1, 10): one-launch block + adaptation", lambda: eng.run(1, 10))
 print("   -> with measure every 10 (refresh on the side stream): %.3e chain-steps/s" % (n * 10 / us * 1e6))
 seq = me.SharedCovarianceEngine(energy_consts=(10.0, -1.0, 0.05, 1.0), temp=.1, n_chains=n, seed=1, record=False,
                                 async_refresh=False)

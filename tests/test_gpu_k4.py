@@ -161,7 +161,7 @@ def test_pooled_moments_and_factor_match_float64_linear_algebra():
     import metropolisengine_b200 as me
     n = 128 * 37 + 128                              # uneven split over the moment CTAs
     eng = me.SharedCovarianceEngine(temp=.1, n_chains=n, seed=4, record=False, sampling_width=0.05)
-    eng.run(52, 4)                                  # crosses n > 50: the factor has been rebuilt from pooled moments
+    eng.run(52, 4, fused_measure=False)             # crosses n > 50: the factor has been rebuilt from pooled moments
     eng.synchronize_refresh()                       # adopt the refresh of the last measure (it runs on a side stream)
     torch.cuda.synchronize()
     lay = eng._lay
@@ -191,6 +191,57 @@ def test_pooled_moments_and_factor_match_float64_linear_algebra():
     got = eng._factor.float()
     assert (got - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()      # equal up to one BF16 rounding
     assert int(eng._psd_status.item()) == 0
+
+
+@pytest.mark.parametrize("nc,n_chains,async_refresh", [(64, 128 * 300, True), (64, 128 * 9, False), (16, 128 * 150, True),
+                                                       (32, 128 * 301, False), (8, 128 * 40, True)])
+def test_one_launch_block_equals_steps_then_measure(nc, n_chains, async_refresh):
+    """me_k4_step_measure (k steps + the measurement + the CTA partials of the pooled moments in ONE launch) against
+    me_k4_step; me_k4_measure; me_k4_moments on a second engine with the same seed.  Until the first factor refresh (50
+    blocks) the chains see identical proposals, so states, means, observable means and time series must be bit-identical;
+    the tensor-core second moments (two BF16 words per coordinate) agree with the FP64 ones to ~1e-6 of the diagonal
+    scale, first moments and scalar sums to FP64 rounding; so do the covariance and (up to single BF16 roundings) the
+    factor built from them at the 50th block."""
+    import metropolisengine_b200 as me
+    rng = np.random.default_rng(nc)
+    x0c = 0.05 * (rng.standard_normal((n_chains, nc)) + 1j * rng.standard_normal((n_chains, nc)))
+    x0r = 0.1 * rng.standard_normal((n_chains, 1))
+    kw = dict(temp=.1, n_chains=n_chains, seed=77, record=True, sampling_width=0.004, n_complex=nc, ts_chunk_rows=64,
+              initial_real_params=x0r, initial_complex_params=x0c, async_refresh=async_refresh)
+    a, b = me.SharedCovarianceEngine(**kw), me.SharedCovarianceEngine(**kw)
+    lay = a._lay
+    for blocks, k in ((7, 3), (43, 1)):
+        a.run(blocks, k, fused_measure=True)
+        b.run(blocks, k, fused_measure=False)
+        torch.cuda.synchronize()
+        assert a.measure_step_counter == b.measure_step_counter and a.steps_done == b.steps_done
+        assert torch.equal(a.state, b.state)          # parameters, energy, widths, means, observable means, counts
+        assert torch.equal(a.time_series, b.time_series)
+        ia, ib = a._inc_full, b._inc_full
+        nw = 4 + nc
+        assert ia[0].real.item() == n_chains
+        scale1 = b.state[lay.X:lay.X + lay.D].abs().sum(dim=1).max().item()
+        assert torch.allclose(ia[:nw], ib[:nw], rtol=1e-12, atol=1e-13 * scale1)
+        sa, sb = ia[nw:].reshape(nc, nc), ib[nw:].reshape(nc, nc)
+        d = torch.sqrt(sb.diagonal().real)
+        rel = ((sa - sb).abs() / torch.outer(d, d)).max().item()
+        assert rel < 2e-5, rel
+    # the 50th block crossed n > 50: covariance and factor rebuilt from the accumulated moments
+    a.synchronize_refresh(); b.synchronize_refresh()
+    torch.cuda.synchronize()
+    assert a.measure_step_counter == 51
+    ca, cb = a._cov_c, b._cov_c
+    d = torch.sqrt(cb.diagonal().real)
+    assert ((ca - cb).abs() / torch.outer(d, d)).max().item() < 2e-5
+    assert torch.allclose(a._cov_a, b._cov_a, rtol=1e-12)
+    fa, fb = a._factor.float(), b._factor.float()
+    assert (fa - fb).abs().max().item() <= 2 ** -7 * fb.abs().max().item()
+    assert (fa != fb).float().mean().item() < 0.05
+    assert int(a._psd_status.item()) == 0
+    # and the sampler keeps going on the tensor-core moments
+    a.run(20, 5)
+    torch.cuda.synchronize()
+    assert int(a._psd_status.item()) == 0 and 0.05 < a.acceptance_rate < 0.9
 
 
 def test_asynchronous_factor_refresh_is_deterministic_and_lags_by_one_measure():
