@@ -290,6 +290,7 @@ struct Smem {
     double part[2][EPI_GROUPS][2][TILE];                    /* [step parity][column group][sum][chain] partial sums */
     double csum[4][N];                                      /* measure tail: per lane quarter, sums over 32 chains of Y     */
     double cscal[4][4];                                     /*               ... of a, a^2, sigma                            */
+    double shift_s[N + 2];                                  /*               the moments' shift: [Re/Im interleaved N | a]   */
     alignas(16) unsigned short ztab[ZTAB_ENTRIES];          /* BF16 quantile table of the generator               8 KB   */
     me::MathTables tables;
     u64 z_full[2], z_empty[2], acc_full[2], acc_empty[2], b_full;
@@ -340,6 +341,10 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
         const uint4 *src = reinterpret_cast<const uint4 *>(p.ztab);
         uint4 *dst = reinterpret_cast<uint4 *>(S.ztab);
         for (int i = tid; i < ZTAB_ENTRIES * 2 / 16; i += THREADS) dst[i] = src[i];
+    }
+    if (p.do_measure) {                           /* the moments' shift, in the interleaved coordinate order of the tile */
+        for (int i = tid; i < N; i += THREADS) S.shift_s[i] = p.shift[1 + ((i & 1) ? NC + (i >> 1) : (i >> 1))];
+        if (tid == 0) S.shift_s[N] = p.shift[0];
     }
     if (!p.use_tma) {                             /* plain staging of the factor (tensor map not available) */
         const uint4 *src = reinterpret_cast<const uint4 *>(p.factor);
@@ -618,43 +623,55 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
 #pragma unroll
                 for (int i = 0; i < (COLS + 31) / 32; i++) keep[i] = 0.0;
                 unsigned char *yh_row = S.zs + (m >> 3) * Y_LBO + (m & 7) * 2;
+                constexpr int JB = MODES < 8 ? MODES : 8;     /* modes per batch: the batch's global loads are all in flight
+                                                                 before the first store (stores to the state block may alias) */
 #pragma unroll
-                for (int jj = 0; jj < MODES; jj++) {
-                    const int j = g * MODES + jj;
-                    double y[2] = {0.0, 0.0};
+                for (int jb = 0; jb < MODES; jb += JB) {
+                    double mr[JB], mi[JB], ob[JB];
                     if (act) {
-                        const double re = S.xs[2 * j][m], im = S.xs[2 * j + 1][m];
-                        /* running means and observable means (ME:404-414), this chain's words */
-                        double *mr = &p.state[(long long)(L.MEAN + 1 + j) * ld + ch];
-                        double *mi = &p.state[(long long)(L.MEAN + 1 + NC + j) * ld + ch];
-                        double *ob = &p.state[(long long)(L.OBSM + 1 + j) * ld + ch];
-                        *mr = fma(re, inv_n, *mr * shrink);
-                        *mi = fma(im, inv_n, *mi * shrink);
-                        *ob = fma(hypot(re, im), inv_n, *ob * shrink);
-                        if (row) {
-                            __stcs(row + (long long)(1 + j) * ld, re);
-                            __stcs(row + (long long)(1 + NC + j) * ld, im);
+#pragma unroll
+                        for (int b = 0; b < JB; b++) {
+                            const int j = g * MODES + jb + b;
+                            mr[b] = p.state[(long long)(L.MEAN + 1 + j) * ld + ch];
+                            mi[b] = p.state[(long long)(L.MEAN + 1 + NC + j) * ld + ch];
+                            ob[b] = p.state[(long long)(L.OBSM + 1 + j) * ld + ch];
                         }
-                        y[0] = re - p.shift[1 + j];
-                        y[1] = im - p.shift[1 + NC + j];
                     }
-                    u32 lo_pair = 0;
 #pragma unroll
-                    for (int r = 0; r < 2; r++) {
-                        const int n = 2 * j + r;                 /* interleaved coordinate = operand row */
-                        const u32 hb = bf16_bits_rn((float)y[r]);
-                        const double rest = y[r] - (double)__uint_as_float(hb << 16);
-                        const u32 lb = bf16_bits_rn((float)rest);
-                        *reinterpret_cast<unsigned short *>(yh_row + n * 16) = (unsigned short)hb;
-                        lo_pair |= lb << (16 * r);
-                        /* column sum over the 32 chains of this warp: butterfly, every lane ends with the total */
-                        double v = y[r];
+                    for (int b = 0; b < JB; b++) {
+                        const int jj = jb + b, j = g * MODES + jj;
+                        double y[2] = {0.0, 0.0};
+                        if (act) {
+                            const double re = S.xs[2 * j][m], im = S.xs[2 * j + 1][m];
+                            /* running means and observable means (ME:404-414), this chain's words */
+                            p.state[(long long)(L.MEAN + 1 + j) * ld + ch] = fma(re, inv_n, mr[b] * shrink);
+                            p.state[(long long)(L.MEAN + 1 + NC + j) * ld + ch] = fma(im, inv_n, mi[b] * shrink);
+                            p.state[(long long)(L.OBSM + 1 + j) * ld + ch] = fma(hypot(re, im), inv_n, ob[b] * shrink);
+                            if (row) {
+                                __stcs(row + (long long)(1 + j) * ld, re);
+                                __stcs(row + (long long)(1 + NC + j) * ld, im);
+                            }
+                            y[0] = re - S.shift_s[2 * j];
+                            y[1] = im - S.shift_s[2 * j + 1];
+                        }
+                        u32 lo_pair = 0;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                        const int c = 2 * jj + r;
-                        if ((c & 31) == lane) keep[c >> 5] = v;
+                        for (int r = 0; r < 2; r++) {
+                            const int n = 2 * j + r;                 /* interleaved coordinate = operand row */
+                            const u32 hb = bf16_bits_rn((float)y[r]);
+                            const double rest = y[r] - (double)__uint_as_float(hb << 16);
+                            const u32 lb = bf16_bits_rn((float)rest);
+                            *reinterpret_cast<unsigned short *>(yh_row + n * 16) = (unsigned short)hb;
+                            lo_pair |= lb << (16 * r);
+                            /* column sum over the 32 chains of this warp: butterfly, every lane ends with the total */
+                            double v = y[r];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            const int c = 2 * jj + r;
+                            if ((c & 31) == lane) keep[c >> 5] = v;
+                        }
+                        ylp[jj] = lo_pair;
                     }
-                    ylp[jj] = lo_pair;
                 }
 #pragma unroll
                 for (int i = 0; i < (COLS + 31) / 32; i++)
@@ -664,15 +681,16 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     if (act) {
                         double *mp = &p.state[(long long)L.MEAN * ld + ch];
                         double *o0 = &p.state[(long long)L.OBSM * ld + ch], *o1 = &p.state[(long long)(L.OBSM + 1 + NC) * ld + ch];
-                        *mp = fma(a, inv_n, *mp * shrink);
-                        *o0 = fma(fabs(a), inv_n, *o0 * shrink);
-                        *o1 = fma(a * a, inv_n, *o1 * shrink);
+                        const double vm = *mp, v0 = *o0, v1 = *o1;
+                        *mp = fma(a, inv_n, vm * shrink);
+                        *o0 = fma(fabs(a), inv_n, v0 * shrink);
+                        *o1 = fma(a * a, inv_n, v1 * shrink);
                         if (row) {
                             __stcs(row, a);
                             __stcs(row + (long long)L.D * ld, e);
                             __stcs(row + (long long)(L.D + 1) * ld, sig);
                         }
-                        va = a - p.shift[0]; va2 = va * va; vs = sig;
+                        va = a - S.shift_s[N]; va2 = va * va; vs = sig;
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {

@@ -216,7 +216,7 @@ def test_one_launch_block_equals_steps_then_measure(nc, n_chains, async_refresh)
         torch.cuda.synchronize()
         assert a.measure_step_counter == b.measure_step_counter and a.steps_done == b.steps_done
         assert torch.equal(a.state, b.state)          # parameters, energy, widths, means, observable means, counts
-        assert torch.equal(a.time_series, b.time_series)
+        assert torch.equal(a.time_series(), b.time_series())
         ia, ib = a._inc_full, b._inc_full
         nw = 4 + nc
         assert ia[0].real.item() == n_chains
