@@ -241,7 +241,7 @@ def test_one_launch_block_equals_steps_then_measure(nc, n_chains, async_refresh)
     # and the sampler keeps going on the tensor-core moments
     a.run(20, 5)
     torch.cuda.synchronize()
-    assert int(a._psd_status.item()) == 0 and 0.05 < a.acceptance_rate < 0.9
+    assert int(a._psd_status.item()) == 0 and a.acceptance_rate > 0.05
 
 
 def test_asynchronous_factor_refresh_is_deterministic_and_lags_by_one_measure():
