@@ -91,7 +91,7 @@ __global__ void k4_measure(MeasureParams p) {
     *mr = fma(re, inv_n, *mr * shrink);
     *mi = fma(im, inv_n, *mi * shrink);
     double *ob = &p.state[(long long)(L.OBSM + 1 + j) * ld + ch];
-    *ob = fma(hypot(re, im), inv_n, *ob * shrink);
+    *ob = fma(k4::cabs_fast(re, im), inv_n, *ob * shrink);
     if (row) {
         __stcs(row + (long long)(1 + j) * ld, re);
         __stcs(row + (long long)(1 + nc + j) * ld, im);

@@ -250,6 +250,12 @@ __device__ __forceinline__ double u53(u32 hi, u32 lo) {
     const double b = __hiloint2double(0x43300000 - (53 << 20), (int)(lo >> 6)) - 0.5;
     return a + b;
 }
+/* |c| of a complex parameter for the observable means (ME:412-414): sqrt(re^2 + im^2) through MUFU.RSQ64H + Newton
+ * (relative error < 2^-52.5) where the sum of squares is comfortably normal, libdevice hypot otherwise (zero, tiny) */
+__device__ __forceinline__ double cabs_fast(double re, double im) {
+    const double w = fma(re, re, im * im);
+    return (w > 1e-280 && w < 1e280) ? me::sqrt_pos_full(w) : hypot(re, im);
+}
 /* round-to-nearest-even BF16 bits of a finite float */
 __device__ __forceinline__ u32 bf16_bits_rn(float f) {
     const u32 b = __float_as_uint(f);
@@ -288,8 +294,8 @@ struct Smem {
     alignas(1024) unsigned char zs[TILE * N * 2];           /* A operand (normals), BF16, HALVES stages            */
     alignas(1024) unsigned char ls[N * N * 2];              /* B operand (factor), BF16                            */
     double part[2][EPI_GROUPS][2][TILE];                    /* [step parity][column group][sum][chain] partial sums */
-    double csum[4][N];                                      /* measure tail: per lane quarter, sums over 32 chains of Y     */
-    double cscal[4][4];                                     /*               ... of a, a^2, sigma                            */
+    alignas(128) unsigned short ones[TILE / 8][16][8];      /* measure tail: a B operand of ones (first moments = Y . 1)     */
+    double cscal[4][4];                                     /*               per lane quarter, sums of a, a^2, sigma         */
     double shift_s[N + 2];                                  /*               the moments' shift: [Re/Im interleaved N | a]   */
     alignas(16) unsigned short ztab[ZTAB_ENTRIES];          /* BF16 quantile table of the generator               8 KB   */
     me::MathTables tables;
@@ -315,7 +321,8 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
     constexpr u32 TCOLS = N < 32 ? 32 : N;        /* TMEM columns per accumulator */
     constexpr u32 IDESC = umma_idesc(N);
     /* TMEM: two step accumulators + the moment accumulator S of the measure tail (N columns), a power of two in total */
-    constexpr u32 TALLOC = 3 * TCOLS <= 128 ? 128 : (3 * TCOLS <= 256 ? 256 : 512);
+    constexpr u32 SCOL = 2 * TCOLS, CCOL = SCOL + N;          /* S, and 16 (identical) columns of first moments */
+    constexpr u32 TALLOC = CCOL + 16 <= 128 ? 128 : (CCOL + 16 <= 256 ? 256 : 512);
     constexpr u32 Y_LBO = N * 16;                 /* moment operands: [TILE / 8 chain chunks][N rows][8 chains] */
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     S_t &S = *reinterpret_cast<S_t *>(smem_raw);
@@ -343,8 +350,10 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
         for (int i = tid; i < ZTAB_ENTRIES * 2 / 16; i += THREADS) dst[i] = src[i];
     }
     if (p.do_measure) {                           /* the moments' shift, in the interleaved coordinate order of the tile */
+        for (int i = tid; i < (TILE / 8) * 16 * 8; i += THREADS) (&S.ones[0][0][0])[i] = 0x3f80;     /* BF16 1.0 */
         for (int i = tid; i < N; i += THREADS) S.shift_s[i] = p.shift[1 + ((i & 1) ? NC + (i >> 1) : (i >> 1))];
         if (tid == 0) S.shift_s[N] = p.shift[0];
+        fence_async_smem();
     }
     if (!p.use_tma) {                             /* plain staging of the factor (tensor map not available) */
         const uint4 *src = reinterpret_cast<const uint4 *>(p.factor);
@@ -442,19 +451,21 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                 if (issuer) {
                     mbar_wait(&S.y_full, (u32)(t & 1));
                     tc_fence_after();
-                    const u32 yh = zs_addr, yl = smem_u32(S.xs);
+                    const u32 yh = zs_addr, yl = smem_u32(S.xs), on = smem_u32(S.ones);
+                    constexpr u32 IDESC1 = umma_idesc(16);
 #pragma unroll
-                    for (int k = 0; k < TILE / 16; k++)
-                        umma_bf16(tmem_base + 2 * TCOLS, umma_desc(yh + 2 * k * Y_LBO, Y_LBO), umma_desc(yh + 2 * k * Y_LBO, Y_LBO),
-                                  IDESC, (t > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TILE / 16; k++) {
+                        const u64 dh = umma_desc(yh + 2 * k * Y_LBO, Y_LBO), d1 = umma_desc(on + 2 * k * 256, 256);
+                        umma_bf16(tmem_base + SCOL, dh, dh, IDESC, (t > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(tmem_base + CCOL, dh, d1, IDESC1, (t > 0 || k > 0) ? 1u : 0u);
+                    }
 #pragma unroll
-                    for (int k = 0; k < TILE / 16; k++)
-                        umma_bf16(tmem_base + 2 * TCOLS, umma_desc(yh + 2 * k * Y_LBO, Y_LBO), umma_desc(yl + 2 * k * Y_LBO, Y_LBO),
-                                  IDESC, 1u);
-#pragma unroll
-                    for (int k = 0; k < TILE / 16; k++)
-                        umma_bf16(tmem_base + 2 * TCOLS, umma_desc(yl + 2 * k * Y_LBO, Y_LBO), umma_desc(yh + 2 * k * Y_LBO, Y_LBO),
-                                  IDESC, 1u);
+                    for (int k = 0; k < TILE / 16; k++) {
+                        const u64 dh = umma_desc(yh + 2 * k * Y_LBO, Y_LBO), dl = umma_desc(yl + 2 * k * Y_LBO, Y_LBO);
+                        umma_bf16(tmem_base + SCOL, dh, dl, IDESC, 1u);
+                        umma_bf16(tmem_base + SCOL, dl, dh, IDESC, 1u);
+                        umma_bf16(tmem_base + CCOL, dl, umma_desc(on + 2 * k * 256, 256), IDESC1, 1u);
+                    }
                     umma_commit(&S.s_done);
                 }
                 __syncwarp();
@@ -476,7 +487,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
         if (!(f > 200.0)) f = 200.0;
         const double g_up = p.ratio * (1 - p.target) / f, g_down = p.ratio * p.target / f;
         const double q_first = (double)(g * MODES - NC / 2);     /* wavenumber of this thread's first mode */
-        double col_acc = 0.0, sc_acc[4] = {0.0, 0.0, 0.0, 0.0};  /* measure tail: sums over this CTA's tiles */
+        double sc_acc[4] = {0.0, 0.0, 0.0, 0.0};                 /* measure tail: scalar sums over this CTA's tiles */
         long long it = 0;
         for (long long t = 0; t < n_tiles; t++) {
             const long long base = range_lo + t * TILE;
@@ -619,9 +630,6 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                 const double dn = (double)p.n_meas_after, inv_n = 1.0 / dn, shrink = (dn - 1.0) * inv_n;
                 double *row = p.record ? p.ts + p.ts_row * (long long)(L.D + 2) * ld + ch : nullptr;
                 u32 ylp[COLS / 2];                            /* low BF16 words of this thread's Y, two per register */
-                double keep[(COLS + 31) / 32];
-#pragma unroll
-                for (int i = 0; i < (COLS + 31) / 32; i++) keep[i] = 0.0;
                 unsigned char *yh_row = S.zs + (m >> 3) * Y_LBO + (m & 7) * 2;
                 constexpr int JB = MODES < 8 ? MODES : 8;     /* modes per batch: the batch's global loads are all in flight
                                                                  before the first store (stores to the state block may alias) */
@@ -646,7 +654,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                             /* running means and observable means (ME:404-414), this chain's words */
                             p.state[(long long)(L.MEAN + 1 + j) * ld + ch] = fma(re, inv_n, mr[b] * shrink);
                             p.state[(long long)(L.MEAN + 1 + NC + j) * ld + ch] = fma(im, inv_n, mi[b] * shrink);
-                            p.state[(long long)(L.OBSM + 1 + j) * ld + ch] = fma(hypot(re, im), inv_n, ob[b] * shrink);
+                            p.state[(long long)(L.OBSM + 1 + j) * ld + ch] = fma(cabs_fast(re, im), inv_n, ob[b] * shrink);
                             if (row) {
                                 __stcs(row + (long long)(1 + j) * ld, re);
                                 __stcs(row + (long long)(1 + NC + j) * ld, im);
@@ -663,19 +671,10 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                             const u32 lb = bf16_bits_rn((float)rest);
                             *reinterpret_cast<unsigned short *>(yh_row + n * 16) = (unsigned short)hb;
                             lo_pair |= lb << (16 * r);
-                            /* column sum over the 32 chains of this warp: butterfly, every lane ends with the total */
-                            double v = y[r];
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                            const int c = 2 * jj + r;
-                            if ((c & 31) == lane) keep[c >> 5] = v;
                         }
                         ylp[jj] = lo_pair;
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < (COLS + 31) / 32; i++)
-                    if (32 * i + lane < COLS) S.csum[q4][g * COLS + 32 * i + lane] = keep[i];
                 if (g == 0) {
                     double va = 0.0, va2 = 0.0, vs = 0.0;
                     if (act) {
@@ -709,8 +708,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     *reinterpret_cast<unsigned short *>(yl_row + (2 * j) * 16) = (unsigned short)(ylp[jj] & 0xffffu);
                     *reinterpret_cast<unsigned short *>(yl_row + (2 * j + 1) * 16) = (unsigned short)(ylp[jj] >> 16);
                 }
-                /* the CTA's running sums: thread n < N owns coordinate n, thread 0 the scalars (fixed order) */
-                if (tid < N) col_acc += (S.csum[0][tid] + S.csum[1][tid]) + (S.csum[2][tid] + S.csum[3][tid]);
+                /* the CTA's running scalar sums (fixed order) */
                 if (tid == 0) {
                     sc_acc[0] += (double)cnt;
                     sc_acc[1] += (S.cscal[0][2] + S.cscal[1][2]) + (S.cscal[2][2] + S.cscal[3][2]);
@@ -728,11 +726,17 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
             double *out = p.mom_part + (long long)blockIdx.x * (4 + N + N * N);
             auto stage_row = [](int i) { return (i & 1) ? NC + (i >> 1) : (i >> 1); };   /* interleaved -> [Re; Im] order */
             if (tid == 0) { out[0] = sc_acc[0]; out[1] = sc_acc[1]; out[2] = sc_acc[2]; out[3] = sc_acc[3]; }
-            if (tid < N) out[4 + stage_row(tid)] = col_acc;
             tc_fence_after();
             const int n_row = 32 * q4 + lane;                  /* TMEM lane = row of S (interleaved coordinate) */
             if (32 * q4 < N) {
-                const u32 scol = tmem_base + 2 * TCOLS + ((u32)(32 * q4) << 16) + (u32)(g * COLS);
+                if (g == 0) {                                  /* first moments: column CCOL of this lane */
+                    u32 raw[4] = {0u, 0u, 0u, 0u};
+                    if (n_tiles > 0) { TmemLd<4>::ld(tmem_base + CCOL + ((u32)(32 * q4) << 16), raw); tmem_ld_wait(); }
+                    if (n_row < N) out[4 + stage_row(n_row)] = f32_bits_to_f64(raw[0]);
+                }
+                /* S is symmetric: lane n writes S[n][c] to the transposed place, so that the 32 lanes of a store fall
+                   into two contiguous runs of 16 doubles */
+                const u32 scol = tmem_base + SCOL + ((u32)(32 * q4) << 16) + (u32)(g * COLS);
 #pragma unroll
                 for (int c = 0; c < COLS; c += LDCH) {
                     u32 raw[LDCH];
@@ -744,7 +748,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     if (n_row < N) {
 #pragma unroll
                         for (int k = 0; k < LDCH; k++)
-                            out[4 + N + stage_row(n_row) * N + stage_row(g * COLS + c + k)] = f32_bits_to_f64(raw[k]);
+                            out[4 + N + stage_row(g * COLS + c + k) * N + stage_row(n_row)] = f32_bits_to_f64(raw[k]);
                     }
                 }
             }
