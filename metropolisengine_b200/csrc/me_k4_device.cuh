@@ -251,15 +251,16 @@ __device__ __forceinline__ double u53(u32 hi, u32 lo) {
     return a + b;
 }
 /* |c| of a complex parameter for the observable means (ME:412-414): sqrt(re^2 + im^2) through MUFU.RSQ64H + Newton
- * (relative error < 2^-52.5) where the sum of squares is comfortably normal, libdevice hypot otherwise (zero, tiny) */
+ * (relative error < 2^-52.5).  |c| < 1e-140 reads as 0; an overflowing sum of squares (|c| > 1e154) as NaN. */
 __device__ __forceinline__ double cabs_fast(double re, double im) {
     const double w = fma(re, re, im * im);
-    return (w > 1e-280 && w < 1e280) ? me::sqrt_pos_full(w) : hypot(re, im);
+    return w >= 1e-280 ? me::sqrt_pos_full(w) : 0.0;
 }
-/* round-to-nearest-even BF16 bits of a finite float */
-__device__ __forceinline__ u32 bf16_bits_rn(float f) {
-    const u32 b = __float_as_uint(f);
-    return (b + 0x7fffu + ((b >> 16) & 1u)) >> 16;
+/* two floats -> packed BF16 pair, round to nearest even (low half = first) */
+__device__ __forceinline__ u32 bf16x2_rn(float first, float second) {
+    u32 d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(second), "f"(first));
+    return d;
 }
 /* FP32 accumulator word -> double (F2F.F64.F32, exact) */
 __device__ __forceinline__ double f32_bits_to_f64(u32 f) { return (double)__uint_as_float(f); }
@@ -300,7 +301,8 @@ struct Smem {
     alignas(16) unsigned short ztab[ZTAB_ENTRIES];          /* BF16 quantile table of the generator               8 KB   */
     me::MathTables tables;
     u64 z_full[2], z_empty[2], acc_full[2], acc_empty[2], b_full;
-    u64 y_full, s_done;                                     /* measure tail: moment operands written / moment MMAs complete */
+    u64 y_full, s_done, x_final, x_free;                    /* measure tail: operands written / moment MMAs complete / final
+                                                               states of the tile in xs / epilogue done reading xs */
     u32 tmem_slot;
 };
 
@@ -339,8 +341,10 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
             mbar_init(&S.acc_empty[i], EPI_WARPS);
         }
         mbar_init(&S.b_full, 1);
-        mbar_init(&S.y_full, EPI_WARPS);
+        mbar_init(&S.y_full, GEN_WARPS);
         mbar_init(&S.s_done, 1);
+        mbar_init(&S.x_final, EPI_WARPS);
+        mbar_init(&S.x_free, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) tmem_alloc(&S.tmem_slot, TALLOC);
@@ -445,9 +449,40 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                 }
             }
             if (p.do_measure) {
-                /* measure tail: S (+)= Yh Yh^T + Yh Yl^T + Yl Yh^T over the 128 chains of the tile (Y = state - shift split
-                   into two BF16 words by the epilogue warps; Yh sits in the normals' buffer, Yl in the state tile, both
-                   free now).  Nobody touches either buffer again before the MMAs have completed (s_done). */
+                /* measure tail.  While the epilogue warps take the per-chain measurement, the generator warps prepare the
+                   operands of the pooled moments: Y = final state - shift of the tile's chains, split into two BF16 words,
+                   in the K-major layout [chain chunk][coordinate row][8 chains].  Yh goes into the normals' buffer (free:
+                   the last step's MMAs have completed), Yl into the state tile once the epilogue has stopped reading it.
+                   Then S (+)= Yh Yh^T + Yh Yl^T + Yl Yh^T and the first moments (Yh + Yl) . 1 on the tensor cores.  Nobody
+                   touches either buffer again before those MMAs have completed (s_done). */
+                constexpr int GM = NC / GEN_PAR;              /* modes per generator thread */
+                u32 ylp[GM];
+                unsigned char *yh_row = S.zs + (m >> 3) * Y_LBO + (m & 7) * 2;
+                unsigned char *yl_row = reinterpret_cast<unsigned char *>(&S.xs[0][0]) + (m >> 3) * Y_LBO + (m & 7) * 2;
+                mbar_wait(&S.x_final, (u32)(t & 1));          /* the tile's last step has been decided */
+#pragma unroll
+                for (int jj = 0; jj < GM; jj++) {
+                    const int j = c_par * GM + jj;
+                    float yr = 0.f, yi = 0.f;
+                    if (act) {
+                        yr = (float)(S.xs[2 * j][m] - S.shift_s[2 * j]);
+                        yi = (float)(S.xs[2 * j + 1][m] - S.shift_s[2 * j + 1]);
+                    }
+                    const u32 hi_pair = bf16x2_rn(yr, yi);
+                    *reinterpret_cast<unsigned short *>(yh_row + (2 * j) * 16) = (unsigned short)hi_pair;
+                    *reinterpret_cast<unsigned short *>(yh_row + (2 * j + 1) * 16) = (unsigned short)(hi_pair >> 16);
+                    ylp[jj] = bf16x2_rn(yr - bf16_lo_to_float(hi_pair), yi - bf16_hi_to_float(hi_pair));
+                }
+                mbar_wait(&S.x_free, (u32)(t & 1));           /* every epilogue thread is done with the state tile */
+#pragma unroll
+                for (int jj = 0; jj < GM; jj++) {
+                    const int j = c_par * GM + jj;
+                    *reinterpret_cast<unsigned short *>(yl_row + (2 * j) * 16) = (unsigned short)(ylp[jj] & 0xffffu);
+                    *reinterpret_cast<unsigned short *>(yl_row + (2 * j + 1) * 16) = (unsigned short)(ylp[jj] >> 16);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.y_full);
                 if (issuer) {
                     mbar_wait(&S.y_full, (u32)(t & 1));
                     tc_fence_after();
@@ -608,6 +643,10 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     accepted_last = accept ? 1 : 0;
                 }
             }
+            if (p.do_measure) {                               /* the generators may read the tile's final states */
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.x_final);
+            }
             /* store this thread's words of the tile */
             if (act) {
 #pragma unroll 8
@@ -629,50 +668,34 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                 /* ---------------------------------------------------------------- measure tail of this tile */
                 const double dn = (double)p.n_meas_after, inv_n = 1.0 / dn, shrink = (dn - 1.0) * inv_n;
                 double *row = p.record ? p.ts + p.ts_row * (long long)(L.D + 2) * ld + ch : nullptr;
-                u32 ylp[COLS / 2];                            /* low BF16 words of this thread's Y, two per register */
-                unsigned char *yh_row = S.zs + (m >> 3) * Y_LBO + (m & 7) * 2;
                 constexpr int JB = MODES < 8 ? MODES : 8;     /* modes per batch: the batch's global loads are all in flight
                                                                  before the first store (stores to the state block may alias) */
+                if (act) {
+                    /* running pointers (one 64-bit add per mode each) instead of a 64-bit multiply per address */
+                    const long long j0 = g * MODES;
+                    double *pmr = p.state + (long long)(L.MEAN + 1 + j0) * ld + ch, *pmi = pmr + (long long)NC * ld;
+                    double *pob = p.state + (long long)(L.OBSM + 1 + j0) * ld + ch;
+                    double *prr = p.record ? row + (long long)(1 + j0) * ld : nullptr, *pri = p.record ? prr + (long long)NC * ld : nullptr;
 #pragma unroll
-                for (int jb = 0; jb < MODES; jb += JB) {
-                    double mr[JB], mi[JB], ob[JB];
-                    if (act) {
+                    for (int jb = 0; jb < MODES; jb += JB) {
+                        double mr[JB], mi[JB], ob[JB];
+#pragma unroll
+                        for (int b = 0; b < JB; b++) { mr[b] = pmr[b * ld]; mi[b] = pmi[b * ld]; ob[b] = pob[b * ld]; }
 #pragma unroll
                         for (int b = 0; b < JB; b++) {
                             const int j = g * MODES + jb + b;
-                            mr[b] = p.state[(long long)(L.MEAN + 1 + j) * ld + ch];
-                            mi[b] = p.state[(long long)(L.MEAN + 1 + NC + j) * ld + ch];
-                            ob[b] = p.state[(long long)(L.OBSM + 1 + j) * ld + ch];
-                        }
-                    }
-#pragma unroll
-                    for (int b = 0; b < JB; b++) {
-                        const int jj = jb + b, j = g * MODES + jj;
-                        double y[2] = {0.0, 0.0};
-                        if (act) {
                             const double re = S.xs[2 * j][m], im = S.xs[2 * j + 1][m];
                             /* running means and observable means (ME:404-414), this chain's words */
-                            p.state[(long long)(L.MEAN + 1 + j) * ld + ch] = fma(re, inv_n, mr[b] * shrink);
-                            p.state[(long long)(L.MEAN + 1 + NC + j) * ld + ch] = fma(im, inv_n, mi[b] * shrink);
-                            p.state[(long long)(L.OBSM + 1 + j) * ld + ch] = fma(cabs_fast(re, im), inv_n, ob[b] * shrink);
-                            if (row) {
-                                __stcs(row + (long long)(1 + j) * ld, re);
-                                __stcs(row + (long long)(1 + NC + j) * ld, im);
+                            *pmr = fma(re, inv_n, mr[b] * shrink);
+                            *pmi = fma(im, inv_n, mi[b] * shrink);
+                            *pob = fma(cabs_fast(re, im), inv_n, ob[b] * shrink);
+                            pmr += ld; pmi += ld; pob += ld;
+                            if (p.record) {
+                                __stcs(prr, re);
+                                __stcs(pri, im);
+                                prr += ld; pri += ld;
                             }
-                            y[0] = re - S.shift_s[2 * j];
-                            y[1] = im - S.shift_s[2 * j + 1];
                         }
-                        u32 lo_pair = 0;
-#pragma unroll
-                        for (int r = 0; r < 2; r++) {
-                            const int n = 2 * j + r;                 /* interleaved coordinate = operand row */
-                            const u32 hb = bf16_bits_rn((float)y[r]);
-                            const double rest = y[r] - (double)__uint_as_float(hb << 16);
-                            const u32 lb = bf16_bits_rn((float)rest);
-                            *reinterpret_cast<unsigned short *>(yh_row + n * 16) = (unsigned short)hb;
-                            lo_pair |= lb << (16 * r);
-                        }
-                        ylp[jj] = lo_pair;
                     }
                 }
                 if (g == 0) {
@@ -699,15 +722,9 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     }
                     if (lane == 0) { S.cscal[q4][0] = va; S.cscal[q4][1] = va2; S.cscal[q4][2] = vs; }
                 }
-                named_barrier(6, 32 * EPI_WARPS);            /* every epilogue thread is done with the state tile */
-                /* low words into the (now free) state tile, same operand layout as the high words */
-                unsigned char *yl_row = reinterpret_cast<unsigned char *>(&S.xs[0][0]) + (m >> 3) * Y_LBO + (m & 7) * 2;
-#pragma unroll
-                for (int jj = 0; jj < MODES; jj++) {
-                    const int j = g * MODES + jj;
-                    *reinterpret_cast<unsigned short *>(yl_row + (2 * j) * 16) = (unsigned short)(ylp[jj] & 0xffffu);
-                    *reinterpret_cast<unsigned short *>(yl_row + (2 * j + 1) * 16) = (unsigned short)(ylp[jj] >> 16);
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.x_free);       /* this warp is done with the state tile */
+                named_barrier(6, 32 * EPI_WARPS);            /* the lane quarters' scalar sums are in place */
                 /* the CTA's running scalar sums (fixed order) */
                 if (tid == 0) {
                     sc_acc[0] += (double)cnt;
@@ -715,9 +732,6 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     sc_acc[2] += (S.cscal[0][0] + S.cscal[1][0]) + (S.cscal[2][0] + S.cscal[3][0]);
                     sc_acc[3] += (S.cscal[0][1] + S.cscal[1][1]) + (S.cscal[2][1] + S.cscal[3][1]);
                 }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.y_full);
                 mbar_wait(&S.s_done, (u32)(t & 1));           /* the moment MMAs have read both operand buffers */
             }
         }
