@@ -511,6 +511,15 @@ __device__ __forceinline__ double adapt_sigma(double sig, bool accept, const Gai
     return fma(sig, accept ? g.up : g.ndown, sig);
 }
 
+/* |c_j| of the observables: libdevice hypot in the parity build; in the throughput build sqrt(re^2 + im^2) through
+ * MUFU.RSQ64H + Newton (relative error < 2^-52.5; |c| < 1e-140 reads as 0, an overflowing sum of squares as NaN). */
+template <bool FAST>
+__device__ __forceinline__ double cabs2(double re, double im) {
+    if (!FAST) return hypot(re, im);
+    const double w = fma(re, re, im * im);
+    return w >= 1e-280 ? sqrt_pos_full(w) : 0.0;
+}
+
 /* ------------------------------------------------------------------------------------------ measure (ME:342-427)
  * Running means, Haario recursion + sigma^2/n regulariser once n > 50, observable means; evaluation order as in
  * the reference.  numpy divides a complex array by a real as multiplication by the reciprocal,
@@ -601,7 +610,7 @@ __device__ __forceinline__ void measure_update(Chain<L> &c, Stats<L> &s, long lo
         s.obsm[i] = s.obsm[i] * shrink + (STRICT ? fabs(c.x[i]) / dn : fabs(c.x[i]) * inv_n);
 #pragma unroll
     for (int j = 0; j < NC; j++) {
-        const double a = hypot(c.x[NR + j], c.x[NR + NC + j]);
+        const double a = cabs2<!STRICT>(c.x[NR + j], c.x[NR + NC + j]);
         s.obsm[NR + j] = s.obsm[NR + j] * shrink + (STRICT ? a / dn : a * inv_n);
     }
 #pragma unroll
@@ -641,6 +650,102 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ME_FULL, v, o);
     return v;
+}
+
+/* Pooled moments of mid-sized shapes (9 < POOLW, D <= 15) on the FP64 tensor cores.  The sums over the 32 chains of a warp
+ * of y y^T, y = [x - s, 1], are a matrix product with the chains as the K dimension: per measure the warp stages y in shared
+ * memory (row = coordinate, column = chain; two rounds of 16 chains), reads it back in mma.m8n8k4 fragment order — the A
+ * and the B fragment of a thread are the same word when the row block equals the column block — and issues
+ * 8 x NBX (NBX + 1) / 2 DMMAs (C3: 24); the observable sums are a second product against a unit vector.  No shuffles and
+ * no CTA barrier: the 87 warp_sum reductions of the 3r+4c shape (870 SHFL + two __syncthreads per measure) were 39 % of
+ * that kernel's time (tests/scripts/c3_probe.py: 13.9 ms with them, 8.5 ms without).  Each accumulator element belongs to
+ * one thread, which adds it to its word of the warp's row of pooled sums (pw). */
+#define ME_POOL_MMA_MAX_BLOCK 128
+#define ME_YB_ROWS 16
+#define ME_YB_LD 20            /* doubles per staged row: 16 chains + 4 of padding (fragment reads take two wavefronts) */
+
+__device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <class L, bool FAST>
+__device__ __forceinline__ void pool_mma_update(const Chain<L> &c, const double (&sh)[L::D], bool active,
+                                                double (*yb)[ME_YB_LD], double *pw) {
+    constexpr int D = L::D, NR = L::NR, NC = L::NC, NOBS = L::NOBS;
+    /* row blocks of [x - s, 1] (instantiated, never executed, for larger shapes: their block count is clamped) */
+    constexpr int NBX = (D + 1 + 7) / 8 <= ME_YB_ROWS / 8 ? (D + 1 + 7) / 8 : ME_YB_ROWS / 8;
+    constexpr int NBO = (NOBS + 7) / 8;            /* row blocks of the observables */
+    const int lane = threadIdx.x & 31, r8 = lane >> 2, k4 = lane & 3, half = lane >> 4, colw = lane & 15;
+    double acc[NBX * (NBX + 1) / 2][2];
+#pragma unroll
+    for (int i = 0; i < NBX * (NBX + 1) / 2; i++) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        __syncwarp();
+        if (half == h) {
+#pragma unroll
+            for (int i = 0; i < D; i++) yb[i][colw] = active ? c.x[i] - sh[i] : 0.0;
+            yb[D][colw] = active ? 1.0 : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            double a[NBX];
+#pragma unroll
+            for (int b = 0; b < NBX; b++) {
+                const double v = yb[8 * b + r8][4 * t + k4];
+                a[b] = (8 * b + r8 <= D) ? v : 0.0;          /* rows beyond the constant 1 are never written */
+            }
+#pragma unroll
+            for (int i = 0; i < NBX; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++) dmma_8x8x4(acc[tri(i, j)][0], acc[tri(i, j)][1], a[i], a[j]);
+        }
+    }
+    /* observables |x_i|, |c_j|, x_i^2: sums over the chains = product with the unit vector e_0 (result column 0) */
+    double ob[NOBS];
+#pragma unroll
+    for (int i = 0; i < NR; i++) ob[i] = active ? fabs(c.x[i]) : 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) ob[NR + j] = active ? cabs2<FAST>(c.x[NR + j], c.x[NR + NC + j]) : 0.0;
+#pragma unroll
+    for (int i = 0; i < NR; i++) ob[NR + NC + i] = active ? c.x[i] * c.x[i] : 0.0;
+    double acco[NBO][2];
+    const double e0 = r8 == 0 ? 1.0 : 0.0;
+#pragma unroll
+    for (int cb = 0; cb < NBO; cb++) {
+        acco[cb][0] = acco[cb][1] = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            __syncwarp();
+            if (half == h) {
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    if (8 * cb + r < NOBS) yb[r][colw] = ob[8 * cb + r];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const double v = yb[r8][4 * t + k4];
+                dmma_8x8x4(acco[cb][0], acco[cb][1], (8 * cb + r8 < NOBS) ? v : 0.0, e0);
+            }
+        }
+    }
+    /* every needed element of the products has exactly one owner in the warp */
+#pragma unroll
+    for (int i = 0; i < NBX; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int r = 8 * i + r8, cc = 8 * j + 2 * k4 + e;
+                if (r < D && cc <= r) pw[D + r * (r + 1) / 2 + cc] += acc[tri(i, j)][e];
+                else if (r == D && cc < D) pw[cc] += acc[tri(i, j)][e];
+            }
+#pragma unroll
+    for (int cb = 0; cb < NBO; cb++)
+        if (k4 == 0 && 8 * cb + r8 < NOBS) pw[D + D * (D + 1) / 2 + 8 * cb + r8] += acco[cb][0];
 }
 
 /* ------------------------------------------------------------------------------------------ one state-dependent step
@@ -733,9 +838,17 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     constexpr bool POOL_REG = L::POOLW <= ME_POOL_REG_MAX;
     constexpr bool POOL_OK = L::POOLW <= ME_MAX_POOLW;        /* static shared-memory budget */
     constexpr int PW = POOL_OK ? L::POOLW : 1;
+#ifndef ME_POOL_MMA
+#define ME_POOL_MMA 1            /* build-time experiment knob: 0 = warp_sum reductions for every shape beyond POOL_REG */
+#endif
+    /* mid-sized shapes: pooled moments on the FP64 tensor cores (pool_mma_update); their CTAs are at most
+       ME_POOL_MMA_MAX_BLOCK threads (choose_dims in me_api.cu follows the same rule) */
+    constexpr bool POOL_MMA = ME_POOL_MMA && !POOL_REG && POOL_OK && L::D + 1 <= ME_YB_ROWS;
+    constexpr int POOL_WARPS = (POOL_MMA ? ME_POOL_MMA_MAX_BLOCK : ME_MAX_BLOCK) / 32;
 
-    __shared__ double pool_warp[ME_MAX_BLOCK / 32][PW];
-    __shared__ double pool_cta[PW];
+    __shared__ double pool_warp[POOL_WARPS][PW];
+    __shared__ double pool_cta[POOL_MMA ? 1 : PW];
+    __shared__ double ybuf[POOL_MMA ? POOL_WARPS : 1][POOL_MMA ? ME_YB_ROWS : 1][ME_YB_LD];
     __shared__ MathTables tables;
     init_math_tables(tables);
     __syncthreads();
@@ -803,8 +916,15 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
 #pragma unroll
         for (int w = 0; w < L::POOLW; w++) pacc[w] = 0.0;
     }
-    const bool pooling = POOL_OK && p.pool != nullptr && p.do_measure;
-    if (pooling && !POOL_REG) {
+#ifndef ME_EXPERIMENT_NO_POOL
+#define ME_EXPERIMENT_NO_POOL 0   /* build-time experiment knob (tests/scripts/c3_probe.py): what the pooled moments cost */
+#endif
+    const bool pooling = POOL_OK && p.pool != nullptr && p.do_measure && !ME_EXPERIMENT_NO_POOL;
+    if (POOL_MMA && blockDim.x > ME_POOL_MMA_MAX_BLOCK) __trap();       /* the host never launches this (choose_dims) */
+    if (pooling && POOL_MMA) {
+        for (int w = threadIdx.x; w < POOL_WARPS * PW; w += blockDim.x) (&pool_warp[0][0])[w] = 0.0;
+        __syncthreads();
+    } else if (pooling && !POOL_REG) {
         for (int w = threadIdx.x; w < L::POOLW; w += blockDim.x) pool_cta[w] = 0.0;
         __syncthreads();
     }
@@ -943,6 +1063,9 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
             if (pooling) {
                 if (POOL_REG) {
 for_each_pool_word<L>(c, shift, [&](int w, double v) { pacc[w] += v; });
+                } else if (POOL_MMA) {
+                    const int warp = threadIdx.x >> 5;
+                    pool_mma_update<L, !STRICT>(c, shift, active, ybuf[warp], pool_warp[warp]);
                 } else {
                     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
                     for_each_pool_word<L>(c, shift, [&](int w, double v) {
@@ -968,12 +1091,14 @@ for_each_pool_word<L>(c, shift, [&](int w, double v) { pacc[w] += v; });
         if (p.last_accept && p.spm > 0 && n_blocks > 0) p.last_accept[ch] = (unsigned char)accept;
     }
     if (pooling) {
-        if (POOL_REG) {
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (POOL_REG || POOL_MMA) {
+            if (POOL_REG) {
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-            for (int w = 0; w < L::POOLW; w++) {
-                const double v = warp_sum(active ? pacc[w] : 0.0);
-                if (lane == 0) pool_warp[warp][w] = v;
+                for (int w = 0; w < L::POOLW; w++) {
+                    const double v = warp_sum(active ? pacc[w] : 0.0);
+                    if (lane == 0) pool_warp[warp][w] = v;
+                }
             }
             __syncthreads();
             const int nw = (blockDim.x + 31) >> 5;
