@@ -39,17 +39,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # algorithmic work per chain-step / bytes per chain-measure (x[D], E, sigma stored in FP64).
-# fp64_inst / wide_inst: FP64 and IMAD.WIDE instructions per chain-step in the SASS of the step loop
-# (tests/scripts/sass_loop.py on the shipped library) — the inputs of the pipe-level roofline below.
+# inst / fp64_inst / wide_inst / dmma_inst: instructions, FP64 instructions, IMAD.WIDE and FP64 tensor-core MMAs per
+# chain-step over one whole MEASURE PERIOD (spm steps + the measure block + the per-measure prologue) in the SASS of the
+# shipped library (tests/scripts/sass_period.py <kernel> <spm>) — the inputs of the pipe-level roofline below.  The step
+# loops alone (tests/scripts/sass_loop.py) are 111 / 31 / 12 (C1), 126.5 / 40 / 12 (C2), 636 / 257 / 52 (C3).
 WORKLOADS = {
     "c1": dict(name="README x^2: 1 real param, T=0.01, measure every step", energy=("x2",), n_r=1, n_c=0, temp=0.01,
-               chains=65536, measures=10000, short_measures=10000, spm=1, flop=10, sf=3, inst=111.0, fp64_inst=31.0, wide_inst=12.0),
+               chains=65536, measures=10000, short_measures=10000, spm=1, flop=10, sf=3, inst=271.0, fp64_inst=75.0, wide_inst=16.0, dmma_inst=0.0),
     "c2": dict(name="demo/toymodel_xypotentialwell: 2 real params, E=x^2+y^2, T=0.1, 65,536 chains x 1e5 steps, "
                     "measure every 10", energy=("xy_well", 1.0), n_r=2, n_c=0, temp=0.1, chains=65536,
-               measures=10000, short_measures=2000, spm=10, flop=20, sf=5, inst=126.5, fp64_inst=40.0, wide_inst=12.0),
+               measures=10000, short_measures=2000, spm=10, flop=20, sf=5, inst=146.3, fp64_inst=48.2, wide_inst=12.3, dmma_inst=0.0),
     "c3": dict(name="mixed 3 real + 4 complex (bounded demo-style well), T=0.1, 262,144 chains, measure every 10",
                energy=("mixed_well", 1.0, -1.0, 0.5, 1.0), n_r=3, n_c=4, temp=0.1, chains=262144, measures=100,
-               short_measures=100, spm=10, flop=170, sf=23, inst=658.0, fp64_inst=257.0, wide_inst=60.0),
+               short_measures=100, spm=10, flop=170, sf=23, inst=787.3, fp64_inst=305.4, wide_inst=54.1, dmma_inst=4.0),
 }
 # the CPU arm also knows config 4 (1 real + 64 complex, the reference's own per-chain covariance: 128x128 SVD per step)
 CPU_WORKLOADS = dict(WORKLOADS)
@@ -381,23 +383,26 @@ class Ctx:
 def pipe_model(wl, chains, steps_per_chain, ker_ms, sm_hz, n_sm):
     """Issue-port roofline of the fused step kernel (DESIGN.md §3 "What bounds the step kernel").  Measured on B200: once an
     SM sub-partition holds >= 3 warps of this kernel its throughput no longer grows with the warp count
-    (tests/scripts/scale_probe.py) and the time per warp-step follows   inst + fp64_inst + 2.5 * wide_inst   cycles of the
-    sub-partition's issue port — every instruction takes one issue cycle, a warp-wide FP64 instruction holds the port a
-    second cycle (64 FP64 lanes per clock and SM = 2 cycles per warp) and an IMAD.WIDE (Philox round) about 3.5 cycles in
-    all (tests/scripts/issue_mix.cu).  The model reproduces both stream definitions of this kernel: v2 (164 / 59 / 18
-    instructions per step) predicts 268 cycles against 295 measured, v3 (this build) 196 against 228.  The bound is that
-    cost (step loop only; the measure block is not counted) times the average number of warps per sub-partition."""
+    (tests/scripts/scale_probe.py) and the time per warp-step follows   inst + fp64_inst + 2.5 * wide_inst + 15 * dmma_inst
+    cycles of the sub-partition's issue port — every instruction takes one issue cycle, a warp-wide FP64 instruction holds
+    the port a second cycle (64 FP64 lanes per clock and SM = 2 cycles per warp), an IMAD.WIDE (Philox round) about 3.5
+    cycles in all (tests/scripts/issue_mix.cu), an FP64 tensor-core mma.m8n8k4 (256 FMA) 16.  The counts cover the whole
+    measure period (steps + measure block + per-measure prologue, tests/scripts/sass_period.py), per chain-step.  The
+    bound is that cost times the average number of warps per sub-partition."""
     warps = -(-chains // 32) / (4.0 * n_sm)
-    cyc = wl["inst"] + wl["fp64_inst"] + 2.5 * wl["wide_inst"]
+    cyc = wl["inst"] + wl["fp64_inst"] + 2.5 * wl["wide_inst"] + 15.0 * wl["dmma_inst"]
     bound_ms = 1e3 * warps * steps_per_chain * cyc / sm_hz
+    fp64_cycles = 2.0 * wl["fp64_inst"] + 16.0 * wl["dmma_inst"]
     return {"inst_per_chain_step": wl["inst"], "fp64_inst_per_chain_step": wl["fp64_inst"],
-            "imad_wide_per_chain_step": wl["wide_inst"], "issue_cycles_per_warp_step_lower_bound": cyc,
+            "imad_wide_per_chain_step": wl["wide_inst"], "fp64_mma_per_chain_step": wl["dmma_inst"],
+            "issue_cycles_per_warp_step_lower_bound": cyc,
             "warps_per_subpartition": warps, "bound_ms": bound_ms, "frac": bound_ms / ker_ms,
-            "fp64_pipe_frac": 1e3 * warps * steps_per_chain * 2.0 * wl["fp64_inst"] / sm_hz / ker_ms,
-            "how": "issue-port cycles the SASS of the step loop needs (1 per instruction + 1 more per FP64 instruction + 2.5 "
-                   "more per IMAD.WIDE; counts from tests/scripts/sass_loop.py on the shipped library, main path of the "
-                   "loop) x average warps per SM sub-partition / measured kernel time; fp64_pipe_frac = FP64-pipe cycles "
-                   "(2 per FP64 instruction) / measured kernel time, the quantity ncu reports as "
+            "fp64_pipe_frac": 1e3 * warps * steps_per_chain * fp64_cycles / sm_hz / ker_ms,
+            "how": "issue-port cycles the SASS of one measure period needs, per chain-step (1 per instruction + 1 more per "
+                   "FP64 instruction + 2.5 more per IMAD.WIDE + 15 more per FP64 tensor-core MMA; counts from "
+                   "tests/scripts/sass_period.py on the shipped library, rarely taken fallback spans left out) x average "
+                   "warps per SM sub-partition / measured kernel time; fp64_pipe_frac = FP64-pipe cycles (2 per FP64 "
+                   "instruction, 16 per MMA) / measured kernel time, the quantity ncu reports as "
                    "sm__pipe_fp64_cycles_active"}
 
 

@@ -274,6 +274,15 @@ def test_pooled_moments_of_a_million_chain_ensemble_use_the_two_stage_reduction(
     nr = eng.num_real_params
     assert np.allclose(ps["mean_real"], x[:, :nr].mean(0), rtol=0, atol=1e-12)
     assert np.allclose(ps["cov_real"], np.cov(x[:, :nr].T), rtol=1e-9, atol=1e-13)
+    if shape == "mixed":
+        # this shape accumulates its moments on the FP64 tensor cores (pool_mma_update): every word of the product, with
+        # the idle lanes of the ragged last warp masked out
+        c = x[:, 3:7] + 1j * x[:, 7:11]
+        cm = c - c.mean(0)
+        assert np.allclose(ps["mean_complex"], c.mean(0), rtol=0, atol=1e-12)
+        assert np.allclose(ps["cov_complex"], cm.T @ cm.conj() / (c.shape[0] - 1), rtol=1e-9, atol=1e-12)
+        obs = np.concatenate([np.abs(x[:, :3]), np.abs(c), x[:, :3] ** 2], axis=1).mean(0)
+        assert np.allclose(ps["observables_mean"], obs, rtol=1e-10, atol=1e-13)
     # a second reduction after the reset sees empty rows
     out = torch.zeros(eng._lay.POOL_WORDS, dtype=torch.float64, device=eng.device)
     eng._launch(eng._lib.me_pool_reduce(eng._h, ctypes.c_void_p(out.data_ptr()), 0, eng._stream()))
