@@ -564,12 +564,11 @@ def c5_pass(ctx, steps=3, warmup=3, total_chains=1 << 20, launches=20):
     wl = WORKLOADS["c2"]
     eng, _ = make_engine(ctx, wl, total_chains, record=False, seed=7)
     M, spm = 10, 10
-    eng.run_graphed(M, spm)        # eager (allocations, communicator)
-    eng.run_graphed(M, spm)        # capture + first replay
+    eng.run_graphed(M, spm, launches)        # eager (allocations, communicator)
+    eng.run_graphed(M, spm, launches)        # capture + first replay
 
     def one():
-        for _ in range(launches):
-            eng.run_graphed(M, spm)
+        eng.run_graphed(M, spm, launches)
 
     ms = ctx.timed(one, steps, warmup)
     value = total_chains * M * spm * launches * steps / (ms * 1e-3)
@@ -585,8 +584,9 @@ def c5_pass(ctx, steps=3, warmup=3, total_chains=1 << 20, launches=20):
                        "all-reduce after every launch" % (total_chains, ctx.world),
            "scaling": "strong", "value": value, "unit": "chain-steps/s", "us_per_launch": 1e3 * ms / (steps * launches),
            "chains_total": total_chains, "chains_per_gpu": total_chains // ctx.world, "launches_per_pass": launches,
-           "how": "each launch = one CUDA-graph replay of [me_run -> me_allreduce_stats (fixed-order reduction, NCCL "
-                  "all-reduce inside the library, device-resident totals)]; one D2H of the totals at the end",
+           "how": "one CUDA graph per pass: %d x [me_run -> me_reduce_stats (fixed-order reduction of the per-CTA rows) -> "
+                  "me_accumulate_stats on a side stream (NCCL all-reduce inside the library, device-resident totals), which "
+                  "overlaps the next me_run]; one D2H of the totals at the end" % launches,
            "eager_value": total_chains * M * spm * launches * steps / (ms_e * 1e-3),
            "pooled_var_x0": float(ps["cov_real"][0, 0]), "pooled_count": ps["count"]}
     del eng

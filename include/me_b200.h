@@ -221,6 +221,12 @@ int me_comm_adopt(void *nccl_comm, int32_t world, int32_t rank, int32_t device, 
 int me_comm_destroy(me_comm *comm);
 const char *me_comm_last_error(void);
 int me_allreduce_stats(me_engine *eng, me_comm *comm, double *inc, double *totals, int64_t n_samples, void *stream);
+/* The two halves of me_allreduce_stats, for hosts that overlap the collective with the next stepping launch (SURVEY.md
+ * §8e "overlap with the next stepping launch"): me_reduce_stats on the stepping stream (it reads and resets the per-CTA
+ * accumulators the next me_run writes), then — ordered after it by an event — me_accumulate_stats on a side stream
+ * (all-reduce of `inc` over the ranks, totals += inc).  Use one `inc` buffer per launch in flight. */
+int me_reduce_stats(me_engine *eng, double *inc, int64_t n_samples, void *stream);
+int me_accumulate_stats(me_engine *eng, me_comm *comm, double *inc, double *totals, void *stream);
 
 /* measure_step_counter (ME:73) and the global step index (Philox counter); for checkpoint / resume. */
 int me_get_counters(me_engine *eng, int64_t *n_measure, uint64_t *step);

@@ -76,6 +76,8 @@ SIGNATURES = {
     "me_comm_destroy": (ctypes.c_int, [_vp]),
     "me_comm_last_error": (_cp, []),
     "me_allreduce_stats": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "me_reduce_stats": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
+    "me_accumulate_stats": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "me_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
     "me_set_counters": (ctypes.c_int, [_vp, _i64, _u64]),
     "me_k4_layout_get": (ctypes.c_int, [ctypes.POINTER(MeK4Layout)]),

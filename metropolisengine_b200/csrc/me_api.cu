@@ -1158,8 +1158,9 @@ int me_comm_destroy(me_comm *c) {
 
 const char *me_comm_last_error(void) { return g_comm_error.c_str(); }
 
-int me_allreduce_stats(me_engine *e, me_comm *comm, double *inc, double *totals, int64_t n_samples, void *stream) {
-    if (!e || !inc || !totals || n_samples < 0) return ME_ERR_INVALID;
+/* first half of me_allreduce_stats: inc = fixed-order sum of the per-CTA accumulators (which are reset) | n_samples */
+int me_reduce_stats(me_engine *e, double *inc, int64_t n_samples, void *stream) {
+    if (!e || !inc || n_samples < 0) return ME_ERR_INVALID;
     if (!e->bound || !e->buf.pool || e->lay.POOL_WORDS == 0) return fail(e, ME_ERR_STATE, "no pool buffer bound");
     DeviceGuard g(e->cfg.device);
     const int words = e->lay.POOL_WORDS;
@@ -1175,6 +1176,19 @@ int me_allreduce_stats(me_engine *e, me_comm *comm, double *inc, double *totals,
     } else {
         k_pool_reduce<<<words + 1, 256, 0, st>>>(e->buf.pool, inc, e->grid, words, 1, 1, (double)n_samples);
     }
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return fail(e, ME_ERR_CUDA, std::string("me_reduce_stats: ") + cudaGetErrorString(ce));
+    return ME_OK;
+}
+
+/* second half: inc summed over the ranks of `comm` in place, totals += inc.  May run on another stream than the stepping
+   launches (ordered after me_reduce_stats by an event), so that the collective overlaps the next launch. */
+int me_accumulate_stats(me_engine *e, me_comm *comm, double *inc, double *totals, void *stream) {
+    if (!e || !inc || !totals) return ME_ERR_INVALID;
+    if (e->lay.POOL_WORDS == 0) return fail(e, ME_ERR_STATE, "no pooled moments for this shape");
+    DeviceGuard g(e->cfg.device);
+    const int words = e->lay.POOL_WORDS;
+    cudaStream_t st = (cudaStream_t)stream;
     if (comm && comm->world > 1) {
         NcclApi &n = nccl_api();
         const int rc = n.allReduce(inc, inc, (size_t)(words + 1), 8 /* ncclDouble */, 0 /* ncclSum */, comm->nccl, st);
@@ -1182,8 +1196,15 @@ int me_allreduce_stats(me_engine *e, me_comm *comm, double *inc, double *totals,
     }
     k_accumulate<<<(words + 1 + 127) / 128, 128, 0, st>>>(totals, inc, words + 1);
     cudaError_t ce = cudaGetLastError();
-    if (ce != cudaSuccess) return fail(e, ME_ERR_CUDA, std::string("me_allreduce_stats: ") + cudaGetErrorString(ce));
+    if (ce != cudaSuccess) return fail(e, ME_ERR_CUDA, std::string("me_accumulate_stats: ") + cudaGetErrorString(ce));
     return ME_OK;
+}
+
+int me_allreduce_stats(me_engine *e, me_comm *comm, double *inc, double *totals, int64_t n_samples, void *stream) {
+    if (!e || !inc || !totals || n_samples < 0) return ME_ERR_INVALID;
+    const int rc = me_reduce_stats(e, inc, n_samples, stream);
+    if (rc != ME_OK) return rc;
+    return me_accumulate_stats(e, comm, inc, totals, stream);
 }
 
 int me_get_counters(me_engine *e, int64_t *n_measure, uint64_t *step) {

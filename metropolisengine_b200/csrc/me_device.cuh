@@ -963,7 +963,8 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     /* static shared-memory budget (48 KB): the pooled-moment staging of a large shape (9 x POOLW doubles, up to 43 KB at
        ME_MAX_POOLW) and the 16 KB table copy do not both fit; such shapes read the table through the read-only path */
     constexpr int TAB_ENTRIES = ME_LOGTAB_ENTRIES + ME_SINTAB_ENTRIES;       /* log table, then the sin/cos table */
-    constexpr bool TAB_FITS = (ME_MAX_BLOCK / 32 + 1) * PW * 8 + TAB_ENTRIES * 16 + 1024 <= 48 * 1024;
+    constexpr int POOL_SMEM = POOL_MMA ? POOL_WARPS * (PW + ME_YB_ROWS * ME_YB_LD) * 8 : (ME_MAX_BLOCK / 32 + 1) * PW * 8;
+    constexpr bool TAB_FITS = POOL_SMEM + TAB_ENTRIES * 16 + 1024 <= 48 * 1024;
     constexpr bool TAB_SMEM = !STRICT && L::D > ME_SEG_MAX_D && TAB_FITS;
     __shared__ double2 logtab_s[TAB_SMEM ? TAB_ENTRIES : 1];
     if (TAB_SMEM) {

@@ -457,21 +457,33 @@ class MetropolisEngine:
         self._pool_pending += n_measures * self.n_chains
         self.step_counter += n_measures * steps_per_measure if self._kind == "complex" else 0
 
-    def run_graphed(self, n_measures, steps_per_measure):
+    def run_graphed(self, n_measures, steps_per_measure, launches=1):
         """``run()`` followed by the pooled-moment reduction and its all-reduce across ranks, as ONE CUDA-graph launch
         (fused device-functor engines, ``record=False``): for ensembles whose launch lasts only a fraction of a
         millisecond the per-launch host work otherwise bounds the job.  The first call runs eagerly (it makes every
         allocation), the second captures, later ones replay; the Philox step index and the measure counter come from
         the device copy of the counters, so a replay continues the chains exactly like an eager call
-        (``test_graph_replay_of_fused_runs_is_bit_identical``)."""
-        n_measures, steps_per_measure = int(n_measures), int(steps_per_measure)
+        (``test_graph_replay_of_fused_runs_is_bit_identical``).
+
+        ``launches > 1`` puts that many consecutive ``[run -> reduction -> all-reduce]`` rounds into the one graph and
+        moves each round's collective (``me_accumulate_stats``: NCCL all-reduce + accumulation into the device-resident
+        totals) to a side stream, where it overlaps the NEXT round's stepping launch; only the fixed-order
+        reduction of the per-CTA rows (``me_reduce_stats``) stays between two stepping launches.  Two increment buffers
+        alternate.  The totals are the same sums in the same order as with ``launches`` separate calls."""
+        n_measures, steps_per_measure, launches = int(n_measures), int(steps_per_measure), int(launches)
         if self._unfused() or self._generic or self.record:
             raise RuntimeError("run_graphed serves fused device-functor engines (D <= 32) with record=False")
-        key = ("fused", n_measures, steps_per_measure)
+        if launches < 1:
+            raise ValueError("launches must be >= 1")
+        key = ("fused", n_measures, steps_per_measure, launches)
         seen = self._graphs.get(key)
         if seen is None:                        # first use: eager, so that no allocation happens under capture
-            self.run(n_measures, steps_per_measure)
-            self._flush_pool()
+            for _ in range(launches):
+                self.run(n_measures, steps_per_measure)
+                self._flush_pool()
+            if launches > 1 and getattr(self, "_pool_inc2", None) is None:
+                self._pool_inc2 = torch.zeros_like(self._pool_inc)
+                self._side_stream = torch.cuda.Stream(device=self.device)
             self._graphs[key] = "warm"
             return
         n, s0 = ctypes.c_int64(), ctypes.c_uint64()
@@ -483,20 +495,40 @@ class MetropolisEngine:
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             pending = self._pool_pending
+            samples = n_measures * self.n_chains
             with torch.cuda.graph(g):
-                self._launch(self._lib.me_run(self._h, n_measures, steps_per_measure, 1, None, 0, self._stream()))
-                self._launch(self._lib.me_allreduce_stats(self._h, self._library_comm(), _ptr(self._pool_inc),
-                                                          _ptr(self._pool_tot), n_measures * self.n_chains,
-                                                          self._stream()))
+                if launches == 1:
+                    self._launch(self._lib.me_run(self._h, n_measures, steps_per_measure, 1, None, 0, self._stream()))
+                    self._launch(self._lib.me_allreduce_stats(self._h, self._library_comm(), _ptr(self._pool_inc),
+                                                              _ptr(self._pool_tot), samples, self._stream()))
+                else:
+                    main, side = torch.cuda.current_stream(self.device), self._side_stream
+                    incs, free = (self._pool_inc, self._pool_inc2), [None, None]
+                    for i in range(launches):
+                        self._launch(self._lib.me_run(self._h, n_measures, steps_per_measure, 1, None, 0, self._stream()))
+                        k = i & 1
+                        if free[k] is not None:
+                            main.wait_event(free[k])            # the collective two rounds ago is done with this buffer
+                        self._launch(self._lib.me_reduce_stats(self._h, _ptr(incs[k]), samples, self._stream()))
+                        ready = torch.cuda.Event()
+                        ready.record(main)
+                        side.wait_event(ready)
+                        with torch.cuda.stream(side):
+                            self._launch(self._lib.me_accumulate_stats(self._h, self._library_comm(), _ptr(incs[k]),
+                                                                       _ptr(self._pool_tot), self._stream()))
+                        free[k] = torch.cuda.Event()
+                        free[k].record(side)
+                    main.wait_stream(side)
             self._check(self._lib.me_set_counters(self._h, n.value, s0.value))     # capture moved the host counters
             self._pool_pending = pending
             self._graphs[key] = seen = g
         if self._pool_pending:
             self._flush_pool()                  # samples of earlier eager runs go in before the graph's own
         seen.replay()
-        self.launch_count += 3
-        self._check(self._lib.me_set_counters(self._h, n.value + n_measures, s0.value + n_measures * steps_per_measure))
-        self.step_counter += n_measures * steps_per_measure if self._kind == "complex" else 0
+        self.launch_count += 3 * launches
+        self._check(self._lib.me_set_counters(self._h, n.value + launches * n_measures,
+                                              s0.value + launches * n_measures * steps_per_measure))
+        self.step_counter += launches * n_measures * steps_per_measure if self._kind == "complex" else 0
 
     def step(self, k=1):
         """``k`` calls of ``step_all()`` in one launch (no measure)."""

@@ -49,13 +49,16 @@ def main():
     g = me.MetropolisEngine(("xy_well", 1.0), n_chains=n, distributed=True, **kw2)
     for _ in range(4):
         g.run_graphed(25, 4)
+    g.run_graphed(25, 4, launches=3)     # eager first use
+    g.run_graphed(25, 4, launches=3)     # capture: three rounds per graph, all-reduce of round i beside the launch of round i + 1
+    g.run_graphed(25, 4, launches=3)     # replay
     gps = g.pooled_statistics()
     if rank == 0:
         ref2 = me.MetropolisEngine(("xy_well", 1.0), n_chains=n, **kw2)
-        for _ in range(4):
+        for _ in range(13):
             ref2.run(25, 4)
         r2 = ref2.pooled_statistics()
-        ok = ok and gps["count"] == r2["count"] == 100 * n
+        ok = ok and gps["count"] == r2["count"] == 13 * 25 * n
         for k in ("mean_real", "cov_real", "observables_mean"):
             ok = ok and np.allclose(gps[k], r2[k], rtol=1e-11, atol=1e-13)
     # every rank must hold the same pooled numbers

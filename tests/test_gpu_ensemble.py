@@ -404,3 +404,20 @@ def test_graph_replay_of_fused_runs_is_bit_identical(shape):
     assert pa["count"] == pb["count"] == (5 * M + 3) * kw["n_chains"]
     for k in ("mean_real", "cov_real", "observables_mean"):
         assert np.allclose(pa[k], pb[k], rtol=1e-12, atol=1e-15), k
+    # several rounds in one graph, each round's collective on a side stream beside the next round's stepping launch
+    # (me_reduce_stats / me_accumulate_stats, two increment buffers): same chains, same totals
+    c = me.MetropolisEngine(energy, **kw)
+    for _ in range(3):
+        c.run_graphed(M, K, launches=5)
+    c.run(3, 2)
+    d = me.MetropolisEngine(energy, **kw)
+    for _ in range(15):
+        d.run(M, K)
+    d.run(3, 2)
+    torch.cuda.synchronize()
+    assert c.measure_step_counter == d.measure_step_counter and c.steps_done == d.steps_done
+    assert torch.equal(c.state, d.state)
+    pc, pd = c.pooled_statistics(), d.pooled_statistics()
+    assert pc["count"] == pd["count"] == (15 * M + 3) * kw["n_chains"]
+    for k in ("mean_real", "cov_real", "observables_mean"):
+        assert np.allclose(pc[k], pd[k], rtol=1e-12, atol=1e-15), k
