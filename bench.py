@@ -478,7 +478,7 @@ def short_fused_pass(ctx, wl_key, fp64_peak, hbm_peak, sm_hz, steps=3, warmup=3)
     return rec
 
 
-def per_chain_large_pass(ctx, hbm_peak, steps=3, warmup=3, chains=8192, measures=20):
+def per_chain_large_pass(ctx, hbm_peak, steps=3, warmup=2, chains=32768, measures=10):
     """The reference's OWN algorithm at the cylinder shape: 1 real + 64 complex with a covariance per chain (ME:274-302), the
     runtime-shape kernel (me_generic.cu, gk_run: one launch per schedule).  HBM-bound: every step streams the chain's 64 x 64
     complex factor (8 n_c^2 = 32,768 B) plus the parameter / proposal / normal vectors."""
