@@ -525,7 +525,10 @@ void choose_dims(me_engine *e) {
     const long long n = e->cfg.n_chains;
     int block = 128;
     if (const char *env = getenv("ME_BLOCK")) block = atoi(env);
-    else if (n <= (long long)e->n_sm * 32 * 32) block = 32;
+    else if (n <= (long long)e->n_sm * 32 * 16) block = 32;     /* up to four warps per sub-partition: finest balance; beyond
+                                                                   that 64-thread CTAs halve the per-CTA fixed cost, which
+                                                                   short launches feel (tests/scripts/c5_launch_probe.py:
+                                                                   131,072 chains x 100 steps, 106.6 -> 100.8 us) */
     else if (n <= (long long)e->n_sm * 32 * 64) block = 64;
     if (block < 32) block = 32;
     if (block > ME_MAX_BLOCK) block = ME_MAX_BLOCK;
