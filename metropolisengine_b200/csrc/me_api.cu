@@ -533,10 +533,11 @@ void choose_dims(me_engine *e) {
     if (block < 32) block = 32;
     if (block > ME_MAX_BLOCK) block = ME_MAX_BLOCK;
     {   /* shapes whose pooled moments run on the FP64 tensor cores stage them per warp in static shared memory sized for
-           ME_POOL_MMA_MAX_BLOCK threads (run_body in me_device.cuh: POOL_MMA) */
+           me_pool_mma_max_block(D) threads (run_body in me_device.cuh: POOL_MMA) */
         const int d = e->cfg.n_real + 2 * e->cfg.n_complex;
         const int poolw = d + d * (d + 1) / 2 + 2 * e->cfg.n_real + e->cfg.n_complex;
-        if (poolw > 9 && d + 1 <= ME_YB_ROWS && block > ME_POOL_MMA_MAX_BLOCK) block = ME_POOL_MMA_MAX_BLOCK;
+        if (me::me_pool_mma_shape(d, poolw) && poolw <= ME_MAX_POOLW && block > me::me_pool_mma_max_block(d))
+            block = me::me_pool_mma_max_block(d);
     }
     block = (block / 32) * 32;
     e->block = block;

@@ -660,9 +660,13 @@ __device__ __forceinline__ double warp_sum(double v) {
  * no CTA barrier: the 87 warp_sum reductions of the 3r+4c shape (870 SHFL + two __syncthreads per measure) were 39 % of
  * that kernel's time (tests/scripts/c3_probe.py: 13.9 ms with them, 8.5 ms without).  Each accumulator element belongs to
  * one thread, which adds it to its word of the warp's row of pooled sums (pw). */
-#define ME_POOL_MMA_MAX_BLOCK 128
-#define ME_YB_ROWS 16
 #define ME_YB_LD 20            /* doubles per staged row: 16 chains + 4 of padding (fragment reads take two wavefronts) */
+/* staging rows (a multiple of 8 holding [x - s, 1]) and the CTA size that keeps the per-warp staging + the warp's row of sums
+   + the math tables inside the 48 KB of static shared memory: D <= 15 -> 16 rows, 128 threads; D <= 23 -> 24 rows, 64
+   threads; D <= 31 -> 32 rows, 32 threads.  choose_dims (me_api.cu) applies the same rule on the host. */
+__host__ __device__ constexpr int me_pool_mma_rows(int d) { return (d + 1 + 7) / 8 * 8; }
+__host__ __device__ constexpr int me_pool_mma_max_block(int d) { return d + 1 <= 16 ? 128 : (d + 1 <= 24 ? 64 : 32); }
+__host__ __device__ constexpr bool me_pool_mma_shape(int d, int poolw) { return poolw > 9 && d + 1 <= 32; }
 
 __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -674,7 +678,7 @@ __device__ __forceinline__ void pool_mma_update(const Chain<L> &c, const double 
                                                 double (*yb)[ME_YB_LD], double *pw) {
     constexpr int D = L::D, NR = L::NR, NC = L::NC, NOBS = L::NOBS;
     /* row blocks of [x - s, 1] (instantiated, never executed, for larger shapes: their block count is clamped) */
-    constexpr int NBX = (D + 1 + 7) / 8 <= ME_YB_ROWS / 8 ? (D + 1 + 7) / 8 : ME_YB_ROWS / 8;
+    constexpr int NBX = (D + 1 + 7) / 8 <= 4 ? (D + 1 + 7) / 8 : 4;
     constexpr int NBO = (NOBS + 7) / 8;            /* row blocks of the observables */
     const int lane = threadIdx.x & 31, r8 = lane >> 2, k4 = lane & 3, half = lane >> 4, colw = lane & 15;
     double acc[NBX * (NBX + 1) / 2][2];
@@ -842,13 +846,14 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
 #define ME_POOL_MMA 1            /* build-time experiment knob: 0 = warp_sum reductions for every shape beyond POOL_REG */
 #endif
     /* mid-sized shapes: pooled moments on the FP64 tensor cores (pool_mma_update); their CTAs are at most
-       ME_POOL_MMA_MAX_BLOCK threads (choose_dims in me_api.cu follows the same rule) */
-    constexpr bool POOL_MMA = ME_POOL_MMA && !POOL_REG && POOL_OK && L::D + 1 <= ME_YB_ROWS;
-    constexpr int POOL_WARPS = (POOL_MMA ? ME_POOL_MMA_MAX_BLOCK : ME_MAX_BLOCK) / 32;
+       me_pool_mma_max_block(D) threads (choose_dims in me_api.cu follows the same rule) */
+    constexpr bool POOL_MMA = ME_POOL_MMA && !POOL_REG && POOL_OK && me_pool_mma_shape(L::D, L::POOLW);
+    constexpr int POOL_MMA_BLOCK = me_pool_mma_max_block(L::D), YB_ROWS = POOL_MMA ? me_pool_mma_rows(L::D) : 1;
+    constexpr int POOL_WARPS = (POOL_MMA ? POOL_MMA_BLOCK : ME_MAX_BLOCK) / 32;
 
     __shared__ double pool_warp[POOL_WARPS][PW];
     __shared__ double pool_cta[POOL_MMA ? 1 : PW];
-    __shared__ double ybuf[POOL_MMA ? POOL_WARPS : 1][POOL_MMA ? ME_YB_ROWS : 1][ME_YB_LD];
+    __shared__ double ybuf[POOL_MMA ? POOL_WARPS : 1][YB_ROWS][ME_YB_LD];
     __shared__ MathTables tables;
     init_math_tables(tables);
     __syncthreads();
@@ -920,7 +925,7 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
 #define ME_EXPERIMENT_NO_POOL 0   /* build-time experiment knob (tests/scripts/c3_probe.py): what the pooled moments cost */
 #endif
     const bool pooling = POOL_OK && p.pool != nullptr && p.do_measure && !ME_EXPERIMENT_NO_POOL;
-    if (POOL_MMA && blockDim.x > ME_POOL_MMA_MAX_BLOCK) __trap();       /* the host never launches this (choose_dims) */
+    if (POOL_MMA && blockDim.x > POOL_MMA_BLOCK) __trap();       /* the host never launches this (choose_dims) */
     if (pooling && POOL_MMA) {
         for (int w = threadIdx.x; w < POOL_WARPS * PW; w += blockDim.x) (&pool_warp[0][0])[w] = 0.0;
         __syncthreads();
@@ -963,7 +968,7 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
     /* static shared-memory budget (48 KB): the pooled-moment staging of a large shape (9 x POOLW doubles, up to 43 KB at
        ME_MAX_POOLW) and the 16 KB table copy do not both fit; such shapes read the table through the read-only path */
     constexpr int TAB_ENTRIES = ME_LOGTAB_ENTRIES + ME_SINTAB_ENTRIES;       /* log table, then the sin/cos table */
-    constexpr int POOL_SMEM = POOL_MMA ? POOL_WARPS * (PW + ME_YB_ROWS * ME_YB_LD) * 8 : (ME_MAX_BLOCK / 32 + 1) * PW * 8;
+    constexpr int POOL_SMEM = POOL_MMA ? POOL_WARPS * (PW + YB_ROWS * ME_YB_LD) * 8 : (ME_MAX_BLOCK / 32 + 1) * PW * 8;
     constexpr bool TAB_FITS = POOL_SMEM + TAB_ENTRIES * 16 + 1024 <= 48 * 1024;
     constexpr bool TAB_SMEM = !STRICT && L::D > ME_SEG_MAX_D && TAB_FITS;
     __shared__ double2 logtab_s[TAB_SMEM ? TAB_ENTRIES : 1];

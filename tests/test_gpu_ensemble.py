@@ -244,6 +244,51 @@ def test_pooled_moments_mixed_shape_against_time_series():
     assert np.allclose(ps["observables_mean"][3:7], np.abs(c).mean(0), rtol=1e-10)
 
 
+@pytest.mark.parametrize("shape", ["1r8c_cylinder", "2r12c_user", "5r0c_user"])
+def test_tensor_core_pooled_moments_of_wider_shapes_against_time_series(shape):
+    """The FP64 tensor-core moment path (pool_mma_update) for shapes with two, three and four row blocks of [x - s, 1]
+    (D = 5, 17, 26: CTAs of 128 / 64 / 32 threads), ragged chain counts: every pooled word against the stored rows."""
+    import metropolisengine_b200 as me
+    quad = """
+__device__ double me_user_energy(const double* x, const double* cr, const double* ci, const double* k) {
+    double e = 0.0;
+    for (int i = 0; i < ME_NR; i++) e += (1.0 + 0.1 * i) * (x[i] - 0.2) * (x[i] - 0.2);
+    for (int j = 0; j < ME_NC; j++) e += (0.5 + 0.05 * j) * (cr[j] * cr[j] + ci[j] * ci[j]);
+    return e;
+}"""
+    if shape == "1r8c_cylinder":
+        nr, nc, n = 1, 8, 3000 + 13
+        energy = me.BuiltinEnergy("cylinder", 10.0, -1.0, 0.05, 1.0, reject=True)
+    elif shape == "2r12c_user":
+        nr, nc, n = 2, 12, 1500 + 5
+        energy = me.CudaEnergy(quad)
+    else:
+        nr, nc, n = 5, 0, 4096 + 31
+        energy = me.CudaEnergy(quad)
+    kw = dict(initial_real_params=np.zeros(nr), temp=.1, n_chains=n, seed=9)
+    if nc:
+        kw["initial_complex_params"] = np.zeros(nc, dtype=complex)
+    eng = me.MetropolisEngine(energy, **kw)
+    eng.run(55, 4)
+    eng.run(6, 3)
+    ps = eng.pooled_statistics()
+    assert ps["count"] == 61 * n
+    d = nr + 2 * nc
+    ts = eng.time_series().cpu().numpy()
+    x = np.transpose(ts[:, :d, :], (0, 2, 1)).reshape(-1, d)
+    assert np.allclose(ps["mean_real"], x[:, :nr].mean(0), rtol=0, atol=1e-12)
+    assert np.allclose(ps["cov_real"], np.atleast_2d(np.cov(x[:, :nr].T)), rtol=1e-9, atol=1e-13)
+    obs = [np.abs(x[:, :nr])]
+    if nc:
+        c = x[:, nr:nr + nc] + 1j * x[:, nr + nc:]
+        cm = c - c.mean(0)
+        assert np.allclose(ps["mean_complex"], c.mean(0), rtol=0, atol=1e-12)
+        assert np.allclose(ps["cov_complex"], cm.T @ cm.conj() / (c.shape[0] - 1), rtol=1e-9, atol=1e-12)
+        obs.append(np.abs(c))
+    obs.append(x[:, :nr] ** 2)
+    assert np.allclose(ps["observables_mean"], np.concatenate(obs, axis=1).mean(0), rtol=1e-10, atol=1e-13)
+
+
 @pytest.mark.parametrize("shape", ["real2", "mixed"])
 def test_pooled_moments_of_a_million_chain_ensemble_use_the_two_stage_reduction(shape):
     """SURVEY §8(d) C5 sizes: beyond 4,096 CTAs of per-CTA moment rows the pooled reduction goes through a coalesced
