@@ -40,10 +40,10 @@ constexpr int MAX_NC = 64;
 constexpr int MAX_N = 2 * MAX_NC;
 
 /* -------------------------------------------------------------------------------------------- step / init entry points */
-template <int NC, class Energy>
+template <int NC, class Energy, bool XP>
 __global__ void __launch_bounds__(k4::THREADS, 1) k4_steps(const __grid_constant__ StepParams p,
                                                            const __grid_constant__ k4::TensorMap bmap) {
-    k4::steps_body<NC, Energy>(p, &bmap);
+    k4::steps_body<NC, Energy, XP>(p, &bmap);
 }
 template <class Energy>
 __global__ void k4_init(const __grid_constant__ StepParams p, const double *x0, int broadcast, double sigma0) {
@@ -391,9 +391,12 @@ const unsigned short *k4_device_ztab(int device) {
 }
 
 /* ahead-of-time step kernels for the built-in functor */
-struct AotEntry { int nc; const void *steps; int smem; };
+/* steps_xp: the instantiation that parks the proposed state in TMEM (me_k4_device.cuh) — launches without a measure tail
+   and CTAs of a single tile */
+struct AotEntry { int nc; const void *steps, *steps_xp; int smem; };
 template <int NC> AotEntry aot_entry() {
-    return AotEntry{NC, (const void *)&k4_steps<NC, k4::EnergyCylinder>, (int)sizeof(k4::Smem<NC>)};
+    return AotEntry{NC, (const void *)&k4_steps<NC, k4::EnergyCylinder, false>,
+                    (const void *)&k4_steps<NC, k4::EnergyCylinder, true>, (int)sizeof(k4::Smem<NC>)};
 }
 
 }  // namespace
@@ -415,7 +418,7 @@ struct me_k4 {
     bool use_v1 = false;           /* ME_K4_V1=1: the first-version step kernel (n_c = 64, built-in functor) */
     bool no_tma = false;           /* ME_K4_NO_TMA=1, or the driver has no cuTensorMapEncodeTiled */
     /* step / init kernels: ahead-of-time (built-in functor) or runtime-compiled (user functor) */
-    const void *steps_rt = nullptr, *init_rt = nullptr;
+    const void *steps_rt = nullptr, *steps_xp_rt = nullptr, *init_rt = nullptr;
     CUfunction steps_drv = nullptr, init_drv = nullptr;
     int steps_smem = 0;
     std::string err;
@@ -462,7 +465,7 @@ static int k4_bind_builtin(me_k4 *e) {
     case 32: t = aot_entry<32>(); break;
     default: t = aot_entry<64>(); break;
     }
-    e->steps_rt = t.steps; e->steps_smem = t.smem; e->steps_drv = nullptr;
+    e->steps_rt = t.steps; e->steps_xp_rt = t.steps_xp; e->steps_smem = t.smem; e->steps_drv = nullptr;
     e->init_rt = (const void *)&k4_init<k4::EnergyCylinder>; e->init_drv = nullptr;
     return ME_OK;
 }
@@ -549,7 +552,7 @@ int me_k4_set_energy_source(me_k4 *e, const char *src, const double *consts, int
     }
     rc = me_rt_set_dynamic_smem(fn[0], (int)smem, log);
     if (rc != ME_OK) return k4_fail(e, rc, log);
-    e->steps_drv = fn[0]; e->init_drv = fn[1]; e->steps_rt = e->init_rt = nullptr; e->steps_smem = (int)smem;
+    e->steps_drv = fn[0]; e->init_drv = fn[1]; e->steps_rt = e->steps_xp_rt = e->init_rt = nullptr; e->steps_smem = (int)smem;
     memset(e->consts, 0, sizeof(e->consts));
     for (int i = 0; i < n_consts; i++) e->consts[i] = consts[i];
     e->use_reject = use_reject ? 1 : 0;
@@ -660,9 +663,13 @@ static int k4_launch_steps(me_k4 *e, int64_t n_steps, const double *s_a, float *
         rc = me_rt_launch(e->steps_drv, grid, k4::THREADS, e->steps_smem, stream, args, err);
     } else {
         /* the attribute is per device: set it before every launch (a host-side table write, no device work) */
-        cudaError_t ce = cudaFuncSetAttribute(e->steps_rt, cudaFuncAttributeMaxDynamicSharedMemorySize, e->steps_smem);
+        /* ME_K4_XP=0 / 1 forces one instantiation (tests, probes) */
+        const char *force = getenv("ME_K4_XP");
+        const bool xp = e->steps_xp_rt != nullptr && (force ? force[0] == '1' : (tail == nullptr || per <= k4::TILE));
+        const void *kern = xp ? e->steps_xp_rt : e->steps_rt;
+        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, e->steps_smem);
         if (ce == cudaSuccess)
-            ce = cudaLaunchKernel(e->steps_rt, dim3(grid), dim3(k4::THREADS), args, (size_t)e->steps_smem, (cudaStream_t)stream);
+            ce = cudaLaunchKernel(kern, dim3(grid), dim3(k4::THREADS), args, (size_t)e->steps_smem, (cudaStream_t)stream);
         if (ce != cudaSuccess) { rc = ME_ERR_CUDA; err = cudaGetErrorString(ce); }
     }
     if (rc != ME_OK) return k4_fail(e, rc, "k4_steps: " + err);

@@ -59,6 +59,16 @@ constexpr int TILE = 128;               /* chains per tile = MMA M = TMEM lanes 
 #ifndef K4_WIDE
 #define K4_WIDE 0
 #endif
+/* Two instantiations of the step kernel (template parameter XP):
+ *   XP = true   the proposed state x' = x + sigma Delta of a step is parked in TMEM (FP64 = two 32-bit columns per coordinate,
+ *               the thread's own lane) between the energy pass and the accept pass, which then is a TMEM load + the stores of
+ *               the accepted chains (measured: 10 steps of 32,768 chains 92.1 -> 85.7 us).  With n_c = 64 the two step
+ *               accumulators and x' fill all 512 TMEM columns, so the measure tail's accumulators reuse the step accumulators
+ *               and hand their sums over to global memory after EVERY tile (s_read): used for launches without a measure
+ *               tail and for CTAs of a single tile, where that costs nothing.
+ *   XP = false  the accept pass recomputes x' from the increments and the state tile; the tail's accumulators have their own
+ *               TMEM columns, accumulate over all tiles of the CTA and are written once (+14 us per measure otherwise at
+ *               two tiles per CTA). */
 constexpr int EPI_GROUPS = K4_WIDE ? 4 : 2;                 /* threads per chain in the epilogue (column groups) */
 constexpr int EPI_WARPS = 4 * EPI_GROUPS, GEN_WARPS = K4_WIDE ? 16 : 8;
 constexpr int GEN_PAR = GEN_WARPS * 32 / TILE;              /* generator threads per operand row */
@@ -222,6 +232,39 @@ template <> struct TmemLd<32> {
 };
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+/* registers -> this thread's TMEM lane, CNT consecutive 32-bit columns */
+template <int CNT> struct TmemSt;
+template <> struct TmemSt<8> {
+    __device__ __forceinline__ static void st(u32 taddr, const u32 *r) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                     : "memory");
+    }
+};
+template <> struct TmemSt<16> {
+    __device__ __forceinline__ static void st(u32 taddr, const u32 *r) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                     "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                     :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                     : "memory");
+    }
+};
+template <> struct TmemSt<32> {
+    __device__ __forceinline__ static void st(u32 taddr, const u32 *r) {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+            :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+               "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+               "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+               "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+            : "memory");
+    }
+};
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 /* -------------------------------------------------------------------------------------------- RNG (FP32 path) */
 struct U4 { u32 x, y, z, w; };
 __device__ __forceinline__ U4 philox(u32 c0, u32 c1, u32 c2, u32 c3, const u32 *rk) {
@@ -301,8 +344,9 @@ struct Smem {
     alignas(16) unsigned short ztab[ZTAB_ENTRIES];          /* BF16 quantile table of the generator               8 KB   */
     me::MathTables tables;
     u64 z_full[2], z_empty[2], acc_full[2], acc_empty[2], b_full;
-    u64 y_full, s_done, x_final, x_free;                    /* measure tail: operands written / moment MMAs complete / final
-                                                               states of the tile in xs / epilogue done reading xs */
+    u64 y_full, s_done, x_final, x_free, s_read;            /* measure tail: operands written / moment MMAs complete / final
+                                                               states of the tile in xs / epilogue done reading xs / the
+                                                               tile's moment sums have left TMEM */
     u32 tmem_slot;
 };
 
@@ -314,7 +358,7 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 /* -------------------------------------------------------------------------------------------- the step kernel */
-template <int NC, class Energy>
+template <int NC, class Energy, bool XP = false>
 __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap *bmap) {
     typedef Smem<NC> S_t;
     constexpr int N = S_t::N, K = N, HALVES = S_t::HALVES, CHUNKS = S_t::CHUNKS;
@@ -322,9 +366,15 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
     constexpr u32 A_LBO = TILE * 16, B_LBO = N * 16;
     constexpr u32 TCOLS = N < 32 ? 32 : N;        /* TMEM columns per accumulator */
     constexpr u32 IDESC = umma_idesc(N);
-    /* TMEM: two step accumulators + the moment accumulator S of the measure tail (N columns), a power of two in total */
-    constexpr u32 SCOL = 2 * TCOLS, CCOL = SCOL + N;          /* S, and 16 (identical) columns of first moments */
-    constexpr u32 TALLOC = CCOL + 16 <= 128 ? 128 : (CCOL + 16 <= 256 ? 256 : 512);
+    /* TMEM columns: two step accumulators [0, 2 TCOLS).  XP: the proposed state [2 TCOLS, 2 TCOLS + 2 N); the accumulators
+       of the measure tail — S (N columns) and 16 (identical) columns of first moments — reuse the step accumulators, which
+       are dead between the last step of a tile and the first step of the next one, and are emptied after every tile.
+       Otherwise S and the first moments follow the step accumulators and live for the whole launch.  A power of two. */
+    constexpr u32 XPCOL = 2 * TCOLS;
+    constexpr u32 SCOL = XP ? 0 : 2 * TCOLS, CCOL = XP ? TCOLS : SCOL + N;
+    constexpr u32 TUSED = XP ? 2 * TCOLS + 2 * N : CCOL + 16;
+    constexpr u32 TALLOC = TUSED <= 128 ? 128 : (TUSED <= 256 ? 256 : 512);
+    static_assert(TUSED <= 512 && N <= TCOLS && 16 <= TCOLS, "TMEM budget");
     constexpr u32 Y_LBO = N * 16;                 /* moment operands: [TILE / 8 chain chunks][N rows][8 chains] */
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     S_t &S = *reinterpret_cast<S_t *>(smem_raw);
@@ -345,6 +395,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
         mbar_init(&S.s_done, 1);
         mbar_init(&S.x_final, EPI_WARPS);
         mbar_init(&S.x_free, EPI_WARPS);
+        mbar_init(&S.s_read, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) tmem_alloc(&S.tmem_slot, TALLOC);
@@ -434,6 +485,8 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     if (issuer) {
                         /* Delta (+)= Z_stage . B_stage^T: CS / 2 x (M128, N, K16), accumulator `a` in TMEM */
                         if (h == 0 && it >= 2) mbar_wait(&S.acc_empty[a], (u32)(((it >> 1) - 1) & 1));
+                        /* the previous tile's moment sums sit in the accumulators until the epilogue has read them */
+                        if (XP && p.do_measure && t > 0 && s == 0 && h == 0) mbar_wait(&S.s_read, (u32)((t - 1) & 1));
                         mbar_wait(&S.z_full[h], (u32)(it & 1));
                         tc_fence_after();
 #pragma unroll
@@ -491,8 +544,8 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
 #pragma unroll
                     for (int k = 0; k < TILE / 16; k++) {
                         const u64 dh = umma_desc(yh + 2 * k * Y_LBO, Y_LBO), d1 = umma_desc(on + 2 * k * 256, 256);
-                        umma_bf16(tmem_base + SCOL, dh, dh, IDESC, (t > 0 || k > 0) ? 1u : 0u);
-                        umma_bf16(tmem_base + CCOL, dh, d1, IDESC1, (t > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(tmem_base + SCOL, dh, dh, IDESC, ((!XP && t > 0) || k > 0) ? 1u : 0u);
+                        umma_bf16(tmem_base + CCOL, dh, d1, IDESC1, ((!XP && t > 0) || k > 0) ? 1u : 0u);
                     }
 #pragma unroll
                     for (int k = 0; k < TILE / 16; k++) {
@@ -517,6 +570,9 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
         constexpr int MODES = NC / EPI_GROUPS;         /* modes per thread */
         constexpr int COLS = 2 * MODES;                /* accumulator columns per thread */
         constexpr int LDCH = COLS < 32 ? COLS : 32;    /* columns per tcgen05.ld */
+        constexpr int LD1 = XP ? (COLS < 16 ? COLS : 16) : LDCH;     /* energy pass: increments per load (x' words are held
+                                                                        until their store: 2 x LD1 registers) */
+        constexpr int LD2 = 2 * COLS < 32 ? 2 * COLS : 32;           /* accept pass: words of x' per load */
         const double s_a = *p.s_a;
         double f = (double)p.n_meas / (double)p.m;
         if (!(f > 200.0)) f = 200.0;
@@ -562,6 +618,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                 mbar_wait(&S.acc_full[acc], (u32)((it >> 1) & 1));
                 tc_fence_after();
                 const u32 tcol = tmem_base + acc * TCOLS + ((u32)(32 * q4) << 16) + (u32)(g * COLS);
+                const u32 xcol = tmem_base + XPCOL + ((u32)(32 * q4) << 16) + (u32)(2 * g * COLS);
                 bool accept = false;
                 double sg = sig;
                 if (act) {
@@ -570,23 +627,27 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                        registers across the decision */
                     double s0 = 0.0, s1 = 0.0, q = q_first;
 #pragma unroll
-                    for (int c = 0; c < COLS; c += LDCH) {
-                        u32 raw[LDCH];
-                        TmemLd<LDCH>::ld(tcol + (u32)c, raw);
+                    for (int c = 0; c < COLS; c += LD1) {
+                        u32 raw[LD1];
+                        TmemLd<LD1>::ld(tcol + (u32)c, raw);
                         tmem_ld_wait();
                         if (s == 0 && p.dbg_delta != nullptr) {
 #pragma unroll
-                            for (int k = 0; k < LDCH; k++)
+                            for (int k = 0; k < LD1; k++)
                                 p.dbg_delta[(long long)(g * COLS + c + k) * ld + ch] = __uint_as_float(raw[k]);
                         }
+                        u32 xw[2 * LD1];
 #pragma unroll
-                        for (int jj = 0; jj < LDCH / 2; jj++) {
+                        for (int jj = 0; jj < LD1 / 2; jj++) {
                             const int j = g * MODES + c / 2 + jj;
                             const double re = fma(sig, f32_bits_to_f64(raw[2 * jj]), S.xs[2 * j][m]);
                             const double im = fma(sig, f32_bits_to_f64(raw[2 * jj + 1]), S.xs[2 * j + 1][m]);
                             Energy::mode(q, re, im, p.consts, s0, s1);
                             q += 1.0;
+                            xw[4 * jj] = (u32)__double2loint(re); xw[4 * jj + 1] = (u32)__double2hiint(re);
+                            xw[4 * jj + 2] = (u32)__double2loint(im); xw[4 * jj + 3] = (u32)__double2hiint(im);
                         }
+                        if (XP) TmemSt<XP ? 2 * LD1 : 8>::st(xcol + (u32)(2 * c), xw);   /* x' parked in this thread's TMEM lane */
                     }
                     S.part[it & 1][g][0][m] = s0;
                     S.part[it & 1][g][1][m] = s1;
@@ -618,7 +679,23 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     if (s == 0 && g == 0 && p.dbg_scal != nullptr) { p.dbg_scal[ch] = za; p.dbg_scal[ld + ch] = u; }
                     /* ---- pass 2: accepted chains take the proposal (the same fma as pass 1: the accepted state is
                        bit-for-bit the one whose energy was evaluated) */
-                    if (__any_sync(0xffffffffu, accept)) {
+                    if (XP) {
+                        /* the very words whose energy was evaluated come back from TMEM */
+                        tmem_st_wait();
+                        if (__any_sync(0xffffffffu, accept)) {
+#pragma unroll
+                            for (int c = 0; c < 2 * COLS; c += LD2) {
+                                u32 w[LD2];
+                                TmemLd<LD2>::ld(xcol + (u32)c, w);
+                                tmem_ld_wait();
+                                if (accept) {
+#pragma unroll
+                                    for (int k = 0; k < LD2 / 2; k++)
+                                        S.xs[g * COLS + c / 2 + k][m] = __hiloint2double((int)w[2 * k + 1], (int)w[2 * k]);
+                                }
+                            }
+                        }
+                    } else if (__any_sync(0xffffffffu, accept)) {
 #pragma unroll
                         for (int c = 0; c < COLS; c += LDCH) {
                             u32 raw[LDCH];
@@ -733,39 +810,52 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     sc_acc[3] += (S.cscal[0][1] + S.cscal[1][1]) + (S.cscal[2][1] + S.cscal[3][1]);
                 }
                 mbar_wait(&S.s_done, (u32)(t & 1));           /* the moment MMAs have read both operand buffers */
+                /* ---------------------------------------------------- the CTA's pooled-moment partial.  XP: this tile's sums
+                   leave TMEM now (the accumulators are the next tile's step accumulators) and the later tiles of the CTA add
+                   theirs to the row; otherwise the sums of all tiles are written once, after the last tile */
+                if (XP || t == n_tiles - 1) {
+                    double *out = p.mom_part + (long long)blockIdx.x * (4 + N + N * N);
+                    auto stage_row = [](int i) { return (i & 1) ? NC + (i >> 1) : (i >> 1); };   /* interleaved -> [Re; Im] */
+                    tc_fence_after();
+                    const int n_row = 32 * q4 + lane;                  /* TMEM lane = row of S (interleaved coordinate) */
+                    if (32 * q4 < N) {
+                        if (g == 0) {                                  /* first moments: column CCOL of this lane */
+                            u32 raw[4];
+                            TmemLd<4>::ld(tmem_base + CCOL + ((u32)(32 * q4) << 16), raw);
+                            tmem_ld_wait();
+                            if (n_row < N) {
+                                double *o = out + 4 + stage_row(n_row);
+                                *o = f32_bits_to_f64(raw[0]) + ((XP && t > 0) ? *o : 0.0);
+                            }
+                        }
+                        /* S is symmetric: lane n writes S[n][c] to the transposed place, so that the 32 lanes of a store fall
+                           into two contiguous runs of 16 doubles */
+                        const u32 scol = tmem_base + SCOL + ((u32)(32 * q4) << 16) + (u32)(g * COLS);
+#pragma unroll
+                        for (int c = 0; c < COLS; c += LDCH) {
+                            u32 raw[LDCH];
+                            TmemLd<LDCH>::ld(scol + (u32)c, raw);
+                            tmem_ld_wait();
+                            if (n_row < N) {
+#pragma unroll
+                                for (int k = 0; k < LDCH; k++) {
+                                    double *o = out + 4 + N + stage_row(g * COLS + c + k) * N + stage_row(n_row);
+                                    *o = f32_bits_to_f64(raw[k]) + ((XP && t > 0) ? *o : 0.0);
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (XP && lane == 0) mbar_arrive(&S.s_read);       /* the accumulators may take the next tile's steps */
+                }
             }
         }
         if (p.do_measure) {
-            /* ------------------------------------------------------------ this CTA's partial of the pooled moments */
             double *out = p.mom_part + (long long)blockIdx.x * (4 + N + N * N);
-            auto stage_row = [](int i) { return (i & 1) ? NC + (i >> 1) : (i >> 1); };   /* interleaved -> [Re; Im] order */
             if (tid == 0) { out[0] = sc_acc[0]; out[1] = sc_acc[1]; out[2] = sc_acc[2]; out[3] = sc_acc[3]; }
-            tc_fence_after();
-            const int n_row = 32 * q4 + lane;                  /* TMEM lane = row of S (interleaved coordinate) */
-            if (32 * q4 < N) {
-                if (g == 0) {                                  /* first moments: column CCOL of this lane */
-                    u32 raw[4] = {0u, 0u, 0u, 0u};
-                    if (n_tiles > 0) { TmemLd<4>::ld(tmem_base + CCOL + ((u32)(32 * q4) << 16), raw); tmem_ld_wait(); }
-                    if (n_row < N) out[4 + stage_row(n_row)] = f32_bits_to_f64(raw[0]);
-                }
-                /* S is symmetric: lane n writes S[n][c] to the transposed place, so that the 32 lanes of a store fall
-                   into two contiguous runs of 16 doubles */
-                const u32 scol = tmem_base + SCOL + ((u32)(32 * q4) << 16) + (u32)(g * COLS);
-#pragma unroll
-                for (int c = 0; c < COLS; c += LDCH) {
-                    u32 raw[LDCH];
-                    if (n_tiles > 0) { TmemLd<LDCH>::ld(scol + (u32)c, raw); tmem_ld_wait(); }
-                    else {
-#pragma unroll
-                        for (int k = 0; k < LDCH; k++) raw[k] = 0u;
-                    }
-                    if (n_row < N) {
-#pragma unroll
-                        for (int k = 0; k < LDCH; k++)
-                            out[4 + N + stage_row(g * COLS + c + k) * N + stage_row(n_row)] = f32_bits_to_f64(raw[k]);
-                    }
-                }
-            }
+            if (n_tiles == 0)                                 /* a CTA without chains contributes zeros */
+                for (int i = tid; i < N + N * N; i += 32 * EPI_WARPS) out[4 + i] = 0.0;
         }
     }
 
