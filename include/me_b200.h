@@ -219,6 +219,17 @@ int me_comm_unique_id(unsigned char *id128);
 int me_comm_create(const unsigned char *id128, int32_t world, int32_t rank, int32_t device, me_comm **out);
 int me_comm_adopt(void *nccl_comm, int32_t world, int32_t rank, int32_t device, me_comm **out);
 int me_comm_destroy(me_comm *comm);
+/* One-shot all-reduce over NVLink peer memory for the ranks of one box: the pooled-moment vectors are
+ * latency-bound, so each rank publishes its vector in a window of its own HBM that the other ranks open through CUDA IPC, and
+ * ONE single-CTA kernel per rank waits for the peers' epoch flags and sums the windows in rank order (every rank gets
+ * bitwise the same sum; replays inside CUDA graphs).  Set-up: me_comm_peer_init (allocates the window for vectors of up to
+ * max_doubles, returns its 64-byte IPC handle) -> the host gathers the handles of all ranks -> me_comm_peer_connect(handles
+ * [world][64]) -> once EVERY rank has connected, me_comm_peer_enable(1).  Vectors that do not fit, and communicators
+ * without windows, go through NCCL.  me_comm_allreduce is the collective itself (sum, in place, stream-ordered). */
+int me_comm_peer_init(me_comm *comm, int64_t max_doubles, unsigned char *handle64);
+int me_comm_peer_connect(me_comm *comm, const unsigned char *handles);
+int me_comm_peer_enable(me_comm *comm, int32_t enable);
+int me_comm_allreduce(me_comm *comm, double *buf, int64_t n, void *stream);
 const char *me_comm_last_error(void);
 int me_allreduce_stats(me_engine *eng, me_comm *comm, double *inc, double *totals, int64_t n_samples, void *stream);
 /* The two halves of me_allreduce_stats, for hosts that overlap the collective with the next stepping launch (SURVEY.md

@@ -77,6 +77,10 @@ SIGNATURES = {
     "me_comm_last_error": (_cp, []),
     "me_allreduce_stats": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "me_reduce_stats": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
+    "me_comm_peer_init": (ctypes.c_int, [_vp, _i64, _vp]),
+    "me_comm_peer_connect": (ctypes.c_int, [_vp, _vp]),
+    "me_comm_peer_enable": (ctypes.c_int, [_vp, ctypes.c_int32]),
+    "me_comm_allreduce": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     "me_accumulate_stats": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "me_get_counters": (ctypes.c_int, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_u64)]),
     "me_set_counters": (ctypes.c_int, [_vp, _i64, _u64]),

@@ -1102,11 +1102,117 @@ NcclApi &nccl_api() {
 std::string g_comm_error;
 }  // namespace
 
+/* One-shot all-reduce over NVLink peer memory (the pooled-moment vectors are a few hundred bytes to 130 KB,
+ * i.e. latency-bound).  Every rank owns one window  [flags | 2 slots of max_doubles]  in its own HBM, opened by the other
+ * ranks of the box through CUDA IPC.  A collective is ONE kernel per rank of up to four CTAs, which walk the chunks of 2,048 doubles (each
+ * chunk with its own flags and epoch): publish the chunk in the slot of this epoch's parity, release the epoch number into the own
+ * flag (system scope), wait until every peer's flag shows the epoch (acquire loads over NVLink), then sum the W slots in
+ * RANK ORDER — so every rank holds bitwise the same result, whatever
+ * the arrival order — and write it back in place.  Two slots suffice: a rank can publish epoch e + 2 only after it has
+ * seen every peer's flag for e + 1, which a peer raises after it has finished reading epoch e.  The epoch counter lives on
+ * the device and is advanced by the kernel, so the collective replays inside CUDA graphs.  Waits are bounded (trap). */
+struct PeerWindow {
+    char *local = nullptr;              /* this rank's window (cudaMalloc) */
+    char **peers_dev = nullptr;         /* device array [world] of window base pointers (own entry = local) */
+    unsigned long long *epoch_dev = nullptr;
+    std::vector<void *> opened;         /* cudaIpcOpenMemHandle results, to close */
+    long long max_doubles = 0;
+    bool connected = false, enabled = false;
+};
+#define ME_PEER_CHUNK 2048              /* doubles per CTA of the collective: each chunk has its own flags and epoch */
+#define ME_PEER_MAX_CHUNKS 32
+#define ME_PEER_HEADER (2 * ME_PEER_MAX_CHUNKS * 8)     /* bytes in front of the slots: flag[2][ME_PEER_MAX_CHUNKS] (u64) */
+#define ME_PEER_THREADS 256
+#define ME_PEER_MAX_CTAS 4              /* the CTAs of one collective fit one SM together (the shared-covariance step kernel
+                                           leaves few SMs free): a CTA takes the chunks b, b + grid, ... in order, the same
+                                           order on every rank, so resident CTAs never wait for chunks of non-resident ones */
+
 struct me_comm {
     void *nccl = nullptr;      /* ncclComm_t */
     int world = 1, rank = 0, device = 0;
     bool owned = false;
+    PeerWindow peer;
 };
+
+/* the chunks of ME_PEER_CHUNK doubles are independent collectives (own flag, own epoch counter) */
+__global__ void __launch_bounds__(ME_PEER_THREADS) k_peer_allreduce(double *buf, long long n, char *const *peers, int world,
+                                                                    int rank, unsigned long long *epoch_ctr,
+                                                                    long long max_doubles) {
+    __shared__ unsigned long long ep;
+    const int n_chunks = (int)((n + ME_PEER_CHUNK - 1) / ME_PEER_CHUNK);
+    for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) ep = epoch_ctr[chunk] + 1ull;
+        __syncthreads();
+        const unsigned long long e = ep;
+        const int par = (int)(e & 1ull);
+        const long long lo = (long long)chunk * ME_PEER_CHUNK;
+        const long long hi = lo + ME_PEER_CHUNK < n ? lo + ME_PEER_CHUNK : n;
+        const long long slot_off = (long long)par * max_doubles;
+        double *mine = reinterpret_cast<double *>(peers[rank] + ME_PEER_HEADER) + slot_off;
+        for (long long i = lo + threadIdx.x; i < hi; i += ME_PEER_THREADS) mine[i] = buf[i];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long *flag = reinterpret_cast<unsigned long long *>(peers[rank]) + par * ME_PEER_MAX_CHUNKS + chunk;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(e) : "memory");
+            epoch_ctr[chunk] = e;
+        }
+        if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+            const unsigned long long *flag =
+                reinterpret_cast<const unsigned long long *>(peers[threadIdx.x]) + par * ME_PEER_MAX_CHUNKS + chunk;
+            unsigned long long seen = 0;
+            unsigned spin = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+                if (seen >= e) break;
+                __nanosleep(spin < 1024u ? 50u : 1000u);
+                if (++spin > (1u << 25)) __trap();         /* > 30 s: a peer never arrived; do not hang the GPU for good */
+            }
+        }
+        __syncthreads();
+        /* eight elements per thread, their loads from one rank in flight together; ranks in order (the sum is the same bits
+           on every rank); cache-volatile loads: the slots are rewritten every other epoch */
+        constexpr int EPT = ME_PEER_CHUNK / ME_PEER_THREADS;
+        double sum[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; k++) sum[k] = 0.0;
+        for (int r = 0; r < world; r++) {
+            const double *slot = reinterpret_cast<const double *>(peers[r] + ME_PEER_HEADER) + slot_off;
+            double v[EPT];
+#pragma unroll
+            for (int k = 0; k < EPT; k++) {
+                const long long i = lo + threadIdx.x + (long long)k * ME_PEER_THREADS;
+                v[k] = i < hi ? __ldcv(slot + i) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < EPT; k++) sum[k] += v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; k++) {
+            const long long i = lo + threadIdx.x + (long long)k * ME_PEER_THREADS;
+            if (i < hi) buf[i] = sum[k];
+        }
+    }
+}
+
+/* sum all-reduce of buf[0..n) over the ranks of `c`, in place, stream-ordered: peer windows when connected, else NCCL */
+static int comm_allreduce(me_comm *c, double *buf, long long n, cudaStream_t st, std::string &err) {
+    if (!c || c->world <= 1 || n <= 0) return ME_OK;
+    if (c->peer.enabled && n <= c->peer.max_doubles) {
+        const int chunks = (int)((n + ME_PEER_CHUNK - 1) / ME_PEER_CHUNK);
+        k_peer_allreduce<<<chunks < ME_PEER_MAX_CTAS ? chunks : ME_PEER_MAX_CTAS, ME_PEER_THREADS, 0, st>>>(buf, n, c->peer.peers_dev, c->world, c->rank,
+                                                             c->peer.epoch_dev, c->peer.max_doubles);
+        cudaError_t ce = cudaGetLastError();
+        if (ce != cudaSuccess) { err = std::string("k_peer_allreduce: ") + cudaGetErrorString(ce); return ME_ERR_CUDA; }
+        return ME_OK;
+    }
+    if (!c->nccl) { err = "no NCCL communicator and no peer windows"; return ME_ERR_STATE; }
+    NcclApi &nc = nccl_api();
+    const int rc = nc.allReduce(buf, buf, (size_t)n, 8 /* ncclDouble */, 0 /* ncclSum */, c->nccl, st);
+    if (rc != 0) { err = std::string("ncclAllReduce: ") + nc.getErrorString(rc); return ME_ERR_CUDA; }
+    return ME_OK;
+}
 
 extern "C" {
 
@@ -1155,9 +1261,89 @@ int me_comm_adopt(void *nccl_comm, int32_t world, int32_t rank, int32_t device, 
 
 int me_comm_destroy(me_comm *c) {
     if (!c) return ME_OK;
+    if (c->peer.local) {
+        DeviceGuard g(c->device);
+        for (void *q : c->peer.opened) cudaIpcCloseMemHandle(q);
+        if (c->peer.peers_dev) cudaFree(c->peer.peers_dev);
+        if (c->peer.epoch_dev) cudaFree(c->peer.epoch_dev);
+        cudaFree(c->peer.local);
+        cudaGetLastError();
+    }
     if (c->owned && c->nccl) nccl_api().commDestroy(c->nccl);
     delete c;
     return ME_OK;
+}
+
+/* Peer windows, step 1: allocate this rank's window for vectors of up to max_doubles and export its CUDA IPC handle
+   (64 bytes) — the host carries the handles of all ranks to every rank (any transport). */
+int me_comm_peer_init(me_comm *c, int64_t max_doubles, unsigned char *handle64) {
+    if (!c || !handle64 || max_doubles <= 0 || max_doubles > (int64_t)ME_PEER_CHUNK * ME_PEER_MAX_CHUNKS) return ME_ERR_INVALID;
+    if (c->peer.local) { g_comm_error = "peer window already initialised"; return ME_ERR_STATE; }
+    DeviceGuard g(c->device);
+    const size_t bytes = ME_PEER_HEADER + sizeof(double) * 2 * (size_t)max_doubles;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    if (cudaMalloc((void **)&c->peer.local, bytes) != cudaSuccess || cudaMemset(c->peer.local, 0, bytes) != cudaSuccess ||
+        cudaMalloc((void **)&c->peer.epoch_dev, sizeof(unsigned long long) * ME_PEER_MAX_CHUNKS) != cudaSuccess ||
+        cudaMemset(c->peer.epoch_dev, 0, sizeof(unsigned long long) * ME_PEER_MAX_CHUNKS) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&h, c->peer.local) != cudaSuccess) {
+        g_comm_error = std::string("me_comm_peer_init: ") + cudaGetErrorString(cudaGetLastError());
+        if (c->peer.local) cudaFree(c->peer.local);
+        if (c->peer.epoch_dev) cudaFree(c->peer.epoch_dev);
+        c->peer.local = nullptr; c->peer.epoch_dev = nullptr;
+        cudaGetLastError();
+        return ME_ERR_CUDA;
+    }
+    c->peer.max_doubles = max_doubles;
+    memcpy(handle64, &h, 64);
+    return ME_OK;
+}
+
+/* step 2: open the windows of all ranks (handles[world][64], own entry ignored).  Collective in spirit: every rank must
+   succeed before any rank enables the windows (step 3), so the host agrees on the outcome in between. */
+int me_comm_peer_connect(me_comm *c, const unsigned char *handles) {
+    if (!c || !handles || !c->peer.local) return ME_ERR_INVALID;
+    DeviceGuard g(c->device);
+    std::vector<char *> ptrs((size_t)c->world, nullptr);
+    for (int r = 0; r < c->world; r++) {
+        if (r == c->rank) { ptrs[r] = c->peer.local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)r, 64);
+        void *q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            g_comm_error = std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " +
+                           cudaGetErrorString(cudaGetLastError());
+            return ME_ERR_CUDA;
+        }
+        c->peer.opened.push_back(q);
+        ptrs[r] = (char *)q;
+    }
+    if (cudaMalloc((void **)&c->peer.peers_dev, sizeof(char *) * (size_t)c->world) != cudaSuccess ||
+        cudaMemcpy(c->peer.peers_dev, ptrs.data(), sizeof(char *) * (size_t)c->world, cudaMemcpyHostToDevice) != cudaSuccess) {
+        g_comm_error = std::string("me_comm_peer_connect: ") + cudaGetErrorString(cudaGetLastError());
+        return ME_ERR_CUDA;
+    }
+    c->peer.connected = true;
+    return ME_OK;
+}
+
+/* step 3: route the collectives of this communicator through the peer windows (enable != 0) or through NCCL */
+int me_comm_peer_enable(me_comm *c, int32_t enable) {
+    if (!c) return ME_ERR_INVALID;
+    if (enable && !c->peer.connected) { g_comm_error = "peer windows are not connected"; return ME_ERR_STATE; }
+    c->peer.enabled = enable != 0;
+    return ME_OK;
+}
+
+/* sum all-reduce of buf[0..n) doubles over the ranks, in place, stream-ordered (peer windows when enabled and n fits, else
+   NCCL); what me_allreduce_stats / me_accumulate_stats use, exported for the shared-covariance path's moment vector */
+int me_comm_allreduce(me_comm *c, double *buf, int64_t n, void *stream) {
+    if (!c || !buf || n < 0) return ME_ERR_INVALID;
+    DeviceGuard g(c->device);
+    std::string err;
+    const int rc = comm_allreduce(c, buf, n, (cudaStream_t)stream, err);
+    if (rc != ME_OK) g_comm_error = err;
+    return rc;
 }
 
 const char *me_comm_last_error(void) { return g_comm_error.c_str(); }
@@ -1194,9 +1380,9 @@ int me_accumulate_stats(me_engine *e, me_comm *comm, double *inc, double *totals
     const int words = e->lay.POOL_WORDS;
     cudaStream_t st = (cudaStream_t)stream;
     if (comm && comm->world > 1) {
-        NcclApi &n = nccl_api();
-        const int rc = n.allReduce(inc, inc, (size_t)(words + 1), 8 /* ncclDouble */, 0 /* ncclSum */, comm->nccl, st);
-        if (rc != 0) return fail(e, ME_ERR_CUDA, std::string("ncclAllReduce: ") + n.getErrorString(rc));
+        std::string err;
+        const int rc = comm_allreduce(comm, inc, words + 1, st, err);
+        if (rc != ME_OK) return fail(e, rc, err);
     }
     k_accumulate<<<(words + 1 + 127) / 128, 128, 0, st>>>(totals, inc, words + 1);
     cudaError_t ce = cudaGetLastError();

@@ -646,6 +646,8 @@ static int k4_launch_steps(me_k4 *e, int64_t n_steps, const double *s_a, float *
     }
     long long per = (e->cfg.n_chains + avail - 1) / avail;
     per = (per + 31) / 32 * 32;
+    /* (whole tiles per CTA — 32,768 chains as 128 CTAs x 2 full tiles, leaving 20 SMs to the side stream — were measured:
+       88.4 us per 10 steps against 85.9 us for 147 CTAs x (128 + 96): a partly filled tile is faster than a full one) */
     p.chains_per_cta = per;
     const int grid = (int)((e->cfg.n_chains + per - 1) / per);
     if (grid_out) *grid_out = grid;

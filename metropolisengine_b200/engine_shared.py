@@ -80,6 +80,7 @@ class SharedCovarianceEngine:
         lo, hi = parallel.shard_range(self.n_chains_total, self._rank, self._world)
         self.chain_offset, self.n_chains = lo, hi - lo
         self._distributed = bool(distributed) and self._world > 1
+        self._comm = None            # library-side communicator (me_comm) of the moment all-reduce, created on first use
         self.temp, self.target_acceptance = temp, target_acceptance
         self.alpha, self.m, self.ratio = adaptation_constants(1, nc, target_acceptance)
         self.params_names = list(params_names) if params_names else ["param_" + str(i) for i in range(1 + nc)]
@@ -139,6 +140,8 @@ class SharedCovarianceEngine:
             self._check(self._lib.me_k4_set_reserved_sms(self._h, 1))
         self._inc = torch.zeros(2, dtype=torch.complex128, device=dev)
         self._psd_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self._distributed:              # collective set-up (every rank constructs its engine)
+            self._comm = parallel.library_comm(self._lib, dev.index) or False
         per_chain = xr.ndim == 2 or xc.ndim == 2
         if per_chain:
             full = np.zeros((lay.D, self.n_chains_total))
@@ -336,7 +339,14 @@ class SharedCovarianceEngine:
         def tail(stream, idx):
             """all-reduce + accumulation (multi-GPU) and the factor refresh, all stream-ordered on `stream`"""
             if not fused:
-                parallel.allreduce_sum_(torch.view_as_real(inc))        # the path's only collective (NCCL)
+                # the path's only collective: inside the library (one-shot sum over the NVLink peer windows, else NCCL)
+                if self._comm is None:
+                    self._comm = parallel.library_comm(_lib.load(), self.device.index) or False
+                if self._comm:
+                    if _lib.load().me_comm_allreduce(self._comm, _ptr(inc), 2 * inc.numel(), self._stream()) != 0:
+                        raise _lib.MeError("me_comm_allreduce: " + _lib.load().me_comm_last_error().decode())
+                else:
+                    parallel.allreduce_sum_(torch.view_as_real(inc))
                 self._mom[0] += inc[0]
                 self._mom[2:] += inc[2:]
                 snap[:-2].copy_(self._mom)

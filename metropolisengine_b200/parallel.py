@@ -127,5 +127,47 @@ def library_comm(lib, device_index, group=None):
     rc = lib.me_comm_create(ident, world_size, rank, device_index, ctypes.byref(comm))
     if rc != 0:
         raise RuntimeError("me_comm_create: " + lib.me_comm_last_error().decode())
+    connect_peer_windows(lib, comm, rank, world_size, device_index, group)
     _LIBRARY_COMMS[key] = comm
     return comm
+
+
+PEER_WINDOW_DOUBLES = 1 << 15      # vectors up to 256 KB go through the peer windows (C4's moment vector: 8,328 complex words)
+
+
+def connect_peer_windows(lib, comm, rank, world_size, device_index, group=None):
+    """Set up the one-shot NVLink all-reduce of a library communicator (``me_comm_peer_*``, include/me_b200.h): every rank
+    allocates its window and exports a CUDA IPC handle, torch.distributed carries the handles, every rank opens its
+    peers' windows, and only when ALL ranks succeeded are the windows switched on (otherwise — ranks on different
+    boxes, IPC not permitted, ``ME_PEER_ALLREDUCE=0`` — the collectives stay on NCCL).  Returns whether they are on."""
+    import ctypes
+    import os
+    import torch
+    import torch.distributed as dist
+    want = os.environ.get("ME_PEER_ALLREDUCE", "1") != "0"
+    dev = torch.device("cuda", device_index)
+    handle = (ctypes.c_ubyte * 64)()
+    ok = want and lib.me_comm_peer_init(comm, PEER_WINDOW_DOUBLES, handle) == 0
+    mine = torch.tensor(list(bytes(handle)) + [1 if ok else 0], dtype=torch.uint8, device=dev)
+    every = torch.empty((world_size, 65), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(every, mine, group=group)
+    every = every.cpu().numpy()
+    ok = bool(every[:, 64].all())
+    if ok:
+        handles = (ctypes.c_ubyte * (64 * world_size)).from_buffer_copy(every[:, :64].tobytes())
+        ok = lib.me_comm_peer_connect(comm, handles) == 0
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    ok = int(flag.item()) == 1
+    if ok:
+        ok = lib.me_comm_peer_enable(comm, 1) == 0
+    _PEER_WINDOWS[comm.value] = ok
+    return ok
+
+
+_PEER_WINDOWS = {}
+
+
+def peer_windows_on(comm):
+    """Whether the collectives of this library communicator run over the NVLink peer windows."""
+    return bool(comm is not None and _PEER_WINDOWS.get(comm.value, False))

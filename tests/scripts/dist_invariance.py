@@ -61,6 +61,49 @@ def main():
         ok = ok and gps["count"] == r2["count"] == 13 * 25 * n
         for k in ("mean_real", "cov_real", "observables_mean"):
             ok = ok and np.allclose(gps[k], r2[k], rtol=1e-11, atol=1e-13)
+    # the library's collective itself (me_comm_allreduce): one-shot sum over the NVLink peer windows when the ranks could open
+    # each other's windows (else NCCL) — exact small-integer sums, back to back without host synchronisation, odd sizes,
+    # and replayed from a CUDA graph
+    import ctypes
+    from metropolisengine_b200 import _lib, parallel
+    lib = _lib.load()
+    comm = parallel.library_comm(lib, local)
+    peer_on = parallel.peer_windows_on(comm)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for size in (1, 13, 601, 8328 * 2, 32768):
+        base = torch.arange(size, dtype=torch.float64, device="cuda")
+        for rep in range(40):
+            buf = base * (rank + 1) + rep
+            assert lib.me_comm_allreduce(comm, ctypes.c_void_p(buf.data_ptr()), size, st) == 0
+            want = base * (world * (world + 1) // 2) + rep * world
+            ok = ok and torch.equal(buf, want)
+    gbuf = torch.zeros(601, dtype=torch.float64, device="cuda")
+    src = torch.arange(601, dtype=torch.float64, device="cuda") * (rank + 1)
+    torch.cuda.synchronize()
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        gbuf.copy_(src)
+        gs = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        assert lib.me_comm_allreduce(comm, ctypes.c_void_p(gbuf.data_ptr()), 601, gs) == 0
+    for rep in range(5):
+        cg.replay()
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(gbuf, torch.arange(601, dtype=torch.float64, device="cuda") * (world * (world + 1) // 2))
+    # shared-covariance path: the pooled covariance (all-reduced moments -> identical Cholesky on every rank) must be the
+    # same on all ranks bit for bit, and the sampler must be healthy
+    k4 = me.SharedCovarianceEngine(energy_consts=(10.0, -1.0, 0.05, 1.0), temp=.1, n_chains=128 * 6 * world, seed=3,
+                                   record=False, n_complex=16, distributed=True, sampling_width=0.02)
+    k4.run(56, 4)
+    k4.synchronize_refresh()
+    torch.cuda.synchronize()
+    cov = torch.view_as_real(k4._cov_c).clone()
+    clo, chi = cov.clone(), cov.clone()
+    dist.all_reduce(clo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(chi, op=dist.ReduceOp.MAX)
+    ok = ok and torch.equal(clo, chi) and bool(torch.isfinite(cov).all()) and int(k4._psd_status.item()) == 0
+    ok = ok and 0.05 < k4.acceptance_rate < 0.9
+    if rank == 0:
+        print("peer windows (one-shot NVLink all-reduce):", "on" if peer_on else "off (NCCL)")
     # every rank must hold the same pooled numbers
     v = torch.tensor(np.concatenate([ps["mean_real"], np.diag(ps["cov_real"])]), device="cuda")
     lo, hi = v.clone(), v.clone()
