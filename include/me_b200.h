@@ -306,6 +306,9 @@ int me_k4_measure(me_k4 *eng, double *ts, int64_t ts_row, void *stream);
  * refresh that runs later on another stream. */
 int me_k4_moments(me_k4 *eng, const double *shift, double *scratch, int64_t scratch_doubles, double *inc, double *mom_accum,
                   double *snapshot, void *stream);
+/* Multi-GPU: after `inc` has been summed over the ranks (me_comm_allreduce), advance the running moments and write the
+ * snapshot the factor refresh reads — on one GPU me_k4_moments / me_k4_step_measure do this themselves. */
+int me_k4_accumulate_moments(me_k4 *eng, const double *inc, double *mom_accum, double *snapshot, void *stream);
 /* Pooled moments -> shared covariance (+ sigma^2/n regulariser, ME:418,425) -> Cholesky -> BF16 operand, one
  * launch, no host sync.  mom / inc are complex (double pairs): mom = [N, -, sum a, sum a^2, sum c[64], sum c c^H
  * [64x64]] about a fixed shift, inc = [chains measured now, sum of their sigma]; cov_c receives the 64x64 complex

@@ -97,6 +97,7 @@ SIGNATURES = {
     "me_k4_measure": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     "me_k4_moments": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "me_k4_refactor": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "me_k4_accumulate_moments": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "me_k4_set_factor": (ctypes.c_int, [_vp, _vp]),
     "me_k4_set_reserved_sms": (ctypes.c_int, [_vp, _i32]),
     "me_k4_normal_table": (ctypes.c_int, [_vp, _i32]),

@@ -710,6 +710,18 @@ static void k4_moments_finish(me_k4 *e, double *scratch, int n_parts, double *in
                                                                        reinterpret_cast<double2 *>(snapshot), nc);
 }
 
+/* multi-GPU: after the all-reduce of `inc` (me_comm_allreduce) the running moments advance and the snapshot for the
+ * factor refresh is written — what stage 2b does by itself on one GPU */
+__global__ void k4_moments_accumulate(const double2 *inc, double2 *mom, double2 *snap, int mw) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= mw) return;
+    const double2 v = inc[w];
+    double2 m = mom[w];
+    if (w != 1) { m.x += v.x; m.y += v.y; mom[w] = m; }
+    snap[w] = m;
+    if (w < 2) snap[mw + w] = v;
+}
+
 /* n_steps x step_all() + measure() in ONE launch of the step kernel, then the two small reduction kernels of the pooled
  * moments: the block a sampling loop repeats (ME README loop: step_all x k, measure).  The per-chain measurement is the
  * one of me_k4_measure bit for bit; the second moments S = sum Y Y^T are formed on the tensor cores from Y split into two
@@ -770,6 +782,18 @@ int me_k4_moments(me_k4 *e, const double *shift, double *scratch, int64_t scratc
     cudaError_t ce = cudaGetLastError();
     cudaSetDevice(prev);
     if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_moments: ") + cudaGetErrorString(ce));
+    return ME_OK;
+}
+
+int me_k4_accumulate_moments(me_k4 *e, const double *inc, double *mom_accum, double *snapshot, void *stream) {
+    if (!e || !inc || !mom_accum || !snapshot) return ME_ERR_INVALID;
+    const int mw = momw(e->nc);
+    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(e->cfg.device);
+    k4_moments_accumulate<<<(mw + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2 *>(inc), reinterpret_cast<double2 *>(mom_accum), reinterpret_cast<double2 *>(snapshot), mw);
+    const cudaError_t ce = cudaGetLastError();
+    cudaSetDevice(prev);
+    if (ce != cudaSuccess) return k4_fail(e, ME_ERR_CUDA, std::string("k4_moments_accumulate: ") + cudaGetErrorString(ce));
     return ME_OK;
 }
 

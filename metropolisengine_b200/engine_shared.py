@@ -347,10 +347,8 @@ class SharedCovarianceEngine:
                         raise _lib.MeError("me_comm_allreduce: " + _lib.load().me_comm_last_error().decode())
                 else:
                     parallel.allreduce_sum_(torch.view_as_real(inc))
-                self._mom[0] += inc[0]
-                self._mom[2:] += inc[2:]
-                snap[:-2].copy_(self._mom)
-                snap[-2:].copy_(inc[:2])
+                self._launch(self._lib.me_k4_accumulate_moments(self._h, _ptr(inc), _ptr(self._mom), _ptr(snap),
+                                                                ctypes.c_void_p(stream.cuda_stream)))
             if refresh:
                 self._launch(self._lib.me_k4_refactor(self._h, _ptr(snap), _ptr(snap[mw:]), n, _ptr(self._cov_c),
                                                       _ptr(self._cov_a), _ptr(self._factors[idx]),
