@@ -561,6 +561,7 @@ def c5_pass(ctx, steps=3, warmup=3, total_chains=1 << 20, launches=20):
     """BASELINE config 5 (strong scaling): 2^20 xy-well chains in TOTAL sharded over the ranks, 100 steps per launch
     (10 x (10 steps + measure)), pooled-moment reduction + all-reduce across ranks after EVERY launch, issued inside
     the library; each launch is one CUDA-graph replay (run_graphed)."""
+    from metropolisengine_b200 import parallel
     wl = WORKLOADS["c2"]
     eng, _ = make_engine(ctx, wl, total_chains, record=False, seed=7)
     M, spm = 10, 10
@@ -587,6 +588,8 @@ def c5_pass(ctx, steps=3, warmup=3, total_chains=1 << 20, launches=20):
            "how": "one CUDA graph per pass: %d x [me_run -> me_reduce_stats (fixed-order reduction of the per-CTA rows) -> "
                   "me_accumulate_stats on a side stream (NCCL all-reduce inside the library, device-resident totals), which "
                   "overlaps the next me_run]; one D2H of the totals at the end" % launches,
+           "collective": ("one-shot sum over NVLink peer windows (me_comm_peer_*)" if parallel.peer_windows_on(eng._library_comm())
+                          else ("NCCL all-reduce inside the library" if ctx.world > 1 else "none (one rank)")),
            "eager_value": total_chains * M * spm * launches * steps / (ms_e * 1e-3),
            "pooled_var_x0": float(ps["cov_real"][0, 0]), "pooled_count": ps["count"]}
     del eng

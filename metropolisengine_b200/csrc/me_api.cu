@@ -1104,7 +1104,7 @@ std::string g_comm_error;
 
 /* One-shot all-reduce over NVLink peer memory (the pooled-moment vectors are a few hundred bytes to 130 KB,
  * i.e. latency-bound).  Every rank owns one window  [flags | 2 slots of max_doubles]  in its own HBM, opened by the other
- * ranks of the box through CUDA IPC.  A collective is ONE kernel per rank of up to four CTAs, which walk the chunks of 2,048 doubles (each
+ * ranks of the box through CUDA IPC.  A collective is ONE kernel per rank of up to four CTAs, which walk the chunks of 1,024 doubles (each
  * chunk with its own flags and epoch): publish the chunk in the slot of this epoch's parity, release the epoch number into the own
  * flag (system scope), wait until every peer's flag shows the epoch (acquire loads over NVLink), then sum the W slots in
  * RANK ORDER — so every rank holds bitwise the same result, whatever
@@ -1119,7 +1119,7 @@ struct PeerWindow {
     long long max_doubles = 0;
     bool connected = false, enabled = false;
 };
-#define ME_PEER_CHUNK 2048              /* doubles per CTA of the collective: each chunk has its own flags and epoch */
+#define ME_PEER_CHUNK 1024              /* doubles per chunk of the collective: each chunk has its own flags and epoch */
 #define ME_PEER_MAX_CHUNKS 32
 #define ME_PEER_HEADER (2 * ME_PEER_MAX_CHUNKS * 8)     /* bytes in front of the slots: flag[2][ME_PEER_MAX_CHUNKS] (u64) */
 #define ME_PEER_THREADS 256
@@ -1171,22 +1171,29 @@ __global__ void __launch_bounds__(ME_PEER_THREADS) k_peer_allreduce(double *buf,
             }
         }
         __syncthreads();
-        /* eight elements per thread, their loads from one rank in flight together; ranks in order (the sum is the same bits
+        /* four elements per thread; ranks in order (the sum is the same bits
            on every rank); cache-volatile loads: the slots are rewritten every other epoch */
         constexpr int EPT = ME_PEER_CHUNK / ME_PEER_THREADS;
         double sum[EPT];
 #pragma unroll
         for (int k = 0; k < EPT; k++) sum[k] = 0.0;
-        for (int r = 0; r < world; r++) {
-            const double *slot = reinterpret_cast<const double *>(peers[r] + ME_PEER_HEADER) + slot_off;
-            double v[EPT];
+        for (int r0 = 0; r0 < world; r0 += 4) {            /* the loads from four ranks in flight together */
+            double v[4][EPT];
 #pragma unroll
-            for (int k = 0; k < EPT; k++) {
-                const long long i = lo + threadIdx.x + (long long)k * ME_PEER_THREADS;
-                v[k] = i < hi ? __ldcv(slot + i) : 0.0;
+            for (int q = 0; q < 4; q++) {
+                const int r = r0 + q < world ? r0 + q : rank;
+                const double *slot = reinterpret_cast<const double *>(peers[r] + ME_PEER_HEADER) + slot_off;
+#pragma unroll
+                for (int k = 0; k < EPT; k++) {
+                    const long long i = lo + threadIdx.x + (long long)k * ME_PEER_THREADS;
+                    v[q][k] = (i < hi && r0 + q < world) ? __ldcv(slot + i) : 0.0;
+                }
             }
 #pragma unroll
-            for (int k = 0; k < EPT; k++) sum[k] += v[k];
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int k = 0; k < EPT; k++)
+                    if (r0 + q < world) sum[k] += v[q][k];
         }
 #pragma unroll
         for (int k = 0; k < EPT; k++) {

@@ -132,7 +132,11 @@ def library_comm(lib, device_index, group=None):
     return comm
 
 
-PEER_WINDOW_DOUBLES = 1 << 15      # vectors up to 256 KB go through the peer windows (C4's moment vector: 8,328 complex words)
+# Vectors up to this many doubles go through the peer windows: the pooled-moment vectors of the fused engines (<= 601
+# doubles, one chunk = one CTA).  The 16,656-double moment vector of the shared-covariance path stays on NCCL: its step kernel
+# leaves one SM to the side stream and there NCCL's all-reduce measured faster at 8 ranks (bench c4: 1.60e10 against
+# 1.35e10 chain-steps/s); ME_PEER_WINDOW_DOUBLES raises the limit (<= 32768).
+PEER_WINDOW_DOUBLES = 1 << 10
 
 
 def connect_peer_windows(lib, comm, rank, world_size, device_index, group=None):
@@ -147,7 +151,8 @@ def connect_peer_windows(lib, comm, rank, world_size, device_index, group=None):
     want = os.environ.get("ME_PEER_ALLREDUCE", "1") != "0"
     dev = torch.device("cuda", device_index)
     handle = (ctypes.c_ubyte * 64)()
-    ok = want and lib.me_comm_peer_init(comm, PEER_WINDOW_DOUBLES, handle) == 0
+    limit = int(os.environ.get("ME_PEER_WINDOW_DOUBLES", PEER_WINDOW_DOUBLES))
+    ok = want and lib.me_comm_peer_init(comm, limit, handle) == 0
     mine = torch.tensor(list(bytes(handle)) + [1 if ok else 0], dtype=torch.uint8, device=dev)
     every = torch.empty((world_size, 65), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(every, mine, group=group)

@@ -18,6 +18,9 @@ def test_sharded_ensemble_is_bit_identical_and_pooled_stats_allreduce():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "scripts",
                                                                                "dist_invariance.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    # windows wide enough that every vector of the script — also the multi-chunk ones and the shared-covariance path's
+    # moment vector — goes through the one-shot NVLink all-reduce (by default only vectors up to 1,024 doubles do)
+    env = dict(os.environ, ME_PEER_WINDOW_DOUBLES="32768")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "OK" in out.stdout
