@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ME_ABI_VERSION 4
+#define ME_ABI_VERSION 5
 
 enum me_status_code {
     ME_OK = 0,
