@@ -357,6 +357,41 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+/* Per-chain measurement of CNT complex modes j0 .. j0 + CNT - 1 of chain `m` of the tile (global chain `ch`): running means
+ * and observable means (ME:404-414) of the chain's words in the state block, and the modes' columns of the time-series row.
+ * Called by the epilogue threads for the first half of their modes and by the generator threads — idle at that point — for the
+ * second half, so twice as many threads keep the read-modify-write traffic of the tail in flight. */
+template <int NC, int CNT>
+__device__ __forceinline__ void measure_modes(const StepParams &p, const Layout &L, const double (*xs)[TILE], int m,
+                                              long long ch, long long ld, int j0, double inv_n, double shrink, double *row) {
+    constexpr int JB = CNT < 8 ? CNT : 8;     /* modes per batch: the batch's global loads are all in flight before the first
+                                                 store (stores to the state block may alias) */
+    /* running pointers (one 64-bit add per mode each) instead of a 64-bit multiply per address */
+    double *pmr = p.state + (long long)(L.MEAN + 1 + j0) * ld + ch, *pmi = pmr + (long long)NC * ld;
+    double *pob = p.state + (long long)(L.OBSM + 1 + j0) * ld + ch;
+    double *prr = row ? row + (long long)(1 + j0) * ld : nullptr, *pri = row ? prr + (long long)NC * ld : nullptr;
+#pragma unroll
+    for (int jb = 0; jb < CNT; jb += JB) {
+        double mr[JB], mi[JB], ob[JB];
+#pragma unroll
+        for (int b = 0; b < JB; b++) { mr[b] = pmr[b * ld]; mi[b] = pmi[b * ld]; ob[b] = pob[b * ld]; }
+#pragma unroll
+        for (int b = 0; b < JB; b++) {
+            const int j = j0 + jb + b;
+            const double re = xs[2 * j][m], im = xs[2 * j + 1][m];
+            *pmr = fma(re, inv_n, mr[b] * shrink);
+            *pmi = fma(im, inv_n, mi[b] * shrink);
+            *pob = fma(cabs_fast(re, im), inv_n, ob[b] * shrink);
+            pmr += ld; pmi += ld; pob += ld;
+            if (row) {
+                __stcs(prr, re);
+                __stcs(pri, im);
+                prr += ld; pri += ld;
+            }
+        }
+    }
+}
+
 /* -------------------------------------------------------------------------------------------- the step kernel */
 template <int NC, class Energy, bool XP = false>
 __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap *bmap) {
@@ -526,6 +561,14 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                     *reinterpret_cast<unsigned short *>(yh_row + (2 * j + 1) * 16) = (unsigned short)(hi_pair >> 16);
                     ylp[jj] = bf16x2_rn(yr - bf16_lo_to_float(hi_pair), yi - bf16_hi_to_float(hi_pair));
                 }
+                if (EPI_GROUPS == GEN_PAR && act) {
+                    /* the second half of the modes of (chain m, column group c_par): their per-chain measurement */
+                    constexpr int EM = NC / EPI_GROUPS, SHARE = EM / 2;
+                    const double dn = (double)p.n_meas_after, inv_n = 1.0 / dn, shrink = (dn - 1.0) * inv_n;
+                    const long long chg = base + m;
+                    double *row = p.record ? p.ts + p.ts_row * (long long)(L.D + 2) * ld + chg : nullptr;
+                    measure_modes<NC, SHARE>(p, L, S.xs, m, chg, ld, c_par * EM + (EM - SHARE), inv_n, shrink, row);
+                }
                 mbar_wait(&S.x_free, (u32)(t & 1));           /* every epilogue thread is done with the state tile */
 #pragma unroll
                 for (int jj = 0; jj < GM; jj++) {
@@ -568,6 +611,7 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
         const int q4 = warp & 3, g = warp >> 2;        /* lane quarter (TMEM lanes 32 q4 ..), column group */
         const int m = 32 * q4 + lane;                  /* chain within the tile = TMEM lane */
         constexpr int MODES = NC / EPI_GROUPS;         /* modes per thread */
+        constexpr int GEN_SHARE = (EPI_GROUPS == GEN_PAR) ? MODES / 2 : 0;   /* modes whose measurement the generators take */
         constexpr int COLS = 2 * MODES;                /* accumulator columns per thread */
         constexpr int LDCH = COLS < 32 ? COLS : 32;    /* columns per tcgen05.ld */
         constexpr int LD1 = XP ? (COLS < 16 ? COLS : 16) : LDCH;     /* energy pass: increments per load (x' words are held
@@ -745,36 +789,8 @@ __device__ __forceinline__ void steps_body(const StepParams &p, const TensorMap 
                 /* ---------------------------------------------------------------- measure tail of this tile */
                 const double dn = (double)p.n_meas_after, inv_n = 1.0 / dn, shrink = (dn - 1.0) * inv_n;
                 double *row = p.record ? p.ts + p.ts_row * (long long)(L.D + 2) * ld + ch : nullptr;
-                constexpr int JB = MODES < 8 ? MODES : 8;     /* modes per batch: the batch's global loads are all in flight
-                                                                 before the first store (stores to the state block may alias) */
-                if (act) {
-                    /* running pointers (one 64-bit add per mode each) instead of a 64-bit multiply per address */
-                    const long long j0 = g * MODES;
-                    double *pmr = p.state + (long long)(L.MEAN + 1 + j0) * ld + ch, *pmi = pmr + (long long)NC * ld;
-                    double *pob = p.state + (long long)(L.OBSM + 1 + j0) * ld + ch;
-                    double *prr = p.record ? row + (long long)(1 + j0) * ld : nullptr, *pri = p.record ? prr + (long long)NC * ld : nullptr;
-#pragma unroll
-                    for (int jb = 0; jb < MODES; jb += JB) {
-                        double mr[JB], mi[JB], ob[JB];
-#pragma unroll
-                        for (int b = 0; b < JB; b++) { mr[b] = pmr[b * ld]; mi[b] = pmi[b * ld]; ob[b] = pob[b * ld]; }
-#pragma unroll
-                        for (int b = 0; b < JB; b++) {
-                            const int j = g * MODES + jb + b;
-                            const double re = S.xs[2 * j][m], im = S.xs[2 * j + 1][m];
-                            /* running means and observable means (ME:404-414), this chain's words */
-                            *pmr = fma(re, inv_n, mr[b] * shrink);
-                            *pmi = fma(im, inv_n, mi[b] * shrink);
-                            *pob = fma(cabs_fast(re, im), inv_n, ob[b] * shrink);
-                            pmr += ld; pmi += ld; pob += ld;
-                            if (p.record) {
-                                __stcs(prr, re);
-                                __stcs(pri, im);
-                                prr += ld; pri += ld;
-                            }
-                        }
-                    }
-                }
+                /* the first half of this thread's modes; the generator thread (m, c_par = g) takes the second half */
+                if (act) measure_modes<NC, MODES - GEN_SHARE>(p, L, S.xs, m, ch, ld, g * MODES, inv_n, shrink, row);
                 if (g == 0) {
                     double va = 0.0, va2 = 0.0, vs = 0.0;
                     if (act) {
