@@ -112,6 +112,24 @@ __device__ __forceinline__ U4 philox4x32(unsigned c0, unsigned c1, unsigned c2, 
  * [1,2) and shifted down with ONE exact subtraction (no integer->double conversion, no magic-number pairs). */
 struct Spare { unsigned w0, x0; };
 
+/* One-parameter shapes (D = 1; the README configuration) would throw away the second normal of every Box-Muller pair and
+ * most of the call's spare bits, so there ONE Philox call serves TWO consecutive steps: steps 2P and 2P + 1 use the call with
+ * counter (chain_lo, chain_hi, P, 0):
+ *   radius uniform  u1 = (K + 1/2) 2^-52,  K = y : 0x80000  (the 32 bits of y; the low 20 mantissa bits are the constant mid-point);
+ *   angle t = z 2^-31;   step 2P proposes with sqrt(-2 ln u1) cos(pi t),  step 2P + 1 with sqrt(-2 ln u1) sin(pi t);
+ *   accept uniform  u = (A + 1/2) 2^-44,  A = w : 0x800 for step 2P,  A = x : 0x800 for step 2P + 1  (32 random bits each).
+ * The two normals of a pair are independent, and so are the four output words, so the chain sees the same law as before;
+ * |z| <= 6.8 and u >= 2^-33 (both ends beyond anything 10^12 steps resolve).  The step loop computes the pair at the even
+ * step and carries the second half to the odd one: -15 % instructions per step at D = 1. */
+template <class L> struct ShareCall { static constexpr bool value = L::D == 1; };
+__device__ __forceinline__ U4 share_radius_bits(const U4 &r) { U4 o = r; o.x = 0x80000000u; return o; }
+__device__ __forceinline__ Spare share_spare(const U4 &r, unsigned step) {
+    Spare sp;
+    sp.w0 = (step & 1u) ? r.x : r.w;
+    sp.x0 = 0x800u;
+    return sp;
+}
+
 struct Rng {
     unsigned c0, c1;
     const unsigned *rk;
@@ -337,6 +355,7 @@ struct Draws {                 /* everything random one step consumes; independe
     double z[(L::D + 1) / 2 * 2];
     double u;                  /* parity build: the accept uniform; throughput build: lower edge of the threshold window */
     double uhi;                /* throughput build: upper edge of the threshold window (Rng::accept_window) */
+    double u2, uhi2;           /* D = 1 (ShareCall): the same two for the odd step of the pair; z[1] is its normal */
 };
 
 template <class L>
@@ -346,14 +365,44 @@ struct Raw {                   /* the generator output one step consumes: one Ph
 
 template <class L>
 __device__ __forceinline__ void gen_bits(const Rng &rng, unsigned step, Raw<L> &raw) {
+    if (ShareCall<L>::value) { raw.r[0] = rng.bits(step >> 1, 0u); return; }
 #pragma unroll
     for (int q = 0; q < (L::D + 1) / 2; q++) raw.r[q] = rng.bits(step, (unsigned)q);
 }
 
+/* D = 1: everything the two steps of a pair consume, from the pair's call: z[0] / (u, uhi) for the even step, z[1] /
+   (u2, uhi2) for the odd one */
+template <class L, bool STRICT, class Tab>
+__device__ __forceinline__ void shape_pair(const Raw<L> &raw, const MathTables &T, Draws<L> &d, const Pins &pins,
+                                           double half_temp, const Tab &logtab) {
+    const U4 r = raw.r[0];
+    Rng::box_muller<STRICT, Tab>(share_radius_bits(r), T, d.z[0], d.z[1], pins.unit, pins.angle, logtab);
+    const Spare se = share_spare(r, 0u), so = share_spare(r, 1u);
+    if (STRICT) {
+        d.u = Rng::accept_uniform(se); d.uhi = 0.0;
+        d.u2 = Rng::accept_uniform(so); d.uhi2 = 0.0;
+    } else {
+        const float t2 = (float)(2.0 * half_temp);
+        Rng::accept_window(se.w0, t2 * 0.69314718f, t2 * 4e-5f, d.u, d.uhi);
+        Rng::accept_window(so.w0, t2 * 0.69314718f, t2 * 4e-5f, d.u2, d.uhi2);
+    }
+}
+/* the odd step of a pair takes over what the even step carried */
+template <class L>
+__device__ __forceinline__ void take_second_half(const Draws<L> &even, Draws<L> &odd) {
+    odd.z[0] = even.z[1]; odd.z[1] = even.z[1];
+    odd.u = even.u2; odd.uhi = even.uhi2; odd.u2 = even.u2; odd.uhi2 = even.uhi2;
+}
+
 template <class L, bool STRICT, class Tab>
 __device__ __forceinline__ void shape_draws(const Raw<L> &raw, const MathTables &T, Draws<L> &d, const Pins &pins,
-                                            double half_temp, const Tab &logtab) {
+                                            double half_temp, const Tab &logtab, unsigned step = 0u) {
     constexpr int NQ = (L::D + 1) / 2;
+    if (ShareCall<L>::value) {            /* stateless form: the draws of `step` from its pair's call */
+        shape_pair<L, STRICT, Tab>(raw, T, d, pins, half_temp, logtab);
+        if (step & 1u) { const Draws<L> e = d; take_second_half<L>(e, d); }
+        return;
+    }
     Spare sp;
     sp.w0 = sp.x0 = 0;
 #pragma unroll
@@ -369,6 +418,7 @@ __device__ __forceinline__ void shape_draws(const Raw<L> &raw, const MathTables 
         const float t2 = (float)(2.0 * half_temp);
         Rng::accept_window(sp.w0, t2 * 0.69314718f, t2 * 4e-5f, d.u, d.uhi);
     }
+    d.u2 = d.uhi2 = 0.0;
 }
 
 template <class L, bool STRICT, class Tab>
@@ -376,7 +426,7 @@ __device__ __forceinline__ void gen_draws(const Rng &rng, unsigned step, const M
                                           const Pins &pins, double half_temp, const Tab &logtab) {
     Raw<L> raw;
     gen_bits<L>(rng, step, raw);
-    shape_draws<L, STRICT, Tab>(raw, T, d, pins, half_temp, logtab);
+    shape_draws<L, STRICT, Tab>(raw, T, d, pins, half_temp, logtab, step);
 }
 
 template <class L>
@@ -785,7 +835,8 @@ __device__ __forceinline__ bool finish_step(Chain<Lay<Cfg::NR, Cfg::NC>> &c, dou
             const bool inside = !accept && diff <= uhi;
             if (__any_sync(__activemask(), inside)) {
                 Spare sp;
-                Rng::keep_spare(rng->bits(step, 0u), 0, sp);
+                if (ShareCall<L>::value) sp = share_spare(rng->bits(step >> 1, 0u), step);
+                else Rng::keep_spare(rng->bits(step, 0u), 0, sp);
                 const double thr = Rng::accept_threshold(sp, *logtab, half_temp);
                 accept = accept | (inside & (diff <= thr));
             }
@@ -996,7 +1047,17 @@ __device__ __forceinline__ void run_body(const MeParams &p) {
             use.u = p.inj_u[s_local * ld + ch];
             s_local++;
         } else {
-            if (DEEP) {
+            if (DEEP && ShareCall<L>::value) {
+                /* one call per pair of steps.  Invariant: `use` holds the draws of this step (with the pair's second half
+                   when the step is even), raw_in the bits of the pair of the NEXT step */
+                if ((step32 & 1u) == 0u) {           /* next step: second half of this pair; step + 2 opens a new pair */
+                    gen_bits<L>(rng, step32 + 2u, raw_out);
+                    take_second_half<L>(use, make);
+                } else {                             /* next step opens the pair whose bits are waiting; step + 2 shares it */
+                    raw_out = raw_in;
+                    shape_pair<L, STRICT, Tab>(raw_in, tables, make, pins, half_temp, logtab);
+                }
+            } else if (DEEP) {
                 gen_bits<L>(rng, step32 + 2u, raw_out);
                 shape_draws<L, STRICT, Tab>(raw_in, tables, make, pins, half_temp, logtab);
             } else if (AHEAD) {
@@ -1265,7 +1326,9 @@ __device__ __forceinline__ void accept_body(const MeParams &p) {
         else if (diff > 0 && p.temp != 0) {      /* regenerate the spare words of Philox calls 0 (and 1) */
             const Rng rng(p, p.chain_offset + (unsigned long long)ch);
             Spare sp;
-            Rng::keep_spare(rng.bits(p.ctr_dev ? (unsigned)p.ctr_dev[0] : (unsigned)p.step0, 0u), 0, sp);
+            const unsigned step_now = p.ctr_dev ? (unsigned)p.ctr_dev[0] : (unsigned)p.step0;
+            if (ShareCall<L>::value) sp = share_spare(rng.bits(step_now >> 1, 0u), step_now);
+            else Rng::keep_spare(rng.bits(step_now, 0u), 0, sp);
             u = STRICT ? Rng::accept_uniform(sp)
                        : Rng::accept_threshold(sp, LogTabGlobal{reinterpret_cast<const double2 *>(p.logtab)}, 0.5 * p.temp);
         }

@@ -185,6 +185,28 @@ void meo_normal_pair(uint64_t seed, uint64_t chain, uint32_t step, uint32_t slot
     *z1 = rad * s;
 }
 
+/* One-parameter shapes (d = 1): ONE call serves the steps 2P and 2P + 1 (me_device.cuh, ShareCall): counter
+ * (chain_lo, chain_hi, P, 0); radius uniform from y alone, K = y : 0x80000; angle t = z 2^-31; step 2P proposes with the
+ * cosine normal, step 2P + 1 with the sine normal; accept uniform A = w : 0x800 (step 2P), A = x : 0x800 (step 2P + 1). */
+double meo_shared_normal(uint64_t seed, uint64_t chain, uint32_t step) {
+    uint32_t r[4];
+    meo_philox(seed, chain, step >> 1, 0, r);
+    uint64_t K = ((uint64_t)r[1] << 20) | (uint64_t)0x80000u;
+    double u1 = ((double)K + 0.5) * (1.0 / 4503599627370496.0);
+    double t = (double)r[2] * (1.0 / 2147483648.0);
+    double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi_d(t, &s, &c);
+    return (step & 1u) ? rad * s : rad * c;
+}
+
+double meo_shared_uniform(uint64_t seed, uint64_t chain, uint32_t step) {
+    uint32_t r[4];
+    meo_philox(seed, chain, step >> 1, 0, r);
+    uint64_t bits = ((uint64_t)((step & 1u) ? r[0] : r[3]) << 12) | (uint64_t)0x800u;
+    return ((double)bits + 0.5) * (1.0 / 17592186044416.0);     /* 2^-44 */
+}
+
 double meo_uniform(uint64_t seed, uint64_t chain, uint32_t step, int n_calls) {
     uint32_t r[4];
     (void)n_calls;
@@ -438,6 +460,7 @@ int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, i
                 const uint32_t step = (uint32_t)(step0 + (uint64_t)s);
                 for (int q = 0; q < (d + 1) / 2; q++) {
                     if (mode == MEO_XOSHIRO) xo_normal_pair(&z[2 * q], &z[2 * q + 1]);
+                    else if (d == 1) { z[0] = meo_shared_normal(seed, chain_id, step); z[1] = 0.0; }
                     else meo_normal_pair(seed, chain_id, step, (uint32_t)q, &z[2 * q], &z[2 * q + 1]);
                 }
                 /* real block: sigma_r * (L z) ; z[0..n_r) */
@@ -476,6 +499,7 @@ int meo_run_group(const meo_config *c, double *st, int mode, int64_t n_blocks, i
                 else if (c->temp == 0) accept = 0;
                 else {
                     double uu = (mode == MEO_INJECT) ? u[s] : (mode == MEO_XOSHIRO) ? xo_uniform()
+                              : (d == 1) ? meo_shared_uniform(seed, chain_id, (uint32_t)(step0 + (uint64_t)s))
                               : meo_uniform(seed, chain_id, (uint32_t)(step0 + (uint64_t)s), (d + 1) / 2);
                     accept = uu <= exp(-1 * diff / c->temp);
                 }
