@@ -42,10 +42,13 @@ if ROOT not in sys.path:
 # inst / fp64_inst / wide_inst / dmma_inst: instructions, FP64 instructions, IMAD.WIDE and FP64 tensor-core MMAs per
 # chain-step over one whole MEASURE PERIOD (spm steps + the measure block + the per-measure prologue) in the SASS of the
 # shipped library (tests/scripts/sass_period.py <kernel> <spm>) — the inputs of the pipe-level roofline below.  The step
-# loops alone (tests/scripts/sass_loop.py) are 111 / 31 / 12 (C1), 126.5 / 40 / 12 (C2), 636 / 257 / 52 (C3).
+# loops alone (tests/scripts/sass_loop.py) are 126.5 / 40 / 12 (C2), 636 / 257 / 52 (C3).  C1's period alternates between two
+# paths (one Philox call and one Box-Muller pair per TWO steps, me_device.cuh ShareCall), so its counts are the dynamic
+# ones of an ncu capture of one bench pass (profiles/r02_ncu_c1_k_run.csv: smsp__inst_executed.sum / warp-steps = 210.1,
+# sm__pipe_fp64_cycles_active -> 65.8 FP64 instructions, 14 IMAD.WIDE per pair of steps).
 WORKLOADS = {
     "c1": dict(name="README x^2: 1 real param, T=0.01, measure every step", energy=("x2",), n_r=1, n_c=0, temp=0.01,
-               chains=65536, measures=10000, short_measures=10000, spm=1, flop=10, sf=3, inst=271.0, fp64_inst=75.0, wide_inst=16.0, dmma_inst=0.0),
+               chains=65536, measures=10000, short_measures=10000, spm=1, flop=10, sf=3, inst=210.1, fp64_inst=65.8, wide_inst=7.0, dmma_inst=0.0),
     "c2": dict(name="demo/toymodel_xypotentialwell: 2 real params, E=x^2+y^2, T=0.1, 65,536 chains x 1e5 steps, "
                     "measure every 10", energy=("xy_well", 1.0), n_r=2, n_c=0, temp=0.1, chains=65536,
                measures=10000, short_measures=2000, spm=10, flop=20, sf=5, inst=146.3, fp64_inst=48.2, wide_inst=12.3, dmma_inst=0.0),
