@@ -122,6 +122,9 @@ struct Spare { unsigned w0, x0; };
  * |z| <= 6.8 and u >= 2^-33 (both ends beyond anything 10^12 steps resolve).  The step loop computes the pair at the even
  * step and carries the second half to the odd one: -15 % instructions per step at D = 1. */
 template <class L> struct ShareCall { static constexpr bool value = L::D == 1; };
+/* (The same idea for the one spare normal of larger odd shapes — the last pair of the 3r+4c shape shared by two steps — was
+ * measured and lost: 10.0 against 9.8 ms per pass; the conditional pair costs the unrolled draw stage more overlap than half
+ * a call saves.) */
 __device__ __forceinline__ U4 share_radius_bits(const U4 &r) { U4 o = r; o.x = 0x80000000u; return o; }
 __device__ __forceinline__ Spare share_spare(const U4 &r, unsigned step) {
     Spare sp;
