@@ -106,7 +106,8 @@ int me_destroy(me_engine *eng);
  *                 __device__ double me_user_energy(const double* x, const double* c_re, const double* c_im, const double* k);
  *             and, when use_reject != 0,
  *                 __device__ bool   me_user_reject(const double* x, const double* c_re, const double* c_im, const double* k);
- *             compiled for sm_100a with NVRTC and fused into the step kernel (ME_NR / ME_NC are predefined macros);
+ *             compiled for sm_100a with NVRTC and fused into the step kernel — for D > 32 into the runtime-shape kernels,
+ *             which hand the functor gathered arrays (ME_NR / ME_NC are predefined macros);
  *   external: the caller evaluates energies itself between me_propose and me_accept. */
 int me_set_energy_builtin(me_engine *eng, int32_t energy_id, const double *consts, int32_t n_consts, int32_t use_reject);
 int me_set_energy_source(me_engine *eng, const char *cuda_source, const double *consts, int32_t n_consts, int32_t use_reject);
@@ -187,11 +188,11 @@ int me_accept(me_engine *eng, const double *prop, const double *e_new, const uns
               const double *inj_u, void *stream);
 
 /* Large parameter spaces (D > 32, e.g. 1 real + 64 complex with per-chain covariance — the reference's own
- * algorithm at the cylinder shape): runtime-shape kernels whose state stays in global memory (csrc/me_generic.cu).  With a
- * built-in functor me_run performs the whole schedule in one launch (me_buffers.prop required); with a caller-evaluated
+ * algorithm at the cylinder shape): runtime-shape kernels whose state stays in global memory (csrc/me_generic.cuh).  With a
+ * device functor (built-in, or user CUDA text) me_run performs the whole schedule in one launch (me_buffers.prop required); with a caller-evaluated
  * energy, a host-side predicate, magnitude / phase moves or injected draws the step is me_propose -> energy -> me_accept
  * and me_run serves measure().
- * me_energy_builtin evaluates the handle's DEVICE functor (built-in, or user CUDA text on fused shapes) and its hard
+ * me_energy_builtin evaluates the handle's DEVICE functor (built-in, or user CUDA text) and its hard
  * wall on a proposal block: e_out[n_chains], rej_out[n_chains] (may be NULL).  Besides the large-shape step it lets a
  * host-side predicate — the reference's python reject_condition (ME:142-146) — sit between me_propose and me_accept
  * of a functor engine of any shape. */

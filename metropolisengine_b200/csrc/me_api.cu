@@ -223,11 +223,11 @@ int me_rt_compile(const std::string &src, const char *name, const std::vector<st
     Nvrtc &n = nvrtc();
     if (!n.ok) { log = n.err; return ME_ERR_UNSUPPORTED; }
     const char *hdr_names[] = {"me_params.h", "me_math.cuh", "me_device.cuh", "me_energies.cuh", "me_kernels.cuh",
-                               "me_k4_device.cuh"};
+                               "me_k4_device.cuh", "me_generic.cuh"};
     const char *hdr_src[] = {me_src_params_h, me_src_math_cuh, me_src_device_cuh, me_src_energies_cuh, me_src_kernels_cuh,
-                             me_src_k4_device_cuh};
+                             me_src_k4_device_cuh, me_src_generic_cuh};
     nvrtcProgram prog = nullptr;
-    int rc = n.createProgram(&prog, src.c_str(), name, 6, hdr_src, hdr_names);
+    int rc = n.createProgram(&prog, src.c_str(), name, 7, hdr_src, hdr_names);
     if (rc != 0) { log = std::string("nvrtcCreateProgram: ") + n.getErrorString(rc); return ME_ERR_COMPILE; }
     std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DME_NVRTC=1"};
     for (auto &o : extra) opts.push_back(o.c_str());
@@ -544,12 +544,45 @@ void choose_dims(me_engine *e) {
     e->grid = (int)((n + block - 1) / block);
 }
 
+/* Runtime compilation of the runtime-shape kernel set (D > 32) around a user functor: same contract as the fused kernels'
+ * (me_user_energy / me_user_reject over x[ME_NR], c_re[ME_NC], c_im[ME_NC]); -fmad=false like the ahead-of-time build. */
+int nvrtc_compile_generic(int n_real, int n_complex, const std::string &user_src, int use_reject, std::vector<char> &cubin,
+                          std::string &log) {
+    std::string src = "#define ME_GENERIC_USER 1\n";
+    if (use_reject) src += "#define ME_GENERIC_USER_REJECT 1\n";
+    src += "#include \"me_kernels.cuh\"\n#line 1 \"user_energy.cu\"\n";
+    src += user_src;
+    src += "\n#include \"me_generic.cuh\"\n";
+    std::vector<std::string> extra = {"-DME_NR=" + std::to_string(n_real), "-DME_NC=" + std::to_string(n_complex),
+                                      "-DME_STRICT=1", "--fmad=false"};
+    return me_rt_compile(src, "me_user_generic_kernels.cu", extra, cubin, log);
+}
+
 int resolve_kernels(me_engine *e, int energy_id, const std::string &user_src) {
     const int nr = e->cfg.n_real, nc = e->cfg.n_complex, strict = e->cfg.strict ? 1 : 0;
+    if (e->generic && energy_id == ME_ENERGY_USER) {
+        /* runtime shape with a user functor: the runtime-shape kernels (me_generic.cuh) compiled around the functor */
+        std::string key = "generic," + std::to_string(nr) + "," + std::to_string(nc) + "," + std::to_string(e->use_reject) +
+                          "," + std::to_string(e->cfg.device) + "|" + user_src;
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cache.find(key);
+        if (it != g_cache.end()) { e->ks = it->second; return ME_OK; }
+        std::vector<char> cubin;
+        std::string log;
+        int rc = nvrtc_compile_generic(nr, nc, user_src, e->use_reject, cubin, log);
+        if (rc != ME_OK) return fail(e, rc, log);
+        static const char *names[5] = {"me_gk_run", "me_gk_init", "me_gk_propose", "me_gk_accept", "me_gk_energy"};
+        CUfunction fn[5];
+        std::string err;
+        rc = me_rt_load(e->cfg.device, cubin, names, 5, fn, err);
+        if (rc != ME_OK) return fail(e, rc, err);
+        KernelSet ks;
+        ks.run.drv = fn[0]; ks.init.drv = fn[1]; ks.propose.drv = fn[2]; ks.accept.drv = fn[3]; ks.energy.drv = fn[4];
+        g_cache[key] = ks;
+        e->ks = ks;
+        return ME_OK;
+    }
     if (e->generic) {
-        if (energy_id == ME_ENERGY_USER)
-            return fail(e, ME_ERR_UNSUPPORTED, "user CUDA functors are fused kernels (D <= 32); for larger parameter "
-                                               "spaces use a built-in functor or a torch callable");
         const void *m, *i, *pr, *ac, *en;
         me_generic_kernels(&m, &i, &pr, &ac, &en);
         e->ks.run.rt = m; e->ks.init.rt = i; e->ks.propose.rt = pr; e->ks.accept.rt = ac; e->ks.energy.rt = en;
@@ -864,7 +897,9 @@ int me_check_energy_source(const char *src, int32_t nr, int32_t nc, int32_t use_
                            int64_t cap) {
     std::vector<char> cubin;
     std::string l;
-    int rc = nvrtc_compile(nr, nc, src ? ME_ENERGY_USER : ME_ENERGY_EXTERNAL, src ? src : "", use_reject, strict, cubin, l);
+    int rc = (src && nr + 2 * nc > ME_FUSED_MAX_D)
+                 ? nvrtc_compile_generic(nr, nc, src, use_reject, cubin, l)
+                 : nvrtc_compile(nr, nc, src ? ME_ENERGY_USER : ME_ENERGY_EXTERNAL, src ? src : "", use_reject, strict, cubin, l);
     if (log && cap > 0) {
         strncpy(log, l.c_str(), (size_t)cap - 1);
         log[cap - 1] = 0;
@@ -928,8 +963,8 @@ static int run_common(me_engine *e, int64_t n_blocks, int64_t spm, int do_measur
     if (spm > 0 && e->energy_id == ME_ENERGY_EXTERNAL)
         return fail(e, ME_ERR_STATE, "external energies step through me_propose / me_accept");
     if (e->generic && spm > 0 &&
-        (delta != nullptr || e->energy_id < 0 || e->energy_id >= ME_ENERGY_EXTERNAL || !e->buf.prop || e->group >= 3))
-        return fail(e, ME_ERR_STATE, "large parameter spaces run whole schedules in one launch only with a built-in functor "
+        (delta != nullptr || e->energy_id < 0 || e->energy_id == ME_ENERGY_EXTERNAL || !e->buf.prop || e->group >= 3))
+        return fail(e, ME_ERR_STATE, "large parameter spaces run whole schedules in one launch only with a device functor "
                                      "(and me_buffers.prop bound); otherwise step through me_propose / me_energy_builtin / "
                                      "me_accept and let me_run measure");
     if (e->step + (unsigned long long)(n_blocks * spm) >= 0xffffffffull)

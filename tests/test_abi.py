@@ -169,3 +169,22 @@ def test_large_fused_shapes_fit_the_static_shared_memory_budget(lib, nr, nc):
     assert 447 < lay.POOL_WORDS <= 600
     ok, log = lib.check_energy_source(None, nr, nc, use_reject=False, strict=False)
     assert ok, log[-400:]
+
+
+def test_user_functor_compiles_for_runtime_shapes(lib):
+    """A user CUDA functor on a shape beyond the register-resident fused kernels (D > 32) is compiled around the
+    runtime-shape kernels (me_generic.cuh) — same contract as for the fused kernels.  Compile-only (NVRTC, no GPU)."""
+    src = """
+__device__ double me_user_energy(const double* x, const double* cr, const double* ci, const double* k) {
+    double e = k[0] * x[0] * x[0];
+    for (int j = 0; j < ME_NC; j++) e += (1.0 + 0.01 * j) * (cr[j] * cr[j] + ci[j] * ci[j]);
+    return e;
+}
+__device__ bool me_user_reject(const double* x, const double* cr, const double* ci, const double* k) { return fabs(x[0]) >= 1.0; }
+"""
+    ok, log = lib.check_energy_source(src, 1, 20, use_reject=True)
+    assert ok, log
+    ok, log = lib.check_energy_source(src, 1, 20, use_reject=False)          # the wall is optional
+    assert ok, log
+    ok, log = lib.check_energy_source(src.replace("k[0] *", "k[0]] *"), 1, 20, use_reject=True)
+    assert not ok and "user_energy.cu" in log

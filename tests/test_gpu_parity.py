@@ -498,6 +498,44 @@ def test_magnitude_phase_philox_matches_c_oracle(x0c):
     assert len(set(np.floor(ang / (np.pi / 2)).astype(int))) == 4
 
 
+def test_user_functor_on_a_runtime_shape_matches_the_builtin_functor():
+    """A user CUDA functor beyond D = 32 (ME:20, 110-120: the energy plugin is the reference's extension point) runs in the
+    runtime-shape kernels compiled around it.  The cylinder energy restated as a user functor (same operation order, hard
+    wall included) must give the built-in functor's chains bit for bit: one-launch schedules and single steps."""
+    import metropolisengine_b200 as me
+    src = """
+__device__ double me_user_energy(const double* x, const double* cr, const double* ci, const double* k) {
+    const double a2 = x[0] * x[0];
+    double quad = 0.0, tot = 0.0;
+    for (int j = 0; j < ME_NC; j++) {
+        const double q = (double)(j - ME_NC / 2);
+        const double m2 = cr[j] * cr[j] + ci[j] * ci[j];
+        quad = quad + (k[1] + (k[2] * (q * q)) * (1.0 + a2)) * m2;
+        tot = tot + m2;
+    }
+    return (k[0] * a2 + quad) + (k[3] / (2.0 * (double)ME_NC)) * (tot * tot);
+}
+__device__ bool me_user_reject(const double* x, const double* cr, const double* ci, const double* k) { return fabs(x[0]) >= 1.0; }
+"""
+    nc, n = 20, 300
+    consts = (10.0, -1.0, 0.05, 1.0)
+    kw = dict(initial_real_params=np.array([0.3]), initial_complex_params=0.05 * np.exp(1j * np.arange(nc)), temp=.1,
+              n_chains=n, seed=4, sampling_width=0.05)
+    a = me.MetropolisEngine(me.BuiltinEnergy("cylinder", *consts, reject=True), **kw)
+    b = me.MetropolisEngine(me.CudaEnergy(src, consts=consts, has_reject=True), **kw)
+    assert a._generic and b._generic
+    assert torch.equal(a.state, b.state)                      # initial energies
+    for eng in (a, b):
+        eng.run(60, 3)                                        # crosses n > 50: per-chain covariances and factors live
+        for _ in range(4):
+            eng.step_all()
+        eng.measure()
+    torch.cuda.synchronize()
+    assert torch.equal(a.state, b.state)
+    assert torch.equal(a.time_series(), b.time_series())
+    assert 0.05 < a.acceptance_rate < 0.9
+
+
 def test_magnitude_phase_large_shape_philox_matches_c_oracle():
     """Magnitude / phase moves of a runtime-shape engine (1 real + 16 complex: 33 words, me_generic.cu gk_propose /
     gk_accept with groups 3 / 4) against the C oracle on the same Philox streams.  Half of the coefficients start at
