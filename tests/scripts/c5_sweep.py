@@ -30,11 +30,15 @@ if world > 1:
 
 SPM, MPL = 10, 10                 # steps per measure, measures per launch (one all-reduce per launch)
 WORKLOADS = {
-    "c2": dict(energy=("xy_well", 1.0), n_r=2, n_c=0, temp=0.1, rate=1.3e11),
-    "c3": dict(energy=("mixed_well", 1.0, -1.0, 0.5, 1.0), n_r=3, n_c=4, temp=0.1, rate=1.7e10),
+    "c2": dict(energy=("xy_well", 1.0), n_r=2, n_c=0, temp=0.1, rate=1.6e11),
+    "c3": dict(energy=("mixed_well", 1.0, -1.0, 0.5, 1.0), n_r=3, n_c=4, temp=0.1, rate=2.6e10),
 }
+# "graph": the launches of a configuration go into CUDA graphs of 10 rounds [run -> reduction -> all-reduce], each round's
+# collective beside the next round's stepping launch (run_graphed(launches=10)); the pooled statistics are read once at the
+# end.  Default: eager launches with a host read-back of the pooled statistics after every launch (the round-1 protocol).
+GRAPH = "graph" in sys.argv[1:]
 only = [a for a in sys.argv[1:] if a in WORKLOADS] or list(WORKLOADS)
-counts = [int(float(a)) for a in sys.argv[1:] if a not in WORKLOADS] or [10**6, 10**7, 10**8]
+counts = [int(float(a)) for a in sys.argv[1:] if a not in WORKLOADS and a != "graph"] or [10**6, 10**7, 10**8]
 
 
 def barrier():
@@ -62,18 +66,30 @@ for name in only:
         launches = max(3, int(0.4 * wl["rate"] * world / (total * SPM * MPL)))
         launches = min(launches, 200)
         eng.run(60, SPM)                     # past the covariance-adaptation threshold (n > 50)
+        eng.pooled_statistics()              # first use: communicator and peer windows are set up outside the timed region
         eng.reset_pooled_statistics()
         stream = torch.cuda.current_stream(dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pooled = None
+        if GRAPH:
+            launches = max(10, launches // 10 * 10)
+            eng.run_graphed(MPL, SPM, 10)             # eager first use
+            eng.run_graphed(MPL, SPM, 10)             # capture + first replay
+            eng.reset_pooled_statistics()
         barrier()
         ev0.record(stream)
-        for i in range(launches):
-            eng.run(MPL, SPM)
-            pooled = eng.pooled_statistics()          # device reduction + the path's one all-reduce
-            if i == 2:
-                pooled3 = pooled                      # same sample set whatever the GPU count: the invariance check
-        ev1.record(stream)
+        if GRAPH:
+            for i in range(launches // 10):
+                eng.run_graphed(MPL, SPM, 10)
+            ev1.record(stream)
+            pooled = pooled3 = eng.pooled_statistics()
+        else:
+            for i in range(launches):
+                eng.run(MPL, SPM)
+                pooled = eng.pooled_statistics()          # device reduction + the path's one all-reduce
+                if i == 2:
+                    pooled3 = pooled                      # same sample set whatever the GPU count: the invariance check
+            ev1.record(stream)
         barrier()
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -85,7 +101,7 @@ for name in only:
                                    np.asarray(pooled["mean_complex"], dtype=np.complex128).view(np.float64)])
             cov = pooled["cov_real"]
             print(json.dumps({
-                "workload": name, "chains": total, "n_gpus": world, "launches": launches,
+                "workload": name, "chains": total, "n_gpus": world, "launches": launches, "mode": "graph" if GRAPH else "eager",
                 "steps_per_launch": SPM * MPL, "ms": round(ms, 3),
                 "chain_steps_per_s": total * launches * SPM * MPL / (ms * 1e-3),
                 "pooled_samples": float(pooled.get("count", float("nan"))),
