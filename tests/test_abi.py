@@ -188,3 +188,17 @@ __device__ bool me_user_reject(const double* x, const double* cr, const double* 
     assert ok, log
     ok, log = lib.check_energy_source(src.replace("k[0] *", "k[0]] *"), 1, 20, use_reject=True)
     assert not ok and "user_energy.cu" in log
+
+
+def test_collective_entry_points_validate_their_arguments(lib):
+    """The pooled-statistics collective and its peer-window set-up reject null handles / buffers without touching a GPU."""
+    L = lib.load()
+    null = ctypes.c_void_p(None)
+    assert L.me_reduce_stats(null, null, 0, null) == lib.ME_ERR_INVALID
+    assert L.me_accumulate_stats(null, null, null, null, null) == lib.ME_ERR_INVALID
+    assert L.me_comm_allreduce(null, null, 0, null) == lib.ME_ERR_INVALID
+    buf = (ctypes.c_ubyte * 64)()
+    assert L.me_comm_peer_init(null, 1024, buf) == lib.ME_ERR_INVALID
+    assert L.me_comm_peer_connect(null, buf) == lib.ME_ERR_INVALID
+    assert L.me_comm_peer_enable(null, 1) == lib.ME_ERR_INVALID
+    assert L.me_k4_accumulate_moments(null, null, null, null, null) == lib.ME_ERR_INVALID
