@@ -35,8 +35,8 @@ __device__ __forceinline__ int g_hlo(int i, int j) { return 2 * (i * (i - 1) / 2
 #define ST(w) st[(long long)(w) * ld + ch]
 
 /* Cholesky factors of the chain's covariances, in place in global memory (me::refactor for runtime shapes).
-   (A row-blocked variant — four entries of a row sharing the loads of G_ik, same bits — was measured slower: 310 against
-   191 ms per 100 steps + 10 measures of 32,768 chains at 1r+64c; its 164 registers cost the step phase its occupancy.) */
+   (Blocked variants with the same bits were measured slower at 1r+64c, 32,768 chains, 100 steps + 10 measures: four entries
+   of a row sharing the loads of G_ik 310 ms, four rows sharing the loads of row j 242 ms, against 191 ms for this loop.) */
 __device__ int g_refactor(double *st, long long ld, long long ch, const GLay &L) {
     int bad = 0;
     for (int i = 0; i < L.nr; i++)
